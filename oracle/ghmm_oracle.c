@@ -1,0 +1,831 @@
+/*
+ * ghmm_oracle.c — CPU restatement of the AUGUSTUS GHMM Viterbi path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this file's shared library; the product (augustus_b200/) never does.
+ *
+ * What it restates (reference = /root/reference, AUGUSTUS 3.5.0), column by column, pull style,
+ * exactly in the reference's loop order so that ties resolve the same way:
+ *   NAMGene::viterbiAndForward      src/namgene.cc:168-365   (column loop, GC-class switching)
+ *   NAMGene::getViterbiPath         src/namgene.cc:432-510   (argmax x termProbs, re-derivation walk)
+ *   IGenicModel::viterbi...         src/igenicmodel.cc:231-357
+ *   IntronModel::viterbi...         src/intronmodel.cc:509-858, emiProbUnderModel :861-1038,
+ *                                   seqProb :1046-1108, aSSProb :1116-1188, dSSProb :1195-1248
+ *   ExonModel::viterbi...           src/exonmodel.cc:899-1179, endPartEmiProb :1272-1400,
+ *                                   notEndPartEmiProb :1417-1859, seqProb :1925-2034,
+ *                                   OpenReadingFrame :101-198
+ *   ContentStairs::computeStairs    src/motif.cc:543-614
+ *   State::setTruncFlag             src/gene.cc:309-321
+ * Scope: ab initio (no hints, softmasking off), no protein profile, no overlap mode — the
+ * configuration BASELINE.json configs 1 and 2 run.  UTR / nc states are rejected.
+ *
+ * Arithmetic: the reference multiplies LLDouble probabilities; this restatement ADDS log
+ * probabilities quantised to Q40 fixed point (int64, 2^-40 nat resolution), the same number
+ * system the CUDA path uses, so CUDA-vs-oracle comparisons are bit-exact while
+ * oracle-vs-reference comparisons are exact on the path and ~1e-9 on the score.
+ *
+ * Known deviation (documented in DESIGN.md): the reference's SnippetProbs memo
+ * (statemodel.cc:283-393) leaks the GC class active at first touch into lessD emissions when a
+ * window has more than one GC class; here lessD uses the class of the current column.
+ * Single-class windows are unaffected.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/augb200_params.h"
+
+typedef int64_t sc_t;
+#define FRAC_BITS 40
+#define NEG  (-((sc_t)1 << 61))
+#define NEGT (-((sc_t)1 << 60))
+static inline int isneg(sc_t x) { return x <= NEGT; }
+static sc_t q(double x) {
+    if (!(x > -1e300)) return NEG;      /* -inf or nan */
+    return (sc_t)llround(ldexp(x, FRAC_BITS));
+}
+
+/* reference StateType values (include/types.hh:492-512) */
+enum { T_IGENIC = 0, T_SINGLE = 1, T_INITIAL0 = 2, T_INTERNAL0 = 5, T_TERMINAL = 8,
+       T_LESSD0 = 9, T_LONGDSS0 = 10, T_EQUALD0 = 11, T_GEO0 = 12, T_LONGASS0 = 13,
+       T_RSINGLE = 36, T_RINITIAL = 37, T_RINTERNAL0 = 38, T_RTERMINAL0 = 41,
+       T_RLESSD0 = 44, T_RLONGDSS0 = 45, T_REQUALD0 = 46, T_RGEO0 = 47, T_RLONGASS0 = 48 };
+enum { K_IGENIC, K_EXON, K_LESSD, K_LONGDSS, K_EQUALD, K_GEO, K_LONGASS };
+enum { E_SINGLE, E_INITIAL, E_INTERNAL, E_TERMINAL, E_RSINGLE, E_RINITIAL, E_RINTERNAL, E_RTERMINAL };
+
+typedef struct {
+    int type, kind, fwd, frame;     /* frame = stateReadingFrames[type] (types.cc:174-188) */
+    int ek;                         /* exon kind */
+    int beginPartLen, innerPartOffset, baseOffset, innerPartEndOffset;
+    int nanc, anc[16];
+} StateInfo;
+
+typedef struct {
+    int S, C, k, d, dss_start, dss_end, ass_start, ass_end, ass_up, tiw, init_len, et_len;
+    int max_exon_len, min_exon_length, dss_gc_allowed, GCwinsize, weighing;
+    int tis_n, tis_k, assm_n, assm_k;
+    int dStateLen;
+    StateInfo* st;
+    sc_t *init, *term, *trans;                   /* trans[c][a][s] */
+    sc_t *xemi, *xinit, *xet;                    /* [c][3][1024] */
+    sc_t *xpls[8];                               /* [l][c][3][4^(l+1)] */
+    sc_t *iemi, *gemi;                           /* [c][1024] */
+    double *gpls[8];                             /* igenic Pls, kept as double logs (ratio of sums) */
+    sc_t *tis, *assm;                            /* [c][n][4^(k+1)] */
+    sc_t *ld_single, *ld_initial, *ld_internal, *ld_terminal, *ld_intron;
+    int n_ld_exon, n_ld_intron;
+    sc_t *ass_pat, *ass_pat_non, *dss_pat, *dss_pat_non;
+    sc_t startp[64]; int isstop[64];
+    sc_t ochre, amber, opal, probN, log025, log3;
+    double centroids[64][4]; int ncent; double wm[4][4];
+} Model;
+
+/* ------------------------------------------------------------------ blob reading */
+typedef struct { char* buf; size_t n; } Blob;
+static const augb200_blob_entry* bfind(const Blob* b, const char* name) {
+    const augb200_blob_header* h = (const augb200_blob_header*)b->buf;
+    const augb200_blob_entry* e = (const augb200_blob_entry*)(b->buf + sizeof *h);
+    for (uint32_t i = 0; i < h->n_entries; i++) if (!strcmp(e[i].name, name)) return &e[i];
+    fprintf(stderr, "oracle: blob entry '%s' missing\n", name); exit(3);
+}
+static int bint(const Blob* b, const char* name) { return *(const int32_t*)(b->buf + bfind(b, name)->offset); }
+static double bdbl(const Blob* b, const char* name) { return *(const double*)(b->buf + bfind(b, name)->offset); }
+static const double* bdarr(const Blob* b, const char* name, size_t* n) {
+    const augb200_blob_entry* e = bfind(b, name); if (n) *n = e->nbytes / 8; return (const double*)(b->buf + e->offset);
+}
+static const int32_t* biarr(const Blob* b, const char* name, size_t* n) {
+    const augb200_blob_entry* e = bfind(b, name); if (n) *n = e->nbytes / 4; return (const int32_t*)(b->buf + e->offset);
+}
+static sc_t* qarr(const Blob* b, const char* name, size_t* n) {
+    size_t m; const double* d = bdarr(b, name, &m);
+    sc_t* r = (sc_t*)malloc(m * sizeof(sc_t));
+    for (size_t i = 0; i < m; i++) r[i] = q(d[i]);
+    if (n) *n = m;
+    return r;
+}
+
+static void classify(StateInfo* s, const Model* m) {
+    int t = s->type;
+    s->fwd = (t < 36); s->frame = 0;
+    if (t == T_IGENIC) { s->kind = K_IGENIC; s->fwd = 1; return; }
+    int e = -1;
+    if (t == T_SINGLE) { e = E_SINGLE; }
+    else if (t >= T_INITIAL0 && t < T_INITIAL0 + 3) { e = E_INITIAL; s->frame = t - T_INITIAL0; }
+    else if (t >= T_INTERNAL0 && t < T_INTERNAL0 + 3) { e = E_INTERNAL; s->frame = t - T_INTERNAL0; }
+    else if (t == T_TERMINAL) { e = E_TERMINAL; }
+    else if (t == T_RSINGLE) { e = E_RSINGLE; s->frame = 2; }
+    else if (t == T_RINITIAL) { e = E_RINITIAL; s->frame = 2; }
+    else if (t >= T_RINTERNAL0 && t < T_RINTERNAL0 + 3) { e = E_RINTERNAL; s->frame = t - T_RINTERNAL0; }
+    else if (t >= T_RTERMINAL0 && t < T_RTERMINAL0 + 3) { e = E_RTERMINAL; s->frame = t - T_RTERMINAL0; }
+    if (e >= 0) {
+        s->kind = K_EXON; s->ek = e;
+        /* ExonModel::ExonModel, exonmodel.cc:231-279 */
+        switch (e) {
+        case E_SINGLE: case E_INITIAL: s->beginPartLen = 3 + m->tiw; s->innerPartOffset = 3; break;
+        case E_RSINGLE: case E_RTERMINAL: s->beginPartLen = s->innerPartOffset = 3; break;
+        default: s->beginPartLen = 0; s->innerPartOffset = s->fwd ? m->ass_end : m->dss_start;
+        }
+        if (e == E_SINGLE || e == E_TERMINAL) { s->baseOffset = 0; s->innerPartEndOffset = 3; }
+        else if (e == E_RSINGLE || e == E_RINITIAL) { s->baseOffset = -m->tiw; s->innerPartEndOffset = 3; }
+        else { s->baseOffset = s->innerPartEndOffset = s->fwd ? m->dss_start : m->ass_end; }
+        return;
+    }
+    int base = s->fwd ? T_LESSD0 : T_RLESSD0;
+    int off = t - base;
+    if (off < 0 || off >= 15) { fprintf(stderr, "oracle: unsupported state type %d (UTR/nc not restated)\n", t); exit(3); }
+    s->frame = off / 5;
+    switch (off % 5) {
+    case 0: s->kind = K_LESSD; break; case 1: s->kind = K_LONGDSS; break; case 2: s->kind = K_EQUALD; break;
+    case 3: s->kind = K_GEO; break; case 4: s->kind = K_LONGASS; break;
+    }
+}
+
+Model* orc_model_load(const char* path) {
+    FILE* f = fopen(path, "rb"); if (!f) { perror(path); return NULL; }
+    Blob b; fseek(f, 0, SEEK_END); b.n = ftell(f); fseek(f, 0, SEEK_SET);
+    b.buf = (char*)malloc(b.n); if (fread(b.buf, 1, b.n, f) != b.n) { fclose(f); return NULL; } fclose(f);
+    if (memcmp(b.buf, AUGB200_BLOB_MAGIC, 8)) { fprintf(stderr, "oracle: bad blob magic\n"); return NULL; }
+    Model* m = (Model*)calloc(1, sizeof *m);
+    m->S = bint(&b, "statecount"); m->C = bint(&b, "num_gc_classes");
+    m->k = bint(&b, "exon_k");
+    if (bint(&b, "intron_k") != m->k || bint(&b, "igenic_k") != m->k) { fprintf(stderr, "oracle: mixed k unsupported\n"); return NULL; }
+    m->d = bint(&b, "intron_d");
+    m->dss_start = bint(&b, "dss_start"); m->dss_end = bint(&b, "dss_end");
+    m->ass_start = bint(&b, "ass_start"); m->ass_end = bint(&b, "ass_end");
+    m->ass_up = bint(&b, "ass_upwindow_size"); m->tiw = bint(&b, "trans_init_window");
+    m->init_len = bint(&b, "init_coding_len"); m->et_len = bint(&b, "et_coding_len");
+    m->max_exon_len = bint(&b, "max_exon_len"); m->min_exon_length = bint(&b, "min_exon_length");
+    m->dss_gc_allowed = bint(&b, "dss_gc_allowed"); m->GCwinsize = bint(&b, "GCwinsize");
+    m->weighing = bint(&b, "basecount_weighing_type");
+    if (bint(&b, "transinit_nbins") > 0) { fprintf(stderr, "oracle: TRANSINITBIN not restated\n"); return NULL; }
+    m->tis_n = bint(&b, "tis_motif_n"); m->tis_k = bint(&b, "tis_motif_k");
+    m->assm_n = bint(&b, "ass_motif_n"); m->assm_k = bint(&b, "ass_motif_k");
+    /* intronmodel.cc:519-520 */
+    m->dStateLen = m->d - 2 - m->dss_end - m->ass_start - 2 - m->ass_up;
+    m->init = qarr(&b, "init_probs", NULL); m->term = qarr(&b, "term_probs", NULL);
+    m->trans = qarr(&b, "trans", NULL);
+    m->xemi = qarr(&b, "exon_emi", NULL); m->xinit = qarr(&b, "exon_initemi", NULL); m->xet = qarr(&b, "exon_etemi", NULL);
+    for (int l = 0; l <= m->k; l++) {
+        char nm[32]; sprintf(nm, "exon_pls%d", l); m->xpls[l] = qarr(&b, nm, NULL);
+        sprintf(nm, "igenic_pls%d", l);
+        size_t n; const double* dd = bdarr(&b, nm, &n);
+        m->gpls[l] = (double*)malloc(n * 8); memcpy(m->gpls[l], dd, n * 8);
+    }
+    m->iemi = qarr(&b, "intron_emi", NULL); m->gemi = qarr(&b, "igenic_emi", NULL);
+    m->tis = qarr(&b, "tis_motif", NULL); m->assm = qarr(&b, "ass_motif", NULL);
+    size_t n;
+    m->ld_single = qarr(&b, "lendist_single", &n); m->n_ld_exon = (int)n;
+    m->ld_initial = qarr(&b, "lendist_initial", NULL); m->ld_internal = qarr(&b, "lendist_internal", NULL);
+    m->ld_terminal = qarr(&b, "lendist_terminal", NULL);
+    m->ld_intron = qarr(&b, "lendist_intron", &n); m->n_ld_intron = (int)n;
+    m->ass_pat = qarr(&b, "ass_pattern", NULL); m->ass_pat_non = qarr(&b, "ass_pattern_nonag", NULL);
+    m->dss_pat = qarr(&b, "dss_pattern", NULL); m->dss_pat_non = qarr(&b, "dss_pattern_nongt", NULL);
+    const double* sp = bdarr(&b, "start_codon_prob", NULL); const int32_t* isx = biarr(&b, "is_stop_codon", NULL);
+    for (int i = 0; i < 64; i++) { m->startp[i] = q(sp[i]); m->isstop[i] = isx[i]; }
+    m->ochre = q(bdbl(&b, "ochreprob")); m->amber = q(bdbl(&b, "amberprob")); m->opal = q(bdbl(&b, "opalprob"));
+    m->probN = q(bdbl(&b, "probNinCoding")); m->log025 = q(log(0.25)); m->log3 = q(log(3.0));
+    const double* cen = bdarr(&b, "gc_centroids", &n); m->ncent = (int)(n / 4);
+    for (int i = 0; i < m->ncent; i++) for (int j = 0; j < 4; j++) m->centroids[i][j] = cen[4 * i + j];
+    const double* w = bdarr(&b, "basecount_weight_matrix", NULL);
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) m->wm[i][j] = w[4 * i + j];
+    const int32_t* stt = biarr(&b, "state_type", NULL);
+    const int32_t* reach = biarr(&b, "state_reachable", NULL);
+    m->st = (StateInfo*)calloc(m->S, sizeof(StateInfo));
+    for (int s = 0; s < m->S; s++) {
+        m->st[s].type = stt[s]; classify(&m->st[s], m);
+        if (!reach[s]) { fprintf(stderr, "oracle: unreachable states not restated\n"); return NULL; }
+        /* StateModel::initPredecessors, statemodel.cc:41-46: ancestors in state-index order */
+        for (int a = 0; a < m->S; a++) if (!isneg(m->trans[(size_t)a * m->S + s])) m->st[s].anc[m->st[s].nanc++] = a;
+    }
+    free(b.buf);
+    return m;
+}
+int orc_model_statecount(const Model* m) { return m->S; }
+
+/* ------------------------------------------------------------------ per-window context */
+typedef struct {
+    const Model* m; int L; const uint8_t* c;   /* c[i] in 0..3, 4 = other */
+    const int* gc;                              /* class per position */
+    int cls;                                    /* class of current column */
+    int *nsf, *nsr;                             /* nearestStopForward / Reverse */
+    sc_t* V;                                    /* [L][S] */
+    sc_t *PX[8][3], *PXR[8][3];                 /* exon content prefix sums [class][phi] (lazily built) */
+    sc_t *PI[8], *PIR[8];                       /* intron content prefix sums per class (fwd k-mer / rc k-mer) */
+} Ctx;
+
+static inline int at(const Ctx* x, int p) { return (p < 0 || p >= x->L) ? 5 : x->c[p]; }
+static inline int cmpl(int b) { return b < 4 ? 3 - b : b; }
+/* Seq2Int::operator() over n bases starting at p (geneticcode.hh:166-173); -1 on invalid nucleotide */
+static int s2i(const Ctx* x, int p, int n) {
+    int e = 0; for (int i = 0; i < n; i++) { int b = at(x, p + i); if (b > 3) return -1; e = (e << 2) | b; } return e;
+}
+/* Seq2Int::rc (geneticcode.hh:174-179) */
+static int s2irc(const Ctx* x, int p, int n) {
+    int e = 0; for (int i = 0; i < n; i++) { int b = at(x, p + i); if (b > 3) return -1; e |= (3 - b) << (2 * i); } return e;
+}
+static inline int mod3(int k) { return k >= 0 ? k % 3 : (k % 3 + 3) % 3; }
+static inline int is2(const Ctx* x, int p, int a, int b) { return at(x, p) == a && at(x, p + 1) == b; }
+enum { A_ = 0, C_ = 1, G_ = 2, T_ = 3 };
+static int onGenDSS(const Ctx* x, int p) { return is2(x, p, G_, T_) || (x->m->dss_gc_allowed && is2(x, p, G_, C_)); }
+static int onGenRDSS(const Ctx* x, int p) { return is2(x, p, A_, C_) || (x->m->dss_gc_allowed && is2(x, p, G_, C_)); }
+/* statemodel.hh:98-117, no hints */
+static int possDSS(const Ctx* x, int pos) { return pos >= 1 && pos <= x->L - 2 && onGenDSS(x, pos); }
+static int possRDSS(const Ctx* x, int pos) { return pos >= 1 && pos <= x->L - 2 && onGenRDSS(x, pos - 1); }
+static int possASS(const Ctx* x, int pos) { return pos >= 1 && pos <= x->L - 2 && is2(x, pos - 1, A_, G_); }
+static int possRASS(const Ctx* x, int pos) { return pos >= 1 && pos <= x->L - 2 && is2(x, pos, C_, T_); }
+static int isStop(const Ctx* x, int p) { int i = s2i(x, p, 3); return i >= 0 && x->m->isstop[i]; }
+static int isRCStop(const Ctx* x, int p) { int i = s2irc(x, p, 3); return i >= 0 && x->m->isstop[i]; }
+
+/* OpenReadingFrame::OpenReadingFrame, exonmodel.cc:101-156 */
+static void orf_init(Ctx* x) {
+    int n = x->L;
+    x->nsf = (int*)calloc(n + 3, sizeof(int)); x->nsr = (int*)calloc(n + 3, sizeof(int));
+    for (int r = 0; r < 3; r++) {
+        int sp = -1; for (int i = r; i <= n - 3; i += 3) { if (isStop(x, i)) sp = i; x->nsf[i] = sp; }
+        sp = -1; for (int i = r; i <= n - 3; i += 3) { if (isRCStop(x, i)) sp = i; x->nsr[i] = sp; }
+    }
+    if (n > 5) {
+        x->nsf[n - 2] = x->nsf[n - 5]; x->nsf[n - 1] = x->nsf[n - 4];
+        x->nsr[n - 2] = x->nsr[n - 5]; x->nsr[n - 1] = x->nsr[n - 4];
+    }
+}
+/* OpenReadingFrame::leftmostExonBegin, exonmodel.cc:165-198 */
+static int leftmostExonBegin(const Ctx* x, int frame, int base, int forward) {
+    int pos, n = x->L;
+    if (forward) pos = (frame == 0 || frame == 1) ? base - frame - 3 : base - frame;
+    else pos = (frame == 1 || frame == 2) ? base + frame - 5 : base - 2;
+    if (pos >= n) pos -= 3 * ((pos - n + 3) / 3);
+    int lmb = pos >= 0 ? (forward ? x->nsf[pos] : x->nsr[pos]) + 1 : 0;
+    const Model* m = x->m;
+    int max_allowed = m->max_exon_len - m->ass_up - m->ass_start - 2 - 2 - m->dss_start;
+    if (lmb < base - max_allowed) lmb = base - max_allowed;
+    return lmb;
+}
+
+/* ------------------------------------------------------------------ GC stairs, motif.cc:543-614 */
+static int nearestClass(const Model* m, const int cnt[4]) {
+    double sum = cnt[0] + cnt[1] + cnt[2] + cnt[3];
+    double r[4] = {0.25, 0.25, 0.25, 0.25};
+    if (sum > 0) for (int i = 0; i < 4; i++) r[i] = cnt[i] / sum;
+    double best = -1; int ret = -1;
+    for (int i = 0; i < m->ncent; i++) {
+        double w;
+        if (m->weighing == 3) {          /* multiNormalKernelWeight, motif.cc:156-177 */
+            double z[4], tmp[4] = {0, 0, 0, 0}, t = 0;
+            for (int j = 0; j < 4; j++) z[j] = r[j] - m->centroids[i][j];
+            for (int j = 0; j < 4; j++) for (int a = 0; a < 4; a++) tmp[j] += z[a] * m->wm[a][j];
+            for (int a = 0; a < 4; a++) t += tmp[a] * z[a];
+            w = 1 + 9 * exp(-t);
+        } else if (m->weighing == 2) {   /* gcContentClassWeight, motif.cc:135-153 */
+            double g1 = r[2] + r[1], g2 = m->centroids[i][2] + m->centroids[i][1];
+            int c1 = g1 < .43 ? 0 : g1 < .51 ? 1 : g1 < .57 ? 2 : 3, c2 = g2 < .43 ? 0 : g2 < .51 ? 1 : g2 < .57 ? 2 : 3;
+            w = c1 == c2;
+        } else w = 1;
+        if (w > best) { best = w; ret = i; }
+    }
+    return ret;
+}
+void orc_gc_stairs(const Model* m, const uint8_t* c, int n, int* idx) {
+    for (int i = 0; i < n; i++) idx[i] = -1;
+    int win = m->GCwinsize; if (win > n || win < 1) win = n;
+    int cnt[4] = {0, 0, 0, 0};
+    for (int i = 0; i < win; i++) if (c[i] < 4) cnt[c[i]]++;
+    int xx = nearestClass(m, cnt);
+    for (int i = 0; i <= win / 2; i++) idx[i] = xx;
+    for (int i = win / 2 + 1; i <= n - (win + 1) / 2; i++) {
+        int a = c[i + (win + 1) / 2 - 1], r = c[i - win / 2 - 1];
+        if (a < 4) cnt[a]++;
+        if (r < 4) cnt[r]--;
+        idx[i] = xx = nearestClass(m, cnt);
+    }
+    for (int i = n - (win + 1) / 2 + 1; i < n; i++) idx[i] = xx;
+    int x2 = -2, lastStep = 0, tot = 1000;
+    for (int i = 0; i < n; i++) if (idx[i] != x2) {
+        if (i - lastStep < tot && lastStep > 0 && idx[lastStep - 1] == idx[i])
+            for (int j = lastStep; j < i; j++) idx[j] = idx[i];
+        lastStep = i; x2 = idx[i];
+    }
+}
+
+/* ------------------------------------------------------------------ content prefix sums */
+static sc_t exon_emi1(const Ctx* x, int cls, int fwd, int f, int p) {
+    const Model* m = x->m;
+    int pn = fwd ? s2i(x, p - m->k, m->k + 1) : s2irc(x, p, m->k + 1);
+    if (pn < 0) return m->probN;
+    return m->xemi[((size_t)cls * 3 + f) << (2 * (m->k + 1)) | pn];
+}
+static void build_PX(Ctx* x, int cls) {
+    int L = x->L;
+    for (int phi = 0; phi < 3; phi++) {
+        sc_t* a = (sc_t*)malloc((L + 1) * sizeof(sc_t)); sc_t* b = (sc_t*)malloc((L + 1) * sizeof(sc_t));
+        /* a[p+1] = sum_{i<=p} fwd emission with frame mod3(phi+i); b likewise reverse with frame mod3(phi-i) */
+        a[0] = b[0] = 0;
+        for (int p = 0; p < L; p++) {
+            a[p + 1] = a[p] + (p >= x->m->k ? exon_emi1(x, cls, 1, mod3(phi + p), p) : 0);
+            b[p + 1] = b[p] + exon_emi1(x, cls, 0, mod3(phi - p), p);
+        }
+        x->PX[cls][phi] = a; x->PXR[cls][phi] = b;
+    }
+}
+/* ExonModel::seqProb, exonmodel.cc:1925-1973: product over [left,right] of the 3-periodic content model */
+static sc_t exon_seqProb(Ctx* x, int fwd, int left, int right, int frameOfRight) {
+    if (left > right) return 0;
+    int cls = x->cls;
+    if (!x->PX[cls][0]) build_PX(x, cls);
+    if (fwd) { int phi = mod3(frameOfRight - right); return x->PX[cls][phi][right + 1] - x->PX[cls][phi][left]; }
+    int phi = mod3(frameOfRight + right); return x->PXR[cls][phi][right + 1] - x->PXR[cls][phi][left];
+}
+/* eTermSeqProb :1979-2012 and initialSeqProb :2018-2034 — short windows, summed directly */
+static sc_t exon_shortProb(const Ctx* x, const sc_t* tab, int fwd, int left, int right, int frameOfRight) {
+    const Model* m = x->m; sc_t s = 0;
+    for (int p = right; p >= left; p--) {
+        int f = fwd ? mod3(frameOfRight - right + p) : mod3(frameOfRight + right - p);
+        int pn = fwd ? s2i(x, p - m->k, m->k + 1) : s2irc(x, p, m->k + 1);
+        s += pn < 0 ? m->probN : tab[((size_t)x->cls * 3 + f) << (2 * (m->k + 1)) | pn];
+    }
+    return s;
+}
+static sc_t intron_emi1(const Ctx* x, int cls, int p) {          /* forward k-mer ending at p */
+    const Model* m = x->m;
+    if (p - m->k < 0) return m->log025;
+    int pn = s2i(x, p - m->k, m->k + 1);
+    return pn < 0 ? m->log025 : m->iemi[((size_t)cls << (2 * (m->k + 1))) | pn];
+}
+static sc_t intron_emi1r(const Ctx* x, int cls, int p) {         /* rc k-mer starting at p, statemodel.cc:298-307 */
+    const Model* m = x->m;
+    if (!(p >= 0 && p + m->k < x->L)) return m->log025;
+    int pn = s2irc(x, p, m->k + 1);
+    return pn < 0 ? m->log025 : m->iemi[((size_t)cls << (2 * (m->k + 1))) | pn];
+}
+static void build_PI(Ctx* x, int cls) {
+    int L = x->L; sc_t* a = (sc_t*)malloc((L + 1) * sizeof(sc_t)); sc_t* b = (sc_t*)malloc((L + 1) * sizeof(sc_t));
+    a[0] = b[0] = 0;
+    for (int p = 0; p < L; p++) { a[p + 1] = a[p] + intron_emi1(x, cls, p); b[p + 1] = b[p] + intron_emi1r(x, cls, p); }
+    x->PI[cls] = a; x->PIR[cls] = b;
+}
+static sc_t intron_sum(Ctx* x, int rc, int left, int right) {   /* sum over [left,right], class of current column */
+    if (left > right) return 0;
+    int cls = x->cls; if (!x->PI[cls]) build_PI(x, cls);
+    const sc_t* P = rc ? x->PIR[cls] : x->PI[cls];
+    return P[right + 1] - P[left];
+}
+
+/* Motif::seqProb, motif.cc:308-331 */
+static sc_t motif_fwd(const Ctx* x, const sc_t* tab, int n, int k, int p) {
+    sc_t s = 0; size_t w = (size_t)1 << (2 * (k + 1));
+    for (int i = 0; i < n; i++) { int pn = s2i(x, p + i - k, k + 1); s += pn < 0 ? x->m->log025 : tab[((size_t)x->cls * n + i) * w + pn]; }
+    return s;
+}
+static sc_t motif_rc(const Ctx* x, const sc_t* tab, int n, int k, int p) {
+    sc_t s = 0; size_t w = (size_t)1 << (2 * (k + 1));
+    for (int i = 0; i < n; i++) { int pn = s2irc(x, p + i, k + 1); s += pn < 0 ? x->m->log025 : tab[((size_t)x->cls * n + (n - 1 - i)) * w + pn]; }
+    return s;
+}
+
+typedef struct { sc_t max; int state, base; } Oli;
+#define VV(j, s) (x->V[(size_t)(j) * m->S + (s)])
+#define TR(a, s) (m->trans[((size_t)x->cls * m->S + (a)) * m->S + (s)])
+
+/* ------------------------------------------------------------------ igenic, igenicmodel.cc:231-357 */
+static sc_t igenic_emi(const Ctx* x, int j) {
+    const Model* m = x->m;
+    if (j > m->k) {
+        int pn = s2i(x, j - m->k, m->k + 1);
+        return pn < 0 ? m->log025 : m->gemi[((size_t)x->cls << (2 * (m->k + 1))) | pn];
+    }
+    int basek = s2i(x, 0, j + 1);
+    if (basek < 0) return m->log025;
+    const double* P = m->gpls[j] + ((size_t)x->cls << (2 * (j + 1)));
+    /* quirk kept: the normaliser indexes basek/4 + i, not 4*(basek/4) + i (igenicmodel.cc:350) */
+    double den = exp(P[basek / 4]) + exp(P[basek / 4 + 1]) + exp(P[basek / 4 + 2]) + exp(P[basek / 4 + 3]);
+    return q(P[basek] - log(den));
+}
+static void igenic_eval(Ctx* x, int s, int j, Oli* o) {
+    const Model* m = x->m; const StateInfo* st = &m->st[s];
+    sc_t emi = igenic_emi(x, j);
+    /* max starts at -1 (igenicmodel.cc:238): the first ancestor is recorded even when every product is 0 */
+    o->base = j - 1; o->max = NEG; o->state = st->nanc ? st->anc[0] : -1;
+    for (int i = 0; i < st->nanc; i++) {
+        int a = st->anc[i]; sc_t pv = VV(j - 1, a);
+        if (isneg(pv)) continue;
+        sc_t cur = pv + (TR(a, s) + emi);
+        if (cur > o->max) { o->max = cur; o->state = a; }
+    }
+}
+
+/* ------------------------------------------------------------------ splice site scores */
+/* IntronModel::dSSProb, intronmodel.cc:1195-1248 */
+static sc_t dSSProb(const Ctx* x, int base, int fwd) {
+    const Model* m = x->m; int nonGT, idx;
+    if (fwd) {
+        int dsspos = base + m->dss_start;
+        if (!possDSS(x, dsspos)) return NEG;
+        nonGT = !is2(x, dsspos, G_, T_);
+        int a = s2i(x, base, m->dss_start), b = s2i(x, dsspos + 2, m->dss_end);
+        if (a < 0 || b < 0) return NEG;
+        idx = (a << (2 * m->dss_end)) | b;
+    } else {
+        int dsspos = base + m->dss_end;
+        if (!possRDSS(x, dsspos + 1)) return NEG;
+        nonGT = !is2(x, dsspos, A_, C_);
+        /* putReverseComplement of seq[dsspos+2, +dss_start) then of seq[base, +dss_end) */
+        int a = 0, b = 0;
+        for (int i = m->dss_start - 1; i >= 0; i--) { int c = at(x, dsspos + 2 + i); if (c > 3) return NEG; a = (a << 2) | (3 - c); }
+        for (int i = m->dss_end - 1; i >= 0; i--) { int c = at(x, base + i); if (c > 3) return NEG; b = (b << 2) | (3 - c); }
+        idx = (a << (2 * m->dss_end)) | b;
+    }
+    return nonGT ? m->dss_pat_non[idx] : m->dss_pat[idx];
+}
+/* IntronModel::aSSProb, intronmodel.cc:1116-1188 */
+static sc_t aSSProb(const Ctx* x, int base, int fwd) {
+    const Model* m = x->m; int nonAG, a, b; sc_t motif;
+    if (fwd) {
+        int asspos = base + m->ass_up + m->ass_start;
+        if (!possASS(x, asspos + 1)) return NEG;
+        nonAG = !is2(x, asspos, A_, G_);
+        a = s2i(x, base + m->ass_up, m->ass_start); b = s2i(x, asspos + 2, m->ass_end);
+        motif = base >= m->assm_k ? motif_fwd(x, m->assm, m->assm_n, m->assm_k, base) : NEG;
+    } else {
+        int asspos = base + m->ass_end;
+        if (!possRASS(x, asspos)) return NEG;
+        nonAG = !is2(x, asspos, C_, T_);
+        a = 0; b = 0;
+        for (int i = m->ass_start - 1; i >= 0; i--) { int c = at(x, asspos + 2 + i); if (c > 3) { a = -1; break; } a = (a << 2) | (3 - c); }
+        for (int i = m->ass_end - 1; i >= 0; i--) { int c = at(x, base + i); if (c > 3) { b = -1; break; } b = (b << 2) | (3 - c); }
+        int motifstart = base + m->ass_start + m->ass_end + 2, motifend = motifstart + m->ass_up;
+        motif = motifend + m->assm_k < x->L ? motif_rc(x, m->assm, m->assm_n, m->assm_k, motifstart) : m->ass_up * m->log025;
+    }
+    sc_t pat;
+    if (a < 0 || b < 0) pat = q(log(0.001) + (m->ass_start + m->ass_end) * log(0.25));
+    else { int idx = (a << (2 * m->ass_end)) | b; pat = nonAG ? m->ass_pat_non[idx] : m->ass_pat[idx]; }
+    if (isneg(motif) || isneg(pat)) return NEG;
+    return motif + pat;
+}
+
+/* ------------------------------------------------------------------ introns, intronmodel.cc:509-858 */
+static void intron_eval(Ctx* x, int s, int j, Oli* o) {
+    const Model* m = x->m; const StateInfo* st = &m->st[s];
+    o->max = NEG; o->state = -1; o->base = -1;
+    int L = x->L, fwd = st->fwd;
+    if (st->kind == K_LESSD) {
+        int eob = fwd ? j + m->ass_up + m->ass_start + 2 : j + m->dss_end + 2;
+        if (fwd ? (eob - 2 + 1 < L - 1 && !possASS(x, eob)) : (eob - 2 + 1 < L - 1 && !possRDSS(x, eob))) return;
+        int lessD0 = fwd && st->frame == 0, rlessD2 = !fwd && st->frame == 2;
+        int cod[3] = {4, 4, 4}, spl = !lessD0 && !rlessD2;
+        if (spl && eob < L - 2) {
+            if (fwd && st->frame == 1) { cod[1] = at(x, eob + 1); cod[2] = at(x, eob + 2); }
+            else if (fwd && st->frame == 2) { cod[2] = at(x, eob + 1); }
+            else if (!fwd && st->frame == 0) { cod[0] = cmpl(at(x, eob + 1)); }
+            else if (!fwd && st->frame == 1) { cod[0] = cmpl(at(x, eob + 2)); cod[1] = cmpl(at(x, eob + 1)); }
+        }
+        int lme = j - m->dStateLen; if (lme < 0) lme = 0;
+        for (int e = j - 1; e >= lme; e--) {
+            int any = 0;
+            for (int i = 0; i < st->nanc; i++) if (!isneg(VV(e, st->anc[i]))) { any = 1; break; }
+            if (!any) continue;
+            /* emiProbUnderModel(e+1, j), lessD branch :924-1000 */
+            int begin = e + 1, bob;
+            if (fwd) { bob = begin - m->dss_end - 2; if (bob >= 0 && !possDSS(x, bob)) continue; }
+            else { bob = begin - (m->ass_up + m->ass_start + 2); if (bob >= 0 && !possRASS(x, bob)) continue; }
+            if (spl && bob > 1) {
+                int c0 = cod[0], c1 = cod[1], c2 = cod[2];
+                if (fwd && st->frame == 1) c0 = at(x, bob - 1);
+                else if (fwd && st->frame == 2) { c0 = at(x, bob - 2); c1 = at(x, bob - 1); }
+                else if (!fwd && st->frame == 0) { c1 = cmpl(at(x, bob - 1)); c2 = cmpl(at(x, bob - 2)); }
+                else if (!fwd && st->frame == 1) { c2 = cmpl(at(x, bob - 1)); }
+                if (c0 < 4 && c1 < 4 && c2 < 4 && m->isstop[(c0 << 4) | (c1 << 2) | c2]) continue;
+            }
+            int ilen = eob - bob + 1;
+            if (ilen > m->d || ilen < 0 || ilen >= m->n_ld_intron) continue;   /* > d only with hints */
+            sc_t ld = m->ld_intron[ilen]; if (isneg(ld)) continue;
+            sc_t emi = ld + intron_sum(x, !fwd, begin, j);
+            for (int i = 0; i < st->nanc; i++) {
+                int a = st->anc[i]; sc_t pv = VV(e, a); if (isneg(pv)) continue;
+                sc_t pp = pv + (TR(a, s) + emi);
+                if (pp > o->max) { o->max = pp; o->state = a; o->base = e; }
+            }
+        }
+        return;
+    }
+    int eop, abort_; sc_t emi;
+    int dssw = m->dss_start + m->dss_end + 2, assw = m->ass_start + m->ass_end + 2;
+    switch (st->kind) {
+    case K_LONGDSS:
+        eop = j - dssw;
+        abort_ = fwd ? (eop < 0 || !possDSS(x, j - m->dss_end - 2 + 1)) : (eop < 0 || !possRDSS(x, j - m->dss_start));
+        break;
+    case K_EQUALD: eop = j - m->dStateLen; abort_ = eop < 0; break;
+    case K_GEO: eop = j - 1; abort_ = 0; break;
+    default: /* K_LONGASS */
+        eop = j - assw - m->ass_up;
+        abort_ = fwd ? (eop < 0 || !possASS(x, j - m->ass_end)) : (eop < 0 || !possRASS(x, j - m->ass_up - m->ass_start - 2 + 1));
+    }
+    if (abort_) return;
+    int any = 0;
+    for (int i = 0; i < st->nanc; i++) if (!isneg(VV(eop, st->anc[i]))) { any = 1; break; }
+    if (!any) return;
+    switch (st->kind) {
+    case K_LONGDSS: emi = dSSProb(x, j - dssw + 1, fwd); break;
+    case K_EQUALD: emi = intron_sum(x, 0, eop + 1, j); break;     /* forward k-mers also for requalD (:1046-1108) */
+    case K_GEO: emi = intron_emi1(x, x->cls, j); break;           /* :895-915, forward k-mer also for rgeometric */
+    default: emi = aSSProb(x, j - assw - m->ass_up + 1, fwd);
+    }
+    if (isneg(emi)) return;
+    o->base = eop;
+    for (int i = 0; i < st->nanc; i++) {
+        int a = st->anc[i]; sc_t pv = VV(eop, a); if (isneg(pv)) continue;
+        sc_t pp = pv + (TR(a, s) + emi);
+        if (pp > o->max) { o->max = pp; o->state = a; }
+    }
+}
+
+/* ------------------------------------------------------------------ exons */
+/* ExonModel::endPartEmiProb, exonmodel.cc:1272-1400 (no hints) */
+static sc_t endPart(Ctx* x, const StateInfo* st, int end) {
+    const Model* m = x->m; int L = x->L;
+    switch (st->ek) {
+    case E_SINGLE: case E_TERMINAL: {
+        int sp = end - 3 + 1;
+        if (sp < 0 || sp > L - 3 || !isStop(x, sp)) return NEG;
+        int a = at(x, sp), b = at(x, sp + 1), c = at(x, sp + 2);
+        if (a == T_ && b == A_ && c == A_) return m->ochre;
+        if (a == T_ && b == A_ && c == G_) return m->amber;
+        if (a == T_ && b == G_ && c == A_) return m->opal;
+        fprintf(stderr, "oracle: unknown stop codon\n"); exit(3);
+    }
+    case E_RSINGLE: case E_RINITIAL: {
+        int sp = end - m->tiw - 3 + 1;
+        if (sp < 0) return NEG;
+        int pn = s2irc(x, sp, 3);
+        if (pn < 0 || isneg(m->startp[pn])) return NEG;
+        sc_t p = m->startp[pn];
+        if (sp + 3 + m->tiw - 1 + m->tis_k < L) p += motif_rc(x, m->tis, m->tis_n, m->tis_k, sp + 3);
+        else p = (L - (sp + 3)) * m->log025;
+        return p;
+    }
+    case E_INITIAL: case E_INTERNAL: {
+        int dsspos = end + m->dss_start + 1;
+        if (end == L - 1) return 0;
+        if ((dsspos + 2 - 1 < L && !possDSS(x, dsspos)) || end + m->dss_start >= L ||
+            leftmostExonBegin(x, st->frame - 1, end + m->dss_start, 1) >= end) return NEG;
+        return 0;
+    }
+    default: { /* E_RTERMINAL, E_RINTERNAL */
+        int asspos = end + m->ass_end + 1;
+        if (end == L - 1) return 0;
+        if (end + m->ass_end + 2 < L && possRASS(x, asspos)) return 0;
+        return NEG;
+    }
+    }
+}
+
+/* ExonModel::notEndPartEmiProb, exonmodel.cc:1417-1859 (no hints) */
+static sc_t notEndPart(Ctx* x, const StateInfo* st, int bos, int right, int frameOfRight) {
+    const Model* m = x->m; int L = x->L, k = m->k, fwd = st->fwd, win = st->frame;
+    sc_t beginPart;
+    int bobe = bos - st->innerPartOffset;
+    switch (st->ek) {
+    case E_SINGLE: case E_INITIAL: {
+        if (!(bobe >= 0 && bobe < L - 2)) return NEG;
+        int pn = s2i(x, bobe, 3);
+        if (pn < 0 || isneg(m->startp[pn])) return NEG;
+        beginPart = m->startp[pn];
+        int tis = bobe - m->tiw;
+        if (tis > m->tis_k) beginPart += motif_fwd(x, m->tis, m->tis_n, m->tis_k, tis);
+        else beginPart += (sc_t)(bos - 3) * m->log025;
+        break;
+    }
+    case E_TERMINAL: case E_INTERNAL:
+        if (bos > 0) {
+            if (bobe < 0 || (bobe - 2 >= 0 && !possASS(x, bobe - 1))) return NEG;
+            beginPart = 0;
+        } else if (bos == 0) beginPart = 0;
+        else return NEG;
+        break;
+    case E_RSINGLE: case E_RTERMINAL: {
+        if (bobe < 0) return NEG;
+        int a = at(x, bobe), b = at(x, bobe + 1), c = at(x, bobe + 2);
+        if (a == T_ && b == T_ && c == A_) beginPart = m->ochre;
+        else if (a == C_ && b == T_ && c == A_) beginPart = m->amber;
+        else if (a == T_ && b == C_ && c == A_) beginPart = m->opal;
+        else return NEG;
+        if (isneg(beginPart)) return NEG;
+        break;
+    }
+    default: /* E_RINITIAL, E_RINTERNAL */
+        if (bos == 0) beginPart = 0;
+        else if (bobe < 0 || (bobe - 2 > 0 && !possRDSS(x, bobe - 1))) return NEG;
+        else beginPart = 0;
+    }
+    sc_t rest;
+    if (bos > right) {
+        rest = -(sc_t)(bos - right - 1) * m->log025;      /* POWER4TOTHE(bos-right-1) */
+    } else if (right - bos <= k) {
+        int l = right - bos;
+        int pn = fwd ? s2i(x, bos, l + 1) : s2irc(x, bos, l + 1);
+        if (pn < 0) rest = (sc_t)(l + 1) * m->probN;
+        else {
+            int f = fwd ? frameOfRight : mod3(frameOfRight + right - bos);
+            rest = m->xpls[l][(((size_t)x->cls * 3 + f) << (2 * (l + 1))) | pn];
+        }
+    } else {
+        int endOfStart = bos + k - 1, beginOfInitP = right - (k - 1);
+        if (k == 0) rest = 0;
+        else {
+            int pn = fwd ? s2i(x, bos, k) : s2irc(x, beginOfInitP, k);
+            if (pn < 0) rest = (sc_t)k * m->probN;
+            else {
+                int f = fwd ? mod3(frameOfRight - right + endOfStart) : mod3(frameOfRight + right - beginOfInitP);
+                rest = m->xpls[k - 1][(((size_t)x->cls * 3 + f) << (2 * k)) | pn];
+            }
+        }
+        if (isneg(rest)) return NEG;
+        int endOfInitial, beginOfTerm, endOfTerm, beginOfInitial;
+        switch (st->ek) {
+        case E_SINGLE:
+            endOfInitial = endOfStart + m->init_len; if (endOfInitial > right) endOfInitial = right;
+            rest += exon_shortProb(x, m->xinit, 1, endOfStart + 1, endOfInitial, mod3(frameOfRight - right + endOfInitial))
+                  + exon_seqProb(x, 1, endOfInitial + 1, right, frameOfRight);
+            break;
+        case E_INITIAL:
+            endOfInitial = endOfStart + m->init_len;
+            if (endOfInitial > right) { endOfInitial = right; beginOfTerm = right + 1; }
+            else { beginOfTerm = right - m->et_len + 1; if (beginOfTerm <= endOfInitial) beginOfTerm = right + 1; }
+            rest += exon_shortProb(x, m->xinit, 1, endOfStart + 1, endOfInitial, mod3(frameOfRight - right + endOfInitial))
+                  + exon_seqProb(x, 1, endOfInitial + 1, beginOfTerm - 1, mod3(frameOfRight - right + (beginOfTerm - 1)))
+                  + exon_shortProb(x, m->xet, 1, beginOfTerm, right, frameOfRight);
+            break;
+        case E_INTERNAL:
+            beginOfTerm = right - m->et_len + 1; if (beginOfTerm <= endOfStart) beginOfTerm = right + 1;
+            rest += exon_seqProb(x, 1, endOfStart + 1, beginOfTerm - 1, mod3(frameOfRight - right + (beginOfTerm - 1)))
+                  + exon_shortProb(x, m->xet, 1, beginOfTerm, right, frameOfRight);
+            break;
+        case E_TERMINAL:
+            rest += exon_seqProb(x, 1, endOfStart + 1, right, frameOfRight);
+            break;
+        case E_RSINGLE:
+            beginOfInitial = beginOfInitP - m->init_len; if (beginOfInitial < bos) beginOfInitial = bos;
+            rest += exon_shortProb(x, m->xinit, 0, beginOfInitial, beginOfInitP - 1, mod3(frameOfRight + right - (beginOfInitP - 1)))
+                  + exon_seqProb(x, 0, bos, beginOfInitial - 1, mod3(frameOfRight + right - (beginOfInitial - 1)));
+            break;
+        case E_RINITIAL:
+            beginOfInitial = beginOfInitP - m->init_len;
+            if (beginOfInitial < bos) { beginOfInitial = bos; endOfTerm = bos - 1; }
+            else { endOfTerm = bos + m->et_len - 1; if (endOfTerm >= beginOfInitial) endOfTerm = bos - 1; }
+            rest += exon_shortProb(x, m->xinit, 0, beginOfInitial, beginOfInitP - 1, mod3(frameOfRight + right - (beginOfInitP - 1)))
+                  + exon_seqProb(x, 0, endOfTerm + 1, beginOfInitial - 1, mod3(frameOfRight + right - (beginOfInitial - 1)))
+                  + exon_shortProb(x, m->xet, 0, bos, endOfTerm, mod3(frameOfRight + right - endOfTerm));
+            break;
+        case E_RINTERNAL:
+            endOfTerm = bos + m->et_len - 1; if (endOfTerm >= beginOfInitP) endOfTerm = bos - 1;
+            rest += exon_seqProb(x, 0, endOfTerm + 1, beginOfInitP - 1, mod3(frameOfRight + right - (beginOfInitP - 1)))
+                  + exon_shortProb(x, m->xet, 0, bos, endOfTerm, mod3(frameOfRight + right - endOfTerm));
+            break;
+        default: /* E_RTERMINAL */
+            rest += exon_seqProb(x, 0, bos, beginOfInitP - 1, mod3(frameOfRight + right - (beginOfInitP - 1)));
+        }
+    }
+    if (isneg(rest)) return NEG;
+    int eobe = right + st->innerPartEndOffset, len = eobe - bobe + 1;
+    if (len < 1 || len >= m->n_ld_exon) return NEG;
+    sc_t lp;
+    switch (st->ek) {
+    case E_SINGLE: case E_RSINGLE: lp = len % 3 == 0 ? m->ld_single[len] : NEG; break;
+    case E_INITIAL: lp = (len % 3 == win && len > 2) ? m->ld_initial[len] : NEG; break;
+    case E_RINITIAL: lp = len > 2 ? m->ld_initial[len] : NEG; break;
+    case E_INTERNAL: case E_RINTERNAL: lp = m->ld_internal[len]; break;
+    case E_TERMINAL: lp = m->ld_terminal[len]; break;
+    default: lp = mod3(2 - len) == win ? m->ld_terminal[len] : NEG;
+    }
+    if (isneg(lp)) return NEG;
+    return beginPart + rest + (m->log3 + lp);
+}
+
+/* ExonModel::viterbiForwardAndSampling, exonmodel.cc:899-1179 */
+static void exon_eval(Ctx* x, int s, int j, Oli* o) {
+    const Model* m = x->m; const StateInfo* st = &m->st[s]; int L = x->L, fwd = st->fwd, win = st->frame;
+    o->max = NEG; o->state = -1; o->base = -1;
+    sc_t ep = endPart(x, st, j);
+    int eobe = j + st->baseOffset, right = eobe - st->innerPartEndOffset;
+    if (isneg(ep) || right < 0) return;
+    int frameOfRight = fwd ? mod3(win - (eobe + 1) + right) : mod3(win + eobe + 1 - right);
+    int eons = (st->ek == E_TERMINAL || st->ek == E_SINGLE) ? eobe - 3 : eobe;
+    if (eons > L - 1) eons = L - 1;
+    int feons = fwd ? mod3(win - 1 - eobe + eons) : mod3(win + 1 + eobe - eons);
+    int ORFleft = leftmostExonBegin(x, feons, eons, fwd);
+    int startMax = eobe + st->innerPartOffset - m->min_exon_length + 1, startMin;
+    if (st->ek == E_RTERMINAL || st->ek == E_RSINGLE) startMin = startMax = ORFleft + 2;
+    else {
+        startMin = ORFleft <= 0 ? 0 : ORFleft + st->innerPartOffset;
+        if (startMax > j + st->beginPartLen) startMax = j + st->beginPartLen;
+    }
+    for (int bos = startMax; bos >= startMin; bos--) {
+        int eop = bos - st->beginPartLen - 1;
+        sc_t nep = notEndPart(x, st, bos, right, frameOfRight);
+        if (isneg(nep) || eop >= L) continue;
+        int col = eop >= 0 ? eop : 0;
+        int bobe = bos - st->innerPartOffset, len = eobe - bobe + 1;
+        for (int i = 0; i < st->nanc; i++) {
+            int a = st->anc[i]; sc_t pv = VV(col, a); if (isneg(pv)) continue;
+            int pf = m->st[a].frame;
+            if (st->ek == E_SINGLE || st->ek == E_RSINGLE || st->ek == E_RTERMINAL || st->ek == E_INITIAL ||
+                win == mod3(fwd ? pf + len : pf - len)) {
+                sc_t pp = pv + (TR(a, s) + ep + nep);
+                if (pp > o->max) { o->max = pp; o->base = eop; o->state = a; }
+            }
+        }
+    }
+}
+
+static void state_eval(Ctx* x, int s, int j, Oli* o) {
+    switch (x->m->st[s].kind) {
+    case K_IGENIC: igenic_eval(x, s, j, o); break;
+    case K_EXON: exon_eval(x, s, j, o); break;
+    default: intron_eval(x, s, j, o);
+    }
+}
+
+/* ------------------------------------------------------------------ driver */
+static int trunc_flag(int type, int end, int predEnd, int L) {      /* gene.cc:309-321 */
+    int isIntron = (type >= T_LESSD0 && type <= 23) || (type >= T_RLESSD0 && type <= 58);
+    int t = 0;
+    if (end == L - 1 && ((type >= 2 && type <= 7) || (type >= 38 && type <= 43) || isIntron)) t |= 2;   /* TRUNC_RIGHT */
+    if ((predEnd == -1 || predEnd == 0) && ((type >= 5 && type <= 8) || (type >= 37 && type <= 40) || isIntron)) t |= 1; /* TRUNC_LEFT */
+    return t;
+}
+
+/*
+ * Decode one window.  dna: ASCII, any case.  gc_in: per-position class or NULL (computed here).
+ * Vout: optional [L][S] int64 Q40 scores (NEG = absent).  Path arrays (capacity cap) are filled in
+ * left-to-right order, one entry per backtrace step exactly as NAMGene::getViterbiPath pushes them.
+ * Returns number of path states, or <0: -1 no feasible path, -2 stuck, -3 capacity.
+ */
+int orc_viterbi(const Model* m, const char* dna, int L, const int* gc_in, int64_t* Vout, int* gc_out,
+                int cap, int* ptype, int* pbegin, int* pend, int* ptrunc, double* logp) {
+    Ctx X; memset(&X, 0, sizeof X); Ctx* x = &X;
+    x->m = m; x->L = L;
+    uint8_t* c = (uint8_t*)malloc(L + 8);
+    int anynuc = 0;
+    for (int i = 0; i < L; i++) {
+        switch (dna[i]) { case 'a': case 'A': c[i] = 0; break; case 'c': case 'C': c[i] = 1; break;
+                          case 'g': case 'G': c[i] = 2; break; case 't': case 'T': c[i] = 3; break; default: c[i] = 4; }
+        anynuc |= c[i] < 4;
+    }
+    x->c = c;
+    int* gc = (int*)malloc(L * sizeof(int));
+    if (gc_in) memcpy(gc, gc_in, L * sizeof(int)); else orc_gc_stairs(m, c, L, gc);
+    if (gc_out) memcpy(gc_out, gc, L * sizeof(int));
+    x->gc = gc;
+    orf_init(x);
+    x->V = (sc_t*)malloc((size_t)L * m->S * sizeof(sc_t));
+    for (int s = 0; s < m->S; s++) x->V[s] = m->init[s];
+    Oli o;
+    if (!anynuc) {   /* namgene.cc:205-226 */
+        for (int j = 1; j < L; j++) for (int s = 0; s < m->S; s++) VV(j, s) = s == 0 ? VV(j - 1, s) + m->log025 : NEG;
+    } else {
+        for (int j = 1; j < L; j++) {
+            x->cls = gc[j];
+            for (int s = 0; s < m->S; s++) { state_eval(x, s, j, &o); VV(j, s) = o.max; }
+        }
+    }
+    if (Vout) memcpy(Vout, x->V, (size_t)L * m->S * sizeof(sc_t));
+    /* getViterbiPath, namgene.cc:432-510 */
+    int ret = 0, state = -1; sc_t best = NEG;
+    for (int s = 0; s < m->S; s++) {
+        sc_t v = VV(L - 1, s); if (isneg(v) || isneg(m->term[s])) continue;
+        v += m->term[s]; if (v > best) { best = v; state = s; }
+    }
+    if (state < 0) ret = -1;
+    else {
+        if (logp) *logp = ldexp((double)best, -FRAC_BITS);
+        int base = L - 1, n = 0;
+        /* collect right-to-left, then reverse */
+        while (base > 0) {
+            if (!anynuc) { o.state = 0; o.base = base - 1; }
+            else { x->cls = gc[base]; state_eval(x, state, base, &o); }
+            if (o.state < 0 || (o.base >= base && o.state == state) || o.base > base + 10) { ret = -2; break; }
+            if (n >= cap) { ret = -3; break; }
+            ptype[n] = m->st[state].type; pbegin[n] = o.base + 1; pend[n] = base;
+            ptrunc[n] = trunc_flag(m->st[state].type, base, o.base, L);
+            n++; base = o.base; state = o.state;
+        }
+        if (ret == 0) {
+            for (int i = 0; i < n / 2; i++) {
+                int t;
+                t = ptype[i]; ptype[i] = ptype[n - 1 - i]; ptype[n - 1 - i] = t;
+                t = pbegin[i]; pbegin[i] = pbegin[n - 1 - i]; pbegin[n - 1 - i] = t;
+                t = pend[i]; pend[i] = pend[n - 1 - i]; pend[n - 1 - i] = t;
+                t = ptrunc[i]; ptrunc[i] = ptrunc[n - 1 - i]; ptrunc[n - 1 - i] = t;
+            }
+            ret = n;
+        }
+    }
+    for (int cl = 0; cl < 8; cl++) {
+        for (int p = 0; p < 3; p++) { free(x->PX[cl][p]); free(x->PXR[cl][p]); }
+        free(x->PI[cl]); free(x->PIR[cl]);
+    }
+    free(x->V); free(x->nsf); free(x->nsr); free(gc); free(c);
+    return ret;
+}
