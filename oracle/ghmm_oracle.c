@@ -24,10 +24,8 @@
  * system the CUDA path uses, so CUDA-vs-oracle comparisons are bit-exact while
  * oracle-vs-reference comparisons are exact on the path and ~1e-9 on the score.
  *
- * Known deviation (documented in DESIGN.md): the reference's SnippetProbs memo
- * (statemodel.cc:283-393) leaks the GC class active at first touch into lessD emissions when a
- * window has more than one GC class; here lessD uses the class of the current column.
- * Single-class windows are unaffected.
+ * History-dependent behaviour that is restated rather than "fixed": the SnippetProbs memo
+ * (statemodel.cc:283-393) keeps the GC class active at first touch, see snip_get() below.
  */
 #include <math.h>
 #include <stdint.h>
@@ -205,6 +203,7 @@ Model* orc_model_load(const char* path) {
 int orc_model_statecount(const Model* m) { return m->S; }
 
 /* ------------------------------------------------------------------ per-window context */
+typedef struct SnipEnt { int len; sc_t val; struct SnipEnt* next; } SnipEnt;
 typedef struct {
     const Model* m; int L; const uint8_t* c;   /* c[i] in 0..3, 4 = other */
     const int* gc;                              /* class per position */
@@ -213,6 +212,7 @@ typedef struct {
     sc_t* V;                                    /* [L][S] */
     sc_t *PX[8][3], *PXR[8][3];                 /* exon content prefix sums [class][phi] (lazily built) */
     sc_t *PI[8], *PIR[8];                       /* intron content prefix sums per class (fwd k-mer / rc k-mer) */
+    struct SnipEnt **snF, **snL;                /* SnippetProbs restatement: per base first/last entry, [2][L] (fwd, rc) */
 } Ctx;
 
 static inline int at(const Ctx* x, int p) { return (p < 0 || p >= x->L) ? 5 : x->c[p]; }
@@ -372,6 +372,57 @@ static sc_t intron_sum(Ctx* x, int rc, int left, int right) {   /* sum over [lef
     return P[right + 1] - P[left];
 }
 
+/*
+ * SnippetProbs::getSeqProb / addProb / SnippetList::getProb, statemodel.cc:283-393.
+ * The memo is restated entry for entry because it is NOT a pure cache: an elementary piece keeps the
+ * emission table (GC class) that was active when it was first computed (IntronModel::updateToLocalGC,
+ * intronmodel.cc:495-503, swaps the table pointer but never clears the lists), so on windows with
+ * more than one GC class the value of a lessD segment depends on the history of calls.
+ */
+static sc_t snip_elem(Ctx* x, int rc, int base, int len) {       /* getElemSeqProb :283-310, current class */
+    int cls = x->cls; if (!x->PI[cls]) build_PI(x, cls);
+    const sc_t* P = rc ? x->PIR[cls] : x->PI[cls];
+    return P[base + 1] - P[base - len + 1];
+}
+static void snip_add(Ctx* x, int rc, int base, int len, sc_t p) { /* addProb :344-370 */
+    SnipEnt** F = x->snF + (size_t)rc * x->L; SnipEnt** La = x->snL + (size_t)rc * x->L;
+    SnipEnt* e = (SnipEnt*)malloc(sizeof *e); e->len = len; e->val = p; e->next = NULL;
+    if (!F[base]) { F[base] = La[base] = e; return; }
+    if (La[base]->len < len) { La[base]->next = e; La[base] = e; return; }
+    SnipEnt* t = F[base];
+    if (t->len > len) { e->next = t; F[base] = e; return; }
+    while (t && t->next && t->next->len < len) t = t->next;
+    if (t->next && t->next->len == len) { free(e); return; }      /* "tried to add snippet of same length" */
+    e->next = t->next; t->next = e;
+}
+static sc_t snip_get(Ctx* x, int rc, int base, int len) {         /* getSeqProb :312-342 */
+    if (len == 0) return 0;
+    SnipEnt** F = x->snF + (size_t)rc * x->L; SnipEnt** La = x->snL + (size_t)rc * x->L;
+    sc_t p;
+    if (F[base]) {
+        if (La[base]->len < len) {
+            int ll = La[base]->len;
+            p = snip_get(x, rc, base - ll, len - ll) + La[base]->val;
+            snip_add(x, rc, base, len, p);
+        } else {
+            int partlen = len; SnipEnt* t = F[base];               /* SnippetList::getProb :379-393 */
+            if (t->len > partlen) { partlen = 0; p = 0; }
+            else {
+                while (t->next && t->next->len < partlen) t = t->next;
+                if (!t->next || t->next->len > partlen) { partlen = t->len; p = t->val; }
+                else p = t->next->val;
+            }
+            if (partlen != len) {
+                sc_t prest;
+                if (partlen == 0) { prest = snip_elem(x, rc, base, len); snip_add(x, rc, base, len, prest); }
+                else prest = snip_get(x, rc, base - partlen, len - partlen);
+                p += prest;
+            }
+        }
+    } else { p = snip_elem(x, rc, base, len); snip_add(x, rc, base, len, p); }
+    return p;
+}
+
 /* Motif::seqProb, motif.cc:308-331 */
 static sc_t motif_fwd(const Ctx* x, const sc_t* tab, int n, int k, int p) {
     sc_t s = 0; size_t w = (size_t)1 << (2 * (k + 1));
@@ -500,7 +551,7 @@ static void intron_eval(Ctx* x, int s, int j, Oli* o) {
             int ilen = eob - bob + 1;
             if (ilen > m->d || ilen < 0 || ilen >= m->n_ld_intron) continue;   /* > d only with hints */
             sc_t ld = m->ld_intron[ilen]; if (isneg(ld)) continue;
-            sc_t emi = ld + intron_sum(x, !fwd, begin, j);
+            sc_t emi = ld + snip_get(x, !fwd, j, j - begin + 1);
             for (int i = 0; i < st->nanc; i++) {
                 int a = st->anc[i]; sc_t pv = VV(e, a); if (isneg(pv)) continue;
                 sc_t pp = pv + (TR(a, s) + emi);
@@ -779,6 +830,7 @@ int orc_viterbi(const Model* m, const char* dna, int L, const int* gc_in, int64_
     if (gc_out) memcpy(gc_out, gc, L * sizeof(int));
     x->gc = gc;
     orf_init(x);
+    x->snF = (SnipEnt**)calloc((size_t)2 * L, sizeof(SnipEnt*)); x->snL = (SnipEnt**)calloc((size_t)2 * L, sizeof(SnipEnt*));
     x->V = (sc_t*)malloc((size_t)L * m->S * sizeof(sc_t));
     for (int s = 0; s < m->S; s++) x->V[s] = m->init[s];
     Oli o;
@@ -826,6 +878,8 @@ int orc_viterbi(const Model* m, const char* dna, int L, const int* gc_in, int64_
         for (int p = 0; p < 3; p++) { free(x->PX[cl][p]); free(x->PXR[cl][p]); }
         free(x->PI[cl]); free(x->PIR[cl]);
     }
+    for (size_t i = 0; i < (size_t)2 * L; i++) { SnipEnt* t = x->snF[i]; while (t) { SnipEnt* nx = t->next; free(t); t = nx; } }
+    free(x->snF); free(x->snL);
     free(x->V); free(x->nsf); free(x->nsr); free(gc); free(c);
     return ret;
 }
