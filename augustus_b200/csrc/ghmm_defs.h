@@ -1,0 +1,130 @@
+/*
+ * ghmm_defs.h — shared definitions of the B200 GHMM decoder (host + device).
+ *
+ * Number system: log probabilities in Q23.40 fixed point (int64).  Sums are exact and associative,
+ * so prefix-sum differences, lazily evaluated self-loop chains and warp-parallel reductions give
+ * bit-identical results in any evaluation order.  SC_NEG stands for probability zero, which is a
+ * structural value in the reference ("state impossible", e.g. exonmodel.cc:1083).
+ */
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define AUGB_HD __host__ __device__ __forceinline__
+#define AUGB_D __device__ __forceinline__
+#else
+#define AUGB_HD inline
+#define AUGB_D inline
+#endif
+
+namespace augb {
+
+typedef int64_t sc_t;
+constexpr int FRAC_BITS = 40;
+constexpr sc_t SC_NEG = -((sc_t)1 << 61);
+constexpr sc_t SC_NEGT = -((sc_t)1 << 60);
+AUGB_HD bool isneg(sc_t x) { return x <= SC_NEGT; }
+AUGB_HD int mod3(int k) { return k >= 0 ? k % 3 : (k % 3 + 3) % 3; }
+
+constexpr int MAXS = 96;      /* states */
+constexpr int MAXC = 8;       /* GC classes */
+constexpr int MAXANC = 8;
+constexpr int NCHAIN = 7;     /* igenic + 3 geometric + 3 reverse geometric */
+
+/* reference StateType values (include/types.hh:492-512) used by the kernels */
+enum : int {
+    T_IGENIC = 0, T_SINGLE = 1, T_INITIAL0 = 2, T_INTERNAL0 = 5, T_TERMINAL = 8,
+    T_LESSD0 = 9, T_LONGDSS0 = 10, T_EQUALD0 = 11, T_GEO0 = 12, T_LONGASS0 = 13,
+    T_RSINGLE = 36, T_RINITIAL = 37, T_RINTERNAL0 = 38, T_RTERMINAL0 = 41,
+    T_RLESSD0 = 44, T_RLONGDSS0 = 45, T_REQUALD0 = 46, T_RGEO0 = 47, T_RLONGASS0 = 48
+};
+enum : int { K_IGENIC, K_EXON, K_LESSD, K_LONGDSS, K_EQUALD, K_GEO, K_LONGASS };
+enum : int { E_SINGLE, E_INITIAL, E_INTERNAL, E_TERMINAL, E_RSINGLE, E_RINITIAL, E_RINTERNAL, E_RTERMINAL };
+
+struct StateDesc {
+    int16_t type;
+    int8_t kind, fwd, frame, ek;
+    int8_t beginPartLen, innerPartOffset, baseOffset, innerPartEndOffset;   /* exonmodel.cc:231-279 */
+    int8_t chain;          /* chain id if this is a self-loop chain state, else -1 */
+    int8_t feeds;          /* chain id this state is an ancestor of (one-base successor), else -1 */
+    int8_t nanc;
+    int8_t anc[MAXANC];    /* ancestors in state-index order (statemodel.cc:41-46) */
+};
+
+/* activity mask bits, one uint16 per column, computed by the prep pass from the sequence alone */
+enum : unsigned {
+    MB_LONGDSS = 1u << 0, MB_LESSD = 1u << 1, MB_LONGASS = 1u << 2, MB_XDSS = 1u << 3, MB_XSTOP = 1u << 4,
+    MB_RLONGASS = 1u << 5, MB_RLESSD = 1u << 6, MB_RLONGDSS = 1u << 7, MB_XRASS = 1u << 8, MB_XRSTART = 1u << 9
+};
+
+/* prefix arrays per GC class, each (L+1) long: P[i+1] - P[l] = sum over positions l..i */
+enum : int { PA_PI = 0, PA_PIR = 1, PA_PX = 2 /* +phi */, PA_PXR = 5 /* +phi */, PA_PER_CLASS = 8 };
+
+struct DevModel {
+    int S, C, k, d, dStateLen;
+    int dss_start, dss_end, ass_start, ass_end, ass_up, tiw, init_len, et_len;
+    int max_exon_len, min_exon_length, dss_gc_allowed;
+    int tis_n, tis_k, assm_n, assm_k, n_ld_exon, n_ld_intron;
+    int GCwinsize, weighing, ncent;
+    StateDesc st[MAXS];
+    int8_t chain_state[NCHAIN];            /* state index of each chain (-1 if absent) */
+    /* role -> state index (-1 if absent) */
+    int8_t r_longdss[2][3], r_lessd[2][3], r_equald[2][3], r_longass[2][3];      /* [0]=fwd [1]=rev */
+    int8_t r_single, r_initial[3], r_internal[3], r_terminal, r_rsingle, r_rinitial, r_rinternal[3], r_rterminal[3];
+    /* tables (device pointers on the GPU, host pointers in the test emulator) */
+    const sc_t *init, *term, *trans;                /* trans[(c*S + a)*S + s] */
+    const sc_t *xemi, *xinit, *xet;                 /* [(c*3+f) << 10 | kmer] */
+    const sc_t* xpls[5];                            /* [(c*3+f) << 2(l+1) | pat] */
+    const sc_t *iemi, *gemi;                        /* [c << 10 | kmer] */
+    const sc_t* gfirst;                             /* igenic emission for columns <= k: [c][off(j)+pat] */
+    const sc_t *tis, *assm;                         /* [(c*n + i) << 2(k+1) | pat] */
+    const sc_t *ld_single, *ld_initial, *ld_internal, *ld_terminal, *ld_intron;
+    const sc_t *ass_pat, *ass_pat_non, *dss_pat, *dss_pat_non;
+    sc_t startp[64];
+    uint8_t isstop[64];
+    sc_t ochre, amber, opal, probN, log025, log3, ass_invalid_pat;
+    double centroids[MAXC * 4 * 4][4];
+    double wm[4][4];
+};
+
+/* one DP cell of a sparse (non-chain) state that is non-zero */
+struct Event {
+    int32_t col;
+    int16_t state, pred;
+    int32_t predbase;
+    int32_t pad;
+    sc_t V;
+};
+/* candidate list entry: a predecessor cell that later state ends look back to */
+struct Cand {
+    int32_t col;        /* column of the predecessor cell (endOfPred) */
+    int32_t state;      /* predecessor state index */
+    sc_t V;
+};
+/* change point of a lazily evaluated self-loop chain: V[col][chain] = tilde + A[col], entered from pred at col-1 */
+struct ChainCP {
+    int32_t col;
+    int32_t pred;       /* -1: initial probability at column 0 */
+    sc_t tilde;
+};
+
+/* candidate lists of a window */
+enum : int { CL_LD = 0 /* +f: longdss_f */, CL_RA = 3 /* +f: rlongass_f */, CL_LA = 6 /* +phase */, CL_RD = 9 /* +phase */, NCL = 12 };
+
+/* per-window view of the workspace (all pointers device/global) */
+struct WinView {
+    int L, nclassmask, ev_cap, cl_cap, cp_cap;
+    const uint8_t* code;       /* 0..3, 4 = unknown */
+    const uint8_t* gc;         /* class per position */
+    const uint16_t* mask;
+    const sc_t* parr;          /* [c][PA_PER_CLASS][L+1] */
+    const sc_t *AIG, *AGEO;    /* chain prefix arrays, [L] */
+    const int32_t *nsf, *nsr;  /* nearestStopForward / Reverse (exonmodel.cc:101-156) */
+    Event* ev; int32_t* evstart;
+    Cand* cl[NCL];
+    ChainCP* cp[NCHAIN];
+    /* results */
+    int32_t* out_n_ev; int32_t* out_ncp; int32_t* out_status;
+};
+
+}  // namespace augb

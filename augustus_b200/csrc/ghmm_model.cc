@@ -1,0 +1,251 @@
+/* ghmm_model.cc — see ghmm_model.h */
+#include "ghmm_model.h"
+
+#include <cstdio>
+
+namespace augb {
+
+namespace {
+struct Reader {
+    HostModel::BlobView b; std::string* err; bool ok = true;
+    const augb200_blob_entry* need(const char* name) {
+        const augb200_blob_entry* e = b.find(name);
+        if (!e) { ok = false; *err = std::string("blob entry missing: ") + name; return nullptr; }
+        if (e->offset + e->nbytes > b.n) { ok = false; *err = std::string("blob entry out of range: ") + name; return nullptr; }
+        return e;
+    }
+    int i32(const char* name) { auto e = need(name); return e ? *(const int32_t*)(b.p + e->offset) : 0; }
+    double f64(const char* name) { auto e = need(name); return e ? *(const double*)(b.p + e->offset) : 0; }
+    const double* darr(const char* name, size_t* n) { auto e = need(name); if (!e) { *n = 0; return nullptr; } *n = e->nbytes / 8; return (const double*)(b.p + e->offset); }
+    const int32_t* iarr(const char* name, size_t* n) { auto e = need(name); if (!e) { *n = 0; return nullptr; } *n = e->nbytes / 4; return (const int32_t*)(b.p + e->offset); }
+};
+}  // namespace
+
+static void classify(StateDesc& s, const DevModel& m) {
+    int t = s.type;
+    s.fwd = t < 36; s.frame = 0; s.chain = -1; s.feeds = -1; s.kind = -1; s.ek = -1;
+    s.beginPartLen = s.innerPartOffset = s.baseOffset = s.innerPartEndOffset = 0;
+    if (t == T_IGENIC) { s.kind = K_IGENIC; s.fwd = 1; return; }
+    int e = -1;
+    if (t == T_SINGLE) e = E_SINGLE;
+    else if (t >= T_INITIAL0 && t < T_INITIAL0 + 3) { e = E_INITIAL; s.frame = t - T_INITIAL0; }
+    else if (t >= T_INTERNAL0 && t < T_INTERNAL0 + 3) { e = E_INTERNAL; s.frame = t - T_INTERNAL0; }
+    else if (t == T_TERMINAL) e = E_TERMINAL;
+    else if (t == T_RSINGLE) { e = E_RSINGLE; s.frame = 2; }
+    else if (t == T_RINITIAL) { e = E_RINITIAL; s.frame = 2; }
+    else if (t >= T_RINTERNAL0 && t < T_RINTERNAL0 + 3) { e = E_RINTERNAL; s.frame = t - T_RINTERNAL0; }
+    else if (t >= T_RTERMINAL0 && t < T_RTERMINAL0 + 3) { e = E_RTERMINAL; s.frame = t - T_RTERMINAL0; }
+    if (e >= 0) {
+        s.kind = K_EXON; s.ek = e;
+        switch (e) {   /* ExonModel::ExonModel, exonmodel.cc:231-279 */
+        case E_SINGLE: case E_INITIAL: s.beginPartLen = 3 + m.tiw; s.innerPartOffset = 3; break;
+        case E_RSINGLE: case E_RTERMINAL: s.beginPartLen = s.innerPartOffset = 3; break;
+        default: s.beginPartLen = 0; s.innerPartOffset = s.fwd ? m.ass_end : m.dss_start;
+        }
+        if (e == E_SINGLE || e == E_TERMINAL) { s.baseOffset = 0; s.innerPartEndOffset = 3; }
+        else if (e == E_RSINGLE || e == E_RINITIAL) { s.baseOffset = -m.tiw; s.innerPartEndOffset = 3; }
+        else { s.baseOffset = s.innerPartEndOffset = s.fwd ? m.dss_start : m.ass_end; }
+        return;
+    }
+    int base = s.fwd ? T_LESSD0 : T_RLESSD0, off = t - base;
+    if (off < 0 || off >= 15) return;     /* kind stays -1: unsupported */
+    s.frame = off / 5;
+    static const int kinds[5] = {K_LESSD, K_LONGDSS, K_EQUALD, K_GEO, K_LONGASS};
+    s.kind = kinds[off % 5];
+}
+
+int HostModel::build(const void* blob, size_t nbytes) {
+    if (nbytes < sizeof(augb200_blob_header) || memcmp(blob, AUGB200_BLOB_MAGIC, 8)) { err = "bad magic"; return AUGB200_ERR_BAD_BLOB; }
+    const augb200_blob_header* h = (const augb200_blob_header*)blob;
+    if (h->version != AUGB200_BLOB_VERSION || sizeof *h + (size_t)h->n_entries * sizeof(augb200_blob_entry) > nbytes) { err = "bad header"; return AUGB200_ERR_BAD_BLOB; }
+    Reader r{{(const char*)blob, nbytes}, &err};
+    memset(&dm, 0, sizeof dm);
+    DevModel& m = dm;
+    m.S = r.i32("statecount"); m.C = r.i32("num_gc_classes");
+    m.k = r.i32("exon_k");
+    int ik = r.i32("intron_k"), gk = r.i32("igenic_k");
+    m.d = r.i32("intron_d");
+    m.dss_start = r.i32("dss_start"); m.dss_end = r.i32("dss_end"); m.ass_start = r.i32("ass_start"); m.ass_end = r.i32("ass_end");
+    m.ass_up = r.i32("ass_upwindow_size"); m.tiw = r.i32("trans_init_window");
+    m.init_len = r.i32("init_coding_len"); m.et_len = r.i32("et_coding_len");
+    m.max_exon_len = r.i32("max_exon_len"); m.min_exon_length = r.i32("min_exon_length");
+    m.dss_gc_allowed = r.i32("dss_gc_allowed"); m.GCwinsize = r.i32("GCwinsize"); m.weighing = r.i32("basecount_weighing_type");
+    m.tis_n = r.i32("tis_motif_n"); m.tis_k = r.i32("tis_motif_k"); m.assm_n = r.i32("ass_motif_n"); m.assm_k = r.i32("ass_motif_k");
+    int nbins = r.i32("transinit_nbins"), utr = r.i32("utr_option_on"), nc = r.i32("nc_option_on");
+    if (!r.ok) return AUGB200_ERR_BAD_BLOB;
+    if (m.S < 1 || m.S > MAXS || m.C < 1 || m.C > MAXC) { err = "state / class count out of range"; return AUGB200_ERR_UNSUPPORTED; }
+    if (ik != m.k || gk != m.k || m.k < 1 || m.k > 4) { err = "content model orders must be equal and <= 4"; return AUGB200_ERR_UNSUPPORTED; }
+    if (nbins > 0) { err = "TRANSINITBIN models are not supported yet"; return AUGB200_ERR_UNSUPPORTED; }
+    if (utr || nc) { err = "UTR / nc state models are not supported yet"; return AUGB200_ERR_UNSUPPORTED; }
+    m.dStateLen = m.d - 2 - m.dss_end - m.ass_start - 2 - m.ass_up;     /* intronmodel.cc:519-520 */
+    if (m.dStateLen < 1) { err = "d too small"; return AUGB200_ERR_UNSUPPORTED; }
+
+    /* ---- tables ---- */
+    tab.clear(); off.clear();
+    auto push = [&](const char* name, size_t expect) -> size_t {
+        size_t n; const double* d = r.darr(name, &n);
+        size_t o = tab.size();
+        if (!d) return o;
+        if (expect && n != expect) { r.ok = false; err = std::string("unexpected size of ") + name; return o; }
+        for (size_t i = 0; i < n; i++) tab.push_back(quantize(d[i]));
+        return o;
+    };
+    const size_t K1 = (size_t)1 << (2 * (m.k + 1));
+    size_t o_init = push("init_probs", m.S), o_term = push("term_probs", m.S), o_trans = push("trans", (size_t)m.C * m.S * m.S);
+    size_t o_xemi = push("exon_emi", m.C * 3 * K1), o_xinit = push("exon_initemi", m.C * 3 * K1), o_xet = push("exon_etemi", m.C * 3 * K1);
+    size_t o_xpls[5] = {0, 0, 0, 0, 0};
+    for (int l = 0; l <= m.k; l++) { char nm[32]; snprintf(nm, sizeof nm, "exon_pls%d", l); o_xpls[l] = push(nm, (size_t)m.C * 3 << (2 * (l + 1))); }
+    size_t o_iemi = push("intron_emi", m.C * K1), o_gemi = push("igenic_emi", m.C * K1);
+    size_t o_tis = push("tis_motif", (size_t)m.C * m.tis_n << (2 * (m.tis_k + 1))), o_assm = push("ass_motif", (size_t)m.C * m.assm_n << (2 * (m.assm_k + 1)));
+    size_t n0 = tab.size();
+    size_t o_lds = push("lendist_single", 0); m.n_ld_exon = (int)(tab.size() - n0);
+    size_t o_ldi = push("lendist_initial", m.n_ld_exon), o_ldn = push("lendist_internal", m.n_ld_exon), o_ldt = push("lendist_terminal", m.n_ld_exon);
+    n0 = tab.size();
+    size_t o_ldx = push("lendist_intron", 0); m.n_ld_intron = (int)(tab.size() - n0);
+    size_t npat_a = (size_t)1 << (2 * (m.ass_start + m.ass_end)), npat_d = (size_t)1 << (2 * (m.dss_start + m.dss_end));
+    size_t o_ap = push("ass_pattern", npat_a), o_apn = push("ass_pattern_nonag", npat_a), o_dp = push("dss_pattern", npat_d), o_dpn = push("dss_pattern_nongt", npat_d);
+    if (!r.ok) return AUGB200_ERR_BAD_BLOB;
+    if (m.n_ld_intron < m.d + 1) { err = "intron length distribution shorter than d"; return AUGB200_ERR_BAD_BLOB; }
+    /* igenic emission of the first k columns (igenicmodel.cc:342-354), incl. the normaliser quirk */
+    size_t o_gfirst = tab.size();
+    {
+        const size_t per = ((size_t)1 << (2 * (m.k + 2))) / 3 - 1;     /* sum_{j<=k} 4^(j+1) = (4^(k+2)-4)/3 */
+        tab.resize(o_gfirst + per * m.C, SC_NEG);
+        for (int j = 0; j <= m.k; j++) {
+            char nm[32]; snprintf(nm, sizeof nm, "igenic_pls%d", j);
+            size_t n; const double* P = r.darr(nm, &n);
+            size_t w = (size_t)1 << (2 * (j + 1));
+            if (!P || n != w * m.C) { err = "bad igenic_pls"; return AUGB200_ERR_BAD_BLOB; }
+            size_t joff = (w - 4) / 3;
+            for (int c = 0; c < m.C; c++)
+                for (size_t b = 0; b < w; b++) {
+                    const double* Pc = P + c * w;
+                    size_t q4 = b / 4;
+                    double den = 0; bool okd = true;
+                    for (int i = 0; i < 4; i++) { if (q4 + i >= w) { okd = false; break; } den += exp(Pc[q4 + i]); }
+                    tab[o_gfirst + c * per + joff + b] = okd ? quantize(Pc[b] - log(den)) : SC_NEG;
+                }
+        }
+    }
+    {
+        size_t n; const double* sp = r.darr("start_codon_prob", &n); size_t n2; const int32_t* st = r.iarr("is_stop_codon", &n2);
+        if (!r.ok || n != 64 || n2 != 64) { err = "bad codon tables"; return AUGB200_ERR_BAD_BLOB; }
+        for (int i = 0; i < 64; i++) { m.startp[i] = quantize(sp[i]); m.isstop[i] = (uint8_t)st[i]; }
+    }
+    m.ochre = quantize(r.f64("ochreprob")); m.amber = quantize(r.f64("amberprob")); m.opal = quantize(r.f64("opalprob"));
+    m.probN = quantize(r.f64("probNinCoding")); m.log025 = quantize(log(0.25)); m.log3 = quantize(log(3.0));
+    m.ass_invalid_pat = quantize(log(0.001) + (m.ass_start + m.ass_end) * log(0.25));
+    {
+        size_t n; const double* cen = r.darr("gc_centroids", &n); size_t n2; const double* wmx = r.darr("basecount_weight_matrix", &n2);
+        if (!r.ok || n % 4 || n / 4 > MAXC * 16 || n2 != 16) { err = "bad gc tables"; return AUGB200_ERR_BAD_BLOB; }
+        m.ncent = (int)(n / 4);
+        for (int i = 0; i < m.ncent; i++) for (int j = 0; j < 4; j++) m.centroids[i][j] = cen[4 * i + j];
+        for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) m.wm[i][j] = wmx[4 * i + j];
+    }
+    if (!r.ok) return AUGB200_ERR_BAD_BLOB;
+
+    /* ---- states ---- */
+    size_t n; const int32_t* stt = r.iarr("state_type", &n); size_t n2; const int32_t* reach = r.iarr("state_reachable", &n2);
+    if (!r.ok || (int)n != m.S || (int)n2 != m.S) { err = "bad state tables"; return AUGB200_ERR_BAD_BLOB; }
+    for (int c = 0; c < NCHAIN; c++) m.chain_state[c] = -1;
+    for (int d = 0; d < 2; d++) for (int f = 0; f < 3; f++) m.r_longdss[d][f] = m.r_lessd[d][f] = m.r_equald[d][f] = m.r_longass[d][f] = -1;
+    m.r_single = m.r_terminal = m.r_rsingle = m.r_rinitial = -1;
+    for (int f = 0; f < 3; f++) m.r_initial[f] = m.r_internal[f] = m.r_rinternal[f] = m.r_rterminal[f] = -1;
+    const sc_t* T = tab.data() + o_trans;
+    for (int s = 0; s < m.S; s++) {
+        StateDesc& sd = m.st[s]; sd.type = (int16_t)stt[s]; classify(sd, m);
+        if (sd.kind < 0) { err = "state type " + std::to_string(stt[s]) + " is not supported"; return AUGB200_ERR_UNSUPPORTED; }
+        if (!reach[s]) { err = "models with unreachable states are not supported"; return AUGB200_ERR_UNSUPPORTED; }
+        sd.nanc = 0;
+        for (int a = 0; a < m.S; a++) if (!isneg(T[(size_t)a * m.S + s])) {
+            if (sd.nanc >= MAXANC) { err = "too many ancestors"; return AUGB200_ERR_UNSUPPORTED; }
+            sd.anc[sd.nanc++] = (int8_t)a;
+        }
+        for (int c = 1; c < m.C; c++)
+            for (int a = 0; a < m.S; a++)
+                if (isneg(T[((size_t)c * m.S + a) * m.S + s]) != isneg(T[(size_t)a * m.S + s])) { err = "transition support differs between GC classes"; return AUGB200_ERR_UNSUPPORTED; }
+        int dir = sd.fwd ? 0 : 1, f = sd.frame;
+        int8_t* slot = nullptr;
+        switch (sd.kind) {
+        case K_IGENIC: sd.chain = 0; slot = &m.chain_state[0]; break;
+        case K_GEO: sd.chain = (int8_t)(1 + dir * 3 + f); slot = &m.chain_state[sd.chain]; break;
+        case K_LONGDSS: slot = &m.r_longdss[dir][f]; break;
+        case K_LESSD: slot = &m.r_lessd[dir][f]; break;
+        case K_EQUALD: slot = &m.r_equald[dir][f]; break;
+        case K_LONGASS: slot = &m.r_longass[dir][f]; break;
+        default:
+            switch (sd.ek) {
+            case E_SINGLE: slot = &m.r_single; break; case E_INITIAL: slot = &m.r_initial[f]; break;
+            case E_INTERNAL: slot = &m.r_internal[f]; break; case E_TERMINAL: slot = &m.r_terminal; break;
+            case E_RSINGLE: slot = &m.r_rsingle; break; case E_RINITIAL: slot = &m.r_rinitial; break;
+            case E_RINTERNAL: slot = &m.r_rinternal[f]; break; default: slot = &m.r_rterminal[f];
+            }
+        }
+        if (*slot >= 0) { err = "duplicate state role"; return AUGB200_ERR_UNSUPPORTED; }
+        *slot = (int8_t)s;
+    }
+    if (m.chain_state[0] < 0) { err = "model has no intergenic state"; return AUGB200_ERR_UNSUPPORTED; }
+    /* topology the kernels rely on (config/model/trans_shadow_*.pbl); anything else is rejected, not approximated */
+    auto kind_of = [&](int a) { return m.st[a].kind; };
+    for (int s = 0; s < m.S; s++) {
+        StateDesc& sd = m.st[s];
+        bool ok = true; bool selfloop = false;
+        for (int i = 0; i < sd.nanc; i++) {
+            int a = sd.anc[i]; const StateDesc& ad = m.st[a];
+            if (a == s) { selfloop = true; continue; }
+            switch (sd.kind) {
+            case K_IGENIC: ok &= ad.kind == K_EXON; break;
+            case K_GEO: ok &= ad.kind == K_EQUALD && ad.fwd == sd.fwd && ad.frame == sd.frame; break;
+            case K_EQUALD: case K_LESSD:
+                ok &= (sd.fwd ? ad.kind == K_LONGDSS : ad.kind == K_LONGASS) && ad.fwd == sd.fwd && ad.frame == sd.frame && sd.nanc == 1; break;
+            case K_LONGDSS: ok &= sd.fwd ? ad.kind == K_EXON : (ad.kind == K_LESSD || ad.kind == K_GEO); break;
+            case K_LONGASS: ok &= sd.fwd ? (ad.kind == K_LESSD || ad.kind == K_GEO) : ad.kind == K_EXON; break;
+            default:
+                switch (sd.ek) {
+                case E_INTERNAL: case E_TERMINAL: ok &= ad.kind == K_LONGASS && ad.fwd; break;
+                case E_RINTERNAL: case E_RINITIAL: ok &= ad.kind == K_LONGDSS && !ad.fwd; break;
+                default: ok &= ad.kind == K_IGENIC && sd.nanc == 1;
+                }
+            }
+        }
+        if (selfloop != (sd.chain >= 0)) ok = false;
+        if (!ok) { err = "unsupported transition topology at state " + std::to_string(s); return AUGB200_ERR_UNSUPPORTED; }
+        (void)kind_of;
+        /* one-base successors of a cell: which chain does this state enter? */
+        for (int c = 0; c < NCHAIN; c++) {
+            int cs = m.chain_state[c]; if (cs < 0 || cs == s) continue;
+            if (!isneg(T[(size_t)s * m.S + cs])) { if (sd.feeds >= 0) { err = "state feeds two chains"; return AUGB200_ERR_UNSUPPORTED; } sd.feeds = (int8_t)c; }
+        }
+    }
+    /* the 6 geometric chains share one prefix array: emission and self-loop must agree per class */
+    for (int c = 0; c < m.C; c++) {
+        sc_t ref = 0; bool have = false;
+        for (int ch = 1; ch < NCHAIN; ch++) {
+            int cs = m.chain_state[ch]; if (cs < 0) continue;
+            sc_t t = T[((size_t)c * m.S + cs) * m.S + cs];
+            if (!have) { ref = t; have = true; } else if (t != ref) { err = "geometric self-loops differ"; return AUGB200_ERR_UNSUPPORTED; }
+        }
+    }
+    /* ---- pointers ---- */
+    const sc_t* b = tab.data();
+    m.init = b + o_init; m.term = b + o_term; m.trans = b + o_trans;
+    m.xemi = b + o_xemi; m.xinit = b + o_xinit; m.xet = b + o_xet;
+    for (int l = 0; l < 5; l++) m.xpls[l] = l <= m.k ? b + o_xpls[l] : nullptr;
+    m.iemi = b + o_iemi; m.gemi = b + o_gemi; m.gfirst = b + o_gfirst; m.tis = b + o_tis; m.assm = b + o_assm;
+    m.ld_single = b + o_lds; m.ld_initial = b + o_ldi; m.ld_internal = b + o_ldn; m.ld_terminal = b + o_ldt; m.ld_intron = b + o_ldx;
+    m.ass_pat = b + o_ap; m.ass_pat_non = b + o_apn; m.dss_pat = b + o_dp; m.dss_pat_non = b + o_dpn;
+    return AUGB200_OK;
+}
+
+DevModel HostModel::rebased(const sc_t* base) const {
+    DevModel r = dm; const sc_t* b = tab.data();
+    auto rb = [&](const sc_t* p) { return p ? base + (p - b) : nullptr; };
+    r.init = rb(dm.init); r.term = rb(dm.term); r.trans = rb(dm.trans); r.xemi = rb(dm.xemi); r.xinit = rb(dm.xinit); r.xet = rb(dm.xet);
+    for (int l = 0; l < 5; l++) r.xpls[l] = rb(dm.xpls[l]);
+    r.iemi = rb(dm.iemi); r.gemi = rb(dm.gemi); r.gfirst = rb(dm.gfirst); r.tis = rb(dm.tis); r.assm = rb(dm.assm);
+    r.ld_single = rb(dm.ld_single); r.ld_initial = rb(dm.ld_initial); r.ld_internal = rb(dm.ld_internal); r.ld_terminal = rb(dm.ld_terminal); r.ld_intron = rb(dm.ld_intron);
+    r.ass_pat = rb(dm.ass_pat); r.ass_pat_non = rb(dm.ass_pat_non); r.dss_pat = rb(dm.dss_pat); r.dss_pat_non = rb(dm.dss_pat_non);
+    return r;
+}
+
+}  // namespace augb

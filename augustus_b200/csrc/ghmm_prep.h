@@ -1,0 +1,167 @@
+/*
+ * ghmm_prep.h — per-window preparation: everything that depends on the sequence but not on the DP.
+ *
+ * Replaces the parts of the reference that are re-evaluated inside its duration loops:
+ *   - Seq2Int k-mer lookups + content-model products (ExonModel::seqProb exonmodel.cc:1925-1973,
+ *     IntronModel::seqProb intronmodel.cc:1046-1108, SnippetProbs statemodel.cc:283-310,
+ *     IGenicModel::emiProbUnderModel igenicmodel.cc:299-357)  -> fixed-point prefix sums;
+ *   - OpenReadingFrame's nearest-stop tables (exonmodel.cc:101-156);
+ *   - ContentStairs::computeStairs (motif.cc:543-614) when the host does not pass the classes;
+ *   - the sequence-only early-return tests of the state models -> activity mask.
+ * This header holds the layout, the per-position formulas (host + device) and a sequential host
+ * builder used by the test emulator; the CUDA kernels in ghmm_kernels.cu evaluate the same formulas in
+ * parallel and scan with integer adds, so both produce identical arrays.
+ */
+#pragma once
+#include <stddef.h>
+#include "ghmm_defs.h"
+#include "ghmm_seq.h"
+
+namespace augb {
+
+/* byte layout of one window's workspace; every section is 16-byte aligned */
+struct WinLayout {
+    size_t code, gc, mask, parr, aig, ageo, nsf, nsr;        /* static (prep) */
+    size_t ev, evstart, cl[NCL], cp[NCHAIN], outs;           /* dynamic (sweep) */
+    size_t path_begin, path_end, path_type, path_trunc;      /* backtrace output */
+    size_t total;
+    int ev_cap, cl_cap, cp_cap, path_cap;
+};
+inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
+inline WinLayout make_layout(int L, int C) {
+    WinLayout w; size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = al16(o + bytes); return r; };
+    w.code = take(L); w.gc = take(L); w.mask = take((size_t)L * 2);
+    w.parr = take((size_t)C * PA_PER_CLASS * (L + 1) * sizeof(sc_t));
+    w.aig = take((size_t)L * sizeof(sc_t)); w.ageo = take((size_t)L * sizeof(sc_t));
+    w.nsf = take((size_t)(L + 3) * 4); w.nsr = take((size_t)(L + 3) * 4);
+    w.ev_cap = 4 * L + 256; w.cl_cap = L / 2 + 64; w.cp_cap = L / 2 + 64; w.path_cap = L / 2 + 64;
+    w.ev = take((size_t)w.ev_cap * sizeof(Event)); w.evstart = take((size_t)(L + 2) * 4);
+    for (int i = 0; i < NCL; i++) w.cl[i] = take((size_t)w.cl_cap * sizeof(Cand));
+    for (int i = 0; i < NCHAIN; i++) w.cp[i] = take((size_t)w.cp_cap * sizeof(ChainCP));
+    w.outs = take(64);
+    w.path_begin = take((size_t)w.path_cap * 4); w.path_end = take((size_t)w.path_cap * 4);
+    w.path_type = take(w.path_cap); w.path_trunc = take(w.path_cap);
+    w.total = al16(o);
+    return w;
+}
+/* result block at WinLayout::outs */
+struct WinOuts { int32_t n_ev, status, path_n, path_status; int32_t ncp[NCHAIN]; int32_t pad; sc_t score; };
+
+inline WinView make_view(char* base, const WinLayout& lay, int L, int classmask) {
+    WinView v; v.L = L; v.nclassmask = classmask; v.ev_cap = lay.ev_cap; v.cl_cap = lay.cl_cap; v.cp_cap = lay.cp_cap;
+    v.code = (const uint8_t*)(base + lay.code); v.gc = (const uint8_t*)(base + lay.gc); v.mask = (const uint16_t*)(base + lay.mask);
+    v.parr = (const sc_t*)(base + lay.parr); v.AIG = (const sc_t*)(base + lay.aig); v.AGEO = (const sc_t*)(base + lay.ageo);
+    v.nsf = (const int32_t*)(base + lay.nsf); v.nsr = (const int32_t*)(base + lay.nsr);
+    v.ev = (Event*)(base + lay.ev); v.evstart = (int32_t*)(base + lay.evstart);
+    for (int i = 0; i < NCL; i++) v.cl[i] = (Cand*)(base + lay.cl[i]);
+    for (int i = 0; i < NCHAIN; i++) v.cp[i] = (ChainCP*)(base + lay.cp[i]);
+    WinOuts* o = (WinOuts*)(base + lay.outs);
+    v.out_n_ev = &o->n_ev; v.out_status = &o->status; v.out_ncp = o->ncp;
+    return v;
+}
+
+AUGB_HD uint8_t base_code(char ch) {
+    switch (ch) {
+    case 'a': case 'A': return 0; case 'c': case 'C': return 1; case 'g': case 'G': return 2; case 't': case 'T': return 3;
+    default: return 4;
+    }
+}
+
+/* nearest GC-content class of a base-count vector: ContentDecomposition::getNearestBaseCountIndex
+ * (motif.cc:493-505) with BaseCount::doubleWeight (motif.cc:105-121) */
+AUGB_HD int nearest_class(const DevModel* m, const int cnt[4]) {
+    double sum = (double)cnt[0] + cnt[1] + cnt[2] + cnt[3];
+    double r[4] = {0.25, 0.25, 0.25, 0.25};
+    if (sum > 0) for (int i = 0; i < 4; i++) r[i] = cnt[i] / sum;
+    double best = -1; int ret = -1;
+    for (int i = 0; i < m->ncent; i++) {
+        double wgt;
+        if (m->weighing == 3) {
+            double z[4], tmp[4] = {0, 0, 0, 0}, t = 0;
+            for (int j = 0; j < 4; j++) z[j] = r[j] - m->centroids[i][j];
+            for (int j = 0; j < 4; j++) for (int a = 0; a < 4; a++) tmp[j] += z[a] * m->wm[a][j];
+            for (int a = 0; a < 4; a++) t += tmp[a] * z[a];
+            wgt = 1 + 9 * exp(-t);
+        } else if (m->weighing == 2) {
+            double g1 = r[2] + r[1], g2 = m->centroids[i][2] + m->centroids[i][1];
+            int c1 = g1 < .43 ? 0 : g1 < .51 ? 1 : g1 < .57 ? 2 : 3, c2 = g2 < .43 ? 0 : g2 < .51 ? 1 : g2 < .57 ? 2 : 3;
+            wgt = c1 == c2;
+        } else wgt = 1;
+        if (wgt > best) { best = wgt; ret = i; }
+    }
+    return ret;
+}
+
+/* ContentStairs::computeStairs (motif.cc:543-614), sequential host version */
+inline void gc_stairs_seq(const DevModel* m, const uint8_t* c, int n, uint8_t* idx) {
+    int win = m->GCwinsize; if (win > n || win < 1) win = n;
+    int cnt[4] = {0, 0, 0, 0};
+    for (int i = 0; i < win; i++) if (c[i] < 4) cnt[c[i]]++;
+    int xx = nearest_class(m, cnt);
+    for (int i = 0; i <= win / 2 && i < n; i++) idx[i] = (uint8_t)xx;
+    for (int i = win / 2 + 1; i <= n - (win + 1) / 2; i++) {
+        int a = c[i + (win + 1) / 2 - 1], r = c[i - win / 2 - 1];
+        if (a < 4) cnt[a]++;
+        if (r < 4) cnt[r]--;
+        idx[i] = (uint8_t)(xx = nearest_class(m, cnt));
+    }
+    for (int i = n - (win + 1) / 2 + 1; i < n; i++) if (i >= 0) idx[i] = (uint8_t)xx;
+    int x2 = -2, lastStep = 0; const int tot = 1000;
+    for (int i = 0; i < n; i++) if (idx[i] != x2) {
+        if (i - lastStep < tot && lastStep > 0 && idx[lastStep - 1] == idx[i]) for (int j = lastStep; j < i; j++) idx[j] = idx[i];
+        lastStep = i; x2 = idx[i];
+    }
+}
+
+/* per-position addends of the scanned arrays */
+AUGB_HD sc_t aig_term(const DevModel* m, const Seq& s, const uint8_t* gc, int j) {      /* j >= 1 */
+    int c = gc[j], ig = m->chain_state[0];
+    return m->trans[((size_t)c * m->S + ig) * m->S + ig] + igenic_emi(m, s, c, j);
+}
+AUGB_HD sc_t ageo_term(const DevModel* m, const Seq& s, const uint8_t* gc, int j) {     /* j >= 1 */
+    int c = gc[j]; int g = -1;
+    for (int ch = 1; ch < NCHAIN; ch++) if (m->chain_state[ch] >= 0) { g = m->chain_state[ch]; break; }
+    if (g < 0) return 0;
+    return m->trans[((size_t)c * m->S + g) * m->S + g] + intron_emi1(m, s, c, j);
+}
+AUGB_HD sc_t parr_term(const DevModel* m, const Seq& s, int c, int which, int p) {
+    switch (which) {
+    case PA_PI: return intron_emi1(m, s, c, p);
+    case PA_PIR: return intron_emi1r(m, s, c, p);
+    case PA_PX: case PA_PX + 1: case PA_PX + 2: return p >= m->k ? exon_emi1(m, s, m->xemi, c, 1, mod3(which - PA_PX + p), p) : 0;
+    default: return exon_emi1(m, s, m->xemi, c, 0, mod3(which - PA_PXR - p), p);
+    }
+}
+
+/* sequential host builder (test emulator) */
+inline void prep_window_seq(const DevModel* m, const char* dna, int L, const int32_t* gc_in, char* base, const WinLayout& lay, int* classmask) {
+    uint8_t* code = (uint8_t*)(base + lay.code); uint8_t* gc = (uint8_t*)(base + lay.gc); uint16_t* mask = (uint16_t*)(base + lay.mask);
+    for (int i = 0; i < L; i++) code[i] = base_code(dna[i]);
+    if (gc_in) for (int i = 0; i < L; i++) gc[i] = (uint8_t)gc_in[i]; else gc_stairs_seq(m, code, L, gc);
+    int cm = 0; for (int i = 0; i < L; i++) cm |= 1 << gc[i];
+    *classmask = cm;
+    Seq s; s.c = code; s.L = L;
+    for (int j = 0; j < L; j++) mask[j] = (uint16_t)column_mask(m, s, j);
+    sc_t* parr = (sc_t*)(base + lay.parr);
+    for (int c = 0; c < m->C; c++) {
+        if (!(cm >> c & 1)) continue;
+        for (int which = 0; which < PA_PER_CLASS; which++) {
+            sc_t* P = parr + ((size_t)c * PA_PER_CLASS + which) * (size_t)(L + 1);
+            P[0] = 0;
+            for (int p = 0; p < L; p++) P[p + 1] = P[p] + parr_term(m, s, c, which, p);
+        }
+    }
+    sc_t* aig = (sc_t*)(base + lay.aig); sc_t* ageo = (sc_t*)(base + lay.ageo);
+    aig[0] = ageo[0] = 0;
+    for (int j = 1; j < L; j++) { aig[j] = aig[j - 1] + aig_term(m, s, gc, j); ageo[j] = ageo[j - 1] + ageo_term(m, s, gc, j); }
+    int32_t* nsf = (int32_t*)(base + lay.nsf); int32_t* nsr = (int32_t*)(base + lay.nsr);
+    for (int i = 0; i < L + 3; i++) nsf[i] = nsr[i] = 0;
+    for (int r = 0; r < 3; r++) {
+        int sp = -1; for (int i = r; i <= L - 3; i += 3) { if (isStop(m, s, i)) sp = i; nsf[i] = sp; }
+        sp = -1; for (int i = r; i <= L - 3; i += 3) { if (isRCStop(m, s, i)) sp = i; nsr[i] = sp; }
+    }
+    if (L > 5) { nsf[L - 2] = nsf[L - 5]; nsf[L - 1] = nsf[L - 4]; nsr[L - 2] = nsr[L - 5]; nsr[L - 1] = nsr[L - 4]; }
+}
+
+}  // namespace augb

@@ -1,0 +1,57 @@
+/*
+ * ghmm_warp.h — warp-cooperative primitives used by the sweep.
+ *
+ * On the device one warp decodes one window: lanes split candidate (predecessor, duration) pairs and
+ * motif positions, and combine with shuffle reductions.  The same source compiles for the host with a
+ * single "lane" (tests/host emulator only — never part of the product library), so the control flow of
+ * the kernel can be checked against the oracle in a container without a GPU.
+ */
+#pragma once
+#include "ghmm_defs.h"
+
+namespace augb {
+
+#if defined(__CUDA_ARCH__)
+#define AUGB_NLANES 32
+AUGB_D int lane_id() { return threadIdx.x & 31; }
+AUGB_D void wsync() { __syncwarp(); }
+AUGB_D sc_t wmax(sc_t v) {
+    for (int o = 16; o; o >>= 1) { sc_t t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+    return v;
+}
+AUGB_D sc_t wsum(sc_t v) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+AUGB_D int wmaxi(int v) {
+    for (int o = 16; o; o >>= 1) { int t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+    return v;
+}
+AUGB_D unsigned wballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+AUGB_D int wbcast(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+AUGB_D sc_t wbcast64(sc_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+AUGB_D int wffs(unsigned b) { return __ffs(b) - 1; }
+#else
+#define AUGB_NLANES 1
+inline int lane_id() { return 0; }
+inline void wsync() {}
+inline sc_t wmax(sc_t v) { return v; }
+inline sc_t wsum(sc_t v) { return v; }
+inline int wmaxi(int v) { return v; }
+inline unsigned wballot(bool p) { return p ? 1u : 0u; }
+inline int wbcast(int v, int) { return v; }
+inline sc_t wbcast64(sc_t v, int) { return v; }
+inline int wffs(unsigned b) { return b ? __builtin_ctz(b) : -1; }
+#endif
+
+/* arg-max over lanes of (score, key): the highest score wins, ties go to the highest key.  Returns the
+ * winning lane or -1 if every score is SC_NEG.  Keys are chosen by the callers so that "highest key" is
+ * the option the reference meets first in its loop order (strict '>' keeps the first maximum). */
+AUGB_D int wargbest(sc_t score, int key) {
+    sc_t m = wmax(score);
+    if (isneg(m)) return -1;
+    int k = wmaxi(score == m ? key : -0x7fffffff);
+    return wffs(wballot(score == m && key == k));
+}
+
+}  // namespace augb

@@ -1,0 +1,118 @@
+/*
+ * augb200.h — C ABI of the B200-native GHMM decoder (libaugb200.so).
+ *
+ * This is the drop-in boundary for AUGUSTUS' DP engine.  Each entry point names the reference
+ * interface (AUGUSTUS 3.5.0, paths relative to the reference tree) it replaces; INTEGRATION.md shows
+ * the C++ shim a maintainer adds to NAMGene to call it.
+ *
+ *   augb200_model_create   <- NAMGene::NAMGene() + StateModel::readAllParameters()
+ *                             (src/namgene.cc:25-142, src/augustus.cc:175-176): the host exports its
+ *                             tables once as an AUGB2PAR blob (include/augb200_params.h).
+ *   augb200_decode_batch   <- NAMGene::viterbiAndForward (src/namgene.cc:168-365) followed by
+ *                             NAMGene::getViterbiPath (src/namgene.cc:432-510), for many windows at
+ *                             once; the StateModel::viterbiForwardAndSampling overrides
+ *                             (exonmodel.cc:899, intronmodel.cc:509, igenicmodel.cc:231) run inside
+ *                             as CUDA kernels.
+ *   augb200_decode         <- the same for one window (what findGenes calls, namgene.cc:776,790).
+ *   augb200_strerror       <- the ProjectError texts thrown at namgene.cc:455-457 / :493-496.
+ *
+ * There is no CPU fallback: every entry point that needs the device fails with
+ * AUGB200_ERR_CUDA / AUGB200_ERR_NO_DEVICE when no sm_100 GPU is usable.
+ *
+ * Plain C types only; all pointers are HOST pointers owned by the caller unless stated otherwise.
+ */
+#ifndef AUGB200_H
+#define AUGB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AUGB200_VERSION 1
+
+/* error codes (0 = success) */
+enum {
+    AUGB200_OK = 0,
+    AUGB200_ERR_BAD_BLOB = 1,        /* malformed / incomplete parameter blob                         */
+    AUGB200_ERR_UNSUPPORTED = 2,     /* model uses states / options this library does not decode      */
+    AUGB200_ERR_NO_DEVICE = 3,       /* no CUDA device                                                */
+    AUGB200_ERR_CUDA = 4,            /* CUDA runtime error (see augb200_last_cuda_error)              */
+    AUGB200_ERR_BAD_ARG = 5,
+    AUGB200_ERR_NO_PATH = 6,         /* "No feasible path found in HMM" (namgene.cc:455-457)          */
+    AUGB200_ERR_STUCK = 7,           /* "Viterbi got stuck" (namgene.cc:493-496)                      */
+    AUGB200_ERR_CAPACITY = 8,        /* internal event capacity exceeded for a window                 */
+    AUGB200_ERR_TOO_LONG = 9         /* window longer than AUGB200_MAX_WINDOW                         */
+};
+
+/* longest window the Q40 fixed-point score range covers */
+#define AUGB200_MAX_WINDOW 500000
+
+/* truncation flags of a path state, as State::truncated (include/types.hh:69-70) */
+#define AUGB200_TRUNC_LEFT 1
+#define AUGB200_TRUNC_RIGHT 2
+
+typedef struct augb200_model augb200_model;
+
+/* One sequence window = one call of NAMGene::viterbiAndForward. */
+typedef struct augb200_window {
+    const char*    dna;       /* ASCII, any case; anything but acgt/ACGT is an unknown base       */
+    int32_t        length;    /* number of bases, 2 .. AUGB200_MAX_WINDOW                          */
+    const int32_t* gc_class;  /* optional: ContentStairs::idx[] (motif.cc:543-614), one class per  */
+                              /* base; NULL = computed on the device with the same rule            */
+} augb200_window;
+
+/*
+ * A decoded state path: StatePath (include/gene.hh) in left-to-right order with runs of identical
+ * non-exon states already merged as StatePath::condenseStatePath does (gene.cc:977-1000).
+ * type[] holds StateType values (include/types.hh:492-512); begin/end are 0-based inclusive.
+ * The arrays are owned by the library and stay valid until the next decode call on the same
+ * model or augb200_model_destroy.
+ */
+typedef struct augb200_path {
+    int32_t        n;         /* number of states                                                  */
+    int32_t        status;    /* AUGB200_OK or AUGB200_ERR_NO_PATH / _STUCK / _CAPACITY            */
+    const int32_t* begin;
+    const int32_t* end;
+    const uint8_t* type;
+    const uint8_t* truncated;
+    double         log_prob;  /* ln of pathemiProb (Viterbi score incl. termProbs)                 */
+} augb200_path;
+
+/* Create a model from an AUGB2PAR blob (copied; the caller may free it afterwards). `device` is the
+ * CUDA device ordinal. */
+int augb200_model_create(const void* blob, size_t nbytes, int device, augb200_model** out);
+void augb200_model_destroy(augb200_model* m);
+
+/* number of GHMM states / GC classes of the model */
+int augb200_model_statecount(const augb200_model* m);
+int augb200_model_num_gc_classes(const augb200_model* m);
+
+/* Decode n windows.  out[i] describes window i.  Returns AUGB200_OK if the batch ran; per-window
+ * DP errors are reported in out[i].status. */
+int augb200_decode_batch(augb200_model* m, int32_t n, const augb200_window* windows, augb200_path* out);
+
+/* Decode one window. */
+int augb200_decode(augb200_model* m, const augb200_window* window, augb200_path* out);
+
+/* Device-resident variant used for kernel-only timing: stage the windows once, run the kernels any
+ * number of times (no host<->device traffic in between), fetch the paths at the end. */
+int augb200_stage_batch(augb200_model* m, int32_t n, const augb200_window* windows);
+int augb200_run_staged(augb200_model* m);                 /* asynchronous on the model's stream    */
+int augb200_fetch_staged(augb200_model* m, augb200_path* out);
+/* the CUDA stream (cudaStream_t) the kernels are launched on, for event timing by the caller */
+void* augb200_model_stream(augb200_model* m);
+/* number of kernel launches issued by the last run / decode call */
+int64_t augb200_last_launch_count(const augb200_model* m);
+/* device milliseconds spent in the sweep kernel during the last run (CUDA events on the model's stream) */
+double augb200_last_sweep_ms(const augb200_model* m);
+
+const char* augb200_strerror(int code);
+const char* augb200_last_cuda_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,72 @@
+/*
+ * hostemu.cc — TEST-ONLY build of the sweep / backtrace source for the host (one "lane").
+ *
+ * The product library (libaugb200.so) runs ghmm_sweep.h on the GPU, one warp per window.  This file
+ * compiles the very same headers with g++ so that the kernel's control flow, data structures and
+ * fixed-point arithmetic can be checked against the oracle in a container that has no GPU.  It is
+ * not linked into, loaded by, or reachable from the product; symbols carry the hostemu_ prefix.
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../augustus_b200/csrc/ghmm_backtrace.h"
+#include "../../augustus_b200/csrc/ghmm_model.h"
+#include "../../augustus_b200/csrc/ghmm_prep.h"
+#include "../../augustus_b200/csrc/ghmm_sweep.h"
+
+using namespace augb;
+
+struct EmuModel { HostModel hm; };
+
+extern "C" {
+
+void* hostemu_model_create(const void* blob, size_t nbytes, char* errbuf, int errcap) {
+    EmuModel* e = new EmuModel();
+    int rc = e->hm.build(blob, nbytes);
+    if (rc) { snprintf(errbuf, errcap, "%d: %s", rc, e->hm.err.c_str()); delete e; return nullptr; }
+    return e;
+}
+void hostemu_model_destroy(void* p) { delete (EmuModel*)p; }
+
+/* decode one window; optional dump of all events (col, state, V) and chain values V[j][chain] */
+int hostemu_decode(void* mp, const char* dna, int L, const int32_t* gc_in,
+                   int cap, int32_t* pbegin, int32_t* pend, uint8_t* ptype, uint8_t* ptrunc, double* logp, int32_t* status,
+                   int evcap, int32_t* ev_col, int32_t* ev_state, int64_t* ev_V, int32_t* n_ev_out,
+                   int64_t* chainV /* [L][NCHAIN] or NULL */, uint8_t* gc_out /* [L] or NULL */) {
+    EmuModel* e = (EmuModel*)mp; const DevModel* m = &e->hm.dm;
+    WinLayout lay = make_layout(L, m->C);
+    std::vector<char> buf(lay.total + 64);
+    char* base = buf.data();
+    int cm = 0;
+    prep_window_seq(m, dna, L, gc_in, base, lay, &cm);
+    WinView v = make_view(base, lay, L, cm);
+    WarpState ws;
+    Sweep sw; sw.m = m; sw.w = v; sw.ws = &ws;
+    sw.run();
+    WinOuts* outs = (WinOuts*)(base + lay.outs);
+    PathOut po; po.cap = lay.path_cap;
+    po.begin = (int32_t*)(base + lay.path_begin); po.end = (int32_t*)(base + lay.path_end);
+    po.type = (uint8_t*)(base + lay.path_type); po.trunc = (uint8_t*)(base + lay.path_trunc);
+    po.n = &outs->path_n; po.status = &outs->path_status; po.score = &outs->score;
+    backtrace_window(m, v, po);
+    *status = outs->path_status;
+    int n = outs->path_n;
+    if (n > cap) { *status = AUGB200_ERR_CAPACITY; n = 0; }
+    for (int i = 0; i < n; i++) { pbegin[i] = po.begin[i]; pend[i] = po.end[i]; ptype[i] = po.type[i]; ptrunc[i] = po.trunc[i]; }
+    *logp = ldexp((double)outs->score, -FRAC_BITS);
+    if (n_ev_out) {
+        int ne = outs->n_ev; *n_ev_out = ne;
+        for (int i = 0; i < ne && i < evcap; i++) { ev_col[i] = v.ev[i].col; ev_state[i] = v.ev[i].state; ev_V[i] = v.ev[i].V; }
+    }
+    if (chainV) {
+        for (int j = 0; j < L; j++)
+            for (int ch = 0; ch < NCHAIN; ch++) chainV[(size_t)j * NCHAIN + ch] = m->chain_state[ch] >= 0 ? sw.chain_value(ch, j) : SC_NEG;
+    }
+    if (gc_out) memcpy(gc_out, v.gc, L);
+    return n;
+}
+int hostemu_chain_state(void* mp, int ch) { return ((EmuModel*)mp)->hm.dm.chain_state[ch]; }
+
+}  // extern "C"
