@@ -1,0 +1,313 @@
+/*
+ * augb200.cu — C ABI (include/augb200.h) on top of the CUDA kernels.  No CPU fallback: every decode
+ * entry point needs a CUDA device and reports AUGB200_ERR_NO_DEVICE / AUGB200_ERR_CUDA otherwise.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/augb200.h"
+#include "ghmm_kernels.cuh"
+#include "ghmm_model.h"
+
+using namespace augb;
+
+static thread_local std::string g_cuda_err;
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \
+    g_cuda_err = std::string(#call) + ": " + cudaGetErrorString(e__); return AUGB200_ERR_CUDA; } } while (0)
+
+namespace {
+template <typename T> struct DevBuf {
+    T* p = nullptr; size_t cap = 0;
+    int reserve(size_t n) {
+        if (n <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e != cudaSuccess) { g_cuda_err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return AUGB200_ERR_CUDA; }
+        cap = n; return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+template <typename T> struct PinBuf {
+    T* p = nullptr; size_t cap = 0;
+    int reserve(size_t n) {
+        if (n <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(&p, n * sizeof(T));
+        if (e != cudaSuccess) { g_cuda_err = std::string("cudaMallocHost: ") + cudaGetErrorString(e); return AUGB200_ERR_CUDA; }
+        cap = n; return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+}  // namespace
+
+struct augb200_model {
+    HostModel hm;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevBuf<sc_t> d_tab; DevBuf<DevModel> d_model;
+    /* batch state */
+    DevBuf<char> d_arena; DevBuf<char> d_dna; DevBuf<uint8_t> d_gc; DevBuf<WinDev> d_wins; DevBuf<int> d_counters;
+    DevBuf<PackHdr> d_hdr; DevBuf<int32_t> d_obegin, d_oend; DevBuf<uint8_t> d_otype, d_otrunc;
+    PinBuf<char> h_dna; PinBuf<uint8_t> h_gc; PinBuf<WinDev> h_wins; PinBuf<PackHdr> h_hdr; PinBuf<int> h_counters;
+    PinBuf<int32_t> h_obegin, h_oend; PinBuf<uint8_t> h_otype, h_otrunc;
+    size_t arena_budget = 0;
+    int staged_n = 0; int ocap = 0;
+    /* results handed to the caller */
+    std::vector<int32_t> r_begin, r_end; std::vector<uint8_t> r_type, r_trunc;
+    int64_t launches = 0; double sweep_ms = 0;
+};
+
+static int upload_windows(augb200_model* M, const augb200_window* w, const int* idx, int count, bool generous) {
+    /* stage DNA (+ optional classes) of windows idx[0..count) and build their descriptors */
+    size_t dna_bytes = 0, gc_bytes = 0, arena = 0;
+    for (int i = 0; i < count; i++) {
+        const augb200_window& x = w[idx[i]];
+        dna_bytes += (size_t)((x.length + 15) & ~15);
+        if (x.gc_class) gc_bytes += (size_t)((x.length + 15) & ~15);
+        arena += make_layout(x.length, M->hm.dm.C, generous).total;
+    }
+    int rc;
+    if ((rc = M->h_dna.reserve(dna_bytes + 16))) return rc;
+    if ((rc = M->d_dna.reserve(dna_bytes + 16))) return rc;
+    if (gc_bytes) { if ((rc = M->h_gc.reserve(gc_bytes + 16))) return rc; if ((rc = M->d_gc.reserve(gc_bytes + 16))) return rc; }
+    if ((rc = M->d_arena.reserve(arena))) return rc;
+    if ((rc = M->h_wins.reserve(count))) return rc;
+    if ((rc = M->d_wins.reserve(count))) return rc;
+    size_t od = 0, og = 0, oa = 0; long total_path_cap = 0;
+    for (int i = 0; i < count; i++) {
+        const augb200_window& x = w[idx[i]];
+        WinDev& d = M->h_wins.p[i];
+        d.L = x.length; d.lay = make_layout(x.length, M->hm.dm.C, generous);
+        d.base = M->d_arena.p + oa; oa += d.lay.total;
+        memcpy(M->h_dna.p + od, x.dna, x.length);
+        d.dna = M->d_dna.p + od; od += (size_t)((x.length + 15) & ~15);
+        if (x.gc_class) {
+            uint8_t* g = M->h_gc.p + og;
+            for (int j = 0; j < x.length; j++) {
+                int c = x.gc_class[j];
+                if (c < 0 || c >= M->hm.dm.C) return AUGB200_ERR_BAD_ARG;
+                g[j] = (uint8_t)c;
+            }
+            d.gc_in = M->d_gc.p + og; og += (size_t)((x.length + 15) & ~15);
+        } else d.gc_in = nullptr;
+        total_path_cap += generous ? x.length + 64 : 512 + x.length / 64;
+    }
+    CK(cudaMemcpyAsync(M->d_dna.p, M->h_dna.p, od, cudaMemcpyHostToDevice, M->stream));
+    if (og) CK(cudaMemcpyAsync(M->d_gc.p, M->h_gc.p, og, cudaMemcpyHostToDevice, M->stream));
+    CK(cudaMemcpyAsync(M->d_wins.p, M->h_wins.p, (size_t)count * sizeof(WinDev), cudaMemcpyHostToDevice, M->stream));
+    M->ocap = (int)std::min<long>(total_path_cap, 0x7fffffff);
+    if ((rc = M->d_obegin.reserve(M->ocap)) || (rc = M->d_oend.reserve(M->ocap)) || (rc = M->d_otype.reserve(M->ocap)) || (rc = M->d_otrunc.reserve(M->ocap))) return rc;
+    if ((rc = M->h_obegin.reserve(M->ocap)) || (rc = M->h_oend.reserve(M->ocap)) || (rc = M->h_otype.reserve(M->ocap)) || (rc = M->h_otrunc.reserve(M->ocap))) return rc;
+    if ((rc = M->d_hdr.reserve(count)) || (rc = M->h_hdr.reserve(count))) return rc;
+    if ((rc = M->d_counters.reserve(4)) || (rc = M->h_counters.reserve(4))) return rc;
+    return 0;
+}
+
+static int run_kernels(augb200_model* M, int count) {
+    CK(cudaMemsetAsync(M->d_counters.p, 0, 4 * sizeof(int), M->stream));
+    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, M->device);
+    int gprep = std::min(count, sms * 8);
+    k_prep<<<gprep, PREP_BS, 0, M->stream>>>(M->d_model.p, M->d_wins.p, count);
+    CK(cudaEventRecord(M->ev0, M->stream));
+    int gsweep = std::min((count + SWEEP_WARPS - 1) / SWEEP_WARPS, sms * 16);
+    k_sweep<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(M->d_model.p, M->d_wins.p, count, M->d_counters.p);
+    CK(cudaEventRecord(M->ev1, M->stream));
+    k_backtrace<<<(count + 63) / 64, 64, 0, M->stream>>>(M->d_model.p, M->d_wins.p, count);
+    k_pack<<<count, 64, 0, M->stream>>>(M->d_wins.p, count, M->d_hdr.p, M->d_counters.p + 1, M->d_obegin.p, M->d_oend.p, M->d_otype.p, M->d_otrunc.p, M->ocap);
+    CK(cudaGetLastError());
+    M->launches += 4;
+    return 0;
+}
+
+static int fetch_results(augb200_model* M, int count, augb200_path* out, const int* idx) {
+    CK(cudaMemcpyAsync(M->h_hdr.p, M->d_hdr.p, (size_t)count * sizeof(PackHdr), cudaMemcpyDeviceToHost, M->stream));
+    CK(cudaMemcpyAsync(M->h_counters.p, M->d_counters.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, M->stream));
+    CK(cudaStreamSynchronize(M->stream));
+    int total = std::min(M->h_counters.p[1], M->ocap);
+    if (total > 0) {
+        CK(cudaMemcpyAsync(M->h_obegin.p, M->d_obegin.p, (size_t)total * 4, cudaMemcpyDeviceToHost, M->stream));
+        CK(cudaMemcpyAsync(M->h_oend.p, M->d_oend.p, (size_t)total * 4, cudaMemcpyDeviceToHost, M->stream));
+        CK(cudaMemcpyAsync(M->h_otype.p, M->d_otype.p, (size_t)total, cudaMemcpyDeviceToHost, M->stream));
+        CK(cudaMemcpyAsync(M->h_otrunc.p, M->d_otrunc.p, (size_t)total, cudaMemcpyDeviceToHost, M->stream));
+        CK(cudaStreamSynchronize(M->stream));
+    }
+    float ms = 0; if (cudaEventElapsedTime(&ms, M->ev0, M->ev1) == cudaSuccess) M->sweep_ms += ms;
+    /* append to the result store; pointers are fixed up by the caller once all sub-batches are in */
+    size_t base = M->r_begin.size();
+    M->r_begin.insert(M->r_begin.end(), M->h_obegin.p, M->h_obegin.p + total);
+    M->r_end.insert(M->r_end.end(), M->h_oend.p, M->h_oend.p + total);
+    M->r_type.insert(M->r_type.end(), M->h_otype.p, M->h_otype.p + total);
+    M->r_trunc.insert(M->r_trunc.end(), M->h_otrunc.p, M->h_otrunc.p + total);
+    for (int i = 0; i < count; i++) {
+        const PackHdr& h = M->h_hdr.p[i]; augb200_path& p = out[idx[i]];
+        p.n = h.n; p.status = h.status; p.log_prob = ldexp((double)h.score, -FRAC_BITS);
+        /* store offsets in the pointer fields for now */
+        p.begin = (const int32_t*)(uintptr_t)(base + h.offset);
+    }
+    return 0;
+}
+
+static void fix_pointers(augb200_model* M, int n, augb200_path* out) {
+    for (int i = 0; i < n; i++) {
+        size_t off = (size_t)(uintptr_t)out[i].begin;
+        out[i].begin = M->r_begin.data() + off; out[i].end = M->r_end.data() + off;
+        out[i].type = M->r_type.data() + off; out[i].truncated = M->r_trunc.data() + off;
+    }
+}
+
+extern "C" {
+
+int augb200_model_create(const void* blob, size_t nbytes, int device, augb200_model** out) {
+    if (!blob || !out) return AUGB200_ERR_BAD_ARG;
+    *out = nullptr;
+    augb200_model* M = new augb200_model();
+    int rc = M->hm.build(blob, nbytes);
+    if (rc) { g_cuda_err = M->hm.err; delete M; return rc; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_cuda_err = "no CUDA device"; delete M; return AUGB200_ERR_NO_DEVICE; }
+    if (device < 0 || device >= ndev) { delete M; return AUGB200_ERR_BAD_ARG; }
+    M->device = device;
+    auto fail = [&](int code) { augb200_model_destroy(M); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) return fail(AUGB200_ERR_CUDA);
+    if (cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(AUGB200_ERR_CUDA);
+    if (cudaEventCreate(&M->ev0) != cudaSuccess || cudaEventCreate(&M->ev1) != cudaSuccess) return fail(AUGB200_ERR_CUDA);
+    if (M->d_tab.reserve(M->hm.tab.size())) return fail(AUGB200_ERR_CUDA);
+    if (cudaMemcpy(M->d_tab.p, M->hm.tab.data(), M->hm.tab.size() * sizeof(sc_t), cudaMemcpyHostToDevice) != cudaSuccess) return fail(AUGB200_ERR_CUDA);
+    DevModel dm = M->hm.rebased(M->d_tab.p);
+    if (M->d_model.reserve(1)) return fail(AUGB200_ERR_CUDA);
+    if (cudaMemcpy(M->d_model.p, &dm, sizeof dm, cudaMemcpyHostToDevice) != cudaSuccess) return fail(AUGB200_ERR_CUDA);
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return fail(AUGB200_ERR_CUDA);
+    M->arena_budget = (size_t)(fr * 0.80);
+    if (const char* e = getenv("AUGB200_ARENA_MB")) { size_t mb = strtoull(e, nullptr, 10); if (mb) M->arena_budget = std::min(M->arena_budget, mb << 20); }
+    *out = M;
+    return AUGB200_OK;
+}
+
+void augb200_model_destroy(augb200_model* M) {
+    if (!M) return;
+    cudaSetDevice(M->device);
+    M->d_tab.release(); M->d_model.release(); M->d_arena.release(); M->d_dna.release(); M->d_gc.release(); M->d_wins.release(); M->d_counters.release();
+    M->d_hdr.release(); M->d_obegin.release(); M->d_oend.release(); M->d_otype.release(); M->d_otrunc.release();
+    M->h_dna.release(); M->h_gc.release(); M->h_wins.release(); M->h_hdr.release(); M->h_counters.release();
+    M->h_obegin.release(); M->h_oend.release(); M->h_otype.release(); M->h_otrunc.release();
+    if (M->ev0) cudaEventDestroy(M->ev0);
+    if (M->ev1) cudaEventDestroy(M->ev1);
+    if (M->stream) cudaStreamDestroy(M->stream);
+    delete M;
+}
+
+int augb200_model_statecount(const augb200_model* M) { return M ? M->hm.dm.S : 0; }
+int augb200_model_num_gc_classes(const augb200_model* M) { return M ? M->hm.dm.C : 0; }
+
+static int check_windows(int32_t n, const augb200_window* w) {
+    if (n < 0 || (n && !w)) return AUGB200_ERR_BAD_ARG;
+    for (int i = 0; i < n; i++) {
+        if (!w[i].dna || w[i].length < 2) return AUGB200_ERR_BAD_ARG;
+        if (w[i].length > AUGB200_MAX_WINDOW) return AUGB200_ERR_TOO_LONG;
+    }
+    return 0;
+}
+
+int augb200_decode_batch(augb200_model* M, int32_t n, const augb200_window* w, augb200_path* out) {
+    if (!M || !out) return AUGB200_ERR_BAD_ARG;
+    int rc = check_windows(n, w); if (rc) return rc;
+    CK(cudaSetDevice(M->device));
+    M->r_begin.clear(); M->r_end.clear(); M->r_type.clear(); M->r_trunc.clear();
+    M->launches = 0; M->sweep_ms = 0;
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    for (int pass = 0; pass < 2 && !order.empty(); pass++) {
+        const bool generous = pass == 1;      /* second pass: windows whose default-sized structures overflowed */
+        size_t first = 0;
+        while (first < order.size()) {
+            size_t bytes = 0; int count = 0;   /* greedy sub-batch under the arena budget */
+            while (first + count < order.size()) {
+                size_t t = make_layout(w[order[first + count]].length, M->hm.dm.C, generous).total;
+                if (count && bytes + t > M->arena_budget) break;
+                bytes += t; count++;
+            }
+            if ((rc = upload_windows(M, w, order.data() + first, count, generous))) return rc;
+            if ((rc = run_kernels(M, count))) return rc;
+            if ((rc = fetch_results(M, count, out, order.data() + first))) return rc;
+            first += count;
+        }
+        std::vector<int> again;
+        if (!generous) for (int i : order) if (out[i].status == AUGB200_ERR_CAPACITY) again.push_back(i);
+        order.swap(again);
+    }
+    fix_pointers(M, n, out);
+    return AUGB200_OK;
+}
+
+int augb200_decode(augb200_model* M, const augb200_window* w, augb200_path* out) { return augb200_decode_batch(M, 1, w, out); }
+
+int augb200_stage_batch(augb200_model* M, int32_t n, const augb200_window* w) {
+    if (!M) return AUGB200_ERR_BAD_ARG;
+    int rc = check_windows(n, w); if (rc) return rc;
+    CK(cudaSetDevice(M->device));
+    size_t bytes = 0; for (int i = 0; i < n; i++) bytes += make_layout(w[i].length, M->hm.dm.C).total;
+    if (bytes > M->arena_budget) return AUGB200_ERR_CAPACITY;
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    if ((rc = upload_windows(M, w, order.data(), n, false))) return rc;
+    CK(cudaStreamSynchronize(M->stream));
+    M->staged_n = n;
+    return AUGB200_OK;
+}
+int augb200_run_staged(augb200_model* M) {
+    if (!M || M->staged_n <= 0) return AUGB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(M->device));
+    M->launches = 0;
+    return run_kernels(M, M->staged_n);
+}
+int augb200_fetch_staged(augb200_model* M, augb200_path* out) {
+    if (!M || !out || M->staged_n <= 0) return AUGB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(M->device));
+    M->r_begin.clear(); M->r_end.clear(); M->r_type.clear(); M->r_trunc.clear(); M->sweep_ms = 0;
+    std::vector<int> order(M->staged_n);
+    for (int i = 0; i < M->staged_n; i++) order[i] = i;
+    int rc = fetch_results(M, M->staged_n, out, order.data()); if (rc) return rc;
+    fix_pointers(M, M->staged_n, out);
+    return AUGB200_OK;
+}
+void* augb200_model_stream(augb200_model* M) { return M ? (void*)M->stream : nullptr; }
+int64_t augb200_last_launch_count(const augb200_model* M) { return M ? M->launches : 0; }
+double augb200_last_sweep_ms(const augb200_model* M) { return M ? M->sweep_ms : 0; }
+
+int64_t augb200_result_store(const augb200_model* M, const int32_t** b, const int32_t** e, const uint8_t** t, const uint8_t** tr) {
+    if (!M) return 0;
+    if (b) *b = M->r_begin.data();
+    if (e) *e = M->r_end.data();
+    if (t) *t = M->r_type.data();
+    if (tr) *tr = M->r_trunc.data();
+    return (int64_t)M->r_begin.size();
+}
+
+const char* augb200_strerror(int code) {
+    switch (code) {
+    case AUGB200_OK: return "ok";
+    case AUGB200_ERR_BAD_BLOB: return "malformed parameter blob";
+    case AUGB200_ERR_UNSUPPORTED: return "model not supported by this library";
+    case AUGB200_ERR_NO_DEVICE: return "no CUDA device";
+    case AUGB200_ERR_CUDA: return "CUDA error";
+    case AUGB200_ERR_BAD_ARG: return "bad argument";
+    case AUGB200_ERR_NO_PATH: return "No feasible path found in HMM";
+    case AUGB200_ERR_STUCK: return "Viterbi got stuck";
+    case AUGB200_ERR_CAPACITY: return "internal capacity exceeded";
+    case AUGB200_ERR_TOO_LONG: return "window longer than AUGB200_MAX_WINDOW";
+    default: return "unknown error";
+    }
+}
+const char* augb200_last_cuda_error(void) { return g_cuda_err.c_str(); }
+
+}  // extern "C"

@@ -30,6 +30,7 @@ constexpr int MAXS = 96;      /* states */
 constexpr int MAXC = 8;       /* GC classes */
 constexpr int MAXANC = 8;
 constexpr int NCHAIN = 7;     /* igenic + 3 geometric + 3 reverse geometric */
+constexpr int WF_ALLN = 1 << 8;
 
 /* reference StateType values (include/types.hh:492-512) used by the kernels */
 enum : int {
@@ -125,6 +126,7 @@ struct WinView {
     ChainCP* cp[NCHAIN];
     /* results */
     int32_t* out_n_ev; int32_t* out_ncp; int32_t* out_status;
+    const int32_t* flags;      /* written by prep: bits 0..7 GC classes present, bit 8 = no a/c/g/t at all */
 };
 
 }  // namespace augb

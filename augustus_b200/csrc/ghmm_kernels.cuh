@@ -1,0 +1,270 @@
+/*
+ * ghmm_kernels.cuh — CUDA kernels (sm_100a): prep pass, warp-per-window sweep, backtrace, result pack.
+ */
+#pragma once
+#include <cuda_runtime.h>
+
+#include "ghmm_backtrace.h"
+#include "ghmm_defs.h"
+#include "ghmm_prep.h"
+#include "ghmm_seq.h"
+#include "ghmm_sweep.h"
+
+namespace augb {
+
+/* per-window descriptor in device memory */
+struct WinDev {
+    char* base;                /* workspace of this window */
+    const char* dna;           /* device copy of the ASCII window */
+    const uint8_t* gc_in;      /* device copy of host-provided classes or nullptr */
+    int L;
+    WinLayout lay;
+};
+
+constexpr int PREP_BS = 256;
+constexpr int PREP_ITEMS = 4;
+constexpr int PREP_TILE = PREP_BS * PREP_ITEMS;
+
+/* exclusive block-wide prefix of one value per thread; returns the prefix, *total = block sum */
+template <typename T>
+__device__ __forceinline__ T block_excl_sum(T v, T* sm /* PREP_BS/32 + 1 */, T* total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    T incl = v;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { T t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) sm[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        T w = lane < PREP_BS / 32 ? sm[lane] : (T)0, wi = w;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { T t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+        if (lane < PREP_BS / 32) sm[lane] = wi - w;
+        if (lane == PREP_BS / 32 - 1) sm[PREP_BS / 32] = wi;
+    }
+    __syncthreads();
+    T r = sm[wid] + incl - v;
+    *total = sm[PREP_BS / 32];
+    __syncthreads();
+    return r;
+}
+
+/* out[off + i] = init + sum_{t<=i} gen(t), i in [0, n) */
+template <typename T, typename Gen>
+__device__ __forceinline__ void block_scan_gen(Gen gen, T* out, int n, T init, T* sm) {
+    T carry = init;
+    for (int t0 = 0; t0 < n; t0 += PREP_TILE) {
+        T v[PREP_ITEMS]; int i0 = t0 + threadIdx.x * PREP_ITEMS;
+        T run = 0;
+        #pragma unroll
+        for (int i = 0; i < PREP_ITEMS; i++) { int idx = i0 + i; T x = idx < n ? gen(idx) : (T)0; run += x; v[i] = run; }
+        T tot; T ex = block_excl_sum<T>(run, sm, &tot);
+        #pragma unroll
+        for (int i = 0; i < PREP_ITEMS; i++) { int idx = i0 + i; if (idx < n) out[idx] = carry + ex + v[i]; }
+        carry += tot;
+    }
+}
+
+/* nearest in-frame stop tables: a max-scan over (last stop position per residue class) */
+struct Int3 { int a, b, c; };
+__device__ __forceinline__ Int3 max3(Int3 x, Int3 y) { Int3 r; r.a = max(x.a, y.a); r.b = max(x.b, y.b); r.c = max(x.c, y.c); return r; }
+
+template <bool RC>
+__device__ void block_stop_scan(const DevModel* m, const Seq& s, int32_t* out, int L, Int3* sm3) {
+    /* positions 0 .. L-3 get the last stop <= i in the residue class of i; L-2, L-1 are patched (exonmodel.cc:147-153) */
+    const int n = L - 2;   /* number of scanned positions (i <= L-3) */
+    Int3 carry; carry.a = carry.b = carry.c = -1;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int t0 = 0; t0 < n; t0 += PREP_TILE) {
+        int i0 = t0 + threadIdx.x * PREP_ITEMS;
+        Int3 v[PREP_ITEMS]; Int3 run; run.a = run.b = run.c = -1;
+        #pragma unroll
+        for (int i = 0; i < PREP_ITEMS; i++) {
+            int idx = i0 + i;
+            if (idx < n && (RC ? isRCStop(m, s, idx) : isStop(m, s, idx))) { int r = idx % 3; if (r == 0) run.a = idx; else if (r == 1) run.b = idx; else run.c = idx; }
+            v[i] = run;
+        }
+        Int3 incl = run;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            Int3 t; t.a = __shfl_up_sync(0xffffffffu, incl.a, o); t.b = __shfl_up_sync(0xffffffffu, incl.b, o); t.c = __shfl_up_sync(0xffffffffu, incl.c, o);
+            if (lane >= o) incl = max3(incl, t);
+        }
+        if (lane == 31) sm3[wid] = incl;
+        __syncthreads();
+        Int3 pre; pre.a = pre.b = pre.c = -1;
+        for (int w2 = 0; w2 < wid; w2++) pre = max3(pre, sm3[w2]);
+        Int3 ex; ex.a = __shfl_up_sync(0xffffffffu, incl.a, 1); ex.b = __shfl_up_sync(0xffffffffu, incl.b, 1); ex.c = __shfl_up_sync(0xffffffffu, incl.c, 1);
+        if (lane == 0) { ex.a = ex.b = ex.c = -1; }
+        ex = max3(max3(ex, pre), carry);
+        #pragma unroll
+        for (int i = 0; i < PREP_ITEMS; i++) {
+            int idx = i0 + i;
+            if (idx < n) { Int3 r = max3(ex, v[i]); int rr = idx % 3; out[idx] = rr == 0 ? r.a : rr == 1 ? r.b : r.c; }
+        }
+        Int3 tot; tot.a = tot.b = tot.c = -1;
+        for (int w2 = 0; w2 < PREP_BS / 32; w2++) tot = max3(tot, sm3[w2]);
+        carry = max3(carry, tot);
+        __syncthreads();
+    }
+}
+
+/* ------------------------------------------------------------------ prep kernel: one CTA per window */
+__global__ void __launch_bounds__(PREP_BS) k_prep(const DevModel* __restrict__ m, const WinDev* __restrict__ wins, int nwin) {
+    __shared__ sc_t sm64[PREP_BS / 32 + 2];
+    __shared__ int sm32[PREP_BS / 32 + 2];
+    __shared__ Int3 sm3[PREP_BS / 32];
+    __shared__ int s_classmask;
+    __shared__ int s_anynuc;
+    __shared__ int s_nruns;
+    for (int wi = blockIdx.x; wi < nwin; wi += gridDim.x) {
+        const WinDev wd = wins[wi];
+        const int L = wd.L; char* base = wd.base; const WinLayout& lay = wd.lay;
+        uint8_t* code = (uint8_t*)(base + lay.code); uint8_t* gc = (uint8_t*)(base + lay.gc); uint16_t* mask = (uint16_t*)(base + lay.mask);
+        if (threadIdx.x == 0) { s_classmask = 0; s_anynuc = 0; }
+        __syncthreads();
+        { bool any = false; for (int i = threadIdx.x; i < L; i += PREP_BS) { uint8_t c = base_code(wd.dna[i]); code[i] = c; any |= c < 4; } if (any) s_anynuc = 1; }
+        __syncthreads();
+        const bool anynuc = s_anynuc != 0;
+        Seq s; s.c = code; s.L = L;
+        /* ---- GC classes: ContentStairs::computeStairs (motif.cc:543-614) ---- */
+        if (wd.gc_in) {
+            for (int i = threadIdx.x; i < L; i += PREP_BS) gc[i] = wd.gc_in[i];
+        } else {
+            int32_t* cnt = (int32_t*)(base + lay.ev);          /* scratch: 4 x (L+1) counts, region unused until the sweep */
+            for (int b = 0; b < 4; b++) {
+                int32_t* cb = cnt + (size_t)b * (L + 1);
+                if (threadIdx.x == 0) cb[0] = 0;
+                block_scan_gen<int>([&](int i) { return code[i] == b ? 1 : 0; }, cb + 1, L, 0, sm32);
+            }
+            __syncthreads();
+            int win = m->GCwinsize; if (win > L || win < 1) win = L;
+            const int half = win / 2, hi = max(L - (win + 1) / 2, half);
+            for (int i = threadIdx.x; i < L; i += PREP_BS) {
+                int ic = min(max(i, half), hi);
+                int lo = ic - half, up = ic + (win + 1) / 2;      /* window [lo, up) */
+                int c4[4];
+                for (int b = 0; b < 4; b++) { const int32_t* cb = cnt + (size_t)b * (L + 1); c4[b] = cb[up] - cb[lo]; }
+                gc[i] = (uint8_t)nearest_class(m, c4);
+            }
+            __syncthreads();
+            /* anti-flicker smoothing: sequential over the raw runs (warp 0 finds them in order) */
+            int32_t* runs = cnt;                               /* reuse scratch: (start, value, curval) triples */
+            if (threadIdx.x < 32) {
+                int nr = 0;
+                for (int i0 = 0; i0 < L; i0 += 32) {
+                    int i = i0 + threadIdx.x; bool chg = false; int v = 0;
+                    if (i < L) { v = gc[i]; chg = i == 0 || gc[i - 1] != v; }
+                    unsigned b = __ballot_sync(0xffffffffu, chg);
+                    if (chg) { int k = nr + __popc(b & ((1u << threadIdx.x) - 1)); runs[3 * k] = i; runs[3 * k + 1] = v; runs[3 * k + 2] = v; }
+                    nr += __popc(b);
+                }
+                if (threadIdx.x == 0) s_nruns = nr;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int nr = s_nruns;
+                /* at run k (start i): lastStep = start of run k-1; fill run k-1 with val_k if short and value before it equals val_k */
+                for (int k = 2; k < nr; k++) {
+                    int i = runs[3 * k], lastStep = runs[3 * (k - 1)];
+                    if (i - lastStep < 1000 && lastStep > 0 && runs[3 * (k - 2) + 2] == runs[3 * k + 1]) runs[3 * (k - 1) + 2] = runs[3 * k + 1];
+                }
+            }
+            __syncthreads();
+            {
+                int nr = s_nruns;
+                for (int k = 1; k + 1 < nr; k++) {
+                    int v = runs[3 * k + 2];
+                    if (v != runs[3 * k + 1]) for (int i = runs[3 * k] + threadIdx.x; i < runs[3 * (k + 1)]; i += PREP_BS) gc[i] = (uint8_t)v;
+                }
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+        { int cm = 0; for (int i = threadIdx.x; i < L; i += PREP_BS) cm |= 1 << gc[i]; if (cm) atomicOr(&s_classmask, cm); }
+        for (int j = threadIdx.x; j < L; j += PREP_BS) mask[j] = anynuc ? (uint16_t)column_mask(m, s, j) : 0;
+        __syncthreads();
+        const int cm = s_classmask | (anynuc ? 0 : WF_ALLN);
+        /* ---- prefix sums ---- */
+        sc_t* parr = (sc_t*)(base + lay.parr);
+        for (int c = 0; c < m->C; c++) {
+            if (!(cm >> c & 1)) continue;
+            for (int which = 0; which < PA_PER_CLASS; which++) {
+                sc_t* P = parr + ((size_t)c * PA_PER_CLASS + which) * (size_t)(L + 1);
+                if (threadIdx.x == 0) P[0] = 0;
+                block_scan_gen<sc_t>([&](int p) { return parr_term(m, s, c, which, p); }, P + 1, L, (sc_t)0, sm64);
+            }
+        }
+        sc_t* aig = (sc_t*)(base + lay.aig); sc_t* ageo = (sc_t*)(base + lay.ageo);
+        if (threadIdx.x == 0) { aig[0] = 0; ageo[0] = 0; }
+        block_scan_gen<sc_t>([&](int i) { return anynuc ? aig_term(m, s, gc, i + 1) : m->log025; }, aig + 1, L - 1, (sc_t)0, sm64);
+        block_scan_gen<sc_t>([&](int i) { return ageo_term(m, s, gc, i + 1); }, ageo + 1, L - 1, (sc_t)0, sm64);
+        /* ---- ORF tables ---- */
+        int32_t* nsf = (int32_t*)(base + lay.nsf); int32_t* nsr = (int32_t*)(base + lay.nsr);
+        for (int i = threadIdx.x; i < L + 3; i += PREP_BS) { nsf[i] = 0; nsr[i] = 0; }
+        __syncthreads();
+        if (L >= 3) { block_stop_scan<false>(m, s, nsf, L, sm3); block_stop_scan<true>(m, s, nsr, L, sm3); }
+        __syncthreads();
+        if (threadIdx.x == 0 && L > 5) { nsf[L - 2] = nsf[L - 5]; nsf[L - 1] = nsf[L - 4]; nsr[L - 2] = nsr[L - 5]; nsr[L - 1] = nsr[L - 4]; }
+        if (threadIdx.x == 0) { WinOuts* o = (WinOuts*)(base + lay.outs); o->pad = cm; }
+        __syncthreads();
+    }
+}
+
+/* ------------------------------------------------------------------ sweep kernel: one warp per window */
+constexpr int SWEEP_WARPS = 4;
+__global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep(const DevModel* __restrict__ m, const WinDev* __restrict__ wins, int nwin, int* __restrict__ next) {
+    __shared__ WarpState wstate[SWEEP_WARPS];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (;;) {
+        int wi = 0;
+        if (lane == 0) wi = atomicAdd(next, 1);
+        wi = __shfl_sync(0xffffffffu, wi, 0);
+        if (wi >= nwin) break;
+        const WinDev& wd = wins[wi];
+        Sweep sw; sw.m = m; sw.ws = &wstate[wid];
+        sw.w = make_view(wd.base, wd.lay, wd.L, 0);
+        sw.run();
+        __syncwarp();
+    }
+}
+
+/* ------------------------------------------------------------------ backtrace: one thread per window */
+__global__ void k_backtrace(const DevModel* __restrict__ m, const WinDev* __restrict__ wins, int nwin) {
+    int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= nwin) return;
+    const WinDev& wd = wins[wi];
+    WinView v = make_view(wd.base, wd.lay, wd.L, 0);
+    WinOuts* outs = (WinOuts*)(wd.base + wd.lay.outs);
+    PathOut po; po.cap = wd.lay.path_cap;
+    po.begin = (int32_t*)(wd.base + wd.lay.path_begin); po.end = (int32_t*)(wd.base + wd.lay.path_end);
+    po.type = (uint8_t*)(wd.base + wd.lay.path_type); po.trunc = (uint8_t*)(wd.base + wd.lay.path_trunc);
+    po.n = &outs->path_n; po.status = &outs->path_status; po.score = &outs->score;
+    backtrace_window(m, v, po);
+}
+
+/* ------------------------------------------------------------------ pack: gather paths into one contiguous result buffer */
+struct PackHdr { int32_t n, status, offset, n_ev; sc_t score; };
+__global__ void k_pack(const WinDev* __restrict__ wins, int nwin, PackHdr* __restrict__ hdr, int* __restrict__ total,
+                       int32_t* __restrict__ obegin, int32_t* __restrict__ oend, uint8_t* __restrict__ otype, uint8_t* __restrict__ otrunc, int ocap) {
+    int wi = blockIdx.x;
+    if (wi >= nwin) return;
+    const WinDev& wd = wins[wi];
+    const WinOuts* outs = (const WinOuts*)(wd.base + wd.lay.outs);
+    __shared__ int s_off;
+    int n = outs->path_n;
+    if (threadIdx.x == 0) {
+        int off = atomicAdd(total, n);
+        s_off = off;
+        PackHdr h; h.n = n; h.status = outs->path_status; h.offset = off; h.n_ev = outs->n_ev; h.score = outs->score;
+        if (off + n > ocap) { h.n = 0; h.status = 8; }
+        hdr[wi] = h;
+    }
+    __syncthreads();
+    int off = s_off;
+    if (off + n > ocap) return;
+    const int32_t* b = (const int32_t*)(wd.base + wd.lay.path_begin); const int32_t* e = (const int32_t*)(wd.base + wd.lay.path_end);
+    const uint8_t* t = (const uint8_t*)(wd.base + wd.lay.path_type); const uint8_t* tr = (const uint8_t*)(wd.base + wd.lay.path_trunc);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { obegin[off + i] = b[i]; oend[off + i] = e[i]; otype[off + i] = t[i]; otrunc[off + i] = tr[i]; }
+}
+
+}  // namespace augb

@@ -27,15 +27,21 @@ struct WinLayout {
     size_t total;
     int ev_cap, cl_cap, cp_cap, path_cap;
 };
-inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
-inline WinLayout make_layout(int L, int C) {
+AUGB_HD size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
+/* Capacities of the dynamic structures.  `generous` = provable upper bounds (every column can hold at most one
+ * cell per state; a candidate list gets at most one entry per column); the default sizes are ~3x what human-like
+ * DNA needs (measured: 1.9 events, 0.03 list entries per base) and a window that overflows them is reported with
+ * status AUGB200_ERR_CAPACITY and decoded again with the generous layout (augb200.cu: decode_batch). */
+inline WinLayout make_layout(int L, int C, bool generous = false) {
     WinLayout w; size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = al16(o + bytes); return r; };
     w.code = take(L); w.gc = take(L); w.mask = take((size_t)L * 2);
     w.parr = take((size_t)C * PA_PER_CLASS * (L + 1) * sizeof(sc_t));
     w.aig = take((size_t)L * sizeof(sc_t)); w.ageo = take((size_t)L * sizeof(sc_t));
     w.nsf = take((size_t)(L + 3) * 4); w.nsr = take((size_t)(L + 3) * 4);
-    w.ev_cap = 4 * L + 256; w.cl_cap = L / 2 + 64; w.cp_cap = L / 2 + 64; w.path_cap = L / 2 + 64;
+    if (generous) { w.ev_cap = 48 * L + 256; w.cl_cap = L + 64; w.cp_cap = L + 64; w.path_cap = L + 64; }
+    else { w.ev_cap = 3 * L + 256; w.cl_cap = L / 6 + 64; w.cp_cap = L / 16 + 64; w.path_cap = L / 8 + 64; }
+    if ((size_t)w.ev_cap * sizeof(Event) < (size_t)4 * (L + 1) * 4) w.ev_cap = (int)(((size_t)4 * (L + 1) * 4) / sizeof(Event) + 1);   /* prep scratch */
     w.ev = take((size_t)w.ev_cap * sizeof(Event)); w.evstart = take((size_t)(L + 2) * 4);
     for (int i = 0; i < NCL; i++) w.cl[i] = take((size_t)w.cl_cap * sizeof(Cand));
     for (int i = 0; i < NCHAIN; i++) w.cp[i] = take((size_t)w.cp_cap * sizeof(ChainCP));
@@ -46,9 +52,9 @@ inline WinLayout make_layout(int L, int C) {
     return w;
 }
 /* result block at WinLayout::outs */
-struct WinOuts { int32_t n_ev, status, path_n, path_status; int32_t ncp[NCHAIN]; int32_t pad; sc_t score; };
+struct WinOuts { int32_t n_ev, status, path_n, path_status; int32_t ncp[NCHAIN]; int32_t pad /* window flags */; sc_t score; };
 
-inline WinView make_view(char* base, const WinLayout& lay, int L, int classmask) {
+AUGB_HD WinView make_view(char* base, const WinLayout& lay, int L, int classmask) {
     WinView v; v.L = L; v.nclassmask = classmask; v.ev_cap = lay.ev_cap; v.cl_cap = lay.cl_cap; v.cp_cap = lay.cp_cap;
     v.code = (const uint8_t*)(base + lay.code); v.gc = (const uint8_t*)(base + lay.gc); v.mask = (const uint16_t*)(base + lay.mask);
     v.parr = (const sc_t*)(base + lay.parr); v.AIG = (const sc_t*)(base + lay.aig); v.AGEO = (const sc_t*)(base + lay.ageo);
@@ -57,7 +63,7 @@ inline WinView make_view(char* base, const WinLayout& lay, int L, int classmask)
     for (int i = 0; i < NCL; i++) v.cl[i] = (Cand*)(base + lay.cl[i]);
     for (int i = 0; i < NCHAIN; i++) v.cp[i] = (ChainCP*)(base + lay.cp[i]);
     WinOuts* o = (WinOuts*)(base + lay.outs);
-    v.out_n_ev = &o->n_ev; v.out_status = &o->status; v.out_ncp = o->ncp;
+    v.out_n_ev = &o->n_ev; v.out_status = &o->status; v.out_ncp = o->ncp; v.flags = &o->pad;
     return v;
 }
 
@@ -139,10 +145,13 @@ inline void prep_window_seq(const DevModel* m, const char* dna, int L, const int
     uint8_t* code = (uint8_t*)(base + lay.code); uint8_t* gc = (uint8_t*)(base + lay.gc); uint16_t* mask = (uint16_t*)(base + lay.mask);
     for (int i = 0; i < L; i++) code[i] = base_code(dna[i]);
     if (gc_in) for (int i = 0; i < L; i++) gc[i] = (uint8_t)gc_in[i]; else gc_stairs_seq(m, code, L, gc);
-    int cm = 0; for (int i = 0; i < L; i++) cm |= 1 << gc[i];
+    int cm = 0; bool anynuc = false;
+    for (int i = 0; i < L; i++) { cm |= 1 << gc[i]; anynuc |= code[i] < 4; }
+    if (!anynuc) cm |= WF_ALLN;
     *classmask = cm;
+    ((WinOuts*)(base + lay.outs))->pad = cm;
     Seq s; s.c = code; s.L = L;
-    for (int j = 0; j < L; j++) mask[j] = (uint16_t)column_mask(m, s, j);
+    for (int j = 0; j < L; j++) mask[j] = anynuc ? (uint16_t)column_mask(m, s, j) : 0;
     sc_t* parr = (sc_t*)(base + lay.parr);
     for (int c = 0; c < m->C; c++) {
         if (!(cm >> c & 1)) continue;
@@ -154,7 +163,7 @@ inline void prep_window_seq(const DevModel* m, const char* dna, int L, const int
     }
     sc_t* aig = (sc_t*)(base + lay.aig); sc_t* ageo = (sc_t*)(base + lay.ageo);
     aig[0] = ageo[0] = 0;
-    for (int j = 1; j < L; j++) { aig[j] = aig[j - 1] + aig_term(m, s, gc, j); ageo[j] = ageo[j - 1] + ageo_term(m, s, gc, j); }
+    for (int j = 1; j < L; j++) { aig[j] = aig[j - 1] + (anynuc ? aig_term(m, s, gc, j) : m->log025); ageo[j] = ageo[j - 1] + ageo_term(m, s, gc, j); }
     int32_t* nsf = (int32_t*)(base + lay.nsf); int32_t* nsr = (int32_t*)(base + lay.nsr);
     for (int i = 0; i < L + 3; i++) nsf[i] = nsr[i] = 0;
     for (int r = 0; r < 3; r++) {

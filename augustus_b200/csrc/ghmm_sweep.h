@@ -605,9 +605,13 @@ struct Sweep {
         cls = w.gc[0];
         fill_evstart(0);
         /* column 0 = initial probabilities (NAMGene::setStatesInitialProbs, namgene.cc:144-150) */
+        /* a window without a single a/c/g/t is all intergenic: viterbi[j][synch] = viterbi[j-1][synch]/4,
+         * every other state erased (namgene.cc:205-226); prep wrote AIG[j] = j*log(1/4) and an empty mask */
+        const bool alln = (*w.flags & WF_ALLN) != 0;
         for (int s = 0; s < m->S; s++) {
             sc_t v = m->init[s]; if (isneg(v)) continue;
             int ch = m->st[s].chain;
+            if (alln && ch != 0) continue;
             if (ch >= 0) {
                 if (lane == 0) { ChainCP c; c.col = 0; c.pred = -1; c.tilde = v; w.cp[ch][0] = c; ws->cp_n[ch] = 1; ws->tilde[ch] = v; }
                 wsync();

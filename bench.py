@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""bench.py — Mbp decoded per second on BASELINE.json config 2 (synthetic 50 kb human-composition windows,
+--species=human ab initio), one JSON line on rank 0.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--windows M] [--impl reference]
+
+A "step" is one pass of the whole hot path (prep -> sweep -> backtrace -> pack) over the rank's batch of
+windows.  `value` is timed with CUDA events on the library's launch stream with the inputs already in
+HBM; `e2e` is the same metric through the public call (augb200_decode_batch) from host buffers, with the
+host->device copy of the windows and the device->host copy of the paths inside the timed region.
+Weak scaling: every rank decodes its own M windows (window index = rank*M + i), no data-path collective;
+one NCCL gather of the final path arrays ends the e2e region.
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref/augustus, the unmodified
+AUGUSTUS binary built by oracle/Makefile) on the box's host cores on a bounded sample of the same
+windows.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WINDOW_LEN = 50000
+DEFAULT_WINDOWS = 10000
+STATES = 47
+ALG_BYTES_PER_BASE = 0.25 + STATES * (8 + 8 + 4)          # 940 B/base (dense S=47 Viterbi)
+METRIC = "Mbp decoded/sec"
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def ref_binary():
+    exe = os.path.join(ROOT, "oracle", "_ref", "augustus")
+    cfg = os.path.join(ROOT, "oracle", "_ref", "config")
+    return (exe, cfg) if os.path.exists(exe) and os.path.isdir(cfg) else (None, None)
+
+
+def run_reference_sample(n_windows, cores, start_index=0):
+    """Decode n_windows synthetic windows with the unmodified reference, `cores` processes in parallel.
+    Returns (Mbp/s, seconds)."""
+    from augustus_b200 import synth
+    exe, cfg = ref_binary()
+    if exe is None:
+        raise RuntimeError("oracle/_ref/augustus is missing (run __graft_entry__.build() in the build container)")
+    env = dict(os.environ, AUGUSTUS_CONFIG_PATH=cfg)
+    with tempfile.TemporaryDirectory() as td:
+        files = []
+        per = [[] for _ in range(cores)]
+        for i in range(n_windows):
+            per[i % cores].append(start_index + i)
+        for c, idxs in enumerate(per):
+            if not idxs:
+                continue
+            fa = os.path.join(td, "c%d.fa" % c)
+            synth.write_fasta(fa, [synth.window(i, WINDOW_LEN) for i in idxs], ["w%d" % i for i in idxs])
+            files.append(fa)
+        t0 = time.perf_counter()
+        procs = []
+        for c, fa in enumerate(files):
+            cmd = [exe, "--species=human", "--softmasking=0", fa]
+            if os.path.exists("/usr/bin/taskset"):
+                cmd = ["taskset", "-c", str(c % (os.cpu_count() or 1))] + cmd
+            procs.append(subprocess.Popen(cmd, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+        for p in procs:
+            if p.wait() != 0:
+                raise RuntimeError("reference process failed")
+        dt = time.perf_counter() - t0
+    return n_windows * WINDOW_LEN / 1e6 / dt, dt
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    use = min(cores, 64)
+    per_step = use * 2
+    exe, _ = ref_binary()
+    base = {"metric": METRIC, "unit": "Mbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (LLDouble)", "data": "synthetic",
+            "impl": "reference",
+            "config": {"workload": "synthetic 50 kb human-composition windows, --species=human ab initio (BASELINE.json configs[1])",
+                       "window_len": WINDOW_LEN, "windows_per_step": per_step}}
+    if exe is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/augustus not built"}))
+        return
+    for w in range(min(args.warmup, 1)):
+        run_reference_sample(use, use, 0)
+    tot_t, tot_w = 0.0, 0
+    for s in range(args.steps):
+        _, dt = run_reference_sample(per_step, use, s * per_step)
+        tot_t += dt
+        tot_w += per_step
+    v = tot_w * WINDOW_LEN / 1e6 / tot_t
+    base.update({"value": v, "ms_per_step": 1e3 * tot_t / args.steps,
+                 "cpu_baseline": {"value": v, "unit": "Mbp/s", "cores": use, "kind": "reference",
+                                  "sample": "%d windows x 50 kb per step, one augustus process per core" % per_step},
+                 "e2e": {"value": v, "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(base))
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--windows", type=int, default=DEFAULT_WINDOWS, help="windows per GPU per step (default: BASELINE.json config 2)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from augustus_b200 import Decoder, synth
+    from tests import util
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    M = args.windows
+    wins = synth.windows_parallel(M, WINDOW_LEN, start=rank * M)
+    wins_b = [w.encode() for w in wins]
+    bases = M * WINDOW_LEN
+    dec = Decoder(util.blob_bytes(), local)
+    stream = torch.cuda.ExternalStream(dec.stream, device=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput: inputs staged in HBM, K timed steps ----
+    dec.stage(wins_b)
+    for _ in range(args.warmup):
+        dec.run_staged()
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    e0.record(stream)
+    for _ in range(args.steps):
+        dec.run_staged()
+        launches += dec.last_launch_count
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    paths = dec.fetch_staged()
+    sweep_ms = dec.last_sweep_ms            # last run's sweep kernel, CUDA events around that launch
+    assert all(p.status == 0 for p in paths)
+    # ---- end-to-end through the public call, host buffers in, host paths out ----
+    dec.decode_batch(wins_b[: max(1, M // 8)])     # warm the staging buffers
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 2))
+    d2h = 0
+    for _ in range(e2e_steps):
+        n_st, status, logp, offset, pb, pe, pt, ptr = dec.decode_batch_raw(wins_b)
+        assert not status.any()
+        d2h = pb.nbytes + pe.nbytes + pt.nbytes + ptr.nbytes + 32 * len(n_st)
+        if world > 1:   # the one gather of the final results (path arrays) over NCCL
+            flat = torch.from_numpy(np.concatenate([pb, pe, pt.astype(np.int32), ptr.astype(np.int32)])).cuda()
+            n = torch.tensor([flat.numel()], device="cuda")
+            sizes = [torch.zeros_like(n) for _ in range(world)]
+            dist.all_gather(sizes, n)
+            mx = int(max(int(x) for x in sizes))
+            pad = torch.zeros(mx, dtype=torch.int32, device="cuda"); pad[: flat.numel()] = flat
+            out = [torch.zeros_like(pad) for _ in range(world)] if rank == 0 else None
+            dist.gather(pad, out, dst=0)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    sampler.stop_flag = True; sampler.join(timeout=2)
+
+    t = torch.tensor([ms, e2e_s, sweep_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_s, sweep_ms = (float(x) for x in t.tolist())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_per_step = ms / args.steps
+    value = world * bases / 1e6 / (ms_per_step / 1e3)
+    peak, how = peaks()
+    achieved = ALG_BYTES_PER_BASE * bases / (sweep_ms / 1e3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int64 (Q23.40 fixed-point log scores)", "data": "synthetic",
+        "config": {"workload": "%d synthetic 50 kb human-composition windows per GPU, --species=human ab initio, 47 states (BASELINE.json configs[1])" % M,
+                   "window_len": WINDOW_LEN, "windows_per_gpu": M, "parallelism": "windows sharded over %d GPU(s), one warp per window" % world,
+                   "l2": "inputs per step (%.0f MB DNA + %.1f GB workspace) exceed the 126 MB L2" % (bases / 1e6, bases * 130 / 1e9)},
+        "e2e": {"value": world * bases / 1e6 / e2e_s, "unit": "Mbp/s", "h2d_bytes_per_step": bases, "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "k_sweep", "peak_source": how,
+                     "note": "achieved = 940 B/base (dense S=47 figure, SURVEY.md 8d) x bases / sweep-kernel time; the sweep stores only non-zero cells (see DESIGN.md)"},
+        "clocks": sampler.summary(),
+        "sweep_ms": sweep_ms,
+    }
+    if not args.no_cpu_baseline:
+        try:
+            cores = min(os.cpu_count() or 1, 64)
+            v, dt = run_reference_sample(cores * 4, cores)
+            line["cpu_baseline"] = {"value": v, "unit": "Mbp/s", "cores": cores, "kind": "reference",
+                                    "sample": "%d windows x 50 kb (%.1f s wall), one unmodified augustus process per core" % (cores * 4, dt)}
+        except Exception as ex:   # the reference binary did not travel: time the oracle port instead
+            orc = util.Oracle(util.blob_bytes())
+            t0 = time.perf_counter(); k = 8
+            for i in range(k):
+                orc.viterbi(wins[i])
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": k * WINDOW_LEN / 1e6 / dt, "unit": "Mbp/s", "cores": 1, "kind": "port",
+                                    "sample": "%d windows x 50 kb, oracle/ghmm_oracle.c, 1 thread (%s)" % (k, ex)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

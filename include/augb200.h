@@ -109,6 +109,11 @@ int64_t augb200_last_launch_count(const augb200_model* m);
 /* device milliseconds spent in the sweep kernel during the last run (CUDA events on the model's stream) */
 double augb200_last_sweep_ms(const augb200_model* m);
 
+/* The contiguous store that every augb200_path of the last decode / fetch call points into (all windows'
+ * states back to back); returns the number of states in it. */
+int64_t augb200_result_store(const augb200_model* m, const int32_t** begin, const int32_t** end,
+                             const uint8_t** type, const uint8_t** truncated);
+
 const char* augb200_strerror(int code);
 const char* augb200_last_cuda_error(void);
 

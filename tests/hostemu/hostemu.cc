@@ -36,16 +36,20 @@ int hostemu_decode(void* mp, const char* dna, int L, const int32_t* gc_in,
                    int evcap, int32_t* ev_col, int32_t* ev_state, int64_t* ev_V, int32_t* n_ev_out,
                    int64_t* chainV /* [L][NCHAIN] or NULL */, uint8_t* gc_out /* [L] or NULL */) {
     EmuModel* e = (EmuModel*)mp; const DevModel* m = &e->hm.dm;
-    WinLayout lay = make_layout(L, m->C);
-    std::vector<char> buf(lay.total + 64);
-    char* base = buf.data();
-    int cm = 0;
-    prep_window_seq(m, dna, L, gc_in, base, lay, &cm);
-    WinView v = make_view(base, lay, L, cm);
-    WarpState ws;
-    Sweep sw; sw.m = m; sw.w = v; sw.ws = &ws;
-    sw.run();
-    WinOuts* outs = (WinOuts*)(base + lay.outs);
+    /* as augb200_decode_batch: default capacities first, the generous layout if a structure overflowed */
+    WinLayout lay; std::vector<char> buf; char* base = nullptr; WinView v; WarpState ws; Sweep sw; WinOuts* outs = nullptr;
+    for (int pass = 0; pass < 2; pass++) {
+        lay = make_layout(L, m->C, pass == 1);
+        buf.assign(lay.total + 64, 0);
+        base = buf.data();
+        int cm = 0;
+        prep_window_seq(m, dna, L, gc_in, base, lay, &cm);
+        v = make_view(base, lay, L, cm);
+        sw = Sweep(); sw.m = m; sw.w = v; sw.ws = &ws;
+        sw.run();
+        outs = (WinOuts*)(base + lay.outs);
+        if (outs->status != AUGB200_ERR_CAPACITY) break;
+    }
     PathOut po; po.cap = lay.path_cap;
     po.begin = (int32_t*)(base + lay.path_begin); po.end = (int32_t*)(base + lay.path_end);
     po.type = (uint8_t*)(base + lay.path_type); po.trunc = (uint8_t*)(base + lay.path_trunc);

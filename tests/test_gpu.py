@@ -1,0 +1,91 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path through the C ABI against the oracle on the same
+inputs, against the committed reference paths, and through size-independent properties at full size."""
+import numpy as np
+import pytest
+
+from augustus_b200 import Decoder, synth
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dec():
+    return Decoder(util.blob_bytes(), 0)
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return util.Oracle(util.blob_bytes())
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return util.golden_paths()
+
+
+def _same(path, o):
+    assert path.status == 0
+    assert path.as_tuples() == o["condensed"]
+    assert path.log_prob == o["log_prob"]          # identical Q40 integers on both sides
+
+
+def test_example_fa_matches_reference_and_oracle(dec, oracle, golden):
+    seqs = util.read_fasta(util.GOLDEN + "/example.fa")
+    paths = dec.decode_batch([s for _, s in seqs])
+    for (name, dna), p, ref in zip(seqs, paths, golden["example"]):
+        assert p.as_tuples() == [tuple(s) for s in ref["states"]]          # the reference's own path
+        assert abs(p.log_prob - ref["log_prob"]) <= 1e-6 * abs(ref["log_prob"])
+        _same(p, oracle.viterbi(dna))
+
+
+def test_synthetic_50k_windows_match_reference(dec, golden):
+    wins = synth.windows(16, 50000)
+    paths = dec.decode_batch(wins)
+    for p, ref in zip(paths, golden["synthetic50k"]):
+        assert p.as_tuples() == [tuple(s) for s in ref["states"]]
+        assert abs(p.log_prob - ref["log_prob"]) <= 1e-6 * abs(ref["log_prob"])
+
+
+def test_seeded_windows_match_oracle(dec, oracle):
+    wins = [synth.window(200 + i, n) for i, n in enumerate([50000, 31000, 12345, 7000, 2048, 999, 120, 41, 9, 3, 2])]
+    paths = dec.decode_batch(wins)
+    for dna, p in zip(wins, paths):
+        _same(p, oracle.viterbi(dna))
+
+
+def test_edge_cases_match_oracle(dec, oracle):
+    base = synth.window(7, 4000)
+    cases = ["N" * 500, base[:1000] + "N" * 300 + base[1000:2000], base.lower(), "ACGT" * 300, "GT" * 700, "AG" * 700,
+             "ATG" * 400 + "TAA" * 3, base[:600]]
+    paths = dec.decode_batch(cases)
+    for dna, p in zip(cases, paths):
+        _same(p, oracle.viterbi(dna))
+
+
+def test_host_supplied_gc_classes_equal_device_computed(dec, oracle):
+    dna = synth.window(11, 20000)
+    o = oracle.viterbi(dna)
+    a = dec.decode_batch([dna])[0]
+    b = dec.decode_batch([dna], gc=[o["gc"]])[0]
+    assert a.as_tuples() == b.as_tuples() == o["condensed"]
+
+
+def test_single_window_seam(dec, oracle):
+    dna = util.read_fasta(util.GOLDEN + "/example.fa")[1][1]
+    dec.viterbiAndForward(dna)
+    _same(dec.getViterbiPath(), oracle.viterbi(dna))
+
+
+def test_full_size_properties(dec):
+    """Size-independent checks on a larger batch: batch order independence, idempotence, path structure."""
+    wins = synth.windows(96, 50000, start=1000)
+    p1 = dec.decode_batch(wins)
+    p2 = dec.decode_batch(wins[::-1])[::-1]
+    for a, b, w in zip(p1, p2, wins):
+        assert a.as_tuples() == b.as_tuples() and a.log_prob == b.log_prob
+        st = a.states
+        assert st[0].begin == 1 and st[-1].end == len(w) - 1
+        for x, y in zip(st, st[1:]):
+            assert y.begin == x.end + 1                 # the path tiles columns 1..L-1
+        assert a.log_prob < 0

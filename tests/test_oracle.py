@@ -1,0 +1,110 @@
+"""CPU tests: the oracle (oracle/ghmm_oracle.c) against the reference's own outputs (tests/golden/),
+and the host build of the kernel source against the oracle.  No GPU needed."""
+import numpy as np
+import pytest
+
+from augustus_b200 import params, synth
+from tests import util
+
+
+@pytest.fixture(scope="module")
+def blob():
+    return util.blob_bytes()
+
+
+@pytest.fixture(scope="module")
+def oracle(blob):
+    return util.Oracle(blob)
+
+
+@pytest.fixture(scope="module")
+def emu(blob):
+    return util.HostEmu(blob)
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return util.golden_paths()
+
+
+def test_blob_parses(blob):
+    p = params.parse(blob)
+    assert int(p["statecount"][0]) == 47 and int(p["num_gc_classes"][0]) == 2
+    assert p["trans"].shape == (2, 47, 47) and p["exon_emi"].shape == (2, 3, 1024)
+    assert np.isneginf(p["lendist_intron"][0])
+
+
+def test_synth_is_reproducible():
+    a, b = synth.window(3, 1000), synth.window(3, 1000)
+    assert a == b and set(a) <= set("ACGT") and synth.window(4, 1000) != a
+    gc = (a.count("G") + a.count("C")) / 1000
+    assert 0.33 < gc < 0.49
+
+
+def _check_against_ref(oracle, dna, ref):
+    r = oracle.viterbi(dna)
+    assert r["n"] > 0
+    # GC-class stairs as ContentStairs::computeStairs (reference motif.cc:543-614)
+    assert (r["gc"] == util.gc_from_runs(ref["gc"], len(dna))).all()
+    # state path: bit-exact
+    assert r["condensed"] == [tuple(s) for s in ref["states"]]
+    # LLDouble score vs Q40 log score: 1e-6 relative is the contract, we are ~1e-13
+    assert abs(r["log_prob"] - ref["log_prob"]) <= 1e-9 * abs(ref["log_prob"])
+
+
+def test_oracle_matches_reference_on_example_fa(oracle, golden):
+    seqs = util.read_fasta(util.GOLDEN + "/example.fa")
+    for (name, dna), ref in zip(seqs, golden["example"]):
+        assert name == ref["name"]
+        _check_against_ref(oracle, dna, ref)
+
+
+def test_oracle_matches_reference_on_multiclass_real_dna(oracle, golden):
+    """Windows with several GC classes and an N run: exercises the restated SnippetProbs memo."""
+    seqs = util.read_fasta(util.GOLDEN + "/real_windows.fa")
+    assert any(len(r["gc"]) > 1 for r in golden["real"])
+    for (name, dna), ref in zip(seqs, golden["real"]):
+        _check_against_ref(oracle, dna, ref)
+
+
+@pytest.mark.parametrize("i", [0, 1, 2, 3])
+def test_oracle_matches_reference_on_synthetic_50k(oracle, golden, i):
+    _check_against_ref(oracle, synth.window(i, 50000), golden["synthetic50k"][i])
+
+
+def test_oracle_matches_reference_on_short_windows(oracle, golden):
+    for (idx, n), ref in zip(golden["synthetic_short_spec"], golden["synthetic_short"]):
+        _check_against_ref(oracle, synth.window(idx, n), ref)
+
+
+# ---------------------------------------------------------------- host build of the kernel source
+def _cells_equal(oracle, emu, dna):
+    o = oracle.viterbi(dna, want_matrix=True)
+    e = emu.decode(dna, want_cells=True)
+    assert e["status"] == 0
+    assert (o["gc"] == e["gc"]).all()
+    assert e["states"] == o["condensed"]
+    assert e["log_prob"] == o["log_prob"]
+    V, E = o["V"], e["cells"]
+    assert ((V <= util.NEGT) == (E <= util.NEGT)).all()
+    ok = V > util.NEGT
+    assert (V[ok] == E[ok]).all()            # bit-exact fixed-point scores in every DP cell
+
+
+def test_kernel_source_on_host_matches_oracle_cells(oracle, emu):
+    for name, dna in util.read_fasta(util.GOLDEN + "/example.fa"):
+        _cells_equal(oracle, emu, dna)
+    _cells_equal(oracle, emu, synth.window(5, 20000))
+    _cells_equal(oracle, emu, synth.window(103, 120))
+
+
+def test_kernel_source_on_host_edge_cases(oracle, emu):
+    base = synth.window(7, 4000)
+    cases = [base[:2], base[:3], base[:9], base[:41], base[:600], "N" * 500, base[:1000] + "N" * 300 + base[1000:2000],
+             base.lower(), "ACGT" * 300, "GT" * 700, "AG" * 700, "ATG" * 400 + "TAA" * 3]
+    for dna in cases:
+        o = oracle.viterbi(dna)
+        e = emu.decode(dna)
+        assert e["status"] == 0 and o["n"] >= 0, len(dna)
+        assert e["states"] == o["condensed"], len(dna)
+        assert e["log_prob"] == o["log_prob"]

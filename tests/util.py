@@ -1,0 +1,148 @@
+"""Test helpers: golden fixtures, the oracle (CPU restatement) and the host emulator of the kernel source.
+
+The oracle and the emulator are TEST INFRASTRUCTURE: nothing in augustus_b200/ imports this module.
+"""
+import ctypes
+import json
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+ORACLE_SO = os.path.join(ROOT, "oracle", "libghmm_oracle.so")
+HOSTEMU_SO = os.path.join(ROOT, "tests", "hostemu", "libaugb200_hostemu.so")
+NEGT = -(1 << 60)
+FRAC = 40
+
+
+def blob_bytes():
+    from augustus_b200 import params
+    return params.load_bytes(os.path.join(GOLDEN, "human.params.xz"))
+
+
+def golden_paths():
+    return json.load(open(os.path.join(GOLDEN, "ref_paths.json")))
+
+
+def read_fasta(path):
+    seqs, name, buf = [], None, []
+    for line in open(path):
+        if line.startswith(">"):
+            if name is not None:
+                seqs.append((name, "".join(buf)))
+            name, buf = line[1:].split()[0], []
+        else:
+            buf.append(line.strip())
+    seqs.append((name, "".join(buf)))
+    return seqs
+
+
+def condense(states):
+    """StatePath::condenseStatePath (reference gene.cc:977-1000) on (type, begin, end, trunc) tuples."""
+    out = []
+    for t, b, e, tr in states:
+        coding = (1 <= t <= 8) or (36 <= t <= 43)
+        if out and out[-1][0] == t and not coding:
+            out[-1][2] = e
+            out[-1][3] |= tr
+        else:
+            out.append([t, b, e, tr])
+    return [tuple(x) for x in out]
+
+
+def gc_from_runs(runs, length):
+    gc = np.zeros(length, dtype=np.int32)
+    for pos, idx in runs:
+        gc[pos:] = idx
+    return gc
+
+
+def _ensure(path, cmd, cwd):
+    if not os.path.exists(path):
+        subprocess.run(cmd, cwd=cwd, check=True)
+
+
+class Oracle:
+    def __init__(self, blob: bytes):
+        _ensure(ORACLE_SO, ["make", "liboracle"], os.path.join(ROOT, "oracle"))
+        self.lib = ctypes.CDLL(ORACLE_SO)
+        self.lib.orc_model_load.restype = ctypes.c_void_p
+        self.lib.orc_model_load.argtypes = [ctypes.c_char_p]
+        self.lib.orc_model_statecount.argtypes = [ctypes.c_void_p]
+        self.lib.orc_viterbi.restype = ctypes.c_int
+        self.lib.orc_viterbi.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 5
+        import tempfile
+        with tempfile.NamedTemporaryFile(suffix=".blob", delete=False) as f:
+            f.write(blob)
+            self._tmp = f.name
+        self.m = self.lib.orc_model_load(self._tmp.encode())
+        os.unlink(self._tmp)
+        assert self.m
+        self.S = self.lib.orc_model_statecount(self.m)
+
+    def viterbi(self, dna: str, gc=None, want_matrix=False):
+        L = len(dna)
+        V = np.zeros((L, self.S), dtype=np.int64) if want_matrix else None
+        gco = np.zeros(L, dtype=np.int32)
+        cap = L + 16
+        pt, pb, pe, ptr = (np.zeros(cap, dtype=np.int32) for _ in range(4))
+        lp = ctypes.c_double()
+        gci = None if gc is None else np.ascontiguousarray(gc, dtype=np.int32)
+        n = self.lib.orc_viterbi(self.m, dna.encode(), L, None if gci is None else gci.ctypes.data,
+                                 None if V is None else V.ctypes.data, gco.ctypes.data, cap,
+                                 pt.ctypes.data, pb.ctypes.data, pe.ctypes.data, ptr.ctypes.data, ctypes.byref(lp))
+        states = [(int(pt[k]), int(pb[k]), int(pe[k]), int(ptr[k])) for k in range(max(n, 0))]
+        return {"n": n, "states": states, "condensed": condense(states), "log_prob": lp.value, "gc": gco, "V": V}
+
+
+class HostEmu:
+    NCHAIN = 7
+
+    def __init__(self, blob: bytes):
+        srcs = ["tests/hostemu/hostemu.cc", "augustus_b200/csrc/ghmm_model.cc"]
+        hdrs = [os.path.join(ROOT, "augustus_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "augustus_b200", "csrc"))]
+        newest = max(os.path.getmtime(p) for p in hdrs + [os.path.join(ROOT, s) for s in srcs])
+        if not os.path.exists(HOSTEMU_SO) or os.path.getmtime(HOSTEMU_SO) < newest:
+            subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", HOSTEMU_SO] + srcs, cwd=ROOT, check=True)
+        self.lib = ctypes.CDLL(HOSTEMU_SO)
+        self.lib.hostemu_model_create.restype = ctypes.c_void_p
+        self.lib.hostemu_model_create.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_int]
+        self.lib.hostemu_decode.restype = ctypes.c_int
+        self.lib.hostemu_decode.argtypes = ([ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+                                            + [ctypes.c_void_p] * 6 + [ctypes.c_int] + [ctypes.c_void_p] * 6)
+        err = ctypes.create_string_buffer(512)
+        self.m = self.lib.hostemu_model_create(blob, len(blob), err, 512)
+        if not self.m:
+            raise RuntimeError(err.value.decode())
+
+    def decode(self, dna: str, gc=None, want_cells=False, S=47):
+        L = len(dna)
+        cap = L // 2 + 64
+        eb, ee = np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=np.int32)
+        et, etr = np.zeros(cap, dtype=np.uint8), np.zeros(cap, dtype=np.uint8)
+        lp, st, nev = ctypes.c_double(), ctypes.c_int32(), ctypes.c_int32()
+        evcap = 4 * L + 256
+        evc, evs = np.zeros(evcap, dtype=np.int32), np.zeros(evcap, dtype=np.int32)
+        evV = np.zeros(evcap, dtype=np.int64)
+        chV = np.zeros((L, self.NCHAIN), dtype=np.int64) if want_cells else None
+        gco = np.zeros(L, dtype=np.uint8)
+        gci = None if gc is None else np.ascontiguousarray(gc, dtype=np.int32)
+        n = self.lib.hostemu_decode(self.m, dna.encode(), L, None if gci is None else gci.ctypes.data, cap,
+                                    eb.ctypes.data, ee.ctypes.data, et.ctypes.data, etr.ctypes.data,
+                                    ctypes.byref(lp), ctypes.byref(st), evcap, evc.ctypes.data, evs.ctypes.data,
+                                    evV.ctypes.data, ctypes.byref(nev), None if chV is None else chV.ctypes.data, gco.ctypes.data)
+        res = {"n": n, "status": st.value, "log_prob": lp.value, "gc": gco,
+               "states": [(int(et[k]), int(eb[k]), int(ee[k]), int(etr[k])) for k in range(n)]}
+        if want_cells:
+            E = np.full((L, S), -(1 << 61), dtype=np.int64)
+            ne = nev.value
+            E[evc[:ne], evs[:ne]] = evV[:ne]
+            for c in range(self.NCHAIN):
+                s = self.lib.hostemu_chain_state(ctypes.c_void_p(self.m), c)
+                if s >= 0:
+                    E[:, s] = chV[:, c]
+            res["cells"] = E
+        return res
