@@ -55,7 +55,7 @@ struct augb200_model {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevBuf<sc_t> d_tab; DevBuf<DevModel> d_model;
     /* batch state */
-    DevBuf<char> d_arena; DevBuf<char> d_dna; DevBuf<uint8_t> d_gc; DevBuf<WinDev> d_wins; DevBuf<int> d_counters;
+    DevBuf<char> d_arena; DevBuf<char> d_pool; DevBuf<unsigned long long> d_pool_used; size_t pool_bytes = 0; DevBuf<char> d_dna; DevBuf<uint8_t> d_gc; DevBuf<WinDev> d_wins; DevBuf<int> d_counters;
     DevBuf<PackHdr> d_hdr; DevBuf<int32_t> d_obegin, d_oend; DevBuf<uint8_t> d_otype, d_otrunc;
     PinBuf<char> h_dna; PinBuf<uint8_t> h_gc; PinBuf<WinDev> h_wins; PinBuf<PackHdr> h_hdr; PinBuf<int> h_counters;
     PinBuf<int32_t> h_obegin, h_oend; PinBuf<uint8_t> h_otype, h_otrunc;
@@ -80,6 +80,16 @@ static int upload_windows(augb200_model* M, const augb200_window* w, const int* 
     if ((rc = M->d_dna.reserve(dna_bytes + 16))) return rc;
     if (gc_bytes) { if ((rc = M->h_gc.reserve(gc_bytes + 16))) return rc; if ((rc = M->d_gc.reserve(gc_bytes + 16))) return rc; }
     if ((rc = M->d_arena.reserve(arena))) return rc;
+    /* slab pool for the prefix arrays of second / third ... GC classes (first class lives in the window) */
+    {
+        size_t need = 0;
+        if (!generous && M->hm.dm.C > 1) for (int i = 0; i < count; i++) need += (size_t)(M->hm.dm.C - 1) * make_layout(w[idx[i]].length, M->hm.dm.C).slab;
+        size_t room = M->arena_budget > arena ? M->arena_budget - arena : 0;
+        size_t pool = std::min(need, room + M->arena_budget / 8);
+        if (pool && (rc = M->d_pool.reserve(pool))) return rc;
+        M->pool_bytes = pool;
+        if ((rc = M->d_pool_used.reserve(1))) return rc;
+    }
     if ((rc = M->h_wins.reserve(count))) return rc;
     if ((rc = M->d_wins.reserve(count))) return rc;
     size_t od = 0, og = 0, oa = 0; long total_path_cap = 0;
@@ -114,9 +124,10 @@ static int upload_windows(augb200_model* M, const augb200_window* w, const int* 
 
 static int run_kernels(augb200_model* M, int count) {
     CK(cudaMemsetAsync(M->d_counters.p, 0, 4 * sizeof(int), M->stream));
+    CK(cudaMemsetAsync(M->d_pool_used.p, 0, sizeof(unsigned long long), M->stream));
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, M->device);
     int gprep = std::min(count, sms * 8);
-    k_prep<<<gprep, PREP_BS, 0, M->stream>>>(M->d_model.p, M->d_wins.p, count);
+    k_prep<<<gprep, PREP_BS, 0, M->stream>>>(M->d_model.p, M->d_wins.p, count, M->pool_bytes ? M->d_pool.p : nullptr, (unsigned long long)M->pool_bytes, M->d_pool_used.p);
     CK(cudaEventRecord(M->ev0, M->stream));
     int gsweep = std::min((count + SWEEP_WARPS - 1) / SWEEP_WARPS, sms * 16);
     k_sweep<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(M->d_model.p, M->d_wins.p, count, M->d_counters.p);
@@ -196,7 +207,7 @@ int augb200_model_create(const void* blob, size_t nbytes, int device, augb200_mo
 void augb200_model_destroy(augb200_model* M) {
     if (!M) return;
     cudaSetDevice(M->device);
-    M->d_tab.release(); M->d_model.release(); M->d_arena.release(); M->d_dna.release(); M->d_gc.release(); M->d_wins.release(); M->d_counters.release();
+    M->d_tab.release(); M->d_model.release(); M->d_arena.release(); M->d_pool.release(); M->d_pool_used.release(); M->d_dna.release(); M->d_gc.release(); M->d_wins.release(); M->d_counters.release();
     M->d_hdr.release(); M->d_obegin.release(); M->d_oend.release(); M->d_otype.release(); M->d_otrunc.release();
     M->h_dna.release(); M->h_gc.release(); M->h_wins.release(); M->h_hdr.release(); M->h_counters.release();
     M->h_obegin.release(); M->h_oend.release(); M->h_otype.release(); M->h_otrunc.release();
@@ -233,7 +244,7 @@ int augb200_decode_batch(augb200_model* M, int32_t n, const augb200_window* w, a
             size_t bytes = 0; int count = 0;   /* greedy sub-batch under the arena budget */
             while (first + count < order.size()) {
                 size_t t = make_layout(w[order[first + count]].length, M->hm.dm.C, generous).total;
-                if (count && bytes + t > M->arena_budget) break;
+                if (count && bytes + t > M->arena_budget - M->arena_budget / 8) break;
                 bytes += t; count++;
             }
             if ((rc = upload_windows(M, w, order.data() + first, count, generous))) return rc;
@@ -256,7 +267,7 @@ int augb200_stage_batch(augb200_model* M, int32_t n, const augb200_window* w) {
     int rc = check_windows(n, w); if (rc) return rc;
     CK(cudaSetDevice(M->device));
     size_t bytes = 0; for (int i = 0; i < n; i++) bytes += make_layout(w[i].length, M->hm.dm.C).total;
-    if (bytes > M->arena_budget) return AUGB200_ERR_CAPACITY;
+    if (bytes > M->arena_budget - M->arena_budget / 8) return AUGB200_ERR_CAPACITY;
     std::vector<int> order(n);
     for (int i = 0; i < n; i++) order[i] = i;
     if ((rc = upload_windows(M, w, order.data(), n, false))) return rc;

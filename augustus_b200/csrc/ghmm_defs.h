@@ -12,9 +12,19 @@
 #if defined(__CUDACC__)
 #define AUGB_HD __host__ __device__ __forceinline__
 #define AUGB_D __device__ __forceinline__
+#define AUGB_DN __device__ __noinline__      /* large routines: one copy in the kernel (instruction-cache footprint) */
 #else
 #define AUGB_HD inline
 #define AUGB_D inline
+#define AUGB_DN inline
+#endif
+
+/* keep loops rolled: the sweep is instruction-fetch bound (one warp walks a long, branchy path per column), so
+ * static code size matters more than loop overhead */
+#if defined(__CUDACC__)
+#define AUGB_ROLLED _Pragma("unroll 1")
+#else
+#define AUGB_ROLLED
 #endif
 
 namespace augb {
@@ -24,13 +34,15 @@ constexpr int FRAC_BITS = 40;
 constexpr sc_t SC_NEG = -((sc_t)1 << 61);
 constexpr sc_t SC_NEGT = -((sc_t)1 << 60);
 AUGB_HD bool isneg(sc_t x) { return x <= SC_NEGT; }
-AUGB_HD int mod3(int k) { return k >= 0 ? k % 3 : (k % 3 + 3) % 3; }
+/* mod3 of types.hh:523 for |k| < 3*2^28: one unsigned remainder instead of two signed ones */
+AUGB_HD int mod3(int k) { return (int)((unsigned)(k + 3 * (1 << 28)) % 3u); }
 
 constexpr int MAXS = 96;      /* states */
 constexpr int MAXC = 8;       /* GC classes */
 constexpr int MAXANC = 8;
 constexpr int NCHAIN = 7;     /* igenic + 3 geometric + 3 reverse geometric */
 constexpr int WF_ALLN = 1 << 8;
+constexpr int WF_NOSLAB = 1 << 9;     /* the prefix-array pool ran out: decode this window again with the generous layout */
 
 /* reference StateType values (include/types.hh:492-512) used by the kernels */
 enum : int {
@@ -71,6 +83,7 @@ struct DevModel {
     int8_t chain_state[NCHAIN];            /* state index of each chain (-1 if absent) */
     /* role -> state index (-1 if absent) */
     int8_t r_longdss[2][3], r_lessd[2][3], r_equald[2][3], r_longass[2][3];      /* [0]=fwd [1]=rev */
+    int8_t xslot[16];          /* exon states in the slot order used by Sweep::process_column */
     int8_t r_single, r_initial[3], r_internal[3], r_terminal, r_rsingle, r_rinitial, r_rinternal[3], r_rterminal[3];
     /* tables (device pointers on the GPU, host pointers in the test emulator) */
     const sc_t *init, *term, *trans;                /* trans[(c*S + a)*S + s] */
@@ -89,11 +102,9 @@ struct DevModel {
 };
 
 /* one DP cell of a sparse (non-chain) state that is non-zero */
-struct Event {
-    int32_t col;
+struct Event {                  /* the column is implied by WinView::evstart */
     int16_t state, pred;
     int32_t predbase;
-    int32_t pad;
     sc_t V;
 };
 /* candidate list entry: a predecessor cell that later state ends look back to */
@@ -109,6 +120,9 @@ struct ChainCP {
     sc_t tilde;
 };
 
+/* per-column signal score arrays written by the prep pass (ghmm_signal.h) */
+enum : int { SG_DSSF = 0, SG_DSSR = 1, SG_ASSF = 2, SG_ASSR = 3, SG_XRS = 4, NSIG = 5 };
+
 /* candidate lists of a window */
 enum : int { CL_LD = 0 /* +f: longdss_f */, CL_RA = 3 /* +f: rlongass_f */, CL_LA = 6 /* +phase */, CL_RD = 9 /* +phase */, NCL = 12 };
 
@@ -118,7 +132,9 @@ struct WinView {
     const uint8_t* code;       /* 0..3, 4 = unknown */
     const uint8_t* gc;         /* class per position */
     const uint16_t* mask;
-    const sc_t* parr;          /* [c][PA_PER_CLASS][L+1] */
+    const uint16_t *kf, *kr;   /* (k+1)-mer code ending / reverse-complement code starting at each position, 0x8000 = invalid */
+    const sc_t* parr_c[MAXC];  /* per GC class present: [PA_PER_CLASS][L+1] (first class in the window, others from the slab pool) */
+    const sc_t* sig;           /* [NSIG][L] */
     const sc_t *AIG, *AGEO;    /* chain prefix arrays, [L] */
     const int32_t *nsf, *nsr;  /* nearestStopForward / Reverse (exonmodel.cc:101-156) */
     Event* ev; int32_t* evstart;

@@ -109,13 +109,16 @@ __device__ void block_stop_scan(const DevModel* m, const Seq& s, int32_t* out, i
 }
 
 /* ------------------------------------------------------------------ prep kernel: one CTA per window */
-__global__ void __launch_bounds__(PREP_BS) k_prep(const DevModel* __restrict__ m, const WinDev* __restrict__ wins, int nwin) {
+__global__ void __launch_bounds__(PREP_BS) k_prep(const DevModel* __restrict__ m, const WinDev* __restrict__ wins, int nwin,
+                                                  char* pool, unsigned long long pool_size, unsigned long long* pool_used) {
     __shared__ sc_t sm64[PREP_BS / 32 + 2];
     __shared__ int sm32[PREP_BS / 32 + 2];
     __shared__ Int3 sm3[PREP_BS / 32];
     __shared__ int s_classmask;
     __shared__ int s_anynuc;
     __shared__ int s_nruns;
+    __shared__ sc_t* s_slab[MAXC];
+    __shared__ int s_noslab;
     for (int wi = blockIdx.x; wi < nwin; wi += gridDim.x) {
         const WinDev wd = wins[wi];
         const int L = wd.L; char* base = wd.base; const WinLayout& lay = wd.lay;
@@ -126,6 +129,12 @@ __global__ void __launch_bounds__(PREP_BS) k_prep(const DevModel* __restrict__ m
         __syncthreads();
         const bool anynuc = s_anynuc != 0;
         Seq s; s.c = code; s.L = L;
+        {
+            uint16_t* kf = (uint16_t*)(base + lay.kf); uint16_t* kr = (uint16_t*)(base + lay.kr);
+            for (int p = threadIdx.x; p < L; p += PREP_BS) { kf[p] = kmer_code_f(s, p, m->k + 1); kr[p] = kmer_code_r(s, p, m->k + 1); }
+            __syncthreads();
+            s.kf = kf; s.kr = kr; s.k1 = m->k + 1;
+        }
         /* ---- GC classes: ContentStairs::computeStairs (motif.cc:543-614) ---- */
         if (wd.gc_in) {
             for (int i = threadIdx.x; i < L; i += PREP_BS) gc[i] = wd.gc_in[i];
@@ -184,12 +193,34 @@ __global__ void __launch_bounds__(PREP_BS) k_prep(const DevModel* __restrict__ m
         for (int j = threadIdx.x; j < L; j += PREP_BS) mask[j] = anynuc ? (uint16_t)column_mask(m, s, j) : 0;
         __syncthreads();
         const int cm = s_classmask | (anynuc ? 0 : WF_ALLN);
+        /* ---- signal scores of every column ---- */
+        {
+            sc_t* sg = (sc_t*)(base + lay.sig);
+            for (int idx = threadIdx.x; idx < NSIG * L; idx += PREP_BS) { int which = idx / L, j = idx - which * L; sg[idx] = anynuc ? signal_term(m, s, gc[j], which, j) : SC_NEG; }
+        }
         /* ---- prefix sums ---- */
-        sc_t* parr = (sc_t*)(base + lay.parr);
+        if (threadIdx.x == 0) {
+            /* slab of each class present: the first lay.nslab_local in the window, the rest from the batch pool */
+            int nloc = 0; s_noslab = 0;
+            WinOuts* wo = (WinOuts*)(base + lay.outs);
+            for (int c = 0; c < MAXC; c++) {
+                sc_t* slab = nullptr;
+                if (c < m->C && (cm >> c & 1)) {
+                    if (nloc < lay.nslab_local) slab = (sc_t*)(base + lay.parr + (size_t)nloc++ * lay.slab);
+                    else {
+                        unsigned long long off = atomicAdd(pool_used, (unsigned long long)lay.slab);
+                        if (pool && off + lay.slab <= pool_size) slab = (sc_t*)(pool + off); else s_noslab = 1;
+                    }
+                }
+                s_slab[c] = slab; wo->slab[c] = slab;
+            }
+        }
+        __syncthreads();
         for (int c = 0; c < m->C; c++) {
-            if (!(cm >> c & 1)) continue;
+            sc_t* slab = s_slab[c];
+            if (!slab) continue;
             for (int which = 0; which < PA_PER_CLASS; which++) {
-                sc_t* P = parr + ((size_t)c * PA_PER_CLASS + which) * (size_t)(L + 1);
+                sc_t* P = slab + (size_t)which * (size_t)(L + 1);
                 if (threadIdx.x == 0) P[0] = 0;
                 block_scan_gen<sc_t>([&](int p) { return parr_term(m, s, c, which, p); }, P + 1, L, (sc_t)0, sm64);
             }
@@ -205,7 +236,7 @@ __global__ void __launch_bounds__(PREP_BS) k_prep(const DevModel* __restrict__ m
         if (L >= 3) { block_stop_scan<false>(m, s, nsf, L, sm3); block_stop_scan<true>(m, s, nsr, L, sm3); }
         __syncthreads();
         if (threadIdx.x == 0 && L > 5) { nsf[L - 2] = nsf[L - 5]; nsf[L - 1] = nsf[L - 4]; nsr[L - 2] = nsr[L - 5]; nsr[L - 1] = nsr[L - 4]; }
-        if (threadIdx.x == 0) { WinOuts* o = (WinOuts*)(base + lay.outs); o->pad = cm; }
+        if (threadIdx.x == 0) { WinOuts* o = (WinOuts*)(base + lay.outs); o->pad = cm | (s_noslab ? WF_NOSLAB : 0); }
         __syncthreads();
     }
 }

@@ -184,6 +184,15 @@ int HostModel::build(const void* blob, size_t nbytes) {
         if (*slot >= 0) { err = "duplicate state role"; return AUGB200_ERR_UNSUPPORTED; }
         *slot = (int8_t)s;
     }
+    {
+        int q = 0;
+        m.xslot[q++] = m.r_single; m.xslot[q++] = m.r_terminal;
+        for (int f = 0; f < 3; f++) m.xslot[q++] = m.r_initial[f];
+        for (int f = 0; f < 3; f++) m.xslot[q++] = m.r_internal[f];
+        m.xslot[q++] = m.r_rsingle; m.xslot[q++] = m.r_rinitial;
+        for (int f = 0; f < 3; f++) m.xslot[q++] = m.r_rinternal[f];
+        for (int f = 0; f < 3; f++) m.xslot[q++] = m.r_rterminal[f];
+    }
     if (m.chain_state[0] < 0) { err = "model has no intergenic state"; return AUGB200_ERR_UNSUPPORTED; }
     /* topology the kernels rely on (config/model/trans_shadow_*.pbl); anything else is rejected, not approximated */
     auto kind_of = [&](int a) { return m.st[a].kind; };

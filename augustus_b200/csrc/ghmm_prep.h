@@ -13,19 +13,27 @@
  * parallel and scan with integer adds, so both produce identical arrays.
  */
 #pragma once
+#include <math.h>
 #include <stddef.h>
 #include "ghmm_defs.h"
 #include "ghmm_seq.h"
+#include "ghmm_signal.h"
 
 namespace augb {
 
+/* result / hand-over block of a window (WinLayout::outs) */
+struct WinOuts {
+    int32_t n_ev, status, path_n, path_status; int32_t ncp[NCHAIN]; int32_t pad /* window flags */; sc_t score;
+    const sc_t* slab[MAXC];     /* prefix-array slab of each GC class (set by prep) */
+};
+
 /* byte layout of one window's workspace; every section is 16-byte aligned */
 struct WinLayout {
-    size_t code, gc, mask, parr, aig, ageo, nsf, nsr;        /* static (prep) */
+    size_t code, gc, mask, kf, kr, parr, sig, aig, ageo, nsf, nsr;        /* static (prep) */
     size_t ev, evstart, cl[NCL], cp[NCHAIN], outs;           /* dynamic (sweep) */
     size_t path_begin, path_end, path_type, path_trunc;      /* backtrace output */
-    size_t total;
-    int ev_cap, cl_cap, cp_cap, path_cap;
+    size_t total, slab;
+    int ev_cap, cl_cap, cp_cap, path_cap, nslab_local;
 };
 AUGB_HD size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
 /* Capacities of the dynamic structures.  `generous` = provable upper bounds (every column can hold at most one
@@ -35,8 +43,13 @@ AUGB_HD size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
 inline WinLayout make_layout(int L, int C, bool generous = false) {
     WinLayout w; size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = al16(o + bytes); return r; };
-    w.code = take(L); w.gc = take(L); w.mask = take((size_t)L * 2);
-    w.parr = take((size_t)C * PA_PER_CLASS * (L + 1) * sizeof(sc_t));
+    w.code = take(L); w.gc = take(L); w.mask = take((size_t)L * 2); w.kf = take((size_t)L * 2); w.kr = take((size_t)L * 2);
+    /* prefix arrays: one slab (PA_PER_CLASS arrays) in the window for the first GC class present; further classes take
+     * slabs from a pool shared by the batch (generous layout: all C slabs in the window) */
+    w.slab = (size_t)PA_PER_CLASS * (L + 1) * sizeof(sc_t);
+    w.nslab_local = generous ? C : 1;
+    w.parr = take(w.slab * w.nslab_local);
+    w.sig = take((size_t)NSIG * L * sizeof(sc_t));
     w.aig = take((size_t)L * sizeof(sc_t)); w.ageo = take((size_t)L * sizeof(sc_t));
     w.nsf = take((size_t)(L + 3) * 4); w.nsr = take((size_t)(L + 3) * 4);
     if (generous) { w.ev_cap = 48 * L + 256; w.cl_cap = L + 64; w.cp_cap = L + 64; w.path_cap = L + 64; }
@@ -45,27 +58,32 @@ inline WinLayout make_layout(int L, int C, bool generous = false) {
     w.ev = take((size_t)w.ev_cap * sizeof(Event)); w.evstart = take((size_t)(L + 2) * 4);
     for (int i = 0; i < NCL; i++) w.cl[i] = take((size_t)w.cl_cap * sizeof(Cand));
     for (int i = 0; i < NCHAIN; i++) w.cp[i] = take((size_t)w.cp_cap * sizeof(ChainCP));
-    w.outs = take(64);
+    w.outs = take(sizeof(WinOuts));
     w.path_begin = take((size_t)w.path_cap * 4); w.path_end = take((size_t)w.path_cap * 4);
     w.path_type = take(w.path_cap); w.path_trunc = take(w.path_cap);
     w.total = al16(o);
     return w;
 }
-/* result block at WinLayout::outs */
-struct WinOuts { int32_t n_ev, status, path_n, path_status; int32_t ncp[NCHAIN]; int32_t pad /* window flags */; sc_t score; };
 
 AUGB_HD WinView make_view(char* base, const WinLayout& lay, int L, int classmask) {
     WinView v; v.L = L; v.nclassmask = classmask; v.ev_cap = lay.ev_cap; v.cl_cap = lay.cl_cap; v.cp_cap = lay.cp_cap;
     v.code = (const uint8_t*)(base + lay.code); v.gc = (const uint8_t*)(base + lay.gc); v.mask = (const uint16_t*)(base + lay.mask);
-    v.parr = (const sc_t*)(base + lay.parr); v.AIG = (const sc_t*)(base + lay.aig); v.AGEO = (const sc_t*)(base + lay.ageo);
+    v.kf = (const uint16_t*)(base + lay.kf); v.kr = (const uint16_t*)(base + lay.kr);
+    v.sig = (const sc_t*)(base + lay.sig); v.AIG = (const sc_t*)(base + lay.aig); v.AGEO = (const sc_t*)(base + lay.ageo);
     v.nsf = (const int32_t*)(base + lay.nsf); v.nsr = (const int32_t*)(base + lay.nsr);
     v.ev = (Event*)(base + lay.ev); v.evstart = (int32_t*)(base + lay.evstart);
     for (int i = 0; i < NCL; i++) v.cl[i] = (Cand*)(base + lay.cl[i]);
     for (int i = 0; i < NCHAIN; i++) v.cp[i] = (ChainCP*)(base + lay.cp[i]);
     WinOuts* o = (WinOuts*)(base + lay.outs);
     v.out_n_ev = &o->n_ev; v.out_status = &o->status; v.out_ncp = o->ncp; v.flags = &o->pad;
+    for (int c = 0; c < MAXC; c++) v.parr_c[c] = o->slab[c];      /* valid once prep has run */
     return v;
 }
+
+/* (k+1)-mer codes of a position: forward code of the k+1 bases ENDING at p, reverse-complement code of the
+ * k+1 bases STARTING at p (Seq2Int::operator() / ::rc, geneticcode.hh:166-179); 0x8000 = not all acgt / off the end */
+AUGB_HD uint16_t kmer_code_f(const Seq& s, int p, int k1) { int v = s.s2i(p - k1 + 1, k1); return v < 0 ? (uint16_t)0x8000 : (uint16_t)v; }
+AUGB_HD uint16_t kmer_code_r(const Seq& s, int p, int k1) { int v = s.s2irc(p, k1); return v < 0 ? (uint16_t)0x8000 : (uint16_t)v; }
 
 AUGB_HD uint8_t base_code(char ch) {
     switch (ch) {
@@ -141,7 +159,8 @@ AUGB_HD sc_t parr_term(const DevModel* m, const Seq& s, int c, int which, int p)
 }
 
 /* sequential host builder (test emulator) */
-inline void prep_window_seq(const DevModel* m, const char* dna, int L, const int32_t* gc_in, char* base, const WinLayout& lay, int* classmask) {
+inline void prep_window_seq(const DevModel* m, const char* dna, int L, const int32_t* gc_in, char* base, const WinLayout& lay, int* classmask,
+                            char* pool = nullptr, size_t pool_size = 0, size_t* pool_used = nullptr) {
     uint8_t* code = (uint8_t*)(base + lay.code); uint8_t* gc = (uint8_t*)(base + lay.gc); uint16_t* mask = (uint16_t*)(base + lay.mask);
     for (int i = 0; i < L; i++) code[i] = base_code(dna[i]);
     if (gc_in) for (int i = 0; i < L; i++) gc[i] = (uint8_t)gc_in[i]; else gc_stairs_seq(m, code, L, gc);
@@ -151,12 +170,29 @@ inline void prep_window_seq(const DevModel* m, const char* dna, int L, const int
     *classmask = cm;
     ((WinOuts*)(base + lay.outs))->pad = cm;
     Seq s; s.c = code; s.L = L;
+    {
+        uint16_t* kf = (uint16_t*)(base + lay.kf); uint16_t* kr = (uint16_t*)(base + lay.kr);
+        for (int p = 0; p < L; p++) { kf[p] = kmer_code_f(s, p, m->k + 1); kr[p] = kmer_code_r(s, p, m->k + 1); }
+        s.kf = kf; s.kr = kr; s.k1 = m->k + 1;
+    }
     for (int j = 0; j < L; j++) mask[j] = anynuc ? (uint16_t)column_mask(m, s, j) : 0;
-    sc_t* parr = (sc_t*)(base + lay.parr);
+    {
+        sc_t* sg = (sc_t*)(base + lay.sig);
+        for (int which = 0; which < NSIG; which++)
+            for (int j = 0; j < L; j++) sg[(size_t)which * L + j] = anynuc ? signal_term(m, s, gc[j], which, j) : SC_NEG;
+    }
+    WinOuts* wo = (WinOuts*)(base + lay.outs);
+    int nloc = 0;
     for (int c = 0; c < m->C; c++) {
+        wo->slab[c] = nullptr;
         if (!(cm >> c & 1)) continue;
+        sc_t* slab;
+        if (nloc < lay.nslab_local) slab = (sc_t*)(base + lay.parr + (size_t)nloc++ * lay.slab);
+        else if (pool && *pool_used + lay.slab <= pool_size) { slab = (sc_t*)(pool + *pool_used); *pool_used += lay.slab; }
+        else { wo->pad |= WF_NOSLAB; *classmask |= WF_NOSLAB; continue; }
+        wo->slab[c] = slab;
         for (int which = 0; which < PA_PER_CLASS; which++) {
-            sc_t* P = parr + ((size_t)c * PA_PER_CLASS + which) * (size_t)(L + 1);
+            sc_t* P = slab + (size_t)which * (size_t)(L + 1);
             P[0] = 0;
             for (int p = 0; p < L; p++) P[p + 1] = P[p] + parr_term(m, s, c, which, p);
         }

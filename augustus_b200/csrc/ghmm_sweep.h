@@ -24,6 +24,7 @@
 #pragma once
 #include "ghmm_defs.h"
 #include "ghmm_seq.h"
+#include "ghmm_signal.h"
 #include "ghmm_warp.h"
 
 namespace augb {
@@ -38,13 +39,16 @@ struct WarpState {
     sc_t pend_val[NCHAIN];
     int pend_pred[NCHAIN];
     int status;
+    int any_pend;
 };
 
 struct Sweep {
     const DevModel* m; WinView w; WarpState* ws; Seq sq; int lane; int cls; int L;
+    const sc_t* trc;            /* transition matrix of the current column's GC class */
 
-    AUGB_D const sc_t* parr(int c, int which) const { return w.parr + ((size_t)c * PA_PER_CLASS + which) * (size_t)(L + 1); }
-    AUGB_D sc_t TR(int a, int s) const { return m->trans[((size_t)cls * m->S + a) * m->S + s]; }
+    AUGB_D const sc_t* parr(int c, int which) const { return w.parr_c[c] + (size_t)which * (size_t)(L + 1); }
+    AUGB_D sc_t TR(int a, int s) const { return trc[a * m->S + s]; }
+    AUGB_D void set_class(int c) { cls = c; trc = m->trans + (size_t)c * m->S * m->S; }
 
     /* ------------------------------------------------------------ chains */
     AUGB_D const sc_t* chainA(int ch) const { return ch == 0 ? w.AIG : w.AGEO; }
@@ -56,6 +60,7 @@ struct Sweep {
         int lo = 0, hi = n - 1;          /* invariant: cp[lo].col <= e (cp[0].col is the first entry column) */
         if (cp[0].col > e) return SC_NEG;
         if (cp[hi].col <= e) lo = hi;
+        AUGB_ROLLED
         while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (cp[mid].col <= e) lo = mid; else hi = mid - 1; }
         return cp[lo].tilde + chainA(ch)[e];
     }
@@ -64,6 +69,7 @@ struct Sweep {
         int ch = m->st[a].chain;
         if (ch >= 0) return chain_value(ch, e);
         int lo = w.evstart[e], hi = w.evstart[e + 1];
+        AUGB_ROLLED
         for (int i = lo; i < hi; i++) if (w.ev[i].state == a) return w.ev[i].V;
         return SC_NEG;
     }
@@ -71,131 +77,73 @@ struct Sweep {
     /* ------------------------------------------------------------ bookkeeping */
     AUGB_D void fill_evstart(int upto) {
         int f = ws->filled, n = ws->n_ev;
+        AUGB_ROLLED
         for (int i = f + 1 + lane; i <= upto; i += AUGB_NLANES) w.evstart[i] = n;
         wsync();
         if (lane == 0) ws->filled = upto;
         wsync();
     }
-    AUGB_D void cl_append(int list, int col, int state, sc_t V) {
+    AUGB_D void cl_append(int list, int col, int state, sc_t V) {       /* lane 0 only; caller syncs */
         int n = ws->cl_n[list];
-        if (n >= w.cl_cap) { if (lane == 0) ws->status = 8; wsync(); return; }
-        if (lane == 0) { Cand c; c.col = col; c.state = state; c.V = V; w.cl[list][n] = c; ws->cl_n[list] = n + 1; }
-        wsync();
+        if (n >= w.cl_cap) { ws->status = 8; return; }
+        Cand c; c.col = col; c.state = state; c.V = V; w.cl[list][n] = c; ws->cl_n[list] = n + 1;
     }
-    /* record a non-zero cell; route it to the structures later columns look back to */
+    /* record a non-zero cell; route it to the structures later columns look back to.  All lanes hold the same
+     * arguments; lane 0 writes, one warp sync publishes. */
     AUGB_D void emit(int j, int s, sc_t V, int pred, int predbase) {
-        int n = ws->n_ev;
-        if (n >= w.ev_cap) { if (lane == 0) ws->status = 8; wsync(); return; }
         if (lane == 0) {
-            Event e; e.col = j; e.state = (int16_t)s; e.pred = (int16_t)pred; e.predbase = predbase; e.pad = 0; e.V = V;
-            w.ev[n] = e; ws->n_ev = n + 1;
-        }
-        wsync();
-        const StateDesc& sd = m->st[s];
-        if (sd.kind == K_LONGDSS) {
-            if (sd.fwd) cl_append(CL_LD + sd.frame, j, s, V);
-            else cl_append(CL_RD + mod3(sd.frame + j - 2 + 3 - m->dss_start), j, s, V);   /* phase = mod3(pf + bobe), bobe = j+1-dss_start */
-        } else if (sd.kind == K_LONGASS) {
-            if (sd.fwd) cl_append(CL_LA + mod3(sd.frame - (j + 1 - m->ass_end)), j, s, V);   /* phase = mod3(pf - bobe) */
-            else cl_append(CL_RA + sd.frame, j, s, V);
-        }
-        int ch = sd.feeds;
-        if (ch >= 0 && j + 1 < L) {
-            /* candidate for V[j+1][chain] in tilde coordinates */
-            int c1 = w.gc[j + 1], cs = m->chain_state[ch];
-            sc_t t_in = m->trans[((size_t)c1 * m->S + s) * m->S + cs], t_self = m->trans[((size_t)c1 * m->S + cs) * m->S + cs];
-            if (!isneg(t_in)) {
-                sc_t val = V + t_in - t_self - chainA(ch)[j];
-                if (lane == 0 && (val > ws->pend_val[ch] || (val == ws->pend_val[ch] && s < ws->pend_pred[ch]))) {
-                    ws->pend_val[ch] = val; ws->pend_pred[ch] = s;
+            int n = ws->n_ev;
+            if (n >= w.ev_cap) ws->status = 8;
+            else {
+                Event e; e.state = (int16_t)s; e.pred = (int16_t)pred; e.predbase = predbase; e.V = V;
+                w.ev[n] = e; ws->n_ev = n + 1;
+                const StateDesc& sd = m->st[s];
+                if (sd.kind == K_LONGDSS) {
+                    if (sd.fwd) cl_append(CL_LD + sd.frame, j, s, V);
+                    else cl_append(CL_RD + mod3(sd.frame + j + 1 - m->dss_start), j, s, V);      /* phase = mod3(pf + bobe), bobe = j+1-dss_start */
+                } else if (sd.kind == K_LONGASS) {
+                    if (sd.fwd) cl_append(CL_LA + mod3(sd.frame - (j + 1 - m->ass_end)), j, s, V);   /* phase = mod3(pf - bobe) */
+                    else cl_append(CL_RA + sd.frame, j, s, V);
                 }
-                wsync();
+                int ch = sd.feeds;
+                if (ch >= 0 && j + 1 < L) {
+                    /* candidate for V[j+1][chain] in tilde coordinates */
+                    int c1 = w.gc[j + 1], cs = m->chain_state[ch];
+                    const sc_t* T1 = m->trans + (size_t)c1 * m->S * m->S;
+                    sc_t t_in = T1[s * m->S + cs], t_self = T1[cs * m->S + cs];
+                    if (!isneg(t_in)) {
+                        sc_t val = V + t_in - t_self - chainA(ch)[j];
+                        if (val > ws->pend_val[ch] || (val == ws->pend_val[ch] && s < ws->pend_pred[ch])) { ws->pend_val[ch] = val; ws->pend_pred[ch] = s; ws->any_pend = 1; }
+                    }
+                }
             }
         }
+        wsync();
     }
     /* end of column j: apply the pending chain entries for column j+1 (ancestors in index order, strict >) */
     AUGB_D void apply_pending(int j) {
-        for (int ch = 0; ch < NCHAIN; ch++) {
-            sc_t pv = ws->pend_val[ch];
-            if (isneg(pv)) continue;
-            int pp = ws->pend_pred[ch], self = m->chain_state[ch];
-            sc_t cur = ws->tilde[ch];
-            bool take = pv > cur || (pv == cur && pp < self);
-            int n = ws->cp_n[ch];
-            if (take && n >= w.cp_cap) { if (lane == 0) ws->status = 8; take = false; }
-            wsync();
-            if (lane == 0) {
+        if (!ws->any_pend) return;
+        if (lane == 0) {
+            AUGB_ROLLED
+            for (int ch = 0; ch < NCHAIN; ch++) {
+                sc_t pv = ws->pend_val[ch];
+                if (isneg(pv)) continue;
+                int pp = ws->pend_pred[ch], self = m->chain_state[ch];
+                sc_t cur = ws->tilde[ch];
+                bool take = pv > cur || (pv == cur && pp < self);
+                int n = ws->cp_n[ch];
+                if (take && n >= w.cp_cap) { ws->status = 8; take = false; }
                 if (take) { ChainCP c; c.col = j + 1; c.pred = pp; c.tilde = pv; w.cp[ch][n] = c; ws->cp_n[ch] = n + 1; ws->tilde[ch] = pv; }
                 ws->pend_val[ch] = SC_NEG; ws->pend_pred[ch] = 0x7fffffff;
             }
-            wsync();
+            ws->any_pend = 0;
         }
+        wsync();
     }
 
-    /* ------------------------------------------------------------ signal scores */
-    /* Motif::seqProb (motif.cc:308-331), lanes over motif positions */
-    AUGB_D sc_t motif_fwd(const sc_t* tab, int n, int k, int p) const {
-        sc_t s = 0; const size_t wd = (size_t)1 << (2 * (k + 1));
-        for (int i = lane; i < n; i += AUGB_NLANES) { int pn = sq.s2i(p + i - k, k + 1); s += pn < 0 ? m->log025 : tab[((size_t)cls * n + i) * wd + pn]; }
-        return wsum(s);
-    }
-    AUGB_D sc_t motif_rc(const sc_t* tab, int n, int k, int p) const {
-        sc_t s = 0; const size_t wd = (size_t)1 << (2 * (k + 1));
-        for (int i = lane; i < n; i += AUGB_NLANES) { int pn = sq.s2irc(p + i, k + 1); s += pn < 0 ? m->log025 : tab[((size_t)cls * n + (n - 1 - i)) * wd + pn]; }
-        return wsum(s);
-    }
-    /* the same, evaluated by one lane alone (inside per-candidate code) */
-    AUGB_D sc_t motif_fwd1(const sc_t* tab, int n, int k, int p) const {
-        sc_t s = 0; const size_t wd = (size_t)1 << (2 * (k + 1));
-        for (int i = 0; i < n; i++) { int pn = sq.s2i(p + i - k, k + 1); s += pn < 0 ? m->log025 : tab[((size_t)cls * n + i) * wd + pn]; }
-        return s;
-    }
-    /* IntronModel::dSSProb (intronmodel.cc:1195-1248) */
-    AUGB_D sc_t dSSProb(int base, int fwd) const {
-        int nonGT, idx;
-        if (fwd) {
-            int dsspos = base + m->dss_start;
-            if (!possDSS(m, sq, dsspos)) return SC_NEG;
-            nonGT = !sq.is2(dsspos, G_, T_);
-            int a = sq.s2i(base, m->dss_start), b = sq.s2i(dsspos + 2, m->dss_end);
-            if (a < 0 || b < 0) return SC_NEG;
-            idx = (a << (2 * m->dss_end)) | b;
-        } else {
-            int dsspos = base + m->dss_end;
-            if (!possRDSS(m, sq, dsspos + 1)) return SC_NEG;
-            nonGT = !sq.is2(dsspos, A_, C_);
-            int a = 0, b = 0;
-            for (int i = m->dss_start - 1; i >= 0; i--) { int c = sq.at(dsspos + 2 + i); if (c > 3) return SC_NEG; a = (a << 2) | (3 - c); }
-            for (int i = m->dss_end - 1; i >= 0; i--) { int c = sq.at(base + i); if (c > 3) return SC_NEG; b = (b << 2) | (3 - c); }
-            idx = (a << (2 * m->dss_end)) | b;
-        }
-        return nonGT ? m->dss_pat_non[idx] : m->dss_pat[idx];
-    }
-    /* IntronModel::aSSProb (intronmodel.cc:1116-1188); warp-cooperative (motif over lanes) */
-    AUGB_D sc_t aSSProb(int base, int fwd) const {
-        int nonAG, a, b; sc_t motif;
-        if (fwd) {
-            int asspos = base + m->ass_up + m->ass_start;
-            if (!possASS(sq, asspos + 1)) return SC_NEG;
-            nonAG = !sq.is2(asspos, A_, G_);
-            a = sq.s2i(base + m->ass_up, m->ass_start); b = sq.s2i(asspos + 2, m->ass_end);
-            motif = base >= m->assm_k ? motif_fwd(m->assm, m->assm_n, m->assm_k, base) : SC_NEG;
-        } else {
-            int asspos = base + m->ass_end;
-            if (!possRASS(sq, asspos)) return SC_NEG;
-            nonAG = !sq.is2(asspos, C_, T_);
-            a = 0; b = 0;
-            for (int i = m->ass_start - 1; i >= 0; i--) { int c = sq.at(asspos + 2 + i); if (c > 3) { a = -1; break; } a = (a << 2) | (3 - c); }
-            for (int i = m->ass_end - 1; i >= 0; i--) { int c = sq.at(base + i); if (c > 3) { b = -1; break; } b = (b << 2) | (3 - c); }
-            int motifstart = base + m->ass_start + m->ass_end + 2, motifend = motifstart + m->ass_up;
-            motif = motifend + m->assm_k < L ? motif_rc(m->assm, m->assm_n, m->assm_k, motifstart) : (sc_t)m->ass_up * m->log025;
-        }
-        sc_t pat;
-        if (a < 0 || b < 0) pat = m->ass_invalid_pat;
-        else { int idx = (a << (2 * m->ass_end)) | b; pat = nonAG ? m->ass_pat_non[idx] : m->ass_pat[idx]; }
-        if (isneg(motif) || isneg(pat)) return SC_NEG;
-        return motif + pat;
-    }
+    /* ------------------------------------------------------------ signal scores (tabulated by the prep pass) */
+    AUGB_D sc_t sig(int which, int j) const { return w.sig[(size_t)which * L + j]; }
+    AUGB_DN sc_t motif_fwd1(const sc_t* tab, int n, int k, int p) const { return motif_fwd(m, sq, cls, tab, n, k, p); }
 
     /* ------------------------------------------------------------ ORF, exonmodel.cc:165-198 */
     AUGB_D int leftmostExonBegin(int frame, int base, int forward) const {
@@ -217,6 +165,7 @@ struct Sweep {
     }
     AUGB_D sc_t exon_shortProb(const sc_t* tab, int fwd, int left, int right, int frameOfRight) const {   /* :1979-2034 */
         sc_t s = 0;
+        AUGB_ROLLED
         for (int p = right; p >= left; p--) {
             int f = fwd ? mod3(frameOfRight - right + p) : mod3(frameOfRight + right - p);
             s += exon_emi1(m, sq, tab, cls, fwd, f, p);
@@ -235,16 +184,7 @@ struct Sweep {
             if (a == T_ && b == G_ && c == A_) return m->opal;
             return SC_NEG;
         }
-        case E_RSINGLE: case E_RINITIAL: {
-            int sp = end - m->tiw - 3 + 1;
-            if (sp < 0) return SC_NEG;
-            int pn = sq.s2irc(sp, 3);
-            if (pn < 0 || isneg(m->startp[pn])) return SC_NEG;
-            sc_t p = m->startp[pn];
-            if (sp + 3 + m->tiw - 1 + m->tis_k < L) p += motif_rc(m->tis, m->tis_n, m->tis_k, sp + 3);
-            else p = (sc_t)(L - (sp + 3)) * m->log025;
-            return p;
-        }
+        case E_RSINGLE: case E_RINITIAL: return sig(SG_XRS, end);
         case E_INITIAL: case E_INTERNAL: {
             int dsspos = end + m->dss_start + 1;
             if (end == L - 1) return 0;
@@ -261,14 +201,14 @@ struct Sweep {
         }
     }
     /* ExonModel::notEndPartEmiProb (exonmodel.cc:1417-1859), no hints; evaluated by one lane per candidate */
-    AUGB_D sc_t notEndPart(const StateDesc& st, int bos, int right, int frameOfRight) const {
+    AUGB_DN sc_t notEndPart(const StateDesc& st, int bos, int right, int frameOfRight) const {
         const int k = m->k, fwd = st.fwd, win = st.frame;
         sc_t beginPart;
         int bobe = bos - st.innerPartOffset;
         switch (st.ek) {
         case E_SINGLE: case E_INITIAL: {
             if (!(bobe >= 0 && bobe < L - 2)) return SC_NEG;
-            int pn = sq.s2i(bobe, 3);
+            int pn = sq.kmer_end(bobe + 2, 3);
             if (pn < 0 || isneg(m->startp[pn])) return SC_NEG;
             beginPart = m->startp[pn];
             int tis = bobe - m->tiw;
@@ -300,14 +240,14 @@ struct Sweep {
         if (bos > right) rest = -(sc_t)(bos - right - 1) * m->log025;
         else if (right - bos <= k) {
             int l = right - bos;
-            int pn = fwd ? sq.s2i(bos, l + 1) : sq.s2irc(bos, l + 1);
+            int pn = fwd ? sq.kmer_end(bos + l, l + 1) : sq.kmer_rc(bos, l + 1);
             if (pn < 0) rest = (sc_t)(l + 1) * m->probN;
             else { int f = fwd ? frameOfRight : mod3(frameOfRight + right - bos); rest = m->xpls[l][(((size_t)cls * 3 + f) << (2 * (l + 1))) | pn]; }
         } else {
             int endOfStart = bos + k - 1, beginOfInitP = right - (k - 1);
             if (k == 0) rest = 0;
             else {
-                int pn = fwd ? sq.s2i(bos, k) : sq.s2irc(beginOfInitP, k);
+                int pn = fwd ? sq.kmer_end(bos + k - 1, k) : sq.kmer_rc(beginOfInitP, k);
                 if (pn < 0) rest = (sc_t)k * m->probN;
                 else {
                     int f = fwd ? mod3(frameOfRight - right + endOfStart) : mod3(frameOfRight + right - beginOfInitP);
@@ -376,96 +316,184 @@ struct Sweep {
         return beginPart + rest + (m->log3 + lp);
     }
 
-    /* ExonModel::viterbiForwardAndSampling (exonmodel.cc:899-1179) for state s ending at column j */
+    /* begin part x initial pattern x initial content of a forward initial / single exon whose start codon is at bobe,
+     * when the inner sequence is long enough for all three (exonmodel.cc:1427-1462, 1596-1603, 1611-1633); df = frameOfRight - right */
+    AUGB_DN sc_t begin_score(int bobe, int df) const {
+        const int k = m->k, bos = bobe + 3;
+        int pn = sq.kmer_end(bobe + 2, 3);
+        if (pn < 0 || isneg(m->startp[pn]) || !(bobe >= 0 && bobe < L - 2)) return SC_NEG;
+        sc_t v = m->startp[pn];
+        int tis = bobe - m->tiw;
+        if (tis > m->tis_k) v += motif_fwd(m, sq, cls, m->tis, m->tis_n, m->tis_k, tis);
+        else v += (sc_t)(bos - 3) * m->log025;
+        const int endOfStart = bos + k - 1;
+        int p4 = sq.kmer_end(endOfStart, k);
+        v += p4 < 0 ? (sc_t)k * m->probN : m->xpls[k - 1][(((size_t)cls * 3 + mod3(df + endOfStart)) << (2 * k)) | p4];
+        const int endOfInitial = endOfStart + m->init_len;
+        return v + exon_shortProb(m->xinit, 1, endOfStart + 1, endOfInitial, mod3(df + endOfInitial));
+    }
+
+    /* ExonModel::viterbiForwardAndSampling (exonmodel.cc:899-1179) for state s ending at column j.
+     *
+     * The duration loop of the reference (beginOfStart = startMax .. startMin, exonmodel.cc:1059) becomes one
+     * candidate stream, 32 candidates per warp step:
+     *   internal / terminal / rinternal / rinitial : the longass_f / rlongdss_f cells of the matching reading-frame phase
+     *   initial / single                           : in-frame start codons, found by scanning the ORF in steps of 3
+     *   rterminal / rsingle                        : the one position behind the nearest in-frame reverse stop
+     * A candidate whose inner sequence is long enough that every sub-model of notEndPartEmiProb applies in full
+     * (the overwhelmingly common case) is scored by the closed form
+     *     begin-signal + P_ls start pattern + content prefix difference + terminal part + 3*lenDist
+     * whose end-dependent terms are computed once per exon end; shorter ones go through the general routine. */
     AUGB_D void exon_eval(int s, int j) {
-        const StateDesc& st = m->st[s]; const int fwd = st.fwd, win = st.frame;
+        const StateDesc& st = m->st[s]; const int fwd = st.fwd, win = st.frame, ek = st.ek, k = m->k;
         sc_t ep = endPart(st, j);
-        int eobe = j + st.baseOffset, right = eobe - st.innerPartEndOffset;
+        const int eobe = j + st.baseOffset, right = eobe - st.innerPartEndOffset;
         if (isneg(ep) || right < 0) return;
-        int frameOfRight = fwd ? mod3(win - (eobe + 1) + right) : mod3(win + eobe + 1 - right);
-        int eons = (st.ek == E_TERMINAL || st.ek == E_SINGLE) ? eobe - 3 : eobe;
+        const int frameOfRight = fwd ? mod3(win - (eobe + 1) + right) : mod3(win + eobe + 1 - right);
+        int eons = (ek == E_TERMINAL || ek == E_SINGLE) ? eobe - 3 : eobe;
         if (eons > L - 1) eons = L - 1;
-        int feons = fwd ? mod3(win - 1 - eobe + eons) : mod3(win + 1 + eobe - eons);
-        int ORFleft = leftmostExonBegin(feons, eons, fwd);
+        const int feons = fwd ? mod3(win - 1 - eobe + eons) : mod3(win + 1 + eobe - eons);
+        const int ORFleft = leftmostExonBegin(feons, eons, fwd);
         int startMax = eobe + st.innerPartOffset - m->min_exon_length + 1, startMin;
-        if (st.ek == E_RTERMINAL || st.ek == E_RSINGLE) startMin = startMax = ORFleft + 2;
+        if (ek == E_RTERMINAL || ek == E_RSINGLE) startMin = startMax = ORFleft + 2;
         else {
             startMin = ORFleft <= 0 ? 0 : ORFleft + st.innerPartOffset;
             if (startMax > j + st.beginPartLen) startMax = j + st.beginPartLen;
         }
-        /* per-lane best */
-        sc_t best = SC_NEG; int bkey = -0x7fffffff, bpred = -1, bbase = -1;
-        #define AUGB_CONSIDER(score_, bos_, a_, eop_) do { sc_t sc__ = (score_); int key__ = (bos_) * 128 + (127 - (a_)); \
-            if (sc__ > best || (sc__ == best && key__ > bkey)) { best = sc__; bkey = key__; bpred = (a_); bbase = (eop_); } } while (0)
-        if (st.ek == E_INTERNAL || st.ek == E_TERMINAL || st.ek == E_RINTERNAL || st.ek == E_RINITIAL) {
-            /* predecessors are longass_f (fwd) / rlongdss_f (rev) cells, kept per reading-frame phase */
-            int list = fwd ? CL_LA + mod3(win - eobe - 1) : CL_RD + mod3(win + eobe + 1);
-            const Cand* cl = w.cl[list]; int n = ws->cl_n[list];
-            int lo = startMin < 1 ? 1 : startMin;
-            bool done = false;
-            for (int base_i = n - 1; base_i >= 0 && !done; base_i -= AUGB_NLANES) {
-                int i = base_i - lane; bool below = false;
-                if (i >= 0) {
-                    Cand c = cl[i]; int bos = c.col + 1;
-                    if (bos < lo) below = true;
-                    else if (bos <= startMax && c.col < j) {
-                        sc_t nep = notEndPart(st, bos, right, frameOfRight);
-                        if (!isneg(nep)) {
-                            int bobe = bos - st.innerPartOffset, len = eobe - bobe + 1, pf = m->st[c.state].frame;
-                            sc_t t = TR(c.state, s);
-                            if (!isneg(t) && win == mod3(fwd ? pf + len : pf - len)) AUGB_CONSIDER(c.V + (t + ep + nep), bos, c.state, c.col);
-                        }
-                    }
-                } else below = true;
-                done = wballot(below) != 0;
-            }
-            if (startMin == 0 && lane == 0) {      /* left-truncated exon: bos = 0 reads column 0 (exonmodel.cc:1067-1068) */
-                sc_t nep = notEndPart(st, 0, right, frameOfRight);
-                if (!isneg(nep)) {
-                    int bobe = 0 - st.innerPartOffset, len = eobe - bobe + 1;
-                    for (int i = 0; i < st.nanc; i++) {
-                        int a = st.anc[i]; sc_t pv = m->init[a], t = TR(a, s); int pf = m->st[a].frame;
-                        if (isneg(pv) || isneg(t)) continue;
-                        if (win == mod3(fwd ? pf + len : pf - len)) AUGB_CONSIDER(pv + (t + ep + nep), 0, a, -1);
-                    }
+        /* ---- end-dependent terms of the closed forms (uniform over lanes) ---- */
+        const int thr = k + m->init_len + m->et_len + 2;          /* inner length from which every sub-model applies in full */
+        const bool listkind = ek == E_INTERNAL || ek == E_TERMINAL || ek == E_RINTERNAL || ek == E_RINITIAL;
+        const bool scankind = ek == E_INITIAL || ek == E_SINGLE;
+        const sc_t* PXp = fwd ? parr(cls, PA_PX + mod3(frameOfRight - right)) : parr(cls, PA_PXR + mod3(frameOfRight + right));
+        const sc_t* ldtab = (ek == E_INTERNAL || ek == E_RINTERNAL) ? m->ld_internal : ek == E_TERMINAL ? m->ld_terminal
+                          : (ek == E_SINGLE || ek == E_RSINGLE) ? m->ld_single : ek == E_RTERMINAL ? m->ld_terminal : m->ld_initial;
+        const int etmin = k + m->et_len - 2;                      /* the exon-terminal part applies iff right - bos > etmin */
+        sc_t endc = 0; int pxhi = right + 1;                      /* closed form = cand terms + PXp[pxhi] - PXp[lo(bos)] + endc */
+        if (k >= 1 && right - k >= 0) {
+            if (ek == E_INTERNAL || ek == E_INITIAL) {
+                if (right - m->et_len + 1 >= 0) { pxhi = right - m->et_len + 1; endc = exon_shortProb(m->xet, 1, right - m->et_len + 1, right, frameOfRight); }
+            } else if (!fwd && ek != E_RTERMINAL && ek != E_RSINGLE) {
+                const int beginOfInitP = right - (k - 1);
+                int pn = sq.kmer_rc(beginOfInitP, k);
+                endc = pn < 0 ? (sc_t)k * m->probN : m->xpls[k - 1][(((size_t)cls * 3 + mod3(frameOfRight + right - beginOfInitP)) << (2 * k)) | pn];
+                pxhi = beginOfInitP;
+                if (ek == E_RINITIAL && beginOfInitP - m->init_len >= 0) {
+                    const int beginOfInitial = beginOfInitP - m->init_len;
+                    pxhi = beginOfInitial;
+                    endc += exon_shortProb(m->xinit, 0, beginOfInitial, beginOfInitP - 1, mod3(frameOfRight + right - (beginOfInitP - 1)));
                 }
-            }
-        } else if (st.ek == E_INITIAL || st.ek == E_SINGLE) {
-            /* predecessor igenic; the length must satisfy len % 3 == win (0 for single): step 3 over bos */
-            int a = st.anc[0]; sc_t t = TR(a, s);
-            int want = mod3(eobe + 1 - (st.ek == E_SINGLE ? 0 : win));          /* bobe mod 3 */
-            int b0 = startMax; while (mod3(b0 - st.innerPartOffset) != want) b0--;
-            if (!isneg(t))
-                for (int bos = b0 - 3 * lane; bos >= startMin; bos -= 3 * AUGB_NLANES) {
-                    int bobe = bos - 3;
-                    if (bobe < 0 || bobe >= L - 2) continue;
-                    int pn = sq.s2i(bobe, 3);
-                    if (pn < 0 || isneg(m->startp[pn])) continue;
-                    int eop = bos - st.beginPartLen - 1;
-                    if (eop >= L) continue;
-                    sc_t nep = notEndPart(st, bos, right, frameOfRight);
-                    if (isneg(nep)) continue;
-                    sc_t pv = lookupV(a, eop >= 0 ? eop : 0);
-                    if (isneg(pv)) continue;
-                    AUGB_CONSIDER(pv + (t + ep + nep), bos, a, eop);
-                }
-        } else {   /* E_RTERMINAL, E_RSINGLE: exactly one candidate */
-            if (lane == 0) {
-                int bos = startMin, eop = bos - st.beginPartLen - 1;
-                sc_t nep = notEndPart(st, bos, right, frameOfRight);
-                if (!isneg(nep) && eop < L)
-                    for (int i = 0; i < st.nanc; i++) {
-                        int a = st.anc[i]; sc_t t = TR(a, s); if (isneg(t)) continue;
-                        sc_t pv = lookupV(a, eop >= 0 ? eop : 0); if (isneg(pv)) continue;
-                        AUGB_CONSIDER(pv + (t + ep + nep), bos, a, eop);
-                    }
             }
         }
-        #undef AUGB_CONSIDER
+        /* ---- candidate stream ---- */
+        const int anc0 = st.anc[0];
+        const sc_t t0 = TR(anc0, s);
+        int list = 0, ncl = 0, scan_b0 = 0;
+        const Cand* cl = nullptr;
+        if (listkind) { list = fwd ? CL_LA + mod3(win - eobe - 1) : CL_RD + mod3(win + eobe + 1); cl = w.cl[list]; ncl = ws->cl_n[list]; }
+        else if (scankind) {
+            const int want = mod3(eobe + 1 - (ek == E_SINGLE ? 0 : win));      /* bobe mod 3 such that len % 3 == win */
+            scan_b0 = startMax; while (mod3(scan_b0 - st.innerPartOffset) != want) scan_b0--;
+        }
+        const int lo = listkind ? (startMin < 1 ? 1 : startMin) : startMin;
+        sc_t best = SC_NEG; int bkey = -0x7fffffff, bpred = -1, bbase = -1;
+        int step = 0; bool more = true;
+        AUGB_ROLLED
+        while (more) {
+            /* lane's candidate: (bos, predecessor a, its cell value pv, its column eop) */
+            bool valid = false, below = false; int bos = 0, a = anc0, eop = 0; sc_t pv = SC_NEG, t = t0;
+            if (listkind) {
+                int i = ncl - 1 - step * AUGB_NLANES - lane;
+                if (i >= 0) {
+                    Cand c = cl[i]; bos = c.col + 1;
+                    if (bos < lo) below = true;
+                    else if (bos <= startMax && c.col < j) { valid = true; a = c.state; pv = c.V; eop = c.col; t = TR(a, s); }
+                } else below = true;
+                more = wballot(below) == 0;
+            } else if (scankind) {
+                bos = scan_b0 - 3 * (step * AUGB_NLANES + lane);
+                if (bos < startMin) below = true;
+                else {
+                    int bobe = bos - 3; eop = bos - st.beginPartLen - 1;
+                    if (bobe >= 0 && bobe < L - 2 && eop < L && !isneg(t0)) {
+                        int pn = sq.kmer_end(bobe + 2, 3);
+                        if (pn >= 0 && !isneg(m->startp[pn])) { pv = lookupV(anc0, eop >= 0 ? eop : 0); valid = !isneg(pv); }
+                    }
+                }
+                more = wballot(below) == 0;
+            } else {
+                more = step * AUGB_NLANES + AUGB_NLANES < st.nanc;
+                if (step * AUGB_NLANES + lane < st.nanc) {
+                    bos = startMin; eop = bos - st.beginPartLen - 1; a = st.anc[step * AUGB_NLANES + lane]; t = TR(a, s);
+                    if (eop < L && !isneg(t)) { pv = lookupV(a, eop >= 0 ? eop : 0); valid = !isneg(pv); }
+                }
+            }
+            step++;
+            /* score: nep = notEndPartEmiProb(bos) */
+            sc_t nep = SC_NEG; bool general = false;
+            if (valid && !isneg(t)) {
+                const int bobe = bos - st.innerPartOffset, len = eobe - bobe + 1, pf = m->st[a].frame, il = right - bos;
+                if (listkind && win != mod3(fwd ? pf + len : pf - len)) valid = false;
+                else if (len < 1 || len >= m->n_ld_exon) valid = false;
+                else if (ek == E_INTERNAL || ek == E_TERMINAL || ek == E_RINTERNAL) {
+                    /* begin part = 1: the splice site was checked by the longass / rlongdss cell (exonmodel.cc:1464-1486, 1518-1535) */
+                    sc_t ld = ldtab[len], rest;
+                    if (isneg(ld)) valid = false;
+                    else {
+                        if (il < 0) rest = -(sc_t)(-il - 1) * m->log025;                          /* begin and end part overlap (:1549-1558) */
+                        else if (il <= k) {                                                        /* only a P_ls pattern (:1559-1574) */
+                            int pn = fwd ? sq.kmer_end(bos + il, il + 1) : sq.kmer_rc(bos, il + 1);
+                            int f = fwd ? frameOfRight : mod3(frameOfRight + il);
+                            rest = pn < 0 ? (sc_t)(il + 1) * m->probN : m->xpls[il][(((size_t)cls * 3 + f) << (2 * (il + 1))) | pn];
+                        } else if (fwd) {
+                            int pn = sq.kmer_end(bos + k - 1, k);
+                            rest = pn < 0 ? (sc_t)k * m->probN : m->xpls[k - 1][(((size_t)cls * 3 + mod3(frameOfRight - il + k - 1)) << (2 * k)) | pn];
+                            if (ek == E_INTERNAL && il > etmin) rest += PXp[pxhi] - PXp[bos + k] + endc;
+                            else rest += PXp[right + 1] - PXp[bos + k];
+                        } else {
+                            rest = endc;
+                            if (il > etmin) { const int endOfTerm = bos + m->et_len - 1; rest += exon_shortProb(m->xet, 0, bos, endOfTerm, mod3(frameOfRight + right - endOfTerm)) + PXp[pxhi] - PXp[endOfTerm + 1]; }
+                            else rest += PXp[pxhi] - PXp[bos];
+                        }
+                        nep = isneg(rest) ? SC_NEG : rest + (m->log3 + ld);
+                    }
+                } else if (il >= thr && right - thr >= 0 && k >= 1 && (ek == E_RINITIAL || scankind)) {
+                    sc_t ld = ldtab[len];
+                    const bool lenok = ek == E_SINGLE ? len % 3 == 0 : ek == E_INITIAL ? (len % 3 == win && len > 2) : len > 2;
+                    if (isneg(ld) || !lenok) valid = false;
+                    else if (ek == E_RINITIAL) {
+                        const int endOfTerm = bos + m->et_len - 1;
+                        nep = endc + exon_shortProb(m->xet, 0, bos, endOfTerm, mod3(frameOfRight + right - endOfTerm)) + (PXp[pxhi] - PXp[endOfTerm + 1]) + (m->log3 + ld);
+                    } else {
+                        /* start codon x TIS motif, initial pattern, initial content (:1427-1462, 1590-1636) */
+                        sc_t bs = begin_score(bobe, frameOfRight - right);
+                        const int endOfInitial = bos + k - 1 + m->init_len;
+                        if (!isneg(bs)) nep = bs + (ek == E_INITIAL ? PXp[pxhi] - PXp[endOfInitial + 1] + endc : PXp[right + 1] - PXp[endOfInitial + 1]) + (m->log3 + ld);
+                    }
+                } else general = true;
+            }
+            if (wballot(valid && general)) { if (valid && general) nep = notEndPart(st, bos, right, frameOfRight); }
+            if (valid && !isneg(nep)) {
+                sc_t sc = pv + (t + ep + nep); int key = bos * 128 + (127 - a);
+                if (sc > best || (sc == best && key > bkey)) { best = sc; bkey = key; bpred = a; bbase = eop; }
+            }
+        }
+        if (listkind && startMin == 0) {
+            /* left-truncated exon, bos = 0: the predecessor is read from column 0 = initial probabilities (exonmodel.cc:1067-1068) */
+            const int len = eobe + st.innerPartOffset + 1;
+            sc_t nep0 = SC_NEG; bool have = false;
+            AUGB_ROLLED
+            for (int i = 0; i < st.nanc; i++) {
+                int a = st.anc[i]; sc_t pv = m->init[a], t = TR(a, s);
+                if (isneg(pv) || isneg(t) || win != mod3(fwd ? m->st[a].frame + len : m->st[a].frame - len)) continue;
+                if (!have) { nep0 = notEndPart(st, 0, right, frameOfRight); have = true; }
+                if (isneg(nep0)) break;
+                sc_t sc = pv + (t + ep + nep0); int key = 127 - a;
+                if (lane == 0 && (sc > best || (sc == best && key > bkey))) { best = sc; bkey = key; bpred = a; bbase = -1; }
+            }
+        }
         int wl = wargbest(best, bkey);
         if (wl < 0) return;
-        sc_t V = wbcast64(best, wl); int pred = wbcast(bpred, wl), pbase = wbcast(bbase, wl);
-        emit(j, s, V, pred, pbase);
+        emit(j, s, wbcast64(best, wl), wbcast(bpred, wl), wbcast(bbase, wl));
     }
 
     /* ------------------------------------------------------------ intron states */
@@ -474,14 +502,16 @@ struct Sweep {
         const int fwd = !dir;
         const int dssw = m->dss_start + m->dss_end + 2, assw = m->ass_start + m->ass_end + 2;
         int eop; sc_t emi;
-        if (kind == K_LONGDSS) { eop = j - dssw; emi = dSSProb(j - dssw + 1, fwd); }
-        else { eop = j - assw - m->ass_up; emi = aSSProb(j - assw - m->ass_up + 1, fwd); }
+        if (kind == K_LONGDSS) { eop = j - dssw; emi = sig(fwd ? SG_DSSF : SG_DSSR, j); }
+        else { eop = j - assw - m->ass_up; emi = sig(fwd ? SG_ASSF : SG_ASSR, j); }
         if (eop < 0 || isneg(emi)) return;
+        AUGB_ROLLED
         for (int f = 0; f < 3; f++) {
             int s = kind == K_LONGDSS ? m->r_longdss[dir][f] : m->r_longass[dir][f];
             if (s < 0) continue;
             const StateDesc& st = m->st[s];
             sc_t best = SC_NEG; int bpred = -1;
+            AUGB_ROLLED
             for (int i = 0; i < st.nanc; i++) {
                 int a = st.anc[i]; sc_t t = TR(a, s); if (isneg(t)) continue;
                 sc_t pv = lookupV(a, eop); if (isneg(pv)) continue;
@@ -513,6 +543,7 @@ struct Sweep {
         int eob = fwd ? j + m->ass_up + m->ass_start + 2 : j + m->dss_end + 2;
         int lme = j - m->dStateLen; if (lme < 0) lme = 0;
         const sc_t* P = parr(cls, fwd ? PA_PI : PA_PIR);
+        AUGB_ROLLED
         for (int f = 0; f < 3; f++) {
             int s = m->r_lessd[dir][f]; if (s < 0) continue;
             int list = (dir ? CL_RA : CL_LD) + f;
@@ -527,6 +558,7 @@ struct Sweep {
             }
             sc_t best = SC_NEG; int bkey = -0x7fffffff, bpred = -1;
             bool done = false;
+            AUGB_ROLLED
             for (int base_i = n - 1; base_i >= 0 && !done; base_i -= AUGB_NLANES) {
                 int i = base_i - lane; bool below = false;
                 if (i >= 0) {
@@ -565,49 +597,50 @@ struct Sweep {
     /* ------------------------------------------------------------ one column */
     AUGB_D void process_column(int j, unsigned mb, unsigned eqbits) {
         fill_evstart(j);
-        cls = w.gc[j];
-        if (mb & MB_LESSD) lessd_eval(0, j);
-        if (mb & MB_RLESSD) lessd_eval(1, j);
+        set_class(w.gc[j]);
+        /* one call site per routine (the bodies are large): loop over the strands / states this column activates */
+        AUGB_ROLLED
+        for (int dir = 0; dir < 2; dir++) if (mb & (dir ? MB_RLESSD : MB_LESSD)) lessd_eval(dir, j);
+        AUGB_ROLLED
         for (int q = 0; q < 6; q++) if (eqbits & (1u << q)) equald_eval(q / 3, q % 3, j);
-        if (mb & MB_LONGDSS) fixed_eval(K_LONGDSS, 0, j);
-        if (mb & MB_RLONGDSS) fixed_eval(K_LONGDSS, 1, j);
-        if (mb & MB_LONGASS) fixed_eval(K_LONGASS, 0, j);
-        if (mb & MB_RLONGASS) fixed_eval(K_LONGASS, 1, j);
-        if (mb & MB_XSTOP) {
-            if (m->r_single >= 0) exon_eval(m->r_single, j);
-            if (m->r_terminal >= 0) exon_eval(m->r_terminal, j);
+        AUGB_ROLLED
+        for (int t = 0; t < 4; t++) {
+            const unsigned bit = t == 0 ? MB_LONGDSS : t == 1 ? MB_RLONGDSS : t == 2 ? MB_LONGASS : MB_RLONGASS;
+            if (mb & bit) fixed_eval(t < 2 ? K_LONGDSS : K_LONGASS, t & 1, j);
         }
-        if (mb & MB_XDSS) for (int f = 0; f < 3; f++) {
-            if (m->r_initial[f] >= 0) exon_eval(m->r_initial[f], j);
-            if (m->r_internal[f] >= 0) exon_eval(m->r_internal[f], j);
-        }
-        if (mb & MB_XRSTART) {
-            if (m->r_rsingle >= 0) exon_eval(m->r_rsingle, j);
-            if (m->r_rinitial >= 0) exon_eval(m->r_rinitial, j);
-        }
-        if (mb & MB_XRASS) for (int f = 0; f < 3; f++) {
-            if (m->r_rinternal[f] >= 0) exon_eval(m->r_rinternal[f], j);
-            if (m->r_rterminal[f] >= 0) exon_eval(m->r_rterminal[f], j);
+        /* exon states whose end signal is present: 16 slots (single, terminal, 3 initial, 3 internal, rsingle, rinitial,
+         * 3 rinternal, 3 rterminal) selected by the mask bits */
+        unsigned slots = ((mb & MB_XSTOP) ? 0x3u : 0u) | ((mb & MB_XDSS) ? 0xfcu : 0u) | ((mb & MB_XRSTART) ? 0x300u : 0u) | ((mb & MB_XRASS) ? 0xfc00u : 0u);
+        AUGB_ROLLED
+        while (slots) {
+            int q = wffs(slots); slots &= slots - 1;
+            int xs = m->xslot[q];
+            if (xs >= 0) exon_eval(xs, j);
         }
         apply_pending(j);
     }
 
     /* ------------------------------------------------------------ whole window */
     AUGB_D void run() {
-        L = w.L; sq.c = w.code; sq.L = L; lane = lane_id();
+        L = w.L; sq.c = w.code; sq.L = L; sq.kf = w.kf; sq.kr = w.kr; sq.k1 = m->k + 1; lane = lane_id();
         if (lane == 0) {
-            ws->n_ev = 0; ws->filled = -1; ws->status = 0;
+            ws->n_ev = 0; ws->filled = -1; ws->status = 0; ws->any_pend = 0;
+            AUGB_ROLLED
             for (int i = 0; i < NCL; i++) ws->cl_n[i] = 0;
+            AUGB_ROLLED
             for (int i = 0; i < 6; i++) ws->eq_cur[i] = 0;
+            AUGB_ROLLED
             for (int i = 0; i < NCHAIN; i++) { ws->cp_n[i] = 0; ws->tilde[i] = SC_NEG; ws->pend_val[i] = SC_NEG; ws->pend_pred[i] = 0x7fffffff; }
         }
         wsync();
-        cls = w.gc[0];
+        set_class(w.gc[0]);
         fill_evstart(0);
         /* column 0 = initial probabilities (NAMGene::setStatesInitialProbs, namgene.cc:144-150) */
         /* a window without a single a/c/g/t is all intergenic: viterbi[j][synch] = viterbi[j-1][synch]/4,
          * every other state erased (namgene.cc:205-226); prep wrote AIG[j] = j*log(1/4) and an empty mask */
         const bool alln = (*w.flags & WF_ALLN) != 0;
+        if (*w.flags & WF_NOSLAB) { if (lane == 0) { *w.out_n_ev = 0; *w.out_status = 8; for (int i = 0; i < NCHAIN; i++) w.out_ncp[i] = 0; } wsync(); return; }
+        AUGB_ROLLED
         for (int s = 0; s < m->S; s++) {
             sc_t v = m->init[s]; if (isneg(v)) continue;
             int ch = m->st[s].chain;
@@ -617,13 +650,15 @@ struct Sweep {
                 wsync();
             } else {
                 int n = ws->n_ev;
-                if (lane == 0) { Event e; e.col = 0; e.state = (int16_t)s; e.pred = -1; e.predbase = -1; e.pad = 0; e.V = v; w.ev[n] = e; ws->n_ev = n + 1; }
+                if (lane == 0) { Event e; e.state = (int16_t)s; e.pred = -1; e.predbase = -1; e.V = v; w.ev[n] = e; ws->n_ev = n + 1; }
                 wsync();
                 const StateDesc& sd = m->st[s];
-                if (sd.kind == K_LONGDSS && sd.fwd) cl_append(CL_LD + sd.frame, 0, s, v);
-                if (sd.kind == K_LONGASS && !sd.fwd) cl_append(CL_RA + sd.frame, 0, s, v);
+                if (lane == 0 && sd.kind == K_LONGDSS && sd.fwd) cl_append(CL_LD + sd.frame, 0, s, v);
+                if (lane == 0 && sd.kind == K_LONGASS && !sd.fwd) cl_append(CL_RA + sd.frame, 0, s, v);
+                wsync();
             }
         }
+        AUGB_ROLLED
         for (int j0 = 1; j0 < L; j0 += 32) {
             /* static activity of the next 32 columns + equalD columns that fall into them */
             unsigned act = 0; unsigned mymask = 0;
@@ -631,23 +666,28 @@ struct Sweep {
             { int j = j0 + lane; mymask = j < L ? w.mask[j] : 0u; act = wballot(mymask != 0); }
 #else
             unsigned maskbuf[32];
+            AUGB_ROLLED
             for (int t = 0; t < 32; t++) { int j = j0 + t; maskbuf[t] = j < L ? w.mask[j] : 0u; if (maskbuf[t]) act |= 1u << t; }
 #endif
             unsigned eqcol[6];
+            AUGB_ROLLED
             for (int q = 0; q < 6; q++) {
                 eqcol[q] = 0;
                 if (m->r_equald[q / 3][q % 3] < 0) continue;
                 int list = (q / 3 ? CL_RA : CL_LD) + q % 3; int cur = ws->eq_cur[q], n = ws->cl_n[list];
+                AUGB_ROLLED
                 for (int i = cur; i < n; i++) {
                     int due = w.cl[list][i].col + m->dStateLen;
                     if (due >= j0 + 32) break;
                     if (due >= j0 && due < L) { eqcol[q] |= 1u << (due - j0); act |= 1u << (due - j0); }
                 }
             }
+            AUGB_ROLLED
             while (act) {
                 int t = wffs(act); act &= act - 1;
                 int j = j0 + t;
                 unsigned eqbits = 0;
+                AUGB_ROLLED
                 for (int q = 0; q < 6; q++) if (eqcol[q] & (1u << t)) eqbits |= 1u << q;
 #if defined(__CUDA_ARCH__)
                 unsigned mb = (unsigned)wbcast((int)mymask, t);
@@ -662,6 +702,7 @@ struct Sweep {
         fill_evstart(L);
         if (lane == 0) {
             *w.out_n_ev = ws->n_ev; *w.out_status = ws->status;
+            AUGB_ROLLED
             for (int i = 0; i < NCHAIN; i++) w.out_ncp[i] = ws->cp_n[i];
         }
         wsync();

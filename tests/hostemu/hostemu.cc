@@ -38,12 +38,14 @@ int hostemu_decode(void* mp, const char* dna, int L, const int32_t* gc_in,
     EmuModel* e = (EmuModel*)mp; const DevModel* m = &e->hm.dm;
     /* as augb200_decode_batch: default capacities first, the generous layout if a structure overflowed */
     WinLayout lay; std::vector<char> buf; char* base = nullptr; WinView v; WarpState ws; Sweep sw; WinOuts* outs = nullptr;
+    std::vector<char> pool; size_t pool_used = 0;
     for (int pass = 0; pass < 2; pass++) {
         lay = make_layout(L, m->C, pass == 1);
         buf.assign(lay.total + 64, 0);
         base = buf.data();
         int cm = 0;
-        prep_window_seq(m, dna, L, gc_in, base, lay, &cm);
+        pool.assign((size_t)(m->C) * lay.slab + 64, 0); pool_used = 0;
+        prep_window_seq(m, dna, L, gc_in, base, lay, &cm, pass == 0 ? pool.data() : nullptr, pool.size(), &pool_used);
         v = make_view(base, lay, L, cm);
         sw = Sweep(); sw.m = m; sw.w = v; sw.ws = &ws;
         sw.run();
@@ -62,7 +64,8 @@ int hostemu_decode(void* mp, const char* dna, int L, const int32_t* gc_in,
     *logp = ldexp((double)outs->score, -FRAC_BITS);
     if (n_ev_out) {
         int ne = outs->n_ev; *n_ev_out = ne;
-        for (int i = 0; i < ne && i < evcap; i++) { ev_col[i] = v.ev[i].col; ev_state[i] = v.ev[i].state; ev_V[i] = v.ev[i].V; }
+        for (int j = 0; j < L; j++) for (int i = v.evstart[j]; i < v.evstart[j + 1] && i < evcap; i++) ev_col[i] = j;
+        for (int i = 0; i < ne && i < evcap; i++) { ev_state[i] = v.ev[i].state; ev_V[i] = v.ev[i].V; }
     }
     if (chainV) {
         for (int j = 0; j < L; j++)

@@ -85,7 +85,7 @@ def test_full_size_properties(dec):
     for a, b, w in zip(p1, p2, wins):
         assert a.as_tuples() == b.as_tuples() and a.log_prob == b.log_prob
         st = a.states
-        assert st[0].begin == 1 and st[-1].end == len(w) - 1
+        assert st[0].begin <= 1 and st[-1].end == len(w) - 1     # a left-truncated first exon may start before the window
         for x, y in zip(st, st[1:]):
             assert y.begin == x.end + 1                 # the path tiles columns 1..L-1
         assert a.log_prob < 0
