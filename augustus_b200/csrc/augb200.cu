@@ -53,7 +53,7 @@ struct augb200_model {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    DevBuf<sc_t> d_tab; DevBuf<DevModel> d_model;
+    DevBuf<sc_t> d_tab; DevModel dm_dev;      /* model with device table pointers; uploaded to the c_model constant */
     /* batch state */
     DevBuf<char> d_arena; DevBuf<char> d_pool; DevBuf<unsigned long long> d_pool_used; size_t pool_bytes = 0; DevBuf<char> d_dna; DevBuf<uint8_t> d_gc; DevBuf<WinDev> d_wins; DevBuf<int> d_counters;
     DevBuf<PackHdr> d_hdr; DevBuf<int32_t> d_obegin, d_oend; DevBuf<uint8_t> d_otype, d_otrunc;
@@ -127,12 +127,16 @@ static int run_kernels(augb200_model* M, int count) {
     CK(cudaMemsetAsync(M->d_pool_used.p, 0, sizeof(unsigned long long), M->stream));
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, M->device);
     int gprep = std::min(count, sms * 8);
-    k_prep<<<gprep, PREP_BS, 0, M->stream>>>(M->d_model.p, M->d_wins.p, count, M->pool_bytes ? M->d_pool.p : nullptr, (unsigned long long)M->pool_bytes, M->d_pool_used.p);
+    CK(cudaMemcpyToSymbolAsync(c_model, &M->dm_dev, sizeof(DevModel), 0, cudaMemcpyHostToDevice, M->stream));
+    k_prep<<<gprep, PREP_BS, 0, M->stream>>>(M->d_wins.p, count, M->pool_bytes ? M->d_pool.p : nullptr, (unsigned long long)M->pool_bytes, M->d_pool_used.p);
     CK(cudaEventRecord(M->ev0, M->stream));
-    int gsweep = std::min((count + SWEEP_WARPS - 1) / SWEEP_WARPS, sms * 16);
-    k_sweep<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(M->d_model.p, M->d_wins.p, count, M->d_counters.p);
+    /* resident sweep warps per SM: the kernel is instruction-fetch bound, more warps than this thrash the instruction cache */
+    static int bps = 0;
+    if (!bps) { const char* e = getenv("AUGB200_SWEEP_BLOCKS_PER_SM"); bps = e ? atoi(e) : 4; if (bps < 1) bps = 1; }
+    int gsweep = std::min((count + SWEEP_WARPS - 1) / SWEEP_WARPS, sms * bps);
+    k_sweep<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(M->d_wins.p, count, M->d_counters.p);
     CK(cudaEventRecord(M->ev1, M->stream));
-    k_backtrace<<<(count + 63) / 64, 64, 0, M->stream>>>(M->d_model.p, M->d_wins.p, count);
+    k_backtrace<<<(count + 63) / 64, 64, 0, M->stream>>>(M->d_wins.p, count);
     k_pack<<<count, 64, 0, M->stream>>>(M->d_wins.p, count, M->d_hdr.p, M->d_counters.p + 1, M->d_obegin.p, M->d_oend.p, M->d_otype.p, M->d_otrunc.p, M->ocap);
     CK(cudaGetLastError());
     M->launches += 4;
@@ -193,9 +197,7 @@ int augb200_model_create(const void* blob, size_t nbytes, int device, augb200_mo
     if (cudaEventCreate(&M->ev0) != cudaSuccess || cudaEventCreate(&M->ev1) != cudaSuccess) return fail(AUGB200_ERR_CUDA);
     if (M->d_tab.reserve(M->hm.tab.size())) return fail(AUGB200_ERR_CUDA);
     if (cudaMemcpy(M->d_tab.p, M->hm.tab.data(), M->hm.tab.size() * sizeof(sc_t), cudaMemcpyHostToDevice) != cudaSuccess) return fail(AUGB200_ERR_CUDA);
-    DevModel dm = M->hm.rebased(M->d_tab.p);
-    if (M->d_model.reserve(1)) return fail(AUGB200_ERR_CUDA);
-    if (cudaMemcpy(M->d_model.p, &dm, sizeof dm, cudaMemcpyHostToDevice) != cudaSuccess) return fail(AUGB200_ERR_CUDA);
+    M->dm_dev = M->hm.rebased(M->d_tab.p);
     size_t fr = 0, tot = 0;
     if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return fail(AUGB200_ERR_CUDA);
     M->arena_budget = (size_t)(fr * 0.80);
@@ -207,7 +209,7 @@ int augb200_model_create(const void* blob, size_t nbytes, int device, augb200_mo
 void augb200_model_destroy(augb200_model* M) {
     if (!M) return;
     cudaSetDevice(M->device);
-    M->d_tab.release(); M->d_model.release(); M->d_arena.release(); M->d_pool.release(); M->d_pool_used.release(); M->d_dna.release(); M->d_gc.release(); M->d_wins.release(); M->d_counters.release();
+    M->d_tab.release(); M->d_arena.release(); M->d_pool.release(); M->d_pool_used.release(); M->d_dna.release(); M->d_gc.release(); M->d_wins.release(); M->d_counters.release();
     M->d_hdr.release(); M->d_obegin.release(); M->d_oend.release(); M->d_otype.release(); M->d_otrunc.release();
     M->h_dna.release(); M->h_gc.release(); M->h_wins.release(); M->h_hdr.release(); M->h_counters.release();
     M->h_obegin.release(); M->h_oend.release(); M->h_otype.release(); M->h_otrunc.release();

@@ -37,7 +37,7 @@ AUGB_HD void backtrace_window(const DevModel* m, const WinView& w, PathOut o) {
     for (int s = 0; s < S; s++) {
         sc_t t = m->term[s]; if (isneg(t)) continue;
         sc_t v = SC_NEG; int ch = m->st[s].chain;
-        if (ch >= 0) { if (ncp[ch] > 0) v = w.cp[ch][ncp[ch] - 1].tilde + (ch == 0 ? w.AIG : w.AGEO)[L - 1]; }
+        if (ch >= 0) { if (ncp[ch] > 0) v = w.cp(ch)[ncp[ch] - 1].tilde + (ch == 0 ? w.AIG : w.AGEO)[L - 1]; }
         else { for (int i = w.evstart[L - 1]; i < w.evstart[L]; i++) if (w.ev[i].state == s) v = w.ev[i].V; }
         if (isneg(v)) continue;
         v += t;
@@ -52,7 +52,7 @@ AUGB_HD void backtrace_window(const DevModel* m, const WinView& w, PathOut o) {
         const StateDesc& sd = m->st[state];
         int ch = sd.chain;
         if (ch >= 0) {
-            const ChainCP* cp = w.cp[ch]; int lo = 0, hi = ncp[ch] - 1;
+            const ChainCP* cp = w.cp(ch); int lo = 0, hi = ncp[ch] - 1;
             if (hi < 0 || cp[0].col > base) { *o.status = 7; *o.n = 0; return; }
             while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (cp[mid].col <= base) lo = mid; else hi = mid - 1; }
             int c = cp[lo].col, b = c == 0 ? 1 : c;

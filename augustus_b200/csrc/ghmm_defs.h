@@ -67,7 +67,8 @@ struct StateDesc {
 /* activity mask bits, one uint16 per column, computed by the prep pass from the sequence alone */
 enum : unsigned {
     MB_LONGDSS = 1u << 0, MB_LESSD = 1u << 1, MB_LONGASS = 1u << 2, MB_XDSS = 1u << 3, MB_XSTOP = 1u << 4,
-    MB_RLONGASS = 1u << 5, MB_RLESSD = 1u << 6, MB_RLONGDSS = 1u << 7, MB_XRASS = 1u << 8, MB_XRSTART = 1u << 9
+    MB_RLONGASS = 1u << 5, MB_RLESSD = 1u << 6, MB_RLONGDSS = 1u << 7, MB_XRASS = 1u << 8, MB_XRSTART = 1u << 9,
+    MB_SLOW = 1u << 10      /* a GC-class boundary is near: lessD emissions go through the restated SnippetProbs memo */
 };
 
 /* prefix arrays per GC class, each (L+1) long: P[i+1] - P[l] = sum over positions l..i */
@@ -123,6 +124,14 @@ struct ChainCP {
 /* per-column signal score arrays written by the prep pass (ghmm_signal.h) */
 enum : int { SG_DSSF = 0, SG_DSSR = 1, SG_ASSF = 2, SG_ASSR = 3, SG_XRS = 4, NSIG = 5 };
 
+/* SnippetProbs memo restated for the columns around GC-class boundaries (Sweep::snip_get) */
+constexpr int SNIP_BEFORE = 540 + 8;    /* emulation starts this many columns before a boundary (>= dStateLen) ... */
+constexpr int SNIP_AFTER = 1080 + 16;   /* ... and ends this many after it (>= 2 * dStateLen) */
+constexpr int SNIP_RING = 2048;         /* key ring (positions), power of two > dStateLen + slack */
+struct SnipEnt { int32_t len; uint32_t next; sc_t val; };        /* next = absolute entry id, 0 = none */
+struct SnipHead { uint32_t first, last; };
+struct SnipFrame { int32_t base, len; int32_t add, pad; sc_t part; };
+
 /* candidate lists of a window */
 enum : int { CL_LD = 0 /* +f: longdss_f */, CL_RA = 3 /* +f: rlongass_f */, CL_LA = 6 /* +phase */, CL_RD = 9 /* +phase */, NCL = 12 };
 
@@ -133,13 +142,19 @@ struct WinView {
     const uint8_t* gc;         /* class per position */
     const uint16_t* mask;
     const uint16_t *kf, *kr;   /* (k+1)-mer code ending / reverse-complement code starting at each position, 0x8000 = invalid */
-    const sc_t* parr_c[MAXC];  /* per GC class present: [PA_PER_CLASS][L+1] (first class in the window, others from the slab pool) */
+    const sc_t* const* parr_c; /* -> WinOuts::slab: per GC class present [PA_PER_CLASS][L+1] (first class in the window, others from the slab pool) */
     const sc_t* sig;           /* [NSIG][L] */
     const sc_t *AIG, *AGEO;    /* chain prefix arrays, [L] */
     const int32_t *nsf, *nsr;  /* nearestStopForward / Reverse (exonmodel.cc:101-156) */
     Event* ev; int32_t* evstart;
-    Cand* cl[NCL];
-    ChainCP* cp[NCHAIN];
+    Cand* cl0; ChainCP* cp0;   /* list i / chain i start at cl0 + i*cl_stride, cp0 + i*cp_stride (no pointer tables: those end up in local memory) */
+    int cl_stride, cp_stride;
+    SnipHead* snip_head;       /* [2][SNIP_RING] */
+    SnipEnt* snip_pool;        /* [2][snip_cap] */
+    SnipFrame* snip_stack;     /* [SNIP_RING] */
+    int snip_cap;              /* power of two */
+    AUGB_HD Cand* cl(int i) const { return cl0 + (size_t)i * cl_stride; }
+    AUGB_HD ChainCP* cp(int i) const { return cp0 + (size_t)i * cp_stride; }
     /* results */
     int32_t* out_n_ev; int32_t* out_ncp; int32_t* out_status;
     const int32_t* flags;      /* written by prep: bits 0..7 GC classes present, bit 8 = no a/c/g/t at all */

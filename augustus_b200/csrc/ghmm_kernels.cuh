@@ -21,6 +21,10 @@ struct WinDev {
     WinLayout lay;
 };
 
+/* The model lives in constant memory: its scalars become instruction operands (c[bank][offset]) instead of loads, which
+ * matters for the sweep's code size.  One symbol per process: the host re-uploads it when another model runs. */
+__constant__ DevModel c_model;
+
 constexpr int PREP_BS = 256;
 constexpr int PREP_ITEMS = 4;
 constexpr int PREP_TILE = PREP_BS * PREP_ITEMS;
@@ -109,8 +113,9 @@ __device__ void block_stop_scan(const DevModel* m, const Seq& s, int32_t* out, i
 }
 
 /* ------------------------------------------------------------------ prep kernel: one CTA per window */
-__global__ void __launch_bounds__(PREP_BS) k_prep(const DevModel* __restrict__ m, const WinDev* __restrict__ wins, int nwin,
+__global__ void __launch_bounds__(PREP_BS) k_prep(const WinDev* __restrict__ wins, int nwin,
                                                   char* pool, unsigned long long pool_size, unsigned long long* pool_used) {
+    const DevModel* m = &c_model;
     __shared__ sc_t sm64[PREP_BS / 32 + 2];
     __shared__ int sm32[PREP_BS / 32 + 2];
     __shared__ Int3 sm3[PREP_BS / 32];
@@ -190,7 +195,19 @@ __global__ void __launch_bounds__(PREP_BS) k_prep(const DevModel* __restrict__ m
         }
         __syncthreads();
         { int cm = 0; for (int i = threadIdx.x; i < L; i += PREP_BS) cm |= 1 << gc[i]; if (cm) atomicOr(&s_classmask, cm); }
-        for (int j = threadIdx.x; j < L; j += PREP_BS) mask[j] = anynuc ? (uint16_t)column_mask(m, s, j) : 0;
+        {
+            /* columns near a GC-class boundary (number of boundaries in (j - SNIP_AFTER, j + SNIP_BEFORE]) get MB_SLOW */
+            int32_t* nb = (int32_t*)(base + lay.ev);           /* scratch: inclusive count of boundaries at positions <= i */
+            block_scan_gen<int>([&](int i) { return i >= 1 && gc[i] != gc[i - 1] ? 1 : 0; }, nb, L, 0, sm32);
+            __syncthreads();
+            for (int j = threadIdx.x; j < L; j += PREP_BS) {
+                unsigned mb = anynuc ? column_mask(m, s, j) : 0u;
+                int hi = min(j + SNIP_BEFORE, L - 1), lo = j - SNIP_AFTER;
+                if (anynuc && j >= 1 && nb[hi] - (lo >= 0 ? nb[lo] : 0) > 0) mb |= MB_SLOW;
+                mask[j] = (uint16_t)mb;
+            }
+            __syncthreads();
+        }
         __syncthreads();
         const int cm = s_classmask | (anynuc ? 0 : WF_ALLN);
         /* ---- signal scores of every column ---- */
@@ -243,7 +260,8 @@ __global__ void __launch_bounds__(PREP_BS) k_prep(const DevModel* __restrict__ m
 
 /* ------------------------------------------------------------------ sweep kernel: one warp per window */
 constexpr int SWEEP_WARPS = 4;
-__global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep(const DevModel* __restrict__ m, const WinDev* __restrict__ wins, int nwin, int* __restrict__ next) {
+__global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep(const WinDev* __restrict__ wins, int nwin, int* __restrict__ next) {
+    const DevModel* m = &c_model;
     __shared__ WarpState wstate[SWEEP_WARPS];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (;;) {
@@ -260,7 +278,8 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep(const DevModel* __re
 }
 
 /* ------------------------------------------------------------------ backtrace: one thread per window */
-__global__ void k_backtrace(const DevModel* __restrict__ m, const WinDev* __restrict__ wins, int nwin) {
+__global__ void k_backtrace(const WinDev* __restrict__ wins, int nwin) {
+    const DevModel* m = &c_model;
     int wi = blockIdx.x * blockDim.x + threadIdx.x;
     if (wi >= nwin) return;
     const WinDev& wd = wins[wi];

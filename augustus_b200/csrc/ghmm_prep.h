@@ -31,6 +31,7 @@ struct WinOuts {
 struct WinLayout {
     size_t code, gc, mask, kf, kr, parr, sig, aig, ageo, nsf, nsr;        /* static (prep) */
     size_t ev, evstart, cl[NCL], cp[NCHAIN], outs;           /* dynamic (sweep) */
+    size_t snip_head, snip_pool, snip_stack; int snip_cap;
     size_t path_begin, path_end, path_type, path_trunc;      /* backtrace output */
     size_t total, slab;
     int ev_cap, cl_cap, cp_cap, path_cap, nslab_local;
@@ -59,6 +60,9 @@ inline WinLayout make_layout(int L, int C, bool generous = false) {
     for (int i = 0; i < NCL; i++) w.cl[i] = take((size_t)w.cl_cap * sizeof(Cand));
     for (int i = 0; i < NCHAIN; i++) w.cp[i] = take((size_t)w.cp_cap * sizeof(ChainCP));
     w.outs = take(sizeof(WinOuts));
+    w.snip_cap = generous ? 262144 : 16384;
+    w.snip_head = take((size_t)2 * SNIP_RING * sizeof(SnipHead)); w.snip_pool = take((size_t)2 * w.snip_cap * sizeof(SnipEnt));
+    w.snip_stack = take((size_t)SNIP_RING * sizeof(SnipFrame));
     w.path_begin = take((size_t)w.path_cap * 4); w.path_end = take((size_t)w.path_cap * 4);
     w.path_type = take(w.path_cap); w.path_trunc = take(w.path_cap);
     w.total = al16(o);
@@ -72,11 +76,12 @@ AUGB_HD WinView make_view(char* base, const WinLayout& lay, int L, int classmask
     v.sig = (const sc_t*)(base + lay.sig); v.AIG = (const sc_t*)(base + lay.aig); v.AGEO = (const sc_t*)(base + lay.ageo);
     v.nsf = (const int32_t*)(base + lay.nsf); v.nsr = (const int32_t*)(base + lay.nsr);
     v.ev = (Event*)(base + lay.ev); v.evstart = (int32_t*)(base + lay.evstart);
-    for (int i = 0; i < NCL; i++) v.cl[i] = (Cand*)(base + lay.cl[i]);
-    for (int i = 0; i < NCHAIN; i++) v.cp[i] = (ChainCP*)(base + lay.cp[i]);
+    v.cl0 = (Cand*)(base + lay.cl[0]); v.cp0 = (ChainCP*)(base + lay.cp[0]);
+    v.snip_head = (SnipHead*)(base + lay.snip_head); v.snip_pool = (SnipEnt*)(base + lay.snip_pool); v.snip_stack = (SnipFrame*)(base + lay.snip_stack); v.snip_cap = lay.snip_cap;
+    v.cl_stride = (int)((lay.cl[1] - lay.cl[0]) / sizeof(Cand)); v.cp_stride = (int)((lay.cp[1] - lay.cp[0]) / sizeof(ChainCP));
     WinOuts* o = (WinOuts*)(base + lay.outs);
     v.out_n_ev = &o->n_ev; v.out_status = &o->status; v.out_ncp = o->ncp; v.flags = &o->pad;
-    for (int c = 0; c < MAXC; c++) v.parr_c[c] = o->slab[c];      /* valid once prep has run */
+    v.parr_c = o->slab;                                          /* filled by prep */
     return v;
 }
 
@@ -176,6 +181,8 @@ inline void prep_window_seq(const DevModel* m, const char* dna, int L, const int
         s.kf = kf; s.kr = kr; s.k1 = m->k + 1;
     }
     for (int j = 0; j < L; j++) mask[j] = anynuc ? (uint16_t)column_mask(m, s, j) : 0;
+    if (anynuc) for (int b = 1; b < L; b++) if (gc[b] != gc[b - 1])        /* GC-class boundary at b */
+        for (int j = (b - SNIP_BEFORE < 1 ? 1 : b - SNIP_BEFORE); j < L && j < b + SNIP_AFTER; j++) mask[j] |= MB_SLOW;
     {
         sc_t* sg = (sc_t*)(base + lay.sig);
         for (int which = 0; which < NSIG; which++)

@@ -40,6 +40,7 @@ struct WarpState {
     int pend_pred[NCHAIN];
     int status;
     int any_pend;
+    unsigned snip_cnt[2];       /* entries allocated so far per strand (ids start at 1) */
 };
 
 struct Sweep {
@@ -56,7 +57,7 @@ struct Sweep {
     AUGB_D sc_t chain_value(int ch, int e) const {
         int n = ws->cp_n[ch];
         if (n == 0) return SC_NEG;
-        const ChainCP* cp = w.cp[ch];
+        const ChainCP* cp = w.cp(ch);
         int lo = 0, hi = n - 1;          /* invariant: cp[lo].col <= e (cp[0].col is the first entry column) */
         if (cp[0].col > e) return SC_NEG;
         if (cp[hi].col <= e) lo = hi;
@@ -86,7 +87,7 @@ struct Sweep {
     AUGB_D void cl_append(int list, int col, int state, sc_t V) {       /* lane 0 only; caller syncs */
         int n = ws->cl_n[list];
         if (n >= w.cl_cap) { ws->status = 8; return; }
-        Cand c; c.col = col; c.state = state; c.V = V; w.cl[list][n] = c; ws->cl_n[list] = n + 1;
+        Cand c; c.col = col; c.state = state; c.V = V; w.cl(list)[n] = c; ws->cl_n[list] = n + 1;
     }
     /* record a non-zero cell; route it to the structures later columns look back to.  All lanes hold the same
      * arguments; lane 0 writes, one warp sync publishes. */
@@ -133,7 +134,7 @@ struct Sweep {
                 bool take = pv > cur || (pv == cur && pp < self);
                 int n = ws->cp_n[ch];
                 if (take && n >= w.cp_cap) { ws->status = 8; take = false; }
-                if (take) { ChainCP c; c.col = j + 1; c.pred = pp; c.tilde = pv; w.cp[ch][n] = c; ws->cp_n[ch] = n + 1; ws->tilde[ch] = pv; }
+                if (take) { ChainCP c; c.col = j + 1; c.pred = pp; c.tilde = pv; w.cp(ch)[n] = c; ws->cp_n[ch] = n + 1; ws->tilde[ch] = pv; }
                 ws->pend_val[ch] = SC_NEG; ws->pend_pred[ch] = 0x7fffffff;
             }
             ws->any_pend = 0;
@@ -389,7 +390,7 @@ struct Sweep {
         const sc_t t0 = TR(anc0, s);
         int list = 0, ncl = 0, scan_b0 = 0;
         const Cand* cl = nullptr;
-        if (listkind) { list = fwd ? CL_LA + mod3(win - eobe - 1) : CL_RD + mod3(win + eobe + 1); cl = w.cl[list]; ncl = ws->cl_n[list]; }
+        if (listkind) { list = fwd ? CL_LA + mod3(win - eobe - 1) : CL_RD + mod3(win + eobe + 1); cl = w.cl(list); ncl = ws->cl_n[list]; }
         else if (scankind) {
             const int want = mod3(eobe + 1 - (ek == E_SINGLE ? 0 : win));      /* bobe mod 3 such that len % 3 == win */
             scan_b0 = startMax; while (mod3(scan_b0 - st.innerPartOffset) != want) scan_b0--;
@@ -525,7 +526,7 @@ struct Sweep {
     AUGB_D void equald_eval(int dir, int f, int j) {
         int s = m->r_equald[dir][f]; int list = (dir ? CL_RA : CL_LD) + f;
         int cur = ws->eq_cur[dir * 3 + f];
-        Cand c = w.cl[list][cur];
+        Cand c = w.cl(list)[cur];
         wsync();
         if (lane == 0) ws->eq_cur[dir * 3 + f] = cur + 1;
         wsync();
@@ -537,17 +538,96 @@ struct Sweep {
         if (isneg(t)) return;
         emit(j, s, c.V + (t + emi), c.state, eop);
     }
+    /* ------------------------------------------------------------ SnippetProbs memo near GC-class boundaries
+     *
+     * SnippetProbs::getSeqProb (statemodel.cc:312-342) memoises products of intron emissions per (right end, length) and
+     * composes longer segments from stored pieces.  IntronModel::updateToLocalGC (intronmodel.cc:495-503) swaps the emission
+     * table when the GC class changes but keeps the memo, so a piece keeps the class that was active when it was first
+     * computed: around a class boundary a lessD emission is a mix of both tables that depends on the order of calls.
+     * Away from boundaries every piece in play has the class of the current column and the value is the plain prefix
+     * difference; within [boundary - SNIP_BEFORE, boundary + SNIP_AFTER) the memo is restated entry for entry (lane 0).
+     * Starting from an empty memo SNIP_BEFORE columns ahead of the boundary is exact: the list of a key only depends on
+     * requests coming from higher keys, all of which are replayed, and everything computed before the boundary has the old
+     * class whatever its decomposition ("GC-class boundaries"). */
+    AUGB_D SnipEnt* snip_ent(int rc, unsigned id) const { return w.snip_pool + (size_t)rc * w.snip_cap + (id & (unsigned)(w.snip_cap - 1)); }
+    AUGB_D bool snip_stale(int rc, unsigned id) const { return id + (unsigned)w.snip_cap <= ws->snip_cnt[rc] + 1u; }
+    AUGB_D sc_t snip_elem(int rc, int base, int len) const {          /* getElemSeqProb :283-310 with the current class */
+        const sc_t* P = parr(cls, rc ? PA_PIR : PA_PI);
+        return P[base + 1] - P[base - len + 1];
+    }
+    AUGB_D void snip_add(int rc, int base, int len, sc_t p) {          /* addProb :344-370 */
+        SnipHead* h = w.snip_head + (size_t)rc * SNIP_RING + (base & (SNIP_RING - 1));
+        unsigned id = ++ws->snip_cnt[rc];
+        SnipEnt* e = snip_ent(rc, id); e->len = len; e->val = p; e->next = 0;
+        if (!h->first) { h->first = h->last = id; return; }
+        SnipEnt* la = snip_ent(rc, h->last);
+        if (la->len < len) { la->next = id; h->last = id; return; }
+        SnipEnt* t = snip_ent(rc, h->first);
+        if (t->len > len) { e->next = h->first; h->first = id; return; }
+        AUGB_ROLLED
+        while (t->next && snip_ent(rc, t->next)->len < len) t = snip_ent(rc, t->next);
+        if (t->next && snip_ent(rc, t->next)->len == len) return;       /* "tried to add snippet of same length": dropped */
+        e->next = t->next; t->next = id;
+    }
+    AUGB_DN sc_t snip_get(int rc, int base0, int len0) {               /* getSeqProb :312-342, recursion unrolled onto a stack */
+        SnipFrame* st = w.snip_stack; int sp = 0; int base = base0, len = len0; sc_t r = 0;
+        AUGB_ROLLED
+        for (;;) {
+            if (len == 0) { r = 0; break; }
+            SnipHead* h = w.snip_head + (size_t)rc * SNIP_RING + (base & (SNIP_RING - 1));
+            if (!h->first) { r = snip_elem(rc, base, len); snip_add(rc, base, len, r); break; }
+            if (snip_stale(rc, h->first) || snip_stale(rc, h->last)) { ws->status = 8; return SC_NEG; }
+            SnipEnt* la = snip_ent(rc, h->last);
+            if (la->len < len) {
+                if (sp >= SNIP_RING) { ws->status = 8; return SC_NEG; }
+                st[sp].base = base; st[sp].len = len; st[sp].add = 1; st[sp].part = la->val; sp++;
+                base -= la->len; len -= la->len; continue;
+            }
+            SnipEnt* t = snip_ent(rc, h->first);                        /* SnippetList::getProb :379-393 */
+            int partlen; sc_t pv;
+            if (t->len > len) { partlen = 0; pv = 0; }
+            else {
+                AUGB_ROLLED
+                while (t->next && snip_ent(rc, t->next)->len < len) t = snip_ent(rc, t->next);
+                if (!t->next || snip_ent(rc, t->next)->len > len) { partlen = t->len; pv = t->val; }
+                else { partlen = len; pv = snip_ent(rc, t->next)->val; }
+            }
+            if (partlen == len) { r = pv; break; }
+            if (partlen == 0) { r = snip_elem(rc, base, len); snip_add(rc, base, len, r); break; }
+            if (sp >= SNIP_RING) { ws->status = 8; return SC_NEG; }
+            st[sp].base = base; st[sp].len = len; st[sp].add = 0; st[sp].part = pv; sp++;
+            base -= partlen; len -= partlen;
+        }
+        AUGB_ROLLED
+        while (sp > 0) { sp--; r += st[sp].part; if (st[sp].add) snip_add(rc, st[sp].base, st[sp].len, r); }
+        return r;
+    }
+    /* a column inside an emulated region: forget what the key ring held for this position (and for the whole ring at the
+     * first column of a region) */
+    AUGB_D void snip_column_begin(int j) {
+        const bool first = j == 1 || !(w.mask[j - 1] & MB_SLOW);
+        if (first) {
+            AUGB_ROLLED
+            for (int i = lane; i < 2 * SNIP_RING; i += AUGB_NLANES) { w.snip_head[i].first = 0; w.snip_head[i].last = 0; }
+        } else if (lane == 0) {
+            AUGB_ROLLED
+            for (int rc = 0; rc < 2; rc++) { SnipHead* h = w.snip_head + (size_t)rc * SNIP_RING + (j & (SNIP_RING - 1)); h->first = h->last = 0; }
+        }
+        wsync();
+    }
+
     /* lessD / rlessD (intronmodel.cc:540-629, 924-1000): max over the longdss / rlongass cells of the last dStateLen columns */
     AUGB_D void lessd_eval(int dir, int j) {
         const int fwd = !dir;
         int eob = fwd ? j + m->ass_up + m->ass_start + 2 : j + m->dss_end + 2;
         int lme = j - m->dStateLen; if (lme < 0) lme = 0;
         const sc_t* P = parr(cls, fwd ? PA_PI : PA_PIR);
+        const bool slow = (w.mask[j] & MB_SLOW) != 0;
         AUGB_ROLLED
         for (int f = 0; f < 3; f++) {
             int s = m->r_lessd[dir][f]; if (s < 0) continue;
             int list = (dir ? CL_RA : CL_LD) + f;
-            const Cand* cl = w.cl[list]; int n = ws->cl_n[list];
+            const Cand* cl = w.cl(list); int n = ws->cl_n[list];
             bool spl = !(fwd && f == 0) && !(!fwd && f == 2);
             int cod0 = 4, cod1 = 4, cod2 = 4;
             if (spl && eob < L - 2) {
@@ -558,10 +638,11 @@ struct Sweep {
             }
             sc_t best = SC_NEG; int bkey = -0x7fffffff, bpred = -1;
             bool done = false;
+            const int nl = slow ? 1 : AUGB_NLANES;            /* emulated columns: lane 0 walks the candidates in the reference's order */
             AUGB_ROLLED
-            for (int base_i = n - 1; base_i >= 0 && !done; base_i -= AUGB_NLANES) {
-                int i = base_i - lane; bool below = false;
-                if (i >= 0) {
+            for (int base_i = n - 1; base_i >= 0 && !done; base_i -= nl) {
+                int i = slow ? base_i : base_i - lane; bool below = false;
+                if (i >= 0 && (!slow || lane == 0)) {
                     Cand c = cl[i]; int e = c.col;
                     if (e < lme) below = true;
                     else if (e < j) {
@@ -580,13 +661,15 @@ struct Sweep {
                         if (ok && !(ilen > m->d || ilen < 0 || ilen >= m->n_ld_intron)) {
                             sc_t ld = m->ld_intron[ilen], t = TR(c.state, s);
                             if (!isneg(ld) && !isneg(t)) {
-                                sc_t sc = c.V + (t + (ld + (P[j + 1] - P[begin])));
+                                /* seqProb is evaluated (and memoised) for every candidate that passes the site tests (:970-972) */
+                                sc_t seq = slow ? snip_get(dir, j, j - begin + 1) : P[j + 1] - P[begin];
+                                sc_t sc = c.V + (t + (ld + seq));
                                 if (sc > best || (sc == best && e > bkey)) { best = sc; bkey = e; bpred = c.state; }
                             }
                         }
                     }
-                } else below = true;
-                done = wballot(below) != 0;
+                } else if (i < 0) below = true;
+                done = slow ? wbcast((int)below, 0) != 0 : wballot(below) != 0;
             }
             int wl = wargbest(best, bkey);
             if (wl < 0) continue;
@@ -598,16 +681,18 @@ struct Sweep {
     AUGB_D void process_column(int j, unsigned mb, unsigned eqbits) {
         fill_evstart(j);
         set_class(w.gc[j]);
+        if (mb & MB_SLOW) snip_column_begin(j);
         /* one call site per routine (the bodies are large): loop over the strands / states this column activates */
         AUGB_ROLLED
-        for (int dir = 0; dir < 2; dir++) if (mb & (dir ? MB_RLESSD : MB_LESSD)) lessd_eval(dir, j);
-        AUGB_ROLLED
-        for (int q = 0; q < 6; q++) if (eqbits & (1u << q)) equald_eval(q / 3, q % 3, j);
-        AUGB_ROLLED
-        for (int t = 0; t < 4; t++) {
-            const unsigned bit = t == 0 ? MB_LONGDSS : t == 1 ? MB_RLONGDSS : t == 2 ? MB_LONGASS : MB_RLONGASS;
-            if (mb & bit) fixed_eval(t < 2 ? K_LONGDSS : K_LONGASS, t & 1, j);
-        }
+        { unsigned lm = ((mb & MB_LESSD) ? 1u : 0u) | ((mb & MB_RLESSD) ? 2u : 0u);
+          AUGB_ROLLED
+          while (lm) { int dir = wffs(lm); lm &= lm - 1; lessd_eval(dir, j); } }
+        { unsigned qm = eqbits;
+          AUGB_ROLLED
+          while (qm) { int q = wffs(qm); qm &= qm - 1; equald_eval(q >= 3, q >= 3 ? q - 3 : q, j); } }
+        { unsigned fm = ((mb & MB_LONGDSS) ? 1u : 0u) | ((mb & MB_RLONGDSS) ? 2u : 0u) | ((mb & MB_LONGASS) ? 4u : 0u) | ((mb & MB_RLONGASS) ? 8u : 0u);
+          AUGB_ROLLED
+          while (fm) { int t = wffs(fm); fm &= fm - 1; fixed_eval(t < 2 ? K_LONGDSS : K_LONGASS, t & 1, j); } }
         /* exon states whose end signal is present: 16 slots (single, terminal, 3 initial, 3 internal, rsingle, rinitial,
          * 3 rinternal, 3 rterminal) selected by the mask bits */
         unsigned slots = ((mb & MB_XSTOP) ? 0x3u : 0u) | ((mb & MB_XDSS) ? 0xfcu : 0u) | ((mb & MB_XRSTART) ? 0x300u : 0u) | ((mb & MB_XRASS) ? 0xfc00u : 0u);
@@ -624,7 +709,7 @@ struct Sweep {
     AUGB_D void run() {
         L = w.L; sq.c = w.code; sq.L = L; sq.kf = w.kf; sq.kr = w.kr; sq.k1 = m->k + 1; lane = lane_id();
         if (lane == 0) {
-            ws->n_ev = 0; ws->filled = -1; ws->status = 0; ws->any_pend = 0;
+            ws->n_ev = 0; ws->filled = -1; ws->status = 0; ws->any_pend = 0; ws->snip_cnt[0] = ws->snip_cnt[1] = 0;
             AUGB_ROLLED
             for (int i = 0; i < NCL; i++) ws->cl_n[i] = 0;
             AUGB_ROLLED
@@ -646,7 +731,7 @@ struct Sweep {
             int ch = m->st[s].chain;
             if (alln && ch != 0) continue;
             if (ch >= 0) {
-                if (lane == 0) { ChainCP c; c.col = 0; c.pred = -1; c.tilde = v; w.cp[ch][0] = c; ws->cp_n[ch] = 1; ws->tilde[ch] = v; }
+                if (lane == 0) { ChainCP c; c.col = 0; c.pred = -1; c.tilde = v; w.cp(ch)[0] = c; ws->cp_n[ch] = 1; ws->tilde[ch] = v; }
                 wsync();
             } else {
                 int n = ws->n_ev;
@@ -669,7 +754,7 @@ struct Sweep {
             AUGB_ROLLED
             for (int t = 0; t < 32; t++) { int j = j0 + t; maskbuf[t] = j < L ? w.mask[j] : 0u; if (maskbuf[t]) act |= 1u << t; }
 #endif
-            unsigned eqcol[6];
+            unsigned eqcol[6]; unsigned eqany = 0;
             AUGB_ROLLED
             for (int q = 0; q < 6; q++) {
                 eqcol[q] = 0;
@@ -677,9 +762,9 @@ struct Sweep {
                 int list = (q / 3 ? CL_RA : CL_LD) + q % 3; int cur = ws->eq_cur[q], n = ws->cl_n[list];
                 AUGB_ROLLED
                 for (int i = cur; i < n; i++) {
-                    int due = w.cl[list][i].col + m->dStateLen;
+                    int due = w.cl(list)[i].col + m->dStateLen;
                     if (due >= j0 + 32) break;
-                    if (due >= j0 && due < L) { eqcol[q] |= 1u << (due - j0); act |= 1u << (due - j0); }
+                    if (due >= j0 && due < L) { eqcol[q] |= 1u << (due - j0); act |= 1u << (due - j0); eqany |= 1u << (due - j0); }
                 }
             }
             AUGB_ROLLED
@@ -687,8 +772,10 @@ struct Sweep {
                 int t = wffs(act); act &= act - 1;
                 int j = j0 + t;
                 unsigned eqbits = 0;
-                AUGB_ROLLED
-                for (int q = 0; q < 6; q++) if (eqcol[q] & (1u << t)) eqbits |= 1u << q;
+                if (eqany & (1u << t)) {
+                    AUGB_ROLLED
+                    for (int q = 0; q < 6; q++) if (eqcol[q] & (1u << t)) eqbits |= 1u << q;
+                }
 #if defined(__CUDA_ARCH__)
                 unsigned mb = (unsigned)wbcast((int)mymask, t);
 #else

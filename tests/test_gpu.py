@@ -47,6 +47,15 @@ def test_synthetic_50k_windows_match_reference(dec, golden):
         assert abs(p.log_prob - ref["log_prob"]) <= 1e-6 * abs(ref["log_prob"])
 
 
+def test_real_dna_with_gc_class_boundaries_matches_reference(dec, oracle, golden):
+    seqs = util.read_fasta(util.GOLDEN + "/real_windows.fa")
+    paths = dec.decode_batch([s for _, s in seqs])
+    for (name, dna), p, ref in zip(seqs, paths, golden["real"]):
+        assert p.as_tuples() == [tuple(s) for s in ref["states"]]
+        assert abs(p.log_prob - ref["log_prob"]) <= 1e-6 * abs(ref["log_prob"])
+        _same(p, oracle.viterbi(dna))
+
+
 def test_seeded_windows_match_oracle(dec, oracle):
     wins = [synth.window(200 + i, n) for i, n in enumerate([50000, 31000, 12345, 7000, 2048, 999, 120, 41, 9, 3, 2])]
     paths = dec.decode_batch(wins)

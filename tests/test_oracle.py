@@ -98,6 +98,13 @@ def test_kernel_source_on_host_matches_oracle_cells(oracle, emu):
     _cells_equal(oracle, emu, synth.window(103, 120))
 
 
+def test_kernel_source_on_host_matches_oracle_cells_across_gc_class_boundaries(oracle, emu):
+    """Real DNA with several GC classes: the windowed restatement of the SnippetProbs memo in the sweep must give
+    the same cells as the oracle's whole-window restatement (which is pinned to the reference)."""
+    for name, dna in util.read_fasta(util.GOLDEN + "/real_windows.fa"):
+        _cells_equal(oracle, emu, dna)
+
+
 def test_kernel_source_on_host_edge_cases(oracle, emu):
     base = synth.window(7, 4000)
     cases = [base[:2], base[:3], base[:9], base[:41], base[:600], "N" * 500, base[:1000] + "N" * 300 + base[1000:2000],
