@@ -115,7 +115,7 @@ def reference_arm(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    use = min(cores, 64)
+    use = cores
     per_step = use * 2
     exe, _ = ref_binary()
     base = {"metric": METRIC, "unit": "Mbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -168,8 +168,11 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    from augustus_b200 import shard
     M = args.windows
-    wins = synth.windows_parallel(M, WINDOW_LEN, start=rank * M)
+    # global list of world*M windows, block-cyclic over ranks (window g -> rank g mod world): rank r decodes g = r, r+world, ...
+    my_idx = shard.shard_indices(world * M, rank, world)
+    wins = synth.windows_parallel_indices(my_idx, WINDOW_LEN)
     wins_b = [w.encode() for w in wins]
     bases = M * WINDOW_LEN
     dec = Decoder(util.blob_bytes(), local)
@@ -209,14 +212,9 @@ def main():
         assert not status.any()
         d2h = pb.nbytes + pe.nbytes + pt.nbytes + ptr.nbytes + 32 * len(n_st)
         if world > 1:   # the one gather of the final results (path arrays) over NCCL
-            flat = torch.from_numpy(np.concatenate([pb, pe, pt.astype(np.int32), ptr.astype(np.int32)])).cuda()
-            n = torch.tensor([flat.numel()], device="cuda")
-            sizes = [torch.zeros_like(n) for _ in range(world)]
-            dist.all_gather(sizes, n)
-            mx = int(max(int(x) for x in sizes))
-            pad = torch.zeros(mx, dtype=torch.int32, device="cuda"); pad[: flat.numel()] = flat
-            out = [torch.zeros_like(pad) for _ in range(world)] if rank == 0 else None
-            dist.gather(pad, out, dst=0)
+            got = shard.gather_to_rank0(shard.pack_paths(n_st, status, logp, offset, pb, pe, pt, ptr), device="cuda")
+            if rank == 0:
+                assert sum(int(v[0]) for v in got) == world * M
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     sampler.stop_flag = True; sampler.join(timeout=2)
@@ -250,10 +248,10 @@ def main():
     }
     if not args.no_cpu_baseline:
         try:
-            cores = min(os.cpu_count() or 1, 64)
-            v, dt = run_reference_sample(cores * 4, cores)
+            cores = os.cpu_count() or 1
+            v, dt = run_reference_sample(cores * 2, cores)
             line["cpu_baseline"] = {"value": v, "unit": "Mbp/s", "cores": cores, "kind": "reference",
-                                    "sample": "%d windows x 50 kb (%.1f s wall), one unmodified augustus process per core" % (cores * 4, dt)}
+                                    "sample": "%d windows x 50 kb (%.1f s wall), one unmodified augustus process per core" % (cores * 2, dt)}
         except Exception as ex:   # the reference binary did not travel: time the oracle port instead
             orc = util.Oracle(util.blob_bytes())
             t0 = time.perf_counter(); k = 8
