@@ -231,6 +231,12 @@ def main():
     value = world * bases / 1e6 / (ms_per_step / 1e3)
     peak, how = peaks()
     achieved = ALG_BYTES_PER_BASE * bases / (sweep_ms / 1e3) / 1e9
+    traffic = None
+    try:   # DRAM bytes of the sweep kernel from the committed ncu --set full capture (per base, scaled to this launch)
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_sweep_2368win.json")))
+        traffic = prof["dram_bytes_per_base"] * bases
+    except Exception:
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": "Mbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -240,9 +246,9 @@ def main():
                    "l2": "inputs per step (%.0f MB DNA + %.1f GB workspace) exceed the 126 MB L2" % (bases / 1e6, bases * 130 / 1e9)},
         "e2e": {"value": world * bases / 1e6 / e2e_s, "unit": "Mbp/s", "h2d_bytes_per_step": bases, "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": "k_sweep", "peak_source": how,
-                     "note": "achieved = 940 B/base (dense S=47 figure, SURVEY.md 8d) x bases / sweep-kernel time; the sweep stores only non-zero cells (see DESIGN.md)"},
+                     "note": "achieved = 940 B/base (dense S=47 figure, SURVEY.md 8d) x bases / sweep-kernel time; traffic = ncu dram bytes/base of profiles/r1_sweep_2368win.json x bases; the sweep stores only non-zero cells and is instruction-fetch bound, not bandwidth bound (DESIGN.md)"},
         "clocks": sampler.summary(),
         "sweep_ms": sweep_ms,
     }
