@@ -213,6 +213,11 @@ typedef struct {
     sc_t *PX[8][3], *PXR[8][3];                 /* exon content prefix sums [class][phi] (lazily built) */
     sc_t *PI[8], *PIR[8];                       /* intron content prefix sums per class (fwd k-mer / rc k-mer) */
     struct SnipEnt **snF, **snL;                /* SnippetProbs restatement: per base first/last entry, [2][L] (fwd, rc) */
+    /* forward / sampling (NAMGene::viterbiAndForward with needForwardTable, getSampledPath namgene.cc:367-426) */
+    int mode;                                   /* 0 Viterbi only, 1 Viterbi + forward fill, 2 sampling step */
+    double* F;                                  /* [L][S] ln forward, -inf = absent */
+    double lse_m, lse_s;                        /* running log-sum-exp of the forward sum of the current cell */
+    struct Opt { int state, base; double lp; } *opts; int nopt, capopt;     /* OptionsList of the current sampling step */
 } Ctx;
 
 static inline int at(const Ctx* x, int p) { return (p < 0 || p >= x->L) ? 5 : x->c[p]; }
@@ -438,6 +443,32 @@ static sc_t motif_rc(const Ctx* x, const sc_t* tab, int n, int k, int p) {
 typedef struct { sc_t max; int state, base; } Oli;
 #define VV(j, s) (x->V[(size_t)(j) * m->S + (s)])
 #define TR(a, s) (m->trans[((size_t)x->cls * m->S + (a)) * m->S + (s)])
+#define FF(j, s) (x->F[(size_t)(j) * m->S + (s)])
+/* value used for the "is this predecessor cell non-zero" tests: the Viterbi matrix while filling, the forward matrix while
+ * sampling (the reference clears the Viterbi matrix before it samples, namgene.cc:807-808) */
+static inline sc_t PVAL(const Ctx* x, int col, int a) {
+    const Model* m = x->m;
+    if (x->mode == 2) return FF(col, a) > -1e300 ? 0 : NEG;
+    return VV(col, a);
+}
+static inline double sc2d(sc_t v) { return ldexp((double)v, -FRAC_BITS); }
+/* one (predecessor a at column col, reported end e) option with log transition*emission `te`:
+ *   fill mode: fwdsum += forward[col][a] * transEmiProb           (e.g. exonmodel.cc:1094-1101, intronmodel.cc:609-617)
+ *   sampling : optionslist->add(a, e, forward[col][a] * transEmiProb) if > 0 */
+static void fwd_option(Ctx* x, int a, int col, int e, sc_t te) {
+    const Model* m = x->m;
+    if (x->mode == 0) return;
+    double f = FF(col, a);
+    if (!(f > -1e300) || isneg(te)) return;
+    double lp = f + sc2d(te);
+    if (x->mode == 1) {
+        if (lp > x->lse_m) { x->lse_s = x->lse_s * exp(x->lse_m - lp) + 1.0; x->lse_m = lp; }
+        else x->lse_s += exp(lp - x->lse_m);
+    } else {
+        if (x->nopt == x->capopt) { x->capopt = x->capopt ? 2 * x->capopt : 256; x->opts = realloc(x->opts, x->capopt * sizeof *x->opts); }
+        x->opts[x->nopt].state = a; x->opts[x->nopt].base = e; x->opts[x->nopt].lp = lp; x->nopt++;
+    }
+}
 
 /* ------------------------------------------------------------------ igenic, igenicmodel.cc:231-357 */
 static sc_t igenic_emi(const Ctx* x, int j) {
@@ -459,8 +490,9 @@ static void igenic_eval(Ctx* x, int s, int j, Oli* o) {
     /* max starts at -1 (igenicmodel.cc:238): the first ancestor is recorded even when every product is 0 */
     o->base = j - 1; o->max = NEG; o->state = st->nanc ? st->anc[0] : -1;
     for (int i = 0; i < st->nanc; i++) {
-        int a = st->anc[i]; sc_t pv = VV(j - 1, a);
+        int a = st->anc[i]; sc_t pv = PVAL(x, j - 1, a);
         if (isneg(pv)) continue;
+        fwd_option(x, a, j - 1, j - 1, TR(a, s) + emi);
         sc_t cur = pv + (TR(a, s) + emi);
         if (cur > o->max) { o->max = cur; o->state = a; }
     }
@@ -534,7 +566,7 @@ static void intron_eval(Ctx* x, int s, int j, Oli* o) {
         int lme = j - m->dStateLen; if (lme < 0) lme = 0;
         for (int e = j - 1; e >= lme; e--) {
             int any = 0;
-            for (int i = 0; i < st->nanc; i++) if (!isneg(VV(e, st->anc[i]))) { any = 1; break; }
+            for (int i = 0; i < st->nanc; i++) if (!isneg(PVAL(x, e, st->anc[i]))) { any = 1; break; }
             if (!any) continue;
             /* emiProbUnderModel(e+1, j), lessD branch :924-1000 */
             int begin = e + 1, bob;
@@ -553,7 +585,8 @@ static void intron_eval(Ctx* x, int s, int j, Oli* o) {
             sc_t ld = m->ld_intron[ilen]; if (isneg(ld)) continue;
             sc_t emi = ld + snip_get(x, !fwd, j, j - begin + 1);
             for (int i = 0; i < st->nanc; i++) {
-                int a = st->anc[i]; sc_t pv = VV(e, a); if (isneg(pv)) continue;
+                int a = st->anc[i]; sc_t pv = PVAL(x, e, a); if (isneg(pv)) continue;
+                fwd_option(x, a, e, e, TR(a, s) + emi);
                 sc_t pp = pv + (TR(a, s) + emi);
                 if (pp > o->max) { o->max = pp; o->state = a; o->base = e; }
             }
@@ -575,7 +608,7 @@ static void intron_eval(Ctx* x, int s, int j, Oli* o) {
     }
     if (abort_) return;
     int any = 0;
-    for (int i = 0; i < st->nanc; i++) if (!isneg(VV(eop, st->anc[i]))) { any = 1; break; }
+    for (int i = 0; i < st->nanc; i++) if (!isneg(PVAL(x, eop, st->anc[i]))) { any = 1; break; }
     if (!any) return;
     switch (st->kind) {
     case K_LONGDSS: emi = dSSProb(x, j - dssw + 1, fwd); break;
@@ -586,7 +619,8 @@ static void intron_eval(Ctx* x, int s, int j, Oli* o) {
     if (isneg(emi)) return;
     o->base = eop;
     for (int i = 0; i < st->nanc; i++) {
-        int a = st->anc[i]; sc_t pv = VV(eop, a); if (isneg(pv)) continue;
+        int a = st->anc[i]; sc_t pv = PVAL(x, eop, a); if (isneg(pv)) continue;
+        fwd_option(x, a, eop, eop, TR(a, s) + emi);
         sc_t pp = pv + (TR(a, s) + emi);
         if (pp > o->max) { o->max = pp; o->state = a; }
     }
@@ -779,10 +813,11 @@ static void exon_eval(Ctx* x, int s, int j, Oli* o) {
         int col = eop >= 0 ? eop : 0;
         int bobe = bos - st->innerPartOffset, len = eobe - bobe + 1;
         for (int i = 0; i < st->nanc; i++) {
-            int a = st->anc[i]; sc_t pv = VV(col, a); if (isneg(pv)) continue;
+            int a = st->anc[i]; sc_t pv = PVAL(x, col, a); if (isneg(pv)) continue;
             int pf = m->st[a].frame;
             if (st->ek == E_SINGLE || st->ek == E_RSINGLE || st->ek == E_RTERMINAL || st->ek == E_INITIAL ||
                 win == mod3(fwd ? pf + len : pf - len)) {
+                fwd_option(x, a, col, eop, TR(a, s) + ep + nep);
                 sc_t pp = pv + (TR(a, s) + ep + nep);
                 if (pp > o->max) { o->max = pp; o->base = eop; o->state = a; }
             }
@@ -807,14 +842,56 @@ static int trunc_flag(int type, int end, int predEnd, int L) {      /* gene.cc:3
     return t;
 }
 
+/* stable descending sort of the options by probability (OptionsList::prepareSampling = list::sort with
+ * operator< "larger probability first", vitmatrix.hh:760-796) */
+typedef struct { double lp; int idx; } OptKey;
+static int optcmp(const void* a, const void* b) {
+    const OptKey* p = (const OptKey*)a; const OptKey* q = (const OptKey*)b;
+    if (p->lp > q->lp) return -1;
+    if (p->lp < q->lp) return 1;
+    return p->idx - q->idx;
+}
+/* OptionsList::sample (vitmatrix.cc:295-320) on x->opts; returns the chosen index, *lognorm = ln(prob / cumprob) */
+static int opt_sample(Ctx* x, double* lognorm) {
+    int n = x->nopt; if (n == 0) return -1;
+    double mx = -INFINITY;
+    for (int i = 0; i < n; i++) if (x->opts[i].lp > mx) mx = x->opts[i].lp;
+    double cum = 0;                                  /* cumprob accumulates in insertion order (OptionsList::add) */
+    for (int i = 0; i < n; i++) cum += exp(x->opts[i].lp - mx);
+    OptKey* k = (OptKey*)malloc(n * sizeof *k);
+    for (int i = 0; i < n; i++) { k[i].lp = x->opts[i].lp; k[i].idx = i; }
+    qsort(k, n, sizeof *k, optcmp);
+    double z = ((double)rand() / RAND_MAX) * cum * 0.99999, cs = 0; int pick = -1;
+    for (int i = 0; i < n && pick < 0; i++) { cs += exp(k[i].lp - mx); if (z < cs) pick = k[i].idx; }
+    if (pick < 0) pick = k[0].idx;                  /* "Sampling Error which should not happen": first option */
+    *lognorm = x->opts[pick].lp - mx - log(cum);
+    free(k);
+    return pick;
+}
+
+/* condense (StatePath::condenseStatePath, gene.cc:977-1000) a left-to-right list in place; returns the new length */
+static int condense_path(int n, int* t, int* b, int* e, int* tr) {
+    int o = 0;
+    for (int i = 0; i < n; i++) {
+        int coding = (t[i] >= 1 && t[i] <= 8) || (t[i] >= 36 && t[i] <= 43);
+        if (o > 0 && t[o - 1] == t[i] && !coding) { e[o - 1] = e[i]; tr[o - 1] |= tr[i]; }
+        else { t[o] = t[i]; b[o] = b[i]; e[o] = e[i]; tr[o] = tr[i]; o++; }
+    }
+    return o;
+}
+
 /*
  * Decode one window.  dna: ASCII, any case.  gc_in: per-position class or NULL (computed here).
  * Vout: optional [L][S] int64 Q40 scores (NEG = absent).  Path arrays (capacity cap) are filled in
  * left-to-right order, one entry per backtrace step exactly as NAMGene::getViterbiPath pushes them.
- * Returns number of path states, or <0: -1 no feasible path, -2 stuck, -3 capacity.
+ * nsample > 1: the forward matrix is filled as well (Fout optional, [L][S] ln values, -inf = absent) and nsample-1 paths
+ * are sampled as NAMGene::findGenes does (namgene.cc:833-871) with glibc rand() restarted at seed 1; they are returned
+ * CONDENSED, concatenated in s_* (capacity scap), s_count[i] states and s_logp[i] = ln pathemiProb for sample i.
+ * Returns number of Viterbi path states, or <0: -1 no feasible path, -2 stuck, -3 capacity.
  */
-int orc_viterbi(const Model* m, const char* dna, int L, const int* gc_in, int64_t* Vout, int* gc_out,
-                int cap, int* ptype, int* pbegin, int* pend, int* ptrunc, double* logp) {
+int orc_decode(const Model* m, const char* dna, int L, const int* gc_in, int64_t* Vout, int* gc_out,
+               int cap, int* ptype, int* pbegin, int* pend, int* ptrunc, double* logp,
+               int nsample, double* Fout, int scap, int* s_type, int* s_begin, int* s_end, int* s_trunc, int* s_count, double* s_logp) {
     Ctx X; memset(&X, 0, sizeof X); Ctx* x = &X;
     x->m = m; x->L = L;
     uint8_t* c = (uint8_t*)malloc(L + 8);
@@ -832,18 +909,30 @@ int orc_viterbi(const Model* m, const char* dna, int L, const int* gc_in, int64_
     orf_init(x);
     x->snF = (SnipEnt**)calloc((size_t)2 * L, sizeof(SnipEnt*)); x->snL = (SnipEnt**)calloc((size_t)2 * L, sizeof(SnipEnt*));
     x->V = (sc_t*)malloc((size_t)L * m->S * sizeof(sc_t));
-    for (int s = 0; s < m->S; s++) x->V[s] = m->init[s];
+    const int fwd = nsample > 1;
+    if (fwd) x->F = (double*)malloc((size_t)L * m->S * sizeof(double));
+    for (int s = 0; s < m->S; s++) { x->V[s] = m->init[s]; if (fwd) x->F[s] = isneg(m->init[s]) ? -INFINITY : sc2d(m->init[s]); }
     Oli o;
+    x->mode = fwd ? 1 : 0;
     if (!anynuc) {   /* namgene.cc:205-226 */
-        for (int j = 1; j < L; j++) for (int s = 0; s < m->S; s++) VV(j, s) = s == 0 ? VV(j - 1, s) + m->log025 : NEG;
+        for (int j = 1; j < L; j++) for (int s = 0; s < m->S; s++) {
+            VV(j, s) = s == 0 ? VV(j - 1, s) + m->log025 : NEG;
+            if (fwd) FF(j, s) = s == 0 ? FF(j - 1, s) + sc2d(m->log025) : -INFINITY;
+        }
     } else {
         for (int j = 1; j < L; j++) {
             x->cls = gc[j];
-            for (int s = 0; s < m->S; s++) { state_eval(x, s, j, &o); VV(j, s) = o.max; }
+            for (int s = 0; s < m->S; s++) {
+                x->lse_m = -INFINITY; x->lse_s = 0;
+                state_eval(x, s, j, &o); VV(j, s) = o.max;
+                if (fwd) FF(j, s) = x->lse_s > 0 ? x->lse_m + log(x->lse_s) : -INFINITY;
+            }
         }
     }
     if (Vout) memcpy(Vout, x->V, (size_t)L * m->S * sizeof(sc_t));
+    if (Fout && fwd) memcpy(Fout, x->F, (size_t)L * m->S * sizeof(double));
     /* getViterbiPath, namgene.cc:432-510 */
+    x->mode = 0;
     int ret = 0, state = -1; sc_t best = NEG;
     for (int s = 0; s < m->S; s++) {
         sc_t v = VV(L - 1, s); if (isneg(v) || isneg(m->term[s])) continue;
@@ -874,12 +963,63 @@ int orc_viterbi(const Model* m, const char* dna, int L, const int* gc_in, int64_
             ret = n;
         }
     }
+    /* sampling, NAMGene::getSampledPath namgene.cc:367-426; the process-wide rand() stream starts at seed 1 */
+    if (fwd && ret >= 0 && s_count) {
+        srand(1);
+        int used = 0;
+        int* tt = (int*)malloc((size_t)(L + 8) * 4 * sizeof(int)); int *tb = tt + L + 8, *te = tb + L + 8, *ttr = te + L + 8;
+        for (int it = 0; it < nsample - 1; it++) {
+            double lpath = 0; int n = 0, bad = 0;
+            if (!anynuc) { tt[0] = m->st[0].type; tb[0] = 0; te[0] = L - 1; ttr[0] = 0; n = 1; lpath = L * log(0.25); }
+            else {
+                x->mode = 2; x->nopt = 0;
+                for (int s = 0; s < m->S; s++) {
+                    double f = FF(L - 1, s);
+                    if (f > -1e300 && !isneg(m->term[s])) {
+                        if (x->nopt == x->capopt) { x->capopt = x->capopt ? 2 * x->capopt : 256; x->opts = realloc(x->opts, x->capopt * sizeof *x->opts); }
+                        x->opts[x->nopt].state = s; x->opts[x->nopt].base = L - 1; x->opts[x->nopt].lp = f + sc2d(m->term[s]); x->nopt++;
+                    }
+                }
+                double ln; int pick = opt_sample(x, &ln);
+                if (pick < 0) { bad = 1; }
+                else {
+                    int base = x->opts[pick].base, st = x->opts[pick].state; lpath += ln;
+                    while (base > 0 && !bad) {
+                        x->cls = gc[base]; x->nopt = 0;
+                        state_eval(x, st, base, &o);
+                        pick = opt_sample(x, &ln);
+                        if (pick < 0 || n >= L + 8) { bad = 1; break; }
+                        int ob = x->opts[pick].base, os = x->opts[pick].state;
+                        tt[n] = m->st[st].type; tb[n] = ob + 1; te[n] = base; ttr[n] = trunc_flag(m->st[st].type, base, ob, L); n++;
+                        base = ob; st = os; lpath += ln;
+                    }
+                }
+            }
+            if (bad) { s_count[it] = -1; s_logp[it] = 0; continue; }
+            for (int i = 0; i < n / 2; i++) {
+                int t;
+                t = tt[i]; tt[i] = tt[n - 1 - i]; tt[n - 1 - i] = t; t = tb[i]; tb[i] = tb[n - 1 - i]; tb[n - 1 - i] = t;
+                t = te[i]; te[i] = te[n - 1 - i]; te[n - 1 - i] = t; t = ttr[i]; ttr[i] = ttr[n - 1 - i]; ttr[n - 1 - i] = t;
+            }
+            n = condense_path(n, tt, tb, te, ttr);
+            if (used + n > scap) { s_count[it] = -3; continue; }
+            memcpy(s_type + used, tt, n * sizeof(int)); memcpy(s_begin + used, tb, n * sizeof(int));
+            memcpy(s_end + used, te, n * sizeof(int)); memcpy(s_trunc + used, ttr, n * sizeof(int));
+            s_count[it] = n; s_logp[it] = lpath; used += n;
+        }
+        free(tt);
+    }
     for (int cl = 0; cl < 8; cl++) {
         for (int p = 0; p < 3; p++) { free(x->PX[cl][p]); free(x->PXR[cl][p]); }
         free(x->PI[cl]); free(x->PIR[cl]);
     }
     for (size_t i = 0; i < (size_t)2 * L; i++) { SnipEnt* t = x->snF[i]; while (t) { SnipEnt* nx = t->next; free(t); t = nx; } }
-    free(x->snF); free(x->snL);
+    free(x->snF); free(x->snL); free(x->opts); free(x->F);
     free(x->V); free(x->nsf); free(x->nsr); free(gc); free(c);
     return ret;
+}
+
+int orc_viterbi(const Model* m, const char* dna, int L, const int* gc_in, int64_t* Vout, int* gc_out,
+                int cap, int* ptype, int* pbegin, int* pend, int* ptrunc, double* logp) {
+    return orc_decode(m, dna, L, gc_in, Vout, gc_out, cap, ptype, pbegin, pend, ptrunc, logp, 0, NULL, 0, NULL, NULL, NULL, NULL, NULL, NULL);
 }

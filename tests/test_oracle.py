@@ -77,6 +77,25 @@ def test_oracle_matches_reference_on_short_windows(oracle, golden):
         _check_against_ref(oracle, synth.window(idx, n), ref)
 
 
+def test_oracle_forward_and_sampling_match_reference(oracle):
+    """Config 5 path (--sample=100 --alternatives-from-sampling=true): the 99 sampled state paths per window are identical
+    to the reference's (same glibc rand() stream, one process per window) and forward cells agree to 1e-9."""
+    gold = util.golden_samples()
+    wins = {"example_HS08198": util.read_fasta(util.GOLDEN + "/example.fa")[1][1],
+            "synthetic_301_20000": synth.window(301, 20000),
+            "real_chr2L_5005000": util.read_fasta(util.GOLDEN + "/real_windows.fa")[0][1]}
+    for name, dna in wins.items():
+        ref = gold[name]
+        r = oracle.sample(dna, 100, want_forward=True)
+        assert len(r["samples"]) == len(ref["samples"]) == 99
+        for mine, theirs in zip(r["samples"], ref["samples"]):
+            assert mine["states"] == [tuple(x) for x in theirs["states"]]
+            assert abs(mine["log_prob"] - theirs["log_prob"]) <= 1e-6 * max(1.0, abs(theirs["log_prob"]))
+        for j, s, v in ref["forward_cells"]:
+            assert abs(r["F"][j, s] - v) <= 1e-9 * abs(v) + 1e-8
+        assert int(np.isfinite(r["F"][[c[0] for c in ref["forward_cells"]]]).sum()) >= len(ref["forward_cells"])
+
+
 # ---------------------------------------------------------------- host build of the kernel source
 def _cells_equal(oracle, emu, dna):
     o = oracle.viterbi(dna, want_matrix=True)

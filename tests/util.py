@@ -22,6 +22,11 @@ def blob_bytes():
     return params.load_bytes(os.path.join(GOLDEN, "human.params.xz"))
 
 
+def golden_samples():
+    import gzip
+    return json.load(gzip.open(os.path.join(GOLDEN, "ref_samples.json.gz"), "rt"))
+
+
 def golden_paths():
     return json.load(open(os.path.join(GOLDEN, "ref_paths.json")))
 
@@ -71,6 +76,9 @@ class Oracle:
         self.lib.orc_model_load.restype = ctypes.c_void_p
         self.lib.orc_model_load.argtypes = [ctypes.c_char_p]
         self.lib.orc_model_statecount.argtypes = [ctypes.c_void_p]
+        self.lib.orc_decode.restype = ctypes.c_int
+        self.lib.orc_decode.argtypes = ([ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+                                        + [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 6)
         self.lib.orc_viterbi.restype = ctypes.c_int
         self.lib.orc_viterbi.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 5
@@ -96,6 +104,31 @@ class Oracle:
                                  pt.ctypes.data, pb.ctypes.data, pe.ctypes.data, ptr.ctypes.data, ctypes.byref(lp))
         states = [(int(pt[k]), int(pb[k]), int(pe[k]), int(ptr[k])) for k in range(max(n, 0))]
         return {"n": n, "states": states, "condensed": condense(states), "log_prob": lp.value, "gc": gco, "V": V}
+
+
+    def sample(self, dna: str, nsample=100, gc=None, want_forward=False):
+        """Viterbi + forward fill + (nsample-1) sampled paths, as NAMGene::findGenes with sample=nsample."""
+        L = len(dna)
+        cap = L + 16
+        pa = [np.zeros(cap, dtype=np.int32) for _ in range(4)]
+        lp = ctypes.c_double()
+        F = np.zeros((L, self.S)) if want_forward else None
+        scap = nsample * (L // 8 + 64)
+        sa = [np.zeros(scap, dtype=np.int32) for _ in range(4)]
+        sc = np.zeros(nsample, dtype=np.int32)
+        slp = np.zeros(nsample)
+        gci = None if gc is None else np.ascontiguousarray(gc, dtype=np.int32)
+        n = self.lib.orc_decode(self.m, dna.encode(), L, None if gci is None else gci.ctypes.data, None, None, cap,
+                                *[a.ctypes.data for a in pa], ctypes.byref(lp), nsample, None if F is None else F.ctypes.data,
+                                scap, *[a.ctypes.data for a in sa], sc.ctypes.data, slp.ctypes.data)
+        samples, pos = [], 0
+        for k in range(nsample - 1):
+            c = int(sc[k])
+            samples.append({"log_prob": float(slp[k]),
+                            "states": [(int(sa[0][pos + q]), int(sa[1][pos + q]), int(sa[2][pos + q]), int(sa[3][pos + q])) for q in range(max(c, 0))]})
+            pos += max(c, 0)
+        viterbi = condense([(int(pa[0][k]), int(pa[1][k]), int(pa[2][k]), int(pa[3][k])) for k in range(max(n, 0))])
+        return {"n": n, "viterbi": viterbi, "log_prob": lp.value, "samples": samples, "F": F}
 
 
 class HostEmu:
