@@ -121,6 +121,9 @@ struct ChainCP {
     sc_t tilde;
 };
 
+/* forward (sum) counterpart of a chain: ln F[col][chain] = ft + A[col] from column col on, until the next entry */
+struct FChainCP { int32_t col; int32_t pad; double ft; };
+
 /* per-column signal score arrays written by the prep pass (ghmm_signal.h) */
 enum : int { SG_DSSF = 0, SG_DSSR = 1, SG_ASSF = 2, SG_ASSR = 3, SG_XRS = 4, NSIG = 5 };
 
@@ -149,6 +152,11 @@ struct WinView {
     Event* ev; int32_t* evstart;
     Cand* cl0; ChainCP* cp0;   /* list i / chain i start at cl0 + i*cl_stride, cp0 + i*cp_stride (no pointer tables: those end up in local memory) */
     int cl_stride, cp_stride;
+    /* forward pass (only when sampling is requested): ln forward value of every event / list entry, chain sums */
+    double* evF; double* clF0; FChainCP* fcp0; int fcp_stride, fcp_cap;
+    AUGB_HD double* clF(int i) const { return clF0 + (size_t)i * cl_stride; }
+    AUGB_HD FChainCP* fcp(int i) const { return fcp0 + (size_t)i * fcp_stride; }
+    int32_t* out_nfcp;
     SnipHead* snip_head;       /* [2][SNIP_RING] */
     SnipEnt* snip_pool;        /* [2][snip_cap] */
     SnipFrame* snip_stack;     /* [SNIP_RING] */

@@ -24,6 +24,7 @@ namespace augb {
 /* result / hand-over block of a window (WinLayout::outs) */
 struct WinOuts {
     int32_t n_ev, status, path_n, path_status; int32_t ncp[NCHAIN]; int32_t pad /* window flags */; sc_t score;
+    int32_t nfcp[NCHAIN]; int32_t pad2;
     const sc_t* slab[MAXC];     /* prefix-array slab of each GC class (set by prep) */
 };
 
@@ -32,6 +33,7 @@ struct WinLayout {
     size_t code, gc, mask, kf, kr, parr, sig, aig, ageo, nsf, nsr;        /* static (prep) */
     size_t ev, evstart, cl[NCL], cp[NCHAIN], outs;           /* dynamic (sweep) */
     size_t snip_head, snip_pool, snip_stack; int snip_cap;
+    size_t evF, clF, fcp; int fcp_cap;                       /* forward pass (0 capacity when not requested) */
     size_t path_begin, path_end, path_type, path_trunc;      /* backtrace output */
     size_t total, slab;
     int ev_cap, cl_cap, cp_cap, path_cap, nslab_local;
@@ -41,7 +43,7 @@ AUGB_HD size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
  * cell per state; a candidate list gets at most one entry per column); the default sizes are ~3x what human-like
  * DNA needs (measured: 1.9 events, 0.03 list entries per base) and a window that overflows them is reported with
  * status AUGB200_ERR_CAPACITY and decoded again with the generous layout (augb200.cu: decode_batch). */
-inline WinLayout make_layout(int L, int C, bool generous = false) {
+inline WinLayout make_layout(int L, int C, bool generous = false, bool forward = false) {
     WinLayout w; size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = al16(o + bytes); return r; };
     w.code = take(L); w.gc = take(L); w.mask = take((size_t)L * 2); w.kf = take((size_t)L * 2); w.kr = take((size_t)L * 2);
@@ -59,6 +61,9 @@ inline WinLayout make_layout(int L, int C, bool generous = false) {
     w.ev = take((size_t)w.ev_cap * sizeof(Event)); w.evstart = take((size_t)(L + 2) * 4);
     for (int i = 0; i < NCL; i++) w.cl[i] = take((size_t)w.cl_cap * sizeof(Cand));
     for (int i = 0; i < NCHAIN; i++) w.cp[i] = take((size_t)w.cp_cap * sizeof(ChainCP));
+    w.fcp_cap = forward ? (generous ? L + 64 : L / 2 + 64) : 0;
+    w.evF = take(forward ? (size_t)w.ev_cap * 8 : 0); w.clF = take(forward ? (size_t)NCL * w.cl_cap * 8 : 0);
+    w.fcp = take((size_t)NCHAIN * w.fcp_cap * sizeof(FChainCP));
     w.outs = take(sizeof(WinOuts));
     w.snip_cap = generous ? 262144 : 16384;
     w.snip_head = take((size_t)2 * SNIP_RING * sizeof(SnipHead)); w.snip_pool = take((size_t)2 * w.snip_cap * sizeof(SnipEnt));
@@ -77,9 +82,11 @@ AUGB_HD WinView make_view(char* base, const WinLayout& lay, int L, int classmask
     v.nsf = (const int32_t*)(base + lay.nsf); v.nsr = (const int32_t*)(base + lay.nsr);
     v.ev = (Event*)(base + lay.ev); v.evstart = (int32_t*)(base + lay.evstart);
     v.cl0 = (Cand*)(base + lay.cl[0]); v.cp0 = (ChainCP*)(base + lay.cp[0]);
+    v.evF = (double*)(base + lay.evF); v.clF0 = (double*)(base + lay.clF); v.fcp0 = (FChainCP*)(base + lay.fcp); v.fcp_cap = lay.fcp_cap; v.fcp_stride = lay.fcp_cap;
     v.snip_head = (SnipHead*)(base + lay.snip_head); v.snip_pool = (SnipEnt*)(base + lay.snip_pool); v.snip_stack = (SnipFrame*)(base + lay.snip_stack); v.snip_cap = lay.snip_cap;
     v.cl_stride = (int)((lay.cl[1] - lay.cl[0]) / sizeof(Cand)); v.cp_stride = (int)((lay.cp[1] - lay.cp[0]) / sizeof(ChainCP));
     WinOuts* o = (WinOuts*)(base + lay.outs);
+    v.out_nfcp = o->nfcp;
     v.out_n_ev = &o->n_ev; v.out_status = &o->status; v.out_ncp = o->ncp; v.flags = &o->pad;
     v.parr_c = o->slab;                                          /* filled by prep */
     return v;

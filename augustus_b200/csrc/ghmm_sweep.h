@@ -41,9 +41,16 @@ struct WarpState {
     int status;
     int any_pend;
     unsigned snip_cnt[2];       /* entries allocated so far per strand (ids start at 1) */
+    /* forward pass */
+    int fcp_n[NCHAIN];
+    double ftilde[NCHAIN];      /* ln F[j][chain] - A[j] of the current column */
+    Lse pend_f[NCHAIN];         /* log-sum of the entries into column j+1 */
 };
 
-struct Sweep {
+/* FWD = also fill the forward (sum) values needed by posterior sampling: the same candidates, log-sum-exp beside max
+ * (exonmodel.cc:1094-1101, intronmodel.cc:609-617, igenicmodel.cc:250-257) */
+template <bool FWD>
+struct SweepT {
     const DevModel* m; WinView w; WarpState* ws; Seq sq; int lane; int cls; int L;
     const sc_t* trc;            /* transition matrix of the current column's GC class */
 
@@ -75,6 +82,28 @@ struct Sweep {
         return SC_NEG;
     }
 
+    AUGB_D static double sc2d(sc_t v) { return (double)v * (1.0 / (double)((sc_t)1 << FRAC_BITS)); }
+    /* ln forward[e][a] (-1e308 = zero) */
+    AUGB_D double chain_fvalue(int ch, int e) const {
+        int n = ws->fcp_n[ch];
+        if (n == 0) return -1e308;
+        const FChainCP* cp = w.fcp(ch);
+        int lo = 0, hi = n - 1;
+        if (cp[0].col > e) return -1e308;
+        if (cp[hi].col <= e) lo = hi;
+        AUGB_ROLLED
+        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (cp[mid].col <= e) lo = mid; else hi = mid - 1; }
+        return cp[lo].ft + sc2d(chainA(ch)[e]);
+    }
+    AUGB_D double lookupF(int a, int e) const {
+        int ch = m->st[a].chain;
+        if (ch >= 0) return chain_fvalue(ch, e);
+        int lo = w.evstart[e], hi = w.evstart[e + 1];
+        AUGB_ROLLED
+        for (int i = lo; i < hi; i++) if (w.ev[i].state == a) return w.evF[i];
+        return -1e308;
+    }
+
     /* ------------------------------------------------------------ bookkeeping */
     AUGB_D void fill_evstart(int upto) {
         int f = ws->filled, n = ws->n_ev;
@@ -84,39 +113,45 @@ struct Sweep {
         if (lane == 0) ws->filled = upto;
         wsync();
     }
-    AUGB_D void cl_append(int list, int col, int state, sc_t V) {       /* lane 0 only; caller syncs */
+    AUGB_D void cl_append(int list, int col, int state, sc_t V, double F) {       /* lane 0 only; caller syncs */
         int n = ws->cl_n[list];
         if (n >= w.cl_cap) { ws->status = 8; return; }
         Cand c; c.col = col; c.state = state; c.V = V; w.cl(list)[n] = c; ws->cl_n[list] = n + 1;
+        if (FWD) w.clF(list)[n] = F;
+    }
+    /* a cell (j, s) whose state has a one-base transition into a self-loop chain: candidate for column j+1 of that chain,
+     * in tilde coordinates (lane 0 only) */
+    AUGB_D void feed_chain(int j, int s, sc_t V, double F) {
+        int ch = m->st[s].feeds;
+        if (ch < 0 || j + 1 >= L) return;
+        int c1 = w.gc[j + 1], cs = m->chain_state[ch];
+        const sc_t* T1 = m->trans + (size_t)c1 * m->S * m->S;
+        sc_t t_in = T1[s * m->S + cs], t_self = T1[cs * m->S + cs];
+        if (isneg(t_in)) return;
+        sc_t val = V + t_in - t_self - chainA(ch)[j];
+        if (val > ws->pend_val[ch] || (val == ws->pend_val[ch] && s < ws->pend_pred[ch])) { ws->pend_val[ch] = val; ws->pend_pred[ch] = s; }
+        ws->any_pend = 1;
+        if (FWD) ws->pend_f[ch].add(F + sc2d(t_in - t_self - chainA(ch)[j]));
     }
     /* record a non-zero cell; route it to the structures later columns look back to.  All lanes hold the same
      * arguments; lane 0 writes, one warp sync publishes. */
-    AUGB_D void emit(int j, int s, sc_t V, int pred, int predbase) {
+    AUGB_D void emit(int j, int s, sc_t V, int pred, int predbase, double F = 0) {
         if (lane == 0) {
             int n = ws->n_ev;
             if (n >= w.ev_cap) ws->status = 8;
             else {
                 Event e; e.state = (int16_t)s; e.pred = (int16_t)pred; e.predbase = predbase; e.V = V;
                 w.ev[n] = e; ws->n_ev = n + 1;
+                if (FWD) w.evF[n] = F;
                 const StateDesc& sd = m->st[s];
                 if (sd.kind == K_LONGDSS) {
-                    if (sd.fwd) cl_append(CL_LD + sd.frame, j, s, V);
-                    else cl_append(CL_RD + mod3(sd.frame + j + 1 - m->dss_start), j, s, V);      /* phase = mod3(pf + bobe), bobe = j+1-dss_start */
+                    if (sd.fwd) cl_append(CL_LD + sd.frame, j, s, V, F);
+                    else cl_append(CL_RD + mod3(sd.frame + j + 1 - m->dss_start), j, s, V, F);      /* phase = mod3(pf + bobe), bobe = j+1-dss_start */
                 } else if (sd.kind == K_LONGASS) {
-                    if (sd.fwd) cl_append(CL_LA + mod3(sd.frame - (j + 1 - m->ass_end)), j, s, V);   /* phase = mod3(pf - bobe) */
-                    else cl_append(CL_RA + sd.frame, j, s, V);
+                    if (sd.fwd) cl_append(CL_LA + mod3(sd.frame - (j + 1 - m->ass_end)), j, s, V, F);   /* phase = mod3(pf - bobe) */
+                    else cl_append(CL_RA + sd.frame, j, s, V, F);
                 }
-                int ch = sd.feeds;
-                if (ch >= 0 && j + 1 < L) {
-                    /* candidate for V[j+1][chain] in tilde coordinates */
-                    int c1 = w.gc[j + 1], cs = m->chain_state[ch];
-                    const sc_t* T1 = m->trans + (size_t)c1 * m->S * m->S;
-                    sc_t t_in = T1[s * m->S + cs], t_self = T1[cs * m->S + cs];
-                    if (!isneg(t_in)) {
-                        sc_t val = V + t_in - t_self - chainA(ch)[j];
-                        if (val > ws->pend_val[ch] || (val == ws->pend_val[ch] && s < ws->pend_pred[ch])) { ws->pend_val[ch] = val; ws->pend_pred[ch] = s; ws->any_pend = 1; }
-                    }
-                }
+                feed_chain(j, s, V, F);
             }
         }
         wsync();
@@ -136,6 +171,15 @@ struct Sweep {
                 if (take && n >= w.cp_cap) { ws->status = 8; take = false; }
                 if (take) { ChainCP c; c.col = j + 1; c.pred = pp; c.tilde = pv; w.cp(ch)[n] = c; ws->cp_n[ch] = n + 1; ws->tilde[ch] = pv; }
                 ws->pend_val[ch] = SC_NEG; ws->pend_pred[ch] = 0x7fffffff;
+                if (FWD && !ws->pend_f[ch].empty()) {
+                    /* forward[j+1][chain] = forward[j][chain]*self + sum of the entries: one more change point */
+                    Lse t = ws->pend_f[ch];
+                    if (ws->fcp_n[ch] > 0) t.add(ws->ftilde[ch]);
+                    int nf = ws->fcp_n[ch];
+                    if (nf >= w.fcp_cap) ws->status = 8;
+                    else { FChainCP c; c.col = j + 1; c.pad = 0; c.ft = t.value(); w.fcp(ch)[nf] = c; ws->fcp_n[ch] = nf + 1; ws->ftilde[ch] = c.ft; }
+                    ws->pend_f[ch].clear();
+                }
             }
             ws->any_pend = 0;
         }
@@ -397,17 +441,18 @@ struct Sweep {
         }
         const int lo = listkind ? (startMin < 1 ? 1 : startMin) : startMin;
         sc_t best = SC_NEG; int bkey = -0x7fffffff, bpred = -1, bbase = -1;
+        Lse fl; fl.clear();
         int step = 0; bool more = true;
         AUGB_ROLLED
         while (more) {
             /* lane's candidate: (bos, predecessor a, its cell value pv, its column eop) */
-            bool valid = false, below = false; int bos = 0, a = anc0, eop = 0; sc_t pv = SC_NEG, t = t0;
+            bool valid = false, below = false; int bos = 0, a = anc0, eop = 0; sc_t pv = SC_NEG, t = t0; double pf = 0;
             if (listkind) {
                 int i = ncl - 1 - step * AUGB_NLANES - lane;
                 if (i >= 0) {
                     Cand c = cl[i]; bos = c.col + 1;
                     if (bos < lo) below = true;
-                    else if (bos <= startMax && c.col < j) { valid = true; a = c.state; pv = c.V; eop = c.col; t = TR(a, s); }
+                    else if (bos <= startMax && c.col < j) { valid = true; a = c.state; pv = c.V; eop = c.col; t = TR(a, s); if (FWD) pf = w.clF(list)[i]; }
                 } else below = true;
                 more = wballot(below) == 0;
             } else if (scankind) {
@@ -417,7 +462,7 @@ struct Sweep {
                     int bobe = bos - 3; eop = bos - st.beginPartLen - 1;
                     if (bobe >= 0 && bobe < L - 2 && eop < L && !isneg(t0)) {
                         int pn = sq.kmer_end(bobe + 2, 3);
-                        if (pn >= 0 && !isneg(m->startp[pn])) { pv = lookupV(anc0, eop >= 0 ? eop : 0); valid = !isneg(pv); }
+                        if (pn >= 0 && !isneg(m->startp[pn])) { pv = lookupV(anc0, eop >= 0 ? eop : 0); valid = !isneg(pv); if (FWD && valid) pf = lookupF(anc0, eop >= 0 ? eop : 0); }
                     }
                 }
                 more = wballot(below) == 0;
@@ -425,7 +470,7 @@ struct Sweep {
                 more = step * AUGB_NLANES + AUGB_NLANES < st.nanc;
                 if (step * AUGB_NLANES + lane < st.nanc) {
                     bos = startMin; eop = bos - st.beginPartLen - 1; a = st.anc[step * AUGB_NLANES + lane]; t = TR(a, s);
-                    if (eop < L && !isneg(t)) { pv = lookupV(a, eop >= 0 ? eop : 0); valid = !isneg(pv); }
+                    if (eop < L && !isneg(t)) { pv = lookupV(a, eop >= 0 ? eop : 0); valid = !isneg(pv); if (FWD && valid) pf = lookupF(a, eop >= 0 ? eop : 0); }
                 }
             }
             step++;
@@ -476,6 +521,7 @@ struct Sweep {
             if (valid && !isneg(nep)) {
                 sc_t sc = pv + (t + ep + nep); int key = bos * 128 + (127 - a);
                 if (sc > best || (sc == best && key > bkey)) { best = sc; bkey = key; bpred = a; bbase = eop; }
+                if (FWD) fl.add(pf + sc2d(t + ep + nep));
             }
         }
         if (listkind && startMin == 0) {
@@ -490,11 +536,14 @@ struct Sweep {
                 if (isneg(nep0)) break;
                 sc_t sc = pv + (t + ep + nep0); int key = 127 - a;
                 if (lane == 0 && (sc > best || (sc == best && key > bkey))) { best = sc; bkey = key; bpred = a; bbase = -1; }
+                if (FWD && lane == 0) fl.add(sc2d(pv) + sc2d(t + ep + nep0));
             }
         }
         int wl = wargbest(best, bkey);
         if (wl < 0) return;
-        emit(j, s, wbcast64(best, wl), wbcast(bpred, wl), wbcast(bbase, wl));
+        double Fv = 0;
+        if (FWD) Fv = wlse(fl).value();
+        emit(j, s, wbcast64(best, wl), wbcast(bpred, wl), wbcast(bbase, wl), Fv);
     }
 
     /* ------------------------------------------------------------ intron states */
@@ -511,22 +560,23 @@ struct Sweep {
             int s = kind == K_LONGDSS ? m->r_longdss[dir][f] : m->r_longass[dir][f];
             if (s < 0) continue;
             const StateDesc& st = m->st[s];
-            sc_t best = SC_NEG; int bpred = -1;
+            sc_t best = SC_NEG; int bpred = -1; Lse fl; fl.clear();
             AUGB_ROLLED
             for (int i = 0; i < st.nanc; i++) {
                 int a = st.anc[i]; sc_t t = TR(a, s); if (isneg(t)) continue;
                 sc_t pv = lookupV(a, eop); if (isneg(pv)) continue;
                 sc_t pp = pv + (t + emi);
                 if (pp > best) { best = pp; bpred = a; }
+                if (FWD) fl.add(lookupF(a, eop) + sc2d(t + emi));
             }
-            if (!isneg(best)) emit(j, s, best, bpred, eop);
+            if (!isneg(best)) emit(j, s, best, bpred, eop, FWD ? fl.value() : 0.0);
         }
     }
     /* equalD / requalD (intronmodel.cc:695-698, 889-894): fires dStateLen columns after a longdss / rlongass cell */
     AUGB_D void equald_eval(int dir, int f, int j) {
         int s = m->r_equald[dir][f]; int list = (dir ? CL_RA : CL_LD) + f;
         int cur = ws->eq_cur[dir * 3 + f];
-        Cand c = w.cl(list)[cur];
+        Cand c = w.cl(list)[cur]; double cf = FWD ? w.clF(list)[cur] : 0.0;
         wsync();
         if (lane == 0) ws->eq_cur[dir * 3 + f] = cur + 1;
         wsync();
@@ -536,7 +586,7 @@ struct Sweep {
         sc_t emi = P[j + 1] - P[eop + 1];
         sc_t t = TR(c.state, s);
         if (isneg(t)) return;
-        emit(j, s, c.V + (t + emi), c.state, eop);
+        emit(j, s, c.V + (t + emi), c.state, eop, cf + sc2d(t + emi));
     }
     /* ------------------------------------------------------------ SnippetProbs memo near GC-class boundaries
      *
@@ -636,7 +686,7 @@ struct Sweep {
                 else if (!fwd && f == 0) { cod0 = cmpl(sq.at(eob + 1)); }
                 else if (!fwd && f == 1) { cod0 = cmpl(sq.at(eob + 2)); cod1 = cmpl(sq.at(eob + 1)); }
             }
-            sc_t best = SC_NEG; int bkey = -0x7fffffff, bpred = -1;
+            sc_t best = SC_NEG; int bkey = -0x7fffffff, bpred = -1; Lse fl; fl.clear();
             bool done = false;
             const int nl = slow ? 1 : AUGB_NLANES;            /* emulated columns: lane 0 walks the candidates in the reference's order */
             AUGB_ROLLED
@@ -665,6 +715,7 @@ struct Sweep {
                                 sc_t seq = slow ? snip_get(dir, j, j - begin + 1) : P[j + 1] - P[begin];
                                 sc_t sc = c.V + (t + (ld + seq));
                                 if (sc > best || (sc == best && e > bkey)) { best = sc; bkey = e; bpred = c.state; }
+                                if (FWD) fl.add(w.clF(list)[i] + sc2d(t + (ld + seq)));
                             }
                         }
                     }
@@ -673,7 +724,9 @@ struct Sweep {
             }
             int wl = wargbest(best, bkey);
             if (wl < 0) continue;
-            emit(j, s, wbcast64(best, wl), wbcast(bpred, wl), wbcast(bkey, wl));
+            double Fv = 0;
+            if (FWD) Fv = wlse(fl).value();
+            emit(j, s, wbcast64(best, wl), wbcast(bpred, wl), wbcast(bkey, wl), Fv);
         }
     }
 
@@ -715,7 +768,7 @@ struct Sweep {
             AUGB_ROLLED
             for (int i = 0; i < 6; i++) ws->eq_cur[i] = 0;
             AUGB_ROLLED
-            for (int i = 0; i < NCHAIN; i++) { ws->cp_n[i] = 0; ws->tilde[i] = SC_NEG; ws->pend_val[i] = SC_NEG; ws->pend_pred[i] = 0x7fffffff; }
+            for (int i = 0; i < NCHAIN; i++) { ws->cp_n[i] = 0; ws->tilde[i] = SC_NEG; ws->pend_val[i] = SC_NEG; ws->pend_pred[i] = 0x7fffffff; ws->fcp_n[i] = 0; ws->ftilde[i] = -1e308; ws->pend_f[i].clear(); }
         }
         wsync();
         set_class(w.gc[0]);
@@ -731,18 +784,23 @@ struct Sweep {
             int ch = m->st[s].chain;
             if (alln && ch != 0) continue;
             if (ch >= 0) {
-                if (lane == 0) { ChainCP c; c.col = 0; c.pred = -1; c.tilde = v; w.cp(ch)[0] = c; ws->cp_n[ch] = 1; ws->tilde[ch] = v; }
+                if (lane == 0) {
+                    ChainCP c; c.col = 0; c.pred = -1; c.tilde = v; w.cp(ch)[0] = c; ws->cp_n[ch] = 1; ws->tilde[ch] = v;
+                    if (FWD) { FChainCP f; f.col = 0; f.pad = 0; f.ft = sc2d(v); w.fcp(ch)[0] = f; ws->fcp_n[ch] = 1; ws->ftilde[ch] = f.ft; }
+                }
                 wsync();
             } else {
                 int n = ws->n_ev;
-                if (lane == 0) { Event e; e.state = (int16_t)s; e.pred = -1; e.predbase = -1; e.V = v; w.ev[n] = e; ws->n_ev = n + 1; }
+                if (lane == 0) { Event e; e.state = (int16_t)s; e.pred = -1; e.predbase = -1; e.V = v; w.ev[n] = e; ws->n_ev = n + 1; if (FWD) w.evF[n] = sc2d(v); }
                 wsync();
                 const StateDesc& sd = m->st[s];
-                if (lane == 0 && sd.kind == K_LONGDSS && sd.fwd) cl_append(CL_LD + sd.frame, 0, s, v);
-                if (lane == 0 && sd.kind == K_LONGASS && !sd.fwd) cl_append(CL_RA + sd.frame, 0, s, v);
+                if (lane == 0 && sd.kind == K_LONGDSS && sd.fwd) cl_append(CL_LD + sd.frame, 0, s, v, sc2d(v));
+                if (lane == 0 && sd.kind == K_LONGASS && !sd.fwd) cl_append(CL_RA + sd.frame, 0, s, v, sc2d(v));
+                if (lane == 0 && !alln) feed_chain(0, s, v, sc2d(v));
                 wsync();
             }
         }
+        apply_pending(0);
         AUGB_ROLLED
         for (int j0 = 1; j0 < L; j0 += 32) {
             /* static activity of the next 32 columns + equalD columns that fall into them */
@@ -790,10 +848,13 @@ struct Sweep {
         if (lane == 0) {
             *w.out_n_ev = ws->n_ev; *w.out_status = ws->status;
             AUGB_ROLLED
-            for (int i = 0; i < NCHAIN; i++) w.out_ncp[i] = ws->cp_n[i];
+            for (int i = 0; i < NCHAIN; i++) { w.out_ncp[i] = ws->cp_n[i]; w.out_nfcp[i] = FWD ? ws->fcp_n[i] : 0; }
         }
         wsync();
     }
 };
+
+typedef SweepT<false> Sweep;
+typedef SweepT<true> SweepFwd;
 
 }  // namespace augb

@@ -7,6 +7,7 @@
  * the kernel can be checked against the oracle in a container without a GPU.
  */
 #pragma once
+#include <math.h>
 #include "ghmm_defs.h"
 
 namespace augb {
@@ -27,6 +28,14 @@ AUGB_D int wmaxi(int v) {
     for (int o = 16; o; o >>= 1) { int t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
     return v;
 }
+AUGB_D double wmaxd(double v) {
+    for (int o = 16; o; o >>= 1) { double t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+    return v;
+}
+AUGB_D double wsumd(double v) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
 AUGB_D unsigned wballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 AUGB_D int wbcast(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 AUGB_D sc_t wbcast64(sc_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -38,6 +47,8 @@ inline void wsync() {}
 inline sc_t wmax(sc_t v) { return v; }
 inline sc_t wsum(sc_t v) { return v; }
 inline int wmaxi(int v) { return v; }
+inline double wmaxd(double v) { return v; }
+inline double wsumd(double v) { return v; }
 inline unsigned wballot(bool p) { return p ? 1u : 0u; }
 inline int wbcast(int v, int) { return v; }
 inline sc_t wbcast64(sc_t v, int) { return v; }
@@ -52,6 +63,23 @@ AUGB_D int wargbest(sc_t score, int key) {
     if (isneg(m)) return -1;
     int k = wmaxi(score == m ? key : -0x7fffffff);
     return wffs(wballot(score == m && key == k));
+}
+
+/* running log-sum-exp: value = m + ln(s); empty = (m = -inf, s = 0) */
+struct Lse {
+    double m, s;
+    AUGB_HD void clear() { m = -1e308; s = 0; }
+    AUGB_HD void add(double lp) {
+        if (lp > m) { s = s * exp(m - lp) + 1.0; m = lp; } else s += exp(lp - m);
+    }
+    AUGB_HD bool empty() const { return !(s > 0); }
+    AUGB_HD double value() const { return s > 0 ? m + log(s) : -1e308; }
+};
+/* combine the per-lane accumulators of a warp */
+AUGB_D Lse wlse(Lse a) {
+    double M = wmaxd(a.m);
+    Lse r; r.m = M; r.s = wsumd(a.s > 0 ? a.s * exp(a.m - M) : 0.0);
+    return r;
 }
 
 }  // namespace augb

@@ -74,6 +74,32 @@ int hostemu_decode(void* mp, const char* dna, int L, const int32_t* gc_in,
     if (gc_out) memcpy(gc_out, v.gc, L);
     return n;
 }
+/* forward fill: returns ln forward of every event (aligned with ev_col / ev_state) and of the chains per column */
+int hostemu_forward(void* mp, const char* dna, int L, const int32_t* gc_in, int evcap, int32_t* ev_col, int32_t* ev_state, double* ev_F,
+                    int32_t* n_ev_out, double* chainF /* [L][NCHAIN] */, int32_t* status) {
+    EmuModel* e = (EmuModel*)mp; const DevModel* m = &e->hm.dm;
+    WinLayout lay; std::vector<char> buf; char* base = nullptr; WinView v; WarpState ws; SweepFwd sw; WinOuts* outs = nullptr;
+    std::vector<char> pool; size_t pool_used = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        lay = make_layout(L, m->C, pass == 1, true);
+        buf.assign(lay.total + 64, 0);
+        base = buf.data();
+        int cm = 0;
+        pool.assign((size_t)(m->C) * lay.slab + 64, 0); pool_used = 0;
+        prep_window_seq(m, dna, L, gc_in, base, lay, &cm, pass == 0 ? pool.data() : nullptr, pool.size(), &pool_used);
+        v = make_view(base, lay, L, cm);
+        sw = SweepFwd(); sw.m = m; sw.w = v; sw.ws = &ws;
+        sw.run();
+        outs = (WinOuts*)(base + lay.outs);
+        if (outs->status != AUGB200_ERR_CAPACITY) break;
+    }
+    *status = outs->status;
+    int ne = outs->n_ev; *n_ev_out = ne;
+    for (int j = 0; j < L; j++) for (int i = v.evstart[j]; i < v.evstart[j + 1] && i < evcap; i++) ev_col[i] = j;
+    for (int i = 0; i < ne && i < evcap; i++) { ev_state[i] = v.ev[i].state; ev_F[i] = v.evF[i]; }
+    if (chainF) for (int j = 0; j < L; j++) for (int ch = 0; ch < NCHAIN; ch++) chainF[(size_t)j * NCHAIN + ch] = m->chain_state[ch] >= 0 ? sw.chain_fvalue(ch, j) : -1e308;
+    return ne;
+}
 int hostemu_chain_state(void* mp, int ch) { return ((EmuModel*)mp)->hm.dm.chain_state[ch]; }
 
 }  // extern "C"
