@@ -124,6 +124,9 @@ struct ChainCP {
 /* forward (sum) counterpart of a chain: ln F[col][chain] = ft + A[col] from column col on, until the next entry */
 struct FChainCP { int32_t col; int32_t pad; double ft; };
 
+/* one (predecessor, predecessor end) option of a sampling step: OptionListItem (vitmatrix.hh:748-770) */
+struct SampleOpt { double lp; int32_t ord /* insertion order in the reference's loops */, pred, eop, pad; };
+
 /* per-column signal score arrays written by the prep pass (ghmm_signal.h) */
 enum : int { SG_DSSF = 0, SG_DSSR = 1, SG_ASSF = 2, SG_ASSR = 3, SG_XRS = 4, NSIG = 5 };
 

@@ -1,0 +1,219 @@
+/*
+ * ghmm_sample.h — posterior sampling of state paths from the forward values (host + device, one warp per window).
+ *
+ * Replaces NAMGene::getSampledPath (namgene.cc:367-426) and the doSampling branches of the state models: at every step
+ * all (predecessor, predecessor end) options of the current cell are listed with probability forward[e][p] * a * emission,
+ * sorted by descending probability (OptionsList::prepareSampling, a stable list::sort, vitmatrix.hh:794-796) and one is
+ * drawn with  z = rand()/RAND_MAX * cumprob * 0.99999  (OptionsList::sample, vitmatrix.cc:295-320).  The draws come from the
+ * caller-supplied stream of rand() values, consumed in the reference's order: one for the last column, then one per path
+ * step — including every single-base step of an intergenic / geometric-intron run, which is why a run of self transitions
+ * is skipped in one go by advancing the stream.
+ */
+#pragma once
+#include "ghmm_sweep.h"
+
+namespace augb {
+
+struct SampleOut {
+    int cap;                         /* capacity of the state arrays (all samples of the window together) */
+    int32_t *begin, *end; uint8_t *type, *trunc;
+    int32_t* count; double* logp;    /* per sample */
+    int32_t* status;
+};
+struct SampleScratch { SampleOpt* opt; int opt_cap; int32_t* sorted; int* nopt; };
+
+AUGB_HD int trunc_flag_s(int type, int end, int predEnd, int L) {
+    bool isIntron = (type >= T_LESSD0 && type <= 23) || (type >= T_RLESSD0 && type <= 58);
+    int t = 0;
+    if (end == L - 1 && ((type >= 2 && type <= 7) || (type >= 38 && type <= 43) || isIntron)) t |= 2;
+    if ((predEnd == -1 || predEnd == 0) && ((type >= 5 && type <= 8) || (type >= 37 && type <= 40) || isIntron)) t |= 1;
+    return t;
+}
+
+struct Sampler {
+    SweepFwd* sw; SampleScratch sc; const uint32_t* rng; int nrng; int cursor; int lane;
+
+    /* draw one option; returns its index in sc.opt (or -1), adds ln(p/cumprob) to *lp */
+    AUGB_D int pick(double* lp) {
+        const int n = *sc.nopt;
+        if (n > sc.opt_cap) return -2;
+        if (n <= 0 || cursor >= nrng) return -1;
+        double mx = -1e308;
+        AUGB_ROLLED
+        for (int i = lane; i < n; i += AUGB_NLANES) { double v = sc.opt[i].lp; mx = v > mx ? v : mx; }
+        mx = wmaxd(mx);
+        /* stable descending order by probability: rank = options that come first */
+        AUGB_ROLLED
+        for (int i = lane; i < n; i += AUGB_NLANES) {
+            const double v = sc.opt[i].lp; const int o = sc.opt[i].ord; int r = 0;
+            AUGB_ROLLED
+            for (int k = 0; k < n; k++) { double u = sc.opt[k].lp; r += (u > v || (u == v && (sc.opt[k].ord < o || (sc.opt[k].ord == o && k < i)))) ? 1 : 0; }
+            sc.sorted[r] = i;
+        }
+        wsync();
+        int res = -1; double add = 0;
+        if (lane == 0) {
+            /* cumprob accumulates in insertion order (OptionsList::add); insertion order = ascending `ord`, which is how the
+             * options sit in the buffer when one lane lists them; with 32 lanes the buffer order is the same because lanes take
+             * candidates in the reference's order */
+            double cum = 0;
+            AUGB_ROLLED
+            for (int i = 0; i < n; i++) cum += exp(sc.opt[i].lp - mx);
+            const double z = ((double)rng[cursor] / 2147483647.0) * cum * 0.99999;
+            double cs = 0;
+            AUGB_ROLLED
+            for (int r = 0; r < n && res < 0; r++) { int i = sc.sorted[r]; cs += exp(sc.opt[i].lp - mx); if (z < cs) res = i; }
+            if (res < 0) res = sc.sorted[0];
+            add = sc.opt[res].lp - mx - log(cum);
+        }
+        res = wbcast(res, 0);
+        cursor++;
+#if defined(__CUDA_ARCH__)
+        add = __shfl_sync(0xffffffffu, add, 0);
+#endif
+        *lp += add;
+        return res;
+    }
+
+    /* all paths of one window */
+    AUGB_D void run(int nsamples, SampleOut out) {
+        SweepFwd& S = *sw; const DevModel* m = S.m; const int L = S.L;
+        lane = lane_id(); cursor = 0;
+        S.opt = sc.opt; S.nopt = sc.nopt; S.opt_cap = sc.opt_cap;
+        int used = 0, status = 0;
+        const bool alln = (*S.w.flags & WF_ALLN) != 0;
+        AUGB_ROLLED
+        for (int it = 0; it < nsamples && !status; it++) {
+            double lp = 0; int first = used, bad = 0;
+            if (alln) {
+                if (used >= out.cap) { status = 8; break; }
+                if (lane == 0) { out.begin[used] = 0; out.end[used] = L - 1; out.type[used] = (uint8_t)m->st[m->chain_state[0]].type; out.trunc[used] = 0; }
+                used++; lp = (double)L * SweepFwd::sc2d(m->log025);
+            } else {
+                /* last column x termProbs (namgene.cc:385-392) */
+                if (lane == 0) *sc.nopt = 0;
+                wsync();
+                AUGB_ROLLED
+                for (int s = 0; s < m->S; s++) {
+                    sc_t t = m->term[s];
+                    double f = isneg(t) ? -1e308 : S.lookupF(s, L - 1);
+                    S.push_opt(lane == 0 && f > -1e300, f + SweepFwd::sc2d(t), s, s, L - 1);
+                }
+                int k = pick(&lp);
+                if (k < 0) { bad = 1; if (k == -2) status = 8; }
+                int state = bad ? 0 : sc.opt[k].pred, base = L - 1;
+                int run_end = -1;      /* right end of the chain run being collected (-1: none) */
+                AUGB_ROLLED
+                while (base > 0 && !bad) {
+                    const StateDesc& sd = m->st[state];
+                    S.set_class(S.w.gc[base]);
+                    if (lane == 0) *sc.nopt = 0;
+                    wsync();
+                    int ch = sd.chain, pred, eop;
+                    if (ch >= 0) {
+                        if (run_end < 0) run_end = base;
+                        /* last forward change point at or left of base */
+                        const FChainCP* cp = S.w.fcp(ch); int lo = 0, hi = S.ws->fcp_n[ch] - 1;
+                        if (hi < 0 || cp[0].col > base) { bad = 1; break; }
+                        if (cp[hi].col <= base) lo = hi;
+                        AUGB_ROLLED
+                        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (cp[mid].col <= base) lo = mid; else hi = mid - 1; }
+                        const int c = cp[lo].col;
+                        if (c < base) { cursor += base - c; base = c; if (cursor > nrng) { bad = 1; break; } }   /* self-only steps, one draw each */
+                        if (base == 0) break;
+                        /* column `base` received entries: choose among the ancestors at base-1, index order (igenicmodel.cc:247-261) */
+                        AUGB_ROLLED
+                        for (int i = 0; i < sd.nanc; i++) {
+                            int a = sd.anc[i]; sc_t t = S.TR(a, state);
+                            double f = isneg(t) ? -1e308 : S.lookupF(a, base - 1);
+                            S.push_opt(lane == 0 && f > -1e300, f + SweepFwd::sc2d(t), i, a, base - 1);
+                        }
+                        k = pick(&lp);
+                        if (k < 0) { bad = 1; if (k == -2) status = 8; break; }
+                        pred = sc.opt[k].pred; eop = base - 1;
+                        if (pred == state) { base = eop; continue; }          /* the run goes on */
+                        if (used >= out.cap) { status = 8; break; }
+                        if (lane == 0) {
+                            out.begin[used] = base; out.end[used] = run_end; out.type[used] = (uint8_t)sd.type;
+                            out.trunc[used] = (uint8_t)((trunc_flag_s(sd.type, run_end, run_end - 1, L) & 2) | (trunc_flag_s(sd.type, base, base - 1, L) & 1));
+                        }
+                        used++; run_end = -1;
+                    } else {
+                        S.only = state;
+                        const int dir = sd.fwd ? 0 : 1;
+                        if (sd.kind == K_EXON) S.exon_eval(state, base);
+                        else if (sd.kind == K_LESSD) S.lessd_eval(dir, base);
+                        else if (sd.kind == K_EQUALD) S.equald_eval(dir, sd.frame, base);
+                        else S.fixed_eval(sd.kind, dir, base);
+                        S.only = -1;
+                        k = pick(&lp);
+                        if (k < 0) { bad = 1; if (k == -2) status = 8; break; }
+                        pred = sc.opt[k].pred; eop = sc.opt[k].eop;
+                        if (used >= out.cap) { status = 8; break; }
+                        if (lane == 0) { out.begin[used] = eop + 1; out.end[used] = base; out.type[used] = (uint8_t)sd.type; out.trunc[used] = (uint8_t)trunc_flag_s(sd.type, base, eop, L); }
+                        used++;
+                    }
+                    state = pred; base = eop;
+                }
+                if (!bad && !status && run_end >= 0) {     /* the walk ended inside a chain run that reaches column 1 */
+                    if (used >= out.cap) status = 8;
+                    else {
+                        const StateDesc& sd = m->st[state];
+                        if (lane == 0) {
+                            out.begin[used] = 1; out.end[used] = run_end; out.type[used] = (uint8_t)sd.type;
+                            out.trunc[used] = (uint8_t)((trunc_flag_s(sd.type, run_end, run_end - 1, L) & 2) | (trunc_flag_s(sd.type, 1, 0, L) & 1));
+                        }
+                        used++;
+                    }
+                }
+            }
+            if (bad && !status) status = 7;
+            if (status) break;
+            /* reverse this sample's states into left-to-right order */
+            wsync();
+            if (lane == 0) {
+                int n = used - first;
+                AUGB_ROLLED
+                for (int i = 0; i < n / 2; i++) {
+                    int a = first + i, b = first + n - 1 - i;
+                    int32_t tb = out.begin[a]; out.begin[a] = out.begin[b]; out.begin[b] = tb;
+                    int32_t te = out.end[a]; out.end[a] = out.end[b]; out.end[b] = te;
+                    uint8_t tt = out.type[a]; out.type[a] = out.type[b]; out.type[b] = tt;
+                    uint8_t tr = out.trunc[a]; out.trunc[a] = out.trunc[b]; out.trunc[b] = tr;
+                }
+                out.count[it] = n; out.logp[it] = lp;
+            }
+            wsync();
+        }
+        if (lane == 0) *out.status = status;
+        S.opt = nullptr; S.nopt = nullptr;
+        wsync();
+    }
+};
+
+/* glibc rand() (random_r, TYPE_3 additive feedback generator: r[i] = r[i-3] + r[i-31], output r[i] >> 1; seeded by the
+ * minimal-standard LCG and 310 discarded outputs) — the stream an unseeded `augustus` process draws from (seed 1) */
+inline void glibc_rand_stream(uint32_t seed, uint32_t* out, size_t n) {
+    int32_t r[34];
+    r[0] = (int32_t)seed;
+    for (int i = 1; i < 31; i++) {
+        long hi = r[i - 1] / 127773, lo = r[i - 1] % 127773;
+        long word = 16807 * lo - 2836 * hi;
+        if (word < 0) word += 2147483647;
+        r[i] = (int32_t)word;
+    }
+    uint32_t st[344];
+    for (int i = 0; i < 31; i++) st[i] = (uint32_t)r[i];
+    for (int i = 31; i < 34; i++) st[i] = st[i - 31];
+    for (int i = 34; i < 344; i++) st[i] = st[i - 31] + st[i - 3];
+    uint32_t ring[34];                   /* ring[i % 34] = r_i for the last 34 indices */
+    for (int i = 310; i < 344; i++) ring[i % 34] = st[i];
+    for (size_t k = 0; k < n; k++) {
+        size_t i = 344 + k;
+        uint32_t v = ring[(i - 31) % 34] + ring[(i - 3) % 34];
+        ring[i % 34] = v;
+        out[k] = v >> 1;
+    }
+}
+
+}  // namespace augb

@@ -53,6 +53,20 @@ template <bool FWD>
 struct SweepT {
     const DevModel* m; WinView w; WarpState* ws; Seq sq; int lane; int cls; int L;
     const sc_t* trc;            /* transition matrix of the current column's GC class */
+    /* sampling step (getSampledPath): when opt != nullptr the routines below list every option of state `only` instead of
+     * reducing and recording a cell */
+    SampleOpt* opt = nullptr; int* nopt = nullptr; int opt_cap = 0; int only = -1;
+    AUGB_D void push_opt(bool have, double lp, int ord, int pred, int eop) {
+        unsigned b = wballot(have);
+        int base = *nopt;
+        if (have) {
+            int k = base + wpopc(b & ((1u << lane) - 1u));
+            if (k < opt_cap) { SampleOpt o; o.lp = lp; o.ord = ord; o.pred = pred; o.eop = eop; o.pad = 0; opt[k] = o; }
+        }
+        wsync();
+        if (lane == 0) *nopt = base + wpopc(b);
+        wsync();
+    }
 
     AUGB_D const sc_t* parr(int c, int which) const { return w.parr_c[c] + (size_t)which * (size_t)(L + 1); }
     AUGB_D sc_t TR(int a, int s) const { return trc[a * m->S + s]; }
@@ -518,10 +532,11 @@ struct SweepT {
                 } else general = true;
             }
             if (wballot(valid && general)) { if (valid && general) nep = notEndPart(st, bos, right, frameOfRight); }
+            if (FWD && opt) push_opt(valid && !isneg(nep), pf + sc2d(t + ep + nep), -(bos * 128 + (127 - a)), a, eop);
             if (valid && !isneg(nep)) {
                 sc_t sc = pv + (t + ep + nep); int key = bos * 128 + (127 - a);
                 if (sc > best || (sc == best && key > bkey)) { best = sc; bkey = key; bpred = a; bbase = eop; }
-                if (FWD) fl.add(pf + sc2d(t + ep + nep));
+                if (FWD && !opt) fl.add(pf + sc2d(t + ep + nep));
             }
         }
         if (listkind && startMin == 0) {
@@ -536,9 +551,11 @@ struct SweepT {
                 if (isneg(nep0)) break;
                 sc_t sc = pv + (t + ep + nep0); int key = 127 - a;
                 if (lane == 0 && (sc > best || (sc == best && key > bkey))) { best = sc; bkey = key; bpred = a; bbase = -1; }
-                if (FWD && lane == 0) fl.add(sc2d(pv) + sc2d(t + ep + nep0));
+                if (FWD && !opt && lane == 0) fl.add(sc2d(pv) + sc2d(t + ep + nep0));
+                if (FWD && opt) push_opt(lane == 0, sc2d(pv) + sc2d(t + ep + nep0), -(127 - a), a, -1);
             }
         }
+        if (FWD && opt) return;
         int wl = wargbest(best, bkey);
         if (wl < 0) return;
         double Fv = 0;
@@ -558,7 +575,7 @@ struct SweepT {
         AUGB_ROLLED
         for (int f = 0; f < 3; f++) {
             int s = kind == K_LONGDSS ? m->r_longdss[dir][f] : m->r_longass[dir][f];
-            if (s < 0) continue;
+            if (s < 0 || (only >= 0 && s != only)) continue;
             const StateDesc& st = m->st[s];
             sc_t best = SC_NEG; int bpred = -1; Lse fl; fl.clear();
             AUGB_ROLLED
@@ -567,15 +584,27 @@ struct SweepT {
                 sc_t pv = lookupV(a, eop); if (isneg(pv)) continue;
                 sc_t pp = pv + (t + emi);
                 if (pp > best) { best = pp; bpred = a; }
-                if (FWD) fl.add(lookupF(a, eop) + sc2d(t + emi));
+                if (FWD && !opt) fl.add(lookupF(a, eop) + sc2d(t + emi));
+                if (FWD && opt) push_opt(lane == 0, lookupF(a, eop) + sc2d(t + emi), i, a, eop);
             }
-            if (!isneg(best)) emit(j, s, best, bpred, eop, FWD ? fl.value() : 0.0);
+            if (!isneg(best) && !(FWD && opt)) emit(j, s, best, bpred, eop, FWD ? fl.value() : 0.0);
         }
     }
     /* equalD / requalD (intronmodel.cc:695-698, 889-894): fires dStateLen columns after a longdss / rlongass cell */
     AUGB_D void equald_eval(int dir, int f, int j) {
         int s = m->r_equald[dir][f]; int list = (dir ? CL_RA : CL_LD) + f;
         int cur = ws->eq_cur[dir * 3 + f];
+        if (FWD && opt) {
+            /* sampling step: the single option is the longdss / rlongass cell dStateLen columns back (binary search by column) */
+            const Cand* cl = w.cl(list); int lo = 0, hi = ws->cl_n[list] - 1, want = j - m->dStateLen;
+            AUGB_ROLLED
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (cl[mid].col < want) lo = mid + 1; else hi = mid; }
+            if (hi < 0 || cl[lo].col != want || s < 0) return;
+            const sc_t* P = parr(cls, PA_PI);
+            sc_t t = TR(cl[lo].state, s);
+            push_opt(lane == 0 && !isneg(t), w.clF(list)[lo] + sc2d(t + (P[j + 1] - P[want + 1])), 0, cl[lo].state, want);
+            return;
+        }
         Cand c = w.cl(list)[cur]; double cf = FWD ? w.clF(list)[cur] : 0.0;
         wsync();
         if (lane == 0) ws->eq_cur[dir * 3 + f] = cur + 1;
@@ -672,10 +701,11 @@ struct SweepT {
         int eob = fwd ? j + m->ass_up + m->ass_start + 2 : j + m->dss_end + 2;
         int lme = j - m->dStateLen; if (lme < 0) lme = 0;
         const sc_t* P = parr(cls, fwd ? PA_PI : PA_PIR);
-        const bool slow = (w.mask[j] & MB_SLOW) != 0;
+        /* (sampling steps use the plain prefix difference: the memo of the forward pass is gone by then) */
+        const bool slow = (w.mask[j] & MB_SLOW) != 0 && !(FWD && opt);
         AUGB_ROLLED
         for (int f = 0; f < 3; f++) {
-            int s = m->r_lessd[dir][f]; if (s < 0) continue;
+            int s = m->r_lessd[dir][f]; if (s < 0 || (only >= 0 && s != only)) continue;
             int list = (dir ? CL_RA : CL_LD) + f;
             const Cand* cl = w.cl(list); int n = ws->cl_n[list];
             bool spl = !(fwd && f == 0) && !(!fwd && f == 2);
@@ -692,6 +722,7 @@ struct SweepT {
             AUGB_ROLLED
             for (int base_i = n - 1; base_i >= 0 && !done; base_i -= nl) {
                 int i = slow ? base_i : base_i - lane; bool below = false;
+                bool okopt = false; double olp = 0; int oe = 0, opred = 0;
                 if (i >= 0 && (!slow || lane == 0)) {
                     Cand c = cl[i]; int e = c.col;
                     if (e < lme) below = true;
@@ -715,13 +746,16 @@ struct SweepT {
                                 sc_t seq = slow ? snip_get(dir, j, j - begin + 1) : P[j + 1] - P[begin];
                                 sc_t sc = c.V + (t + (ld + seq));
                                 if (sc > best || (sc == best && e > bkey)) { best = sc; bkey = e; bpred = c.state; }
-                                if (FWD) fl.add(w.clF(list)[i] + sc2d(t + (ld + seq)));
+                                if (FWD && !opt) fl.add(w.clF(list)[i] + sc2d(t + (ld + seq)));
+                                if (FWD && opt) { okopt = true; olp = w.clF(list)[i] + sc2d(t + (ld + seq)); oe = e; opred = c.state; }
                             }
                         }
                     }
                 } else if (i < 0) below = true;
+                if (FWD && opt) push_opt(okopt, olp, -oe, opred, oe);
                 done = slow ? wbcast((int)below, 0) != 0 : wballot(below) != 0;
             }
+            if (FWD && opt) continue;
             int wl = wargbest(best, bkey);
             if (wl < 0) continue;
             double Fv = 0;

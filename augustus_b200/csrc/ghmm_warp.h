@@ -40,6 +40,7 @@ AUGB_D unsigned wballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 AUGB_D int wbcast(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 AUGB_D sc_t wbcast64(sc_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 AUGB_D int wffs(unsigned b) { return __ffs(b) - 1; }
+AUGB_D int wpopc(unsigned b) { return __popc(b); }
 #else
 #define AUGB_NLANES 1
 inline int lane_id() { return 0; }
@@ -53,6 +54,7 @@ inline unsigned wballot(bool p) { return p ? 1u : 0u; }
 inline int wbcast(int v, int) { return v; }
 inline sc_t wbcast64(sc_t v, int) { return v; }
 inline int wffs(unsigned b) { return b ? __builtin_ctz(b) : -1; }
+inline int wpopc(unsigned b) { return __builtin_popcount(b); }
 #endif
 
 /* arg-max over lanes of (score, key): the highest score wins, ties go to the highest key.  Returns the

@@ -14,6 +14,7 @@
 #include "../../augustus_b200/csrc/ghmm_backtrace.h"
 #include "../../augustus_b200/csrc/ghmm_model.h"
 #include "../../augustus_b200/csrc/ghmm_prep.h"
+#include "../../augustus_b200/csrc/ghmm_sample.h"
 #include "../../augustus_b200/csrc/ghmm_sweep.h"
 
 using namespace augb;
@@ -99,6 +100,39 @@ int hostemu_forward(void* mp, const char* dna, int L, const int32_t* gc_in, int 
     for (int i = 0; i < ne && i < evcap; i++) { ev_state[i] = v.ev[i].state; ev_F[i] = v.evF[i]; }
     if (chainF) for (int j = 0; j < L; j++) for (int ch = 0; ch < NCHAIN; ch++) chainF[(size_t)j * NCHAIN + ch] = m->chain_state[ch] >= 0 ? sw.chain_fvalue(ch, j) : -1e308;
     return ne;
+}
+/* glibc rand() stream restatement, for checking against libc */
+void hostemu_rand_stream(uint32_t seed, uint32_t* out, int n) { glibc_rand_stream(seed, out, (size_t)n); }
+
+/* forward fill + nsamples sampled paths (condensed, concatenated) */
+int hostemu_sample(void* mp, const char* dna, int L, const int32_t* gc_in, int nsamples, int cap,
+                   int32_t* sb, int32_t* se, uint8_t* st_, uint8_t* str_, int32_t* scount, double* slogp, int32_t* status) {
+    EmuModel* e = (EmuModel*)mp; const DevModel* m = &e->hm.dm;
+    WinLayout lay; std::vector<char> buf; char* base = nullptr; WinView v; WarpState ws; SweepFwd sw; WinOuts* outs = nullptr;
+    std::vector<char> pool; size_t pool_used = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        lay = make_layout(L, m->C, pass == 1, true);
+        buf.assign(lay.total + 64, 0);
+        base = buf.data();
+        int cm = 0;
+        pool.assign((size_t)(m->C) * lay.slab + 64, 0); pool_used = 0;
+        prep_window_seq(m, dna, L, gc_in, base, lay, &cm, pass == 0 ? pool.data() : nullptr, pool.size(), &pool_used);
+        v = make_view(base, lay, L, cm);
+        sw = SweepFwd(); sw.m = m; sw.w = v; sw.ws = &ws;
+        sw.run();
+        outs = (WinOuts*)(base + lay.outs);
+        if (outs->status != AUGB200_ERR_CAPACITY) break;
+    }
+    if (outs->status) { *status = outs->status; return -1; }
+    size_t nrng = (size_t)nsamples * (L + 2);
+    std::vector<uint32_t> rng(nrng);
+    glibc_rand_stream(1, rng.data(), nrng);
+    std::vector<SampleOpt> opts(L + 4096); std::vector<int32_t> sorted(L + 4096); int nopt = 0;
+    Sampler sp; sp.sw = &sw; sp.sc.opt = opts.data(); sp.sc.opt_cap = (int)opts.size(); sp.sc.sorted = sorted.data(); sp.sc.nopt = &nopt;
+    sp.rng = rng.data(); sp.nrng = (int)nrng;
+    SampleOut so; so.cap = cap; so.begin = sb; so.end = se; so.type = st_; so.trunc = str_; so.count = scount; so.logp = slogp; so.status = status;
+    sp.run(nsamples, so);
+    return *status ? -1 : nsamples;
 }
 int hostemu_chain_state(void* mp, int ch) { return ((EmuModel*)mp)->hm.dm.chain_state[ch]; }
 
