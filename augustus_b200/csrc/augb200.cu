@@ -64,6 +64,14 @@ struct augb200_model {
     /* results handed to the caller */
     std::vector<int32_t> r_begin, r_end; std::vector<uint8_t> r_type, r_trunc;
     int64_t launches = 0; double sweep_ms = 0;
+    /* sampling */
+    int nsamp = 0;                       /* sampled paths per window of the current batch (0 = Viterbi only) */
+    augb200_path* samples_out = nullptr;
+    DevBuf<uint32_t> d_rng; size_t rng_n = 0;
+    DevBuf<SampHdr> d_shdr; PinBuf<SampHdr> h_shdr; DevBuf<int32_t> d_sstatus; PinBuf<int32_t> h_sstatus;
+    DevBuf<int32_t> d_sbegin, d_send; DevBuf<uint8_t> d_stype, d_strunc; PinBuf<int32_t> h_sbegin, h_send; PinBuf<uint8_t> h_stype, h_strunc;
+    int scap = 0;
+    std::vector<int32_t> rs_begin, rs_end; std::vector<uint8_t> rs_type, rs_trunc;
 };
 
 static int upload_windows(augb200_model* M, const augb200_window* w, const int* idx, int count, bool generous) {
@@ -73,7 +81,7 @@ static int upload_windows(augb200_model* M, const augb200_window* w, const int* 
         const augb200_window& x = w[idx[i]];
         dna_bytes += (size_t)((x.length + 15) & ~15);
         if (x.gc_class) gc_bytes += (size_t)((x.length + 15) & ~15);
-        arena += make_layout(x.length, M->hm.dm.C, generous).total;
+        arena += make_layout(x.length, M->hm.dm.C, generous, M->nsamp > 0, M->nsamp).total;
     }
     int rc;
     if ((rc = M->h_dna.reserve(dna_bytes + 16))) return rc;
@@ -96,7 +104,7 @@ static int upload_windows(augb200_model* M, const augb200_window* w, const int* 
     for (int i = 0; i < count; i++) {
         const augb200_window& x = w[idx[i]];
         WinDev& d = M->h_wins.p[i];
-        d.L = x.length; d.lay = make_layout(x.length, M->hm.dm.C, generous);
+        d.L = x.length; d.lay = make_layout(x.length, M->hm.dm.C, generous, M->nsamp > 0, M->nsamp);
         d.base = M->d_arena.p + oa; oa += d.lay.total;
         memcpy(M->h_dna.p + od, x.dna, x.length);
         d.dna = M->d_dna.p + od; od += (size_t)((x.length + 15) & ~15);
@@ -119,6 +127,25 @@ static int upload_windows(augb200_model* M, const augb200_window* w, const int* 
     if ((rc = M->h_obegin.reserve(M->ocap)) || (rc = M->h_oend.reserve(M->ocap)) || (rc = M->h_otype.reserve(M->ocap)) || (rc = M->h_otrunc.reserve(M->ocap))) return rc;
     if ((rc = M->d_hdr.reserve(count)) || (rc = M->h_hdr.reserve(count))) return rc;
     if ((rc = M->d_counters.reserve(4)) || (rc = M->h_counters.reserve(4))) return rc;
+    if (M->nsamp > 0) {
+        long sc = 0; int maxL = 0;
+        for (int i = 0; i < count; i++) { sc += M->h_wins.p[i].lay.samp_cap; maxL = std::max(maxL, M->h_wins.p[i].L); }
+        M->scap = (int)std::min<long>(sc, 0x7fffffff);
+        if ((rc = M->d_sbegin.reserve(M->scap)) || (rc = M->d_send.reserve(M->scap)) || (rc = M->d_stype.reserve(M->scap)) || (rc = M->d_strunc.reserve(M->scap))) return rc;
+        if ((rc = M->h_sbegin.reserve(M->scap)) || (rc = M->h_send.reserve(M->scap)) || (rc = M->h_stype.reserve(M->scap)) || (rc = M->h_strunc.reserve(M->scap))) return rc;
+        size_t nh = (size_t)count * M->nsamp;
+        if ((rc = M->d_shdr.reserve(nh)) || (rc = M->h_shdr.reserve(nh)) || (rc = M->d_sstatus.reserve(count)) || (rc = M->h_sstatus.reserve(count))) return rc;
+        /* the rand() stream every window draws from: an unseeded reference process per window = glibc seed 1 */
+        size_t need = (size_t)M->nsamp * ((size_t)maxL + 2);
+        if (need > M->rng_n) {
+            std::vector<uint32_t> host(need);
+            glibc_rand_stream(1, host.data(), need);
+            if ((rc = M->d_rng.reserve(need))) return rc;
+            CK(cudaMemcpyAsync(M->d_rng.p, host.data(), need * 4, cudaMemcpyHostToDevice, M->stream));
+            CK(cudaStreamSynchronize(M->stream));
+            M->rng_n = need;
+        }
+    }
     return 0;
 }
 
@@ -134,10 +161,15 @@ static int run_kernels(augb200_model* M, int count) {
     static int bps = 0;
     if (!bps) { const char* e = getenv("AUGB200_SWEEP_BLOCKS_PER_SM"); bps = e ? atoi(e) : 4; if (bps < 1) bps = 1; }
     int gsweep = std::min((count + SWEEP_WARPS - 1) / SWEEP_WARPS, sms * bps);
-    k_sweep<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(M->d_wins.p, count, M->d_counters.p);
+    if (M->nsamp > 0) k_sweep_sample<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(M->d_wins.p, count, M->d_counters.p, M->d_rng.p, (int)std::min<size_t>(M->rng_n, 0x7fffffff));
+    else k_sweep<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(M->d_wins.p, count, M->d_counters.p);
     CK(cudaEventRecord(M->ev1, M->stream));
     k_backtrace<<<(count + 63) / 64, 64, 0, M->stream>>>(M->d_wins.p, count);
     k_pack<<<count, 64, 0, M->stream>>>(M->d_wins.p, count, M->d_hdr.p, M->d_counters.p + 1, M->d_obegin.p, M->d_oend.p, M->d_otype.p, M->d_otrunc.p, M->ocap);
+    if (M->nsamp > 0) {
+        k_pack_samples<<<count, 64, 0, M->stream>>>(M->d_wins.p, count, M->d_shdr.p, M->d_sstatus.p, M->d_counters.p + 2, M->d_sbegin.p, M->d_send.p, M->d_stype.p, M->d_strunc.p, M->scap);
+        M->launches += 1;
+    }
     CK(cudaGetLastError());
     M->launches += 4;
     return 0;
@@ -154,6 +186,32 @@ static int fetch_results(augb200_model* M, int count, augb200_path* out, const i
         CK(cudaMemcpyAsync(M->h_otype.p, M->d_otype.p, (size_t)total, cudaMemcpyDeviceToHost, M->stream));
         CK(cudaMemcpyAsync(M->h_otrunc.p, M->d_otrunc.p, (size_t)total, cudaMemcpyDeviceToHost, M->stream));
         CK(cudaStreamSynchronize(M->stream));
+    }
+    if (M->nsamp > 0 && M->samples_out) {
+        size_t nh = (size_t)count * M->nsamp;
+        CK(cudaMemcpyAsync(M->h_shdr.p, M->d_shdr.p, nh * sizeof(SampHdr), cudaMemcpyDeviceToHost, M->stream));
+        CK(cudaMemcpyAsync(M->h_sstatus.p, M->d_sstatus.p, (size_t)count * 4, cudaMemcpyDeviceToHost, M->stream));
+        int stot = std::min(M->h_counters.p[2], M->scap);
+        if (stot > 0) {
+            CK(cudaMemcpyAsync(M->h_sbegin.p, M->d_sbegin.p, (size_t)stot * 4, cudaMemcpyDeviceToHost, M->stream));
+            CK(cudaMemcpyAsync(M->h_send.p, M->d_send.p, (size_t)stot * 4, cudaMemcpyDeviceToHost, M->stream));
+            CK(cudaMemcpyAsync(M->h_stype.p, M->d_stype.p, (size_t)stot, cudaMemcpyDeviceToHost, M->stream));
+            CK(cudaMemcpyAsync(M->h_strunc.p, M->d_strunc.p, (size_t)stot, cudaMemcpyDeviceToHost, M->stream));
+        }
+        CK(cudaStreamSynchronize(M->stream));
+        size_t sbase = M->rs_begin.size();
+        M->rs_begin.insert(M->rs_begin.end(), M->h_sbegin.p, M->h_sbegin.p + stot);
+        M->rs_end.insert(M->rs_end.end(), M->h_send.p, M->h_send.p + stot);
+        M->rs_type.insert(M->rs_type.end(), M->h_stype.p, M->h_stype.p + stot);
+        M->rs_trunc.insert(M->rs_trunc.end(), M->h_strunc.p, M->h_strunc.p + stot);
+        for (int i = 0; i < count; i++)
+            for (int k = 0; k < M->nsamp; k++) {
+                const SampHdr& h = M->h_shdr.p[(size_t)i * M->nsamp + k]; augb200_path& p = M->samples_out[(size_t)idx[i] * M->nsamp + k];
+                p.n = h.n; p.status = M->h_sstatus.p[i]; p.log_prob = h.logp;
+                p.begin = (const int32_t*)(uintptr_t)(sbase + h.offset);
+            }
+        /* a window whose sample buffers overflowed is decoded again as a whole */
+        for (int i = 0; i < count; i++) if (M->h_sstatus.p[i] == AUGB200_ERR_CAPACITY && out[idx[i]].status == 0) out[idx[i]].status = AUGB200_ERR_CAPACITY;
     }
     float ms = 0; if (cudaEventElapsedTime(&ms, M->ev0, M->ev1) == cudaSuccess) M->sweep_ms += ms;
     /* append to the result store; pointers are fixed up by the caller once all sub-batches are in */
@@ -213,6 +271,8 @@ void augb200_model_destroy(augb200_model* M) {
     M->d_hdr.release(); M->d_obegin.release(); M->d_oend.release(); M->d_otype.release(); M->d_otrunc.release();
     M->h_dna.release(); M->h_gc.release(); M->h_wins.release(); M->h_hdr.release(); M->h_counters.release();
     M->h_obegin.release(); M->h_oend.release(); M->h_otype.release(); M->h_otrunc.release();
+    M->d_rng.release(); M->d_shdr.release(); M->h_shdr.release(); M->d_sstatus.release(); M->h_sstatus.release();
+    M->d_sbegin.release(); M->d_send.release(); M->d_stype.release(); M->d_strunc.release(); M->h_sbegin.release(); M->h_send.release(); M->h_stype.release(); M->h_strunc.release();
     if (M->ev0) cudaEventDestroy(M->ev0);
     if (M->ev1) cudaEventDestroy(M->ev1);
     if (M->stream) cudaStreamDestroy(M->stream);
@@ -231,8 +291,10 @@ static int check_windows(int32_t n, const augb200_window* w) {
     return 0;
 }
 
-int augb200_decode_batch(augb200_model* M, int32_t n, const augb200_window* w, augb200_path* out) {
+static int decode_batch_impl(augb200_model* M, int32_t n, const augb200_window* w, augb200_path* out, int nsamp, augb200_path* samples) {
     if (!M || !out) return AUGB200_ERR_BAD_ARG;
+    M->nsamp = nsamp; M->samples_out = samples;
+    M->rs_begin.clear(); M->rs_end.clear(); M->rs_type.clear(); M->rs_trunc.clear();
     int rc = check_windows(n, w); if (rc) return rc;
     CK(cudaSetDevice(M->device));
     M->r_begin.clear(); M->r_end.clear(); M->r_type.clear(); M->r_trunc.clear();
@@ -245,7 +307,7 @@ int augb200_decode_batch(augb200_model* M, int32_t n, const augb200_window* w, a
         while (first < order.size()) {
             size_t bytes = 0; int count = 0;   /* greedy sub-batch under the arena budget */
             while (first + count < order.size()) {
-                size_t t = make_layout(w[order[first + count]].length, M->hm.dm.C, generous).total;
+                size_t t = make_layout(w[order[first + count]].length, M->hm.dm.C, generous, M->nsamp > 0, M->nsamp).total;
                 if (count && bytes + t > M->arena_budget - M->arena_budget / 8) break;
                 bytes += t; count++;
             }
@@ -259,7 +321,21 @@ int augb200_decode_batch(augb200_model* M, int32_t n, const augb200_window* w, a
         order.swap(again);
     }
     fix_pointers(M, n, out);
+    if (samples)
+        for (size_t i = 0; i < (size_t)n * nsamp; i++) {
+            size_t off = (size_t)(uintptr_t)samples[i].begin;
+            samples[i].begin = M->rs_begin.data() + off; samples[i].end = M->rs_end.data() + off;
+            samples[i].type = M->rs_type.data() + off; samples[i].truncated = M->rs_trunc.data() + off;
+        }
+    M->nsamp = 0; M->samples_out = nullptr;
     return AUGB200_OK;
+}
+
+int augb200_decode_batch(augb200_model* M, int32_t n, const augb200_window* w, augb200_path* out) { return decode_batch_impl(M, n, w, out, 0, nullptr); }
+
+int augb200_decode_batch_sampling(augb200_model* M, int32_t n, const augb200_window* w, int32_t nsample, augb200_path* out, augb200_path* samples) {
+    if (nsample < 2 || !samples) return AUGB200_ERR_BAD_ARG;
+    return decode_batch_impl(M, n, w, out, nsample - 1, samples);
 }
 
 int augb200_decode(augb200_model* M, const augb200_window* w, augb200_path* out) { return augb200_decode_batch(M, 1, w, out); }

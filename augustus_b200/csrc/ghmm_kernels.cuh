@@ -7,6 +7,7 @@
 #include "ghmm_backtrace.h"
 #include "ghmm_defs.h"
 #include "ghmm_prep.h"
+#include "ghmm_sample.h"
 #include "ghmm_seq.h"
 #include "ghmm_sweep.h"
 
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(PREP_BS) k_prep(const WinDev* __restrict__ win
 
 /* ------------------------------------------------------------------ sweep kernel: one warp per window */
 constexpr int SWEEP_WARPS = 4;
-__global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep(const WinDev* __restrict__ wins, int nwin, int* __restrict__ next) {
+__global__ void __launch_bounds__(SWEEP_WARPS * 32, 4) k_sweep(const WinDev* __restrict__ wins, int nwin, int* __restrict__ next) {
     const DevModel* m = &c_model;
     __shared__ WarpState wstate[SWEEP_WARPS];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -275,6 +276,68 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep(const WinDev* __rest
         sw.run();
         __syncwarp();
     }
+}
+
+/* ------------------------------------------------------------------ forward sweep + posterior sampling: one warp per window */
+__global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep_sample(const WinDev* __restrict__ wins, int nwin, int* __restrict__ next,
+                                                                   const uint32_t* __restrict__ rng, int nrng) {
+    const DevModel* m = &c_model;
+    __shared__ WarpState wstate[SWEEP_WARPS];
+    __shared__ int s_nopt[SWEEP_WARPS];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (;;) {
+        int wi = 0;
+        if (lane == 0) wi = atomicAdd(next, 1);
+        wi = __shfl_sync(0xffffffffu, wi, 0);
+        if (wi >= nwin) break;
+        const WinDev& wd = wins[wi];
+        SweepFwd sw; sw.m = m; sw.ws = &wstate[wid];
+        sw.w = make_view(wd.base, wd.lay, wd.L, 0);
+        sw.run();
+        __syncwarp();
+        WinOuts* outs = (WinOuts*)(wd.base + wd.lay.outs);
+        if (wd.lay.nsamp > 0) {
+            if (wstate[wid].status) { if (lane == 0) outs->samp_status = wstate[wid].status; }
+            else {
+                Sampler sp; sp.sw = &sw;
+                sp.sc.opt = (SampleOpt*)(wd.base + wd.lay.opt); sp.sc.opt_cap = wd.lay.opt_cap; sp.sc.sorted = (int32_t*)(wd.base + wd.lay.sorted); sp.sc.nopt = &s_nopt[wid];
+                sp.rng = rng; sp.nrng = nrng;
+                SampleOut so; so.cap = wd.lay.samp_cap;
+                so.begin = (int32_t*)(wd.base + wd.lay.s_begin); so.end = (int32_t*)(wd.base + wd.lay.s_end);
+                so.type = (uint8_t*)(wd.base + wd.lay.s_type); so.trunc = (uint8_t*)(wd.base + wd.lay.s_trunc);
+                so.count = (int32_t*)(wd.base + wd.lay.s_count); so.logp = (double*)(wd.base + wd.lay.s_logp); so.status = &outs->samp_status;
+                sp.run(wd.lay.nsamp, so);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+/* gather the sampled paths of all windows: per (window, sample) a header, states contiguous per window */
+struct SampHdr { int32_t n, offset; double logp; };
+__global__ void k_pack_samples(const WinDev* __restrict__ wins, int nwin, SampHdr* __restrict__ hdr, int32_t* __restrict__ wstatus, int* __restrict__ total,
+                               int32_t* __restrict__ obegin, int32_t* __restrict__ oend, uint8_t* __restrict__ otype, uint8_t* __restrict__ otrunc, int ocap) {
+    int wi = blockIdx.x;
+    if (wi >= nwin) return;
+    const WinDev& wd = wins[wi];
+    const WinOuts* outs = (const WinOuts*)(wd.base + wd.lay.outs);
+    const int ns = wd.lay.nsamp;
+    const int32_t* cnt = (const int32_t*)(wd.base + wd.lay.s_count); const double* lp = (const double*)(wd.base + wd.lay.s_logp);
+    __shared__ int s_off, s_tot;
+    if (threadIdx.x == 0) {
+        int st = outs->samp_status, tot = 0;
+        if (!st) for (int k = 0; k < ns; k++) tot += cnt[k];
+        int off = atomicAdd(total, tot);
+        if (off + tot > ocap) { st = 8; tot = 0; }
+        wstatus[wi] = st; s_off = off; s_tot = tot;
+        int o = off;
+        for (int k = 0; k < ns; k++) { SampHdr h; h.n = st ? 0 : cnt[k]; h.offset = o; h.logp = st ? 0.0 : lp[k]; hdr[(size_t)wi * ns + k] = h; o += h.n; }
+    }
+    __syncthreads();
+    const int off = s_off, tot = s_tot;
+    const int32_t* b = (const int32_t*)(wd.base + wd.lay.s_begin); const int32_t* e = (const int32_t*)(wd.base + wd.lay.s_end);
+    const uint8_t* t = (const uint8_t*)(wd.base + wd.lay.s_type); const uint8_t* tr = (const uint8_t*)(wd.base + wd.lay.s_trunc);
+    for (int i = threadIdx.x; i < tot; i += blockDim.x) { obegin[off + i] = b[i]; oend[off + i] = e[i]; otype[off + i] = t[i]; otrunc[off + i] = tr[i]; }
 }
 
 /* ------------------------------------------------------------------ backtrace: one thread per window */

@@ -24,7 +24,7 @@ namespace augb {
 /* result / hand-over block of a window (WinLayout::outs) */
 struct WinOuts {
     int32_t n_ev, status, path_n, path_status; int32_t ncp[NCHAIN]; int32_t pad /* window flags */; sc_t score;
-    int32_t nfcp[NCHAIN]; int32_t pad2;
+    int32_t nfcp[NCHAIN]; int32_t samp_status;
     const sc_t* slab[MAXC];     /* prefix-array slab of each GC class (set by prep) */
 };
 
@@ -34,6 +34,7 @@ struct WinLayout {
     size_t ev, evstart, cl[NCL], cp[NCHAIN], outs;           /* dynamic (sweep) */
     size_t snip_head, snip_pool, snip_stack; int snip_cap;
     size_t evF, clF, fcp; int fcp_cap;                       /* forward pass (0 capacity when not requested) */
+    size_t opt, sorted, s_begin, s_end, s_type, s_trunc, s_count, s_logp; int opt_cap, samp_cap, nsamp;   /* sampling */
     size_t path_begin, path_end, path_type, path_trunc;      /* backtrace output */
     size_t total, slab;
     int ev_cap, cl_cap, cp_cap, path_cap, nslab_local;
@@ -43,7 +44,7 @@ AUGB_HD size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
  * cell per state; a candidate list gets at most one entry per column); the default sizes are ~3x what human-like
  * DNA needs (measured: 1.9 events, 0.03 list entries per base) and a window that overflows them is reported with
  * status AUGB200_ERR_CAPACITY and decoded again with the generous layout (augb200.cu: decode_batch). */
-inline WinLayout make_layout(int L, int C, bool generous = false, bool forward = false) {
+inline WinLayout make_layout(int L, int C, bool generous = false, bool forward = false, int nsamp = 0) {
     WinLayout w; size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = al16(o + bytes); return r; };
     w.code = take(L); w.gc = take(L); w.mask = take((size_t)L * 2); w.kf = take((size_t)L * 2); w.kr = take((size_t)L * 2);
@@ -64,6 +65,11 @@ inline WinLayout make_layout(int L, int C, bool generous = false, bool forward =
     w.fcp_cap = forward ? (generous ? L + 64 : L / 2 + 64) : 0;
     w.evF = take(forward ? (size_t)w.ev_cap * 8 : 0); w.clF = take(forward ? (size_t)NCL * w.cl_cap * 8 : 0);
     w.fcp = take((size_t)NCHAIN * w.fcp_cap * sizeof(FChainCP));
+    w.nsamp = forward ? nsamp : 0;
+    w.opt_cap = w.nsamp ? w.cl_cap + 1024 : 0; w.samp_cap = w.nsamp ? (generous ? w.nsamp * (L / 8 + 64) : w.nsamp * 160 + L / 4) : 0;
+    w.opt = take((size_t)w.opt_cap * sizeof(SampleOpt)); w.sorted = take((size_t)w.opt_cap * 4);
+    w.s_begin = take((size_t)w.samp_cap * 4); w.s_end = take((size_t)w.samp_cap * 4); w.s_type = take(w.samp_cap); w.s_trunc = take(w.samp_cap);
+    w.s_count = take((size_t)w.nsamp * 4 + 16); w.s_logp = take((size_t)w.nsamp * 8);
     w.outs = take(sizeof(WinOuts));
     w.snip_cap = generous ? 262144 : 16384;
     w.snip_head = take((size_t)2 * SNIP_RING * sizeof(SnipHead)); w.snip_pool = take((size_t)2 * w.snip_cap * sizeof(SnipEnt));

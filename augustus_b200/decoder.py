@@ -98,6 +98,8 @@ def _load():
     for f in ("augb200_decode_batch",):
         getattr(lib, f).restype = ctypes.c_int
         getattr(lib, f).argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(_Window), ctypes.POINTER(_Path)]
+    lib.augb200_decode_batch_sampling.restype = ctypes.c_int
+    lib.augb200_decode_batch_sampling.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(_Window), ctypes.c_int32, ctypes.POINTER(_Path), ctypes.POINTER(_Path)]
     lib.augb200_decode.restype = ctypes.c_int
     lib.augb200_decode.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Window), ctypes.POINTER(_Path)]
     lib.augb200_stage_batch.restype = ctypes.c_int
@@ -228,6 +230,18 @@ class Decoder:
         return (rec["n"].copy(), rec["status"].copy(), rec["log_prob"].copy(), offset,
                 arr_of(ptrs[0], ctypes.c_int32, np.int32), arr_of(ptrs[1], ctypes.c_int32, np.int32),
                 arr_of(ptrs[2], ctypes.c_uint8, np.uint8), arr_of(ptrs[3], ctypes.c_uint8, np.uint8))
+
+    def decode_batch_sampling(self, seqs: Sequence, nsample: int = 100, gc: Optional[Sequence] = None):
+        """findGenes with --sample=nsample: returns (viterbi_paths, samples) where samples[i] is the list of the nsample-1
+        posterior state paths of window i (NAMGene::getSampledPath, namgene.cc:367)."""
+        arr, keep = self._windows(seqs, gc)
+        nw, ns = len(seqs), nsample - 1
+        out = (_Path * nw)()
+        samp = (_Path * (nw * ns))()
+        self._check(self._lib.augb200_decode_batch_sampling(self._h, nw, arr, nsample, out, samp))
+        vit = self._paths(out, nw)
+        allp = self._paths(samp, nw * ns)
+        return vit, [allp[i * ns:(i + 1) * ns] for i in range(nw)]
 
     def viterbiAndForward(self, dna, gc=None):
         """NAMGene::viterbiAndForward (namgene.cc:168) for one window; the path is kept for getViterbiPath."""

@@ -94,6 +94,16 @@ int augb200_model_num_gc_classes(const augb200_model* m);
  * DP errors are reported in out[i].status. */
 int augb200_decode_batch(augb200_model* m, int32_t n, const augb200_window* windows, augb200_path* out);
 
+/*
+ * Viterbi path plus posterior samples: NAMGene::findGenes with --sample=nsample (namgene.cc:833-871).  The forward matrix
+ * is filled beside the Viterbi matrix and nsample-1 state paths are drawn as NAMGene::getSampledPath does
+ * (namgene.cc:367-426).  Every window draws from its own rand() stream started at glibc's default seed, i.e. the stream an
+ * `augustus` process running that window alone consumes.  samples[i*(nsample-1) + k] is sample k of window i (condensed
+ * like the Viterbi path; log_prob = ln of the product of the normalised option probabilities, StatePath::pathemiProb).
+ */
+int augb200_decode_batch_sampling(augb200_model* m, int32_t n, const augb200_window* windows, int32_t nsample,
+                                  augb200_path* out, augb200_path* samples);
+
 /* Decode one window. */
 int augb200_decode(augb200_model* m, const augb200_window* window, augb200_path* out);
 

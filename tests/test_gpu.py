@@ -86,6 +86,33 @@ def test_single_window_seam(dec, oracle):
     _same(dec.getViterbiPath(), oracle.viterbi(dna))
 
 
+def test_posterior_sampling_matches_reference_and_oracle(dec, oracle):
+    """Config 5 path: forward fill + 99 sampled paths per window through the C ABI."""
+    gold = util.golden_samples()
+    wins = {"example_HS08198": util.read_fasta(util.GOLDEN + "/example.fa")[1][1],
+            "synthetic_301_20000": synth.window(301, 20000),
+            "real_chr2L_5005000": util.read_fasta(util.GOLDEN + "/real_windows.fa")[0][1]}
+    names = list(wins)
+    vit, samples = dec.decode_batch_sampling([wins[k] for k in names], 100)
+    for k, v, ss in zip(names, vit, samples):
+        o = oracle.viterbi(wins[k])
+        assert v.as_tuples() == o["condensed"]
+        ref = gold[k]["samples"]
+        assert len(ss) == len(ref) == 99
+        for mine, theirs in zip(ss, ref):
+            assert mine.status == 0
+            assert mine.as_tuples() == [tuple(x) for x in theirs["states"]]                 # the reference's own sampled path
+            assert abs(mine.log_prob - theirs["log_prob"]) <= 1e-6 * max(1.0, abs(theirs["log_prob"]))
+    # more windows against the oracle (ragged lengths)
+    more = [synth.window(700 + i, n) for i, n in enumerate([30000, 7777, 2000, 300])] + ["N" * 200]
+    vit, samples = dec.decode_batch_sampling(more, 100)
+    for dna, ss in zip(more, samples):
+        o = oracle.sample(dna, 100)
+        for mine, theirs in zip(ss, o["samples"]):
+            assert mine.as_tuples() == theirs["states"]
+            assert abs(mine.log_prob - theirs["log_prob"]) <= 1e-6 * max(1.0, abs(theirs["log_prob"]))
+
+
 def test_full_size_properties(dec):
     """Size-independent checks on a larger batch: batch order independence, idempotence, path structure."""
     wins = synth.windows(96, 50000, start=1000)

@@ -124,6 +124,27 @@ def test_kernel_source_on_host_matches_oracle_cells_across_gc_class_boundaries(o
         _cells_equal(oracle, emu, dna)
 
 
+def test_sampler_source_on_host_matches_oracle(oracle, emu):
+    """ghmm_sample.h + the forward mode of ghmm_sweep.h compiled for the host: every one of the 99 sampled paths (and
+    its ln pathemiProb) equals the oracle's, which is pinned to the reference's; also checks the glibc rand() restatement."""
+    import ctypes
+    libc = ctypes.CDLL("libc.so.6"); libc.srand(1)
+    ref = np.array([libc.rand() for _ in range(20000)], dtype=np.uint32)
+    mine = np.zeros(20000, dtype=np.uint32)
+    emu.lib.hostemu_rand_stream.argtypes = [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int]
+    emu.lib.hostemu_rand_stream(1, mine.ctypes.data, 20000)
+    assert (ref == mine).all()
+    wins = [util.read_fasta(util.GOLDEN + "/example.fa")[1][1], synth.window(300, 12000), util.read_fasta(util.GOLDEN + "/real_windows.fa")[0][1],
+            "N" * 300, synth.window(9, 400)]
+    for dna in wins:
+        o = oracle.sample(dna, 100)
+        e = emu.sample(dna, 99)
+        assert e["status"] == 0 and len(e["samples"]) == 99
+        for a, b in zip(e["samples"], o["samples"]):
+            assert a["states"] == b["states"]
+            assert abs(a["log_prob"] - b["log_prob"]) <= 1e-9 * max(1.0, abs(b["log_prob"]))
+
+
 def test_kernel_source_on_host_edge_cases(oracle, emu):
     base = synth.window(7, 4000)
     cases = [base[:2], base[:3], base[:9], base[:41], base[:600], "N" * 500, base[:1000] + "N" * 300 + base[1000:2000],

@@ -151,6 +151,25 @@ class HostEmu:
         if not self.m:
             raise RuntimeError(err.value.decode())
 
+    def sample(self, dna: str, nsamples=99, gc=None):
+        """Forward fill + sampled paths with the host build of ghmm_sweep.h / ghmm_sample.h."""
+        self.lib.hostemu_sample.restype = ctypes.c_int
+        self.lib.hostemu_sample.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 7
+        L = len(dna)
+        cap = nsamples * (L // 8 + 64)
+        sb, se = np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=np.int32)
+        st, tr = np.zeros(cap, dtype=np.uint8), np.zeros(cap, dtype=np.uint8)
+        cnt, lp, status = np.zeros(nsamples, dtype=np.int32), np.zeros(nsamples), ctypes.c_int32()
+        gci = None if gc is None else np.ascontiguousarray(gc, dtype=np.int32)
+        rc = self.lib.hostemu_sample(self.m, dna.encode(), L, None if gci is None else gci.ctypes.data, nsamples, cap, sb.ctypes.data,
+                                     se.ctypes.data, st.ctypes.data, tr.ctypes.data, cnt.ctypes.data, lp.ctypes.data, ctypes.byref(status))
+        out, pos = [], 0
+        for k in range(nsamples if rc >= 0 else 0):
+            c = int(cnt[k])
+            out.append({"log_prob": float(lp[k]), "states": [(int(st[pos + q]), int(sb[pos + q]), int(se[pos + q]), int(tr[pos + q])) for q in range(c)]})
+            pos += c
+        return {"status": status.value, "samples": out}
+
     def decode(self, dna: str, gc=None, want_cells=False, S=47):
         L = len(dna)
         cap = L // 2 + 64
