@@ -382,6 +382,15 @@ int64_t augb200_result_store(const augb200_model* M, const int32_t** b, const in
     return (int64_t)M->r_begin.size();
 }
 
+int64_t augb200_sample_store(const augb200_model* M, const int32_t** b, const int32_t** e, const uint8_t** t, const uint8_t** tr) {
+    if (!M) return 0;
+    if (b) *b = M->rs_begin.data();
+    if (e) *e = M->rs_end.data();
+    if (t) *t = M->rs_type.data();
+    if (tr) *tr = M->rs_trunc.data();
+    return (int64_t)M->rs_begin.size();
+}
+
 const char* augb200_strerror(int code) {
     switch (code) {
     case AUGB200_OK: return "ok";

@@ -116,6 +116,8 @@ def _load():
     lib.augb200_last_sweep_ms.argtypes = [ctypes.c_void_p]
     lib.augb200_result_store.restype = ctypes.c_int64
     lib.augb200_result_store.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_void_p)] * 4
+    lib.augb200_sample_store.restype = ctypes.c_int64
+    lib.augb200_sample_store.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_void_p)] * 4
     lib.augb200_strerror.restype = ctypes.c_char_p
     lib.augb200_strerror.argtypes = [ctypes.c_int]
     lib.augb200_last_cuda_error.restype = ctypes.c_char_p
@@ -215,9 +217,9 @@ class Decoder:
         self._check(self._lib.augb200_decode_batch(self._h, nw, arr, out))
         return self._raw(out, nw)
 
-    def _raw(self, out, nw):
+    def _raw(self, out, nw, store=None):
         ptrs = [ctypes.c_void_p() for _ in range(4)]
-        total = self._lib.augb200_result_store(self._h, *[ctypes.byref(p) for p in ptrs])
+        total = (store or self._lib.augb200_result_store)(self._h, *[ctypes.byref(p) for p in ptrs])
         rec = np.frombuffer(out, dtype=np.dtype([("n", "<i4"), ("status", "<i4"), ("begin", "<u8"), ("end", "<u8"),
                                                  ("type", "<u8"), ("trunc", "<u8"), ("log_prob", "<f8")]), count=nw)
         base = ptrs[0].value or 0
@@ -242,6 +244,16 @@ class Decoder:
         vit = self._paths(out, nw)
         allp = self._paths(samp, nw * ns)
         return vit, [allp[i * ns:(i + 1) * ns] for i in range(nw)]
+
+    def decode_batch_sampling_raw(self, seqs: Sequence, nsample: int = 100, gc: Optional[Sequence] = None):
+        """As decode_batch_sampling, results as flat numpy arrays: (viterbi_raw, samples_raw), each the tuple of _raw();
+        sample k of window i is row i*(nsample-1)+k."""
+        arr, keep = self._windows(seqs, gc)
+        nw, ns = len(seqs), nsample - 1
+        out = (_Path * nw)()
+        samp = (_Path * (nw * ns))()
+        self._check(self._lib.augb200_decode_batch_sampling(self._h, nw, arr, nsample, out, samp))
+        return self._raw(out, nw), self._raw(samp, nw * ns, self._lib.augb200_sample_store)
 
     def viterbiAndForward(self, dna, gc=None):
         """NAMGene::viterbiAndForward (namgene.cc:168) for one window; the path is kept for getViterbiPath."""

@@ -78,7 +78,7 @@ def ref_binary():
     return (exe, cfg) if os.path.exists(exe) and os.path.isdir(cfg) else (None, None)
 
 
-def run_reference_sample(n_windows, cores, start_index=0):
+def run_reference_sample(n_windows, cores, start_index=0, extra_args=()):
     """Decode n_windows synthetic windows with the unmodified reference, `cores` processes in parallel.
     Returns (Mbp/s, seconds)."""
     from augustus_b200 import synth
@@ -100,7 +100,7 @@ def run_reference_sample(n_windows, cores, start_index=0):
         t0 = time.perf_counter()
         procs = []
         for c, fa in enumerate(files):
-            cmd = [exe, "--species=human", "--softmasking=0", fa]
+            cmd = [exe, "--species=human", "--softmasking=0"] + list(extra_args) + [fa]
             if os.path.exists("/usr/bin/taskset"):
                 cmd = ["taskset", "-c", str(c % (os.cpu_count() or 1))] + cmd
             procs.append(subprocess.Popen(cmd, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
@@ -150,6 +150,7 @@ def main():
     ap.add_argument("--windows", type=int, default=DEFAULT_WINDOWS, help="windows per GPU per step (default: BASELINE.json config 2)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the config-5 (posterior sampling) side measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
@@ -266,6 +267,24 @@ def main():
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": k * WINDOW_LEN / 1e6 / dt, "unit": "Mbp/s", "cores": 1, "kind": "port",
                                     "sample": "%d windows x 50 kb, oracle/ghmm_oracle.c, 1 thread (%s)" % (k, ex)}
+    if not args.no_secondary:
+        # BASELINE.json configs[4]: --sample=100 --alternatives-from-sampling=true on 1000 x 50 kb windows (forward + sampling kernels)
+        try:
+            n5 = min(1000, M)
+            dec.decode_batch_sampling_raw(wins_b[:8], 100)
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            vit5, samp5 = dec.decode_batch_sampling_raw(wins_b[:n5], 100)
+            torch.cuda.synchronize(); dt5 = time.perf_counter() - t0
+            assert not samp5[1].any()
+            sec = {"workload": "%d x 50 kb windows, --sample=100 --alternatives-from-sampling=true (Viterbi + forward + 99 sampled paths per window), 1 GPU, e2e from host buffers through augb200_decode_batch_sampling" % n5,
+                   "value": n5 * WINDOW_LEN / 1e6 / dt5, "unit": "Mbp/s", "sampled_paths": int(len(samp5[0]))}
+            if not args.no_cpu_baseline:
+                cores = os.cpu_count() or 1
+                v5, d5 = run_reference_sample(cores, cores, extra_args=("--sample=100", "--alternatives-from-sampling=true"))
+                sec["cpu_baseline"] = {"value": v5, "unit": "Mbp/s", "cores": cores, "kind": "reference", "sample": "%d windows x 50 kb (%.1f s wall)" % (cores, d5)}
+            line["secondary"] = {"config5_sampling": sec}
+        except Exception as ex:
+            line["secondary"] = {"config5_sampling": {"error": str(ex)}}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

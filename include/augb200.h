@@ -124,6 +124,10 @@ double augb200_last_sweep_ms(const augb200_model* m);
 int64_t augb200_result_store(const augb200_model* m, const int32_t** begin, const int32_t** end,
                              const uint8_t** type, const uint8_t** truncated);
 
+/* the same for the sampled paths of the last augb200_decode_batch_sampling call */
+int64_t augb200_sample_store(const augb200_model* m, const int32_t** begin, const int32_t** end,
+                             const uint8_t** type, const uint8_t** truncated);
+
 const char* augb200_strerror(int code);
 const char* augb200_last_cuda_error(void);
 
