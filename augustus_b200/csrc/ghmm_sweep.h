@@ -474,7 +474,7 @@ struct SweepT {
                 if (bos < startMin) below = true;
                 else {
                     int bobe = bos - 3; eop = bos - st.beginPartLen - 1;
-                    if (bobe >= 0 && bobe < L - 2 && eop < L && !isneg(t0)) {
+                    if (bobe >= 0 && bobe < L - 2 && eop < j && !isneg(t0)) {
                         int pn = sq.kmer_end(bobe + 2, 3);
                         if (pn >= 0 && !isneg(m->startp[pn])) { pv = lookupV(anc0, eop >= 0 ? eop : 0); valid = !isneg(pv); if (FWD && valid) pf = lookupF(anc0, eop >= 0 ? eop : 0); }
                     }
@@ -484,7 +484,10 @@ struct SweepT {
                 more = step * AUGB_NLANES + AUGB_NLANES < st.nanc;
                 if (step * AUGB_NLANES + lane < st.nanc) {
                     bos = startMin; eop = bos - st.beginPartLen - 1; a = st.anc[step * AUGB_NLANES + lane]; t = TR(a, s);
-                    if (eop < L && !isneg(t)) { pv = lookupV(a, eop >= 0 ? eop : 0); valid = !isneg(pv); if (FWD && valid) pf = lookupF(a, eop >= 0 ? eop : 0); }
+                    /* the one candidate can end AT the current column (reverse stop inside the end part): the reference then reads the
+                     * cell of this very column, which exists only for states evaluated earlier in the column (lower index; here the
+                     * intergenic chain); behind the current column the matrix is still empty */
+                    if ((eop < j || (eop == j && a < s && m->st[a].chain >= 0)) && !isneg(t)) { pv = lookupV(a, eop >= 0 ? eop : 0); valid = !isneg(pv); if (FWD && valid) pf = lookupF(a, eop >= 0 ? eop : 0); }
                 }
             }
             step++;

@@ -909,8 +909,9 @@ int orc_decode(const Model* m, const char* dna, int L, const int* gc_in, int64_t
     orf_init(x);
     x->snF = (SnipEnt**)calloc((size_t)2 * L, sizeof(SnipEnt*)); x->snL = (SnipEnt**)calloc((size_t)2 * L, sizeof(SnipEnt*));
     x->V = (sc_t*)malloc((size_t)L * m->S * sizeof(sc_t));
+    for (size_t i = 0; i < (size_t)L * m->S; i++) x->V[i] = NEG;      /* columns not reached yet are empty (viterbi.assign, namgene.cc:178) */
     const int fwd = nsample > 1;
-    if (fwd) x->F = (double*)malloc((size_t)L * m->S * sizeof(double));
+    if (fwd) { x->F = (double*)malloc((size_t)L * m->S * sizeof(double)); for (size_t i = 0; i < (size_t)L * m->S; i++) x->F[i] = -INFINITY; }
     for (int s = 0; s < m->S; s++) { x->V[s] = m->init[s]; if (fwd) x->F[s] = isneg(m->init[s]) ? -INFINITY : sc2d(m->init[s]); }
     Oli o;
     x->mode = fwd ? 1 : 0;

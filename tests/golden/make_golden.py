@@ -39,11 +39,11 @@ def condense(states):
     return out
 
 
-def run_ref(fasta, species="human"):
+def run_ref(fasta, species="human", extra=()):
     with tempfile.TemporaryDirectory() as td:
         pf = os.path.join(td, "p")
         env = dict(ENV, AUGDUMP_PATH=pf)
-        subprocess.run([AUGDUMP, "--species=" + species, "--softmasking=0", fasta], env=env, check=True,
+        subprocess.run([AUGDUMP, "--species=" + species, "--softmasking=0"] + list(extra) + [fasta], env=env, check=True,
                        stdout=subprocess.DEVNULL)
         res, cur = [], None
         for line in open(pf):
@@ -82,6 +82,16 @@ def main():
         synth.write_fasta(fa, [synth.window(i, n) for i, n in shorts], ["short%d_%d" % s for s in shorts])
         out["synthetic_short"] = run_ref(fa)
         out["synthetic_short_spec"] = shorts
+    # second parameter set with a different signal geometry (ass_start 1 / ass_end 4, no exon-terminal content, d = 929, one
+    # GC class): --species=fly --UTR=off --softmasking=0, the 47-state variant of BASELINE.json configs[2]
+    with tempfile.TemporaryDirectory() as td:
+        blob = os.path.join(td, "fly.blob")
+        fa = os.path.join(HERE, "fly_window.fa")
+        synth.write_fasta(fa, [seq[5000000:5060000]], ["chr2L_5000000_60000"])
+        subprocess.run([AUGDUMP, "--species=fly", "--UTR=off", "--softmasking=0", fa], env=dict(ENV, AUGDUMP_PARAMS=blob), check=True, stdout=subprocess.DEVNULL)
+        with lzma.open(os.path.join(HERE, "fly_noutr.params.xz"), "wb", preset=9) as f:
+            f.write(open(blob, "rb").read())
+    out["fly"] = run_ref(os.path.join(HERE, "fly_window.fa"), species="fly", extra=("--UTR=off",))
     json.dump(out, open(os.path.join(HERE, "ref_paths.json"), "w"), separators=(",", ":"))
     print("golden fixtures written to", HERE)
 

@@ -27,10 +27,10 @@ ENV = dict(os.environ, AUGUSTUS_CONFIG_PATH=REF + "/config")
 S = 47
 
 
-def run(dna):
+def run(dna, species="human", extra=()):
     with tempfile.TemporaryDirectory() as td:
         fa = os.path.join(td, "w.fa"); synth.write_fasta(fa, [dna])
-        subprocess.run([AUGDUMP, "--species=human", "--softmasking=0", "--sample=100", "--alternatives-from-sampling=true", fa],
+        subprocess.run([AUGDUMP, "--species=" + species, "--softmasking=0", "--sample=100", "--alternatives-from-sampling=true"] + list(extra) + [fa],
                        env=dict(ENV, AUGDUMP_PATH=os.path.join(td, "p"), AUGDUMP_MATRIX=os.path.join(td, "m")), check=True, stdout=subprocess.DEVNULL)
         samples, cur = [], None
         for line in open(os.path.join(td, "p")):
@@ -52,6 +52,7 @@ def main():
             "synthetic_301_20000": synth.window(301, 20000),
             "real_chr2L_5005000": util.read_fasta(os.path.join(HERE, "real_windows.fa"))[0][1]}
     out = {k: run(v) for k, v in wins.items()}
+    out["fly_chr2L_5000000"] = run(util.read_fasta(os.path.join(HERE, "fly_window.fa"))[0][1], "fly", ("--UTR=off",))
     with gzip.open(os.path.join(HERE, "ref_samples.json.gz"), "wt") as f:
         json.dump(out, f, separators=(",", ":"))
     print({k: len(v["samples"]) for k, v in out.items()})

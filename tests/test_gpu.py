@@ -113,6 +113,22 @@ def test_posterior_sampling_matches_reference_and_oracle(dec, oracle):
             assert abs(mine.log_prob - theirs["log_prob"]) <= 1e-6 * max(1.0, abs(theirs["log_prob"]))
 
 
+def test_second_parameter_set_fly(golden):
+    """--species=fly --UTR=off parameters (different splice-site geometry) through the C ABI: Viterbi path and the 99 samples
+    equal the reference's."""
+    dec2 = Decoder(util.blob_bytes("fly_noutr"), 0)
+    dna = util.read_fasta(util.GOLDEN + "/fly_window.fa")[0][1]
+    vit, samples = dec2.decode_batch_sampling([dna, dna[:25000]], 100)
+    ref = golden["fly"][0]
+    assert vit[0].as_tuples() == [tuple(s) for s in ref["states"]]
+    assert abs(vit[0].log_prob - ref["log_prob"]) <= 1e-6 * abs(ref["log_prob"])
+    for mine, theirs in zip(samples[0], util.golden_samples()["fly_chr2L_5000000"]["samples"]):
+        assert mine.as_tuples() == [tuple(x) for x in theirs["states"]]
+    orc = util.Oracle(util.blob_bytes("fly_noutr"))
+    assert vit[1].as_tuples() == orc.viterbi(dna[:25000])["condensed"]
+    dec2.close()
+
+
 def test_full_size_properties(dec):
     """Size-independent checks on a larger batch: batch order independence, idempotence, path structure."""
     wins = synth.windows(96, 50000, start=1000)

@@ -96,6 +96,28 @@ def test_oracle_forward_and_sampling_match_reference(oracle):
         assert int(np.isfinite(r["F"][[c[0] for c in ref["forward_cells"]]]).sum()) >= len(ref["forward_cells"])
 
 
+def test_second_parameter_set_fly(golden):
+    """--species=fly --UTR=off: other signal geometry (ass_start 1, ass_end 4, trans_init_window 25, no exon-terminal content,
+    d = 929).  Oracle vs the reference's path and samples; host build of the kernel source vs the oracle, cell for cell."""
+    blob = util.blob_bytes("fly_noutr")
+    orc, emu = util.Oracle(blob), util.HostEmu(blob)
+    dna = util.read_fasta(util.GOLDEN + "/fly_window.fa")[0][1]
+    ref = golden["fly"][0]
+    r = orc.viterbi(dna, want_matrix=True)
+    assert r["condensed"] == [tuple(s) for s in ref["states"]]
+    assert abs(r["log_prob"] - ref["log_prob"]) <= 1e-9 * abs(ref["log_prob"])
+    e = emu.decode(dna, want_cells=True)
+    assert e["states"] == r["condensed"] and e["log_prob"] == r["log_prob"]
+    V, E = r["V"], e["cells"]
+    assert ((V <= util.NEGT) == (E <= util.NEGT)).all() and (V[V > util.NEGT] == E[V > util.NEGT]).all()
+    gs = util.golden_samples()["fly_chr2L_5000000"]["samples"]
+    os_ = orc.sample(dna, 100)["samples"]
+    es = emu.sample(dna, 99)["samples"]
+    for a, b, c in zip(os_, gs, es):
+        assert a["states"] == [tuple(x) for x in b["states"]] == c["states"]
+        assert abs(a["log_prob"] - b["log_prob"]) <= 1e-6 * max(1.0, abs(b["log_prob"]))
+
+
 # ---------------------------------------------------------------- host build of the kernel source
 def _cells_equal(oracle, emu, dna):
     o = oracle.viterbi(dna, want_matrix=True)

@@ -17,9 +17,10 @@ NEGT = -(1 << 60)
 FRAC = 40
 
 
-def blob_bytes():
+def blob_bytes(name="human"):
+    """Parameter blobs exported from the reference: 'human' (--species=human) or 'fly_noutr' (--species=fly --UTR=off)."""
     from augustus_b200 import params
-    return params.load_bytes(os.path.join(GOLDEN, "human.params.xz"))
+    return params.load_bytes(os.path.join(GOLDEN, name + ".params.xz"))
 
 
 def golden_samples():
