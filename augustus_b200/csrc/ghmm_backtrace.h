@@ -19,10 +19,12 @@ struct PathOut {
 };
 
 AUGB_HD int trunc_flag(int type, int end, int predEnd, int L) {
-    bool isIntron = (type >= T_LESSD0 && type <= 23) || (type >= T_RLESSD0 && type <= 58);
+    const bool utrIntron = type == 26 || type == 27 || type == 32 || type == 33 || type == 61 || type == 62 || type == 67 || type == 68;
+    const bool isIntron = (type >= T_LESSD0 && type <= 23) || (type >= T_RLESSD0 && type <= 58) || utrIntron;
+    const bool utrExon = ((type >= T_UTR5SINGLE && type <= T_UTR3TERM) || (type >= T_RUTR5SINGLE && type <= T_RUTR3TERM)) && !utrIntron;
     int t = 0;
-    if (end == L - 1 && ((type >= 2 && type <= 7) || (type >= 38 && type <= 43) || isIntron)) t |= 2;
-    if ((predEnd == -1 || predEnd == 0) && ((type >= 5 && type <= 8) || (type >= 37 && type <= 40) || isIntron)) t |= 1;
+    if (end == L - 1 && ((type >= 2 && type <= 7) || (type >= 38 && type <= 43) || isIntron || type == T_UTR3SINGLE || type == T_UTR3TERM)) t |= 2;
+    if ((predEnd == -1 || predEnd == 0) && ((type >= 5 && type <= 8) || (type >= 37 && type <= 40) || isIntron || utrExon)) t |= 1;
     return t;
 }
 
@@ -37,7 +39,7 @@ AUGB_HD void backtrace_window(const DevModel* m, const WinView& w, PathOut o) {
     for (int s = 0; s < S; s++) {
         sc_t t = m->term[s]; if (isneg(t)) continue;
         sc_t v = SC_NEG; int ch = m->st[s].chain;
-        if (ch >= 0) { if (ncp[ch] > 0) v = w.cp(ch)[ncp[ch] - 1].tilde + (ch == 0 ? w.AIG : w.AGEO)[L - 1]; }
+        if (ch >= 0) { if (ncp[ch] > 0) v = w.cp(ch)[ncp[ch] - 1].tilde + (ch == 0 ? w.AIG[L - 1] : ch < CH_UTR ? w.AGEO[L - 1] : w.AINT[L - 1] + (sc_t)(L - 1) * m->utr_tself); }
         else { for (int i = w.evstart[L - 1]; i < w.evstart[L]; i++) if (w.ev[i].state == s) v = w.ev[i].V; }
         if (isneg(v)) continue;
         v += t;

@@ -40,7 +40,8 @@ AUGB_HD int mod3(int k) { return (int)((unsigned)(k + 3 * (1 << 28)) % 3u); }
 constexpr int MAXS = 96;      /* states */
 constexpr int MAXC = 8;       /* GC classes */
 constexpr int MAXANC = 8;
-constexpr int NCHAIN = 7;     /* igenic + 3 geometric + 3 reverse geometric */
+constexpr int NCHAIN = 11;    /* igenic + 3 geometric + 3 reverse geometric + 4 UTR introns (utr5, utr3, rutr5, rutr3) */
+constexpr int CH_UTR = 7;     /* first UTR-intron chain */
 constexpr int WF_ALLN = 1 << 8;
 constexpr int WF_NOSLAB = 1 << 9;     /* the prefix-array pool ran out: decode this window again with the generous layout */
 
@@ -49,14 +50,17 @@ enum : int {
     T_IGENIC = 0, T_SINGLE = 1, T_INITIAL0 = 2, T_INTERNAL0 = 5, T_TERMINAL = 8,
     T_LESSD0 = 9, T_LONGDSS0 = 10, T_EQUALD0 = 11, T_GEO0 = 12, T_LONGASS0 = 13,
     T_RSINGLE = 36, T_RINITIAL = 37, T_RINTERNAL0 = 38, T_RTERMINAL0 = 41,
-    T_RLESSD0 = 44, T_RLONGDSS0 = 45, T_REQUALD0 = 46, T_RGEO0 = 47, T_RLONGASS0 = 48
+    T_RLESSD0 = 44, T_RLONGDSS0 = 45, T_REQUALD0 = 46, T_RGEO0 = 47, T_RLONGASS0 = 48,
+    T_UTR5SINGLE = 24, T_UTR3SINGLE = 30, T_UTR3TERM = 35, T_RUTR5SINGLE = 59, T_RUTR3TERM = 70
 };
-enum : int { K_IGENIC, K_EXON, K_LESSD, K_LONGDSS, K_EQUALD, K_GEO, K_LONGASS };
+enum : int { K_IGENIC, K_EXON, K_LESSD, K_LONGDSS, K_EQUALD, K_GEO, K_LONGASS, K_UTR };
+enum : int { U_SINGLE, U_INIT, U_INTRON, U_INTRONVAR, U_INTERNAL, U_TERM };      /* order of the utr5.. / utr3.. types (types.hh:498-499) */
 enum : int { E_SINGLE, E_INITIAL, E_INTERNAL, E_TERMINAL, E_RSINGLE, E_RINITIAL, E_RINTERNAL, E_RTERMINAL };
 
 struct StateDesc {
     int16_t type;
-    int8_t kind, fwd, frame, ek;
+    int8_t kind, fwd, frame, ek;     /* ek: exon kind (E_*), or index into DevModel::ud for UTR states */
+    int8_t uk, u5;                   /* UTR kind (U_*), 1 = 5' UTR */
     int8_t beginPartLen, innerPartOffset, baseOffset, innerPartEndOffset;   /* exonmodel.cc:231-279 */
     int8_t chain;          /* chain id if this is a self-loop chain state, else -1 */
     int8_t feeds;          /* chain id this state is an ancestor of (one-base successor), else -1 */
@@ -68,11 +72,37 @@ struct StateDesc {
 enum : unsigned {
     MB_LONGDSS = 1u << 0, MB_LESSD = 1u << 1, MB_LONGASS = 1u << 2, MB_XDSS = 1u << 3, MB_XSTOP = 1u << 4,
     MB_RLONGASS = 1u << 5, MB_RLESSD = 1u << 6, MB_RLONGDSS = 1u << 7, MB_XRASS = 1u << 8, MB_XRSTART = 1u << 9,
-    MB_SLOW = 1u << 10      /* a GC-class boundary is near: lessD emissions go through the restated SnippetProbs memo */
+    MB_SLOW = 1u << 10,     /* a GC-class boundary is near: lessD emissions go through the restated SnippetProbs memo */
+    /* UTR models only.  Ends: a UTR exon state can end at this column */
+    MB_U5ATG = 1u << 11,    /* utr5single / utr5term: start codon behind the translation-initiation window */
+    MB_UTTS = 1u << 12,     /* utr3single / utr3term: polyA signal + cleavage window ends here (or last column) */
+    MB_URTSS = 1u << 13,    /* rutr5single / rutr5init: reverse TSS window ends here */
+    MB_URSTOP = 1u << 14,   /* rutr3single / rutr3init: reverse stop codon follows */
+    /* Begins: a begin signal starts at this column, the predecessor chain's value at column - 1 goes to a candidate list */
+    MB_TSSB = 1u << 15, MB_ASSB = 1u << 16, MB_RDSSB = 1u << 17, MB_RTTSB = 1u << 18,
+    MB_UTR_ENDS = MB_U5ATG | MB_UTTS | MB_URTSS | MB_URSTOP, MB_UTR_BEGINS = MB_TSSB | MB_ASSB | MB_RDSSB | MB_RTTSB
 };
+typedef uint32_t mask_t;
 
 /* prefix arrays per GC class, each (L+1) long: P[i+1] - P[l] = sum over positions l..i */
 enum : int { PA_PI = 0, PA_PIR = 1, PA_PX = 2 /* +phi */, PA_PXR = 5 /* +phi */, PA_PER_CLASS = 8 };
+
+/* how one UTR exon state scores a (predecessor end, duration) candidate: UtrModel::notEndPartEmiProb (utrmodel.cc:1167-1405) as
+ * begin signal + content prefix difference + length distribution, all table driven */
+enum : int { BS_NONE, BS_TSSF, BS_ASSF, BS_DSSR, BS_TTSR };           /* begin signal */
+enum : int { UE_ATG, UE_DSSF, UE_TTSF, UE_TSSR, UE_ASSR, UE_RSTOP };  /* end part (utrmodel.cc:1072-1110) */
+enum : int { US_INIT5 = 0, US_5 = 1, US_3 = 2, US_RINIT5 = 3, US_R5 = 4, US_R3 = 5, NUSEG = 6 };   /* SegProbs arrays (utrmodel.cc:701-712) */
+struct UtrDesc {
+    int8_t list;            /* candidate list */
+    int8_t begsig, endkind, seg;
+    int8_t shortrule;       /* middle part shorter than nothing: 0 = plain, 1 = 2^n, 2 = 4^n (utrmodel.cc:1180,1238,1250,1273,1323,1335) */
+    int8_t trunc;           /* 1 = left-truncated begins (before the window) are allowed: TSS / reverse polyA signal partly outside */
+    int16_t bom_off, bobe_off;      /* beginOfMiddle, beginOfBioExon relative to begin */
+    int16_t lm_off, rm_off;         /* leftMost / rightMost endOfPred = base - off */
+    int16_t eobe_off, boe_off;      /* endOfBioExon = base + eobe_off, beginOfEndPart = base + boe_off (getEndPositions :1572-1643) */
+    int16_t maxlen_n;       /* entries of the length table */
+    int8_t ldi;             /* index into DevModel::uld */
+};
 
 struct DevModel {
     int S, C, k, d, dStateLen;
@@ -100,6 +130,18 @@ struct DevModel {
     sc_t ochre, amber, opal, probN, log025, log3, ass_invalid_pat;
     double centroids[MAXC * 4 * 4][4];
     double wm[4][4];
+    /* ---- UTR states (UtrModel), only when utr != 0 ---- */
+    int utr;
+    int tuw, tss_start, tss_end, tata_start, tata_end, d_tata_min, d_tata_max, tssup_k, dpc, boxlen, tts_spacing;
+    int umax, umax3s, umax3t;
+    int tssm_n, tssm_k, tsstm_n, tsstm_k, tatam_n, tatam_k, ttsm_n, ttsm_k;
+    int8_t r_utr[2][2][6];          /* [rev][5'][U_*] -> state */
+    UtrDesc ud[16]; int8_t uslot[16];   /* UTR exon states: descriptors and state index per slot */
+    const sc_t *u5i, *u5, *u3, *tup;    /* content tables [c << 2(k+1) | kmer] */
+    const sc_t *tssm, *tsstm, *tatam, *ttsm, *aataaa;
+    const sc_t* uld[10]; int n_uld[10]; /* 5single,5init,5internal,5term,3single,3init,3internal,3term, tail5single, tail3single */
+    sc_t log_polya, log_nopolya, log2, utr_tself;
+    uint8_t isstart[64];
 };
 
 /* one DP cell of a sparse (non-chain) state that is non-zero */
@@ -139,18 +181,24 @@ struct SnipHead { uint32_t first, last; };
 struct SnipFrame { int32_t base, len; int32_t add, pad; sc_t part; };
 
 /* candidate lists of a window */
-enum : int { CL_LD = 0 /* +f: longdss_f */, CL_RA = 3 /* +f: rlongass_f */, CL_LA = 6 /* +phase */, CL_RD = 9 /* +phase */, NCL = 12 };
+enum : int { CL_LD = 0 /* +f: longdss_f */, CL_RA = 3 /* +f: rlongass_f */, CL_LA = 6 /* +phase */, CL_RD = 9 /* +phase */, NCL_BASE = 12,
+             /* UTR models: (begin-signal site, predecessor chain value) lists and the exon cells UTR states follow */
+             CL_T5 = 12 /* TSS, igenic */, CL_A5 = 13 /* ASS, utr5intron */, CL_A3 = 14 /* ASS, utr3intron */, CL_R5 = 15 /* rDSS, rutr5intron */,
+             CL_R3 = 16 /* rDSS, rutr3intron */, CL_TR = 17 /* reverse polyA, igenic */, CL_X3 = 18 /* single, terminal */, CL_XR = 19 /* rsingle, rinitial */,
+             NCL = 20 };
 
 /* per-window view of the workspace (all pointers device/global) */
 struct WinView {
     int L, nclassmask, ev_cap, cl_cap, cp_cap;
     const uint8_t* code;       /* 0..3, 4 = unknown */
     const uint8_t* gc;         /* class per position */
-    const uint16_t* mask;
+    const mask_t* mask;
     const uint16_t *kf, *kr;   /* (k+1)-mer code ending / reverse-complement code starting at each position, 0x8000 = invalid */
     const sc_t* const* parr_c; /* -> WinOuts::slab: per GC class present [PA_PER_CLASS][L+1] (first class in the window, others from the slab pool) */
     const sc_t* sig;           /* [NSIG][L] */
     const sc_t *AIG, *AGEO;    /* chain prefix arrays, [L] */
+    /* UTR models: intron emission prefix of the UTR-intron chains [L], SegProbs cumulative sums [NUSEG][L+1], TSS / TTS scores */
+    const sc_t *AINT, *useg, *tssF, *tssR, *ttsF, *ttsR;     /* tss*[L] by left end of the window, tts*[L+1] by first base of the polyA box */
     const int32_t *nsf, *nsr;  /* nearestStopForward / Reverse (exonmodel.cc:101-156) */
     Event* ev; int32_t* evstart;
     Cand* cl0; ChainCP* cp0;   /* list i / chain i start at cl0 + i*cl_stride, cp0 + i*cp_stride (no pointer tables: those end up in local memory) */

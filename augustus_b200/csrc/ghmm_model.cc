@@ -47,6 +47,13 @@ static void classify(StateDesc& s, const DevModel& m) {
         else { s.baseOffset = s.innerPartEndOffset = s.fwd ? m.dss_start : m.ass_end; }
         return;
     }
+    s.uk = -1; s.u5 = 0;
+    if ((t >= T_UTR5SINGLE && t <= T_UTR3TERM) || (t >= T_RUTR5SINGLE && t <= T_RUTR3TERM)) {
+        if (!m.utr) return;
+        int o = t - (s.fwd ? T_UTR5SINGLE : T_RUTR5SINGLE);
+        s.kind = K_UTR; s.u5 = o < 6; s.uk = (int8_t)(o % 6);
+        return;
+    }
     int base = s.fwd ? T_LESSD0 : T_RLESSD0, off = t - base;
     if (off < 0 || off >= 15) return;     /* kind stays -1: unsupported */
     s.frame = off / 5;
@@ -76,7 +83,8 @@ int HostModel::build(const void* blob, size_t nbytes) {
     if (m.S < 1 || m.S > MAXS || m.C < 1 || m.C > MAXC) { err = "state / class count out of range"; return AUGB200_ERR_UNSUPPORTED; }
     if (ik != m.k || gk != m.k || m.k < 1 || m.k > 4) { err = "content model orders must be equal and <= 4"; return AUGB200_ERR_UNSUPPORTED; }
     if (nbins > 0) { err = "TRANSINITBIN models are not supported yet"; return AUGB200_ERR_UNSUPPORTED; }
-    if (utr || nc) { err = "UTR / nc state models are not supported yet"; return AUGB200_ERR_UNSUPPORTED; }
+    if (nc) { err = "nc state models are not supported yet"; return AUGB200_ERR_UNSUPPORTED; }
+    m.utr = utr ? 1 : 0;
     m.dStateLen = m.d - 2 - m.dss_end - m.ass_start - 2 - m.ass_up;     /* intronmodel.cc:519-520 */
     if (m.dStateLen < 1) { err = "d too small"; return AUGB200_ERR_UNSUPPORTED; }
 
@@ -104,6 +112,32 @@ int HostModel::build(const void* blob, size_t nbytes) {
     size_t o_ldx = push("lendist_intron", 0); m.n_ld_intron = (int)(tab.size() - n0);
     size_t npat_a = (size_t)1 << (2 * (m.ass_start + m.ass_end)), npat_d = (size_t)1 << (2 * (m.dss_start + m.dss_end));
     size_t o_ap = push("ass_pattern", npat_a), o_apn = push("ass_pattern_nonag", npat_a), o_dp = push("dss_pattern", npat_d), o_dpn = push("dss_pattern_nongt", npat_d);
+    /* ---- UtrModel tables (utrmodel.cc:540-696) ---- */
+    size_t o_u5i = 0, o_u5 = 0, o_u3 = 0, o_tup = 0, o_tssm = 0, o_tsstm = 0, o_tatam = 0, o_ttsm = 0, o_aat = 0, o_uld[10] = {0};
+    if (m.utr) {
+        if (r.i32("utr_k") != m.k) { err = "content model orders must be equal"; return AUGB200_ERR_UNSUPPORTED; }
+        m.tssup_k = r.i32("tssup_k"); m.tss_start = r.i32("tss_start"); m.tss_end = r.i32("tss_end");
+        m.tata_start = r.i32("tata_start"); m.tata_end = r.i32("tata_end"); m.d_tata_min = r.i32("d_tss_tata_min"); m.d_tata_max = r.i32("d_tss_tata_max");
+        m.tuw = r.i32("tss_upwindow_size"); m.dpc = r.i32("d_polyasig_cleavage"); m.boxlen = r.i32("aataaa_boxlen"); m.tts_spacing = r.i32("tts_spacing");
+        m.umax = r.i32("utr_max_exon_length"); m.umax3s = r.i32("utr_max3singlelength"); m.umax3t = r.i32("utr_max3termlength");
+        m.tssm_n = r.i32("tss_motif_n"); m.tssm_k = r.i32("tss_motif_k"); m.tsstm_n = r.i32("tsstata_motif_n"); m.tsstm_k = r.i32("tsstata_motif_k");
+        m.tatam_n = r.i32("tata_motif_n"); m.tatam_k = r.i32("tata_motif_k"); m.ttsm_n = r.i32("tts_motif_n"); m.ttsm_k = r.i32("tts_motif_k");
+        if (!r.ok) return AUGB200_ERR_BAD_BLOB;
+        if (m.tssup_k < 0 || m.tssup_k > m.k || m.tssm_k > m.k || m.tsstm_k > m.k || m.tatam_k > m.k || m.ttsm_k > m.k || m.boxlen < 1 || m.boxlen > 8 || m.tts_spacing < 1)
+            { err = "UTR motif orders / polyA box out of range"; return AUGB200_ERR_UNSUPPORTED; }
+        o_u5i = push("utr5init_emi", m.C * K1); o_u5 = push("utr5_emi", m.C * K1); o_u3 = push("utr3_emi", m.C * K1);
+        o_tup = push("tssup_emi", (size_t)m.C << (2 * (m.tssup_k + 1)));
+        o_tssm = push("tss_motif", (size_t)m.C * m.tssm_n << (2 * (m.tssm_k + 1))); o_tsstm = push("tsstata_motif", (size_t)m.C * m.tsstm_n << (2 * (m.tsstm_k + 1)));
+        o_tatam = push("tata_motif", (size_t)m.C * m.tatam_n << (2 * (m.tatam_k + 1))); o_ttsm = push("tts_motif", (size_t)m.C * m.ttsm_n << (2 * (m.ttsm_k + 1)));
+        o_aat = push("aataaa_probs", (size_t)1 << (2 * m.boxlen));
+        static const char* ldn[10] = {"lendist_utr5single", "lendist_utr5initial", "lendist_utr5internal", "lendist_utr5terminal", "lendist_utr3single",
+                                      "lendist_utr3initial", "lendist_utr3internal", "lendist_utr3terminal", "taillendist_utr5single", "taillendist_utr3single"};
+        for (int i = 0; i < 10; i++) { size_t b0 = tab.size(); o_uld[i] = push(ldn[i], 0); m.n_uld[i] = (int)(tab.size() - b0); }
+        m.log_polya = quantize(r.f64("log_prob_polya")); m.log_nopolya = quantize(r.f64("log_no_polya")); m.log2 = quantize(log(2.0));
+        size_t n3; const int32_t* iss = r.iarr("is_start_codon", &n3);
+        if (!r.ok || n3 != 64) { err = "bad UTR tables"; return AUGB200_ERR_BAD_BLOB; }
+        for (int i = 0; i < 64; i++) m.isstart[i] = (uint8_t)iss[i];
+    }
     if (!r.ok) return AUGB200_ERR_BAD_BLOB;
     if (m.n_ld_intron < m.d + 1) { err = "intron length distribution shorter than d"; return AUGB200_ERR_BAD_BLOB; }
     /* igenic emission of the first k columns (igenicmodel.cc:342-354), incl. the normaliser quirk */
@@ -151,6 +185,8 @@ int HostModel::build(const void* blob, size_t nbytes) {
     for (int d = 0; d < 2; d++) for (int f = 0; f < 3; f++) m.r_longdss[d][f] = m.r_lessd[d][f] = m.r_equald[d][f] = m.r_longass[d][f] = -1;
     m.r_single = m.r_terminal = m.r_rsingle = m.r_rinitial = -1;
     for (int f = 0; f < 3; f++) m.r_initial[f] = m.r_internal[f] = m.r_rinternal[f] = m.r_rterminal[f] = -1;
+    for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) for (int c = 0; c < 6; c++) m.r_utr[a][b][c] = -1;
+    for (int i = 0; i < 16; i++) m.uslot[i] = -1;
     const sc_t* T = tab.data() + o_trans;
     for (int s = 0; s < m.S; s++) {
         StateDesc& sd = m.st[s]; sd.type = (int16_t)stt[s]; classify(sd, m);
@@ -173,6 +209,10 @@ int HostModel::build(const void* blob, size_t nbytes) {
         case K_LESSD: slot = &m.r_lessd[dir][f]; break;
         case K_EQUALD: slot = &m.r_equald[dir][f]; break;
         case K_LONGASS: slot = &m.r_longass[dir][f]; break;
+        case K_UTR:
+            slot = &m.r_utr[dir][sd.u5][sd.uk];
+            if (sd.uk == U_INTRON) sd.chain = (int8_t)(CH_UTR + dir * 2 + (sd.u5 ? 0 : 1));
+            break;
         default:
             switch (sd.ek) {
             case E_SINGLE: slot = &m.r_single; break; case E_INITIAL: slot = &m.r_initial[f]; break;
@@ -183,6 +223,64 @@ int HostModel::build(const void* blob, size_t nbytes) {
         }
         if (*slot >= 0) { err = "duplicate state role"; return AUGB200_ERR_UNSUPPORTED; }
         *slot = (int8_t)s;
+        if (sd.chain >= CH_UTR) m.chain_state[sd.chain] = (int8_t)s;
+    }
+    if (m.utr) {
+        /* UTR exon states: slot order of Sweep::process_column and the table-driven geometry of UtrModel::viterbiForwardAndSampling
+         * (utrmodel.cc:821-916), getEndPositions (:1572-1643) and notEndPartEmiProb (:1173-1404) */
+        const int TUW = m.tuw, TE = m.tss_end, TIW = m.tiw, DW = m.dss_start + m.dss_end + 2, AW = m.ass_start + m.ass_end + 2, UP = m.ass_up,
+                  DE = m.dss_end, AS = m.ass_start, AE = m.ass_end, PB = m.boxlen, DPC = m.dpc;
+        static const int kinds[4] = {U_SINGLE, U_INIT, U_INTERNAL, U_TERM};
+        for (int dir = 0; dir < 2; dir++) for (int three = 0; three < 2; three++) for (int q = 0; q < 4; q++) {
+            const int slot = dir * 8 + three * 4 + q, uk = kinds[q], st = m.r_utr[dir][three ? 0 : 1][uk];
+            UtrDesc& u = m.ud[slot]; memset(&u, 0, sizeof u);
+            m.uslot[slot] = (int8_t)st;
+            if (st < 0) continue;
+            m.st[st].ek = (int8_t)slot;
+            u.ldi = (int8_t)(three * 4 + q);
+            const int term5rm = (-UP - AW + TIW + AE < 0) ? UP + AW - TIW - AE : UP + AW;
+            const int single5rm = TUW + 1 - TIW > 1 ? TUW + 1 - TIW : 1;
+            if (!dir && !three) {
+                switch (uk) {
+                case U_SINGLE: u = UtrDesc{CL_T5, BS_TSSF, UE_ATG, US_INIT5, 1, 1, (int16_t)(TUW + TE), (int16_t)TUW, (int16_t)(m.umax - TIW + TUW), (int16_t)single5rm, (int16_t)TIW, 1, 0, u.ldi}; break;
+                case U_INIT: u = UtrDesc{CL_T5, BS_TSSF, UE_DSSF, US_INIT5, 0, 1, (int16_t)(TUW + TE), (int16_t)TUW, (int16_t)(m.umax + 2 + DE + TUW), (int16_t)(TUW + TE + DW), (int16_t)(-(DE + 2)), (int16_t)(-DW + 1), 0, u.ldi}; break;
+                case U_INTERNAL: u = UtrDesc{CL_A5, BS_ASSF, UE_DSSF, US_5, 0, 0, (int16_t)(UP + AW), (int16_t)(UP + AS + 2), (int16_t)(m.umax + 2 + DE + UP + AS + 2), (int16_t)(DW + UP + AW), (int16_t)(-(DE + 2)), (int16_t)(-DW + 1), 0, u.ldi}; break;
+                default: u = UtrDesc{CL_A5, BS_ASSF, UE_ATG, US_5, 2, 0, (int16_t)(UP + AW), (int16_t)(UP + AS + 2), (int16_t)(m.umax - TIW + UP + AS + 2), (int16_t)term5rm, (int16_t)TIW, 1, 0, u.ldi};
+                }
+            } else if (!dir) {
+                switch (uk) {
+                case U_SINGLE: u = UtrDesc{CL_X3, BS_NONE, UE_TTSF, US_3, 0, 0, 0, 0, (int16_t)m.umax3s, (int16_t)(DPC + PB), 0, (int16_t)(-DPC - PB + 1), 0, u.ldi}; break;
+                case U_INIT: u = UtrDesc{CL_X3, BS_NONE, UE_DSSF, US_3, 2, 0, 0, 0, (int16_t)(m.umax + 2 + DE), (int16_t)(DE + 2), (int16_t)(-(DE + 2)), (int16_t)(-DW + 1), 0, u.ldi}; break;
+                case U_INTERNAL: u = UtrDesc{CL_A3, BS_ASSF, UE_DSSF, US_3, 0, 0, (int16_t)(UP + AW), (int16_t)(UP + AS + 2), (int16_t)(m.umax + 2 + DE + 2 + AS + UP), (int16_t)(DW + UP + AW), (int16_t)(-(DE + 2)), (int16_t)(-DW + 1), 0, u.ldi}; break;
+                default: u = UtrDesc{CL_A3, BS_ASSF, UE_TTSF, US_3, 0, 0, (int16_t)(UP + AW), (int16_t)(UP + AS + 2), (int16_t)(m.umax3t + 2 + AS + UP), (int16_t)(DPC + PB + AW + UP), 0, (int16_t)(-DPC - PB + 1), 0, u.ldi};
+                }
+            } else if (!three) {
+                switch (uk) {
+                case U_SINGLE: u = UtrDesc{CL_XR, BS_NONE, UE_TSSR, US_RINIT5, 1, 0, 0, (int16_t)(-TIW), (int16_t)(m.umax - TIW + TUW), (int16_t)single5rm, (int16_t)(-TUW), (int16_t)(-TUW - TE + 1), 0, u.ldi}; break;
+                case U_INIT: u = UtrDesc{CL_R5, BS_DSSR, UE_TSSR, US_RINIT5, 0, 0, (int16_t)DW, (int16_t)(DE + 2), (int16_t)(m.umax + 2 + DE + TUW), (int16_t)(TUW + TE + DW), (int16_t)(-TUW), (int16_t)(-TUW - TE + 1), 0, u.ldi}; break;
+                case U_INTERNAL: u = UtrDesc{CL_R5, BS_DSSR, UE_ASSR, US_R5, 0, 0, (int16_t)DW, (int16_t)(DE + 2), (int16_t)(m.umax + 2 + DE + UP + AS + 2), (int16_t)(DW + UP + AW), (int16_t)(-(UP + AS + 2)), (int16_t)(-AW - UP + 1), 0, u.ldi}; break;
+                default: u = UtrDesc{CL_XR, BS_NONE, UE_ASSR, US_R5, 2, 0, 0, (int16_t)(-TIW), (int16_t)(m.umax - TIW + UP + AS + 2), (int16_t)term5rm, (int16_t)(-(UP + AS + 2)), (int16_t)(-AW - UP + 1), 0, u.ldi};
+                }
+            } else {
+                switch (uk) {
+                case U_SINGLE: u = UtrDesc{CL_TR, BS_TTSR, UE_RSTOP, US_R3, 0, 1, (int16_t)(PB + DPC), 0, (int16_t)m.umax3s, (int16_t)(DPC + PB), 0, 1, 0, u.ldi}; break;
+                case U_INIT: u = UtrDesc{CL_R3, BS_DSSR, UE_RSTOP, US_R3, 2, 0, (int16_t)DW, (int16_t)(DE + 2), (int16_t)(m.umax + 2 + DE), (int16_t)(DE + 2), 0, 1, 0, u.ldi}; break;
+                case U_INTERNAL: u = UtrDesc{CL_R3, BS_DSSR, UE_ASSR, US_R3, 0, 0, (int16_t)DW, (int16_t)(DE + 2), (int16_t)(m.umax + 2 + DE + UP + AS + 2), (int16_t)(DW + UP + AW), (int16_t)(-(UP + AS + 2)), (int16_t)(-AW - UP + 1), 0, u.ldi}; break;
+                default: u = UtrDesc{CL_TR, BS_TTSR, UE_ASSR, US_R3, 0, 1, (int16_t)(PB + DPC), 0, (int16_t)(m.umax3t + 2 + AS + UP), (int16_t)(DPC + PB + AW + UP), (int16_t)(-(UP + AS + 2)), (int16_t)(-AW - UP + 1), 0, u.ldi};
+                }
+            }
+            /* every endOfPred of the loop must index the length table: lm_off bounds the length */
+            if (u.rm_off < 1) { err = "UTR geometry lets a state end before it begins"; return AUGB200_ERR_UNSUPPORTED; }
+        }
+        /* the four UTR-intron chains share the intron emission prefix and need one class-independent self transition */
+        bool have = false;
+        for (int ch = CH_UTR; ch < NCHAIN; ch++) {
+            int cs = m.chain_state[ch]; if (cs < 0) continue;
+            for (int c = 0; c < m.C; c++) {
+                sc_t t = T[((size_t)c * m.S + cs) * m.S + cs];
+                if (!have) { m.utr_tself = t; have = true; } else if (t != m.utr_tself) { err = "UTR intron self-loops differ"; return AUGB200_ERR_UNSUPPORTED; }
+            }
+        }
     }
     {
         int q = 0;
@@ -203,7 +301,21 @@ int HostModel::build(const void* blob, size_t nbytes) {
             int a = sd.anc[i]; const StateDesc& ad = m.st[a];
             if (a == s) { selfloop = true; continue; }
             switch (sd.kind) {
-            case K_IGENIC: ok &= ad.kind == K_EXON; break;
+            case K_IGENIC: ok &= ad.kind == K_EXON || (ad.kind == K_UTR && ad.uk != U_INTRON); break;
+            case K_UTR: {
+                /* the predecessor kinds the candidate lists of Sweep::utr_eval are built for; intronvar states (hint-only) never hold a cell */
+                if (ad.kind == K_UTR && ad.uk == U_INTRONVAR) break;
+                if (sd.uk == U_INTRONVAR) break;
+                if (sd.uk == U_INTRON) { ok &= ad.kind == K_UTR && ad.fwd == sd.fwd && ad.u5 == sd.u5 && ad.uk != U_INTRON; break; }
+                const UtrDesc& u = m.ud[sd.ek];
+                switch (u.list) {
+                case CL_T5: case CL_TR: ok &= ad.kind == K_IGENIC; break;
+                case CL_A5: case CL_A3: case CL_R5: case CL_R3: ok &= ad.kind == K_UTR && ad.uk == U_INTRON && ad.fwd == sd.fwd && ad.u5 == sd.u5; break;
+                case CL_X3: ok &= ad.kind == K_EXON && (ad.ek == E_SINGLE || ad.ek == E_TERMINAL); break;
+                default: ok &= ad.kind == K_EXON && (ad.ek == E_RSINGLE || ad.ek == E_RINITIAL);
+                }
+                break;
+            }
             case K_GEO: ok &= ad.kind == K_EQUALD && ad.fwd == sd.fwd && ad.frame == sd.frame; break;
             case K_EQUALD: case K_LESSD:
                 ok &= (sd.fwd ? ad.kind == K_LONGDSS : ad.kind == K_LONGASS) && ad.fwd == sd.fwd && ad.frame == sd.frame && sd.nanc == 1; break;
@@ -213,10 +325,14 @@ int HostModel::build(const void* blob, size_t nbytes) {
                 switch (sd.ek) {
                 case E_INTERNAL: case E_TERMINAL: ok &= ad.kind == K_LONGASS && ad.fwd; break;
                 case E_RINTERNAL: case E_RINITIAL: ok &= ad.kind == K_LONGDSS && !ad.fwd; break;
-                default: ok &= ad.kind == K_IGENIC && sd.nanc == 1;
+                case E_SINGLE: case E_INITIAL:      /* igenic, or (UTR models) the 5' UTR states that end before the start codon */
+                    ok &= m.utr ? (ad.kind == K_UTR && ad.fwd && ad.u5 && (ad.uk == U_SINGLE || ad.uk == U_TERM)) : (ad.kind == K_IGENIC && sd.nanc == 1); break;
+                default:                            /* rsingle, rterminal */
+                    ok &= m.utr ? (ad.kind == K_UTR && !ad.fwd && !ad.u5 && (ad.uk == U_SINGLE || ad.uk == U_INIT)) : (ad.kind == K_IGENIC && sd.nanc == 1);
                 }
             }
         }
+        if (sd.kind == K_UTR && sd.uk == U_INTRONVAR) { if (!isneg(tab[o_init + s])) ok = false; }     /* must stay empty */
         if (selfloop != (sd.chain >= 0)) ok = false;
         if (!ok) { err = "unsupported transition topology at state " + std::to_string(s); return AUGB200_ERR_UNSUPPORTED; }
         (void)kind_of;
@@ -229,7 +345,7 @@ int HostModel::build(const void* blob, size_t nbytes) {
     /* the 6 geometric chains share one prefix array: emission and self-loop must agree per class */
     for (int c = 0; c < m.C; c++) {
         sc_t ref = 0; bool have = false;
-        for (int ch = 1; ch < NCHAIN; ch++) {
+        for (int ch = 1; ch < CH_UTR; ch++) {
             int cs = m.chain_state[ch]; if (cs < 0) continue;
             sc_t t = T[((size_t)c * m.S + cs) * m.S + cs];
             if (!have) { ref = t; have = true; } else if (t != ref) { err = "geometric self-loops differ"; return AUGB200_ERR_UNSUPPORTED; }
@@ -243,6 +359,11 @@ int HostModel::build(const void* blob, size_t nbytes) {
     m.iemi = b + o_iemi; m.gemi = b + o_gemi; m.gfirst = b + o_gfirst; m.tis = b + o_tis; m.assm = b + o_assm;
     m.ld_single = b + o_lds; m.ld_initial = b + o_ldi; m.ld_internal = b + o_ldn; m.ld_terminal = b + o_ldt; m.ld_intron = b + o_ldx;
     m.ass_pat = b + o_ap; m.ass_pat_non = b + o_apn; m.dss_pat = b + o_dp; m.dss_pat_non = b + o_dpn;
+    if (m.utr) {
+        m.u5i = b + o_u5i; m.u5 = b + o_u5; m.u3 = b + o_u3; m.tup = b + o_tup;
+        m.tssm = b + o_tssm; m.tsstm = b + o_tsstm; m.tatam = b + o_tatam; m.ttsm = b + o_ttsm; m.aataaa = b + o_aat;
+        for (int i = 0; i < 10; i++) m.uld[i] = b + o_uld[i];
+    }
     return AUGB200_OK;
 }
 
@@ -254,6 +375,9 @@ DevModel HostModel::rebased(const sc_t* base) const {
     r.iemi = rb(dm.iemi); r.gemi = rb(dm.gemi); r.gfirst = rb(dm.gfirst); r.tis = rb(dm.tis); r.assm = rb(dm.assm);
     r.ld_single = rb(dm.ld_single); r.ld_initial = rb(dm.ld_initial); r.ld_internal = rb(dm.ld_internal); r.ld_terminal = rb(dm.ld_terminal); r.ld_intron = rb(dm.ld_intron);
     r.ass_pat = rb(dm.ass_pat); r.ass_pat_non = rb(dm.ass_pat_non); r.dss_pat = rb(dm.dss_pat); r.dss_pat_non = rb(dm.dss_pat_non);
+    r.u5i = rb(dm.u5i); r.u5 = rb(dm.u5); r.u3 = rb(dm.u3); r.tup = rb(dm.tup);
+    r.tssm = rb(dm.tssm); r.tsstm = rb(dm.tsstm); r.tatam = rb(dm.tatam); r.ttsm = rb(dm.ttsm); r.aataaa = rb(dm.aataaa);
+    for (int i = 0; i < 10; i++) r.uld[i] = rb(dm.uld[i]);
     return r;
 }
 

@@ -31,6 +31,7 @@ struct WinOuts {
 /* byte layout of one window's workspace; every section is 16-byte aligned */
 struct WinLayout {
     size_t code, gc, mask, kf, kr, parr, sig, aig, ageo, nsf, nsr;        /* static (prep) */
+    size_t aint, useg, tssF, tssR, ttsF, ttsR; int utr, ncl, nchain;      /* UTR models only */
     size_t ev, evstart, cl[NCL], cp[NCHAIN], outs;           /* dynamic (sweep) */
     size_t snip_head, snip_pool, snip_stack; int snip_cap;
     size_t evF, clF, fcp; int fcp_cap;                       /* forward pass (0 capacity when not requested) */
@@ -44,10 +45,10 @@ AUGB_HD size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
  * cell per state; a candidate list gets at most one entry per column); the default sizes are ~3x what human-like
  * DNA needs (measured: 1.9 events, 0.03 list entries per base) and a window that overflows them is reported with
  * status AUGB200_ERR_CAPACITY and decoded again with the generous layout (augb200.cu: decode_batch). */
-inline WinLayout make_layout(int L, int C, bool generous = false, bool forward = false, int nsamp = 0) {
+inline WinLayout make_layout(int L, int C, bool generous = false, bool forward = false, int nsamp = 0, bool utr = false) {
     WinLayout w; size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = al16(o + bytes); return r; };
-    w.code = take(L); w.gc = take(L); w.mask = take((size_t)L * 2); w.kf = take((size_t)L * 2); w.kr = take((size_t)L * 2);
+    w.code = take(L); w.gc = take(L); w.mask = take((size_t)L * sizeof(mask_t)); w.kf = take((size_t)L * 2); w.kr = take((size_t)L * 2);
     /* prefix arrays: one slab (PA_PER_CLASS arrays) in the window for the first GC class present; further classes take
      * slabs from a pool shared by the batch (generous layout: all C slabs in the window) */
     w.slab = (size_t)PA_PER_CLASS * (L + 1) * sizeof(sc_t);
@@ -56,15 +57,19 @@ inline WinLayout make_layout(int L, int C, bool generous = false, bool forward =
     w.sig = take((size_t)NSIG * L * sizeof(sc_t));
     w.aig = take((size_t)L * sizeof(sc_t)); w.ageo = take((size_t)L * sizeof(sc_t));
     w.nsf = take((size_t)(L + 3) * 4); w.nsr = take((size_t)(L + 3) * 4);
+    w.utr = utr ? 1 : 0; w.ncl = utr ? NCL : NCL_BASE; w.nchain = utr ? NCHAIN : CH_UTR;
+    w.aint = take(utr ? (size_t)L * sizeof(sc_t) : 0); w.useg = take(utr ? (size_t)NUSEG * (L + 1) * sizeof(sc_t) : 0);
+    w.tssF = take(utr ? (size_t)L * sizeof(sc_t) : 0); w.tssR = take(utr ? (size_t)L * sizeof(sc_t) : 0);
+    w.ttsF = take(utr ? (size_t)(L + 1) * sizeof(sc_t) : 0); w.ttsR = take(utr ? (size_t)(L + 1) * sizeof(sc_t) : 0);
     if (generous) { w.ev_cap = 48 * L + 256; w.cl_cap = L + 64; w.cp_cap = L + 64; w.path_cap = L + 64; }
     else { w.ev_cap = 3 * L + 256; w.cl_cap = L / 6 + 64; w.cp_cap = L / 16 + 64; w.path_cap = L / 8 + 64; }
     if ((size_t)w.ev_cap * sizeof(Event) < (size_t)4 * (L + 1) * 4) w.ev_cap = (int)(((size_t)4 * (L + 1) * 4) / sizeof(Event) + 1);   /* prep scratch */
     w.ev = take((size_t)w.ev_cap * sizeof(Event)); w.evstart = take((size_t)(L + 2) * 4);
-    for (int i = 0; i < NCL; i++) w.cl[i] = take((size_t)w.cl_cap * sizeof(Cand));
-    for (int i = 0; i < NCHAIN; i++) w.cp[i] = take((size_t)w.cp_cap * sizeof(ChainCP));
+    for (int i = 0; i < NCL; i++) w.cl[i] = take(i < w.ncl ? (size_t)w.cl_cap * sizeof(Cand) : 0);
+    for (int i = 0; i < NCHAIN; i++) w.cp[i] = take(i < w.nchain ? (size_t)w.cp_cap * sizeof(ChainCP) : 0);
     w.fcp_cap = forward ? (generous ? L + 64 : L / 2 + 64) : 0;
-    w.evF = take(forward ? (size_t)w.ev_cap * 8 : 0); w.clF = take(forward ? (size_t)NCL * w.cl_cap * 8 : 0);
-    w.fcp = take((size_t)NCHAIN * w.fcp_cap * sizeof(FChainCP));
+    w.evF = take(forward ? (size_t)w.ev_cap * 8 : 0); w.clF = take(forward ? (size_t)w.ncl * w.cl_cap * 8 : 0);
+    w.fcp = take((size_t)w.nchain * w.fcp_cap * sizeof(FChainCP));
     w.nsamp = forward ? nsamp : 0;
     w.opt_cap = w.nsamp ? w.cl_cap + 1024 : 0; w.samp_cap = w.nsamp ? (generous ? w.nsamp * (L / 8 + 64) : w.nsamp * 160 + L / 4) : 0;
     w.opt = take((size_t)w.opt_cap * sizeof(SampleOpt)); w.sorted = take((size_t)w.opt_cap * 4);
@@ -82,10 +87,12 @@ inline WinLayout make_layout(int L, int C, bool generous = false, bool forward =
 
 AUGB_HD WinView make_view(char* base, const WinLayout& lay, int L, int classmask) {
     WinView v; v.L = L; v.nclassmask = classmask; v.ev_cap = lay.ev_cap; v.cl_cap = lay.cl_cap; v.cp_cap = lay.cp_cap;
-    v.code = (const uint8_t*)(base + lay.code); v.gc = (const uint8_t*)(base + lay.gc); v.mask = (const uint16_t*)(base + lay.mask);
+    v.code = (const uint8_t*)(base + lay.code); v.gc = (const uint8_t*)(base + lay.gc); v.mask = (const mask_t*)(base + lay.mask);
     v.kf = (const uint16_t*)(base + lay.kf); v.kr = (const uint16_t*)(base + lay.kr);
     v.sig = (const sc_t*)(base + lay.sig); v.AIG = (const sc_t*)(base + lay.aig); v.AGEO = (const sc_t*)(base + lay.ageo);
     v.nsf = (const int32_t*)(base + lay.nsf); v.nsr = (const int32_t*)(base + lay.nsr);
+    v.AINT = (const sc_t*)(base + lay.aint); v.useg = (const sc_t*)(base + lay.useg);
+    v.tssF = (const sc_t*)(base + lay.tssF); v.tssR = (const sc_t*)(base + lay.tssR); v.ttsF = (const sc_t*)(base + lay.ttsF); v.ttsR = (const sc_t*)(base + lay.ttsR);
     v.ev = (Event*)(base + lay.ev); v.evstart = (int32_t*)(base + lay.evstart);
     v.cl0 = (Cand*)(base + lay.cl[0]); v.cp0 = (ChainCP*)(base + lay.cp[0]);
     v.evF = (double*)(base + lay.evF); v.clF0 = (double*)(base + lay.clF); v.fcp0 = (FChainCP*)(base + lay.fcp); v.fcp_cap = lay.fcp_cap; v.fcp_stride = lay.fcp_cap;
@@ -163,7 +170,7 @@ AUGB_HD sc_t aig_term(const DevModel* m, const Seq& s, const uint8_t* gc, int j)
 }
 AUGB_HD sc_t ageo_term(const DevModel* m, const Seq& s, const uint8_t* gc, int j) {     /* j >= 1 */
     int c = gc[j]; int g = -1;
-    for (int ch = 1; ch < NCHAIN; ch++) if (m->chain_state[ch] >= 0) { g = m->chain_state[ch]; break; }
+    for (int ch = 1; ch < CH_UTR; ch++) if (m->chain_state[ch] >= 0) { g = m->chain_state[ch]; break; }
     if (g < 0) return 0;
     return m->trans[((size_t)c * m->S + g) * m->S + g] + intron_emi1(m, s, c, j);
 }
@@ -179,7 +186,7 @@ AUGB_HD sc_t parr_term(const DevModel* m, const Seq& s, int c, int which, int p)
 /* sequential host builder (test emulator) */
 inline void prep_window_seq(const DevModel* m, const char* dna, int L, const int32_t* gc_in, char* base, const WinLayout& lay, int* classmask,
                             char* pool = nullptr, size_t pool_size = 0, size_t* pool_used = nullptr) {
-    uint8_t* code = (uint8_t*)(base + lay.code); uint8_t* gc = (uint8_t*)(base + lay.gc); uint16_t* mask = (uint16_t*)(base + lay.mask);
+    uint8_t* code = (uint8_t*)(base + lay.code); uint8_t* gc = (uint8_t*)(base + lay.gc); mask_t* mask = (mask_t*)(base + lay.mask);
     for (int i = 0; i < L; i++) code[i] = base_code(dna[i]);
     if (gc_in) for (int i = 0; i < L; i++) gc[i] = (uint8_t)gc_in[i]; else gc_stairs_seq(m, code, L, gc);
     int cm = 0; bool anynuc = false;
@@ -193,13 +200,31 @@ inline void prep_window_seq(const DevModel* m, const char* dna, int L, const int
         for (int p = 0; p < L; p++) { kf[p] = kmer_code_f(s, p, m->k + 1); kr[p] = kmer_code_r(s, p, m->k + 1); }
         s.kf = kf; s.kr = kr; s.k1 = m->k + 1;
     }
-    for (int j = 0; j < L; j++) mask[j] = anynuc ? (uint16_t)column_mask(m, s, j) : 0;
+    for (int j = 0; j < L; j++) mask[j] = anynuc ? (mask_t)column_mask(m, s, j) : 0;
     if (anynuc) for (int b = 1; b < L; b++) if (gc[b] != gc[b - 1])        /* GC-class boundary at b */
         for (int j = (b - SNIP_BEFORE < 1 ? 1 : b - SNIP_BEFORE); j < L && j < b + SNIP_AFTER; j++) mask[j] |= MB_SLOW;
     {
         sc_t* sg = (sc_t*)(base + lay.sig);
         for (int which = 0; which < NSIG; which++)
             for (int j = 0; j < L; j++) sg[(size_t)which * L + j] = anynuc ? signal_term(m, s, gc[j], which, j) : SC_NEG;
+    }
+    if (lay.utr) {
+        /* UTR models: TSS / TTS scores, SegProbs cumulative sums, intron emission prefix of the UTR-intron chains, mask bits */
+        sc_t* tssF = (sc_t*)(base + lay.tssF); sc_t* tssR = (sc_t*)(base + lay.tssR); sc_t* ttsF = (sc_t*)(base + lay.ttsF); sc_t* ttsR = (sc_t*)(base + lay.ttsR);
+        for (int i = 0; i < L; i++) {
+            int r = i + m->tuw + m->tss_end - 1; int c = gc[r < L ? r : L - 1];
+            tssF[i] = anynuc ? tss_score(m, s, c, 1, i) : SC_NEG; tssR[i] = anynuc ? tss_score(m, s, c, 0, i) : SC_NEG;
+        }
+        for (int b = 0; b <= L; b++) { int c = gc[b < L ? b : L - 1]; ttsF[b] = anynuc ? tts_score(m, s, c, 1, b) : SC_NEG; ttsR[b] = anynuc ? tts_score(m, s, c, 0, b) : SC_NEG; }
+        sc_t* useg = (sc_t*)(base + lay.useg);
+        for (int g = 0; g < NUSEG; g++) {
+            sc_t* cum = useg + (size_t)g * (L + 1); cum[0] = m->log025;
+            for (int i = 1; i <= L; i++) cum[i] = cum[i - 1] + useg_term(m, s, gc[i < L ? i : L - 1], g, i);
+        }
+        sc_t* aint = (sc_t*)(base + lay.aint); aint[0] = 0;
+        for (int j = 1; j < L; j++) aint[j] = aint[j - 1] + intron_emi1(m, s, gc[j], j);
+        const sc_t* sg = (const sc_t*)(base + lay.sig);
+        if (anynuc) for (int j = 0; j < L; j++) mask[j] |= (mask_t)utr_column_mask(m, s, j, sg, tssF, tssR, ttsF, ttsR);
     }
     WinOuts* wo = (WinOuts*)(base + lay.outs);
     int nloc = 0;

@@ -10,6 +10,7 @@
  * is skipped in one go by advancing the stream.
  */
 #pragma once
+#include "ghmm_backtrace.h"
 #include "ghmm_sweep.h"
 
 namespace augb {
@@ -22,13 +23,7 @@ struct SampleOut {
 };
 struct SampleScratch { SampleOpt* opt; int opt_cap; int32_t* sorted; int* nopt; };
 
-AUGB_HD int trunc_flag_s(int type, int end, int predEnd, int L) {
-    bool isIntron = (type >= T_LESSD0 && type <= 23) || (type >= T_RLESSD0 && type <= 58);
-    int t = 0;
-    if (end == L - 1 && ((type >= 2 && type <= 7) || (type >= 38 && type <= 43) || isIntron)) t |= 2;
-    if ((predEnd == -1 || predEnd == 0) && ((type >= 5 && type <= 8) || (type >= 37 && type <= 40) || isIntron)) t |= 1;
-    return t;
-}
+AUGB_HD int trunc_flag_s(int type, int end, int predEnd, int L) { return trunc_flag(type, end, predEnd, L); }
 
 struct Sampler {
     SweepFwd* sw; SampleScratch sc; const uint32_t* rng; int nrng; int cursor; int lane;
@@ -142,6 +137,7 @@ struct Sampler {
                         S.only = state;
                         const int dir = sd.fwd ? 0 : 1;
                         if (sd.kind == K_EXON) S.exon_eval(state, base);
+                        else if (sd.kind == K_UTR) S.utr_eval(state, base);
                         else if (sd.kind == K_LESSD) S.lessd_eval(dir, base);
                         else if (sd.kind == K_EQUALD) S.equald_eval(dir, sd.frame, base);
                         else S.fixed_eval(sd.kind, dir, base);

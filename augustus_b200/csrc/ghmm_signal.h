@@ -89,6 +89,110 @@ AUGB_HD sc_t rstart_endpart(const DevModel* m, const Seq& sq, int cls, int end) 
     else p = (sc_t)(L - (sp + 3)) * m->log025;
     return p;
 }
+
+/* ---- UTR signals (UtrModel) ---- */
+/* UtrModel::tssupSeqProb (utrmodel.cc:1731-1750) */
+AUGB_HD sc_t tssup_sum(const DevModel* m, const Seq& sq, int cls, int left, int right, int reverse) {
+    sc_t s = 0; const int k = m->tssup_k; const sc_t* tab = m->tup + ((size_t)cls << (2 * (k + 1)));
+    AUGB_ROLLED
+    for (int p = right; p >= left; p--) {
+        int pn = -1;
+        if (!reverse && p - k >= 0) pn = sq.kmer_end(p, k + 1);
+        else if (reverse && p >= 0 && p + k < sq.L) pn = sq.kmer_rc(p, k + 1);
+        s += pn < 0 ? m->log025 : tab[pn];
+    }
+    return s;
+}
+/* UtrModel::tssProb (utrmodel.cc:1761-1833) without hints: TATA search (findTATA :271-285), TSS motif, TATA motif, upstream window.
+ * `left` = first base of the whole TSS window; only every tts_spacing-th position can start a transcript (:1785) */
+AUGB_HD sc_t tss_score(const DevModel* m, const Seq& sq, int cls, int fwd, int left) {
+    const int right = left + m->tuw + m->tss_end - 1;
+    if (left < 0 || right >= sq.L || left % m->tts_spacing != 0) return SC_NEG;
+    const int maxpos = m->d_tata_max - m->d_tata_min - 1;
+    sc_t mot, tata = 0, up;
+    if (fwd) {
+        const int p0 = right - m->tss_end - m->d_tata_max + 1; int rel = -1;
+        AUGB_ROLLED
+        for (int pos = 0; pos <= maxpos && rel < 0; pos++)
+            if (sq.at(p0 + pos) == T_ && sq.at(p0 + pos + 1) == A_ && sq.at(p0 + pos + 2) == T_ && sq.at(p0 + pos + 3) == A_ && sq.at(p0 + pos + 5) == A_) rel = pos;
+        const int pm = right - m->tss_end - m->tss_start + 1;
+        if (rel >= 0) {
+            const int tatapos = p0 + rel;
+            mot = motif_fwd(m, sq, cls, m->tsstm, m->tsstm_n, m->tsstm_k, pm);
+            tata = motif_fwd(m, sq, cls, m->tatam, m->tatam_n, m->tatam_k, tatapos - m->tata_start);
+            up = tssup_sum(m, sq, cls, left, tatapos - m->tata_start - 1, 0) + tssup_sum(m, sq, cls, tatapos + m->tata_end, right - m->tss_end - m->tss_start, 0);
+        } else {
+            mot = motif_fwd(m, sq, cls, m->tssm, m->tssm_n, m->tssm_k, pm);
+            up = tssup_sum(m, sq, cls, left, right - m->tss_end - m->tss_start, 0);
+        }
+    } else {
+        const int p0 = left + m->tss_end + m->d_tata_max - 1; int rel = 1;
+        AUGB_ROLLED
+        for (int pos = 0; pos >= -maxpos && rel > 0; pos--)
+            if (sq.at(p0 + pos) == A_ && sq.at(p0 + pos - 1) == T_ && sq.at(p0 + pos - 2) == A_ && sq.at(p0 + pos - 3) == T_ && sq.at(p0 + pos - 5) == T_) rel = pos;
+        if (rel <= 0) {
+            const int tatapos = p0 + rel;
+            mot = motif_rc(m, sq, cls, m->tsstm, m->tsstm_n, m->tsstm_k, left);
+            tata = motif_rc(m, sq, cls, m->tatam, m->tatam_n, m->tatam_k, tatapos - m->tata_end + 1);
+            up = tssup_sum(m, sq, cls, left + m->tata_end + m->tata_start - 1, tatapos - m->tata_end, 1) + tssup_sum(m, sq, cls, tatapos + m->tata_start + 1, right, 1);
+        } else {
+            mot = motif_rc(m, sq, cls, m->tssm, m->tssm_n, m->tssm_k, left);
+            up = tssup_sum(m, sq, cls, left + m->tss_end + m->tss_start, right, 1);
+        }
+    }
+    if (isneg(mot) || isneg(tata) || isneg(up)) return SC_NEG;
+    return mot + tata + up;
+}
+/* UtrModel::computeTtsProbs (utrmodel.cc:1840-1912) without hints; b = first base of the polyA signal box.
+ * Kept: the reverse-strand bounds test zeroes the PLUS entry (:1886-1887), so ttsProbPlus is 0 for b < d_polyasig_cleavage. */
+AUGB_HD sc_t tts_score(const DevModel* m, const Seq& sq, int cls, int fwd, int b) {
+    const int L = sq.L;
+    if (b < 0 || b > L) return SC_NEG;
+    if (fwd) {
+        if (b + m->boxlen + m->dpc - 1 >= L) return SC_NEG;
+        if (b - m->dpc < 0 || b + m->boxlen - 1 >= L) return SC_NEG;
+        int pn = sq.s2i(b, m->boxlen);
+        sc_t prob = (pn < 0 || isneg(m->aataaa[pn])) ? SC_NEG : m->aataaa[pn] + m->log_polya;
+        if (b % m->tts_spacing == 0 && isneg(prob)) prob = m->log_nopolya;
+        if (isneg(prob)) return SC_NEG;
+        return prob + motif_fwd(m, sq, cls, m->ttsm, m->ttsm_n, m->ttsm_k, b + m->boxlen);
+    }
+    const int ttspos = b - m->dpc;
+    if (ttspos < 0 || b + m->boxlen - 1 >= L) return SC_NEG;
+    int pn = sq.s2irc(b, m->boxlen);
+    sc_t prob = (pn < 0 || isneg(m->aataaa[pn])) ? SC_NEG : m->aataaa[pn] + m->log_polya;
+    if (b % m->tts_spacing == 0 && isneg(prob)) prob = m->log_nopolya;
+    if (isneg(prob)) return SC_NEG;
+    return prob + motif_rc(m, sq, cls, m->ttsm, m->ttsm_n, m->ttsm_k, ttspos);
+}
+/* one factor of a SegProbs cumulative product (SegProbs::setEmiProbs, statemodel.cc:413-432), position i in 1..L */
+AUGB_HD sc_t useg_term(const DevModel* m, const Seq& sq, int cls, int g, int i) {
+    const sc_t* tab = (g == US_INIT5 || g == US_RINIT5) ? m->u5i : (g == US_5 || g == US_R5) ? m->u5 : m->u3;
+    int pn;
+    if (g < US_RINIT5) pn = i < m->k ? -1 : sq.kmer_end(i, m->k + 1);
+    else pn = i >= sq.L - m->k ? -1 : sq.kmer_rc(i, m->k + 1);
+    return pn < 0 ? m->log025 : tab[((size_t)cls << (2 * (m->k + 1))) | pn];
+}
+/* UTR part of the activity mask of column j (ends of UTR exon states, begin-signal sites); tss* / tts* arrays already written */
+AUGB_HD unsigned utr_column_mask(const DevModel* m, const Seq& s, int j, const sc_t* sg, const sc_t* tssF, const sc_t* tssR, const sc_t* ttsF, const sc_t* ttsR) {
+    unsigned mb = 0; const int L = s.L;
+    const int dssw = m->dss_start + m->dss_end + 2, assw = m->ass_start + m->ass_end + 2;
+    { int eobe = j + m->tiw; bool ok = true; if (eobe + 3 <= L - 1) { int c = s.kmer_end(eobe + 3, 3); ok = c >= 0 && m->isstart[c]; } if (ok) mb |= MB_U5ATG; }
+    { int b0 = j - m->dpc - m->boxlen + 1; if (j == L - 1 || (b0 >= 0 && b0 + m->boxlen - 1 < L && !isneg(ttsF[b0]))) mb |= MB_UTTS; }
+    { int b0 = j - m->tuw - m->tss_end + 1; if (b0 >= 0 && !isneg(tssR[b0])) mb |= MB_URTSS; }
+    if (!(j + 3 > L - 1 || !isRCStop(m, s, j + 1))) mb |= MB_URSTOP;
+    /* ends that reuse the intron-state bits: one column earlier than longdss / rlongass can end (the window may start at base 0) */
+    if (j == dssw - 1 && possDSS(m, s, j - m->dss_end - 2 + 1)) mb |= MB_LONGDSS;
+    if (j == assw + m->ass_up - 1 && possRASS(s, j - m->ass_up - m->ass_start - 2 + 1)) mb |= MB_RLONGASS;
+    if (j >= 1) {
+        if (!isneg(tssF[j])) mb |= MB_TSSB;
+        { int jj = j + assw + m->ass_up - 1; if (jj < L && !isneg(sg[(size_t)SG_ASSF * L + jj])) mb |= MB_ASSB; }
+        { int jj = j + dssw - 1; if (jj < L && !isneg(sg[(size_t)SG_DSSR * L + jj])) mb |= MB_RDSSB; }
+        if (j + m->dpc <= L && !isneg(ttsR[j + m->dpc])) mb |= MB_RTTSB;
+    }
+    return mb;
+}
+
 /* value of signal array `which` at column j */
 AUGB_HD sc_t signal_term(const DevModel* m, const Seq& sq, int cls, int which, int j) {
     const int dssw = m->dss_start + m->dss_end + 2, assw = m->ass_start + m->ass_end + 2;

@@ -73,7 +73,9 @@ struct SweepT {
     AUGB_D void set_class(int c) { cls = c; trc = m->trans + (size_t)c * m->S * m->S; }
 
     /* ------------------------------------------------------------ chains */
-    AUGB_D const sc_t* chainA(int ch) const { return ch == 0 ? w.AIG : w.AGEO; }
+    /* A[e] of a chain: prefix sum of (emission + self transition); the UTR-intron chains share the intron emission prefix and a
+     * class-independent self transition (checked when the model is built) */
+    AUGB_D sc_t chainAv(int ch, int e) const { return ch == 0 ? w.AIG[e] : ch < CH_UTR ? w.AGEO[e] : w.AINT[e] + (sc_t)e * m->utr_tself; }
     /* V[e][chain]: last change point with col <= e */
     AUGB_D sc_t chain_value(int ch, int e) const {
         int n = ws->cp_n[ch];
@@ -84,7 +86,7 @@ struct SweepT {
         if (cp[hi].col <= e) lo = hi;
         AUGB_ROLLED
         while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (cp[mid].col <= e) lo = mid; else hi = mid - 1; }
-        return cp[lo].tilde + chainA(ch)[e];
+        return cp[lo].tilde + chainAv(ch, e);
     }
     /* V[e][a] for any state a and any finished column e */
     AUGB_D sc_t lookupV(int a, int e) const {
@@ -107,7 +109,7 @@ struct SweepT {
         if (cp[hi].col <= e) lo = hi;
         AUGB_ROLLED
         while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (cp[mid].col <= e) lo = mid; else hi = mid - 1; }
-        return cp[lo].ft + sc2d(chainA(ch)[e]);
+        return cp[lo].ft + sc2d(chainAv(ch, e));
     }
     AUGB_D double lookupF(int a, int e) const {
         int ch = m->st[a].chain;
@@ -142,10 +144,11 @@ struct SweepT {
         const sc_t* T1 = m->trans + (size_t)c1 * m->S * m->S;
         sc_t t_in = T1[s * m->S + cs], t_self = T1[cs * m->S + cs];
         if (isneg(t_in)) return;
-        sc_t val = V + t_in - t_self - chainA(ch)[j];
+        const sc_t Aj = chainAv(ch, j);
+        sc_t val = V + t_in - t_self - Aj;
         if (val > ws->pend_val[ch] || (val == ws->pend_val[ch] && s < ws->pend_pred[ch])) { ws->pend_val[ch] = val; ws->pend_pred[ch] = s; }
         ws->any_pend = 1;
-        if (FWD) ws->pend_f[ch].add(F + sc2d(t_in - t_self - chainA(ch)[j]));
+        if (FWD) ws->pend_f[ch].add(F + sc2d(t_in - t_self - Aj));
     }
     /* record a non-zero cell; route it to the structures later columns look back to.  All lanes hold the same
      * arguments; lane 0 writes, one warp sync publishes. */
@@ -164,6 +167,10 @@ struct SweepT {
                 } else if (sd.kind == K_LONGASS) {
                     if (sd.fwd) cl_append(CL_LA + mod3(sd.frame - (j + 1 - m->ass_end)), j, s, V, F);   /* phase = mod3(pf - bobe) */
                     else cl_append(CL_RA + sd.frame, j, s, V, F);
+                } else if (sd.kind == K_EXON && m->utr) {
+                    /* cells the 3' UTR (forward) / 5' UTR (reverse) states look back to */
+                    if (sd.ek == E_SINGLE || sd.ek == E_TERMINAL) cl_append(CL_X3, j, s, V, F);
+                    else if (sd.ek == E_RSINGLE || sd.ek == E_RINITIAL) cl_append(CL_XR, j, s, V, F);
                 }
                 feed_chain(j, s, V, F);
             }
@@ -444,8 +451,6 @@ struct SweepT {
             }
         }
         /* ---- candidate stream ---- */
-        const int anc0 = st.anc[0];
-        const sc_t t0 = TR(anc0, s);
         int list = 0, ncl = 0, scan_b0 = 0;
         const Cand* cl = nullptr;
         if (listkind) { list = fwd ? CL_LA + mod3(win - eobe - 1) : CL_RD + mod3(win + eobe + 1); cl = w.cl(list); ncl = ws->cl_n[list]; }
@@ -456,6 +461,13 @@ struct SweepT {
         const int lo = listkind ? (startMin < 1 ? 1 : startMin) : startMin;
         sc_t best = SC_NEG; int bkey = -0x7fffffff, bpred = -1, bbase = -1;
         Lse fl; fl.clear();
+        /* initial / single exons: one pass over the in-frame start codons per ancestor (igenic; with UTR states the two 5' UTR
+         * states that end trans_init_window bases before the start codon) */
+        const int npass = scankind ? st.nanc : 1;
+        AUGB_ROLLED
+        for (int ai = 0; ai < npass; ai++) {
+        const int anc0 = st.anc[ai];
+        const sc_t t0 = TR(anc0, s);
         int step = 0; bool more = true;
         AUGB_ROLLED
         while (more) {
@@ -541,6 +553,7 @@ struct SweepT {
                 if (sc > best || (sc == best && key > bkey)) { best = sc; bkey = key; bpred = a; bbase = eop; }
                 if (FWD && !opt) fl.add(pf + sc2d(t + ep + nep));
             }
+        }
         }
         if (listkind && startMin == 0) {
             /* left-truncated exon, bos = 0: the predecessor is read from column 0 = initial probabilities (exonmodel.cc:1067-1068) */
@@ -767,11 +780,150 @@ struct SweepT {
         }
     }
 
+    /* ------------------------------------------------------------ UTR states (UtrModel, utrmodel.cc:796-1064)
+     *
+     * The 16 UTR exon states share one skeleton: end part (a signal of the column) x max over (predecessor end, duration) of
+     * predecessor cell x transition x begin signal x content product x length probability.  The reference walks endOfPred from
+     * rightMost down to leftMost (up to 5500 positions, skipping with its EOPList); here the positions worth visiting are
+     * exactly the entries of a candidate list:
+     *   - predecessor = a self-loop chain (igenic, UTR intron) and a begin signal (TSS, ASS, reverse DSS, reverse polyA):
+     *     one entry per signal site, holding the chain's value just before the site (appended when the sweep passes the site);
+     *   - predecessor = coding exon cells (3' UTR after terminal / single, reverse 5' UTR after rinitial / rsingle): the cells.
+     * Content products are differences of the SegProbs-style cumulative sums written by the prep pass (WinView::useg).
+     * UTR intron states are one-base self-loop states: four more lazily evaluated chains. */
+    AUGB_D void site_append(int list, int ch, int j) {
+        const int cs = m->chain_state[ch];
+        if (cs < 0) return;
+        const sc_t v = chain_value(ch, j - 1);
+        if (isneg(v)) return;
+        const double f = FWD ? chain_fvalue(ch, j - 1) : 0.0;
+        if (lane == 0) cl_append(list, j - 1, cs, v, f);
+        wsync();
+    }
+    AUGB_D void utr_begins(int j, unsigned mb) {
+        if (mb & MB_TSSB) site_append(CL_T5, 0, j);
+        if (mb & MB_RTTSB) site_append(CL_TR, 0, j);
+        if (mb & MB_ASSB) { site_append(CL_A5, CH_UTR + 0, j); site_append(CL_A3, CH_UTR + 1, j); }
+        if (mb & MB_RDSSB) { site_append(CL_R5, CH_UTR + 2, j); site_append(CL_R3, CH_UTR + 3, j); }
+    }
+    AUGB_DN void utr_eval(int s, int j) {
+        const StateDesc& st = m->st[s]; const UtrDesc& u = m->ud[st.ek];
+        const int dssw = m->dss_start + m->dss_end + 2, assw = m->ass_start + m->ass_end + 2;
+        const bool last = j == L - 1;
+        const int eobe = j + u.eobe_off;
+        int boe = j + u.boe_off, rm = j - u.rm_off, lm = j - u.lm_off;
+        const sc_t* ld = m->uld[u.ldi]; int nld = m->n_uld[u.ldi];
+        sc_t ep;
+        switch (u.endkind) {                                      /* UtrModel::endPartEmiProb, utrmodel.cc:1072-1110 */
+        case UE_ATG: { ep = 0; if (eobe + 3 <= L - 1) { int c = sq.kmer_end(eobe + 3, 3); if (c < 0 || !m->isstart[c]) ep = SC_NEG; } break; }
+        case UE_DSSF: ep = boe < 0 ? SC_NEG : (j >= dssw ? sig(SG_DSSF, j) : dSSProb(m, sq, boe, 1)); break;
+        case UE_TTSF:
+            if (last) {                                           /* right-truncated 3' UTR: no signal, tail of the single-exon length distribution */
+                ep = 0; boe = L; rm = u.begsig == BS_NONE ? j - 1 : j - assw - m->ass_up; ld = m->uld[9]; nld = m->n_uld[9];
+            } else ep = (boe < 0 || boe + m->boxlen - 1 >= L) ? SC_NEG : w.ttsF[boe];
+            break;
+        case UE_TSSR: ep = boe < 0 ? SC_NEG : w.tssR[boe]; break;
+        case UE_ASSR: ep = boe < 0 ? SC_NEG : (j - assw - m->ass_up >= 0 ? sig(SG_ASSR, j) : aSSProb(m, sq, cls, boe, 0)); break;
+        default: ep = (j + 3 > L - 1 || !isRCStop(m, sq, j + 1)) ? SC_NEG : 0;
+        }
+        if (isneg(ep)) return;
+        const int eom = boe - 1;                                  /* endOfMiddle */
+        const sc_t* cum = w.useg + (size_t)u.seg * (size_t)(L + 1);
+        const sc_t cumE = eom >= 0 ? cum[eom > L ? L : eom] : 0;
+        const sc_t shortfac = u.shortrule == 1 ? m->log2 : -m->log025;
+        const Cand* cl = w.cl(u.list); const int ncl = ws->cl_n[u.list];
+        sc_t best = SC_NEG; int bkey = -0x7fffffff, bpred = -1, bbase = -1;
+        Lse fl; fl.clear();
+        int step = 0; bool more = true;
+        AUGB_ROLLED
+        while (more) {
+            const int i = ncl - 1 - step * AUGB_NLANES - lane; step++;
+            bool below = i < 0, valid = false; int a = 0, eop = 0; sc_t pv = SC_NEG, te = SC_NEG; double pf = 0;
+            if (!below) {
+                const Cand c = cl[i]; eop = c.col;
+                if (eop < lm) below = true;
+                else if (eop <= rm) {
+                    a = c.state; pv = c.V;
+                    const sc_t t = TR(a, s);
+                    const int b = eop + 1, bom = b + u.bom_off, bobe = b + u.bobe_off, len = eobe - bobe + 1, mlen = eom - bom + 1;
+                    sc_t bp = 0;
+                    switch (u.begsig) {
+                    case BS_TSSF: bp = w.tssF[b]; break;
+                    case BS_ASSF: { int jj = b + assw + m->ass_up - 1; bp = (jj < L && bobe < L) ? sig(SG_ASSF, jj) : SC_NEG; break; }
+                    case BS_DSSR: { int jj = b + dssw - 1; bp = jj < L ? sig(SG_DSSR, jj) : SC_NEG; break; }
+                    case BS_TTSR: bp = w.ttsR[b + m->dpc]; break;
+                    default: break;
+                    }
+                    if (!isneg(t) && !isneg(bp) && len >= 0 && len < nld) {
+                        const sc_t lp = ld[len];
+                        sc_t mid;
+                        if (mlen >= 0 || u.shortrule == 0) mid = bom > eom ? 0 : cumE - (bom < 1 ? 0 : cum[bom - 1]);
+                        else mid = shortfac * (sc_t)(-mlen);
+                        if (!isneg(lp)) { te = t + ((bp + mid + lp) + ep); valid = true; if (FWD) pf = w.clF(u.list)[i]; }
+                    }
+                }
+            }
+            more = wballot(below) == 0;
+            if (FWD && opt) push_opt(valid, pf + sc2d(te), -(eop * 128 + (127 - a)), a, eop);
+            if (valid) {
+                const sc_t sc = pv + te; const int key = eop * 128 + (127 - a);
+                if (sc > best || (sc == best && key > bkey)) { best = sc; bkey = key; bpred = a; bbase = eop; }
+                if (FWD && !opt) fl.add(pf + sc2d(te));
+            }
+        }
+        if (u.trunc && lm < 0) {
+            /* the begin signal lies (partly) before the window: predecessor = column 0 = initial probabilities (utrmodel.cc:932-937,
+             * 1184-1190, 1200-1204, 1301-1310, 1376-1380) */
+            const int lo = u.begsig == BS_TSSF ? -m->tuw : -m->boxlen - m->dpc;
+            if (lm < lo) lm = lo;
+            const int top = rm < -1 ? rm : -1;
+            AUGB_ROLLED
+            for (int e0 = top; e0 >= lm; e0 -= AUGB_NLANES) {
+                const int eop = e0 - lane; bool valid = false; sc_t te = SC_NEG;
+                const int b = eop + 1, bom = b + u.bom_off, bobe = b + u.bobe_off, mlen = eom - bom + 1; int len = eobe - bobe + 1;
+                if (eop >= lm) {
+                    sc_t bp; const sc_t* ldt = ld; int nl = nld;
+                    if (u.begsig == BS_TSSF) {
+                        bp = b == 0 ? w.tssF[0] : m->log025 * (sc_t)(bom - 1);
+                        if (b < 0 && b + m->tuw == 0) { ldt = m->uld[8]; nl = m->n_uld[8]; if (st.uk == U_SINGLE) len = eom - b + 1 + m->tiw - m->tuw; }
+                    } else {
+                        bp = (st.uk == U_TERM || bom > 0) ? m->log025 * (sc_t)(bom - 1) : 0;
+                        if (st.uk == U_SINGLE) { ldt = m->uld[9]; nl = m->n_uld[9]; }
+                    }
+                    if (!isneg(bp) && len >= 0 && len < nl && !isneg(ldt[len])) {
+                        sc_t mid;
+                        if (mlen >= 0 || u.shortrule == 0) mid = bom > eom ? 0 : cumE - (bom < 1 ? 0 : cum[bom - 1]);
+                        else mid = shortfac * (sc_t)(-mlen);
+                        te = (bp + mid + ldt[len]) + ep; valid = true;
+                    }
+                }
+                AUGB_ROLLED
+                for (int ia = 0; ia < st.nanc; ia++) {
+                    const int a = st.anc[ia]; const sc_t pv = m->init[a], t = TR(a, s);
+                    const bool ok = valid && !isneg(pv) && !isneg(t);
+                    if (FWD && opt) push_opt(ok, sc2d(pv) + sc2d(t + te), -(eop * 128 + (127 - a)), a, eop);
+                    if (ok) {
+                        const sc_t sc = pv + (t + te); const int key = eop * 128 + (127 - a);
+                        if (sc > best || (sc == best && key > bkey)) { best = sc; bkey = key; bpred = a; bbase = eop; }
+                        if (FWD && !opt) fl.add(sc2d(pv) + sc2d(t + te));
+                    }
+                }
+            }
+        }
+        if (FWD && opt) return;
+        const int wl = wargbest(best, bkey);
+        if (wl < 0) return;
+        double Fv = 0;
+        if (FWD) Fv = wlse(fl).value();
+        emit(j, s, wbcast64(best, wl), wbcast(bpred, wl), wbcast(bbase, wl), Fv);
+    }
+
     /* ------------------------------------------------------------ one column */
     AUGB_D void process_column(int j, unsigned mb, unsigned eqbits) {
         fill_evstart(j);
         set_class(w.gc[j]);
         if (mb & MB_SLOW) snip_column_begin(j);
+        if (mb & MB_UTR_BEGINS) utr_begins(j, mb);
         /* one call site per routine (the bodies are large): loop over the strands / states this column activates */
         AUGB_ROLLED
         { unsigned lm = ((mb & MB_LESSD) ? 1u : 0u) | ((mb & MB_RLESSD) ? 2u : 0u);
@@ -791,6 +943,19 @@ struct SweepT {
             int q = wffs(slots); slots &= slots - 1;
             int xs = m->xslot[q];
             if (xs >= 0) exon_eval(xs, j);
+        }
+        if (mb & (MB_UTR_ENDS | MB_LONGDSS | MB_RLONGASS)) {
+            /* UTR exon states by end signal: slots 0-15 = utr5single, utr5init, utr5internal, utr5term, utr3single, utr3init,
+             * utr3internal, utr3term, then the same for the reverse strand */
+            unsigned us = ((mb & MB_U5ATG) ? 0x0009u : 0u) | ((mb & MB_LONGDSS) ? 0x0066u : 0u) | ((mb & MB_UTTS) ? 0x0090u : 0u)
+                        | ((mb & MB_URTSS) ? 0x0300u : 0u) | ((mb & MB_RLONGASS) ? 0xcc00u : 0u) | ((mb & MB_URSTOP) ? 0x3000u : 0u);
+            if (!m->utr) us = 0;
+            AUGB_ROLLED
+            while (us) {
+                int q = wffs(us); us &= us - 1;
+                int xs = m->uslot[q];
+                if (xs >= 0) utr_eval(xs, j);
+            }
         }
         apply_pending(j);
     }
@@ -833,6 +998,8 @@ struct SweepT {
                 const StateDesc& sd = m->st[s];
                 if (lane == 0 && sd.kind == K_LONGDSS && sd.fwd) cl_append(CL_LD + sd.frame, 0, s, v, sc2d(v));
                 if (lane == 0 && sd.kind == K_LONGASS && !sd.fwd) cl_append(CL_RA + sd.frame, 0, s, v, sc2d(v));
+                if (lane == 0 && sd.kind == K_EXON && m->utr && (sd.ek == E_SINGLE || sd.ek == E_TERMINAL)) cl_append(CL_X3, 0, s, v, sc2d(v));
+                if (lane == 0 && sd.kind == K_EXON && m->utr && (sd.ek == E_RSINGLE || sd.ek == E_RINITIAL)) cl_append(CL_XR, 0, s, v, sc2d(v));
                 if (lane == 0 && !alln) feed_chain(0, s, v, sc2d(v));
                 wsync();
             }

@@ -238,6 +238,54 @@ static void export_params(NAMGene& ng, const char* fn) {
     export_motif(bw, "tis_motif", ExonModel::GCtransInitMotif, C);
     export_motif(bw, "ass_motif", IntronModel::GCassMotif, C);
 
+    if (Constant::utr_option_on) {
+        // UtrModel tables (utrmodel.cc:540-696), the content tables AFTER the mixing with the intron table (:680-688)
+        std::vector<double> u5i, u5, u3, tup;
+        for (int c = 0; c < C; c++) {
+            { auto t = lgv(UtrModel::GCutr5init_emiprobs[c].probs); u5i.insert(u5i.end(), t.begin(), t.end()); }
+            { auto t = lgv(UtrModel::GCutr5_emiprobs[c].probs); u5.insert(u5.end(), t.begin(), t.end()); }
+            { auto t = lgv(UtrModel::GCutr3_emiprobs[c].probs); u3.insert(u3.end(), t.begin(), t.end()); }
+            { auto t = lgv(UtrModel::GCtssup_emiprobs[c]); tup.insert(tup.end(), t.begin(), t.end()); }
+        }
+        uint64_t KU = 1ull << (2 * (UtrModel::k + 1));
+        bw.scalar_i("utr_k", UtrModel::k); bw.scalar_i("tssup_k", UtrModel::tssup_k);
+        bw.f64("utr5init_emi", {(uint64_t)C, KU}, u5i); bw.f64("utr5_emi", {(uint64_t)C, KU}, u5); bw.f64("utr3_emi", {(uint64_t)C, KU}, u3);
+        bw.f64("tssup_emi", {(uint64_t)C, 1ull << (2 * (UtrModel::tssup_k + 1))}, tup);
+        export_motif(bw, "tss_motif", UtrModel::GCtssMotif, C);
+        export_motif(bw, "tsstata_motif", UtrModel::GCtssMotifTATA, C);
+        export_motif(bw, "tata_motif", UtrModel::GCtataMotif, C);
+        export_motif(bw, "tts_motif", UtrModel::GCttsMotif, C);
+        bw.f64("aataaa_probs", {(uint64_t)UtrModel::aataaa_probs.size()}, lgv(UtrModel::aataaa_probs));
+        bw.f64("lendist_utr5single", {(uint64_t)UtrModel::lenDist5Single.size()}, lgv(UtrModel::lenDist5Single));
+        bw.f64("lendist_utr5initial", {(uint64_t)UtrModel::lenDist5Initial.size()}, lgv(UtrModel::lenDist5Initial));
+        bw.f64("lendist_utr5internal", {(uint64_t)UtrModel::lenDist5Internal.size()}, lgv(UtrModel::lenDist5Internal));
+        bw.f64("lendist_utr5terminal", {(uint64_t)UtrModel::lenDist5Terminal.size()}, lgv(UtrModel::lenDist5Terminal));
+        bw.f64("lendist_utr3single", {(uint64_t)UtrModel::lenDist3Single.size()}, lgv(UtrModel::lenDist3Single));
+        bw.f64("lendist_utr3initial", {(uint64_t)UtrModel::lenDist3Initial.size()}, lgv(UtrModel::lenDist3Initial));
+        bw.f64("lendist_utr3internal", {(uint64_t)UtrModel::lenDist3Internal.size()}, lgv(UtrModel::lenDist3Internal));
+        bw.f64("lendist_utr3terminal", {(uint64_t)UtrModel::lenDist3Terminal.size()}, lgv(UtrModel::lenDist3Terminal));
+        bw.f64("taillendist_utr5single", {(uint64_t)UtrModel::tailLenDist5Single.size()}, lgv(UtrModel::tailLenDist5Single));
+        bw.f64("taillendist_utr3single", {(uint64_t)UtrModel::tailLenDist3Single.size()}, lgv(UtrModel::tailLenDist3Single));
+        bw.scalar_i("utr_max_exon_length", UtrModel::max_exon_length);
+        bw.scalar_i("utr_max3singlelength", UtrModel::max3singlelength);
+        bw.scalar_i("utr_max3termlength", UtrModel::max3termlength);
+        bw.scalar_i("tss_start", UtrModel::tss_start); bw.scalar_i("tss_end", UtrModel::tss_end);
+        bw.scalar_i("tata_start", UtrModel::tata_start); bw.scalar_i("tata_end", UtrModel::tata_end);
+        bw.scalar_i("d_tss_tata_min", UtrModel::d_tss_tata_min); bw.scalar_i("d_tss_tata_max", UtrModel::d_tss_tata_max);
+        bw.scalar_i("tss_upwindow_size", Constant::tss_upwindow_size);
+        bw.scalar_i("d_polyasig_cleavage", Constant::d_polyasig_cleavage);
+        bw.scalar_i("aataaa_boxlen", UtrModel::aataaa_boxlen);
+        bw.scalar_i("tts_spacing", UtrModel::ttsSpacing);
+        {   // utrmodel.cc:1850,1872-1878: aataaa_probs[..] * prob_polya, and (1 - prob_polya) * 4^-boxlen without a box
+            Double randProb = 1.0 / POWER4TOTHE(UtrModel::aataaa_boxlen);
+            Double pp = UtrModel::prob_polya, np = (1 - UtrModel::prob_polya) * randProb;
+            bw.scalar_f("log_prob_polya", lg(pp)); bw.scalar_f("log_no_polya", lg(np));
+        }
+        std::vector<int32_t> isstart(64);
+        for (int c = 0; c < 64; c++) isstart[c] = GeneticCode::start_codons[c];
+        bw.i32("is_start_codon", {64}, isstart);
+    }
+
     // global tables
     bw.f64("lendist_single", {(uint64_t)ExonModel::lenDistSingle.size()}, lgv(ExonModel::lenDistSingle));
     bw.f64("lendist_initial", {(uint64_t)ExonModel::lenDistInitial.size()}, lgv(ExonModel::lenDistInitial));

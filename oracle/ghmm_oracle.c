@@ -50,12 +50,15 @@ enum { T_IGENIC = 0, T_SINGLE = 1, T_INITIAL0 = 2, T_INTERNAL0 = 5, T_TERMINAL =
        T_LESSD0 = 9, T_LONGDSS0 = 10, T_EQUALD0 = 11, T_GEO0 = 12, T_LONGASS0 = 13,
        T_RSINGLE = 36, T_RINITIAL = 37, T_RINTERNAL0 = 38, T_RTERMINAL0 = 41,
        T_RLESSD0 = 44, T_RLONGDSS0 = 45, T_REQUALD0 = 46, T_RGEO0 = 47, T_RLONGASS0 = 48 };
-enum { K_IGENIC, K_EXON, K_LESSD, K_LONGDSS, K_EQUALD, K_GEO, K_LONGASS };
+enum { K_IGENIC, K_EXON, K_LESSD, K_LONGDSS, K_EQUALD, K_GEO, K_LONGASS, K_UTR };
+enum { U_SINGLE, U_INIT, U_INTRON, U_INTRONVAR, U_INTERNAL, U_TERM };     /* order of the utr5.. / utr3.. types, types.hh:498-499 */
+enum { T_UTR5SINGLE = 24, T_UTR3SINGLE = 30, T_UTR3TERM = 35, T_RUTR5SINGLE = 59, T_RUTR3SINGLE = 65 };
 enum { E_SINGLE, E_INITIAL, E_INTERNAL, E_TERMINAL, E_RSINGLE, E_RINITIAL, E_RINTERNAL, E_RTERMINAL };
 
 typedef struct {
     int type, kind, fwd, frame;     /* frame = stateReadingFrames[type] (types.cc:174-188) */
     int ek;                         /* exon kind */
+    int uk, u5;                     /* UTR kind (U_*), 1 = 5' UTR */
     int beginPartLen, innerPartOffset, baseOffset, innerPartEndOffset;
     int nanc, anc[16];
 } StateInfo;
@@ -78,6 +81,13 @@ typedef struct {
     sc_t startp[64]; int isstop[64];
     sc_t ochre, amber, opal, probN, log025, log3;
     double centroids[64][4]; int ncent; double wm[4][4];
+    /* UtrModel (utrmodel.cc), only with --UTR=on */
+    int utr, utr_k, tssup_k, tss_start, tss_end, tata_start, tata_end, d_tata_min, d_tata_max, tuw, dpc, boxlen, tts_spacing;
+    int umax, umax3s, umax3t;
+    sc_t *u5i, *u5, *u3, *tup;                   /* [c][4^(k+1)] */
+    sc_t *tssm, *tsstm, *tatam, *ttsm; int tssm_n, tssm_k, tsstm_n, tsstm_k, tatam_n, tatam_k, ttsm_n, ttsm_k;
+    sc_t *aataaa, log_polya, log_nopolya, log2, isstart[64];
+    sc_t *uld[2][6], *utl5s, *utl3s; int n_uld[2][6], n_utl5s, n_utl3s;   /* [5'/3' = 1/0][U_*] length distributions */
 } Model;
 
 /* ------------------------------------------------------------------ blob reading */
@@ -106,7 +116,7 @@ static sc_t* qarr(const Blob* b, const char* name, size_t* n) {
 
 static void classify(StateInfo* s, const Model* m) {
     int t = s->type;
-    s->fwd = (t < 36); s->frame = 0;
+    s->fwd = (t < 36); s->frame = 0; s->uk = -1;
     if (t == T_IGENIC) { s->kind = K_IGENIC; s->fwd = 1; return; }
     int e = -1;
     if (t == T_SINGLE) { e = E_SINGLE; }
@@ -128,6 +138,11 @@ static void classify(StateInfo* s, const Model* m) {
         if (e == E_SINGLE || e == E_TERMINAL) { s->baseOffset = 0; s->innerPartEndOffset = 3; }
         else if (e == E_RSINGLE || e == E_RINITIAL) { s->baseOffset = -m->tiw; s->innerPartEndOffset = 3; }
         else { s->baseOffset = s->innerPartEndOffset = s->fwd ? m->dss_start : m->ass_end; }
+        return;
+    }
+    if ((t >= T_UTR5SINGLE && t <= T_UTR3TERM) || (t >= T_RUTR5SINGLE && t <= T_RUTR5SINGLE + 11)) {
+        int o = t - (s->fwd ? T_UTR5SINGLE : T_RUTR5SINGLE);
+        s->kind = K_UTR; s->u5 = o < 6; s->uk = o % 6;
         return;
     }
     int base = s->fwd ? T_LESSD0 : T_RLESSD0;
@@ -188,6 +203,32 @@ Model* orc_model_load(const char* path) {
     for (int i = 0; i < m->ncent; i++) for (int j = 0; j < 4; j++) m->centroids[i][j] = cen[4 * i + j];
     const double* w = bdarr(&b, "basecount_weight_matrix", NULL);
     for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) m->wm[i][j] = w[4 * i + j];
+    m->utr = bint(&b, "utr_option_on");
+    if (bint(&b, "nc_option_on")) { fprintf(stderr, "oracle: nc states not restated\n"); return NULL; }
+    if (m->utr) {
+        m->utr_k = bint(&b, "utr_k"); m->tssup_k = bint(&b, "tssup_k");
+        if (m->utr_k != m->k) { fprintf(stderr, "oracle: mixed k unsupported\n"); return NULL; }
+        m->tss_start = bint(&b, "tss_start"); m->tss_end = bint(&b, "tss_end");
+        m->tata_start = bint(&b, "tata_start"); m->tata_end = bint(&b, "tata_end");
+        m->d_tata_min = bint(&b, "d_tss_tata_min"); m->d_tata_max = bint(&b, "d_tss_tata_max");
+        m->tuw = bint(&b, "tss_upwindow_size"); m->dpc = bint(&b, "d_polyasig_cleavage");
+        m->boxlen = bint(&b, "aataaa_boxlen"); m->tts_spacing = bint(&b, "tts_spacing");
+        m->umax = bint(&b, "utr_max_exon_length"); m->umax3s = bint(&b, "utr_max3singlelength"); m->umax3t = bint(&b, "utr_max3termlength");
+        m->u5i = qarr(&b, "utr5init_emi", NULL); m->u5 = qarr(&b, "utr5_emi", NULL); m->u3 = qarr(&b, "utr3_emi", NULL);
+        m->tup = qarr(&b, "tssup_emi", NULL);
+        m->tssm = qarr(&b, "tss_motif", NULL); m->tssm_n = bint(&b, "tss_motif_n"); m->tssm_k = bint(&b, "tss_motif_k");
+        m->tsstm = qarr(&b, "tsstata_motif", NULL); m->tsstm_n = bint(&b, "tsstata_motif_n"); m->tsstm_k = bint(&b, "tsstata_motif_k");
+        m->tatam = qarr(&b, "tata_motif", NULL); m->tatam_n = bint(&b, "tata_motif_n"); m->tatam_k = bint(&b, "tata_motif_k");
+        m->ttsm = qarr(&b, "tts_motif", NULL); m->ttsm_n = bint(&b, "tts_motif_n"); m->ttsm_k = bint(&b, "tts_motif_k");
+        m->aataaa = qarr(&b, "aataaa_probs", NULL);
+        m->log_polya = q(bdbl(&b, "log_prob_polya")); m->log_nopolya = q(bdbl(&b, "log_no_polya")); m->log2 = q(log(2.0));
+        const int32_t* iss = biarr(&b, "is_start_codon", NULL); for (int i = 0; i < 64; i++) m->isstart[i] = iss[i];
+        static const char* nm[2][6] = { { "lendist_utr3single", "lendist_utr3initial", NULL, NULL, "lendist_utr3internal", "lendist_utr3terminal" },
+                                        { "lendist_utr5single", "lendist_utr5initial", NULL, NULL, "lendist_utr5internal", "lendist_utr5terminal" } };
+        for (int f = 0; f < 2; f++) for (int u = 0; u < 6; u++) if (nm[f][u]) { m->uld[f][u] = qarr(&b, nm[f][u], &n); m->n_uld[f][u] = (int)n; }
+        m->utl5s = qarr(&b, "taillendist_utr5single", &n); m->n_utl5s = (int)n;
+        m->utl3s = qarr(&b, "taillendist_utr3single", &n); m->n_utl3s = (int)n;
+    }
     const int32_t* stt = biarr(&b, "state_type", NULL);
     const int32_t* reach = biarr(&b, "state_reachable", NULL);
     m->st = (StateInfo*)calloc(m->S, sizeof(StateInfo));
@@ -218,6 +259,15 @@ typedef struct {
     double* F;                                  /* [L][S] ln forward, -inf = absent */
     double lse_m, lse_s;                        /* running log-sum-exp of the forward sum of the current cell */
     struct Opt { int state, base; double lp; } *opts; int nopt, capopt;     /* OptionsList of the current sampling step */
+    /* UtrModel per-sequence state */
+    const char* raw;                            /* lower-case sequence (findTATA compares characters) */
+    int cur_gc;                                 /* NAMGene::curGCIdx */
+    int walking;                                /* 1 while backtracking / sampling (algovar doBacktracking / doSampling) */
+    sc_t* seg[7];                               /* SegProbs::cumProds, [L+1], NEG = 0 = not computed */
+    sc_t *tssP[2], *ttsP[2];                    /* tssProbsPlus/Minus memo (UNSET = -1), ttsProbPlus/Minus; index 0 = plus */
+    struct Eop { int *v, n, cap, it, inCache; } *eop;   /* EOPList per state */
+    int eop_off;                                /* debugging: 1 = scan every endOfPred (no EOPList) */
+    sc_t* assMemo[2]; int* assMemoGen[2]; int assGen, assN;     /* IntronModel::aSSProb memoF / memoR */
 } Ctx;
 
 static inline int at(const Ctx* x, int p) { return (p < 0 || p >= x->L) ? 5 : x->c[p]; }
@@ -522,8 +572,9 @@ static sc_t dSSProb(const Ctx* x, int base, int fwd) {
     return nonGT ? m->dss_pat_non[idx] : m->dss_pat[idx];
 }
 /* IntronModel::aSSProb, intronmodel.cc:1116-1188 */
-static sc_t aSSProb(const Ctx* x, int base, int fwd) {
+static sc_t aSSProb_raw(const Ctx* x, int base, int fwd, int* stored) {
     const Model* m = x->m; int nonAG, a, b; sc_t motif;
+    *stored = 0;
     if (fwd) {
         int asspos = base + m->ass_up + m->ass_start;
         if (!possASS(x, asspos + 1)) return NEG;
@@ -543,8 +594,21 @@ static sc_t aSSProb(const Ctx* x, int base, int fwd) {
     sc_t pat;
     if (a < 0 || b < 0) pat = q(log(0.001) + (m->ass_start + m->ass_end) * log(0.25));
     else { int idx = (a << (2 * m->ass_end)) | b; pat = nonAG ? m->ass_pat_non[idx] : m->ass_pat[idx]; }
+    *stored = 1;
     if (isneg(motif) || isneg(pat)) return NEG;
     return motif + pat;
+}
+/* the memo of IntronModel::aSSProb (intronmodel.cc:1119-1136,1181-1185): values are kept per first base and strand until more
+ * than 1000 forward entries have accumulated (or a reset call with base < 0); a kept value carries the GC class (motif) that
+ * was active when it was computed.  Only visible with UTR states, which ask for splice sites far behind the current column. */
+static sc_t aSSProb(Ctx* x, int base, int fwd) {
+    if (base < 0 || x->assN > 1000) { x->assGen++; x->assN = 0; if (base < 0) return NEG; }
+    int slot = base <= x->L ? base : x->L;
+    sc_t* val = x->assMemo[fwd ? 0 : 1]; int* gen = x->assMemoGen[fwd ? 0 : 1];
+    if (gen[slot] == x->assGen && base <= x->L) return val[slot];
+    int stored; sc_t v = aSSProb_raw(x, base, fwd, &stored);
+    if (stored && base <= x->L) { val[slot] = v; gen[slot] = x->assGen; if (fwd) x->assN++; }
+    return v;
 }
 
 /* ------------------------------------------------------------------ introns, intronmodel.cc:509-858 */
@@ -825,20 +889,396 @@ static void exon_eval(Ctx* x, int s, int j, Oli* o) {
     }
 }
 
+
+/* ================================================================== UTR states, utrmodel.cc */
+#define UNSET ((sc_t)1 << 62)
+enum { SG_RINIT5, SG_INIT5, SG_3, SG_R3, SG_INTRON, SG_5, SG_R5 };        /* UtrModel::initSnippetProbs, utrmodel.cc:701-712 */
+static const int seg_fwd[7] = { 0, 1, 1, 0, 1, 1, 0 };
+static const sc_t* seg_table(const Ctx* x, int g) {                        /* the static table the SegProbs points at: current class */
+    const Model* m = x->m; size_t w = (size_t)1 << (2 * (m->k + 1));
+    switch (g) {
+    case SG_RINIT5: case SG_INIT5: return m->u5i + x->cls * w;
+    case SG_3: case SG_R3: return m->u3 + x->cls * w;
+    case SG_INTRON: return m->iemi + x->cls * w;
+    default: return m->u5 + x->cls * w;
+    }
+}
+static sc_t seg_emi1(const Ctx* x, int g, int i) {                         /* one factor of SegProbs::setEmiProbs, statemodel.cc:413-432 */
+    const Model* m = x->m; int pn;
+    if (seg_fwd[g]) pn = i < m->k ? -1 : s2i(x, i - m->k, m->k + 1);
+    else pn = i >= x->L - m->k ? -1 : s2irc(x, i, m->k + 1);
+    return pn < 0 ? m->log025 : seg_table(x, g)[pn];
+}
+/* SegProbs::setEmiProbs, statemodel.cc:398-436 */
+static void seg_set(Ctx* x, int g, int from, int to) {
+    int n = x->L; sc_t* cum = x->seg[g];
+    if (from < 0 || to < 0) { from = 1; to = n; }
+    if (from == 1) cum[0] = x->m->log025;
+    if (to > n) to = n;
+    if (cum[from - 1] == NEG) cum[from - 1] = 0;                          /* "previous emiprobs not computed": set to 1 */
+    for (int i = from; i <= to; i++) cum[i] = cum[i - 1] + seg_emi1(x, g, i);
+}
+/* SegProbs::getSeqProb, statemodel.cc:441-465 */
+static sc_t seg_get(const Ctx* x, int g, int from, int to) {
+    const Model* m = x->m;
+    if (from == to) {
+        int pn;
+        if (seg_fwd[g]) { if (to < m->k) return m->log025; pn = s2i(x, to - m->k, m->k + 1); }
+        else pn = s2irc(x, to, m->k + 1);
+        return pn < 0 ? m->log025 : seg_table(x, g)[pn];
+    }
+    if (from > to) return 0;
+    if (to > x->L) to = x->L;
+    sc_t r = x->seg[g][to];
+    return from < 1 ? r : r - x->seg[g][from - 1];
+}
+/* UtrModel::tssupSeqProb, utrmodel.cc:1731-1750 */
+static sc_t tssup(const Ctx* x, int left, int right, int reverse) {
+    const Model* m = x->m; sc_t s = 0; int k = m->tssup_k; const sc_t* tab = m->tup + ((size_t)x->cls << (2 * (k + 1)));
+    for (int p = right; p >= left; p--) {
+        int pn = -1;
+        if (!reverse && p - k >= 0) pn = s2i(x, p - k, k + 1);
+        else if (reverse && p >= 0 && p + k < x->L) pn = s2irc(x, p, k + 1);
+        s += pn < 0 ? m->log025 : tab[pn];
+    }
+    return s;
+}
+static inline int rawc(const Ctx* x, int p) { return (p < 0 || p >= x->L) ? 0 : x->raw[p]; }
+/* UtrModel::tssProb, utrmodel.cc:1761-1833 (no hints: extrinsicProb = 1); memo keeps the class active at first evaluation */
+static sc_t tssProb(Ctx* x, int fwd, int left) {
+    const Model* m = x->m;
+    int right = left + m->tuw + m->tss_end - 1;
+    if (right >= x->L) return NEG;
+    if (left % m->tts_spacing != 0) return NEG;
+    sc_t* memo = x->tssP[fwd ? 0 : 1];
+    if (memo[left] != UNSET) return memo[left];
+    sc_t tssMotifProb, tataMotifProb = 0, up; int maxpos = m->d_tata_max - m->d_tata_min - 1;
+    if (fwd) {
+        int p0 = right - m->tss_end - m->d_tata_max + 1, rel = -1;        /* findTATA, utrmodel.cc:271-285 */
+        for (int pos = 0; pos <= maxpos && rel < 0; pos++)
+            if (rawc(x, p0 + pos) == 't' && rawc(x, p0 + pos + 1) == 'a' && rawc(x, p0 + pos + 2) == 't' && rawc(x, p0 + pos + 3) == 'a' && rawc(x, p0 + pos + 5) == 'a') rel = pos;
+        int pm = right - m->tss_end - m->tss_start + 1;
+        if (rel >= 0) {
+            int tatapos = p0 + rel;
+            tssMotifProb = motif_fwd(x, m->tsstm, m->tsstm_n, m->tsstm_k, pm);
+            tataMotifProb = motif_fwd(x, m->tatam, m->tatam_n, m->tatam_k, tatapos - m->tata_start);
+            up = tssup(x, left, tatapos - m->tata_start - 1, 0) + tssup(x, tatapos + m->tata_end, right - m->tss_end - m->tss_start, 0);
+        } else {
+            tssMotifProb = motif_fwd(x, m->tssm, m->tssm_n, m->tssm_k, pm);
+            up = tssup(x, left, right - m->tss_end - m->tss_start, 0);
+        }
+    } else {
+        int p0 = left + m->tss_end + m->d_tata_max - 1, rel = 1;
+        for (int pos = 0; pos >= -maxpos && rel > 0; pos--)
+            if (rawc(x, p0 + pos) == 'a' && rawc(x, p0 + pos - 1) == 't' && rawc(x, p0 + pos - 2) == 'a' && rawc(x, p0 + pos - 3) == 't' && rawc(x, p0 + pos - 5) == 't') rel = pos;
+        if (rel <= 0) {
+            int tatapos = p0 + rel;
+            tssMotifProb = motif_rc(x, m->tsstm, m->tsstm_n, m->tsstm_k, left);
+            tataMotifProb = motif_rc(x, m->tatam, m->tatam_n, m->tatam_k, tatapos - m->tata_end + 1);
+            up = tssup(x, left + m->tata_end + m->tata_start - 1, tatapos - m->tata_end, 1) + tssup(x, tatapos + m->tata_start + 1, right, 1);
+        } else {
+            tssMotifProb = motif_rc(x, m->tssm, m->tssm_n, m->tssm_k, left);
+            up = tssup(x, left + m->tss_end + m->tss_start, right, 1);
+        }
+    }
+    sc_t prob = (isneg(tssMotifProb) || isneg(tataMotifProb) || isneg(up)) ? NEG : tssMotifProb + tataMotifProb + up;
+    memo[left] = prob;
+    return prob;
+}
+/* UtrModel::computeTtsProbs, utrmodel.cc:1840-1912 (no hints) */
+static void compute_tts(Ctx* x, int from, int to) {
+    const Model* m = x->m; int L = x->L;
+    if (from < 0 || to < 0) { from = 0; to = L; }
+    if (to > L) to = L;
+    for (int b = from; b <= to; b++) {
+        int ttspos = b + m->boxlen + m->dpc - 1;
+        if (ttspos >= L) x->ttsP[0][b] = NEG;
+        else {
+            int pn = s2i(x, b, m->boxlen);
+            sc_t prob = (pn < 0 || isneg(m->aataaa[pn])) ? NEG : m->aataaa[pn] + m->log_polya;
+            if (b % m->tts_spacing == 0 && isneg(prob)) prob = m->log_nopolya;
+            if (!isneg(prob)) prob += motif_fwd(x, m->ttsm, m->ttsm_n, m->ttsm_k, b + m->boxlen);
+            x->ttsP[0][b] = prob;
+        }
+        ttspos = b - m->dpc;
+        if (ttspos < 0 || b + m->boxlen - 1 >= L) x->ttsP[0][b] = NEG;     /* sic: the reference zeroes the PLUS entry here (:1887) */
+        else {
+            int pn = s2irc(x, b, m->boxlen);
+            sc_t prob = (pn < 0 || isneg(m->aataaa[pn])) ? NEG : m->aataaa[pn] + m->log_polya;
+            if (b % m->tts_spacing == 0 && isneg(prob)) prob = m->log_nopolya;
+            if (!isneg(prob)) prob += motif_rc(x, m->ttsm, m->ttsm_n, m->ttsm_k, ttspos);
+            x->ttsP[1][b] = prob;
+        }
+    }
+}
+/* UtrModel::updateToLocalGC, utrmodel.cc:768-791; x->cls is already the new class */
+static void utr_update_gc(Ctx* x, int from, int to) {
+    if (!x->m->utr) return;
+    for (int i = from; i < to && i >= 0; i++) x->tssP[0][i] = x->tssP[1][i] = UNSET;
+    compute_tts(x, from, to);
+    for (int g = 0; g < 7; g++) seg_set(x, g, from, to + 5);
+}
+
+/* EOPList, statemodel.cc:473-520.  it == n plays the role of end(); dereferencing end() of a libstdc++ std::list<int>
+ * reads the low word of the size field kept in the sentinel node, which is what the reference build here does in
+ * update()'s first comparison when the iterator sits at end(). */
+static void eop_insert(struct Eop* e, int at, int v) {
+    if (e->n == e->cap) { e->cap = e->cap ? 2 * e->cap : 64; e->v = (int*)realloc(e->v, e->cap * sizeof(int)); }
+    memmove(e->v + at + 1, e->v + at, (e->n - at) * sizeof(int)); e->v[at] = v; e->n++;
+}
+static void eop_decrement(struct Eop* e, int* endOfPred) {
+    if (e->inCache && e->it != e->n && e->v[e->it] == *endOfPred && ++e->it != e->n) *endOfPred = e->v[e->it];
+    else (*endOfPred)--;
+}
+static void eop_update(struct Eop* e, int endOfPred) {
+    if (e->n == 0) { eop_insert(e, 0, endOfPred); e->it = e->n; return; }          /* eopit stays end() */
+    if (endOfPred == (e->it == e->n ? e->n : e->v[e->it])) return;                 /* case A */
+    if (endOfPred >= e->v[0]) { if (endOfPred > e->v[0]) eop_insert(e, 0, endOfPred); e->it = 0; return; }   /* case B */
+    if (endOfPred < e->v[e->n - 1]) { eop_insert(e, e->n, endOfPred); e->it = e->n - 1; return; }              /* case C */
+    if (e->it != e->n && endOfPred < e->v[e->it]) {                                 /* case D */
+        int nxt = e->it + 1;
+        if (nxt != e->n && endOfPred == e->v[nxt]) { e->it = nxt; e->inCache = 1; return; }
+        if (nxt == e->n || endOfPred > e->v[nxt]) { eop_insert(e, nxt, endOfPred); e->it = nxt; return; }
+        while (e->it != e->n && e->v[e->it] > endOfPred) e->it++;
+        eop_update(e, endOfPred);
+        return;
+    }
+    fprintf(stderr, "oracle: EOPList state the reference would throw on (Error 2 in UtrModel::updatePossibleEOPs)\n"); exit(4);
+}
+
+/* UtrModel::getEndPositions, utrmodel.cc:1572-1643 */
+static void utr_end_positions(const Ctx* x, const StateInfo* st, int end, int* boe, int* eobe) {
+    const Model* m = x->m; int DW = m->dss_start + m->dss_end + 2, AW = m->ass_start + m->ass_end + 2;
+    *boe = end + 1; *eobe = end;
+    if (st->uk == U_INTRON || st->uk == U_INTRONVAR) return;
+    if (st->u5) {
+        if (st->fwd) {
+            if (st->uk == U_SINGLE || st->uk == U_TERM) { *eobe = end + m->tiw; }
+            else { *boe = end - DW + 1; *eobe = end - m->dss_end - 2; }                     /* init, internal */
+        } else {
+            if (st->uk == U_SINGLE || st->uk == U_INIT) { *boe = end - m->tuw - m->tss_end + 1; *eobe = end - m->tuw; }
+            else { *boe = end - AW - m->ass_up + 1; *eobe = end - m->ass_up - m->ass_start - 2; }   /* internal, term */
+        }
+    } else {
+        if (st->fwd) {
+            if (st->uk == U_SINGLE || st->uk == U_TERM) {
+                if (end != x->L - 1) { *boe = end - m->dpc - m->boxlen + 1; *eobe = end; }
+                else { *boe = x->L; *eobe = x->L - 1; }
+            } else { *boe = end - DW + 1; *eobe = end - m->dss_end - 2; }
+        } else {
+            if (st->uk == U_INTERNAL || st->uk == U_TERM) { *boe = end - AW - m->ass_up + 1; *eobe = end - m->ass_up - m->ass_start - 2; }
+            /* rutr3single, rutr3init: no end signal */
+        }
+    }
+}
+/* UtrModel::endPartEmiProb, utrmodel.cc:1072-1161 (no hints) */
+static sc_t utr_endPart(Ctx* x, const StateInfo* st, int begin, int end, int eobe) {
+    const Model* m = x->m; int L = x->L, DW = m->dss_start + m->dss_end + 2, AW = m->ass_start + m->ass_end + 2;
+    if (st->uk == U_INTRON) return 0;
+    if (st->uk == U_INTRONVAR) return NEG;            /* only reachable through intron hints (:990-1040) */
+    if (st->fwd) {
+        if (st->u5 && (st->uk == U_SINGLE || st->uk == U_TERM)) {
+            if (eobe + 3 <= L - 1) { int c = s2i(x, eobe + 1, 3); if (c < 0 || !m->isstart[c]) return NEG; }
+            return 0;
+        }
+        if (st->uk == U_INIT || st->uk == U_INTERNAL) return dSSProb(x, end - DW + 1, 1);
+        /* utr3single, utr3term */
+        if (end == L - 1) return 0;
+        if (begin < 0 || begin + m->boxlen - 1 >= L) return NEG;
+        return x->ttsP[0][begin];
+    }
+    if (st->u5) {
+        if (st->uk == U_SINGLE || st->uk == U_INIT) return tssProb(x, 0, begin);
+        return aSSProb(x, end - m->ass_up - AW + 1, 0);
+    }
+    if (st->uk == U_SINGLE || st->uk == U_INIT) return (end + 3 > L - 1 || !isRCStop(x, end + 1)) ? NEG : 0;
+    return aSSProb(x, end - m->ass_up - AW + 1, 0);
+}
+static sc_t uld_get(const Model* m, int u5, int uk, int len) {
+    if (len < 0 || len >= m->n_uld[u5][uk]) { fprintf(stderr, "oracle: UTR length %d outside the distribution (%d,%d)\n", len, u5, uk); exit(4); }
+    return m->uld[u5][uk][len];
+}
+static sc_t tail_get(const sc_t* t, int n, int len) {
+    if (len < 0 || len >= n) { fprintf(stderr, "oracle: UTR tail length %d outside the distribution\n", len); exit(4); }
+    return t[len];
+}
+/* UtrModel::notEndPartEmiProb, utrmodel.cc:1167-1548 (no hints: extrinsicQuot = 1) */
+static sc_t utr_notEndPart(Ctx* x, const StateInfo* st, int begin, int endOfMiddle, int eobe) {
+    const Model* m = x->m; int L = x->L, DW = m->dss_start + m->dss_end + 2, AW = m->ass_start + m->ass_end + 2;
+    sc_t beginPart = 0, middle = 0, lenp = 0; int bom, bobe;
+    if (st->uk == U_INTRON) {                          /* :1254-1265, :1387-1399 — one base, intron content of the current class */
+        for (int pos = begin; pos <= endOfMiddle; pos++) {
+            int pn = pos - m->k >= 0 ? s2i(x, pos - m->k, m->k + 1) : -1;
+            sc_t e = pn < 0 ? m->log025 : m->iemi[((size_t)x->cls << (2 * (m->k + 1))) | pn];
+            if (st->u5) middle += e; else middle = e;
+        }
+        return middle;
+    }
+    if (st->uk == U_INTRONVAR) return NEG;
+    if (st->fwd && st->u5) {
+        switch (st->uk) {
+        case U_SINGLE: case U_INIT:
+            bom = begin + m->tuw + m->tss_end; bobe = begin + m->tuw;
+            if (st->uk == U_INIT || endOfMiddle - bom + 1 >= 0) middle = seg_get(x, SG_INIT5, bom, endOfMiddle);
+            else middle = m->log2 * (-(endOfMiddle - bom + 1));
+            lenp = uld_get(m, 1, st->uk, eobe - bobe + 1);
+            if (begin >= 0) beginPart = tssProb(x, 1, begin);
+            else {
+                beginPart = m->log025 * (bom - 1);
+                if (begin + m->tuw == 0)
+                    lenp = st->uk == U_SINGLE ? tail_get(m->utl5s, m->n_utl5s, endOfMiddle - begin + 1 + m->tiw - m->tuw)
+                                              : tail_get(m->utl5s, m->n_utl5s, eobe - bobe + 1);
+            }
+            break;
+        case U_INTERNAL:
+            beginPart = aSSProb(x, begin, 1); bobe = begin + m->ass_up + m->ass_start + 2;
+            if (!isneg(beginPart)) { bom = begin + m->ass_up + AW; middle = seg_get(x, SG_5, bom, endOfMiddle); lenp = uld_get(m, 1, U_INTERNAL, eobe - bobe + 1); }
+            break;
+        default: /* U_TERM */
+            bobe = begin + m->ass_up + m->ass_start + 2;
+            beginPart = bobe >= L ? NEG : aSSProb(x, begin, 1);
+            if (!isneg(beginPart)) {
+                bom = begin + m->ass_up + AW;
+                if (endOfMiddle - bom + 1 >= 0) middle = seg_get(x, SG_5, bom, endOfMiddle);
+                else middle = (-m->log025) * (-(endOfMiddle - bom + 1));
+                lenp = uld_get(m, 1, U_TERM, eobe - bobe + 1);
+            }
+        }
+    } else if (!st->fwd && st->u5) {
+        switch (st->uk) {
+        case U_INTERNAL: case U_INIT:
+            beginPart = dSSProb(x, begin, 0); bobe = begin + m->dss_end + 2;
+            if (!isneg(beginPart)) { bom = begin + DW; middle = seg_get(x, st->uk == U_INIT ? SG_RINIT5 : SG_R5, bom, endOfMiddle); lenp = uld_get(m, 1, st->uk, eobe - bobe + 1); }
+            break;
+        default: /* rutr5term, rutr5single */
+            bom = begin; bobe = begin - m->tiw;
+            if (endOfMiddle - bom + 1 >= 0) middle = seg_get(x, st->uk == U_TERM ? SG_R5 : SG_RINIT5, bom, endOfMiddle);
+            else middle = (st->uk == U_TERM ? -m->log025 : m->log2) * (-(endOfMiddle - bom + 1));
+            lenp = uld_get(m, 1, st->uk, eobe - bobe + 1);
+        }
+    } else if (st->fwd) {   /* 3' forward */
+        switch (st->uk) {
+        case U_SINGLE:
+            bom = bobe = begin; middle = seg_get(x, SG_3, bom, endOfMiddle);
+            lenp = eobe != L - 1 ? uld_get(m, 0, U_SINGLE, eobe - bobe + 1) : tail_get(m->utl3s, m->n_utl3s, eobe - bobe + 1);
+            break;
+        case U_INIT:
+            bom = bobe = begin;
+            if (endOfMiddle - bom + 1 >= 0) middle = seg_get(x, SG_3, bom, endOfMiddle);
+            else middle = (-m->log025) * (-(endOfMiddle - bom + 1));
+            lenp = uld_get(m, 0, U_INIT, eobe - bobe + 1);
+            break;
+        default: /* internal, term */
+            beginPart = aSSProb(x, begin, 1); bobe = begin + m->ass_up + m->ass_start + 2;
+            if (!isneg(beginPart)) {
+                bom = begin + m->ass_up + AW; middle = seg_get(x, SG_3, bom, endOfMiddle);
+                if (st->uk == U_INTERNAL || eobe != L - 1) lenp = uld_get(m, 0, st->uk, eobe - bobe + 1);
+                else lenp = tail_get(m->utl3s, m->n_utl3s, eobe - bobe + 1);
+            }
+        }
+    } else {                /* 3' reverse */
+        switch (st->uk) {
+        case U_SINGLE: case U_TERM:
+            bobe = begin; bom = begin + m->boxlen + m->dpc;
+            if (begin > 0) { beginPart = x->ttsP[1][begin + m->dpc]; if (st->uk == U_SINGLE) lenp = uld_get(m, 0, U_SINGLE, eobe - bobe + 1); }
+            else {
+                beginPart = (st->uk == U_TERM || bom > 0) ? m->log025 * (bom - 1) : 0;
+                if (st->uk == U_SINGLE) lenp = tail_get(m->utl3s, m->n_utl3s, eobe - bobe + 1);
+            }
+            if (!isneg(beginPart)) { middle = seg_get(x, SG_R3, bom, endOfMiddle); if (st->uk == U_TERM) lenp = uld_get(m, 0, U_TERM, eobe - bobe + 1); }
+            break;
+        default: /* rutr3init, rutr3internal */
+            beginPart = dSSProb(x, begin, 0); bobe = begin + m->dss_end + 2;
+            if (!isneg(beginPart)) {
+                bom = begin + DW;
+                if (st->uk == U_INTERNAL || endOfMiddle - bom + 1 >= 0) middle = seg_get(x, SG_R3, bom, endOfMiddle);
+                else middle = (-m->log025) * (-(endOfMiddle - bom + 1));
+                lenp = uld_get(m, 0, st->uk, eobe - bobe + 1);
+            }
+        }
+    }
+    if (isneg(beginPart) || isneg(middle) || isneg(lenp)) return NEG;
+    return beginPart + middle + lenp;
+}
+/* UtrModel::viterbiForwardAndSampling, utrmodel.cc:796-1064 */
+static void utr_eval(Ctx* x, int s, int j, Oli* o) {
+    const Model* m = x->m; const StateInfo* st = &m->st[s]; int L = x->L, base = j;
+    int DW = m->dss_start + m->dss_end + 2, AW = m->ass_start + m->ass_end + 2;
+    o->max = NEG; o->state = -1; o->base = -1;
+    int boe, eobe, lm, rm;
+    utr_end_positions(x, st, base, &boe, &eobe);
+    switch (st->uk) {
+    case U_SINGLE:
+        if (st->u5) {
+            lm = base - (m->umax - m->tiw + m->tuw);
+            rm = st->fwd ? base - m->tuw - m->tss_end - 1 + m->tiw + m->tss_end : base - m->tuw - 1 + m->tiw;
+            if (rm > base - 1) rm = base - 1;
+        } else {
+            lm = base - m->umax3s;
+            rm = (st->fwd && base == L - 1) ? base - 1 : base - m->dpc - m->boxlen;
+        }
+        break;
+    case U_INIT:
+        if (st->u5) { lm = base - (m->umax + 2 + m->dss_end + m->tuw); rm = base - m->tuw - m->tss_end - DW; }
+        else { lm = base - (m->umax + 2 + m->dss_end); rm = base - m->dss_end - 2; }
+        break;
+    case U_INTERNAL:
+        lm = base - (m->umax + 2 + m->dss_end + m->ass_up + m->ass_start + 2); rm = base - DW - m->ass_up - AW;
+        break;
+    case U_TERM:
+        if (st->u5) {
+            lm = base - (m->umax - m->tiw + m->ass_up + m->ass_start + 2); rm = base - m->ass_up - AW;
+            if (-m->ass_up - AW + m->tiw + m->ass_end < 0) rm = base - m->ass_up - AW + m->tiw + m->ass_end;
+        } else {
+            lm = base - (m->umax3t + 2 + m->ass_start + m->ass_up);
+            rm = (st->fwd && base == L - 1) ? base - AW - m->ass_up : base - m->dpc - m->boxlen - AW - m->ass_up;
+        }
+        break;
+    default: lm = rm = base - 1;
+    }
+    sc_t ep = boe >= 0 ? utr_endPart(x, st, boe, base, eobe) : NEG;
+    if (isneg(ep)) return;
+    if (st->uk == U_INTRONVAR) return;
+    if (st->fwd && st->u5 && (st->uk == U_SINGLE || st->uk == U_INIT)) { if (lm < -m->tuw) lm = -m->tuw; }
+    else if (!st->fwd && !st->u5 && (st->uk == U_SINGLE || st->uk == U_TERM)) { if (lm < -m->boxlen - m->dpc) lm = -m->boxlen - m->dpc; }
+    else if (lm < 0) lm = 0;
+    struct Eop* e = &x->eop[s];
+    if (x->walking) e->n = 0;
+    e->it = 0; e->inCache = 0;
+    for (int endOfPred = rm; endOfPred >= lm; x->eop_off ? (void)endOfPred-- : eop_decrement(e, &endOfPred)) {
+        int col = endOfPred > 0 ? endOfPred : 0, i0 = 0;
+        while (i0 < st->nanc && isneg(PVAL(x, col, st->anc[i0]))) i0++;
+        if (i0 == st->nanc) continue;
+        sc_t nep = utr_notEndPart(x, st, endOfPred + 1, boe - 1, eobe);
+        if (isneg(nep)) continue;
+        if (!x->eop_off) eop_update(e, endOfPred);
+        for (int i = i0; i < st->nanc; i++) {
+            int a = st->anc[i]; sc_t pv = PVAL(x, col, a); if (isneg(pv)) continue;
+            sc_t te = TR(a, s) + (nep + ep);
+            fwd_option(x, a, col, endOfPred, te);
+            sc_t pp = pv + te;
+            if (pp > o->max) { o->max = pp; o->state = a; o->base = endOfPred; }
+        }
+    }
+}
+
 static void state_eval(Ctx* x, int s, int j, Oli* o) {
     switch (x->m->st[s].kind) {
     case K_IGENIC: igenic_eval(x, s, j, o); break;
     case K_EXON: exon_eval(x, s, j, o); break;
+    case K_UTR: utr_eval(x, s, j, o); break;
     default: intron_eval(x, s, j, o);
     }
 }
 
 /* ------------------------------------------------------------------ driver */
 static int trunc_flag(int type, int end, int predEnd, int L) {      /* gene.cc:309-321 */
-    int isIntron = (type >= T_LESSD0 && type <= 23) || (type >= T_RLESSD0 && type <= 58);
+    int utrIntron = type == 26 || type == 27 || type == 32 || type == 33 || type == 61 || type == 62 || type == 67 || type == 68;
+    int isIntron = (type >= T_LESSD0 && type <= 23) || (type >= T_RLESSD0 && type <= 58) || utrIntron;
+    int utrExon = ((type >= 24 && type <= 35) || (type >= 59 && type <= 70)) && !utrIntron;
     int t = 0;
-    if (end == L - 1 && ((type >= 2 && type <= 7) || (type >= 38 && type <= 43) || isIntron)) t |= 2;   /* TRUNC_RIGHT */
-    if ((predEnd == -1 || predEnd == 0) && ((type >= 5 && type <= 8) || (type >= 37 && type <= 40) || isIntron)) t |= 1; /* TRUNC_LEFT */
+    if (end == L - 1 && ((type >= 2 && type <= 7) || (type >= 38 && type <= 43) || isIntron || type == 30 || type == 35)) t |= 2;   /* TRUNC_RIGHT */
+    if ((predEnd == -1 || predEnd == 0) && ((type >= 5 && type <= 8) || (type >= 37 && type <= 40) || isIntron || utrExon)) t |= 1; /* TRUNC_LEFT */
     return t;
 }
 
@@ -915,6 +1355,20 @@ int orc_decode(const Model* m, const char* dna, int L, const int* gc_in, int64_t
     for (int s = 0; s < m->S; s++) { x->V[s] = m->init[s]; if (fwd) x->F[s] = isneg(m->init[s]) ? -INFINITY : sc2d(m->init[s]); }
     Oli o;
     x->mode = fwd ? 1 : 0;
+    char* raw = (char*)malloc(L + 1);
+    for (int i = 0; i < L; i++) raw[i] = (dna[i] >= 'A' && dna[i] <= 'Z') ? dna[i] + 32 : dna[i];
+    raw[L] = 0; x->raw = raw; x->cur_gc = -1; x->walking = 0;
+    x->eop_off = getenv("ORC_EOP_OFF") != NULL;
+    for (int g = 0; g < 2; g++) { x->assMemo[g] = (sc_t*)malloc((size_t)(L + 1) * sizeof(sc_t)); x->assMemoGen[g] = (int*)calloc(L + 1, sizeof(int)); }
+    x->assGen = 1; x->assN = 0;
+    if (m->utr) {
+        for (int g = 0; g < 7; g++) { x->seg[g] = (sc_t*)malloc((size_t)(L + 1) * sizeof(sc_t)); for (int i = 0; i <= L; i++) x->seg[g][i] = NEG; }
+        for (int g = 0; g < 2; g++) {
+            x->tssP[g] = (sc_t*)malloc((size_t)(L + 1) * sizeof(sc_t)); x->ttsP[g] = (sc_t*)malloc((size_t)(L + 1) * sizeof(sc_t));
+            for (int i = 0; i <= L; i++) { x->tssP[g][i] = UNSET; x->ttsP[g][i] = NEG; }
+        }
+        x->eop = (struct Eop*)calloc(m->S, sizeof(struct Eop));
+    }
     if (!anynuc) {   /* namgene.cc:205-226 */
         for (int j = 1; j < L; j++) for (int s = 0; s < m->S; s++) {
             VV(j, s) = s == 0 ? VV(j - 1, s) + m->log025 : NEG;
@@ -923,6 +1377,10 @@ int orc_decode(const Model* m, const char* dna, int L, const int* gc_in, int64_t
     } else {
         for (int j = 1; j < L; j++) {
             x->cls = gc[j];
+            if (gc[j] != x->cur_gc) {            /* namgene.cc:245-248: updateToLocalGCEach(idx, j, nextStep(j) - 1) */
+                int nx = j + 1; while (nx < L && gc[nx] == gc[j]) nx++;
+                x->cur_gc = gc[j]; utr_update_gc(x, j, nx - 1);
+            }
             for (int s = 0; s < m->S; s++) {
                 x->lse_m = -INFINITY; x->lse_s = 0;
                 state_eval(x, s, j, &o); VV(j, s) = o.max;
@@ -933,7 +1391,7 @@ int orc_decode(const Model* m, const char* dna, int L, const int* gc_in, int64_t
     if (Vout) memcpy(Vout, x->V, (size_t)L * m->S * sizeof(sc_t));
     if (Fout && fwd) memcpy(Fout, x->F, (size_t)L * m->S * sizeof(double));
     /* getViterbiPath, namgene.cc:432-510 */
-    x->mode = 0;
+    x->mode = 0; x->walking = 1;
     int ret = 0, state = -1; sc_t best = NEG;
     for (int s = 0; s < m->S; s++) {
         sc_t v = VV(L - 1, s); if (isneg(v) || isneg(m->term[s])) continue;
@@ -946,7 +1404,11 @@ int orc_decode(const Model* m, const char* dna, int L, const int* gc_in, int64_t
         /* collect right-to-left, then reverse */
         while (base > 0) {
             if (!anynuc) { o.state = 0; o.base = base - 1; }
-            else { x->cls = gc[base]; state_eval(x, state, base, &o); }
+            else {
+                x->cls = gc[base];
+                if (gc[base] != x->cur_gc) { x->cur_gc = gc[base]; utr_update_gc(x, 2, 1); }      /* namgene.cc:476-481 */
+                state_eval(x, state, base, &o);
+            }
             if (o.state < 0 || (o.base >= base && o.state == state) || o.base > base + 10) { ret = -2; break; }
             if (n >= cap) { ret = -3; break; }
             ptype[n] = m->st[state].type; pbegin[n] = o.base + 1; pend[n] = base;
@@ -987,6 +1449,7 @@ int orc_decode(const Model* m, const char* dna, int L, const int* gc_in, int64_t
                     int base = x->opts[pick].base, st = x->opts[pick].state; lpath += ln;
                     while (base > 0 && !bad) {
                         x->cls = gc[base]; x->nopt = 0;
+                        if (gc[base] != x->cur_gc) { x->cur_gc = gc[base]; utr_update_gc(x, 2, 1); }  /* namgene.cc:401-406 */
                         state_eval(x, st, base, &o);
                         pick = opt_sample(x, &ln);
                         if (pick < 0 || n >= L + 8) { bad = 1; break; }
@@ -1015,6 +1478,13 @@ int orc_decode(const Model* m, const char* dna, int L, const int* gc_in, int64_t
         free(x->PI[cl]); free(x->PIR[cl]);
     }
     for (size_t i = 0; i < (size_t)2 * L; i++) { SnipEnt* t = x->snF[i]; while (t) { SnipEnt* nx = t->next; free(t); t = nx; } }
+    if (m->utr) {
+        for (int g = 0; g < 7; g++) free(x->seg[g]);
+        for (int g = 0; g < 2; g++) { free(x->tssP[g]); free(x->ttsP[g]); }
+        for (int s = 0; s < m->S; s++) free(x->eop[s].v);
+        free(x->eop);
+    }
+    free(raw); for (int g = 0; g < 2; g++) { free(x->assMemo[g]); free(x->assMemoGen[g]); }
     free(x->snF); free(x->snL); free(x->opts); free(x->F);
     free(x->V); free(x->nsf); free(x->nsr); free(gc); free(c);
     return ret;

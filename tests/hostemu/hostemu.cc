@@ -41,7 +41,7 @@ int hostemu_decode(void* mp, const char* dna, int L, const int32_t* gc_in,
     WinLayout lay; std::vector<char> buf; char* base = nullptr; WinView v; WarpState ws; Sweep sw; WinOuts* outs = nullptr;
     std::vector<char> pool; size_t pool_used = 0;
     for (int pass = 0; pass < 2; pass++) {
-        lay = make_layout(L, m->C, pass == 1);
+        lay = make_layout(L, m->C, pass == 1, false, 0, m->utr != 0);
         buf.assign(lay.total + 64, 0);
         base = buf.data();
         int cm = 0;
@@ -82,7 +82,7 @@ int hostemu_forward(void* mp, const char* dna, int L, const int32_t* gc_in, int 
     WinLayout lay; std::vector<char> buf; char* base = nullptr; WinView v; WarpState ws; SweepFwd sw; WinOuts* outs = nullptr;
     std::vector<char> pool; size_t pool_used = 0;
     for (int pass = 0; pass < 2; pass++) {
-        lay = make_layout(L, m->C, pass == 1, true);
+        lay = make_layout(L, m->C, pass == 1, true, 0, m->utr != 0);
         buf.assign(lay.total + 64, 0);
         base = buf.data();
         int cm = 0;
@@ -111,7 +111,7 @@ int hostemu_sample(void* mp, const char* dna, int L, const int32_t* gc_in, int n
     WinLayout lay; std::vector<char> buf; char* base = nullptr; WinView v; WarpState ws; SweepFwd sw; WinOuts* outs = nullptr;
     std::vector<char> pool; size_t pool_used = 0;
     for (int pass = 0; pass < 2; pass++) {
-        lay = make_layout(L, m->C, pass == 1, true);
+        lay = make_layout(L, m->C, pass == 1, true, 0, m->utr != 0);
         buf.assign(lay.total + 64, 0);
         base = buf.data();
         int cm = 0;
@@ -134,6 +134,8 @@ int hostemu_sample(void* mp, const char* dna, int L, const int32_t* gc_in, int n
     sp.run(nsamples, so);
     return *status ? -1 : nsamples;
 }
+int hostemu_nchain(void) { return NCHAIN; }
+int hostemu_statecount(void* mp) { return ((EmuModel*)mp)->hm.dm.S; }
 int hostemu_chain_state(void* mp, int ch) { return ((EmuModel*)mp)->hm.dm.chain_state[ch]; }
 
 }  // extern "C"

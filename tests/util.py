@@ -133,7 +133,7 @@ class Oracle:
 
 
 class HostEmu:
-    NCHAIN = 7
+    NCHAIN = 11
 
     def __init__(self, blob: bytes):
         srcs = ["tests/hostemu/hostemu.cc", "augustus_b200/csrc/ghmm_model.cc"]
@@ -171,13 +171,14 @@ class HostEmu:
             pos += c
         return {"status": status.value, "samples": out}
 
-    def decode(self, dna: str, gc=None, want_cells=False, S=47):
+    def decode(self, dna: str, gc=None, want_cells=False, S=None):
         L = len(dna)
+        S = S or self.lib.hostemu_statecount(ctypes.c_void_p(self.m))
         cap = L // 2 + 64
         eb, ee = np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=np.int32)
         et, etr = np.zeros(cap, dtype=np.uint8), np.zeros(cap, dtype=np.uint8)
         lp, st, nev = ctypes.c_double(), ctypes.c_int32(), ctypes.c_int32()
-        evcap = 4 * L + 256
+        evcap = 8 * L + 256
         evc, evs = np.zeros(evcap, dtype=np.int32), np.zeros(evcap, dtype=np.int32)
         evV = np.zeros(evcap, dtype=np.int64)
         chV = np.zeros((L, self.NCHAIN), dtype=np.int64) if want_cells else None
