@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(PREP_BS) k_prep(const WinDev* __restrict__ win
     for (int wi = blockIdx.x; wi < nwin; wi += gridDim.x) {
         const WinDev wd = wins[wi];
         const int L = wd.L; char* base = wd.base; const WinLayout& lay = wd.lay;
-        uint8_t* code = (uint8_t*)(base + lay.code); uint8_t* gc = (uint8_t*)(base + lay.gc); uint16_t* mask = (uint16_t*)(base + lay.mask);
+        uint8_t* code = (uint8_t*)(base + lay.code); uint8_t* gc = (uint8_t*)(base + lay.gc); mask_t* mask = (mask_t*)(base + lay.mask);
         if (threadIdx.x == 0) { s_classmask = 0; s_anynuc = 0; }
         __syncthreads();
         { bool any = false; for (int i = threadIdx.x; i < L; i += PREP_BS) { uint8_t c = base_code(wd.dna[i]); code[i] = c; any |= c < 4; } if (any) s_anynuc = 1; }
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(PREP_BS) k_prep(const WinDev* __restrict__ win
                 unsigned mb = anynuc ? column_mask(m, s, j) : 0u;
                 int hi = min(j + SNIP_BEFORE, L - 1), lo = j - SNIP_AFTER;
                 if (anynuc && j >= 1 && nb[hi] - (lo >= 0 ? nb[lo] : 0) > 0) mb |= MB_SLOW;
-                mask[j] = (uint16_t)mb;
+                mask[j] = (mask_t)mb;
             }
             __syncthreads();
         }
@@ -215,6 +215,31 @@ __global__ void __launch_bounds__(PREP_BS) k_prep(const WinDev* __restrict__ win
         {
             sc_t* sg = (sc_t*)(base + lay.sig);
             for (int idx = threadIdx.x; idx < NSIG * L; idx += PREP_BS) { int which = idx / L, j = idx - which * L; sg[idx] = anynuc ? signal_term(m, s, gc[j], which, j) : SC_NEG; }
+        }
+        if (lay.utr) {
+            /* ---- UTR models: TSS / TTS scores, UTR ends and begin-signal sites in the activity mask, SegProbs cumulative sums,
+             * intron emission prefix of the UTR-intron chains (formulas in ghmm_signal.h, same as the sequential host builder) ---- */
+            sc_t* tssF = (sc_t*)(base + lay.tssF); sc_t* tssR = (sc_t*)(base + lay.tssR); sc_t* ttsF = (sc_t*)(base + lay.ttsF); sc_t* ttsR = (sc_t*)(base + lay.ttsR);
+            __syncthreads();
+            for (int i = threadIdx.x; i < L; i += PREP_BS) {
+                int r = i + m->tuw + m->tss_end - 1; int c = gc[r < L ? r : L - 1];
+                tssF[i] = anynuc ? tss_score(m, s, c, 1, i) : SC_NEG; tssR[i] = anynuc ? tss_score(m, s, c, 0, i) : SC_NEG;
+            }
+            for (int b = threadIdx.x; b <= L; b += PREP_BS) { int c = gc[b < L ? b : L - 1]; ttsF[b] = anynuc ? tts_score(m, s, c, 1, b) : SC_NEG; ttsR[b] = anynuc ? tts_score(m, s, c, 0, b) : SC_NEG; }
+            __syncthreads();
+            if (anynuc) {
+                const sc_t* sg = (const sc_t*)(base + lay.sig);
+                for (int j = threadIdx.x; j < L; j += PREP_BS) mask[j] |= (mask_t)utr_column_mask(m, s, j, sg, tssF, tssR, ttsF, ttsR);
+            }
+            sc_t* useg = (sc_t*)(base + lay.useg);
+            for (int g = 0; g < NUSEG; g++) {
+                sc_t* cum = useg + (size_t)g * (size_t)(L + 1);
+                if (threadIdx.x == 0) cum[0] = m->log025;
+                block_scan_gen<sc_t>([&](int i) { int p = i + 1; return useg_term(m, s, gc[p < L ? p : L - 1], g, p); }, cum + 1, L, m->log025, sm64);
+            }
+            sc_t* aint = (sc_t*)(base + lay.aint);
+            if (threadIdx.x == 0) aint[0] = 0;
+            block_scan_gen<sc_t>([&](int i) { return intron_emi1(m, s, gc[i + 1], i + 1); }, aint + 1, L - 1, (sc_t)0, sm64);
         }
         /* ---- prefix sums ---- */
         if (threadIdx.x == 0) {
@@ -261,7 +286,8 @@ __global__ void __launch_bounds__(PREP_BS) k_prep(const WinDev* __restrict__ win
 
 /* ------------------------------------------------------------------ sweep kernel: one warp per window */
 constexpr int SWEEP_WARPS = 4;
-__global__ void __launch_bounds__(SWEEP_WARPS * 32, 4) k_sweep(const WinDev* __restrict__ wins, int nwin, int* __restrict__ next) {
+template <class SW>
+__device__ __forceinline__ void sweep_body(const WinDev* __restrict__ wins, int nwin, int* __restrict__ next) {
     const DevModel* m = &c_model;
     __shared__ WarpState wstate[SWEEP_WARPS];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -271,16 +297,19 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32, 4) k_sweep(const WinDev* __r
         wi = __shfl_sync(0xffffffffu, wi, 0);
         if (wi >= nwin) break;
         const WinDev& wd = wins[wi];
-        Sweep sw; sw.m = m; sw.ws = &wstate[wid];
+        SW sw; sw.m = m; sw.ws = &wstate[wid];
         sw.w = make_view(wd.base, wd.lay, wd.L, 0);
         sw.run();
         __syncwarp();
     }
 }
+__global__ void __launch_bounds__(SWEEP_WARPS * 32, 4) k_sweep(const WinDev* __restrict__ wins, int nwin, int* __restrict__ next) { sweep_body<Sweep>(wins, nwin, next); }
+/* models with UTR states (71 states, four more chains, eight more candidate lists) */
+__global__ void __launch_bounds__(SWEEP_WARPS * 32, 3) k_sweep_utr(const WinDev* __restrict__ wins, int nwin, int* __restrict__ next) { sweep_body<SweepUtr>(wins, nwin, next); }
 
 /* ------------------------------------------------------------------ forward sweep + posterior sampling: one warp per window */
-__global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep_sample(const WinDev* __restrict__ wins, int nwin, int* __restrict__ next,
-                                                                   const uint32_t* __restrict__ rng, int nrng) {
+template <class SW>
+__device__ __forceinline__ void sweep_sample_body(const WinDev* __restrict__ wins, int nwin, int* __restrict__ next, const uint32_t* __restrict__ rng, int nrng) {
     const DevModel* m = &c_model;
     __shared__ WarpState wstate[SWEEP_WARPS];
     __shared__ int s_nopt[SWEEP_WARPS];
@@ -291,7 +320,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep_sample(const WinDev*
         wi = __shfl_sync(0xffffffffu, wi, 0);
         if (wi >= nwin) break;
         const WinDev& wd = wins[wi];
-        SweepFwd sw; sw.m = m; sw.ws = &wstate[wid];
+        SW sw; sw.m = m; sw.ws = &wstate[wid];
         sw.w = make_view(wd.base, wd.lay, wd.L, 0);
         sw.run();
         __syncwarp();
@@ -299,7 +328,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep_sample(const WinDev*
         if (wd.lay.nsamp > 0) {
             if (wstate[wid].status) { if (lane == 0) outs->samp_status = wstate[wid].status; }
             else {
-                Sampler sp; sp.sw = &sw;
+                SamplerT<SW> sp; sp.sw = &sw;
                 sp.sc.opt = (SampleOpt*)(wd.base + wd.lay.opt); sp.sc.opt_cap = wd.lay.opt_cap; sp.sc.sorted = (int32_t*)(wd.base + wd.lay.sorted); sp.sc.nopt = &s_nopt[wid];
                 sp.rng = rng; sp.nrng = nrng;
                 SampleOut so; so.cap = wd.lay.samp_cap;
@@ -312,6 +341,11 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep_sample(const WinDev*
         __syncwarp();
     }
 }
+
+__global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep_sample(const WinDev* __restrict__ wins, int nwin, int* __restrict__ next,
+                                                                   const uint32_t* __restrict__ rng, int nrng) { sweep_sample_body<SweepFwd>(wins, nwin, next, rng, nrng); }
+__global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep_sample_utr(const WinDev* __restrict__ wins, int nwin, int* __restrict__ next,
+                                                                       const uint32_t* __restrict__ rng, int nrng) { sweep_sample_body<SweepFwdUtr>(wins, nwin, next, rng, nrng); }
 
 /* gather the sampled paths of all windows: per (window, sample) a header, states contiguous per window */
 struct SampHdr { int32_t n, offset; double logp; };

@@ -62,7 +62,7 @@ inline WinLayout make_layout(int L, int C, bool generous = false, bool forward =
     w.tssF = take(utr ? (size_t)L * sizeof(sc_t) : 0); w.tssR = take(utr ? (size_t)L * sizeof(sc_t) : 0);
     w.ttsF = take(utr ? (size_t)(L + 1) * sizeof(sc_t) : 0); w.ttsR = take(utr ? (size_t)(L + 1) * sizeof(sc_t) : 0);
     if (generous) { w.ev_cap = 48 * L + 256; w.cl_cap = L + 64; w.cp_cap = L + 64; w.path_cap = L + 64; }
-    else { w.ev_cap = 3 * L + 256; w.cl_cap = L / 6 + 64; w.cp_cap = L / 16 + 64; w.path_cap = L / 8 + 64; }
+    else { w.ev_cap = (utr ? 5 : 3) * L + 256; w.cl_cap = L / 6 + 64; w.cp_cap = L / 16 + 64; w.path_cap = L / 8 + 64; }
     if ((size_t)w.ev_cap * sizeof(Event) < (size_t)4 * (L + 1) * 4) w.ev_cap = (int)(((size_t)4 * (L + 1) * 4) / sizeof(Event) + 1);   /* prep scratch */
     w.ev = take((size_t)w.ev_cap * sizeof(Event)); w.evstart = take((size_t)(L + 2) * 4);
     for (int i = 0; i < NCL; i++) w.cl[i] = take(i < w.ncl ? (size_t)w.cl_cap * sizeof(Cand) : 0);

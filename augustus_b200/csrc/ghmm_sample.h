@@ -25,8 +25,9 @@ struct SampleScratch { SampleOpt* opt; int opt_cap; int32_t* sorted; int* nopt; 
 
 AUGB_HD int trunc_flag_s(int type, int end, int predEnd, int L) { return trunc_flag(type, end, predEnd, L); }
 
-struct Sampler {
-    SweepFwd* sw; SampleScratch sc; const uint32_t* rng; int nrng; int cursor; int lane;
+template <class SW>
+struct SamplerT {
+    SW* sw; SampleScratch sc; const uint32_t* rng; int nrng; int cursor; int lane;
 
     /* draw one option; returns its index in sc.opt (or -1), adds ln(p/cumprob) to *lp */
     AUGB_D int pick(double* lp) {
@@ -72,7 +73,7 @@ struct Sampler {
 
     /* all paths of one window */
     AUGB_D void run(int nsamples, SampleOut out) {
-        SweepFwd& S = *sw; const DevModel* m = S.m; const int L = S.L;
+        SW& S = *sw; const DevModel* m = S.m; const int L = S.L;
         lane = lane_id(); cursor = 0;
         S.opt = sc.opt; S.nopt = sc.nopt; S.opt_cap = sc.opt_cap;
         int used = 0, status = 0;
@@ -83,7 +84,7 @@ struct Sampler {
             if (alln) {
                 if (used >= out.cap) { status = 8; break; }
                 if (lane == 0) { out.begin[used] = 0; out.end[used] = L - 1; out.type[used] = (uint8_t)m->st[m->chain_state[0]].type; out.trunc[used] = 0; }
-                used++; lp = (double)L * SweepFwd::sc2d(m->log025);
+                used++; lp = (double)L * SW::sc2d(m->log025);
             } else {
                 /* last column x termProbs (namgene.cc:385-392) */
                 if (lane == 0) *sc.nopt = 0;
@@ -92,7 +93,7 @@ struct Sampler {
                 for (int s = 0; s < m->S; s++) {
                     sc_t t = m->term[s];
                     double f = isneg(t) ? -1e308 : S.lookupF(s, L - 1);
-                    S.push_opt(lane == 0 && f > -1e300, f + SweepFwd::sc2d(t), s, s, L - 1);
+                    S.push_opt(lane == 0 && f > -1e300, f + SW::sc2d(t), s, s, L - 1);
                 }
                 int k = pick(&lp);
                 if (k < 0) { bad = 1; if (k == -2) status = 8; }
@@ -121,7 +122,7 @@ struct Sampler {
                         for (int i = 0; i < sd.nanc; i++) {
                             int a = sd.anc[i]; sc_t t = S.TR(a, state);
                             double f = isneg(t) ? -1e308 : S.lookupF(a, base - 1);
-                            S.push_opt(lane == 0 && f > -1e300, f + SweepFwd::sc2d(t), i, a, base - 1);
+                            S.push_opt(lane == 0 && f > -1e300, f + SW::sc2d(t), i, a, base - 1);
                         }
                         k = pick(&lp);
                         if (k < 0) { bad = 1; if (k == -2) status = 8; break; }
@@ -186,6 +187,9 @@ struct Sampler {
         wsync();
     }
 };
+
+typedef SamplerT<SweepFwd> Sampler;
+typedef SamplerT<SweepFwdUtr> SamplerUtr;
 
 /* glibc rand() (random_r, TYPE_3 additive feedback generator: r[i] = r[i-3] + r[i-31], output r[i] >> 1; seeded by the
  * minimal-standard LCG and 310 discarded outputs) — the stream an unseeded `augustus` process draws from (seed 1) */

@@ -49,7 +49,8 @@ struct WarpState {
 
 /* FWD = also fill the forward (sum) values needed by posterior sampling: the same candidates, log-sum-exp beside max
  * (exonmodel.cc:1094-1101, intronmodel.cc:609-617, igenicmodel.cc:250-257) */
-template <bool FWD>
+/* UTR = the model has UtrModel states: compiled as a separate kernel so that the 47-state kernel keeps its code size */
+template <bool FWD, bool UTR = false>
 struct SweepT {
     const DevModel* m; WinView w; WarpState* ws; Seq sq; int lane; int cls; int L;
     const sc_t* trc;            /* transition matrix of the current column's GC class */
@@ -75,7 +76,7 @@ struct SweepT {
     /* ------------------------------------------------------------ chains */
     /* A[e] of a chain: prefix sum of (emission + self transition); the UTR-intron chains share the intron emission prefix and a
      * class-independent self transition (checked when the model is built) */
-    AUGB_D sc_t chainAv(int ch, int e) const { return ch == 0 ? w.AIG[e] : ch < CH_UTR ? w.AGEO[e] : w.AINT[e] + (sc_t)e * m->utr_tself; }
+    AUGB_D sc_t chainAv(int ch, int e) const { return ch == 0 ? w.AIG[e] : (!UTR || ch < CH_UTR) ? w.AGEO[e] : w.AINT[e] + (sc_t)e * m->utr_tself; }
     /* V[e][chain]: last change point with col <= e */
     AUGB_D sc_t chain_value(int ch, int e) const {
         int n = ws->cp_n[ch];
@@ -167,7 +168,7 @@ struct SweepT {
                 } else if (sd.kind == K_LONGASS) {
                     if (sd.fwd) cl_append(CL_LA + mod3(sd.frame - (j + 1 - m->ass_end)), j, s, V, F);   /* phase = mod3(pf - bobe) */
                     else cl_append(CL_RA + sd.frame, j, s, V, F);
-                } else if (sd.kind == K_EXON && m->utr) {
+                } else if (UTR && sd.kind == K_EXON) {
                     /* cells the 3' UTR (forward) / 5' UTR (reverse) states look back to */
                     if (sd.ek == E_SINGLE || sd.ek == E_TERMINAL) cl_append(CL_X3, j, s, V, F);
                     else if (sd.ek == E_RSINGLE || sd.ek == E_RINITIAL) cl_append(CL_XR, j, s, V, F);
@@ -182,7 +183,7 @@ struct SweepT {
         if (!ws->any_pend) return;
         if (lane == 0) {
             AUGB_ROLLED
-            for (int ch = 0; ch < NCHAIN; ch++) {
+            for (int ch = 0; ch < (UTR ? NCHAIN : CH_UTR); ch++) {
                 sc_t pv = ws->pend_val[ch];
                 if (isneg(pv)) continue;
                 int pp = ws->pend_pred[ch], self = m->chain_state[ch];
@@ -463,7 +464,7 @@ struct SweepT {
         Lse fl; fl.clear();
         /* initial / single exons: one pass over the in-frame start codons per ancestor (igenic; with UTR states the two 5' UTR
          * states that end trans_init_window bases before the start codon) */
-        const int npass = scankind ? st.nanc : 1;
+        const int npass = (UTR && scankind) ? st.nanc : 1;
         AUGB_ROLLED
         for (int ai = 0; ai < npass; ai++) {
         const int anc0 = st.anc[ai];
@@ -923,7 +924,7 @@ struct SweepT {
         fill_evstart(j);
         set_class(w.gc[j]);
         if (mb & MB_SLOW) snip_column_begin(j);
-        if (mb & MB_UTR_BEGINS) utr_begins(j, mb);
+        if (UTR && (mb & MB_UTR_BEGINS)) utr_begins(j, mb);
         /* one call site per routine (the bodies are large): loop over the strands / states this column activates */
         AUGB_ROLLED
         { unsigned lm = ((mb & MB_LESSD) ? 1u : 0u) | ((mb & MB_RLESSD) ? 2u : 0u);
@@ -944,12 +945,11 @@ struct SweepT {
             int xs = m->xslot[q];
             if (xs >= 0) exon_eval(xs, j);
         }
-        if (mb & (MB_UTR_ENDS | MB_LONGDSS | MB_RLONGASS)) {
+        if (UTR && (mb & (MB_UTR_ENDS | MB_LONGDSS | MB_RLONGASS))) {
             /* UTR exon states by end signal: slots 0-15 = utr5single, utr5init, utr5internal, utr5term, utr3single, utr3init,
              * utr3internal, utr3term, then the same for the reverse strand */
             unsigned us = ((mb & MB_U5ATG) ? 0x0009u : 0u) | ((mb & MB_LONGDSS) ? 0x0066u : 0u) | ((mb & MB_UTTS) ? 0x0090u : 0u)
                         | ((mb & MB_URTSS) ? 0x0300u : 0u) | ((mb & MB_RLONGASS) ? 0xcc00u : 0u) | ((mb & MB_URSTOP) ? 0x3000u : 0u);
-            if (!m->utr) us = 0;
             AUGB_ROLLED
             while (us) {
                 int q = wffs(us); us &= us - 1;
@@ -966,7 +966,7 @@ struct SweepT {
         if (lane == 0) {
             ws->n_ev = 0; ws->filled = -1; ws->status = 0; ws->any_pend = 0; ws->snip_cnt[0] = ws->snip_cnt[1] = 0;
             AUGB_ROLLED
-            for (int i = 0; i < NCL; i++) ws->cl_n[i] = 0;
+            for (int i = 0; i < (UTR ? NCL : NCL_BASE); i++) ws->cl_n[i] = 0;
             AUGB_ROLLED
             for (int i = 0; i < 6; i++) ws->eq_cur[i] = 0;
             AUGB_ROLLED
@@ -998,8 +998,8 @@ struct SweepT {
                 const StateDesc& sd = m->st[s];
                 if (lane == 0 && sd.kind == K_LONGDSS && sd.fwd) cl_append(CL_LD + sd.frame, 0, s, v, sc2d(v));
                 if (lane == 0 && sd.kind == K_LONGASS && !sd.fwd) cl_append(CL_RA + sd.frame, 0, s, v, sc2d(v));
-                if (lane == 0 && sd.kind == K_EXON && m->utr && (sd.ek == E_SINGLE || sd.ek == E_TERMINAL)) cl_append(CL_X3, 0, s, v, sc2d(v));
-                if (lane == 0 && sd.kind == K_EXON && m->utr && (sd.ek == E_RSINGLE || sd.ek == E_RINITIAL)) cl_append(CL_XR, 0, s, v, sc2d(v));
+                if (UTR && lane == 0 && sd.kind == K_EXON && (sd.ek == E_SINGLE || sd.ek == E_TERMINAL)) cl_append(CL_X3, 0, s, v, sc2d(v));
+                if (UTR && lane == 0 && sd.kind == K_EXON && (sd.ek == E_RSINGLE || sd.ek == E_RINITIAL)) cl_append(CL_XR, 0, s, v, sc2d(v));
                 if (lane == 0 && !alln) feed_chain(0, s, v, sc2d(v));
                 wsync();
             }
@@ -1058,7 +1058,9 @@ struct SweepT {
     }
 };
 
-typedef SweepT<false> Sweep;
-typedef SweepT<true> SweepFwd;
+typedef SweepT<false, false> Sweep;
+typedef SweepT<true, false> SweepFwd;
+typedef SweepT<false, true> SweepUtr;
+typedef SweepT<true, true> SweepFwdUtr;
 
 }  // namespace augb

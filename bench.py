@@ -78,7 +78,7 @@ def ref_binary():
     return (exe, cfg) if os.path.exists(exe) and os.path.isdir(cfg) else (None, None)
 
 
-def run_reference_sample(n_windows, cores, start_index=0, extra_args=()):
+def run_reference_sample(n_windows, cores, start_index=0, extra_args=(), window_len=None):
     """Decode n_windows synthetic windows with the unmodified reference, `cores` processes in parallel.
     Returns (Mbp/s, seconds)."""
     from augustus_b200 import synth
@@ -86,6 +86,7 @@ def run_reference_sample(n_windows, cores, start_index=0, extra_args=()):
     if exe is None:
         raise RuntimeError("oracle/_ref/augustus is missing (run __graft_entry__.build() in the build container)")
     env = dict(os.environ, AUGUSTUS_CONFIG_PATH=cfg)
+    wlen = window_len or WINDOW_LEN
     with tempfile.TemporaryDirectory() as td:
         files = []
         per = [[] for _ in range(cores)]
@@ -95,7 +96,7 @@ def run_reference_sample(n_windows, cores, start_index=0, extra_args=()):
             if not idxs:
                 continue
             fa = os.path.join(td, "c%d.fa" % c)
-            synth.write_fasta(fa, [synth.window(i, WINDOW_LEN) for i in idxs], ["w%d" % i for i in idxs])
+            synth.write_fasta(fa, [synth.window(i, wlen) for i in idxs], ["w%d" % i for i in idxs])
             files.append(fa)
         t0 = time.perf_counter()
         procs = []
@@ -108,7 +109,7 @@ def run_reference_sample(n_windows, cores, start_index=0, extra_args=()):
             if p.wait() != 0:
                 raise RuntimeError("reference process failed")
         dt = time.perf_counter() - t0
-    return n_windows * WINDOW_LEN / 1e6 / dt, dt
+    return n_windows * wlen / 1e6 / dt, dt
 
 
 def reference_arm(args, rank, world):
@@ -176,6 +177,9 @@ def main():
     wins = synth.windows_parallel_indices(my_idx, WINDOW_LEN)
     wins_b = [w.encode() for w in wins]
     bases = M * WINDOW_LEN
+    # inputs of the config-4 side measurement (generated here, before CUDA work starts, by the same process pool)
+    n4, l4 = 1000, 200000
+    wins4_b = [w.encode() for w in synth.windows_parallel(n4, l4)] if (not args.no_secondary and rank == 0 and world == 1) else None
     dec = Decoder(util.blob_bytes(), local)
     stream = torch.cuda.ExternalStream(dec.stream, device=torch.device("cuda", local))
 
@@ -267,7 +271,7 @@ def main():
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": k * WINDOW_LEN / 1e6 / dt, "unit": "Mbp/s", "cores": 1, "kind": "port",
                                     "sample": "%d windows x 50 kb, oracle/ghmm_oracle.c, 1 thread (%s)" % (k, ex)}
-    if not args.no_secondary:
+    if not args.no_secondary and world == 1:
         # BASELINE.json configs[4]: --sample=100 --alternatives-from-sampling=true on 1000 x 50 kb windows (forward + sampling kernels)
         try:
             n5 = min(1000, M)
@@ -285,6 +289,25 @@ def main():
             line["secondary"] = {"config5_sampling": sec}
         except Exception as ex:
             line["secondary"] = {"config5_sampling": {"error": str(ex)}}
+        # BASELINE.json configs[3]: --species=human --UTR=on over 1000 x 200 kb windows (71 states: UtrModel next to the coding states)
+        try:
+            dec.close()
+            dec4 = Decoder(util.blob_bytes("human_utr"), local)
+            dec4.decode_batch_raw(wins4_b[:16])
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            out4 = dec4.decode_batch_raw(wins4_b)
+            torch.cuda.synchronize(); dt4 = time.perf_counter() - t0
+            assert not out4[1].any()
+            sec4 = {"workload": "%d x 200 kb synthetic windows, --species=human --UTR=on --softmasking=0 (71 states), 1 GPU, e2e from host buffers through augb200_decode_batch" % n4,
+                    "value": n4 * l4 / 1e6 / dt4, "unit": "Mbp/s", "sweep_ms": dec4.last_sweep_ms, "path_states": int(out4[0].sum())}
+            if not args.no_cpu_baseline:
+                cores = os.cpu_count() or 1
+                v4, d4 = run_reference_sample(cores, cores, extra_args=("--UTR=on",), window_len=l4)
+                sec4["cpu_baseline"] = {"value": v4, "unit": "Mbp/s", "cores": cores, "kind": "reference", "sample": "%d windows x 200 kb (%.1f s wall)" % (cores, d4)}
+            line["secondary"]["config4_utr"] = sec4
+            dec4.close()
+        except Exception as ex:
+            line["secondary"]["config4_utr"] = {"error": repr(ex)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

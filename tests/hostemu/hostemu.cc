@@ -31,14 +31,16 @@ void* hostemu_model_create(const void* blob, size_t nbytes, char* errbuf, int er
 }
 void hostemu_model_destroy(void* p) { delete (EmuModel*)p; }
 
-/* decode one window; optional dump of all events (col, state, V) and chain values V[j][chain] */
-int hostemu_decode(void* mp, const char* dna, int L, const int32_t* gc_in,
+}  // extern "C"
+/* implementation, instantiated for the 47-state and the UTR variant of the sweep */
+template <class SW>
+static int decode_impl(void* mp, const char* dna, int L, const int32_t* gc_in,
                    int cap, int32_t* pbegin, int32_t* pend, uint8_t* ptype, uint8_t* ptrunc, double* logp, int32_t* status,
                    int evcap, int32_t* ev_col, int32_t* ev_state, int64_t* ev_V, int32_t* n_ev_out,
                    int64_t* chainV /* [L][NCHAIN] or NULL */, uint8_t* gc_out /* [L] or NULL */) {
     EmuModel* e = (EmuModel*)mp; const DevModel* m = &e->hm.dm;
     /* as augb200_decode_batch: default capacities first, the generous layout if a structure overflowed */
-    WinLayout lay; std::vector<char> buf; char* base = nullptr; WinView v; WarpState ws; Sweep sw; WinOuts* outs = nullptr;
+    WinLayout lay; std::vector<char> buf; char* base = nullptr; WinView v; WarpState ws; SW sw; WinOuts* outs = nullptr;
     std::vector<char> pool; size_t pool_used = 0;
     for (int pass = 0; pass < 2; pass++) {
         lay = make_layout(L, m->C, pass == 1, false, 0, m->utr != 0);
@@ -48,7 +50,7 @@ int hostemu_decode(void* mp, const char* dna, int L, const int32_t* gc_in,
         pool.assign((size_t)(m->C) * lay.slab + 64, 0); pool_used = 0;
         prep_window_seq(m, dna, L, gc_in, base, lay, &cm, pass == 0 ? pool.data() : nullptr, pool.size(), &pool_used);
         v = make_view(base, lay, L, cm);
-        sw = Sweep(); sw.m = m; sw.w = v; sw.ws = &ws;
+        sw = SW(); sw.m = m; sw.w = v; sw.ws = &ws;
         sw.run();
         outs = (WinOuts*)(base + lay.outs);
         if (outs->status != AUGB200_ERR_CAPACITY) break;
@@ -76,10 +78,11 @@ int hostemu_decode(void* mp, const char* dna, int L, const int32_t* gc_in,
     return n;
 }
 /* forward fill: returns ln forward of every event (aligned with ev_col / ev_state) and of the chains per column */
-int hostemu_forward(void* mp, const char* dna, int L, const int32_t* gc_in, int evcap, int32_t* ev_col, int32_t* ev_state, double* ev_F,
+template <class SW>
+static int forward_impl(void* mp, const char* dna, int L, const int32_t* gc_in, int evcap, int32_t* ev_col, int32_t* ev_state, double* ev_F,
                     int32_t* n_ev_out, double* chainF /* [L][NCHAIN] */, int32_t* status) {
     EmuModel* e = (EmuModel*)mp; const DevModel* m = &e->hm.dm;
-    WinLayout lay; std::vector<char> buf; char* base = nullptr; WinView v; WarpState ws; SweepFwd sw; WinOuts* outs = nullptr;
+    WinLayout lay; std::vector<char> buf; char* base = nullptr; WinView v; WarpState ws; SW sw; WinOuts* outs = nullptr;
     std::vector<char> pool; size_t pool_used = 0;
     for (int pass = 0; pass < 2; pass++) {
         lay = make_layout(L, m->C, pass == 1, true, 0, m->utr != 0);
@@ -89,7 +92,7 @@ int hostemu_forward(void* mp, const char* dna, int L, const int32_t* gc_in, int 
         pool.assign((size_t)(m->C) * lay.slab + 64, 0); pool_used = 0;
         prep_window_seq(m, dna, L, gc_in, base, lay, &cm, pass == 0 ? pool.data() : nullptr, pool.size(), &pool_used);
         v = make_view(base, lay, L, cm);
-        sw = SweepFwd(); sw.m = m; sw.w = v; sw.ws = &ws;
+        sw = SW(); sw.m = m; sw.w = v; sw.ws = &ws;
         sw.run();
         outs = (WinOuts*)(base + lay.outs);
         if (outs->status != AUGB200_ERR_CAPACITY) break;
@@ -101,14 +104,12 @@ int hostemu_forward(void* mp, const char* dna, int L, const int32_t* gc_in, int 
     if (chainF) for (int j = 0; j < L; j++) for (int ch = 0; ch < NCHAIN; ch++) chainF[(size_t)j * NCHAIN + ch] = m->chain_state[ch] >= 0 ? sw.chain_fvalue(ch, j) : -1e308;
     return ne;
 }
-/* glibc rand() stream restatement, for checking against libc */
-void hostemu_rand_stream(uint32_t seed, uint32_t* out, int n) { glibc_rand_stream(seed, out, (size_t)n); }
-
 /* forward fill + nsamples sampled paths (condensed, concatenated) */
-int hostemu_sample(void* mp, const char* dna, int L, const int32_t* gc_in, int nsamples, int cap,
+template <class SW>
+static int sample_impl(void* mp, const char* dna, int L, const int32_t* gc_in, int nsamples, int cap,
                    int32_t* sb, int32_t* se, uint8_t* st_, uint8_t* str_, int32_t* scount, double* slogp, int32_t* status) {
     EmuModel* e = (EmuModel*)mp; const DevModel* m = &e->hm.dm;
-    WinLayout lay; std::vector<char> buf; char* base = nullptr; WinView v; WarpState ws; SweepFwd sw; WinOuts* outs = nullptr;
+    WinLayout lay; std::vector<char> buf; char* base = nullptr; WinView v; WarpState ws; SW sw; WinOuts* outs = nullptr;
     std::vector<char> pool; size_t pool_used = 0;
     for (int pass = 0; pass < 2; pass++) {
         lay = make_layout(L, m->C, pass == 1, true, 0, m->utr != 0);
@@ -118,7 +119,7 @@ int hostemu_sample(void* mp, const char* dna, int L, const int32_t* gc_in, int n
         pool.assign((size_t)(m->C) * lay.slab + 64, 0); pool_used = 0;
         prep_window_seq(m, dna, L, gc_in, base, lay, &cm, pass == 0 ? pool.data() : nullptr, pool.size(), &pool_used);
         v = make_view(base, lay, L, cm);
-        sw = SweepFwd(); sw.m = m; sw.w = v; sw.ws = &ws;
+        sw = SW(); sw.m = m; sw.w = v; sw.ws = &ws;
         sw.run();
         outs = (WinOuts*)(base + lay.outs);
         if (outs->status != AUGB200_ERR_CAPACITY) break;
@@ -128,11 +129,32 @@ int hostemu_sample(void* mp, const char* dna, int L, const int32_t* gc_in, int n
     std::vector<uint32_t> rng(nrng);
     glibc_rand_stream(1, rng.data(), nrng);
     std::vector<SampleOpt> opts(L + 4096); std::vector<int32_t> sorted(L + 4096); int nopt = 0;
-    Sampler sp; sp.sw = &sw; sp.sc.opt = opts.data(); sp.sc.opt_cap = (int)opts.size(); sp.sc.sorted = sorted.data(); sp.sc.nopt = &nopt;
+    SamplerT<SW> sp; sp.sw = &sw; sp.sc.opt = opts.data(); sp.sc.opt_cap = (int)opts.size(); sp.sc.sorted = sorted.data(); sp.sc.nopt = &nopt;
     sp.rng = rng.data(); sp.nrng = (int)nrng;
     SampleOut so; so.cap = cap; so.begin = sb; so.end = se; so.type = st_; so.trunc = str_; so.count = scount; so.logp = slogp; so.status = status;
     sp.run(nsamples, so);
     return *status ? -1 : nsamples;
+}
+extern "C" {
+static bool is_utr(void* mp) { return ((EmuModel*)mp)->hm.dm.utr != 0; }
+/* decode one window; optional dump of all events (col, state, V) and chain values V[j][chain] */
+int hostemu_decode(void* mp, const char* dna, int L, const int32_t* gc_in,
+                   int cap, int32_t* pbegin, int32_t* pend, uint8_t* ptype, uint8_t* ptrunc, double* logp, int32_t* status,
+                   int evcap, int32_t* ev_col, int32_t* ev_state, int64_t* ev_V, int32_t* n_ev_out, int64_t* chainV, uint8_t* gc_out) {
+    return is_utr(mp) ? decode_impl<SweepUtr>(mp, dna, L, gc_in, cap, pbegin, pend, ptype, ptrunc, logp, status, evcap, ev_col, ev_state, ev_V, n_ev_out, chainV, gc_out)
+                      : decode_impl<Sweep>(mp, dna, L, gc_in, cap, pbegin, pend, ptype, ptrunc, logp, status, evcap, ev_col, ev_state, ev_V, n_ev_out, chainV, gc_out);
+}
+int hostemu_forward(void* mp, const char* dna, int L, const int32_t* gc_in, int evcap, int32_t* ev_col, int32_t* ev_state, double* ev_F,
+                    int32_t* n_ev_out, double* chainF, int32_t* status) {
+    return is_utr(mp) ? forward_impl<SweepFwdUtr>(mp, dna, L, gc_in, evcap, ev_col, ev_state, ev_F, n_ev_out, chainF, status)
+                      : forward_impl<SweepFwd>(mp, dna, L, gc_in, evcap, ev_col, ev_state, ev_F, n_ev_out, chainF, status);
+}
+/* glibc rand() stream restatement, for checking against libc */
+void hostemu_rand_stream(uint32_t seed, uint32_t* out, int n) { glibc_rand_stream(seed, out, (size_t)n); }
+int hostemu_sample(void* mp, const char* dna, int L, const int32_t* gc_in, int nsamples, int cap,
+                   int32_t* sb, int32_t* se, uint8_t* st_, uint8_t* str_, int32_t* scount, double* slogp, int32_t* status) {
+    return is_utr(mp) ? sample_impl<SweepFwdUtr>(mp, dna, L, gc_in, nsamples, cap, sb, se, st_, str_, scount, slogp, status)
+                      : sample_impl<SweepFwd>(mp, dna, L, gc_in, nsamples, cap, sb, se, st_, str_, scount, slogp, status);
 }
 int hostemu_nchain(void) { return NCHAIN; }
 int hostemu_statecount(void* mp) { return ((EmuModel*)mp)->hm.dm.S; }

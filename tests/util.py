@@ -28,8 +28,50 @@ def golden_samples():
     return json.load(gzip.open(os.path.join(GOLDEN, "ref_samples.json.gz"), "rt"))
 
 
-def golden_paths():
-    return json.load(open(os.path.join(GOLDEN, "ref_paths.json")))
+def golden_paths(utr=False):
+    return json.load(open(os.path.join(GOLDEN, "ref_paths_utr.json" if utr else "ref_paths.json")))
+
+
+def golden_samples_utr():
+    import gzip
+    return json.load(gzip.open(os.path.join(GOLDEN, "ref_samples_utr.json.gz"), "rt"))
+
+
+def path_features(states, par):
+    """Biological coordinates (1-based, as in GFF) of what a condensed state path predicts: CDS parts, transcription start and
+    end sites.  The state geometry is the reference's (ExonModel::ExonModel exonmodel.cc:231-279: a coding-exon state begins
+    beginPartLen - innerPartOffset bases before / after the exon and ends baseOffset bases before it; UtrModel::getEndPositions
+    utrmodel.cc:1572-1643).  `par` = parsed parameter blob."""
+    tiw, dss_start, ass_end, tuw = (int(par[k][0]) for k in ("trans_init_window", "dss_start", "ass_end", "tss_upwindow_size"))
+    cds, tss, tts = [], [], []
+    for t, b, e, tr in states:
+        if t in (1, 2, 3, 4):            # single, initial: the state starts trans_init_window bases before the start codon
+            cds.append((b + tiw + 1, e + (0 if t == 1 else dss_start) + 1, "+"))
+        elif 5 <= t <= 8:                # internal, terminal
+            cds.append((b - ass_end + 1, e + (0 if t == 8 else dss_start) + 1, "+"))
+        elif t in (36, 37):              # rsingle, rinitial end trans_init_window bases behind the (reverse) start codon
+            cds.append((b - (0 if t == 36 else dss_start) + 1, e - tiw + 1, "-"))
+        elif 38 <= t <= 43:              # rinternal, rterminal
+            cds.append((b - (dss_start if t <= 40 else 0) + 1, e + ass_end + 1, "-"))
+        elif t in (24, 25) and not (tr & 1) and b >= -tuw + 1:      # utr5single, utr5init begin with the TSS window
+            tss.append((b + tuw + 1, "+"))
+        elif t in (30, 35) and not (tr & 2):
+            tts.append((e + 1, "+"))
+        elif t in (59, 60):
+            tss.append((e - tuw + 1, "-"))
+        elif t in (65, 70) and not (tr & 1) and b > 0:
+            tts.append((b + 1, "-"))
+    return {"CDS": cds, "tss": tss, "tts": tts}
+
+
+def gff_features(path, seqname):
+    out = {"CDS": [], "tss": [], "tts": []}
+    for line in open(path):
+        f = line.rstrip("\n").split("\t")
+        if len(f) < 8 or f[0] != seqname or f[2] not in out:
+            continue
+        out[f[2]].append((int(f[3]), int(f[4]), f[6]) if f[2] == "CDS" else (int(f[3]), f[6]))
+    return out
 
 
 def read_fasta(path):
