@@ -183,9 +183,14 @@ struct SnipFrame { int32_t base, len; int32_t add, pad; sc_t part; };
 /* candidate lists of a window */
 enum : int { CL_LD = 0 /* +f: longdss_f */, CL_RA = 3 /* +f: rlongass_f */, CL_LA = 6 /* +phase */, CL_RD = 9 /* +phase */, NCL_BASE = 12,
              /* UTR models: (begin-signal site, predecessor chain value) lists and the exon cells UTR states follow */
-             CL_T5 = 12 /* TSS, igenic */, CL_A5 = 13 /* ASS, utr5intron */, CL_A3 = 14 /* ASS, utr3intron */, CL_R5 = 15 /* rDSS, rutr5intron */,
-             CL_R3 = 16 /* rDSS, rutr3intron */, CL_TR = 17 /* reverse polyA, igenic */, CL_X3 = 18 /* single, terminal */, CL_XR = 19 /* rsingle, rinitial */,
-             NCL = 20 };
+             CL_T5 = 12 /* TSS, igenic */, CL_A5 = 13 /* ASS, utr5intron */, CL_A3 = 14 /* ASS, utr3intron */,
+             CL_R5I = 15 /* rDSS, rutr5intron, for rutr5init */, CL_R5N = 16 /* the same sites for rutr5internal (other content table) */,
+             CL_R3 = 17 /* rDSS, rutr3intron */, CL_TR = 18 /* reverse polyA, igenic */, CL_X3 = 19 /* single, terminal cells */,
+             CL_XRS = 20 /* rsingle, rinitial cells for rutr5single */, CL_XRT = 21 /* the same cells for rutr5term */,
+             NCL = 22 };
+/* An entry of a UTR list holds V[col][pred] + g, g = begin-signal score - SegProbs cumulative sum just before the middle part of an exon
+ * that begins at col + 1: everything of a candidate's score that does not depend on where the exon ends (forward mode keeps g beside
+ * ln F in WinView::clG). */
 
 /* per-window view of the workspace (all pointers device/global) */
 struct WinView {
@@ -205,6 +210,8 @@ struct WinView {
     int cl_stride, cp_stride;
     /* forward pass (only when sampling is requested): ln forward value of every event / list entry, chain sums */
     double* evF; double* clF0; FChainCP* fcp0; int fcp_stride, fcp_cap;
+    sc_t* clG0;                /* g of the UTR list entries (forward mode), indexed like clF */
+    AUGB_HD sc_t* clG(int i) const { return clG0 + (size_t)i * cl_stride; }
     AUGB_HD double* clF(int i) const { return clF0 + (size_t)i * cl_stride; }
     AUGB_HD FChainCP* fcp(int i) const { return fcp0 + (size_t)i * fcp_stride; }
     int32_t* out_nfcp;

@@ -256,10 +256,10 @@ int HostModel::build(const void* blob, size_t nbytes) {
                 }
             } else if (!three) {
                 switch (uk) {
-                case U_SINGLE: u = UtrDesc{CL_XR, BS_NONE, UE_TSSR, US_RINIT5, 1, 0, 0, (int16_t)(-TIW), (int16_t)(m.umax - TIW + TUW), (int16_t)single5rm, (int16_t)(-TUW), (int16_t)(-TUW - TE + 1), 0, u.ldi}; break;
-                case U_INIT: u = UtrDesc{CL_R5, BS_DSSR, UE_TSSR, US_RINIT5, 0, 0, (int16_t)DW, (int16_t)(DE + 2), (int16_t)(m.umax + 2 + DE + TUW), (int16_t)(TUW + TE + DW), (int16_t)(-TUW), (int16_t)(-TUW - TE + 1), 0, u.ldi}; break;
-                case U_INTERNAL: u = UtrDesc{CL_R5, BS_DSSR, UE_ASSR, US_R5, 0, 0, (int16_t)DW, (int16_t)(DE + 2), (int16_t)(m.umax + 2 + DE + UP + AS + 2), (int16_t)(DW + UP + AW), (int16_t)(-(UP + AS + 2)), (int16_t)(-AW - UP + 1), 0, u.ldi}; break;
-                default: u = UtrDesc{CL_XR, BS_NONE, UE_ASSR, US_R5, 2, 0, 0, (int16_t)(-TIW), (int16_t)(m.umax - TIW + UP + AS + 2), (int16_t)term5rm, (int16_t)(-(UP + AS + 2)), (int16_t)(-AW - UP + 1), 0, u.ldi};
+                case U_SINGLE: u = UtrDesc{CL_XRS, BS_NONE, UE_TSSR, US_RINIT5, 1, 0, 0, (int16_t)(-TIW), (int16_t)(m.umax - TIW + TUW), (int16_t)single5rm, (int16_t)(-TUW), (int16_t)(-TUW - TE + 1), 0, u.ldi}; break;
+                case U_INIT: u = UtrDesc{CL_R5I, BS_DSSR, UE_TSSR, US_RINIT5, 0, 0, (int16_t)DW, (int16_t)(DE + 2), (int16_t)(m.umax + 2 + DE + TUW), (int16_t)(TUW + TE + DW), (int16_t)(-TUW), (int16_t)(-TUW - TE + 1), 0, u.ldi}; break;
+                case U_INTERNAL: u = UtrDesc{CL_R5N, BS_DSSR, UE_ASSR, US_R5, 0, 0, (int16_t)DW, (int16_t)(DE + 2), (int16_t)(m.umax + 2 + DE + UP + AS + 2), (int16_t)(DW + UP + AW), (int16_t)(-(UP + AS + 2)), (int16_t)(-AW - UP + 1), 0, u.ldi}; break;
+                default: u = UtrDesc{CL_XRT, BS_NONE, UE_ASSR, US_R5, 2, 0, 0, (int16_t)(-TIW), (int16_t)(m.umax - TIW + UP + AS + 2), (int16_t)term5rm, (int16_t)(-(UP + AS + 2)), (int16_t)(-AW - UP + 1), 0, u.ldi};
                 }
             } else {
                 switch (uk) {
@@ -310,7 +310,7 @@ int HostModel::build(const void* blob, size_t nbytes) {
                 const UtrDesc& u = m.ud[sd.ek];
                 switch (u.list) {
                 case CL_T5: case CL_TR: ok &= ad.kind == K_IGENIC; break;
-                case CL_A5: case CL_A3: case CL_R5: case CL_R3: ok &= ad.kind == K_UTR && ad.uk == U_INTRON && ad.fwd == sd.fwd && ad.u5 == sd.u5; break;
+                case CL_A5: case CL_A3: case CL_R5I: case CL_R5N: case CL_R3: ok &= ad.kind == K_UTR && ad.uk == U_INTRON && ad.fwd == sd.fwd && ad.u5 == sd.u5; break;
                 case CL_X3: ok &= ad.kind == K_EXON && (ad.ek == E_SINGLE || ad.ek == E_TERMINAL); break;
                 default: ok &= ad.kind == K_EXON && (ad.ek == E_RSINGLE || ad.ek == E_RINITIAL);
                 }

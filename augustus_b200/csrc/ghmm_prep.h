@@ -34,7 +34,7 @@ struct WinLayout {
     size_t aint, useg, tssF, tssR, ttsF, ttsR; int utr, ncl, nchain;      /* UTR models only */
     size_t ev, evstart, cl[NCL], cp[NCHAIN], outs;           /* dynamic (sweep) */
     size_t snip_head, snip_pool, snip_stack; int snip_cap;
-    size_t evF, clF, fcp; int fcp_cap;                       /* forward pass (0 capacity when not requested) */
+    size_t evF, clF, clG, fcp; int fcp_cap;                       /* forward pass (0 capacity when not requested) */
     size_t opt, sorted, s_begin, s_end, s_type, s_trunc, s_count, s_logp; int opt_cap, samp_cap, nsamp;   /* sampling */
     size_t path_begin, path_end, path_type, path_trunc;      /* backtrace output */
     size_t total, slab;
@@ -68,7 +68,7 @@ inline WinLayout make_layout(int L, int C, bool generous = false, bool forward =
     for (int i = 0; i < NCL; i++) w.cl[i] = take(i < w.ncl ? (size_t)w.cl_cap * sizeof(Cand) : 0);
     for (int i = 0; i < NCHAIN; i++) w.cp[i] = take(i < w.nchain ? (size_t)w.cp_cap * sizeof(ChainCP) : 0);
     w.fcp_cap = forward ? (generous ? L + 64 : L / 2 + 64) : 0;
-    w.evF = take(forward ? (size_t)w.ev_cap * 8 : 0); w.clF = take(forward ? (size_t)w.ncl * w.cl_cap * 8 : 0);
+    w.evF = take(forward ? (size_t)w.ev_cap * 8 : 0); w.clF = take(forward ? (size_t)w.ncl * w.cl_cap * 8 : 0); w.clG = take(forward && utr ? (size_t)w.ncl * w.cl_cap * 8 : 0);
     w.fcp = take((size_t)w.nchain * w.fcp_cap * sizeof(FChainCP));
     w.nsamp = forward ? nsamp : 0;
     w.opt_cap = w.nsamp ? w.cl_cap + 1024 : 0; w.samp_cap = w.nsamp ? (generous ? w.nsamp * (L / 8 + 64) : w.nsamp * 160 + L / 4) : 0;
@@ -95,7 +95,7 @@ AUGB_HD WinView make_view(char* base, const WinLayout& lay, int L, int classmask
     v.tssF = (const sc_t*)(base + lay.tssF); v.tssR = (const sc_t*)(base + lay.tssR); v.ttsF = (const sc_t*)(base + lay.ttsF); v.ttsR = (const sc_t*)(base + lay.ttsR);
     v.ev = (Event*)(base + lay.ev); v.evstart = (int32_t*)(base + lay.evstart);
     v.cl0 = (Cand*)(base + lay.cl[0]); v.cp0 = (ChainCP*)(base + lay.cp[0]);
-    v.evF = (double*)(base + lay.evF); v.clF0 = (double*)(base + lay.clF); v.fcp0 = (FChainCP*)(base + lay.fcp); v.fcp_cap = lay.fcp_cap; v.fcp_stride = lay.fcp_cap;
+    v.evF = (double*)(base + lay.evF); v.clF0 = (double*)(base + lay.clF); v.clG0 = (sc_t*)(base + lay.clG); v.fcp0 = (FChainCP*)(base + lay.fcp); v.fcp_cap = lay.fcp_cap; v.fcp_stride = lay.fcp_cap;
     v.snip_head = (SnipHead*)(base + lay.snip_head); v.snip_pool = (SnipEnt*)(base + lay.snip_pool); v.snip_stack = (SnipFrame*)(base + lay.snip_stack); v.snip_cap = lay.snip_cap;
     v.cl_stride = (int)((lay.cl[1] - lay.cl[0]) / sizeof(Cand)); v.cp_stride = (int)((lay.cp[1] - lay.cp[0]) / sizeof(ChainCP));
     WinOuts* o = (WinOuts*)(base + lay.outs);

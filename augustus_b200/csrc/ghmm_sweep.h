@@ -130,12 +130,13 @@ struct SweepT {
         if (lane == 0) ws->filled = upto;
         wsync();
     }
-    AUGB_D void cl_append(int list, int col, int state, sc_t V, double F) {       /* lane 0 only; caller syncs */
+    AUGB_D void cl_append(int list, int col, int state, sc_t V, double F, sc_t G = 0) {       /* lane 0 only; caller syncs */
         int n = ws->cl_n[list];
         if (n >= w.cl_cap) { ws->status = 8; return; }
-        Cand c; c.col = col; c.state = state; c.V = V; w.cl(list)[n] = c; ws->cl_n[list] = n + 1;
-        if (FWD) w.clF(list)[n] = F;
+        Cand c; c.col = col; c.state = state; c.V = V + G; w.cl(list)[n] = c; ws->cl_n[list] = n + 1;
+        if (FWD) { w.clF(list)[n] = F; if (UTR && list >= NCL_BASE) w.clG(list)[n] = G; }
     }
+    AUGB_D const sc_t* usegp(int g) const { return w.useg + (size_t)g * (size_t)(L + 1); }
     /* a cell (j, s) whose state has a one-base transition into a self-loop chain: candidate for column j+1 of that chain,
      * in tilde coordinates (lane 0 only) */
     AUGB_D void feed_chain(int j, int s, sc_t V, double F) {
@@ -170,8 +171,8 @@ struct SweepT {
                     else cl_append(CL_RA + sd.frame, j, s, V, F);
                 } else if (UTR && sd.kind == K_EXON) {
                     /* cells the 3' UTR (forward) / 5' UTR (reverse) states look back to */
-                    if (sd.ek == E_SINGLE || sd.ek == E_TERMINAL) cl_append(CL_X3, j, s, V, F);
-                    else if (sd.ek == E_RSINGLE || sd.ek == E_RINITIAL) cl_append(CL_XR, j, s, V, F);
+                    if (sd.ek == E_SINGLE || sd.ek == E_TERMINAL) cl_append(CL_X3, j, s, V, F, -usegp(US_3)[j]);
+                    else if (sd.ek == E_RSINGLE || sd.ek == E_RINITIAL) { cl_append(CL_XRS, j, s, V, F, -usegp(US_RINIT5)[j]); cl_append(CL_XRT, j, s, V, F, -usegp(US_R5)[j]); }
                 }
                 feed_chain(j, s, V, F);
             }
@@ -792,20 +793,31 @@ struct SweepT {
      *   - predecessor = coding exon cells (3' UTR after terminal / single, reverse 5' UTR after rinitial / rsingle): the cells.
      * Content products are differences of the SegProbs-style cumulative sums written by the prep pass (WinView::useg).
      * UTR intron states are one-base self-loop states: four more lazily evaluated chains. */
-    AUGB_D void site_append(int list, int ch, int j) {
+    /* site at column j (first base of the begin signal): g = signal score - cumulative content sum at beginOfMiddle - 1 */
+    AUGB_D void site_append(int list, int list2, int ch, int j, sc_t sigv, int seg, int seg2, int bom_off) {
         const int cs = m->chain_state[ch];
         if (cs < 0) return;
         const sc_t v = chain_value(ch, j - 1);
         if (isneg(v)) return;
         const double f = FWD ? chain_fvalue(ch, j - 1) : 0.0;
-        if (lane == 0) cl_append(list, j - 1, cs, v, f);
+        if (lane == 0) {
+            cl_append(list, j - 1, cs, v, f, sigv - usegp(seg)[j + bom_off - 1]);
+            if (list2 >= 0) cl_append(list2, j - 1, cs, v, f, sigv - usegp(seg2)[j + bom_off - 1]);
+        }
         wsync();
     }
     AUGB_D void utr_begins(int j, unsigned mb) {
-        if (mb & MB_TSSB) site_append(CL_T5, 0, j);
-        if (mb & MB_RTTSB) site_append(CL_TR, 0, j);
-        if (mb & MB_ASSB) { site_append(CL_A5, CH_UTR + 0, j); site_append(CL_A3, CH_UTR + 1, j); }
-        if (mb & MB_RDSSB) { site_append(CL_R5, CH_UTR + 2, j); site_append(CL_R3, CH_UTR + 3, j); }
+        const int dssw = m->dss_start + m->dss_end + 2, assw = m->ass_start + m->ass_end + 2;
+        if (mb & MB_TSSB) site_append(CL_T5, -1, 0, j, w.tssF[j], US_INIT5, 0, m->tuw + m->tss_end);
+        if (mb & MB_RTTSB) site_append(CL_TR, -1, 0, j, w.ttsR[j + m->dpc], US_R3, 0, m->boxlen + m->dpc);
+        if (mb & MB_ASSB) {
+            const sc_t sv = sig(SG_ASSF, j + assw + m->ass_up - 1);
+            site_append(CL_A5, -1, CH_UTR + 0, j, sv, US_5, 0, m->ass_up + assw); site_append(CL_A3, -1, CH_UTR + 1, j, sv, US_3, 0, m->ass_up + assw);
+        }
+        if (mb & MB_RDSSB) {
+            const sc_t sv = sig(SG_DSSR, j + dssw - 1);
+            site_append(CL_R5I, CL_R5N, CH_UTR + 2, j, sv, US_RINIT5, US_R5, dssw); site_append(CL_R3, -1, CH_UTR + 3, j, sv, US_R3, 0, dssw);
+        }
     }
     AUGB_DN void utr_eval(int s, int j) {
         const StateDesc& st = m->st[s]; const UtrDesc& u = m->ud[st.ek];
@@ -844,23 +856,19 @@ struct SweepT {
                 const Cand c = cl[i]; eop = c.col;
                 if (eop < lm) below = true;
                 else if (eop <= rm) {
-                    a = c.state; pv = c.V;
+                    /* c.V = V[eop][a] + g: the begin signal and the content sum up to the middle part are already in (site_append / emit) */
+                    a = c.state;
                     const sc_t t = TR(a, s);
                     const int b = eop + 1, bom = b + u.bom_off, bobe = b + u.bobe_off, len = eobe - bobe + 1, mlen = eom - bom + 1;
-                    sc_t bp = 0;
-                    switch (u.begsig) {
-                    case BS_TSSF: bp = w.tssF[b]; break;
-                    case BS_ASSF: { int jj = b + assw + m->ass_up - 1; bp = (jj < L && bobe < L) ? sig(SG_ASSF, jj) : SC_NEG; break; }
-                    case BS_DSSR: { int jj = b + dssw - 1; bp = jj < L ? sig(SG_DSSR, jj) : SC_NEG; break; }
-                    case BS_TTSR: bp = w.ttsR[b + m->dpc]; break;
-                    default: break;
-                    }
-                    if (!isneg(t) && !isneg(bp) && len >= 0 && len < nld) {
+                    if (!isneg(t) && len >= 0 && len < nld) {
                         const sc_t lp = ld[len];
-                        sc_t mid;
-                        if (mlen >= 0 || u.shortrule == 0) mid = bom > eom ? 0 : cumE - (bom < 1 ? 0 : cum[bom - 1]);
-                        else mid = shortfac * (sc_t)(-mlen);
-                        if (!isneg(lp)) { te = t + ((bp + mid + lp) + ep); valid = true; if (FWD) pf = w.clF(u.list)[i]; }
+                        sc_t mid;                                  /* content of the middle part + cum[bom - 1] */
+                        if (mlen >= 0) mid = cumE;
+                        else mid = cum[bom - 1] + (u.shortrule ? shortfac * (sc_t)(-mlen) : (sc_t)0);
+                        if (!isneg(lp)) {
+                            te = t + ((mid + lp) + ep); valid = true;
+                            if (FWD) { const sc_t g = w.clG(u.list)[i]; pf = w.clF(u.list)[i]; pv = c.V - g; te += g; } else pv = c.V;
+                        }
                     }
                 }
             }
@@ -998,8 +1006,8 @@ struct SweepT {
                 const StateDesc& sd = m->st[s];
                 if (lane == 0 && sd.kind == K_LONGDSS && sd.fwd) cl_append(CL_LD + sd.frame, 0, s, v, sc2d(v));
                 if (lane == 0 && sd.kind == K_LONGASS && !sd.fwd) cl_append(CL_RA + sd.frame, 0, s, v, sc2d(v));
-                if (UTR && lane == 0 && sd.kind == K_EXON && (sd.ek == E_SINGLE || sd.ek == E_TERMINAL)) cl_append(CL_X3, 0, s, v, sc2d(v));
-                if (UTR && lane == 0 && sd.kind == K_EXON && (sd.ek == E_RSINGLE || sd.ek == E_RINITIAL)) cl_append(CL_XR, 0, s, v, sc2d(v));
+                if (UTR && lane == 0 && sd.kind == K_EXON && (sd.ek == E_SINGLE || sd.ek == E_TERMINAL)) cl_append(CL_X3, 0, s, v, sc2d(v), -usegp(US_3)[0]);
+                if (UTR && lane == 0 && sd.kind == K_EXON && (sd.ek == E_RSINGLE || sd.ek == E_RINITIAL)) { cl_append(CL_XRS, 0, s, v, sc2d(v), -usegp(US_RINIT5)[0]); cl_append(CL_XRT, 0, s, v, sc2d(v), -usegp(US_R5)[0]); }
                 if (lane == 0 && !alln) feed_chain(0, s, v, sc2d(v));
                 wsync();
             }
