@@ -81,7 +81,7 @@ static int upload_windows(augb200_model* M, const augb200_window* w, const int* 
         const augb200_window& x = w[idx[i]];
         dna_bytes += (size_t)((x.length + 15) & ~15);
         if (x.gc_class) gc_bytes += (size_t)((x.length + 15) & ~15);
-        arena += make_layout(x.length, M->hm.dm.C, generous, M->nsamp > 0, M->nsamp, M->hm.dm.utr != 0).total;
+        arena += make_layout(x.length, M->hm.dm.C, generous, M->nsamp > 0, M->nsamp, M->hm.dm.utr != 0, M->hm.dm.softmask != 0).total;
     }
     int rc;
     if ((rc = M->h_dna.reserve(dna_bytes + 16))) return rc;
@@ -104,7 +104,7 @@ static int upload_windows(augb200_model* M, const augb200_window* w, const int* 
     for (int i = 0; i < count; i++) {
         const augb200_window& x = w[idx[i]];
         WinDev& d = M->h_wins.p[i];
-        d.L = x.length; d.lay = make_layout(x.length, M->hm.dm.C, generous, M->nsamp > 0, M->nsamp, M->hm.dm.utr != 0);
+        d.L = x.length; d.lay = make_layout(x.length, M->hm.dm.C, generous, M->nsamp > 0, M->nsamp, M->hm.dm.utr != 0, M->hm.dm.softmask != 0);
         d.base = M->d_arena.p + oa; oa += d.lay.total;
         memcpy(M->h_dna.p + od, x.dna, x.length);
         d.dna = M->d_dna.p + od; od += (size_t)((x.length + 15) & ~15);
@@ -312,7 +312,7 @@ static int decode_batch_impl(augb200_model* M, int32_t n, const augb200_window* 
         while (first < order.size()) {
             size_t bytes = 0; int count = 0;   /* greedy sub-batch under the arena budget */
             while (first + count < order.size()) {
-                size_t t = make_layout(w[order[first + count]].length, M->hm.dm.C, generous, M->nsamp > 0, M->nsamp, M->hm.dm.utr != 0).total;
+                size_t t = make_layout(w[order[first + count]].length, M->hm.dm.C, generous, M->nsamp > 0, M->nsamp, M->hm.dm.utr != 0, M->hm.dm.softmask != 0).total;
                 if (count && bytes + t > M->arena_budget - M->arena_budget / 8) break;
                 bytes += t; count++;
             }
@@ -349,7 +349,7 @@ int augb200_stage_batch(augb200_model* M, int32_t n, const augb200_window* w) {
     if (!M) return AUGB200_ERR_BAD_ARG;
     int rc = check_windows(n, w); if (rc) return rc;
     CK(cudaSetDevice(M->device));
-    size_t bytes = 0; for (int i = 0; i < n; i++) bytes += make_layout(w[i].length, M->hm.dm.C, false, false, 0, M->hm.dm.utr != 0).total;
+    size_t bytes = 0; for (int i = 0; i < n; i++) bytes += make_layout(w[i].length, M->hm.dm.C, false, false, 0, M->hm.dm.utr != 0, M->hm.dm.softmask != 0).total;
     if (bytes > M->arena_budget - M->arena_budget / 8) return AUGB200_ERR_CAPACITY;
     std::vector<int> order(n);
     for (int i = 0; i < n; i++) order[i] = i;

@@ -130,6 +130,8 @@ struct DevModel {
     sc_t ochre, amber, opal, probN, log025, log3, ass_invalid_pat;
     double centroids[MAXC * 4 * 4][4];
     double wm[4][4];
+    /* softmasking (extrinsicinfo.cc:1696-1724): every lower-case run of the input is a nonexonpart hint; ln of its bonus */
+    int softmask; sc_t nep_bonus;
     /* ---- UTR states (UtrModel), only when utr != 0 ---- */
     int utr;
     int tuw, tss_start, tss_end, tata_start, tata_end, d_tata_min, d_tata_max, tssup_k, dpc, boxlen, tts_spacing;
@@ -205,6 +207,7 @@ struct WinView {
     /* UTR models: intron emission prefix of the UTR-intron chains [L], SegProbs cumulative sums [NUSEG][L+1], TSS / TTS scores */
     const sc_t *AINT, *useg, *tssF, *tssR, *ttsF, *ttsR;     /* tss*[L] by left end of the window, tts*[L+1] by first base of the polyA box */
     const int32_t *nsf, *nsr;  /* nearestStopForward / Reverse (exonmodel.cc:101-156) */
+    const int32_t* pmask;      /* softmasking models: number of lower-case input bases before position i, [L+1] */
     Event* ev; int32_t* evstart;
     Cand* cl0; ChainCP* cp0;   /* list i / chain i start at cl0 + i*cl_stride, cp0 + i*cp_stride (no pointer tables: those end up in local memory) */
     int cl_stride, cp_stride;

@@ -133,6 +133,12 @@ __global__ void __launch_bounds__(PREP_BS) k_prep(const WinDev* __restrict__ win
         __syncthreads();
         { bool any = false; for (int i = threadIdx.x; i < L; i += PREP_BS) { uint8_t c = base_code(wd.dna[i]); code[i] = c; any |= c < 4; } if (any) s_anynuc = 1; }
         __syncthreads();
+        int32_t* pmask = (int32_t*)(base + lay.pmask);
+        if (lay.softmask) {         /* lower-case input bases = soft-masked (SequenceFeatureCollection::prepare, extrinsicinfo.cc:1696-1724) */
+            if (threadIdx.x == 0) pmask[0] = 0;
+            block_scan_gen<int>([&](int i) { char ch = wd.dna[i]; return (ch >= 'a' && ch <= 'z') ? 1 : 0; }, pmask + 1, L, 0, sm32);
+            __syncthreads();
+        }
         const bool anynuc = s_anynuc != 0;
         Seq s; s.c = code; s.L = L;
         {
@@ -239,7 +245,7 @@ __global__ void __launch_bounds__(PREP_BS) k_prep(const WinDev* __restrict__ win
             }
             sc_t* aint = (sc_t*)(base + lay.aint);
             if (threadIdx.x == 0) aint[0] = 0;
-            block_scan_gen<sc_t>([&](int i) { return intron_emi1(m, s, gc[i + 1], i + 1); }, aint + 1, L - 1, (sc_t)0, sm64);
+            block_scan_gen<sc_t>([&](int i) { return intron_emi1(m, s, gc[i + 1], i + 1) + nep_term(m, pmask, i + 1); }, aint + 1, L - 1, (sc_t)0, sm64);
         }
         /* ---- prefix sums ---- */
         if (threadIdx.x == 0) {
@@ -270,8 +276,8 @@ __global__ void __launch_bounds__(PREP_BS) k_prep(const WinDev* __restrict__ win
         }
         sc_t* aig = (sc_t*)(base + lay.aig); sc_t* ageo = (sc_t*)(base + lay.ageo);
         if (threadIdx.x == 0) { aig[0] = 0; ageo[0] = 0; }
-        block_scan_gen<sc_t>([&](int i) { return anynuc ? aig_term(m, s, gc, i + 1) : m->log025; }, aig + 1, L - 1, (sc_t)0, sm64);
-        block_scan_gen<sc_t>([&](int i) { return ageo_term(m, s, gc, i + 1); }, ageo + 1, L - 1, (sc_t)0, sm64);
+        block_scan_gen<sc_t>([&](int i) { return anynuc ? aig_term(m, s, gc, i + 1, pmask) : m->log025; }, aig + 1, L - 1, (sc_t)0, sm64);
+        block_scan_gen<sc_t>([&](int i) { return ageo_term(m, s, gc, i + 1, pmask); }, ageo + 1, L - 1, (sc_t)0, sm64);
         /* ---- ORF tables ---- */
         int32_t* nsf = (int32_t*)(base + lay.nsf); int32_t* nsr = (int32_t*)(base + lay.nsr);
         for (int i = threadIdx.x; i < L + 3; i += PREP_BS) { nsf[i] = 0; nsr[i] = 0; }

@@ -85,6 +85,10 @@ int HostModel::build(const void* blob, size_t nbytes) {
     if (nbins > 0) { err = "TRANSINITBIN models are not supported yet"; return AUGB200_ERR_UNSUPPORTED; }
     if (nc) { err = "nc state models are not supported yet"; return AUGB200_ERR_UNSUPPORTED; }
     m.utr = utr ? 1 : 0;
+    if (r.b.find("softmasking")) {          /* blobs written before softmasking support carry no entry: off */
+        m.softmask = r.i32("softmasking") ? 1 : 0; m.nep_bonus = quantize(r.f64("softmask_bonus"));
+        if (m.softmask && !r.i32("extrinsic_malus_all_one")) { err = "extrinsic configurations with a malus are not supported"; return AUGB200_ERR_UNSUPPORTED; }
+    }
     m.dStateLen = m.d - 2 - m.dss_end - m.ass_start - 2 - m.ass_up;     /* intronmodel.cc:519-520 */
     if (m.dStateLen < 1) { err = "d too small"; return AUGB200_ERR_UNSUPPORTED; }
 

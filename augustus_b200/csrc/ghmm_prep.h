@@ -32,6 +32,7 @@ struct WinOuts {
 struct WinLayout {
     size_t code, gc, mask, kf, kr, parr, sig, aig, ageo, nsf, nsr;        /* static (prep) */
     size_t aint, useg, tssF, tssR, ttsF, ttsR; int utr, ncl, nchain;      /* UTR models only */
+    size_t pmask; int softmask;                                           /* softmasking models only */
     size_t ev, evstart, cl[NCL], cp[NCHAIN], outs;           /* dynamic (sweep) */
     size_t snip_head, snip_pool, snip_stack; int snip_cap;
     size_t evF, clF, clG, fcp; int fcp_cap;                       /* forward pass (0 capacity when not requested) */
@@ -45,7 +46,7 @@ AUGB_HD size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
  * cell per state; a candidate list gets at most one entry per column); the default sizes are ~3x what human-like
  * DNA needs (measured: 1.9 events, 0.03 list entries per base) and a window that overflows them is reported with
  * status AUGB200_ERR_CAPACITY and decoded again with the generous layout (augb200.cu: decode_batch). */
-inline WinLayout make_layout(int L, int C, bool generous = false, bool forward = false, int nsamp = 0, bool utr = false) {
+inline WinLayout make_layout(int L, int C, bool generous = false, bool forward = false, int nsamp = 0, bool utr = false, bool softmask = false) {
     WinLayout w; size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = al16(o + bytes); return r; };
     w.code = take(L); w.gc = take(L); w.mask = take((size_t)L * sizeof(mask_t)); w.kf = take((size_t)L * 2); w.kr = take((size_t)L * 2);
@@ -57,6 +58,7 @@ inline WinLayout make_layout(int L, int C, bool generous = false, bool forward =
     w.sig = take((size_t)NSIG * L * sizeof(sc_t));
     w.aig = take((size_t)L * sizeof(sc_t)); w.ageo = take((size_t)L * sizeof(sc_t));
     w.nsf = take((size_t)(L + 3) * 4); w.nsr = take((size_t)(L + 3) * 4);
+    w.softmask = softmask ? 1 : 0; w.pmask = take(softmask ? (size_t)(L + 1) * 4 : 0);
     w.utr = utr ? 1 : 0; w.ncl = utr ? NCL : NCL_BASE; w.nchain = utr ? NCHAIN : CH_UTR;
     w.aint = take(utr ? (size_t)L * sizeof(sc_t) : 0); w.useg = take(utr ? (size_t)NUSEG * (L + 1) * sizeof(sc_t) : 0);
     w.tssF = take(utr ? (size_t)L * sizeof(sc_t) : 0); w.tssR = take(utr ? (size_t)L * sizeof(sc_t) : 0);
@@ -91,6 +93,7 @@ AUGB_HD WinView make_view(char* base, const WinLayout& lay, int L, int classmask
     v.kf = (const uint16_t*)(base + lay.kf); v.kr = (const uint16_t*)(base + lay.kr);
     v.sig = (const sc_t*)(base + lay.sig); v.AIG = (const sc_t*)(base + lay.aig); v.AGEO = (const sc_t*)(base + lay.ageo);
     v.nsf = (const int32_t*)(base + lay.nsf); v.nsr = (const int32_t*)(base + lay.nsr);
+    v.pmask = (const int32_t*)(base + lay.pmask);
     v.AINT = (const sc_t*)(base + lay.aint); v.useg = (const sc_t*)(base + lay.useg);
     v.tssF = (const sc_t*)(base + lay.tssF); v.tssR = (const sc_t*)(base + lay.tssR); v.ttsF = (const sc_t*)(base + lay.ttsF); v.ttsR = (const sc_t*)(base + lay.ttsR);
     v.ev = (Event*)(base + lay.ev); v.evstart = (int32_t*)(base + lay.evstart);
@@ -164,15 +167,17 @@ inline void gc_stairs_seq(const DevModel* m, const uint8_t* c, int n, uint8_t* i
 }
 
 /* per-position addends of the scanned arrays */
-AUGB_HD sc_t aig_term(const DevModel* m, const Seq& s, const uint8_t* gc, int j) {      /* j >= 1 */
+/* softmasking bonus of position j (ln; 0 when the base is not masked) */
+AUGB_HD sc_t nep_term(const DevModel* m, const int32_t* pmask, int j) { return (m->softmask && pmask[j + 1] != pmask[j]) ? m->nep_bonus : (sc_t)0; }
+AUGB_HD sc_t aig_term(const DevModel* m, const Seq& s, const uint8_t* gc, int j, const int32_t* pmask = nullptr) {      /* j >= 1 */
     int c = gc[j], ig = m->chain_state[0];
-    return m->trans[((size_t)c * m->S + ig) * m->S + ig] + igenic_emi(m, s, c, j);
+    return m->trans[((size_t)c * m->S + ig) * m->S + ig] + igenic_emi(m, s, c, j) + nep_term(m, pmask, j);
 }
-AUGB_HD sc_t ageo_term(const DevModel* m, const Seq& s, const uint8_t* gc, int j) {     /* j >= 1 */
+AUGB_HD sc_t ageo_term(const DevModel* m, const Seq& s, const uint8_t* gc, int j, const int32_t* pmask = nullptr) {     /* j >= 1 */
     int c = gc[j]; int g = -1;
     for (int ch = 1; ch < CH_UTR; ch++) if (m->chain_state[ch] >= 0) { g = m->chain_state[ch]; break; }
     if (g < 0) return 0;
-    return m->trans[((size_t)c * m->S + g) * m->S + g] + intron_emi1(m, s, c, j);
+    return m->trans[((size_t)c * m->S + g) * m->S + g] + intron_emi1(m, s, c, j) + nep_term(m, pmask, j);
 }
 AUGB_HD sc_t parr_term(const DevModel* m, const Seq& s, int c, int which, int p) {
     switch (which) {
@@ -188,6 +193,8 @@ inline void prep_window_seq(const DevModel* m, const char* dna, int L, const int
                             char* pool = nullptr, size_t pool_size = 0, size_t* pool_used = nullptr) {
     uint8_t* code = (uint8_t*)(base + lay.code); uint8_t* gc = (uint8_t*)(base + lay.gc); mask_t* mask = (mask_t*)(base + lay.mask);
     for (int i = 0; i < L; i++) code[i] = base_code(dna[i]);
+    int32_t* pmask = (int32_t*)(base + lay.pmask);
+    if (lay.softmask) { pmask[0] = 0; for (int i = 0; i < L; i++) pmask[i + 1] = pmask[i] + (dna[i] >= 'a' && dna[i] <= 'z'); }
     if (gc_in) for (int i = 0; i < L; i++) gc[i] = (uint8_t)gc_in[i]; else gc_stairs_seq(m, code, L, gc);
     int cm = 0; bool anynuc = false;
     for (int i = 0; i < L; i++) { cm |= 1 << gc[i]; anynuc |= code[i] < 4; }
@@ -222,7 +229,7 @@ inline void prep_window_seq(const DevModel* m, const char* dna, int L, const int
             for (int i = 1; i <= L; i++) cum[i] = cum[i - 1] + useg_term(m, s, gc[i < L ? i : L - 1], g, i);
         }
         sc_t* aint = (sc_t*)(base + lay.aint); aint[0] = 0;
-        for (int j = 1; j < L; j++) aint[j] = aint[j - 1] + intron_emi1(m, s, gc[j], j);
+        for (int j = 1; j < L; j++) aint[j] = aint[j - 1] + intron_emi1(m, s, gc[j], j) + nep_term(m, pmask, j);
         const sc_t* sg = (const sc_t*)(base + lay.sig);
         if (anynuc) for (int j = 0; j < L; j++) mask[j] |= (mask_t)utr_column_mask(m, s, j, sg, tssF, tssR, ttsF, ttsR);
     }
@@ -244,7 +251,7 @@ inline void prep_window_seq(const DevModel* m, const char* dna, int L, const int
     }
     sc_t* aig = (sc_t*)(base + lay.aig); sc_t* ageo = (sc_t*)(base + lay.ageo);
     aig[0] = ageo[0] = 0;
-    for (int j = 1; j < L; j++) { aig[j] = aig[j - 1] + (anynuc ? aig_term(m, s, gc, j) : m->log025); ageo[j] = ageo[j - 1] + ageo_term(m, s, gc, j); }
+    for (int j = 1; j < L; j++) { aig[j] = aig[j - 1] + (anynuc ? aig_term(m, s, gc, j, pmask) : m->log025); ageo[j] = ageo[j - 1] + ageo_term(m, s, gc, j, pmask); }
     int32_t* nsf = (int32_t*)(base + lay.nsf); int32_t* nsr = (int32_t*)(base + lay.nsr);
     for (int i = 0; i < L + 3; i++) nsf[i] = nsr[i] = 0;
     for (int r = 0; r < 3; r++) {

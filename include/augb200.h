@@ -58,7 +58,9 @@ typedef struct augb200_model augb200_model;
 
 /* One sequence window = one call of NAMGene::viterbiAndForward. */
 typedef struct augb200_window {
-    const char*    dna;       /* ASCII, any case; anything but acgt/ACGT is an unknown base       */
+    const char*    dna;       /* ASCII; anything but acgt/ACGT is an unknown base.  Case matters only for models exported with
+                                  softmasking on: a lower-case base is soft-masked (SequenceFeatureCollection::prepare,
+                                  extrinsicinfo.cc:1696-1724) and gets the nonexonpart bonus in every non-exon state */
     int32_t        length;    /* number of bases, 2 .. AUGB200_MAX_WINDOW                          */
     const int32_t* gc_class;  /* optional: ContentStairs::idx[] (motif.cc:543-614), one class per  */
                               /* base; NULL = computed on the device with the same rule            */

@@ -142,13 +142,27 @@ static void export_motif(BlobWriter& bw, const char* name, Motif* arr, int C) {
     std::string s(name); bw.scalar_i((s + "_n").c_str(), n); bw.scalar_i((s + "_k").c_str(), k);
 }
 
-static void export_params(NAMGene& ng, const char* fn) {
+static void export_params(NAMGene& ng, const char* fn, FeatureCollection& fc) {
     BlobWriter bw;
     const int S = ng.statecount, C = Constant::decomp_num_steps;
     bw.scalar_i("statecount", S);
     bw.scalar_i("num_gc_classes", C);
     bw.scalar_i("synchstate", Properties::getIntProperty("/NAMGene/SynchState"));
     bw.scalar_i("utr_option_on", Constant::utr_option_on);
+    {   // softmasking (extrinsicinfo.cc:1696-1724): every lower-case run becomes a nonexonpart hint of source RM; with the default
+        // extrinsic.cfg its bonus (1.15) is the only factor different from 1 — every malus / local malus is 1
+        double lb = 0; int plain = 1;
+        if (Constant::softmasking) {
+            Feature rm(0, 0, nonexonpartF, bothstrands, -1, "RM");
+            rm.source = "softmask"; rm.feature = "nep"; rm.score = 0; rm.groupname = ""; rm.priority = -1; rm.mult = 1; rm.gradeclass = 0;
+            fc.setBonusMalus(rm);
+            lb = log(rm.bonus);
+            for (int t = 0; t < NUM_FEATURE_TYPES; t++) if (fc.typeInfo[t].malus != 1.0 || fc.typeInfo[t].localMalus != 1.0) plain = 0;
+        }
+        bw.scalar_i("softmasking", Constant::softmasking ? 1 : 0);
+        bw.scalar_f("softmask_bonus", lb);
+        bw.scalar_i("extrinsic_malus_all_one", plain);
+    }
     bw.scalar_i("nc_option_on", Constant::nc_option_on);
     bw.scalar_i("dss_gc_allowed", Constant::dss_gc_allowed);
     bw.scalar_i("dss_start", Constant::dss_start); bw.scalar_i("dss_end", Constant::dss_end);
@@ -354,7 +368,7 @@ int main(int argc, char* argv[]) {
         PP::initConstants();
         NAMGene namgene;
         StateModel::readAllParameters();
-        if (fparams) { export_params(namgene, fparams); }
+        if (fparams) { export_params(namgene, fparams, extrinsicFeatures); }
         if (!fpath && !fmat) return 0;
 
         FILE* fp = fpath ? fopen(fpath, "w") : NULL;

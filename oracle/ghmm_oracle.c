@@ -81,6 +81,7 @@ typedef struct {
     sc_t startp[64]; int isstop[64];
     sc_t ochre, amber, opal, probN, log025, log3;
     double centroids[64][4]; int ncent; double wm[4][4];
+    int softmask; sc_t nep_bonus;               /* softmasking: ln bonus of a nonexonpart hint of source RM (extrinsicinfo.cc:1696-1724) */
     /* UtrModel (utrmodel.cc), only with --UTR=on */
     int utr, utr_k, tssup_k, tss_start, tss_end, tata_start, tata_end, d_tata_min, d_tata_max, tuw, dpc, boxlen, tts_spacing;
     int umax, umax3s, umax3t;
@@ -97,6 +98,12 @@ static const augb200_blob_entry* bfind(const Blob* b, const char* name) {
     const augb200_blob_entry* e = (const augb200_blob_entry*)(b->buf + sizeof *h);
     for (uint32_t i = 0; i < h->n_entries; i++) if (!strcmp(e[i].name, name)) return &e[i];
     fprintf(stderr, "oracle: blob entry '%s' missing\n", name); exit(3);
+}
+static int bhas(const Blob* b, const char* name) {
+    const augb200_blob_header* h = (const augb200_blob_header*)b->buf;
+    const augb200_blob_entry* e = (const augb200_blob_entry*)(b->buf + sizeof *h);
+    for (uint32_t i = 0; i < h->n_entries; i++) if (!strcmp(e[i].name, name)) return 1;
+    return 0;
 }
 static int bint(const Blob* b, const char* name) { return *(const int32_t*)(b->buf + bfind(b, name)->offset); }
 static double bdbl(const Blob* b, const char* name) { return *(const double*)(b->buf + bfind(b, name)->offset); }
@@ -203,6 +210,8 @@ Model* orc_model_load(const char* path) {
     for (int i = 0; i < m->ncent; i++) for (int j = 0; j < 4; j++) m->centroids[i][j] = cen[4 * i + j];
     const double* w = bdarr(&b, "basecount_weight_matrix", NULL);
     for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) m->wm[i][j] = w[4 * i + j];
+    if (bhas(&b, "softmasking")) { m->softmask = bint(&b, "softmasking"); m->nep_bonus = q(bdbl(&b, "softmask_bonus")); }   /* absent in older blobs: off */
+    if (m->softmask && !bint(&b, "extrinsic_malus_all_one")) { fprintf(stderr, "oracle: extrinsic configurations with a malus are not restated\n"); return NULL; }
     m->utr = bint(&b, "utr_option_on");
     if (bint(&b, "nc_option_on")) { fprintf(stderr, "oracle: nc states not restated\n"); return NULL; }
     if (m->utr) {
@@ -261,6 +270,7 @@ typedef struct {
     struct Opt { int state, base; double lp; } *opts; int nopt, capopt;     /* OptionsList of the current sampling step */
     /* UtrModel per-sequence state */
     const char* raw;                            /* lower-case sequence (findTATA compares characters) */
+    int* pmask;                                 /* softmasking: pmask[i] = number of lower-case input bases before i; [L+1] */
     int cur_gc;                                 /* NAMGene::curGCIdx */
     int walking;                                /* 1 while backtracking / sampling (algovar doBacktracking / doSampling) */
     sc_t* seg[7];                               /* SegProbs::cumProds, [L+1], NEG = 0 = not computed */
@@ -272,6 +282,14 @@ typedef struct {
 
 static inline int at(const Ctx* x, int p) { return (p < 0 || p >= x->L) ? 5 : x->c[p]; }
 static inline int cmpl(int b) { return b < 4 ? 3 - b : b; }
+/* product of the nonexonpart bonuses over positions lo..hi (each lower-case run is one hint covering its positions; the runs are
+ * disjoint): the intronpart / nonexonpart loops of igenicmodel.cc:306-316, intronmodel.cc:1011-1036, utrmodel.cc:1143-1158,1521-1545 */
+static inline sc_t NB(const Ctx* x, int lo, int hi) {
+    if (!x->m->softmask) return 0;
+    if (lo < 0) lo = 0;
+    if (hi > x->L - 1) hi = x->L - 1;
+    return lo > hi ? 0 : x->m->nep_bonus * (sc_t)(x->pmask[hi + 1] - x->pmask[lo]);
+}
 /* Seq2Int::operator() over n bases starting at p (geneticcode.hh:166-173); -1 on invalid nucleotide */
 static int s2i(const Ctx* x, int p, int n) {
     int e = 0; for (int i = 0; i < n; i++) { int b = at(x, p + i); if (b > 3) return -1; e = (e << 2) | b; } return e;
@@ -536,7 +554,7 @@ static sc_t igenic_emi(const Ctx* x, int j) {
 }
 static void igenic_eval(Ctx* x, int s, int j, Oli* o) {
     const Model* m = x->m; const StateInfo* st = &m->st[s];
-    sc_t emi = igenic_emi(x, j);
+    sc_t emi = igenic_emi(x, j) + NB(x, j, j);
     /* max starts at -1 (igenicmodel.cc:238): the first ancestor is recorded even when every product is 0 */
     o->base = j - 1; o->max = NEG; o->state = st->nanc ? st->anc[0] : -1;
     for (int i = 0; i < st->nanc; i++) {
@@ -647,7 +665,7 @@ static void intron_eval(Ctx* x, int s, int j, Oli* o) {
             int ilen = eob - bob + 1;
             if (ilen > m->d || ilen < 0 || ilen >= m->n_ld_intron) continue;   /* > d only with hints */
             sc_t ld = m->ld_intron[ilen]; if (isneg(ld)) continue;
-            sc_t emi = ld + snip_get(x, !fwd, j, j - begin + 1);
+            sc_t emi = ld + snip_get(x, !fwd, j, j - begin + 1) + NB(x, begin, j);
             for (int i = 0; i < st->nanc; i++) {
                 int a = st->anc[i]; sc_t pv = PVAL(x, e, a); if (isneg(pv)) continue;
                 fwd_option(x, a, e, e, TR(a, s) + emi);
@@ -674,13 +692,16 @@ static void intron_eval(Ctx* x, int s, int j, Oli* o) {
     int any = 0;
     for (int i = 0; i < st->nanc; i++) if (!isneg(PVAL(x, eop, st->anc[i]))) { any = 1; break; }
     if (!any) return;
+    /* the part of [eop+1, j] that belongs to the intron gets the nonexonpart bonus (intronBegin / intronEnd, :873-922,1011-1032) */
+    int ib = eop + 1, ie = j;
     switch (st->kind) {
-    case K_LONGDSS: emi = dSSProb(x, j - dssw + 1, fwd); break;
+    case K_LONGDSS: emi = dSSProb(x, j - dssw + 1, fwd); if (fwd) ib = j - 2 - m->dss_end + 1; else ie = j - m->dss_start; break;
     case K_EQUALD: emi = intron_sum(x, 0, eop + 1, j); break;     /* forward k-mers also for requalD (:1046-1108) */
     case K_GEO: emi = intron_emi1(x, x->cls, j); break;           /* :895-915, forward k-mer also for rgeometric */
-    default: emi = aSSProb(x, j - assw - m->ass_up + 1, fwd);
+    default: emi = aSSProb(x, j - assw - m->ass_up + 1, fwd); if (fwd) ie = j - m->ass_end; else ib = eop + 1 + m->ass_end;
     }
     if (isneg(emi)) return;
+    emi += NB(x, ib, ie);
     o->base = eop;
     for (int i = 0; i < st->nanc; i++) {
         int a = st->anc[i]; sc_t pv = PVAL(x, eop, a); if (isneg(pv)) continue;
@@ -1112,7 +1133,7 @@ static sc_t utr_notEndPart(Ctx* x, const StateInfo* st, int begin, int endOfMidd
             sc_t e = pn < 0 ? m->log025 : m->iemi[((size_t)x->cls << (2 * (m->k + 1))) | pn];
             if (st->u5) middle += e; else middle = e;
         }
-        return middle;
+        return middle + NB(x, begin, endOfMiddle);                   /* :1521-1531 */
     }
     if (st->uk == U_INTRONVAR) return NEG;
     if (st->fwd && st->u5) {
@@ -1198,7 +1219,10 @@ static sc_t utr_notEndPart(Ctx* x, const StateInfo* st, int begin, int endOfMidd
         }
     }
     if (isneg(beginPart) || isneg(middle) || isneg(lenp)) return NEG;
-    return beginPart + middle + lenp;
+    /* intron positions in front of the biological exon (utrmodel.cc:1532-1545) */
+    sc_t nb = 0;
+    if ((st->fwd && (st->uk == U_INTERNAL || st->uk == U_TERM)) || (!st->fwd && (st->uk == U_INTERNAL || st->uk == U_INIT))) nb = NB(x, begin, bobe - 1);
+    return beginPart + middle + lenp + nb;
 }
 /* UtrModel::viterbiForwardAndSampling, utrmodel.cc:796-1064 */
 static void utr_eval(Ctx* x, int s, int j, Oli* o) {
@@ -1239,6 +1263,9 @@ static void utr_eval(Ctx* x, int s, int j, Oli* o) {
     sc_t ep = boe >= 0 ? utr_endPart(x, st, boe, base, eobe) : NEG;
     if (isneg(ep)) return;
     if (st->uk == U_INTRONVAR) return;
+    /* intron positions handled inside an exon state behind its biological end (utrmodel.cc:1143-1158) */
+    if (st->uk != U_INTRON && eobe < base && !(st->fwd && !st->u5 && (st->uk == U_SINGLE || st->uk == U_TERM)) && !(!st->fwd && st->u5 && (st->uk == U_SINGLE || st->uk == U_INIT)))
+        ep += NB(x, eobe + 1, base);
     if (st->fwd && st->u5 && (st->uk == U_SINGLE || st->uk == U_INIT)) { if (lm < -m->tuw) lm = -m->tuw; }
     else if (!st->fwd && !st->u5 && (st->uk == U_SINGLE || st->uk == U_TERM)) { if (lm < -m->boxlen - m->dpc) lm = -m->boxlen - m->dpc; }
     else if (lm < 0) lm = 0;
@@ -1358,6 +1385,8 @@ int orc_decode(const Model* m, const char* dna, int L, const int* gc_in, int64_t
     char* raw = (char*)malloc(L + 1);
     for (int i = 0; i < L; i++) raw[i] = (dna[i] >= 'A' && dna[i] <= 'Z') ? dna[i] + 32 : dna[i];
     raw[L] = 0; x->raw = raw; x->cur_gc = -1; x->walking = 0;
+    x->pmask = (int*)malloc((size_t)(L + 1) * sizeof(int)); x->pmask[0] = 0;
+    for (int i = 0; i < L; i++) x->pmask[i + 1] = x->pmask[i] + (dna[i] >= 'a' && dna[i] <= 'z');
     x->eop_off = getenv("ORC_EOP_OFF") != NULL;
     for (int g = 0; g < 2; g++) { x->assMemo[g] = (sc_t*)malloc((size_t)(L + 1) * sizeof(sc_t)); x->assMemoGen[g] = (int*)calloc(L + 1, sizeof(int)); }
     x->assGen = 1; x->assN = 0;
@@ -1484,7 +1513,7 @@ int orc_decode(const Model* m, const char* dna, int L, const int* gc_in, int64_t
         for (int s = 0; s < m->S; s++) free(x->eop[s].v);
         free(x->eop);
     }
-    free(raw); for (int g = 0; g < 2; g++) { free(x->assMemo[g]); free(x->assMemoGen[g]); }
+    free(raw); free(x->pmask); for (int g = 0; g < 2; g++) { free(x->assMemo[g]); free(x->assMemoGen[g]); }
     free(x->snF); free(x->snL); free(x->opts); free(x->F);
     free(x->V); free(x->nsf); free(x->nsr); free(gc); free(c);
     return ret;

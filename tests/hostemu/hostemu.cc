@@ -43,7 +43,7 @@ static int decode_impl(void* mp, const char* dna, int L, const int32_t* gc_in,
     WinLayout lay; std::vector<char> buf; char* base = nullptr; WinView v; WarpState ws; SW sw; WinOuts* outs = nullptr;
     std::vector<char> pool; size_t pool_used = 0;
     for (int pass = 0; pass < 2; pass++) {
-        lay = make_layout(L, m->C, pass == 1, false, 0, m->utr != 0);
+        lay = make_layout(L, m->C, pass == 1, false, 0, m->utr != 0, m->softmask != 0);
         buf.assign(lay.total + 64, 0);
         base = buf.data();
         int cm = 0;
@@ -85,7 +85,7 @@ static int forward_impl(void* mp, const char* dna, int L, const int32_t* gc_in, 
     WinLayout lay; std::vector<char> buf; char* base = nullptr; WinView v; WarpState ws; SW sw; WinOuts* outs = nullptr;
     std::vector<char> pool; size_t pool_used = 0;
     for (int pass = 0; pass < 2; pass++) {
-        lay = make_layout(L, m->C, pass == 1, true, 0, m->utr != 0);
+        lay = make_layout(L, m->C, pass == 1, true, 0, m->utr != 0, m->softmask != 0);
         buf.assign(lay.total + 64, 0);
         base = buf.data();
         int cm = 0;
@@ -112,7 +112,7 @@ static int sample_impl(void* mp, const char* dna, int L, const int32_t* gc_in, i
     WinLayout lay; std::vector<char> buf; char* base = nullptr; WinView v; WarpState ws; SW sw; WinOuts* outs = nullptr;
     std::vector<char> pool; size_t pool_used = 0;
     for (int pass = 0; pass < 2; pass++) {
-        lay = make_layout(L, m->C, pass == 1, true, 0, m->utr != 0);
+        lay = make_layout(L, m->C, pass == 1, true, 0, m->utr != 0, m->softmask != 0);
         buf.assign(lay.total + 64, 0);
         base = buf.data();
         int cm = 0;
