@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(PREP_BS) k_prep(const WinDev* __restrict__ win
         /* ---- signal scores of every column ---- */
         {
             sc_t* sg = (sc_t*)(base + lay.sig);
-            for (int idx = threadIdx.x; idx < NSIG * L; idx += PREP_BS) { int which = idx / L, j = idx - which * L; sg[idx] = anynuc ? signal_term(m, s, gc[j], which, j) : SC_NEG; }
+            for (int idx = threadIdx.x; idx < NSIG * L; idx += PREP_BS) { int which = idx / L, j = idx - which * L; sg[idx] = anynuc ? signal_term(m, s, gc[j], which, j, pmask) : SC_NEG; }
         }
         if (lay.utr) {
             /* ---- UTR models: TSS / TTS scores, UTR ends and begin-signal sites in the activity mask, SegProbs cumulative sums,
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(PREP_BS) k_prep(const WinDev* __restrict__ win
             for (int which = 0; which < PA_PER_CLASS; which++) {
                 sc_t* P = slab + (size_t)which * (size_t)(L + 1);
                 if (threadIdx.x == 0) P[0] = 0;
-                block_scan_gen<sc_t>([&](int p) { return parr_term(m, s, c, which, p); }, P + 1, L, (sc_t)0, sm64);
+                block_scan_gen<sc_t>([&](int p) { return parr_term(m, s, c, which, p, pmask); }, P + 1, L, (sc_t)0, sm64);
             }
         }
         sc_t* aig = (sc_t*)(base + lay.aig); sc_t* ageo = (sc_t*)(base + lay.ageo);

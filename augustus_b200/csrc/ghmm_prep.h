@@ -179,10 +179,11 @@ AUGB_HD sc_t ageo_term(const DevModel* m, const Seq& s, const uint8_t* gc, int j
     if (g < 0) return 0;
     return m->trans[((size_t)c * m->S + g) * m->S + g] + intron_emi1(m, s, c, j) + nep_term(m, pmask, j);
 }
-AUGB_HD sc_t parr_term(const DevModel* m, const Seq& s, int c, int which, int p) {
+/* intron content arrays carry the softmasking bonus of their position (lessD / equalD emissions are differences of them) */
+AUGB_HD sc_t parr_term(const DevModel* m, const Seq& s, int c, int which, int p, const int32_t* pmask = nullptr) {
     switch (which) {
-    case PA_PI: return intron_emi1(m, s, c, p);
-    case PA_PIR: return intron_emi1r(m, s, c, p);
+    case PA_PI: return intron_emi1(m, s, c, p) + nep_term(m, pmask, p);
+    case PA_PIR: return intron_emi1r(m, s, c, p) + nep_term(m, pmask, p);
     case PA_PX: case PA_PX + 1: case PA_PX + 2: return p >= m->k ? exon_emi1(m, s, m->xemi, c, 1, mod3(which - PA_PX + p), p) : 0;
     default: return exon_emi1(m, s, m->xemi, c, 0, mod3(which - PA_PXR - p), p);
     }
@@ -213,7 +214,7 @@ inline void prep_window_seq(const DevModel* m, const char* dna, int L, const int
     {
         sc_t* sg = (sc_t*)(base + lay.sig);
         for (int which = 0; which < NSIG; which++)
-            for (int j = 0; j < L; j++) sg[(size_t)which * L + j] = anynuc ? signal_term(m, s, gc[j], which, j) : SC_NEG;
+            for (int j = 0; j < L; j++) sg[(size_t)which * L + j] = anynuc ? signal_term(m, s, gc[j], which, j, pmask) : SC_NEG;
     }
     if (lay.utr) {
         /* UTR models: TSS / TTS scores, SegProbs cumulative sums, intron emission prefix of the UTR-intron chains, mask bits */
@@ -246,7 +247,7 @@ inline void prep_window_seq(const DevModel* m, const char* dna, int L, const int
         for (int which = 0; which < PA_PER_CLASS; which++) {
             sc_t* P = slab + (size_t)which * (size_t)(L + 1);
             P[0] = 0;
-            for (int p = 0; p < L; p++) P[p + 1] = P[p] + parr_term(m, s, c, which, p);
+            for (int p = 0; p < L; p++) P[p + 1] = P[p] + parr_term(m, s, c, which, p, pmask);
         }
     }
     sc_t* aig = (sc_t*)(base + lay.aig); sc_t* ageo = (sc_t*)(base + lay.ageo);

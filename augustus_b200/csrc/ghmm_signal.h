@@ -193,16 +193,29 @@ AUGB_HD unsigned utr_column_mask(const DevModel* m, const Seq& s, int j, const s
     return mb;
 }
 
-/* value of signal array `which` at column j */
-AUGB_HD sc_t signal_term(const DevModel* m, const Seq& sq, int cls, int which, int j) {
-    const int dssw = m->dss_start + m->dss_end + 2, assw = m->ass_start + m->ass_end + 2;
+/* softmasking: ln of the nonexonpart bonuses over positions lo..hi — every lower-case run of the input is one hint (disjoint), its
+ * bonus multiplies each covered intron position (intronmodel.cc:1011-1036, utrmodel.cc:1143-1158,1521-1545); pmask = prefix counts */
+AUGB_HD sc_t nep_range(const DevModel* m, const int32_t* pmask, int L, int lo, int hi) {
+    if (!m->softmask) return 0;
+    if (lo < 0) lo = 0;
+    if (hi > L - 1) hi = L - 1;
+    return lo > hi ? (sc_t)0 : m->nep_bonus * (sc_t)(pmask[hi + 1] - pmask[lo]);
+}
+/* value of signal array `which` at column j (defined as soon as the signal window starts at base >= 0; the intron states need one more
+ * column in front for their predecessor, Sweep::fixed_eval checks that).  With softmasking the bonus of the intron bases inside the signal window is part of
+ * the value: the window of a (r)longdss / (r)longass state ending at j and the window a UTR exon state begins or ends with cover the
+ * same intron bases (intronBegin / intronEnd of intronmodel.cc:873-922 = begin .. beginOfBioExon-1 / endOfBioExon+1 .. end of utrmodel.cc) */
+AUGB_HD sc_t signal_term(const DevModel* m, const Seq& sq, int cls, int which, int j, const int32_t* pmask = nullptr) {
+    const int dssw = m->dss_start + m->dss_end + 2, assw = m->ass_start + m->ass_end + 2, L = sq.L;
+    sc_t v; int lo = 0, hi = -1;
     switch (which) {
-    case SG_DSSF: return j - dssw >= 0 ? dSSProb(m, sq, j - dssw + 1, 1) : SC_NEG;
-    case SG_DSSR: return j - dssw >= 0 ? dSSProb(m, sq, j - dssw + 1, 0) : SC_NEG;
-    case SG_ASSF: return j - assw - m->ass_up >= 0 ? aSSProb(m, sq, cls, j - assw - m->ass_up + 1, 1) : SC_NEG;
-    case SG_ASSR: return j - assw - m->ass_up >= 0 ? aSSProb(m, sq, cls, j - assw - m->ass_up + 1, 0) : SC_NEG;
+    case SG_DSSF: v = j - dssw + 1 >= 0 ? dSSProb(m, sq, j - dssw + 1, 1) : SC_NEG; lo = j - 2 - m->dss_end + 1; hi = j; break;
+    case SG_DSSR: v = j - dssw + 1 >= 0 ? dSSProb(m, sq, j - dssw + 1, 0) : SC_NEG; lo = j - dssw + 1; hi = j - m->dss_start; break;
+    case SG_ASSF: v = j - assw - m->ass_up + 1 >= 0 ? aSSProb(m, sq, cls, j - assw - m->ass_up + 1, 1) : SC_NEG; lo = j - assw - m->ass_up + 1; hi = j - m->ass_end; break;
+    case SG_ASSR: v = j - assw - m->ass_up + 1 >= 0 ? aSSProb(m, sq, cls, j - assw - m->ass_up + 1, 0) : SC_NEG; lo = j - assw - m->ass_up + 1 + m->ass_end; hi = j; break;
     default: return rstart_endpart(m, sq, cls, j);
     }
+    return isneg(v) ? v : v + nep_range(m, pmask, L, lo, hi);
 }
 
 }  // namespace augb

@@ -136,14 +136,6 @@ struct SweepT {
         Cand c; c.col = col; c.state = state; c.V = V + G; w.cl(list)[n] = c; ws->cl_n[list] = n + 1;
         if (FWD) { w.clF(list)[n] = F; if (UTR && list >= NCL_BASE) w.clG(list)[n] = G; }
     }
-    /* softmasking: ln of the nonexonpart bonuses over positions lo..hi (disjoint lower-case runs, one hint each): the intronpart /
-     * nonexonpart loops of intronmodel.cc:1011-1036 and utrmodel.cc:1143-1158,1521-1545 */
-    AUGB_D sc_t NB(int lo, int hi) const {
-        if (!m->softmask) return 0;
-        if (lo < 0) lo = 0;
-        if (hi > L - 1) hi = L - 1;
-        return lo > hi ? (sc_t)0 : m->nep_bonus * (sc_t)(w.pmask[hi + 1] - w.pmask[lo]);
-    }
     AUGB_D const sc_t* usegp(int g) const { return w.useg + (size_t)g * (size_t)(L + 1); }
     /* a cell (j, s) whose state has a one-base transition into a self-loop chain: candidate for column j+1 of that chain,
      * in tilde coordinates (lane 0 only) */
@@ -598,10 +590,6 @@ struct SweepT {
         if (kind == K_LONGDSS) { eop = j - dssw; emi = sig(fwd ? SG_DSSF : SG_DSSR, j); }
         else { eop = j - assw - m->ass_up; emi = sig(fwd ? SG_ASSF : SG_ASSR, j); }
         if (eop < 0 || isneg(emi)) return;
-        if (m->softmask) {      /* intron part of the state (intronBegin / intronEnd, intronmodel.cc:873-922) */
-            if (kind == K_LONGDSS) emi += fwd ? NB(j - 2 - m->dss_end + 1, j) : NB(eop + 1, j - m->dss_start);
-            else emi += fwd ? NB(eop + 1, j - m->ass_end) : NB(eop + 1 + m->ass_end, j);
-        }
         AUGB_ROLLED
         for (int f = 0; f < 3; f++) {
             int s = kind == K_LONGDSS ? m->r_longdss[dir][f] : m->r_longass[dir][f];
@@ -632,7 +620,7 @@ struct SweepT {
             if (hi < 0 || cl[lo].col != want || s < 0) return;
             const sc_t* P = parr(cls, PA_PI);
             sc_t t = TR(cl[lo].state, s);
-            push_opt(lane == 0 && !isneg(t), w.clF(list)[lo] + sc2d(t + ((P[j + 1] - P[want + 1]) + NB(want + 1, j))), 0, cl[lo].state, want);
+            push_opt(lane == 0 && !isneg(t), w.clF(list)[lo] + sc2d(t + (P[j + 1] - P[want + 1])), 0, cl[lo].state, want);
             return;
         }
         Cand c = w.cl(list)[cur]; double cf = FWD ? w.clF(list)[cur] : 0.0;
@@ -642,7 +630,7 @@ struct SweepT {
         if (s < 0) return;
         int eop = j - m->dStateLen;
         const sc_t* P = parr(cls, PA_PI);                 /* forward k-mers also for requalD (intronmodel.cc:1046-1108) */
-        sc_t emi = (P[j + 1] - P[eop + 1]) + NB(eop + 1, j);
+        sc_t emi = P[j + 1] - P[eop + 1];
         sc_t t = TR(c.state, s);
         if (isneg(t)) return;
         emit(j, s, c.V + (t + emi), c.state, eop, cf + sc2d(t + emi));
@@ -774,7 +762,6 @@ struct SweepT {
                             if (!isneg(ld) && !isneg(t)) {
                                 /* seqProb is evaluated (and memoised) for every candidate that passes the site tests (:970-972) */
                                 sc_t seq = slow ? snip_get(dir, j, j - begin + 1) : P[j + 1] - P[begin];
-                                if (m->softmask) seq += NB(begin, j);
                                 sc_t sc = c.V + (t + (ld + seq));
                                 if (sc > best || (sc == best && e > bkey)) { best = sc; bkey = e; bpred = c.state; }
                                 if (FWD && !opt) fl.add(w.clF(list)[i] + sc2d(t + (ld + seq)));
@@ -823,13 +810,12 @@ struct SweepT {
         const int dssw = m->dss_start + m->dss_end + 2, assw = m->ass_start + m->ass_end + 2;
         if (mb & MB_TSSB) site_append(CL_T5, -1, 0, j, w.tssF[j], US_INIT5, 0, m->tuw + m->tss_end);
         if (mb & MB_RTTSB) site_append(CL_TR, -1, 0, j, w.ttsR[j + m->dpc], US_R3, 0, m->boxlen + m->dpc);
-        /* splice-site begins: the intron bases in front of the biological exon get the nonexonpart bonus (utrmodel.cc:1532-1545) */
         if (mb & MB_ASSB) {
-            const sc_t sv = sig(SG_ASSF, j + assw + m->ass_up - 1) + NB(j, j + m->ass_up + m->ass_start + 2 - 1);
+            const sc_t sv = sig(SG_ASSF, j + assw + m->ass_up - 1);
             site_append(CL_A5, -1, CH_UTR + 0, j, sv, US_5, 0, m->ass_up + assw); site_append(CL_A3, -1, CH_UTR + 1, j, sv, US_3, 0, m->ass_up + assw);
         }
         if (mb & MB_RDSSB) {
-            const sc_t sv = sig(SG_DSSR, j + dssw - 1) + NB(j, j + m->dss_end + 2 - 1);
+            const sc_t sv = sig(SG_DSSR, j + dssw - 1);
             site_append(CL_R5I, CL_R5N, CH_UTR + 2, j, sv, US_RINIT5, US_R5, dssw); site_append(CL_R3, -1, CH_UTR + 3, j, sv, US_R3, 0, dssw);
         }
     }
@@ -843,19 +829,17 @@ struct SweepT {
         sc_t ep;
         switch (u.endkind) {                                      /* UtrModel::endPartEmiProb, utrmodel.cc:1072-1110 */
         case UE_ATG: { ep = 0; if (eobe + 3 <= L - 1) { int c = sq.kmer_end(eobe + 3, 3); if (c < 0 || !m->isstart[c]) ep = SC_NEG; } break; }
-        case UE_DSSF: ep = boe < 0 ? SC_NEG : (j >= dssw ? sig(SG_DSSF, j) : dSSProb(m, sq, boe, 1)); break;
+        case UE_DSSF: ep = boe < 0 ? SC_NEG : sig(SG_DSSF, j); break;
         case UE_TTSF:
             if (last) {                                           /* right-truncated 3' UTR: no signal, tail of the single-exon length distribution */
                 ep = 0; boe = L; rm = u.begsig == BS_NONE ? j - 1 : j - assw - m->ass_up; ld = m->uld[9]; nld = m->n_uld[9];
             } else ep = (boe < 0 || boe + m->boxlen - 1 >= L) ? SC_NEG : w.ttsF[boe];
             break;
         case UE_TSSR: ep = boe < 0 ? SC_NEG : w.tssR[boe]; break;
-        case UE_ASSR: ep = boe < 0 ? SC_NEG : (j - assw - m->ass_up >= 0 ? sig(SG_ASSR, j) : aSSProb(m, sq, cls, boe, 0)); break;
+        case UE_ASSR: ep = boe < 0 ? SC_NEG : sig(SG_ASSR, j); break;
         default: ep = (j + 3 > L - 1 || !isRCStop(m, sq, j + 1)) ? SC_NEG : 0;
         }
         if (isneg(ep)) return;
-        /* intron bases behind the biological exon end that the state still covers (utrmodel.cc:1143-1158) */
-        if (m->softmask && eobe < j && u.endkind != UE_TTSF && u.endkind != UE_TSSR) ep += NB(eobe + 1, j);
         const int eom = boe - 1;                                  /* endOfMiddle */
         const sc_t* cum = w.useg + (size_t)u.seg * (size_t)(L + 1);
         const sc_t cumE = eom >= 0 ? cum[eom > L ? L : eom] : 0;
