@@ -68,6 +68,8 @@ struct augb200_model {
     int nsamp = 0;                       /* sampled paths per window of the current batch (0 = Viterbi only) */
     augb200_path* samples_out = nullptr;
     DevBuf<uint32_t> d_rng; size_t rng_n = 0;
+    uint64_t rand_pos = 0;               /* where in the rand() stream the windows of the next sampling call start */
+    int64_t rand_used0 = 0;              /* draws window 0 of the last sampling call consumed */
     DevBuf<SampHdr> d_shdr; PinBuf<SampHdr> h_shdr; DevBuf<int32_t> d_sstatus; PinBuf<int32_t> h_sstatus;
     DevBuf<int32_t> d_sbegin, d_send; DevBuf<uint8_t> d_stype, d_strunc; PinBuf<int32_t> h_sbegin, h_send; PinBuf<uint8_t> h_stype, h_strunc;
     int scap = 0;
@@ -134,9 +136,9 @@ static int upload_windows(augb200_model* M, const augb200_window* w, const int* 
         if ((rc = M->d_sbegin.reserve(M->scap)) || (rc = M->d_send.reserve(M->scap)) || (rc = M->d_stype.reserve(M->scap)) || (rc = M->d_strunc.reserve(M->scap))) return rc;
         if ((rc = M->h_sbegin.reserve(M->scap)) || (rc = M->h_send.reserve(M->scap)) || (rc = M->h_stype.reserve(M->scap)) || (rc = M->h_strunc.reserve(M->scap))) return rc;
         size_t nh = (size_t)count * M->nsamp;
-        if ((rc = M->d_shdr.reserve(nh)) || (rc = M->h_shdr.reserve(nh)) || (rc = M->d_sstatus.reserve(count)) || (rc = M->h_sstatus.reserve(count))) return rc;
+        if ((rc = M->d_shdr.reserve(nh)) || (rc = M->h_shdr.reserve(nh)) || (rc = M->d_sstatus.reserve(2 * (size_t)count)) || (rc = M->h_sstatus.reserve(2 * (size_t)count))) return rc;
         /* the rand() stream every window draws from: an unseeded reference process per window = glibc seed 1 */
-        size_t need = (size_t)M->nsamp * ((size_t)maxL + 2);
+        size_t need = (size_t)M->rand_pos + (size_t)M->nsamp * ((size_t)maxL + 2);
         if (need > M->rng_n) {
             std::vector<uint32_t> host(need);
             glibc_rand_stream(1, host.data(), need);
@@ -163,9 +165,10 @@ static int run_kernels(augb200_model* M, int count) {
     int gsweep = std::min((count + SWEEP_WARPS - 1) / SWEEP_WARPS, sms * bps);
     const bool utr = M->hm.dm.utr != 0;
     if (utr) gsweep = std::min(gsweep, sms * std::min(bps, 3));
-    const int nrng = (int)std::min<size_t>(M->rng_n, 0x7fffffff);
-    if (M->nsamp > 0 && utr) k_sweep_sample_utr<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(M->d_wins.p, count, M->d_counters.p, M->d_rng.p, nrng);
-    else if (M->nsamp > 0) k_sweep_sample<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(M->d_wins.p, count, M->d_counters.p, M->d_rng.p, nrng);
+    const int nrng = (int)std::min<size_t>(M->rng_n - std::min<size_t>(M->rng_n, M->rand_pos), 0x7fffffff);
+    const uint32_t* d_rng = M->d_rng.p ? M->d_rng.p + M->rand_pos : nullptr;
+    if (M->nsamp > 0 && utr) k_sweep_sample_utr<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(M->d_wins.p, count, M->d_counters.p, d_rng, nrng);
+    else if (M->nsamp > 0) k_sweep_sample<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(M->d_wins.p, count, M->d_counters.p, d_rng, nrng);
     else if (utr) k_sweep_utr<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(M->d_wins.p, count, M->d_counters.p);
     else k_sweep<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(M->d_wins.p, count, M->d_counters.p);
     CK(cudaEventRecord(M->ev1, M->stream));
@@ -195,7 +198,7 @@ static int fetch_results(augb200_model* M, int count, augb200_path* out, const i
     if (M->nsamp > 0 && M->samples_out) {
         size_t nh = (size_t)count * M->nsamp;
         CK(cudaMemcpyAsync(M->h_shdr.p, M->d_shdr.p, nh * sizeof(SampHdr), cudaMemcpyDeviceToHost, M->stream));
-        CK(cudaMemcpyAsync(M->h_sstatus.p, M->d_sstatus.p, (size_t)count * 4, cudaMemcpyDeviceToHost, M->stream));
+        CK(cudaMemcpyAsync(M->h_sstatus.p, M->d_sstatus.p, (size_t)count * 8, cudaMemcpyDeviceToHost, M->stream));
         int stot = std::min(M->h_counters.p[2], M->scap);
         if (stot > 0) {
             CK(cudaMemcpyAsync(M->h_sbegin.p, M->d_sbegin.p, (size_t)stot * 4, cudaMemcpyDeviceToHost, M->stream));
@@ -212,11 +215,12 @@ static int fetch_results(augb200_model* M, int count, augb200_path* out, const i
         for (int i = 0; i < count; i++)
             for (int k = 0; k < M->nsamp; k++) {
                 const SampHdr& h = M->h_shdr.p[(size_t)i * M->nsamp + k]; augb200_path& p = M->samples_out[(size_t)idx[i] * M->nsamp + k];
-                p.n = h.n; p.status = M->h_sstatus.p[i]; p.log_prob = h.logp;
+                p.n = h.n; p.status = M->h_sstatus.p[2 * i]; p.log_prob = h.logp;
                 p.begin = (const int32_t*)(uintptr_t)(sbase + h.offset);
             }
         /* a window whose sample buffers overflowed is decoded again as a whole */
-        for (int i = 0; i < count; i++) if (M->h_sstatus.p[i] == AUGB200_ERR_CAPACITY && out[idx[i]].status == 0) out[idx[i]].status = AUGB200_ERR_CAPACITY;
+        for (int i = 0; i < count; i++) if (M->h_sstatus.p[2 * i] == AUGB200_ERR_CAPACITY && out[idx[i]].status == 0) out[idx[i]].status = AUGB200_ERR_CAPACITY;
+        for (int i = 0; i < count; i++) if (idx[i] == 0) M->rand_used0 = M->h_sstatus.p[2 * i + 1];
     }
     float ms = 0; if (cudaEventElapsedTime(&ms, M->ev0, M->ev1) == cudaSuccess) M->sweep_ms += ms;
     /* append to the result store; pointers are fixed up by the caller once all sub-batches are in */
@@ -344,6 +348,13 @@ int augb200_decode_batch_sampling(augb200_model* M, int32_t n, const augb200_win
 }
 
 int augb200_decode(augb200_model* M, const augb200_window* w, augb200_path* out) { return augb200_decode_batch(M, 1, w, out); }
+
+int augb200_set_rand_position(augb200_model* M, uint64_t draws_consumed) {
+    if (!M || draws_consumed > ((uint64_t)1 << 31)) return AUGB200_ERR_BAD_ARG;
+    M->rand_pos = draws_consumed;
+    return AUGB200_OK;
+}
+int64_t augb200_last_rand_consumed(const augb200_model* M) { return M ? M->rand_used0 : 0; }
 
 int augb200_stage_batch(augb200_model* M, int32_t n, const augb200_window* w) {
     if (!M) return AUGB200_ERR_BAD_ARG;

@@ -13,7 +13,15 @@
 #define AUGB_HD __host__ __device__ __forceinline__
 #define AUGB_D __device__ __forceinline__
 #define AUGB_DN __device__ __noinline__      /* large routines: one copy in the kernel (instruction-cache footprint) */
+#define AUGB_HDN __host__ __device__ __noinline__
+#ifdef AUGB_VAR_EMIT_INLINE
+#define AUGB_EMIT __device__ __forceinline__
 #else
+#define AUGB_EMIT __device__ __noinline__
+#endif
+#else
+#define AUGB_HDN inline
+#define AUGB_EMIT inline
 #define AUGB_HD inline
 #define AUGB_D inline
 #define AUGB_DN inline
@@ -85,7 +93,11 @@ enum : unsigned {
 typedef uint32_t mask_t;
 
 /* prefix arrays per GC class, each (L+1) long: P[i+1] - P[l] = sum over positions l..i */
-enum : int { PA_PI = 0, PA_PIR = 1, PA_PX = 2 /* +phi */, PA_PXR = 5 /* +phi */, PA_PER_CLASS = 8 };
+/* per-class prefix arrays; the +phi families are 3-periodic content sums (term of position p uses reading frame mod3(phi + p)
+ * on the forward strand, mod3(phi - p) on the reverse strand).  XET / XIN = exon-terminal and initial content
+ * (ExonModel::eTermSeqProb / initialSeqProb, exonmodel.cc:1979-2034) so that the sweep never loops over positions */
+enum : int { PA_PI = 0, PA_PIR = 1, PA_PX = 2 /* +phi */, PA_PXR = 5 /* +phi */, PA_XET = 8 /* +phi */, PA_XETR = 11 /* +phi */,
+             PA_XIN = 14 /* +phi */, PA_XINR = 17 /* +phi */, PA_PER_CLASS = 20 };
 
 /* how one UTR exon state scores a (predecessor end, duration) candidate: UtrModel::notEndPartEmiProb (utrmodel.cc:1167-1405) as
  * begin signal + content prefix difference + length distribution, all table driven */

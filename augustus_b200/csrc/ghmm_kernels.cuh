@@ -291,7 +291,13 @@ __global__ void __launch_bounds__(PREP_BS) k_prep(const WinDev* __restrict__ win
 }
 
 /* ------------------------------------------------------------------ sweep kernel: one warp per window */
-constexpr int SWEEP_WARPS = 4;
+#ifndef AUGB_SWEEP_WARPS
+#define AUGB_SWEEP_WARPS 4
+#endif
+#ifndef AUGB_SWEEP_MINB
+#define AUGB_SWEEP_MINB 4
+#endif
+constexpr int SWEEP_WARPS = AUGB_SWEEP_WARPS;
 template <class SW>
 __device__ __forceinline__ void sweep_body(const WinDev* __restrict__ wins, int nwin, int* __restrict__ next) {
     const DevModel* m = &c_model;
@@ -309,7 +315,7 @@ __device__ __forceinline__ void sweep_body(const WinDev* __restrict__ wins, int 
         __syncwarp();
     }
 }
-__global__ void __launch_bounds__(SWEEP_WARPS * 32, 4) k_sweep(const WinDev* __restrict__ wins, int nwin, int* __restrict__ next) { sweep_body<Sweep>(wins, nwin, next); }
+__global__ void __launch_bounds__(SWEEP_WARPS * 32, AUGB_SWEEP_MINB) k_sweep(const WinDev* __restrict__ wins, int nwin, int* __restrict__ next) { sweep_body<Sweep>(wins, nwin, next); }
 /* models with UTR states (71 states, four more chains, eight more candidate lists) */
 __global__ void __launch_bounds__(SWEEP_WARPS * 32, 3) k_sweep_utr(const WinDev* __restrict__ wins, int nwin, int* __restrict__ next) { sweep_body<SweepUtr>(wins, nwin, next); }
 
@@ -340,7 +346,7 @@ __device__ __forceinline__ void sweep_sample_body(const WinDev* __restrict__ win
                 SampleOut so; so.cap = wd.lay.samp_cap;
                 so.begin = (int32_t*)(wd.base + wd.lay.s_begin); so.end = (int32_t*)(wd.base + wd.lay.s_end);
                 so.type = (uint8_t*)(wd.base + wd.lay.s_type); so.trunc = (uint8_t*)(wd.base + wd.lay.s_trunc);
-                so.count = (int32_t*)(wd.base + wd.lay.s_count); so.logp = (double*)(wd.base + wd.lay.s_logp); so.status = &outs->samp_status;
+                so.count = (int32_t*)(wd.base + wd.lay.s_count); so.logp = (double*)(wd.base + wd.lay.s_logp); so.status = &outs->samp_status; so.rand_used = &outs->rand_used;
                 sp.run(wd.lay.nsamp, so);
             }
         }
@@ -369,7 +375,7 @@ __global__ void k_pack_samples(const WinDev* __restrict__ wins, int nwin, SampHd
         if (!st) for (int k = 0; k < ns; k++) tot += cnt[k];
         int off = atomicAdd(total, tot);
         if (off + tot > ocap) { st = 8; tot = 0; }
-        wstatus[wi] = st; s_off = off; s_tot = tot;
+        wstatus[2 * wi] = st; wstatus[2 * wi + 1] = outs->rand_used; s_off = off; s_tot = tot;      /* (status, rand() draws consumed) per window */
         int o = off;
         for (int k = 0; k < ns; k++) { SampHdr h; h.n = st ? 0 : cnt[k]; h.offset = o; h.logp = st ? 0.0 : lp[k]; hdr[(size_t)wi * ns + k] = h; o += h.n; }
     }

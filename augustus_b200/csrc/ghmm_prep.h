@@ -25,6 +25,7 @@ namespace augb {
 struct WinOuts {
     int32_t n_ev, status, path_n, path_status; int32_t ncp[NCHAIN]; int32_t pad /* window flags */; sc_t score;
     int32_t nfcp[NCHAIN]; int32_t samp_status;
+    int32_t rand_used, pad2;    /* rand() draws the sampling walks of this window consumed */
     const sc_t* slab[MAXC];     /* prefix-array slab of each GC class (set by prep) */
 };
 
@@ -185,7 +186,11 @@ AUGB_HD sc_t parr_term(const DevModel* m, const Seq& s, int c, int which, int p,
     case PA_PI: return intron_emi1(m, s, c, p) + nep_term(m, pmask, p);
     case PA_PIR: return intron_emi1r(m, s, c, p) + nep_term(m, pmask, p);
     case PA_PX: case PA_PX + 1: case PA_PX + 2: return p >= m->k ? exon_emi1(m, s, m->xemi, c, 1, mod3(which - PA_PX + p), p) : 0;
-    default: return exon_emi1(m, s, m->xemi, c, 0, mod3(which - PA_PXR - p), p);
+    case PA_PXR: case PA_PXR + 1: case PA_PXR + 2: return exon_emi1(m, s, m->xemi, c, 0, mod3(which - PA_PXR - p), p);
+    case PA_XET: case PA_XET + 1: case PA_XET + 2: return exon_emi1(m, s, m->xet, c, 1, mod3(which - PA_XET + p), p);
+    case PA_XETR: case PA_XETR + 1: case PA_XETR + 2: return exon_emi1(m, s, m->xet, c, 0, mod3(which - PA_XETR - p), p);
+    case PA_XIN: case PA_XIN + 1: case PA_XIN + 2: return exon_emi1(m, s, m->xinit, c, 1, mod3(which - PA_XIN + p), p);
+    default: return exon_emi1(m, s, m->xinit, c, 0, mod3(which - PA_XINR - p), p);
     }
 }
 

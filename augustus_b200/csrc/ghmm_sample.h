@@ -20,6 +20,7 @@ struct SampleOut {
     int32_t *begin, *end; uint8_t *type, *trunc;
     int32_t* count; double* logp;    /* per sample */
     int32_t* status;
+    int32_t* rand_used = nullptr;    /* out: draws consumed (cursor at the end) */
 };
 struct SampleScratch { SampleOpt* opt; int opt_cap; int32_t* sorted; int* nopt; };
 
@@ -182,7 +183,7 @@ struct SamplerT {
             }
             wsync();
         }
-        if (lane == 0) *out.status = status;
+        if (lane == 0) { *out.status = status; if (out.rand_used) *out.rand_used = cursor; }
         S.opt = nullptr; S.nopt = nullptr;
         wsync();
     }

@@ -23,14 +23,14 @@ struct Seq {
         return s2irc(p, n);
     }
     /* Seq2Int::operator() (geneticcode.hh:166-173); -1 = InvalidNucleotideError */
-    AUGB_HD int s2i(int p, int n) const {
+    AUGB_HDN int s2i(int p, int n) const {
         int e = 0;
         AUGB_ROLLED
         for (int i = 0; i < n; i++) { int b = at(p + i); if (b > 3) return -1; e = (e << 2) | b; }
         return e;
     }
     /* Seq2Int::rc (geneticcode.hh:174-179) */
-    AUGB_HD int s2irc(int p, int n) const {
+    AUGB_HDN int s2irc(int p, int n) const {
         int e = 0;
         AUGB_ROLLED
         for (int i = 0; i < n; i++) { int b = at(p + i); if (b > 3) return -1; e |= (3 - b) << (2 * i); }

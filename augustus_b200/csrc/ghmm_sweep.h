@@ -154,7 +154,7 @@ struct SweepT {
     }
     /* record a non-zero cell; route it to the structures later columns look back to.  All lanes hold the same
      * arguments; lane 0 writes, one warp sync publishes. */
-    AUGB_D void emit(int j, int s, sc_t V, int pred, int predbase, double F = 0) {
+    AUGB_EMIT void emit(int j, int s, sc_t V, int pred, int predbase, double F = 0) {
         if (lane == 0) {
             int n = ws->n_ev;
             if (n >= w.ev_cap) ws->status = 8;
@@ -231,7 +231,15 @@ struct SweepT {
         if (fwd) { const sc_t* P = parr(cls, PA_PX + mod3(frameOfRight - right)); return P[right + 1] - P[left]; }
         const sc_t* P = parr(cls, PA_PXR + mod3(frameOfRight + right)); return P[right + 1] - P[left];
     }
-    AUGB_D sc_t exon_shortProb(const sc_t* tab, int fwd, int left, int right, int frameOfRight) const {   /* :1979-2034 */
+    /* initial / exon-terminal content of [left, right] (ExonModel::initialSeqProb / eTermSeqProb, exonmodel.cc:1979-2034):
+     * difference of the 3-periodic prefix arrays PA_XIN / PA_XET written by the prep pass (exact in fixed point) */
+    AUGB_D sc_t exon_shortProb(int pa, int fwd, int left, int right, int frameOfRight) const {
+        if (left > right) return 0;
+        if (left < 0 || right >= L) return exon_shortProb_loop(pa == PA_XET ? m->xet : m->xinit, fwd, left, right, frameOfRight);
+        const sc_t* P = fwd ? parr(cls, pa + mod3(frameOfRight - right)) : parr(cls, pa + 3 + mod3(frameOfRight + right));
+        return P[right + 1] - P[left];
+    }
+    AUGB_DN sc_t exon_shortProb_loop(const sc_t* tab, int fwd, int left, int right, int frameOfRight) const {   /* ranges that leave the window */
         sc_t s = 0;
         AUGB_ROLLED
         for (int p = right; p >= left; p--) {
@@ -327,42 +335,42 @@ struct SweepT {
             switch (st.ek) {
             case E_SINGLE:
                 endOfInitial = endOfStart + m->init_len; if (endOfInitial > right) endOfInitial = right;
-                rest += exon_shortProb(m->xinit, 1, endOfStart + 1, endOfInitial, mod3(frameOfRight - right + endOfInitial))
+                rest += exon_shortProb(PA_XIN, 1, endOfStart + 1, endOfInitial, mod3(frameOfRight - right + endOfInitial))
                       + exon_seqProb(1, endOfInitial + 1, right, frameOfRight);
                 break;
             case E_INITIAL:
                 endOfInitial = endOfStart + m->init_len;
                 if (endOfInitial > right) { endOfInitial = right; beginOfTerm = right + 1; }
                 else { beginOfTerm = right - m->et_len + 1; if (beginOfTerm <= endOfInitial) beginOfTerm = right + 1; }
-                rest += exon_shortProb(m->xinit, 1, endOfStart + 1, endOfInitial, mod3(frameOfRight - right + endOfInitial))
+                rest += exon_shortProb(PA_XIN, 1, endOfStart + 1, endOfInitial, mod3(frameOfRight - right + endOfInitial))
                       + exon_seqProb(1, endOfInitial + 1, beginOfTerm - 1, mod3(frameOfRight - right + (beginOfTerm - 1)))
-                      + exon_shortProb(m->xet, 1, beginOfTerm, right, frameOfRight);
+                      + exon_shortProb(PA_XET, 1, beginOfTerm, right, frameOfRight);
                 break;
             case E_INTERNAL:
                 beginOfTerm = right - m->et_len + 1; if (beginOfTerm <= endOfStart) beginOfTerm = right + 1;
                 rest += exon_seqProb(1, endOfStart + 1, beginOfTerm - 1, mod3(frameOfRight - right + (beginOfTerm - 1)))
-                      + exon_shortProb(m->xet, 1, beginOfTerm, right, frameOfRight);
+                      + exon_shortProb(PA_XET, 1, beginOfTerm, right, frameOfRight);
                 break;
             case E_TERMINAL:
                 rest += exon_seqProb(1, endOfStart + 1, right, frameOfRight);
                 break;
             case E_RSINGLE:
                 beginOfInitial = beginOfInitP - m->init_len; if (beginOfInitial < bos) beginOfInitial = bos;
-                rest += exon_shortProb(m->xinit, 0, beginOfInitial, beginOfInitP - 1, mod3(frameOfRight + right - (beginOfInitP - 1)))
+                rest += exon_shortProb(PA_XIN, 0, beginOfInitial, beginOfInitP - 1, mod3(frameOfRight + right - (beginOfInitP - 1)))
                       + exon_seqProb(0, bos, beginOfInitial - 1, mod3(frameOfRight + right - (beginOfInitial - 1)));
                 break;
             case E_RINITIAL:
                 beginOfInitial = beginOfInitP - m->init_len;
                 if (beginOfInitial < bos) { beginOfInitial = bos; endOfTerm = bos - 1; }
                 else { endOfTerm = bos + m->et_len - 1; if (endOfTerm >= beginOfInitial) endOfTerm = bos - 1; }
-                rest += exon_shortProb(m->xinit, 0, beginOfInitial, beginOfInitP - 1, mod3(frameOfRight + right - (beginOfInitP - 1)))
+                rest += exon_shortProb(PA_XIN, 0, beginOfInitial, beginOfInitP - 1, mod3(frameOfRight + right - (beginOfInitP - 1)))
                       + exon_seqProb(0, endOfTerm + 1, beginOfInitial - 1, mod3(frameOfRight + right - (beginOfInitial - 1)))
-                      + exon_shortProb(m->xet, 0, bos, endOfTerm, mod3(frameOfRight + right - endOfTerm));
+                      + exon_shortProb(PA_XET, 0, bos, endOfTerm, mod3(frameOfRight + right - endOfTerm));
                 break;
             case E_RINTERNAL:
                 endOfTerm = bos + m->et_len - 1; if (endOfTerm >= beginOfInitP) endOfTerm = bos - 1;
                 rest += exon_seqProb(0, endOfTerm + 1, beginOfInitP - 1, mod3(frameOfRight + right - (beginOfInitP - 1)))
-                      + exon_shortProb(m->xet, 0, bos, endOfTerm, mod3(frameOfRight + right - endOfTerm));
+                      + exon_shortProb(PA_XET, 0, bos, endOfTerm, mod3(frameOfRight + right - endOfTerm));
                 break;
             default:
                 rest += exon_seqProb(0, bos, beginOfInitP - 1, mod3(frameOfRight + right - (beginOfInitP - 1)));
@@ -398,7 +406,7 @@ struct SweepT {
         int p4 = sq.kmer_end(endOfStart, k);
         v += p4 < 0 ? (sc_t)k * m->probN : m->xpls[k - 1][(((size_t)cls * 3 + mod3(df + endOfStart)) << (2 * k)) | p4];
         const int endOfInitial = endOfStart + m->init_len;
-        return v + exon_shortProb(m->xinit, 1, endOfStart + 1, endOfInitial, mod3(df + endOfInitial));
+        return v + exon_shortProb(PA_XIN, 1, endOfStart + 1, endOfInitial, mod3(df + endOfInitial));
     }
 
     /* ExonModel::viterbiForwardAndSampling (exonmodel.cc:899-1179) for state s ending at column j.
@@ -439,7 +447,7 @@ struct SweepT {
         sc_t endc = 0; int pxhi = right + 1;                      /* closed form = cand terms + PXp[pxhi] - PXp[lo(bos)] + endc */
         if (k >= 1 && right - k >= 0) {
             if (ek == E_INTERNAL || ek == E_INITIAL) {
-                if (right - m->et_len + 1 >= 0) { pxhi = right - m->et_len + 1; endc = exon_shortProb(m->xet, 1, right - m->et_len + 1, right, frameOfRight); }
+                if (right - m->et_len + 1 >= 0) { pxhi = right - m->et_len + 1; endc = exon_shortProb(PA_XET, 1, right - m->et_len + 1, right, frameOfRight); }
             } else if (!fwd && ek != E_RTERMINAL && ek != E_RSINGLE) {
                 const int beginOfInitP = right - (k - 1);
                 int pn = sq.kmer_rc(beginOfInitP, k);
@@ -448,7 +456,7 @@ struct SweepT {
                 if (ek == E_RINITIAL && beginOfInitP - m->init_len >= 0) {
                     const int beginOfInitial = beginOfInitP - m->init_len;
                     pxhi = beginOfInitial;
-                    endc += exon_shortProb(m->xinit, 0, beginOfInitial, beginOfInitP - 1, mod3(frameOfRight + right - (beginOfInitP - 1)));
+                    endc += exon_shortProb(PA_XIN, 0, beginOfInitial, beginOfInitP - 1, mod3(frameOfRight + right - (beginOfInitP - 1)));
                 }
             }
         }
@@ -528,7 +536,7 @@ struct SweepT {
                             else rest += PXp[right + 1] - PXp[bos + k];
                         } else {
                             rest = endc;
-                            if (il > etmin) { const int endOfTerm = bos + m->et_len - 1; rest += exon_shortProb(m->xet, 0, bos, endOfTerm, mod3(frameOfRight + right - endOfTerm)) + PXp[pxhi] - PXp[endOfTerm + 1]; }
+                            if (il > etmin) { const int endOfTerm = bos + m->et_len - 1; rest += exon_shortProb(PA_XET, 0, bos, endOfTerm, mod3(frameOfRight + right - endOfTerm)) + PXp[pxhi] - PXp[endOfTerm + 1]; }
                             else rest += PXp[pxhi] - PXp[bos];
                         }
                         nep = isneg(rest) ? SC_NEG : rest + (m->log3 + ld);
@@ -539,7 +547,7 @@ struct SweepT {
                     if (isneg(ld) || !lenok) valid = false;
                     else if (ek == E_RINITIAL) {
                         const int endOfTerm = bos + m->et_len - 1;
-                        nep = endc + exon_shortProb(m->xet, 0, bos, endOfTerm, mod3(frameOfRight + right - endOfTerm)) + (PXp[pxhi] - PXp[endOfTerm + 1]) + (m->log3 + ld);
+                        nep = endc + exon_shortProb(PA_XET, 0, bos, endOfTerm, mod3(frameOfRight + right - endOfTerm)) + (PXp[pxhi] - PXp[endOfTerm + 1]) + (m->log3 + ld);
                     } else {
                         /* start codon x TIS motif, initial pattern, initial content (:1427-1462, 1590-1636) */
                         sc_t bs = begin_score(bobe, frameOfRight - right);

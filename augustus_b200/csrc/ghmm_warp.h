@@ -61,6 +61,10 @@ inline int wpopc(unsigned b) { return __builtin_popcount(b); }
  * winning lane or -1 if every score is SC_NEG.  Keys are chosen by the callers so that "highest key" is
  * the option the reference meets first in its loop order (strict '>' keeps the first maximum). */
 AUGB_D int wargbest(sc_t score, int key) {
+    /* the common cases need no reduction: no lane holds a candidate, or exactly one does */
+    const unsigned have = wballot(!isneg(score));
+    if (have == 0) return -1;
+    if ((have & (have - 1u)) == 0) return wffs(have);
     sc_t m = wmax(score);
     if (isneg(m)) return -1;
     int k = wmaxi(score == m ? key : -0x7fffffff);

@@ -42,7 +42,8 @@ class AugB200Error(RuntimeError):
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libaugb200.so")
+    # AUGB200_LIB: another build of the same library (kernel experiments); never a different implementation
+    return os.environ.get("AUGB200_LIB") or os.path.join(_HERE, "libaugb200.so")
 
 
 class _Window(ctypes.Structure):

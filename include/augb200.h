@@ -106,6 +106,16 @@ int augb200_decode_batch(augb200_model* m, int32_t n, const augb200_window* wind
 int augb200_decode_batch_sampling(augb200_model* m, int32_t n, const augb200_window* windows, int32_t nsample,
                                   augb200_path* out, augb200_path* samples);
 
+/*
+ * rand() stream position for hosts that predict several sequences in ONE process (the reference shares one glibc rand() stream,
+ * seed 1, across all getSampledPath calls of a run, vitmatrix.cc:300): the windows of the next augb200_decode_batch_sampling call
+ * start `draws_consumed` values into that stream (default 0 = a fresh process per window, the protocol of BASELINE.md), and
+ * augb200_last_rand_consumed returns how many values the sampled paths of window 0 of the last call took.  A host that decodes
+ * one window per call in input order and adds up the consumed counts reproduces a single reference process exactly.
+ */
+int augb200_set_rand_position(augb200_model* m, uint64_t draws_consumed);
+int64_t augb200_last_rand_consumed(const augb200_model* m);
+
 /* Decode one window. */
 int augb200_decode(augb200_model* m, const augb200_window* window, augb200_path* out);
 

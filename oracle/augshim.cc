@@ -1,0 +1,123 @@
+/*
+ * augshim.cc — INTEGRATION DEMONSTRATOR (built only where /root/reference exists, into oracle/_ref/).
+ *
+ * The reference-side binding of INTEGRATION.md as working code: strong definitions of the three DP
+ * entry points of NAMGene,
+ *     NAMGene::viterbiAndForward   (reference src/namgene.cc:168-365)
+ *     NAMGene::getViterbiPath      (src/namgene.cc:432-510)
+ *     NAMGene::getSampledPath      (src/namgene.cc:367-426)
+ * that call the C ABI of libaugb200.so (include/augb200.h) instead of running the CPU matrices.
+ * oracle/Makefile links them with the UNMODIFIED reference objects (main = src/augustus.cc) after
+ * weakening those three symbols in a copy of namgene.o (objcopy --weaken-symbol), so every call site
+ * in the reference (findGenes, namgene.cc:776,790,848) lands here.  The result, oracle/_ref/augustus_b200,
+ * takes the augustus command line and config/species files and prints GFF through the reference's own
+ * post-processing; tests/test_dropin.py compares that GFF with the one of oracle/_ref/augustus.
+ *
+ * No CPU fallback: configurations the library does not decode (hints files, protein profiles, overlap
+ * mode, CRF training, pieces cut by getNextCutEndPoint) raise ProjectError.
+ */
+#include "aug_export.h"
+#include "augb200.h"
+
+namespace {
+
+struct ShimState {
+    augb200_model* model = nullptr;
+    std::vector<char> blob;
+    augb200_path vit;
+    std::vector<augb200_path> samples;
+    int next_sample = 0;
+    long dnalen = 0;
+    bool have = false;
+    std::string masked;           /* the window with soft-masked runs in lower case, the rest upper case */
+    long calls = 0;
+    uint64_t rand_pos = 0;        /* rand() values the sampled paths of this process have consumed so far (vitmatrix.cc:300) */
+};
+ShimState g;
+
+void fail(const std::string& what, int rc) {
+    throw ProjectError("augb200: " + what + ": " + augb200_strerror(rc) + " " + augb200_last_cuda_error());
+}
+
+void ensure_model(NAMGene& ng) {
+    if (g.model) return;
+    FeatureCollection fc;
+    if (Constant::softmasking) fc.readExtrinsicCFGFile();
+    BlobWriter bw;
+    build_params(ng, fc, bw);
+    g.blob = bw.bytes();
+    int dev = 0;
+    if (const char* e = getenv("AUGB200_DEVICE")) dev = atoi(e);
+    int rc = augb200_model_create(g.blob.data(), g.blob.size(), dev, &g.model);
+    if (rc) { g.model = nullptr; fail("model_create", rc); }
+    if (getenv("AUGSHIM_VERBOSE")) fprintf(stderr, "augshim: model with %d states, %d GC classes on device %d\n",
+                                            augb200_model_statecount(g.model), augb200_model_num_gc_classes(g.model), dev);
+}
+
+StatePath* to_statepath(const augb200_path& p, const char* seqname) {
+    if (p.status == AUGB200_ERR_NO_PATH) throw ProjectError("No feasible path found in HMM");                       /* namgene.cc:455-457 */
+    if (p.status) throw ProjectError(std::string("Viterbi got stuck: ") + augb200_strerror(p.status));             /* :493-496 */
+    StatePath* sp = new StatePath();
+    if (seqname) sp->seqname = seqname;
+    sp->pathemiProb = LLDouble::exp(p.log_prob);
+    for (int i = p.n - 1; i >= 0; i--) {             /* push() prepends (gene.hh:217-220): go right to left */
+        State* s = new State(p.begin[i], p.end[i], (StateType)p.type[i]);
+        s->truncated = (char)p.truncated[i];
+        sp->push(s);
+    }
+    return sp;
+}
+
+}  // namespace
+
+void NAMGene::viterbiAndForward(const char* dna, bool useProfile) {
+    if (useProfile || profileModel) throw ProjectError("augb200: protein profile models are not decoded on the GPU");
+    if (Constant::overlapmode) throw ProjectError("augb200: overlap mode is not decoded on the GPU");
+    if (inCRFTraining) throw ProjectError("augb200: CRF training runs on the CPU build");
+    ensure_model(*this);
+    const long n = (long)strlen(dna);
+    /* the DP sees a lower-cased sequence (SequenceFeatureCollection::prepare, extrinsicinfo.cc:1726-1727); soft-masked runs
+     * arrive as nonexonpart hints of source RM (:1696-1724).  The library takes the case of the window instead, so rebuild it. */
+    g.masked.assign(dna, dna + n);
+    for (long i = 0; i < n; i++) g.masked[i] = (char)toupper((unsigned char)g.masked[i]);
+    SequenceFeatureCollection* sfc = StateModel::seqFeatColl;
+    if (sfc) {
+        for (int t = 0; t < NUM_FEATURE_TYPES; t++) {
+            const std::list<Feature>& fl = sfc->featureLists[t];
+            for (std::list<Feature>::const_iterator it = fl.begin(); it != fl.end(); ++it) {
+                const bool rm = t == (int)nonexonpartF && it->source == "softmask";
+                if (!rm) throw ProjectError("augb200: hints other than softmasking are not decoded on the GPU");
+                if (!it->active) continue;
+                for (long p = std::max<long>(0, it->start); p <= it->end && p < n; p++) g.masked[p] = (char)tolower((unsigned char)g.masked[p]);
+            }
+        }
+    }
+    augb200_window w; w.dna = g.masked.data(); w.length = (int32_t)n; w.gc_class = nullptr;
+    /* cs is public state other reference code reads (printing of GC classes); keep it filled as the original does (:228) */
+    cs.computeStairs(dna);
+    w.gc_class = cs.idx;
+    int rc;
+    const int ns = sampleiterations > 1 && needForwardTable ? sampleiterations : 1;
+    if (ns > 1) {
+        g.samples.assign(ns - 1, augb200_path());
+        if ((rc = augb200_set_rand_position(g.model, g.rand_pos))) fail("set_rand_position", rc);
+        rc = augb200_decode_batch_sampling(g.model, 1, &w, ns, &g.vit, g.samples.data());
+        if (!rc) g.rand_pos += (uint64_t)augb200_last_rand_consumed(g.model);
+    } else {
+        g.samples.clear();
+        rc = augb200_decode(g.model, &w, &g.vit);
+    }
+    if (rc) fail("decode", rc);
+    g.next_sample = 0; g.dnalen = n; g.have = true; g.calls++;
+}
+
+StatePath* NAMGene::getViterbiPath(const char* dna, const char* seqname) {
+    if (!g.have) throw ProjectError("augb200: getViterbiPath before viterbiAndForward");
+    return to_statepath(g.vit, seqname);
+}
+
+StatePath* NAMGene::getSampledPath(const char* dna, const char* seqname) {
+    if (!needForwardTable) return new StatePath();                                   /* namgene.cc:369-370 */
+    if (!g.have || g.next_sample >= (int)g.samples.size()) throw ProjectError("augb200: more sampled paths requested than --sample");
+    return to_statepath(g.samples[g.next_sample++], seqname);
+}
