@@ -97,7 +97,8 @@ typedef uint32_t mask_t;
  * on the forward strand, mod3(phi - p) on the reverse strand).  XET / XIN = exon-terminal and initial content
  * (ExonModel::eTermSeqProb / initialSeqProb, exonmodel.cc:1979-2034) so that the sweep never loops over positions */
 enum : int { PA_PI = 0, PA_PIR = 1, PA_PX = 2 /* +phi */, PA_PXR = 5 /* +phi */, PA_XET = 8 /* +phi */, PA_XETR = 11 /* +phi */,
-             PA_XIN = 14 /* +phi */, PA_XINR = 17 /* +phi */, PA_PER_CLASS = 20 };
+             PA_XIN = 14 /* +phi */, PA_XINR = 17 /* +phi */, PA_NSCAN = 20 /* the arrays above are prefix sums */,
+             PA_BEG = 20 /* per position, not a sum: begin score of a forward initial / single exon whose start codon is there */, PA_PER_CLASS = 21 };
 
 /* how one UTR exon state scores a (predecessor end, duration) candidate: UtrModel::notEndPartEmiProb (utrmodel.cc:1167-1405) as
  * begin signal + content prefix difference + length distribution, all table driven */

@@ -268,11 +268,12 @@ __global__ void __launch_bounds__(PREP_BS) k_prep(const WinDev* __restrict__ win
         for (int c = 0; c < m->C; c++) {
             sc_t* slab = s_slab[c];
             if (!slab) continue;
-            for (int which = 0; which < PA_PER_CLASS; which++) {
+            for (int which = 0; which < PA_NSCAN; which++) {
                 sc_t* P = slab + (size_t)which * (size_t)(L + 1);
                 if (threadIdx.x == 0) P[0] = 0;
                 block_scan_gen<sc_t>([&](int p) { return parr_term(m, s, c, which, p, pmask); }, P + 1, L, (sc_t)0, sm64);
             }
+            { sc_t* B = slab + (size_t)PA_BEG * (size_t)(L + 1); for (int p = threadIdx.x; p <= L; p += PREP_BS) B[p] = begin_term(m, s, c, p); }
         }
         sc_t* aig = (sc_t*)(base + lay.aig); sc_t* ageo = (sc_t*)(base + lay.ageo);
         if (threadIdx.x == 0) { aig[0] = 0; ageo[0] = 0; }

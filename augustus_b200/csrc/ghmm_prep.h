@@ -194,6 +194,28 @@ AUGB_HD sc_t parr_term(const DevModel* m, const Seq& s, int c, int which, int p,
     }
 }
 
+/* PA_BEG[bobe]: start codon x TIS motif, P_ls start pattern and initial content of a forward initial / single exon whose start
+ * codon begins at bobe (exonmodel.cc:1427-1462, 1596-1603, 1611-1633), with the tables of class c.  The reading frame of a
+ * position p of such an exon is mod3(p - bobe), whatever state and exon end ask for it; SC_NEG = no start codon here. */
+AUGB_HD sc_t begin_term(const DevModel* m, const Seq& s, int c, int bobe) {
+    const int k = m->k, bos = bobe + 3, L = s.L;
+    if (!(bobe >= 0 && bobe < L - 2)) return SC_NEG;
+    int pn = s.kmer_end(bobe + 2, 3);
+    if (pn < 0 || isneg(m->startp[pn])) return SC_NEG;
+    sc_t v = m->startp[pn];
+    int tis = bobe - m->tiw;
+    if (tis > m->tis_k) v += motif_fwd(m, s, c, m->tis, m->tis_n, m->tis_k, tis);
+    else v += (sc_t)(bos - 3) * m->log025;
+    const int endOfStart = bos + k - 1;
+    if (k >= 1) {
+        int p4 = s.kmer_end(endOfStart, k);
+        v += p4 < 0 ? (sc_t)k * m->probN : m->xpls[k - 1][(((size_t)c * 3 + mod3(endOfStart - bobe)) << (2 * k)) | p4];
+    }
+    const int endOfInitial = endOfStart + m->init_len;
+    for (int p = endOfInitial; p > endOfStart; p--) v += exon_emi1(m, s, m->xinit, c, 1, mod3(p - bobe), p);
+    return v;
+}
+
 /* sequential host builder (test emulator) */
 inline void prep_window_seq(const DevModel* m, const char* dna, int L, const int32_t* gc_in, char* base, const WinLayout& lay, int* classmask,
                             char* pool = nullptr, size_t pool_size = 0, size_t* pool_used = nullptr) {
@@ -249,11 +271,12 @@ inline void prep_window_seq(const DevModel* m, const char* dna, int L, const int
         else if (pool && *pool_used + lay.slab <= pool_size) { slab = (sc_t*)(pool + *pool_used); *pool_used += lay.slab; }
         else { wo->pad |= WF_NOSLAB; *classmask |= WF_NOSLAB; continue; }
         wo->slab[c] = slab;
-        for (int which = 0; which < PA_PER_CLASS; which++) {
+        for (int which = 0; which < PA_NSCAN; which++) {
             sc_t* P = slab + (size_t)which * (size_t)(L + 1);
             P[0] = 0;
             for (int p = 0; p < L; p++) P[p + 1] = P[p] + parr_term(m, s, c, which, p, pmask);
         }
+        { sc_t* B = slab + (size_t)PA_BEG * (size_t)(L + 1); for (int p = 0; p <= L; p++) B[p] = begin_term(m, s, c, p); }
     }
     sc_t* aig = (sc_t*)(base + lay.aig); sc_t* ageo = (sc_t*)(base + lay.ageo);
     aig[0] = ageo[0] = 0;

@@ -394,7 +394,12 @@ struct SweepT {
 
     /* begin part x initial pattern x initial content of a forward initial / single exon whose start codon is at bobe,
      * when the inner sequence is long enough for all three (exonmodel.cc:1427-1462, 1596-1603, 1611-1633); df = frameOfRight - right */
-    AUGB_DN sc_t begin_score(int bobe, int df) const {
+    AUGB_D sc_t begin_score(int bobe, int df) const {
+        /* tabulated by the prep pass (PA_BEG) for the frame every valid candidate has: position p is in frame mod3(p - bobe) */
+        if (mod3(df + bobe) == 0 && bobe >= 0 && bobe <= L) return parr(cls, PA_BEG)[bobe];
+        return begin_score_calc(bobe, df);
+    }
+    AUGB_DN sc_t begin_score_calc(int bobe, int df) const {
         const int k = m->k, bos = bobe + 3;
         int pn = sq.kmer_end(bobe + 2, 3);
         if (pn < 0 || isneg(m->startp[pn]) || !(bobe >= 0 && bobe < L - 2)) return SC_NEG;

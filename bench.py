@@ -78,8 +78,9 @@ def ref_binary():
     return (exe, cfg) if os.path.exists(exe) and os.path.isdir(cfg) else (None, None)
 
 
-def run_reference_sample(n_windows, cores, start_index=0, extra_args=(), window_len=None):
-    """Decode n_windows synthetic windows with the unmodified reference, `cores` processes in parallel.
+def run_reference_sample(n_windows, cores, start_index=0, extra_args=(), window_len=None, seqs=None, base_args=("--species=human", "--softmasking=0"),
+                         one_per_process=False):
+    """Decode n_windows synthetic windows (or the given sequences) with the unmodified reference, `cores` processes in parallel.
     Returns (Mbp/s, seconds)."""
     from augustus_b200 import synth
     exe, cfg = ref_binary()
@@ -87,21 +88,35 @@ def run_reference_sample(n_windows, cores, start_index=0, extra_args=(), window_
         raise RuntimeError("oracle/_ref/augustus is missing (run __graft_entry__.build() in the build container)")
     env = dict(os.environ, AUGUSTUS_CONFIG_PATH=cfg)
     wlen = window_len or WINDOW_LEN
+    if seqs is not None:
+        n_windows = len(seqs)
     with tempfile.TemporaryDirectory() as td:
         files = []
-        per = [[] for _ in range(cores)]
+        nfile = n_windows if one_per_process else cores
+        per = [[] for _ in range(nfile)]
         for i in range(n_windows):
-            per[i % cores].append(start_index + i)
+            per[i % nfile].append(start_index + i)
         for c, idxs in enumerate(per):
             if not idxs:
                 continue
             fa = os.path.join(td, "c%d.fa" % c)
-            synth.write_fasta(fa, [synth.window(i, wlen) for i in idxs], ["w%d" % i for i in idxs])
+            synth.write_fasta(fa, [seqs[i - start_index] if seqs is not None else synth.window(i, wlen) for i in idxs], ["w%d" % i for i in idxs])
             files.append(fa)
         t0 = time.perf_counter()
         procs = []
+        if one_per_process and len(files) > cores:      # more windows than cores: a pool of `cores` running processes
+            import concurrent.futures as cf
+            def one(a):
+                c, fa = a
+                cmd = [exe] + list(base_args) + list(extra_args) + [fa]
+                return subprocess.run(cmd, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL).returncode
+            with cf.ThreadPoolExecutor(cores) as ex:
+                if any(ex.map(one, enumerate(files))):
+                    raise RuntimeError("reference process failed")
+            dt = time.perf_counter() - t0
+            return sum(len(s) for s in seqs) / 1e6 / dt if seqs is not None else n_windows * wlen / 1e6 / dt, dt
         for c, fa in enumerate(files):
-            cmd = [exe, "--species=human", "--softmasking=0"] + list(extra_args) + [fa]
+            cmd = [exe] + list(base_args) + list(extra_args) + [fa]
             if os.path.exists("/usr/bin/taskset"):
                 cmd = ["taskset", "-c", str(c % (os.cpu_count() or 1))] + cmd
             procs.append(subprocess.Popen(cmd, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
@@ -109,7 +124,27 @@ def run_reference_sample(n_windows, cores, start_index=0, extra_args=(), window_
             if p.wait() != 0:
                 raise RuntimeError("reference process failed")
         dt = time.perf_counter() - t0
+    if seqs is not None:
+        return sum(len(x) for x in seqs) / 1e6 / dt, dt
     return n_windows * wlen / 1e6 / dt, dt
+
+
+def chr2l_windows(window=200000, step=150000):
+    """BASELINE.json configs[2]: examples/chr2L cut into 200 kb windows stepping 150 kb (157 windows).  The FASTA is
+    reference DATA copied to oracle/_ref/data/ by oracle/Makefile (it travels with the built checker; never read from /root/reference)."""
+    import gzip
+    path = os.path.join(ROOT, "oracle", "_ref", "data", "chr2L.sm.fa.gz")
+    if not os.path.exists(path):
+        return None
+    seq = "".join(l.strip() for l in gzip.open(path, "rt") if not l.startswith(">"))
+    out = []
+    a = 0
+    while True:
+        out.append(seq[a:a + window])
+        if a + window >= len(seq):
+            break
+        a += step
+    return out
 
 
 def reference_arm(args, rank, world):
@@ -308,6 +343,33 @@ def main():
             dec4.close()
         except Exception as ex:
             line["secondary"]["config4_utr"] = {"error": repr(ex)}
+    if not args.no_secondary and world == 1:
+        # BASELINE.json configs[2]: examples/chr2L --species=fly (defaults: UTR on, softmasking on, sample=100) in 200 kb windows
+        try:
+            w3 = chr2l_windows()
+            if w3 is None:
+                raise RuntimeError("oracle/_ref/data/chr2L.sm.fa.gz not present")
+            w3b = [w.encode() for w in w3]
+            dec3 = Decoder(util.blob_bytes("fly_softmask_utr"), local)
+            dec3.decode_batch_sampling_raw(w3b[:4], 100)
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            vit3, samp3 = dec3.decode_batch_sampling_raw(w3b, 100)
+            torch.cuda.synchronize(); dt3 = time.perf_counter() - t0
+            assert not vit3[1].any() and not samp3[1].any()
+            mbp3 = sum(len(w) for w in w3) / 1e6
+            sec3 = {"workload": "examples/chr2L (23.5 Mbp, soft-masked) in %d windows of 200 kb stepping 150 kb, --species=fly defaults (UTR on = 71 states, softmasking on, "
+                                "sample=100: Viterbi + forward + 99 sampled paths per window), 1 GPU, e2e from host buffers through augb200_decode_batch_sampling" % len(w3),
+                    "value": mbp3 / dt3, "unit": "Mbp/s", "windows": len(w3), "sweep_ms": dec3.last_sweep_ms, "path_states": int(vit3[0].sum()), "sampled_paths": int(len(samp3[0]))}
+            if not args.no_cpu_baseline:
+                cores = os.cpu_count() or 1
+                sub = w3[: min(len(w3), cores)]
+                v3, d3 = run_reference_sample(0, cores, seqs=sub, base_args=("--species=fly",), one_per_process=True)
+                sec3["cpu_baseline"] = {"value": v3, "unit": "Mbp/s", "cores": min(cores, len(sub)), "kind": "reference",
+                                        "sample": "%d of the windows, one unmodified augustus --species=fly process per window (%.1f s wall)" % (len(sub), d3)}
+            line.setdefault("secondary", {})["config3_chr2L"] = sec3
+            dec3.close()
+        except Exception as ex:
+            line.setdefault("secondary", {})["config3_chr2L"] = {"error": repr(ex)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

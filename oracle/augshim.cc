@@ -41,11 +41,18 @@ void fail(const std::string& what, int rc) {
 
 void ensure_model(NAMGene& ng) {
     if (g.model) return;
-    FeatureCollection fc;
-    if (Constant::softmasking) fc.readExtrinsicCFGFile();
-    BlobWriter bw;
-    build_params(ng, fc, bw);
-    g.blob = bw.bytes();
+    /* the export reads extrinsic.cfg and swaps GC classes through the models; both chat on cout / cerr, which must not leak into
+     * the GFF (the front end already printed its own "Sources of extrinsic information" line) */
+    std::ostringstream sink;
+    std::streambuf* oc = std::cout.rdbuf(sink.rdbuf()); std::streambuf* oe = std::cerr.rdbuf(sink.rdbuf());
+    try {
+        FeatureCollection fc;
+        if (Constant::softmasking) fc.readExtrinsicCFGFile();
+        BlobWriter bw;
+        build_params(ng, fc, bw);
+        g.blob = bw.bytes();
+    } catch (...) { std::cout.rdbuf(oc); std::cerr.rdbuf(oe); throw; }
+    std::cout.rdbuf(oc); std::cerr.rdbuf(oe);
     int dev = 0;
     if (const char* e = getenv("AUGB200_DEVICE")) dev = atoi(e);
     int rc = augb200_model_create(g.blob.data(), g.blob.size(), dev, &g.model);
@@ -74,7 +81,6 @@ void NAMGene::viterbiAndForward(const char* dna, bool useProfile) {
     if (useProfile || profileModel) throw ProjectError("augb200: protein profile models are not decoded on the GPU");
     if (Constant::overlapmode) throw ProjectError("augb200: overlap mode is not decoded on the GPU");
     if (inCRFTraining) throw ProjectError("augb200: CRF training runs on the CPU build");
-    ensure_model(*this);
     const long n = (long)strlen(dna);
     /* the DP sees a lower-cased sequence (SequenceFeatureCollection::prepare, extrinsicinfo.cc:1726-1727); soft-masked runs
      * arrive as nonexonpart hints of source RM (:1696-1724).  The library takes the case of the window instead, so rebuild it. */
@@ -86,12 +92,13 @@ void NAMGene::viterbiAndForward(const char* dna, bool useProfile) {
             const std::list<Feature>& fl = sfc->featureLists[t];
             for (std::list<Feature>::const_iterator it = fl.begin(); it != fl.end(); ++it) {
                 const bool rm = t == (int)nonexonpartF && it->source == "softmask";
-                if (!rm) throw ProjectError("augb200: hints other than softmasking are not decoded on the GPU");
+                if (!rm) throw ProjectError("augb200: hints other than softmasking are not decoded on the GPU (feature type " + std::to_string(t) + " source " + it->source + ")");
                 if (!it->active) continue;
                 for (long p = std::max<long>(0, it->start); p <= it->end && p < n; p++) g.masked[p] = (char)tolower((unsigned char)g.masked[p]);
             }
         }
     }
+    ensure_model(*this);
     augb200_window w; w.dna = g.masked.data(); w.length = (int32_t)n; w.gc_class = nullptr;
     /* cs is public state other reference code reads (printing of GC classes); keep it filled as the original does (:228) */
     cs.computeStairs(dna);
