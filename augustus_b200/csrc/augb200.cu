@@ -53,6 +53,8 @@ struct augb200_model {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> wave_ev;     /* sweep timing of the 2nd.. wave of a staged batch */
+    std::vector<std::pair<int, int>> waves;                        /* (first window, count): groups of windows that share the arena in turn */
     DevBuf<sc_t> d_tab; DevModel dm_dev;      /* model with device table pointers; uploaded to the c_model constant */
     /* batch state */
     DevBuf<char> d_arena; DevBuf<char> d_pool; DevBuf<unsigned long long> d_pool_used; size_t pool_bytes = 0; DevBuf<char> d_dna; DevBuf<uint8_t> d_gc; DevBuf<WinDev> d_wins; DevBuf<int> d_counters;
@@ -76,14 +78,28 @@ struct augb200_model {
     std::vector<int32_t> rs_begin, rs_end; std::vector<uint8_t> rs_type, rs_trunc;
 };
 
-static int upload_windows(augb200_model* M, const augb200_window* w, const int* idx, int count, bool generous) {
-    /* stage DNA (+ optional classes) of windows idx[0..count) and build their descriptors */
-    size_t dna_bytes = 0, gc_bytes = 0, arena = 0;
+static int upload_windows(augb200_model* M, const augb200_window* w, const int* idx, int count, bool generous, size_t wave_cap = 0) {
+    /* stage DNA (+ optional classes) of windows idx[0..count) and build their descriptors.  The workspaces of the windows live
+     * in the arena; with wave_cap > 0 the windows are split into waves of (nearly) equal size <= wave_cap bytes that use the
+     * arena one after the other (M->waves), so a staged batch may be larger than the device memory left for workspaces */
+    size_t dna_bytes = 0, gc_bytes = 0, arena = 0, all = 0;
     for (int i = 0; i < count; i++) {
         const augb200_window& x = w[idx[i]];
         dna_bytes += (size_t)((x.length + 15) & ~15);
         if (x.gc_class) gc_bytes += (size_t)((x.length + 15) & ~15);
-        arena += make_layout(x.length, M->hm.dm.C, generous, M->nsamp > 0, M->nsamp, M->hm.dm.utr != 0, M->hm.dm.softmask != 0).total;
+        all += make_layout(x.length, M->hm.dm.C, generous, M->nsamp > 0, M->nsamp, M->hm.dm.utr != 0, M->hm.dm.softmask != 0).total;
+    }
+    M->waves.clear();
+    {
+        const size_t nw = wave_cap && all > wave_cap ? (all + wave_cap - 1) / wave_cap : 1;
+        const size_t target = (all + nw - 1) / nw;
+        size_t cur = 0; int first = 0;
+        for (int i = 0; i < count; i++) {
+            size_t t = make_layout(w[idx[i]].length, M->hm.dm.C, generous, M->nsamp > 0, M->nsamp, M->hm.dm.utr != 0, M->hm.dm.softmask != 0).total;
+            if (wave_cap && i > first && (cur + t > wave_cap || cur >= target)) { M->waves.push_back({first, i - first}); arena = std::max(arena, cur); first = i; cur = 0; }
+            cur += t;
+        }
+        M->waves.push_back({first, count - first}); arena = std::max(arena, cur);
     }
     int rc;
     if ((rc = M->h_dna.reserve(dna_bytes + 16))) return rc;
@@ -93,7 +109,12 @@ static int upload_windows(augb200_model* M, const augb200_window* w, const int* 
     /* slab pool for the prefix arrays of second / third ... GC classes (first class lives in the window) */
     {
         size_t need = 0;
-        if (!generous && M->hm.dm.C > 1) for (int i = 0; i < count; i++) need += (size_t)(M->hm.dm.C - 1) * make_layout(w[idx[i]].length, M->hm.dm.C).slab;
+        if (!generous && M->hm.dm.C > 1)
+            for (const auto& wv : M->waves) {
+                size_t nd = 0;
+                for (int i = wv.first; i < wv.first + wv.second; i++) nd += (size_t)(M->hm.dm.C - 1) * make_layout(w[idx[i]].length, M->hm.dm.C).slab;
+                need = std::max(need, nd);
+            }
         size_t room = M->arena_budget > arena ? M->arena_budget - arena : 0;
         size_t pool = std::min(need, room + M->arena_budget / 8);
         if (pool && (rc = M->d_pool.reserve(pool))) return rc;
@@ -103,7 +124,9 @@ static int upload_windows(augb200_model* M, const augb200_window* w, const int* 
     if ((rc = M->h_wins.reserve(count))) return rc;
     if ((rc = M->d_wins.reserve(count))) return rc;
     size_t od = 0, og = 0, oa = 0; long total_path_cap = 0;
+    size_t wvi = 0;
     for (int i = 0; i < count; i++) {
+        if (wvi + 1 < M->waves.size() && i == M->waves[wvi + 1].first) { wvi++; oa = 0; }      /* next wave: the arena starts over */
         const augb200_window& x = w[idx[i]];
         WinDev& d = M->h_wins.p[i];
         d.L = x.length; d.lay = make_layout(x.length, M->hm.dm.C, generous, M->nsamp > 0, M->nsamp, M->hm.dm.utr != 0, M->hm.dm.softmask != 0);
@@ -153,33 +176,45 @@ static int upload_windows(augb200_model* M, const augb200_window* w, const int* 
 
 static int run_kernels(augb200_model* M, int count) {
     CK(cudaMemsetAsync(M->d_counters.p, 0, 4 * sizeof(int), M->stream));
-    CK(cudaMemsetAsync(M->d_pool_used.p, 0, sizeof(unsigned long long), M->stream));
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, M->device);
-    int gprep = std::min(count, sms * 8);
     CK(cudaMemcpyToSymbolAsync(c_model, &M->dm_dev, sizeof(DevModel), 0, cudaMemcpyHostToDevice, M->stream));
-    k_prep<<<gprep, PREP_BS, 0, M->stream>>>(M->d_wins.p, count, M->pool_bytes ? M->d_pool.p : nullptr, (unsigned long long)M->pool_bytes, M->d_pool_used.p);
-    CK(cudaEventRecord(M->ev0, M->stream));
     /* resident sweep warps per SM: the kernel is instruction-fetch bound, more warps than this thrash the instruction cache */
     static int bps = 0;
     if (!bps) { const char* e = getenv("AUGB200_SWEEP_BLOCKS_PER_SM"); bps = e ? atoi(e) : 4; if (bps < 1) bps = 1; }
-    int gsweep = std::min((count + SWEEP_WARPS - 1) / SWEEP_WARPS, sms * bps);
     const bool utr = M->hm.dm.utr != 0;
-    if (utr) gsweep = std::min(gsweep, sms * std::min(bps, 3));
     const int nrng = (int)std::min<size_t>(M->rng_n - std::min<size_t>(M->rng_n, M->rand_pos), 0x7fffffff);
     const uint32_t* d_rng = M->d_rng.p ? M->d_rng.p + M->rand_pos : nullptr;
-    if (M->nsamp > 0 && utr) k_sweep_sample_utr<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(M->d_wins.p, count, M->d_counters.p, d_rng, nrng);
-    else if (M->nsamp > 0) k_sweep_sample<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(M->d_wins.p, count, M->d_counters.p, d_rng, nrng);
-    else if (utr) k_sweep_utr<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(M->d_wins.p, count, M->d_counters.p);
-    else k_sweep<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(M->d_wins.p, count, M->d_counters.p);
-    CK(cudaEventRecord(M->ev1, M->stream));
-    k_backtrace<<<(count + 63) / 64, 64, 0, M->stream>>>(M->d_wins.p, count);
-    k_pack<<<count, 64, 0, M->stream>>>(M->d_wins.p, count, M->d_hdr.p, M->d_counters.p + 1, M->d_obegin.p, M->d_oend.p, M->d_otype.p, M->d_otrunc.p, M->ocap);
-    if (M->nsamp > 0) {
-        k_pack_samples<<<count, 64, 0, M->stream>>>(M->d_wins.p, count, M->d_shdr.p, M->d_sstatus.p, M->d_counters.p + 2, M->d_sbegin.p, M->d_send.p, M->d_stype.p, M->d_strunc.p, M->scap);
-        M->launches += 1;
+    if (M->waves.empty() || M->waves.back().first + M->waves.back().second != count) { M->waves.clear(); M->waves.push_back({0, count}); }
+    while (M->wave_ev.size() + 1 < M->waves.size()) {
+        std::pair<cudaEvent_t, cudaEvent_t> e;
+        CK(cudaEventCreate(&e.first)); CK(cudaEventCreate(&e.second));
+        M->wave_ev.push_back(e);
     }
-    CK(cudaGetLastError());
-    M->launches += 4;
+    for (size_t wv = 0; wv < M->waves.size(); wv++) {
+        const int first = M->waves[wv].first, n = M->waves[wv].second;
+        const WinDev* wins = M->d_wins.p + first;
+        if (wv) CK(cudaMemsetAsync(M->d_counters.p, 0, sizeof(int), M->stream));      /* the window queue of the sweep; the output offsets run on */
+        CK(cudaMemsetAsync(M->d_pool_used.p, 0, sizeof(unsigned long long), M->stream));
+        int gprep = std::min(n, sms * 8);
+        k_prep<<<gprep, PREP_BS, 0, M->stream>>>(wins, n, M->pool_bytes ? M->d_pool.p : nullptr, (unsigned long long)M->pool_bytes, M->d_pool_used.p);
+        CK(cudaEventRecord(wv ? M->wave_ev[wv - 1].first : M->ev0, M->stream));
+        int gsweep = std::min((n + SWEEP_WARPS - 1) / SWEEP_WARPS, sms * bps);
+        if (utr) gsweep = std::min(gsweep, sms * std::min(bps, 3));
+        if (M->nsamp > 0 && utr) k_sweep_sample_utr<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(wins, n, M->d_counters.p, d_rng, nrng);
+        else if (M->nsamp > 0) k_sweep_sample<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(wins, n, M->d_counters.p, d_rng, nrng);
+        else if (utr) k_sweep_utr<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(wins, n, M->d_counters.p);
+        else k_sweep<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(wins, n, M->d_counters.p);
+        CK(cudaEventRecord(wv ? M->wave_ev[wv - 1].second : M->ev1, M->stream));
+        k_backtrace<<<(n + 63) / 64, 64, 0, M->stream>>>(wins, n);
+        k_pack<<<n, 64, 0, M->stream>>>(wins, n, M->d_hdr.p + first, M->d_counters.p + 1, M->d_obegin.p, M->d_oend.p, M->d_otype.p, M->d_otrunc.p, M->ocap);
+        if (M->nsamp > 0) {
+            k_pack_samples<<<n, 64, 0, M->stream>>>(wins, n, M->d_shdr.p + (size_t)first * M->nsamp, M->d_sstatus.p + 2 * (size_t)first, M->d_counters.p + 2,
+                                                     M->d_sbegin.p, M->d_send.p, M->d_stype.p, M->d_strunc.p, M->scap);
+            M->launches += 1;
+        }
+        CK(cudaGetLastError());
+        M->launches += 4;
+    }
     return 0;
 }
 
@@ -218,11 +253,11 @@ static int fetch_results(augb200_model* M, int count, augb200_path* out, const i
                 p.n = h.n; p.status = M->h_sstatus.p[2 * i]; p.log_prob = h.logp;
                 p.begin = (const int32_t*)(uintptr_t)(sbase + h.offset);
             }
-        /* a window whose sample buffers overflowed is decoded again as a whole */
-        for (int i = 0; i < count; i++) if (M->h_sstatus.p[2 * i] == AUGB200_ERR_CAPACITY && out[idx[i]].status == 0) out[idx[i]].status = AUGB200_ERR_CAPACITY;
         for (int i = 0; i < count; i++) if (idx[i] == 0) M->rand_used0 = M->h_sstatus.p[2 * i + 1];
     }
     float ms = 0; if (cudaEventElapsedTime(&ms, M->ev0, M->ev1) == cudaSuccess) M->sweep_ms += ms;
+    for (size_t wv = 1; wv < M->waves.size() && wv - 1 < M->wave_ev.size(); wv++)
+        if (cudaEventElapsedTime(&ms, M->wave_ev[wv - 1].first, M->wave_ev[wv - 1].second) == cudaSuccess) M->sweep_ms += ms;
     /* append to the result store; pointers are fixed up by the caller once all sub-batches are in */
     size_t base = M->r_begin.size();
     M->r_begin.insert(M->r_begin.end(), M->h_obegin.p, M->h_obegin.p + total);
@@ -235,6 +270,9 @@ static int fetch_results(augb200_model* M, int count, augb200_path* out, const i
         /* store offsets in the pointer fields for now */
         p.begin = (const int32_t*)(uintptr_t)(base + h.offset);
     }
+    /* a window whose sample buffers overflowed is decoded again as a whole (after the Viterbi status above is in place) */
+    if (M->nsamp > 0 && M->samples_out)
+        for (int i = 0; i < count; i++) if (M->h_sstatus.p[2 * i] == AUGB200_ERR_CAPACITY && out[idx[i]].status == 0) out[idx[i]].status = AUGB200_ERR_CAPACITY;
     return 0;
 }
 
@@ -284,6 +322,7 @@ void augb200_model_destroy(augb200_model* M) {
     M->d_sbegin.release(); M->d_send.release(); M->d_stype.release(); M->d_strunc.release(); M->h_sbegin.release(); M->h_send.release(); M->h_stype.release(); M->h_strunc.release();
     if (M->ev0) cudaEventDestroy(M->ev0);
     if (M->ev1) cudaEventDestroy(M->ev1);
+    for (auto& e : M->wave_ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (M->stream) cudaStreamDestroy(M->stream);
     delete M;
 }
@@ -313,11 +352,17 @@ static int decode_batch_impl(augb200_model* M, int32_t n, const augb200_window* 
     for (int pass = 0; pass < 2 && !order.empty(); pass++) {
         const bool generous = pass == 1;      /* second pass: windows whose default-sized structures overflowed */
         size_t first = 0;
+        /* sub-batches under the arena budget, of (nearly) equal size: every sub-batch ends with a tail of windows that run at low
+         * occupancy, so two halves beat "as many as fit, then the rest" */
+        const size_t cap = M->arena_budget - M->arena_budget / 8;
+        size_t all = 0;
+        for (int i : order) all += make_layout(w[i].length, M->hm.dm.C, generous, M->nsamp > 0, M->nsamp, M->hm.dm.utr != 0, M->hm.dm.softmask != 0).total;
+        const size_t nsub = all > cap ? (all + cap - 1) / cap : 1, target = (all + nsub - 1) / nsub;
         while (first < order.size()) {
-            size_t bytes = 0; int count = 0;   /* greedy sub-batch under the arena budget */
+            size_t bytes = 0; int count = 0;
             while (first + count < order.size()) {
                 size_t t = make_layout(w[order[first + count]].length, M->hm.dm.C, generous, M->nsamp > 0, M->nsamp, M->hm.dm.utr != 0, M->hm.dm.softmask != 0).total;
-                if (count && bytes + t > M->arena_budget - M->arena_budget / 8) break;
+                if (count && (bytes + t > cap || bytes >= target)) break;
                 bytes += t; count++;
             }
             if ((rc = upload_windows(M, w, order.data() + first, count, generous))) return rc;
@@ -360,11 +405,11 @@ int augb200_stage_batch(augb200_model* M, int32_t n, const augb200_window* w) {
     if (!M) return AUGB200_ERR_BAD_ARG;
     int rc = check_windows(n, w); if (rc) return rc;
     CK(cudaSetDevice(M->device));
-    size_t bytes = 0; for (int i = 0; i < n; i++) bytes += make_layout(w[i].length, M->hm.dm.C, false, false, 0, M->hm.dm.utr != 0, M->hm.dm.softmask != 0).total;
-    if (bytes > M->arena_budget - M->arena_budget / 8) return AUGB200_ERR_CAPACITY;
+    /* the DNA and the descriptors of all windows stay on the device; workspaces are taken from the arena wave by wave */
     std::vector<int> order(n);
     for (int i = 0; i < n; i++) order[i] = i;
-    if ((rc = upload_windows(M, w, order.data(), n, false))) return rc;
+    M->nsamp = 0; M->samples_out = nullptr;
+    if ((rc = upload_windows(M, w, order.data(), n, false, M->arena_budget - M->arena_budget / 8))) return rc;
     CK(cudaStreamSynchronize(M->stream));
     M->staged_n = n;
     return AUGB200_OK;

@@ -74,7 +74,7 @@ inline WinLayout make_layout(int L, int C, bool generous = false, bool forward =
     w.evF = take(forward ? (size_t)w.ev_cap * 8 : 0); w.clF = take(forward ? (size_t)w.ncl * w.cl_cap * 8 : 0); w.clG = take(forward && utr ? (size_t)w.ncl * w.cl_cap * 8 : 0);
     w.fcp = take((size_t)w.nchain * w.fcp_cap * sizeof(FChainCP));
     w.nsamp = forward ? nsamp : 0;
-    w.opt_cap = w.nsamp ? w.cl_cap + 1024 : 0; w.samp_cap = w.nsamp ? (generous ? w.nsamp * (L / 8 + 64) : w.nsamp * 160 + L / 4) : 0;
+    w.opt_cap = w.nsamp ? w.cl_cap + 1024 : 0; w.samp_cap = w.nsamp ? (generous ? w.nsamp * (L / 8 + 64) : w.nsamp * (128 + L / 128)) : 0;   /* gene-dense fly DNA: ~3.5 path states per kb and sample */
     w.opt = take((size_t)w.opt_cap * sizeof(SampleOpt)); w.sorted = take((size_t)w.opt_cap * 4);
     w.s_begin = take((size_t)w.samp_cap * 4); w.s_end = take((size_t)w.samp_cap * 4); w.s_type = take(w.samp_cap); w.s_trunc = take(w.samp_cap);
     w.s_count = take((size_t)w.nsamp * 4 + 16); w.s_logp = take((size_t)w.nsamp * 8);

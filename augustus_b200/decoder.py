@@ -113,6 +113,10 @@ def _load():
     lib.augb200_model_stream.argtypes = [ctypes.c_void_p]
     lib.augb200_last_launch_count.restype = ctypes.c_int64
     lib.augb200_last_launch_count.argtypes = [ctypes.c_void_p]
+    lib.augb200_set_rand_position.restype = ctypes.c_int
+    lib.augb200_set_rand_position.argtypes = [ctypes.c_void_p, ctypes.c_uint64]
+    lib.augb200_last_rand_consumed.restype = ctypes.c_int64
+    lib.augb200_last_rand_consumed.argtypes = [ctypes.c_void_p]
     lib.augb200_last_sweep_ms.restype = ctypes.c_double
     lib.augb200_last_sweep_ms.argtypes = [ctypes.c_void_p]
     lib.augb200_result_store.restype = ctypes.c_int64
@@ -255,6 +259,15 @@ class Decoder:
         samp = (_Path * (nw * ns))()
         self._check(self._lib.augb200_decode_batch_sampling(self._h, nw, arr, nsample, out, samp))
         return self._raw(out, nw), self._raw(samp, nw * ns, self._lib.augb200_sample_store)
+
+    def set_rand_position(self, draws_consumed: int):
+        """Where in the process-wide rand() stream (vitmatrix.cc:300) the next sampling call starts; 0 = a fresh process."""
+        self._check(self._lib.augb200_set_rand_position(self._h, draws_consumed))
+
+    @property
+    def last_rand_consumed(self) -> int:
+        """rand() draws the sampled paths of window 0 of the last sampling call took."""
+        return self._lib.augb200_last_rand_consumed(self._h)
 
     def viterbiAndForward(self, dna, gc=None):
         """NAMGene::viterbiAndForward (namgene.cc:168) for one window; the path is kept for getViterbiPath."""

@@ -242,7 +242,7 @@ def main():
     sweep_ms = dec.last_sweep_ms            # last run's sweep kernel, CUDA events around that launch
     assert all(p.status == 0 for p in paths)
     # ---- end-to-end through the public call, host buffers in, host paths out ----
-    dec.decode_batch(wins_b[: max(1, M // 8)])     # warm the staging buffers
+    dec.decode_batch_raw(wins_b)                   # untimed warm-up of the public call at full size (pinned + device buffers reach their final size)
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 2))
@@ -283,7 +283,7 @@ def main():
         "dtype": "int64 (Q23.40 fixed-point log scores)", "data": "synthetic",
         "config": {"workload": "%d synthetic 50 kb human-composition windows per GPU, --species=human ab initio, 47 states (BASELINE.json configs[1])" % M,
                    "window_len": WINDOW_LEN, "windows_per_gpu": M, "parallelism": "windows sharded over %d GPU(s), one warp per window" % world,
-                   "l2": "inputs per step (%.0f MB DNA + %.1f GB workspace) exceed the 126 MB L2" % (bases / 1e6, bases * 130 / 1e9)},
+                   "l2": "inputs per step (%.0f MB DNA + %.0f GB of per-window workspace written and read by the kernels) exceed the 126 MB L2" % (bases / 1e6, bases * 332 / 1e9)},
         "e2e": {"value": world * bases / 1e6 / e2e_s, "unit": "Mbp/s", "h2d_bytes_per_step": bases, "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -141,3 +141,26 @@ def test_full_size_properties(dec):
         for x, y in zip(st, st[1:]):
             assert y.begin == x.end + 1                 # the path tiles columns 1..L-1
         assert a.log_prob < 0
+
+
+def test_staged_batch_larger_than_the_arena_runs_in_waves(dec, monkeypatch):
+    """augb200_stage_batch keeps DNA + descriptors of all windows on the device and hands the workspace arena from wave to wave
+    when the batch does not fit (bench.py stages 10 000 windows): same paths as the plain call, run twice to check re-use."""
+    wins = [synth.window(700 + i, n) for i, n in enumerate([20000, 18000, 9000, 21000, 15000, 8000, 22000, 5000, 17000, 19000, 4000, 20000])]
+    want = dec.decode_batch(wins)
+    monkeypatch.setenv("AUGB200_ARENA_MB", "24")          # a 20 kb window needs ~7 MB: 2-3 windows per wave
+    small = Decoder(util.blob_bytes(), 0)
+    try:
+        small.stage(wins)
+        for _ in range(2):
+            small.run_staged()
+        got = small.fetch_staged()
+        assert small.last_launch_count >= 4 * 4             # at least four waves of (prep, sweep, backtrace, pack)
+        for a, b in zip(got, want):
+            assert a.status == 0 and a.as_tuples() == b.as_tuples() and a.log_prob == b.log_prob
+        assert small.last_sweep_ms > 0
+        # the plain call on the same small arena goes through sub-batches
+        for a, b in zip(small.decode_batch(wins), want):
+            assert a.as_tuples() == b.as_tuples()
+    finally:
+        small.close()
