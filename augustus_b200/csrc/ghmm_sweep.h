@@ -425,11 +425,20 @@ struct SweepT {
      * (the overwhelmingly common case) is scored by the closed form
      *     begin-signal + P_ls start pattern + content prefix difference + terminal part + 3*lenDist
      * whose end-dependent terms are computed once per exon end; shorter ones go through the general routine. */
-    AUGB_D void exon_eval(int s, int j) {
+    /* Up to three exon states of one kind (the three reading frames) are evaluated in ONE pass on the device: the warp splits into
+     * groups of `gl` lanes (8, or 32 for a single state), every lane carries the state of its group in `s` (-1: no state), so the
+     * end-dependent terms, the candidate stream and the scoring below are the same instruction stream for all frames; reductions
+     * and the final arg-best run per group.  The host build (one lane) and the forward / sampling kernels pass gl = all lanes. */
+    AUGB_D void exon_eval(int s, int j, int gl = AUGB_NLANES) {
+        const int g0 = lane & ~(gl - 1), li = lane - g0;                       /* first lane of my group, my index in it */
+        const unsigned gmask = (gl >= 32 ? 0xffffffffu : ((1u << gl) - 1u)) << g0;
+        bool alive = s >= 0;
+        if (!alive) s = m->xslot[0] >= 0 ? m->xslot[0] : 0;                    /* any valid state: the lanes of an empty group idle along */
         const StateDesc& st = m->st[s]; const int fwd = st.fwd, win = st.frame, ek = st.ek, k = m->k;
-        sc_t ep = endPart(st, j);
+        sc_t ep = alive ? endPart(st, j) : SC_NEG;
         const int eobe = j + st.baseOffset, right = eobe - st.innerPartEndOffset;
-        if (isneg(ep) || right < 0) return;
+        if (isneg(ep) || right < 0) alive = false;
+        if (wballot(alive) == 0) return;
         const int frameOfRight = fwd ? mod3(win - (eobe + 1) + right) : mod3(win + eobe + 1 - right);
         int eons = (ek == E_TERMINAL || ek == E_SINGLE) ? eobe - 3 : eobe;
         if (eons > L - 1) eons = L - 1;
@@ -441,7 +450,7 @@ struct SweepT {
             startMin = ORFleft <= 0 ? 0 : ORFleft + st.innerPartOffset;
             if (startMax > j + st.beginPartLen) startMax = j + st.beginPartLen;
         }
-        /* ---- end-dependent terms of the closed forms (uniform over lanes) ---- */
+        /* ---- end-dependent terms of the closed forms (uniform over the lanes of a group) ---- */
         const int thr = k + m->init_len + m->et_len + 2;          /* inner length from which every sub-model applies in full */
         const bool listkind = ek == E_INTERNAL || ek == E_TERMINAL || ek == E_RINTERNAL || ek == E_RINITIAL;
         const bool scankind = ek == E_INITIAL || ek == E_SINGLE;
@@ -450,7 +459,7 @@ struct SweepT {
                           : (ek == E_SINGLE || ek == E_RSINGLE) ? m->ld_single : ek == E_RTERMINAL ? m->ld_terminal : m->ld_initial;
         const int etmin = k + m->et_len - 2;                      /* the exon-terminal part applies iff right - bos > etmin */
         sc_t endc = 0; int pxhi = right + 1;                      /* closed form = cand terms + PXp[pxhi] - PXp[lo(bos)] + endc */
-        if (k >= 1 && right - k >= 0) {
+        if (alive && k >= 1 && right - k >= 0) {
             if (ek == E_INTERNAL || ek == E_INITIAL) {
                 if (right - m->et_len + 1 >= 0) { pxhi = right - m->et_len + 1; endc = exon_shortProb(PA_XET, 1, right - m->et_len + 1, right, frameOfRight); }
             } else if (!fwd && ek != E_RTERMINAL && ek != E_RSINGLE) {
@@ -471,33 +480,34 @@ struct SweepT {
         if (listkind) { list = fwd ? CL_LA + mod3(win - eobe - 1) : CL_RD + mod3(win + eobe + 1); cl = w.cl(list); ncl = ws->cl_n[list]; }
         else if (scankind) {
             const int want = mod3(eobe + 1 - (ek == E_SINGLE ? 0 : win));      /* bobe mod 3 such that len % 3 == win */
-            scan_b0 = startMax; while (mod3(scan_b0 - st.innerPartOffset) != want) scan_b0--;
+            scan_b0 = startMax - mod3(startMax - st.innerPartOffset - want);
         }
         const int lo = listkind ? (startMin < 1 ? 1 : startMin) : startMin;
         sc_t best = SC_NEG; int bkey = -0x7fffffff, bpred = -1, bbase = -1;
         Lse fl; fl.clear();
         /* initial / single exons: one pass over the in-frame start codons per ancestor (igenic; with UTR states the two 5' UTR
          * states that end trans_init_window bases before the start codon) */
-        const int npass = (UTR && scankind) ? st.nanc : 1;
+        const int npass = UTR ? wmaxi(alive && scankind ? (int)st.nanc : 1) : 1;       /* (collective: every lane takes part) */
         AUGB_ROLLED
         for (int ai = 0; ai < npass; ai++) {
-        const int anc0 = st.anc[ai];
+        const bool pass_on = alive && ai < (scankind ? (int)st.nanc : 1);
+        const int anc0 = st.anc[pass_on ? ai : 0];
         const sc_t t0 = TR(anc0, s);
-        int step = 0; bool more = true;
+        int step = 0; bool more = true, gdone = !pass_on;
         AUGB_ROLLED
         while (more) {
             /* lane's candidate: (bos, predecessor a, its cell value pv, its column eop) */
-            bool valid = false, below = false; int bos = 0, a = anc0, eop = 0; sc_t pv = SC_NEG, t = t0; double pf = 0;
-            if (listkind) {
-                int i = ncl - 1 - step * AUGB_NLANES - lane;
+            bool valid = false, below = gdone; int bos = 0, a = anc0, eop = 0; sc_t pv = SC_NEG, t = t0; double pf = 0;
+            if (gdone) {
+            } else if (listkind) {
+                int i = ncl - 1 - step * gl - li;
                 if (i >= 0) {
                     Cand c = cl[i]; bos = c.col + 1;
                     if (bos < lo) below = true;
                     else if (bos <= startMax && c.col < j) { valid = true; a = c.state; pv = c.V; eop = c.col; t = TR(a, s); if (FWD) pf = w.clF(list)[i]; }
                 } else below = true;
-                more = wballot(below) == 0;
             } else if (scankind) {
-                bos = scan_b0 - 3 * (step * AUGB_NLANES + lane);
+                bos = scan_b0 - 3 * (step * gl + li);
                 if (bos < startMin) below = true;
                 else {
                     int bobe = bos - 3; eop = bos - st.beginPartLen - 1;
@@ -506,16 +516,20 @@ struct SweepT {
                         if (pn >= 0 && !isneg(m->startp[pn])) { pv = lookupV(anc0, eop >= 0 ? eop : 0); valid = !isneg(pv); if (FWD && valid) pf = lookupF(anc0, eop >= 0 ? eop : 0); }
                     }
                 }
-                more = wballot(below) == 0;
             } else {
-                more = step * AUGB_NLANES + AUGB_NLANES < st.nanc;
-                if (step * AUGB_NLANES + lane < st.nanc) {
-                    bos = startMin; eop = bos - st.beginPartLen - 1; a = st.anc[step * AUGB_NLANES + lane]; t = TR(a, s);
+                if (step * gl + gl >= st.nanc) below = true;              /* last step of this group */
+                if (step * gl + li < st.nanc) {
+                    bos = startMin; eop = bos - st.beginPartLen - 1; a = st.anc[step * gl + li]; t = TR(a, s);
                     /* the one candidate can end AT the current column (reverse stop inside the end part): the reference then reads the
                      * cell of this very column, which exists only for states evaluated earlier in the column (lower index; here the
                      * intergenic chain); behind the current column the matrix is still empty */
                     if ((eop < j || (eop == j && a < s && m->st[a].chain >= 0)) && !isneg(t)) { pv = lookupV(a, eop >= 0 ? eop : 0); valid = !isneg(pv); if (FWD && valid) pf = lookupF(a, eop >= 0 ? eop : 0); }
                 }
+            }
+            {   /* a group stops after the step in which one of its lanes ran past the range; the warp goes on while any group does */
+                const unsigned bb = wballot(below);
+                if (bb & gmask) gdone = true;
+                more = wballot(!gdone) != 0;
             }
             step++;
             /* score: nep = notEndPartEmiProb(bos) */
@@ -570,28 +584,37 @@ struct SweepT {
             }
         }
         }
-        if (listkind && startMin == 0) {
-            /* left-truncated exon, bos = 0: the predecessor is read from column 0 = initial probabilities (exonmodel.cc:1067-1068) */
+        if (wballot(alive && listkind && startMin == 0)) {
+            /* left-truncated exon, bos = 0: the predecessor is read from column 0 = initial probabilities (exonmodel.cc:1067-1068);
+             * every lane of the group walks the ancestors, its first lane keeps the result */
+            const bool mine = alive && listkind && startMin == 0;
             const int len = eobe + st.innerPartOffset + 1;
-            sc_t nep0 = SC_NEG; bool have = false;
+            sc_t nep0 = SC_NEG; bool have = false, stop = !mine;
+            const int na = wmaxi(mine ? (int)st.nanc : 0);
             AUGB_ROLLED
-            for (int i = 0; i < st.nanc; i++) {
-                int a = st.anc[i]; sc_t pv = m->init[a], t = TR(a, s);
-                if (isneg(pv) || isneg(t) || win != mod3(fwd ? m->st[a].frame + len : m->st[a].frame - len)) continue;
-                if (!have) { nep0 = notEndPart(st, 0, right, frameOfRight); have = true; }
-                if (isneg(nep0)) break;
+            for (int i = 0; i < na; i++) {
+                const bool in = !stop && i < st.nanc;
+                int a = st.anc[in ? i : 0]; sc_t pv = m->init[a], t = TR(a, s);
+                const bool ok = in && !(isneg(pv) || isneg(t) || win != mod3(fwd ? m->st[a].frame + len : m->st[a].frame - len));
+                if (wballot(ok && !have)) { if (ok && !have) { nep0 = notEndPart(st, 0, right, frameOfRight); have = true; } }
+                if (ok && isneg(nep0)) stop = true;
+                const bool use = ok && !stop;
                 sc_t sc = pv + (t + ep + nep0); int key = 127 - a;
-                if (lane == 0 && (sc > best || (sc == best && key > bkey))) { best = sc; bkey = key; bpred = a; bbase = -1; }
-                if (FWD && !opt && lane == 0) fl.add(sc2d(pv) + sc2d(t + ep + nep0));
-                if (FWD && opt) push_opt(lane == 0, sc2d(pv) + sc2d(t + ep + nep0), -(127 - a), a, -1);
+                if (use && li == 0 && (sc > best || (sc == best && key > bkey))) { best = sc; bkey = key; bpred = a; bbase = -1; }
+                if (FWD && !opt && use && li == 0) fl.add(sc2d(pv) + sc2d(t + ep + nep0));
+                if (FWD && opt) push_opt(use && li == 0, sc2d(pv) + sc2d(t + ep + nep0), -(127 - a), a, -1);
             }
         }
         if (FWD && opt) return;
-        int wl = wargbest(best, bkey);
-        if (wl < 0) return;
+        const int wl = gargbest(best, bkey, gl, gmask);       /* winning lane of my group, -1: none */
+        if (wballot(wl >= 0) == 0) return;
         double Fv = 0;
-        if (FWD) Fv = wlse(fl).value();
-        emit(j, s, wbcast64(best, wl), wbcast(bpred, wl), wbcast(bbase, wl), Fv);
+        if (FWD) Fv = wlse(fl).value();                         /* forward kernels evaluate one state per call (gl = all lanes) */
+        AUGB_ROLLED
+        for (int g = 0; g < AUGB_NLANES; g += gl) {
+            const int wg = wbcast(wl, g);
+            if (wg >= 0) emit(j, wbcast(s, g), wbcast64(best, wg), wbcast(bpred, wg), wbcast(bbase, wg), Fv);
+        }
     }
 
     /* ------------------------------------------------------------ intron states */
@@ -963,8 +986,17 @@ struct SweepT {
         AUGB_ROLLED
         while (slots) {
             int q = wffs(slots); slots &= slots - 1;
-            int xs = m->xslot[q];
-            if (xs >= 0) exon_eval(xs, j);
+            int xs = m->xslot[q], gl = AUGB_NLANES;
+#if defined(__CUDA_ARCH__)
+            /* slots 2-4, 5-7, 10-12, 13-15 are the three frames of one kind (set together by the mask): one pass, 8 lanes per frame */
+            if (!FWD && (q == 2 || q == 5 || q == 10 || q == 13) && (slots & (3u << (q + 1))) == (3u << (q + 1))) {
+                slots &= ~(3u << (q + 1));
+                const int f = lane >> 3;
+                xs = f < 3 ? m->xslot[q + f] : -1; gl = 8;
+            } else
+#endif
+            if (xs < 0) continue;
+            exon_eval(xs, j, gl);
         }
         if (UTR && (mb & (MB_UTR_ENDS | MB_LONGDSS | MB_RLONGASS))) {
             /* UTR exon states by end signal: slots 0-15 = utr5single, utr5init, utr5internal, utr5term, utr3single, utr3init,

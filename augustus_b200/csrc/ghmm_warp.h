@@ -71,6 +71,26 @@ AUGB_D int wargbest(sc_t score, int key) {
     return wffs(wballot(score == m && key == k));
 }
 
+/* the same per group of gl lanes (gl a power of two, groups aligned; gmask = the lanes of the caller's group): every lane gets the
+ * winning lane of its own group */
+AUGB_D int gargbest(sc_t score, int key, int gl, unsigned gmask) {
+#if defined(__CUDA_ARCH__)
+    if (gl >= 32) return wargbest(score, key);
+    const unsigned have = wballot(!isneg(score));
+    const unsigned hg = have & gmask;
+    /* no reduction unless some group holds more than one candidate */
+    if (wballot((hg & (hg - 1u)) != 0) == 0) return hg ? wffs(hg) : -1;
+    sc_t m = score;
+    for (int o = gl >> 1; o; o >>= 1) { sc_t t = __shfl_xor_sync(0xffffffffu, m, o); m = t > m ? t : m; }
+    int k = score == m ? key : -0x7fffffff;
+    for (int o = gl >> 1; o; o >>= 1) { int t = __shfl_xor_sync(0xffffffffu, k, o); k = t > k ? t : k; }
+    const unsigned win = wballot(!isneg(score) && score == m && key == k) & gmask;
+    return win ? wffs(win) : -1;
+#else
+    return wargbest(score, key);
+#endif
+}
+
 /* running log-sum-exp: value = m + ln(s); empty = (m = -inf, s = 0) */
 struct Lse {
     double m, s;

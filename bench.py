@@ -260,8 +260,17 @@ def main():
     sampler.stop_flag = True; sampler.join(timeout=2)
 
     t = torch.tensor([ms, e2e_s, sweep_ms], dtype=torch.float64, device="cuda")
+    clk = sampler.summary()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    # every rank samples its own GPU: report the slowest median SM clock and the union of the throttle reasons, plus per-rank kernel times
+    c = torch.tensor([-(clk["sm_mhz"] or 0)] + [1.0 if n in clk["reasons"] else 0.0 for n in names], dtype=torch.float64, device="cuda")
+    per_rank = torch.zeros(world, dtype=torch.float64, device="cuda"); per_rank[rank] = sweep_ms
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.MAX)
+        dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
+        clk["sm_mhz"] = int(-c[0].item()); clk["reasons"] = [n for n, v in zip(names, c[1:].tolist()) if v > 0]
+        clk["per_rank_sweep_ms"] = [round(x, 1) for x in per_rank.tolist()]
     ms, e2e_s, sweep_ms = (float(x) for x in t.tolist())
     if rank != 0:
         if world > 1:
@@ -289,7 +298,7 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": "k_sweep", "peak_source": how,
                      "note": "achieved = 940 B/base (dense S=47 figure, SURVEY.md 8d) x bases / sweep-kernel time; traffic = ncu dram bytes/base of profiles/r1_sweep_2368win.json x bases; the sweep stores only non-zero cells and is instruction-fetch bound, not bandwidth bound (DESIGN.md)"},
-        "clocks": sampler.summary(),
+        "clocks": clk,
         "sweep_ms": sweep_ms,
     }
     if not args.no_cpu_baseline:
