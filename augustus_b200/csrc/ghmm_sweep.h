@@ -626,6 +626,27 @@ struct SweepT {
         if (kind == K_LONGDSS) { eop = j - dssw; emi = sig(fwd ? SG_DSSF : SG_DSSR, j); }
         else { eop = j - assw - m->ass_up; emi = sig(fwd ? SG_ASSF : SG_ASSR, j); }
         if (eop < 0 || isneg(emi)) return;
+#if defined(__CUDA_ARCH__)
+        if (!FWD) {
+            /* Viterbi kernels: lane = (frame, ancestor); the strict '>' of the reference keeps the first maximum in ancestor order */
+            const int f = lane >> 3, i = lane & 7;
+            const int s = f < 3 ? (kind == K_LONGDSS ? m->r_longdss[dir][f] : m->r_longass[dir][f]) : -1;
+            sc_t pp = SC_NEG; int a = -1;
+            if (s >= 0 && i < m->st[s].nanc) {
+                a = m->st[s].anc[i];
+                const sc_t t = TR(a, s);
+                if (!isneg(t)) { const sc_t pv = lookupV(a, eop); if (!isneg(pv)) pp = pv + (t + emi); }
+            }
+            const int wl = gargbest(pp, -i, 8, 0xffu << (lane & ~7));
+            if (wballot(wl >= 0) == 0) return;
+            AUGB_ROLLED
+            for (int g = 0; g < 24; g += 8) {
+                const int wg = wbcast(wl, g);
+                if (wg >= 0) emit(j, wbcast(s, g), wbcast64(pp, wg), wbcast(a, wg), eop, 0.0);
+            }
+            return;
+        }
+#endif
         AUGB_ROLLED
         for (int f = 0; f < 3; f++) {
             int s = kind == K_LONGDSS ? m->r_longdss[dir][f] : m->r_longass[dir][f];
@@ -757,11 +778,19 @@ struct SweepT {
         const sc_t* P = parr(cls, fwd ? PA_PI : PA_PIR);
         /* (sampling steps use the plain prefix difference: the memo of the forward pass is gone by then) */
         const bool slow = (w.mask[j] & MB_SLOW) != 0 && !(FWD && opt);
+        /* Viterbi kernels away from GC-class boundaries: the three frames in one pass, 8 lanes each (as Sweep::exon_eval) */
+        const int gl = (AUGB_NLANES == 32 && !FWD && !slow) ? 8 : AUGB_NLANES;
+        const int g0 = lane & ~(gl - 1), li = lane - g0;
+        const unsigned gmask = (gl >= 32 ? 0xffffffffu : ((1u << gl) - 1u)) << g0;
         AUGB_ROLLED
-        for (int f = 0; f < 3; f++) {
-            int s = m->r_lessd[dir][f]; if (s < 0 || (only >= 0 && s != only)) continue;
-            int list = (dir ? CL_RA : CL_LD) + f;
-            const Cand* cl = w.cl(list); int n = ws->cl_n[list];
+        for (int f0 = 0; f0 < 3; f0 += (gl == 8 ? 3 : 1)) {
+            const int f = gl == 8 ? (lane >> 3) : f0;
+            int s = f < 3 ? m->r_lessd[dir][f] : -1;
+            const bool alive = s >= 0 && !(only >= 0 && s != only);
+            if (wballot(alive) == 0) continue;
+            if (s < 0) s = 0;
+            const int list = (dir ? CL_RA : CL_LD) + (f < 3 ? f : 0);
+            const Cand* cl = w.cl(list); const int n = alive ? ws->cl_n[list] : 0;
             bool spl = !(fwd && f == 0) && !(!fwd && f == 2);
             int cod0 = 4, cod1 = 4, cod2 = 4;
             if (spl && eob < L - 2) {
@@ -771,13 +800,14 @@ struct SweepT {
                 else if (!fwd && f == 1) { cod0 = cmpl(sq.at(eob + 2)); cod1 = cmpl(sq.at(eob + 1)); }
             }
             sc_t best = SC_NEG; int bkey = -0x7fffffff, bpred = -1; Lse fl; fl.clear();
-            bool done = false;
-            const int nl = slow ? 1 : AUGB_NLANES;            /* emulated columns: lane 0 walks the candidates in the reference's order */
+            const int nl = slow ? 1 : gl;                     /* emulated columns: lane 0 walks the candidates in the reference's order */
+            bool gdone = n <= 0; int step = 0;
+            bool more = wballot(!gdone) != 0;
             AUGB_ROLLED
-            for (int base_i = n - 1; base_i >= 0 && !done; base_i -= nl) {
-                int i = slow ? base_i : base_i - lane; bool below = false;
+            while (more) {
+                const int i = slow ? n - 1 - step : n - 1 - step * gl - li; bool below = false;
                 bool okopt = false; double olp = 0; int oe = 0, opred = 0;
-                if (i >= 0 && (!slow || lane == 0)) {
+                if (!gdone && i >= 0 && (!slow || lane == 0)) {
                     Cand c = cl[i]; int e = c.col;
                     if (e < lme) below = true;
                     else if (e < j) {
@@ -805,16 +835,24 @@ struct SweepT {
                             }
                         }
                     }
-                } else if (i < 0) below = true;
+                } else if (!gdone && i < 0) below = true;
                 if (FWD && opt) push_opt(okopt, olp, -oe, opred, oe);
-                done = slow ? wbcast((int)below, 0) != 0 : wballot(below) != 0;
+                /* a frame is finished when one of its lanes ran past the dStateLen range or its list is used up */
+                const bool gb = slow ? wbcast((int)below, 0) != 0 : (wballot(below) & gmask) != 0;
+                step++;
+                if (gb || n - 1 - step * nl < 0) gdone = true;
+                more = wballot(!gdone) != 0;
             }
             if (FWD && opt) continue;
-            int wl = wargbest(best, bkey);
-            if (wl < 0) continue;
+            const int wl = gargbest(best, bkey, gl, gmask);
+            if (wballot(wl >= 0) == 0) continue;
             double Fv = 0;
             if (FWD) Fv = wlse(fl).value();
-            emit(j, s, wbcast64(best, wl), wbcast(bpred, wl), wbcast(bkey, wl), Fv);
+            AUGB_ROLLED
+            for (int g = 0; g < AUGB_NLANES; g += gl) {
+                const int wg = wbcast(wl, g);
+                if (wg >= 0) emit(j, wbcast(s, g), wbcast64(best, wg), wbcast(bpred, wg), wbcast(bkey, wg), Fv);
+            }
         }
     }
 
