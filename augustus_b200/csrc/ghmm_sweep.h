@@ -149,7 +149,7 @@ struct SweepT {
         const sc_t Aj = chainAv(ch, j);
         sc_t val = V + t_in - t_self - Aj;
         if (val > ws->pend_val[ch] || (val == ws->pend_val[ch] && s < ws->pend_pred[ch])) { ws->pend_val[ch] = val; ws->pend_pred[ch] = s; }
-        ws->any_pend = 1;
+        ws->any_pend |= 1 << ch;          /* bit per chain with a pending entry */
         if (FWD) ws->pend_f[ch].add(F + sc2d(t_in - t_self - Aj));
     }
     /* record a non-zero cell; route it to the structures later columns look back to.  All lanes hold the same
@@ -183,8 +183,10 @@ struct SweepT {
     AUGB_D void apply_pending(int j) {
         if (!ws->any_pend) return;
         if (lane == 0) {
+            unsigned pm = (unsigned)ws->any_pend;
             AUGB_ROLLED
-            for (int ch = 0; ch < (UTR ? NCHAIN : CH_UTR); ch++) {
+            while (pm) {
+                const int ch = wffs(pm); pm &= pm - 1;
                 sc_t pv = ws->pend_val[ch];
                 if (isneg(pv)) continue;
                 int pp = ws->pend_pred[ch], self = m->chain_state[ch];

@@ -282,7 +282,7 @@ def main():
     achieved = ALG_BYTES_PER_BASE * bases / (sweep_ms / 1e3) / 1e9
     traffic = None
     try:   # DRAM bytes of the sweep kernel from the committed ncu --set full capture (per base, scaled to this launch)
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_sweep_2368win.json")))
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_sweep_2368win_final.json")))
         traffic = prof["dram_bytes_per_base"] * bases
     except Exception:
         pass
@@ -297,7 +297,7 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": "k_sweep", "peak_source": how,
-                     "note": "achieved = 940 B/base (dense S=47 figure, SURVEY.md 8d) x bases / sweep-kernel time; traffic = ncu dram bytes/base of profiles/r1_sweep_2368win.json x bases; the sweep stores only non-zero cells and is instruction-fetch bound, not bandwidth bound (DESIGN.md)"},
+                     "note": "achieved = 940 B/base (dense S=47 figure, SURVEY.md 8d) x bases / sweep-kernel time (CUDA events around the sweep launches of the last step); traffic = ncu dram bytes/base of profiles/r1_sweep_2368win_final.json x bases; the sweep stores only non-zero cells and is bound by instruction delivery (GPC instruction cache at 94 % of its request rate, profiles/r1_sweep_fetch_bound.txt), not by HBM"},
         "clocks": clk,
         "sweep_ms": sweep_ms,
     }
