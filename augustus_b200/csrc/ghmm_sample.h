@@ -65,7 +65,7 @@ struct SamplerT {
         }
         res = wbcast(res, 0);
         cursor++;
-#if defined(__CUDA_ARCH__)
+#if AUGB_SIMT
         add = __shfl_sync(0xffffffffu, add, 0);
 #endif
         *lp += add;

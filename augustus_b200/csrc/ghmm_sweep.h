@@ -181,9 +181,11 @@ struct SweepT {
     }
     /* end of column j: apply the pending chain entries for column j+1 (ancestors in index order, strict >) */
     AUGB_D void apply_pending(int j) {
-        if (!ws->any_pend) return;
+        const unsigned pend = (unsigned)ws->any_pend;
+        if (!pend) return;
+        wsync();                              /* every lane has read the flags before lane 0 clears them */
         if (lane == 0) {
-            unsigned pm = (unsigned)ws->any_pend;
+            unsigned pm = pend;
             AUGB_ROLLED
             while (pm) {
                 const int ch = wffs(pm); pm &= pm - 1;
@@ -628,7 +630,7 @@ struct SweepT {
         if (kind == K_LONGDSS) { eop = j - dssw; emi = sig(fwd ? SG_DSSF : SG_DSSR, j); }
         else { eop = j - assw - m->ass_up; emi = sig(fwd ? SG_ASSF : SG_ASSR, j); }
         if (eop < 0 || isneg(emi)) return;
-#if defined(__CUDA_ARCH__)
+#if AUGB_SIMT
         if (!FWD) {
             /* Viterbi kernels: lane = (frame, ancestor); the strict '>' of the reference keeps the first maximum in ancestor order */
             const int f = lane >> 3, i = lane & 7;
@@ -781,7 +783,10 @@ struct SweepT {
         /* (sampling steps use the plain prefix difference: the memo of the forward pass is gone by then) */
         const bool slow = (w.mask[j] & MB_SLOW) != 0 && !(FWD && opt);
         /* Viterbi kernels away from GC-class boundaries: the three frames in one pass, 8 lanes each (as Sweep::exon_eval) */
-        const int gl = (AUGB_NLANES == 32 && !FWD && !slow) ? 8 : AUGB_NLANES;
+#ifndef AUGB_LESSD_GL
+#define AUGB_LESSD_GL 8
+#endif
+        const int gl = (AUGB_NLANES == 32 && !FWD && !slow) ? AUGB_LESSD_GL : AUGB_NLANES;
         const int g0 = lane & ~(gl - 1), li = lane - g0;
         const unsigned gmask = (gl >= 32 ? 0xffffffffu : ((1u << gl) - 1u)) << g0;
         AUGB_ROLLED
@@ -1027,7 +1032,7 @@ struct SweepT {
         while (slots) {
             int q = wffs(slots); slots &= slots - 1;
             int xs = m->xslot[q], gl = AUGB_NLANES;
-#if defined(__CUDA_ARCH__)
+#if AUGB_SIMT
             /* slots 2-4, 5-7, 10-12, 13-15 are the three frames of one kind (set together by the mask): one pass, 8 lanes per frame */
             if (!FWD && (q == 2 || q == 5 || q == 10 || q == 13) && (slots & (3u << (q + 1))) == (3u << (q + 1))) {
                 slots &= ~(3u << (q + 1));
@@ -1054,8 +1059,9 @@ struct SweepT {
     }
 
     /* ------------------------------------------------------------ whole window */
+    AUGB_D void attach() { L = w.L; sq.c = w.code; sq.L = L; sq.kf = w.kf; sq.kr = w.kr; sq.k1 = m->k + 1; }      /* per-thread view of the window */
     AUGB_D void run() {
-        L = w.L; sq.c = w.code; sq.L = L; sq.kf = w.kf; sq.kr = w.kr; sq.k1 = m->k + 1; lane = lane_id();
+        attach(); lane = lane_id();
         if (lane == 0) {
             ws->n_ev = 0; ws->filled = -1; ws->status = 0; ws->any_pend = 0; ws->snip_cnt[0] = ws->snip_cnt[1] = 0;
             AUGB_ROLLED
@@ -1102,7 +1108,7 @@ struct SweepT {
         for (int j0 = 1; j0 < L; j0 += 32) {
             /* static activity of the next 32 columns + equalD columns that fall into them */
             unsigned act = 0; unsigned mymask = 0;
-#if defined(__CUDA_ARCH__)
+#if AUGB_SIMT
             { int j = j0 + lane; mymask = j < L ? w.mask[j] : 0u; act = wballot(mymask != 0); }
 #else
             unsigned maskbuf[32];
@@ -1131,7 +1137,7 @@ struct SweepT {
                     AUGB_ROLLED
                     for (int q = 0; q < 6; q++) if (eqcol[q] & (1u << t)) eqbits |= 1u << q;
                 }
-#if defined(__CUDA_ARCH__)
+#if AUGB_SIMT
                 unsigned mb = (unsigned)wbcast((int)mymask, t);
 #else
                 unsigned mb = maskbuf[t];

@@ -12,9 +12,19 @@
 
 namespace augb {
 
-#if defined(__CUDA_ARCH__)
+/* AUGB_SIMT: the 32-lane flavour of the source — the device, or tests/hostemu/simt32.h (32 fibers per warp on the CPU, test only) */
+#if defined(__CUDA_ARCH__) || defined(AUGB_SIMT32)
+#define AUGB_SIMT 1
+#else
+#define AUGB_SIMT 0
+#endif
+#if AUGB_SIMT
 #define AUGB_NLANES 32
+#if defined(__CUDA_ARCH__)
 AUGB_D int lane_id() { return threadIdx.x & 31; }
+#else
+inline int lane_id() { return simt::lane(); }
+#endif
 AUGB_D void wsync() { __syncwarp(); }
 AUGB_D sc_t wmax(sc_t v) {
     for (int o = 16; o; o >>= 1) { sc_t t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
@@ -74,7 +84,7 @@ AUGB_D int wargbest(sc_t score, int key) {
 /* the same per group of gl lanes (gl a power of two, groups aligned; gmask = the lanes of the caller's group): every lane gets the
  * winning lane of its own group */
 AUGB_D int gargbest(sc_t score, int key, int gl, unsigned gmask) {
-#if defined(__CUDA_ARCH__)
+#if AUGB_SIMT
     if (gl >= 32) return wargbest(score, key);
     const unsigned have = wballot(!isneg(score));
     const unsigned hg = have & gmask;

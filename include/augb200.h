@@ -120,7 +120,10 @@ int64_t augb200_last_rand_consumed(const augb200_model* m);
 int augb200_decode(augb200_model* m, const augb200_window* window, augb200_path* out);
 
 /* Device-resident variant used for kernel-only timing: stage the windows once, run the kernels any
- * number of times (no host<->device traffic in between), fetch the paths at the end. */
+ * number of times (no host<->device traffic in between), fetch the paths at the end.  DNA and window
+ * descriptors of the whole batch stay on the device; the per-window workspaces come from one arena that
+ * equal-sized waves of windows use in turn, so the batch may be larger than the device memory left for
+ * workspaces (10 000 x 50 kb = two waves on a 180 GB part). */
 int augb200_stage_batch(augb200_model* m, int32_t n, const augb200_window* windows);
 int augb200_run_staged(augb200_model* m);                 /* asynchronous on the model's stream    */
 int augb200_fetch_staged(augb200_model* m, augb200_path* out);

@@ -11,6 +11,9 @@
 #include <cstring>
 #include <vector>
 
+#ifdef AUGB_SIMT32
+#include "simt32.h"          /* 32 fibers per warp: runs the lane-group paths of the device source (see the header) */
+#endif
 #include "../../augustus_b200/csrc/ghmm_backtrace.h"
 #include "../../augustus_b200/csrc/ghmm_model.h"
 #include "../../augustus_b200/csrc/ghmm_prep.h"
@@ -18,6 +21,17 @@
 #include "../../augustus_b200/csrc/ghmm_sweep.h"
 
 using namespace augb;
+
+/* run the sweep of one window: one lane, or 32 fibers that each own a copy of the per-thread state like the threads of a warp */
+template <class SW>
+static void run_sweep(SW& proto) {
+#ifdef AUGB_SIMT32
+    simt::run([&]() { SW mine = proto; mine.run(); });
+    proto.attach();
+#else
+    proto.run();
+#endif
+}
 
 struct EmuModel { HostModel hm; };
 
@@ -51,7 +65,7 @@ static int decode_impl(void* mp, const char* dna, int L, const int32_t* gc_in,
         prep_window_seq(m, dna, L, gc_in, base, lay, &cm, pass == 0 ? pool.data() : nullptr, pool.size(), &pool_used);
         v = make_view(base, lay, L, cm);
         sw = SW(); sw.m = m; sw.w = v; sw.ws = &ws;
-        sw.run();
+        run_sweep(sw);
         outs = (WinOuts*)(base + lay.outs);
         if (outs->status != AUGB200_ERR_CAPACITY) break;
     }
@@ -93,7 +107,7 @@ static int forward_impl(void* mp, const char* dna, int L, const int32_t* gc_in, 
         prep_window_seq(m, dna, L, gc_in, base, lay, &cm, pass == 0 ? pool.data() : nullptr, pool.size(), &pool_used);
         v = make_view(base, lay, L, cm);
         sw = SW(); sw.m = m; sw.w = v; sw.ws = &ws;
-        sw.run();
+        run_sweep(sw);
         outs = (WinOuts*)(base + lay.outs);
         if (outs->status != AUGB200_ERR_CAPACITY) break;
     }
@@ -120,7 +134,7 @@ static int sample_impl(void* mp, const char* dna, int L, const int32_t* gc_in, i
         prep_window_seq(m, dna, L, gc_in, base, lay, &cm, pass == 0 ? pool.data() : nullptr, pool.size(), &pool_used);
         v = make_view(base, lay, L, cm);
         sw = SW(); sw.m = m; sw.w = v; sw.ws = &ws;
-        sw.run();
+        run_sweep(sw);
         outs = (WinOuts*)(base + lay.outs);
         if (outs->status != AUGB200_ERR_CAPACITY) break;
     }
@@ -132,7 +146,11 @@ static int sample_impl(void* mp, const char* dna, int L, const int32_t* gc_in, i
     SamplerT<SW> sp; sp.sw = &sw; sp.sc.opt = opts.data(); sp.sc.opt_cap = (int)opts.size(); sp.sc.sorted = sorted.data(); sp.sc.nopt = &nopt;
     sp.rng = rng.data(); sp.nrng = (int)nrng;
     SampleOut so; so.cap = cap; so.begin = sb; so.end = se; so.type = st_; so.trunc = str_; so.count = scount; so.logp = slogp; so.status = status;
+#ifdef AUGB_SIMT32
+    simt::run([&]() { SW mine = sw; mine.attach(); mine.lane = lane_id(); SamplerT<SW> sp2 = sp; sp2.sw = &mine; sp2.run(nsamples, so); });
+#else
     sp.run(nsamples, so);
+#endif
     return *status ? -1 : nsamples;
 }
 extern "C" {
