@@ -242,7 +242,10 @@ def main():
     sweep_ms = dec.last_sweep_ms            # last run's sweep kernel, CUDA events around that launch
     assert all(p.status == 0 for p in paths)
     # ---- end-to-end through the public call, host buffers in, host paths out ----
-    dec.decode_batch_raw(wins_b)                   # untimed warm-up of the public call at full size (pinned + device buffers reach their final size)
+    # untimed warm-up of the public call at full size (pinned + device buffers reach their final size; NCCL sets up its gather)
+    n_st, status, logp, offset, pb, pe, pt, ptr = dec.decode_batch_raw(wins_b)
+    if world > 1:
+        shard.gather_to_rank0(shard.pack_paths(n_st, status, logp, offset, pb, pe, pt, ptr), device="cuda")
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 2))
