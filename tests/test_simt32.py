@@ -49,3 +49,38 @@ def test_forward_and_sampling_kernels_32_lanes():
     dna = util.read_fasta(util.GOLDEN + "/example.fa")[1][1]
     o, e = orc.sample(dna, 30)["samples"], emu.sample(dna, 29)
     assert e["status"] == 0 and all(a["states"] == b["states"] for a, b in zip(e["samples"], o))
+
+
+def test_random_windows_with_class_shifts_n_runs_and_masks():
+    """Small fixed-seed slice of tools/fuzz_simt32.py (composition shifts = GC-class boundaries, N runs, soft-masked runs, tiny
+    windows): 32-lane device flavour == one-lane build on every cell, == oracle on every cell for the models without class-history
+    memos (47 states; fly has one GC class)."""
+    import random
+    for name, cases in (("human", 10), ("fly_softmask_utr", 6)):
+        blob = util.blob_bytes(name)
+        orc, e1, e32 = util.Oracle(blob), util.HostEmu(blob), util.HostEmu(blob, simt32=True)
+        rng = random.Random(31)
+        for _ in range(cases):
+            L = rng.choice([2, 7, 150, 1200, 5000, 8000])
+            parts = []
+            while sum(map(len, parts)) < L:
+                gc = rng.choice([0.3, 0.41, 0.62, 0.7]); at = (1 - gc) / 2
+                parts.append("".join(rng.choices("ACGT", weights=(at, gc / 2, gc / 2, at), k=rng.randint(1, max(1, L // 2)))))
+            s = list("".join(parts)[:L])
+            for _ in range(rng.randint(0, 2)):
+                a = rng.randrange(L)
+                for i in range(a, min(L, a + rng.randint(1, 30))):
+                    s[i] = "N"
+            if "softmask" in name:
+                for _ in range(rng.randint(0, 4)):
+                    a = rng.randrange(L)
+                    for i in range(a, min(L, a + rng.randint(1, 400))):
+                        s[i] = s[i].lower()
+            dna = "".join(s)
+            a, b = e1.decode(dna, want_cells=True), e32.decode(dna, want_cells=True)
+            assert a["status"] == b["status"] == 0 and a["states"] == b["states"] and a["log_prob"] == b["log_prob"] and (a["cells"] == b["cells"]).all()
+            r = orc.viterbi(dna, want_matrix=True)
+            assert b["states"] == r["condensed"] and b["log_prob"] == r["log_prob"]
+            if set(dna.upper()) - {"N"}:
+                V, E = r["V"], b["cells"]
+                assert ((V <= util.NEGT) == (E <= util.NEGT)).all() and (V[V > util.NEGT] == E[V > util.NEGT]).all()
