@@ -12,7 +12,8 @@
 
 namespace augb {
 
-/* AUGB_SIMT: the 32-lane flavour of the source — the device, or tests/hostemu/simt32.h (32 fibers per warp on the CPU, test only) */
+/* AUGB_SIMT: the 32-lane flavour of the source — the device, or (AUGB_SIMT32, set by the test suite only) a CPU executor that runs
+ * 32 fibers per warp and supplies the warp intrinsics; the product library is never built with it */
 #if defined(__CUDA_ARCH__) || defined(AUGB_SIMT32)
 #define AUGB_SIMT 1
 #else
