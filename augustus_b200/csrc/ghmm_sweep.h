@@ -613,11 +613,11 @@ struct SweepT {
         const int wl = gargbest(best, bkey, gl, gmask);       /* winning lane of my group, -1: none */
         if (wballot(wl >= 0) == 0) return;
         double Fv = 0;
-        if (FWD) Fv = wlse(fl).value();                         /* forward kernels evaluate one state per call (gl = all lanes) */
+        if (FWD) Fv = glse(fl, gl).value();                     /* forward value of my group's state */
         AUGB_ROLLED
         for (int g = 0; g < AUGB_NLANES; g += gl) {
             const int wg = wbcast(wl, g);
-            if (wg >= 0) emit(j, wbcast(s, g), wbcast64(best, wg), wbcast(bpred, wg), wbcast(bbase, wg), Fv);
+            if (wg >= 0) emit(j, wbcast(s, g), wbcast64(best, wg), wbcast(bpred, wg), wbcast(bbase, wg), FWD ? wbcastd(Fv, g) : 0.0);
         }
     }
 
@@ -786,7 +786,7 @@ struct SweepT {
 #ifndef AUGB_LESSD_GL
 #define AUGB_LESSD_GL 8
 #endif
-        const int gl = (AUGB_NLANES == 32 && !FWD && !slow) ? AUGB_LESSD_GL : AUGB_NLANES;
+        const int gl = (AUGB_NLANES == 32 && !(FWD && opt) && !slow) ? AUGB_LESSD_GL : AUGB_NLANES;
         const int g0 = lane & ~(gl - 1), li = lane - g0;
         const unsigned gmask = (gl >= 32 ? 0xffffffffu : ((1u << gl) - 1u)) << g0;
         AUGB_ROLLED
@@ -854,11 +854,11 @@ struct SweepT {
             const int wl = gargbest(best, bkey, gl, gmask);
             if (wballot(wl >= 0) == 0) continue;
             double Fv = 0;
-            if (FWD) Fv = wlse(fl).value();
+            if (FWD) Fv = glse(fl, gl).value();
             AUGB_ROLLED
             for (int g = 0; g < AUGB_NLANES; g += gl) {
                 const int wg = wbcast(wl, g);
-                if (wg >= 0) emit(j, wbcast(s, g), wbcast64(best, wg), wbcast(bpred, wg), wbcast(bkey, wg), Fv);
+                if (wg >= 0) emit(j, wbcast(s, g), wbcast64(best, wg), wbcast(bpred, wg), wbcast(bkey, wg), FWD ? wbcastd(Fv, g) : 0.0);
             }
         }
     }
@@ -1034,7 +1034,7 @@ struct SweepT {
             int xs = m->xslot[q], gl = AUGB_NLANES;
 #if AUGB_SIMT
             /* slots 2-4, 5-7, 10-12, 13-15 are the three frames of one kind (set together by the mask): one pass, 8 lanes per frame */
-            if (!FWD && (q == 2 || q == 5 || q == 10 || q == 13) && (slots & (3u << (q + 1))) == (3u << (q + 1))) {
+            if ((q == 2 || q == 5 || q == 10 || q == 13) && (slots & (3u << (q + 1))) == (3u << (q + 1))) {
                 slots &= ~(3u << (q + 1));
                 const int f = lane >> 3;
                 xs = f < 3 ? m->xslot[q + f] : -1; gl = 8;

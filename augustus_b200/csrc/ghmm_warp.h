@@ -112,6 +112,26 @@ struct Lse {
     AUGB_HD bool empty() const { return !(s > 0); }
     AUGB_HD double value() const { return s > 0 ? m + log(s) : -1e308; }
 };
+/* combine the per-lane accumulators of a group of gl lanes (aligned, power of two); every lane gets its group's result */
+AUGB_D Lse glse(Lse a, int gl) {
+#if AUGB_SIMT
+    double M = a.m;
+    for (int o = gl >> 1; o; o >>= 1) { double t = __shfl_xor_sync(0xffffffffu, M, o); M = t > M ? t : M; }
+    double s = a.s > 0 ? a.s * exp(a.m - M) : 0.0;
+    for (int o = gl >> 1; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    Lse r; r.m = M; r.s = s;
+    return r;
+#else
+    return a;
+#endif
+}
+AUGB_D double wbcastd(double v, int src) {
+#if AUGB_SIMT
+    return __shfl_sync(0xffffffffu, v, src);
+#else
+    return v;
+#endif
+}
 /* combine the per-lane accumulators of a warp */
 AUGB_D Lse wlse(Lse a) {
     double M = wmaxd(a.m);

@@ -44,11 +44,15 @@ def test_71_state_utr_models():
 
 
 def test_forward_and_sampling_kernels_32_lanes():
-    blob = util.blob_bytes()
-    orc, emu = util.Oracle(blob), util.HostEmu(blob, simt32=True)
-    dna = util.read_fasta(util.GOLDEN + "/example.fa")[1][1]
-    o, e = orc.sample(dna, 30)["samples"], emu.sample(dna, 29)
-    assert e["status"] == 0 and all(a["states"] == b["states"] for a, b in zip(e["samples"], o))
+    """forward fill with the frames of a kind in one pass (per-group log-sum-exp) + the sampling walks: sampled paths == oracle"""
+    for name, fa, sl, ns in (("human", "example.fa", slice(0, 2344), 30), ("human", "example.fa", slice(0, 6000), 12),
+                             ("fly_softmask_utr", "fly_softmask_window.fa", slice(2000, 11000), 20)):
+        blob = util.blob_bytes(name)
+        orc, emu = util.Oracle(blob), util.HostEmu(blob, simt32=True)
+        seqs = util.read_fasta(util.GOLDEN + "/" + fa)
+        dna = (seqs[1][1] if sl.stop == 2344 else seqs[0][1])[sl]
+        o, e = orc.sample(dna, ns)["samples"], emu.sample(dna, ns - 1)
+        assert e["status"] == 0 and len(e["samples"]) == ns - 1 and all(a["states"] == b["states"] for a, b in zip(e["samples"], o))
 
 
 def test_random_windows_with_class_shifts_n_runs_and_masks():
@@ -84,3 +88,19 @@ def test_random_windows_with_class_shifts_n_runs_and_masks():
             if set(dna.upper()) - {"N"}:
                 V, E = r["V"], b["cells"]
                 assert ((V <= util.NEGT) == (E <= util.NEGT)).all() and (V[V > util.NEGT] == E[V > util.NEGT]).all()
+
+
+def test_forward_matrix_32_lanes_matches_oracle():
+    """ln forward of every cell from the grouped forward fill against the oracle's forward matrix (the reference's LLDouble values are
+    pinned to the oracle's in test_oracle): same zero pattern, values within 1e-9 (they differ by summation order only)."""
+    for name, fa, n in (("human", "example.fa", 5000), ("human_utr", "example.fa", 4000)):
+        blob = util.blob_bytes(name)
+        orc, emu = util.Oracle(blob), util.HostEmu(blob, simt32=True)
+        dna = util.read_fasta(util.GOLDEN + "/" + fa)[0][1][:n]
+        Fo = orc.sample(dna, 2, want_forward=True)["F"]
+        Fo = np.where(Fo < -1e300, -np.inf, Fo)
+        r = emu.forward(dna)
+        assert r["status"] == 0
+        F = r["F"]; fin = np.isfinite(F)
+        assert (np.isfinite(Fo) == fin).all()
+        assert np.abs(F[fin] - Fo[fin]).max() <= 1e-9

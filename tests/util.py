@@ -217,6 +217,28 @@ class HostEmu:
             pos += c
         return {"status": status.value, "samples": out}
 
+    def forward(self, dna: str, gc=None):
+        """ln forward of every cell as a dense (L, S) matrix (-inf = zero) from the forward fill of the kernel source."""
+        self.lib.hostemu_forward.restype = ctypes.c_int
+        self.lib.hostemu_forward.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 6
+        self.lib.hostemu_chain_state.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L = len(dna); S = self.lib.hostemu_statecount(ctypes.c_void_p(self.m))
+        cap = 48 * L + 256
+        col, st, F = np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=np.int32), np.zeros(cap)
+        nev, status = ctypes.c_int32(), ctypes.c_int32()
+        chainF = np.zeros((L, self.NCHAIN))
+        gci = None if gc is None else np.ascontiguousarray(gc, dtype=np.int32)
+        self.lib.hostemu_forward(self.m, dna.encode(), L, None if gci is None else gci.ctypes.data, cap, col.ctypes.data, st.ctypes.data, F.ctypes.data,
+                                 ctypes.byref(nev), chainF.ctypes.data, ctypes.byref(status))
+        out = np.full((L, S), -np.inf)
+        n = nev.value
+        out[col[:n], st[:n]] = F[:n]
+        for ch in range(self.NCHAIN):
+            cs = self.lib.hostemu_chain_state(ctypes.c_void_p(self.m), ch)
+            if cs >= 0:
+                v = chainF[:, ch]; out[:, cs] = np.where(v < -1e300, -np.inf, v)
+        return {"status": status.value, "F": out}
+
     def decode(self, dna: str, gc=None, want_cells=False, S=None):
         L = len(dna)
         S = S or self.lib.hostemu_statecount(ctypes.c_void_p(self.m))
