@@ -219,6 +219,12 @@ static void build_params(NAMGene& ng, FeatureCollection& fc, BlobWriter& bw) {
     const char* dummy = "acgtacgtacgtacgtacgtacgtacgtacgt";
     StateModel::sequence = dummy; StateModel::dnalen = strlen(dummy);
     IntronModel::initSnippetProbs();
+    static SequenceFeatureCollection nc_sfc(&fc);     // NcModel::initAlgorithms reads hints through StateModel::seqFeatColl (ncmodel.cc:744)
+    if (Constant::nc_option_on) {
+        nc_sfc.setSeqLen(strlen(dummy));
+        if (!StateModel::seqFeatColl) StateModel::setSFC(&nc_sfc);
+        NcModel::initSnippetProbs();
+    }
     ng.initAlgorithms();
     for (int c = 0; c < C; c++) {
         ng.updateToLocalGCEach(c, 2, 1);

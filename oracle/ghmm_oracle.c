@@ -50,9 +50,10 @@ enum { T_IGENIC = 0, T_SINGLE = 1, T_INITIAL0 = 2, T_INTERNAL0 = 5, T_TERMINAL =
        T_LESSD0 = 9, T_LONGDSS0 = 10, T_EQUALD0 = 11, T_GEO0 = 12, T_LONGASS0 = 13,
        T_RSINGLE = 36, T_RINITIAL = 37, T_RINTERNAL0 = 38, T_RTERMINAL0 = 41,
        T_RLESSD0 = 44, T_RLONGDSS0 = 45, T_REQUALD0 = 46, T_RGEO0 = 47, T_RLONGASS0 = 48 };
-enum { K_IGENIC, K_EXON, K_LESSD, K_LONGDSS, K_EQUALD, K_GEO, K_LONGASS, K_UTR };
+enum { K_IGENIC, K_EXON, K_LESSD, K_LONGDSS, K_EQUALD, K_GEO, K_LONGASS, K_UTR, K_NC };
 enum { U_SINGLE, U_INIT, U_INTRON, U_INTRONVAR, U_INTERNAL, U_TERM };     /* order of the utr5.. / utr3.. types, types.hh:498-499 */
 enum { T_UTR5SINGLE = 24, T_UTR3SINGLE = 30, T_UTR3TERM = 35, T_RUTR5SINGLE = 59, T_RUTR3SINGLE = 65 };
+enum { T_NCSINGLE = 74, T_RNCSINGLE = 80 };   /* ncsingle, ncinit, ncintron, ncintronvar, ncinternal, ncterm; then the reverse six (types.hh:508-511) */
 enum { E_SINGLE, E_INITIAL, E_INTERNAL, E_TERMINAL, E_RSINGLE, E_RINITIAL, E_RINTERNAL, E_RTERMINAL };
 
 typedef struct {
@@ -83,6 +84,7 @@ typedef struct {
     double centroids[64][4]; int ncent; double wm[4][4];
     int softmask; sc_t nep_bonus;               /* softmasking: ln bonus of a nonexonpart hint of source RM (extrinsicinfo.cc:1696-1724) */
     /* UtrModel (utrmodel.cc), only with --UTR=on */
+    int nc;                                     /* NcModel states present (--nc=on) */
     int utr, utr_k, tssup_k, tss_start, tss_end, tata_start, tata_end, d_tata_min, d_tata_max, tuw, dpc, boxlen, tts_spacing;
     int umax, umax3s, umax3t;
     sc_t *u5i, *u5, *u3, *tup;                   /* [c][4^(k+1)] */
@@ -124,6 +126,10 @@ static sc_t* qarr(const Blob* b, const char* name, size_t* n) {
 static void classify(StateInfo* s, const Model* m) {
     int t = s->type;
     s->fwd = (t < 36); s->frame = 0; s->uk = -1;
+    if (t >= T_NCSINGLE && t < T_NCSINGLE + 12) {          /* NcModel::NcModel, ncmodel.cc:41-44: uk = position in the six nc types */
+        s->kind = K_NC; s->fwd = t < T_RNCSINGLE; s->uk = (t - T_NCSINGLE) % 6; s->u5 = 0;
+        return;
+    }
     if (t == T_IGENIC) { s->kind = K_IGENIC; s->fwd = 1; return; }
     int e = -1;
     if (t == T_SINGLE) { e = E_SINGLE; }
@@ -213,7 +219,8 @@ Model* orc_model_load(const char* path) {
     if (bhas(&b, "softmasking")) { m->softmask = bint(&b, "softmasking"); m->nep_bonus = q(bdbl(&b, "softmask_bonus")); }   /* absent in older blobs: off */
     if (m->softmask && !bint(&b, "extrinsic_malus_all_one")) { fprintf(stderr, "oracle: extrinsic configurations with a malus are not restated\n"); return NULL; }
     m->utr = bint(&b, "utr_option_on");
-    if (bint(&b, "nc_option_on")) { fprintf(stderr, "oracle: nc states not restated\n"); return NULL; }
+    m->nc = bint(&b, "nc_option_on");
+    if (m->nc && (!m->utr || m->softmask)) { fprintf(stderr, "oracle: nc states are restated for --UTR=on --softmasking=0 only\n"); return NULL; }
     if (m->utr) {
         m->utr_k = bint(&b, "utr_k"); m->tssup_k = bint(&b, "tssup_k");
         if (m->utr_k != m->k) { fprintf(stderr, "oracle: mixed k unsupported\n"); return NULL; }
@@ -273,7 +280,7 @@ typedef struct {
     int* pmask;                                 /* softmasking: pmask[i] = number of lower-case input bases before i; [L+1] */
     int cur_gc;                                 /* NAMGene::curGCIdx */
     int walking;                                /* 1 while backtracking / sampling (algovar doBacktracking / doSampling) */
-    sc_t* seg[7];                               /* SegProbs::cumProds, [L+1], NEG = 0 = not computed */
+    sc_t* seg[8];                               /* SegProbs::cumProds, [L+1], NEG = 0 = not computed; [7] = NcModel::segProbs */
     sc_t *tssP[2], *ttsP[2];                    /* tssProbsPlus/Minus memo (UNSET = -1), ttsProbPlus/Minus; index 0 = plus */
     struct Eop { int *v, n, cap, it, inCache; } *eop;   /* EOPList per state */
     int eop_off;                                /* debugging: 1 = scan every endOfPred (no EOPList) */
@@ -914,13 +921,14 @@ static void exon_eval(Ctx* x, int s, int j, Oli* o) {
 /* ================================================================== UTR states, utrmodel.cc */
 #define UNSET ((sc_t)1 << 62)
 enum { SG_RINIT5, SG_INIT5, SG_3, SG_R3, SG_INTRON, SG_5, SG_R5 };        /* UtrModel::initSnippetProbs, utrmodel.cc:701-712 */
-static const int seg_fwd[7] = { 0, 1, 1, 0, 1, 1, 0 };
+enum { SG_NC = 7 };                                                         /* NcModel::initSnippetProbs, ncmodel.cc:95-100: intron content, forward */
+static const int seg_fwd[8] = { 0, 1, 1, 0, 1, 1, 0, 1 };
 static const sc_t* seg_table(const Ctx* x, int g) {                        /* the static table the SegProbs points at: current class */
     const Model* m = x->m; size_t w = (size_t)1 << (2 * (m->k + 1));
     switch (g) {
     case SG_RINIT5: case SG_INIT5: return m->u5i + x->cls * w;
     case SG_3: case SG_R3: return m->u3 + x->cls * w;
-    case SG_INTRON: return m->iemi + x->cls * w;
+    case SG_INTRON: case SG_NC: return m->iemi + x->cls * w;
     default: return m->u5 + x->cls * w;
     }
 }
@@ -1038,6 +1046,7 @@ static void utr_update_gc(Ctx* x, int from, int to) {
     for (int i = from; i < to && i >= 0; i++) x->tssP[0][i] = x->tssP[1][i] = UNSET;
     compute_tts(x, from, to);
     for (int g = 0; g < 7; g++) seg_set(x, g, from, to + 5);
+    if (x->m->nc) seg_set(x, SG_NC, from, to);                                /* NcModel::updateToLocalGC, ncmodel.cc:125-127 */
 }
 
 /* EOPList, statemodel.cc:473-520.  it == n plays the role of end(); dereferencing end() of a libstdc++ std::list<int>
@@ -1289,11 +1298,115 @@ static void utr_eval(Ctx* x, int s, int j, Oli* o) {
     }
 }
 
+/* ------------------------------------------------------------------ NcModel (ncmodel.cc), --nc=on, no hints
+ *
+ * Transcript boundaries of non-coding genes exist only where hints put them (precomputeTxEndProbs, ncmodel.cc:744-826: without tss /
+ * tts / exonpart hints all four tss / tts arrays are zero), so ab initio the states that begin or end with a transcript boundary
+ * (ncsingle, ncinit, ncterm, rncsingle, rncinit, rncterm) never hold a cell beyond column 0, the hint-only ncintronvar / rncintronvar
+ * neither; ncintron / rncintron (one base, self loop) and ncinternal / rncinternal (splice site to splice site) live on the initial
+ * probabilities of column 0.  The evaluation order, the aSSProb calls (they feed the memo shared with IntronModel) and the EOPList of the
+ * reference are kept for every state. */
+static void nc_end_positions(const Ctx* x, const StateInfo* st, int end, int* boe, int* eobe) {     /* NcModel::getEndPositions :702-725 */
+    const Model* m = x->m; int DW = m->dss_start + m->dss_end + 2, AW = m->ass_start + m->ass_end + 2;
+    *boe = end + 1; *eobe = end;
+    if (st->fwd && (st->uk == U_INTERNAL || st->uk == U_INIT)) { *boe = end - DW + 1; *eobe = end - m->dss_end - 2; }
+    else if (!st->fwd && (st->uk == U_INTERNAL || st->uk == U_TERM)) { *boe = end - AW - m->ass_up + 1; *eobe = end - m->ass_up - m->ass_start - 2; }
+}
+static sc_t nc_endPart(Ctx* x, const StateInfo* st, int begin, int end) {                              /* NcModel::endPartEmiProb :366-441, no hints */
+    const Model* m = x->m;
+    if (st->uk == U_INTRON) return 0;
+    if (st->uk == U_INTRONVAR) {
+        if (st->fwd) return possASS(x, end + m->ass_up + m->ass_start + 2) ? 0 : NEG;
+        return possRDSS(x, end + m->dss_end + 2) ? 0 : NEG;
+    }
+    if (st->fwd) {
+        if (st->uk == U_SINGLE || st->uk == U_TERM) return NEG;                 /* ttsProbPlus[end] = 0 without hints */
+        return dSSProb(x, begin, 1);                                            /* ncinit, ncinternal */
+    }
+    if (st->uk == U_SINGLE || st->uk == U_INIT) return NEG;                     /* tssProbMinus[end] = 0 without hints */
+    return aSSProb(x, begin, 0);                                                /* rncterm, rncinternal */
+}
+static sc_t nc_notEndPart(Ctx* x, const StateInfo* st, int begin, int endOfMiddle, int eobe) {        /* NcModel::notEndPartEmiProb :447-676, no hints */
+    const Model* m = x->m; int DW = m->dss_start + m->dss_end + 2, AW = m->ass_start + m->ass_end + 2;
+    sc_t beginPart, middle = 0; int bobe, bom;
+    if (st->uk == U_INTRON) {                                                   /* :528-539: content of the base(s), current class */
+        for (int pos = begin; pos <= endOfMiddle; pos++) {
+            int pn = pos - m->k >= 0 ? s2i(x, pos - m->k, m->k + 1) : -1;
+            middle += pn < 0 ? m->log025 : m->iemi[((size_t)x->cls << (2 * (m->k + 1))) | pn];
+        }
+        return middle;
+    }
+    if (st->uk == U_INTRONVAR) return NEG;                                      /* (never asked: the caller handles hint introns only) */
+    if (st->fwd) {
+        if (st->uk == U_SINGLE || st->uk == U_INIT) return NEG;                 /* tssProbPlus[begin] = 0 */
+        bobe = begin + m->ass_up + m->ass_start + 2;
+        if (st->uk == U_TERM && bobe >= x->L) return NEG;
+        beginPart = aSSProb(x, begin, 1);                                       /* ncinternal :471-479, ncterm :480-495 */
+        if (isneg(beginPart)) return NEG;
+        bom = begin + m->ass_up + AW;
+        if (st->uk == U_TERM && endOfMiddle - bom + 1 < 0) middle = -m->log025 * (sc_t)(-(endOfMiddle - bom + 1));
+        else middle = seg_get(x, SG_NC, bom, endOfMiddle);
+    } else {
+        if (st->uk == U_SINGLE || st->uk == U_TERM) return NEG;                 /* ttsProbMinus[begin] = 0 */
+        beginPart = dSSProb(x, begin, 0);                                       /* rncinternal :505-513, rncinit :526-534 */
+        if (isneg(beginPart)) return NEG;
+        bobe = begin + m->dss_end + 2; bom = begin + DW;
+        middle = seg_get(x, SG_NC, bom, endOfMiddle);
+    }
+    int len = eobe - bobe + 1;
+    if (len < 0 || len >= m->n_ld_exon) { fprintf(stderr, "oracle: nc exon length %d outside the distribution\n", len); exit(4); }
+    sc_t lp = m->ld_internal[len];                                              /* NcModel::lenDistInternal = ExonModel::lenDistInternal :146 */
+    if (isneg(lp) || isneg(middle)) return NEG;
+    return beginPart + middle + lp;
+}
+static void nc_eval(Ctx* x, int s, int j, Oli* o) {                                                    /* NcModel::viterbiForwardAndSampling :154-359 */
+    const Model* m = x->m; const StateInfo* st = &m->st[s]; int base = j;
+    int DW = m->dss_start + m->dss_end + 2, AW = m->ass_start + m->ass_end + 2;
+    o->max = NEG; o->state = -1; o->base = -1;
+    int boe, eobe, lm, rm;
+    nc_end_positions(x, st, base, &boe, &eobe);
+    switch (st->uk) {
+    case U_SINGLE: lm = base - m->max_exon_len; rm = base - 1; break;
+    case U_INIT: lm = base - (m->max_exon_len + 2 + m->dss_end); rm = base - DW; break;
+    case U_INTERNAL: lm = base - (m->max_exon_len + 2 + m->dss_end + m->ass_up + m->ass_start + 2); rm = base - 2 - m->dss_end - m->ass_up - m->ass_start - 2 - 1; break;
+    case U_TERM: lm = base - (m->max_exon_len + m->ass_up + m->ass_start + 2); rm = base - m->ass_up - AW; break;
+    default: lm = rm = base - 1;
+    }
+    sc_t ep = boe >= 0 ? nc_endPart(x, st, boe, base) : NEG;
+    if (isneg(ep)) return;
+    if (st->uk == U_INTRONVAR) return;                                          /* only through intron hints (:286-330) */
+    if (lm < 0) lm = 0;
+    if (st->uk != U_INTRON) {                                                   /* no exon hints: at most 200 bases back (:219-235) */
+        int minE = rm + 1;
+        if (minE > lm) { lm = minE; if (lm > rm - 200) { lm = rm - 200; if (lm < 0) lm = 0; } }
+    }
+    struct Eop* e = &x->eop[s];
+    const int use_eop = st->uk != U_INTRON && !x->eop_off;                      /* (leftMost == rightMost for the one-base introns: the list never matters) */
+    if (x->walking) e->n = 0;
+    e->it = 0; e->inCache = 0;
+    for (int endOfPred = rm; endOfPred >= lm; use_eop ? eop_decrement(e, &endOfPred) : (void)endOfPred--) {
+        int col = endOfPred > 0 ? endOfPred : 0, i0 = 0;
+        while (i0 < st->nanc && isneg(PVAL(x, col, st->anc[i0]))) i0++;
+        if (i0 == st->nanc) continue;
+        sc_t nep = nc_notEndPart(x, st, endOfPred + 1, boe - 1, eobe);
+        if (isneg(nep)) continue;
+        if (use_eop) eop_update(e, endOfPred);
+        for (int i = i0; i < st->nanc; i++) {
+            int a = st->anc[i]; sc_t pv = PVAL(x, col, a); if (isneg(pv)) continue;
+            sc_t te = TR(a, s) + (nep + ep);                                    /* (malus(intronF) = 1 without a hints file, :266-268) */
+            fwd_option(x, a, col, endOfPred, te);
+            sc_t pp = pv + te;
+            if (pp > o->max) { o->max = pp; o->state = a; o->base = endOfPred; }
+        }
+    }
+}
+
 static void state_eval(Ctx* x, int s, int j, Oli* o) {
     switch (x->m->st[s].kind) {
     case K_IGENIC: igenic_eval(x, s, j, o); break;
     case K_EXON: exon_eval(x, s, j, o); break;
     case K_UTR: utr_eval(x, s, j, o); break;
+    case K_NC: nc_eval(x, s, j, o); break;
     default: intron_eval(x, s, j, o);
     }
 }
@@ -1391,7 +1504,7 @@ int orc_decode(const Model* m, const char* dna, int L, const int* gc_in, int64_t
     for (int g = 0; g < 2; g++) { x->assMemo[g] = (sc_t*)malloc((size_t)(L + 1) * sizeof(sc_t)); x->assMemoGen[g] = (int*)calloc(L + 1, sizeof(int)); }
     x->assGen = 1; x->assN = 0;
     if (m->utr) {
-        for (int g = 0; g < 7; g++) { x->seg[g] = (sc_t*)malloc((size_t)(L + 1) * sizeof(sc_t)); for (int i = 0; i <= L; i++) x->seg[g][i] = NEG; }
+        for (int g = 0; g < (m->nc ? 8 : 7); g++) { x->seg[g] = (sc_t*)malloc((size_t)(L + 1) * sizeof(sc_t)); for (int i = 0; i <= L; i++) x->seg[g][i] = NEG; }
         for (int g = 0; g < 2; g++) {
             x->tssP[g] = (sc_t*)malloc((size_t)(L + 1) * sizeof(sc_t)); x->ttsP[g] = (sc_t*)malloc((size_t)(L + 1) * sizeof(sc_t));
             for (int i = 0; i <= L; i++) { x->tssP[g][i] = UNSET; x->ttsP[g][i] = NEG; }
