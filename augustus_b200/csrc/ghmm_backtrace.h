@@ -39,7 +39,7 @@ AUGB_HD void backtrace_window(const DevModel* m, const WinView& w, PathOut o) {
     for (int s = 0; s < S; s++) {
         sc_t t = m->term[s]; if (isneg(t)) continue;
         sc_t v = SC_NEG; int ch = m->st[s].chain;
-        if (ch >= 0) { if (ncp[ch] > 0) v = w.cp(ch)[ncp[ch] - 1].tilde + (ch == 0 ? w.AIG[L - 1] : ch < CH_UTR ? w.AGEO[L - 1] : w.AINT[L - 1] + (sc_t)(L - 1) * m->utr_tself); }
+        if (ch >= 0) { if (ncp[ch] > 0) v = w.cp(ch)[ncp[ch] - 1].tilde + (ch == 0 ? w.AIG[L - 1] : ch < CH_UTR ? w.AGEO[L - 1] : w.AINT[L - 1] + (sc_t)(L - 1) * (ch < CH_NC ? m->utr_tself : m->nc_tself)); }
         else { for (int i = w.evstart[L - 1]; i < w.evstart[L]; i++) if (w.ev[i].state == s) v = w.ev[i].V; }
         if (isneg(v)) continue;
         v += t;

@@ -47,9 +47,10 @@ AUGB_HD int mod3(int k) { return (int)((unsigned)(k + 3 * (1 << 28)) % 3u); }
 
 constexpr int MAXS = 96;      /* states */
 constexpr int MAXC = 8;       /* GC classes */
-constexpr int MAXANC = 8;
-constexpr int NCHAIN = 11;    /* igenic + 3 geometric + 3 reverse geometric + 4 UTR introns (utr5, utr3, rutr5, rutr3) */
+constexpr int MAXANC = 12;   /* (the intergenic state of the 83-state model has 10) */
+constexpr int NCHAIN = 13;    /* igenic + 3 geometric + 3 reverse geometric + 4 UTR introns (utr5, utr3, rutr5, rutr3) + ncintron, rncintron */
 constexpr int CH_UTR = 7;     /* first UTR-intron chain */
+constexpr int CH_NC = 11;     /* ncintron, rncintron (NcModel, --nc=on) */
 constexpr int WF_ALLN = 1 << 8;
 constexpr int WF_NOSLAB = 1 << 9;     /* the prefix-array pool ran out: decode this window again with the generous layout */
 
@@ -59,9 +60,11 @@ enum : int {
     T_LESSD0 = 9, T_LONGDSS0 = 10, T_EQUALD0 = 11, T_GEO0 = 12, T_LONGASS0 = 13,
     T_RSINGLE = 36, T_RINITIAL = 37, T_RINTERNAL0 = 38, T_RTERMINAL0 = 41,
     T_RLESSD0 = 44, T_RLONGDSS0 = 45, T_REQUALD0 = 46, T_RGEO0 = 47, T_RLONGASS0 = 48,
-    T_UTR5SINGLE = 24, T_UTR3SINGLE = 30, T_UTR3TERM = 35, T_RUTR5SINGLE = 59, T_RUTR3TERM = 70
+    T_UTR5SINGLE = 24, T_UTR3SINGLE = 30, T_UTR3TERM = 35, T_RUTR5SINGLE = 59, T_RUTR3TERM = 70,
+    T_NCSINGLE = 74, T_RNCSINGLE = 80      /* ncsingle, ncinit, ncintron, ncintronvar, ncinternal, ncterm; then the reverse six */
 };
-enum : int { K_IGENIC, K_EXON, K_LESSD, K_LONGDSS, K_EQUALD, K_GEO, K_LONGASS, K_UTR };
+enum : int { K_IGENIC, K_EXON, K_LESSD, K_LONGDSS, K_EQUALD, K_GEO, K_LONGASS, K_UTR,
+             K_DEAD /* nc states that need a transcript boundary: zero without hints, only their column-0 cell exists (ncmodel.cc:744-826) */ };
 enum : int { U_SINGLE, U_INIT, U_INTRON, U_INTRONVAR, U_INTERNAL, U_TERM };      /* order of the utr5.. / utr3.. types (types.hh:498-499) */
 enum : int { E_SINGLE, E_INITIAL, E_INTERNAL, E_TERMINAL, E_RSINGLE, E_RINITIAL, E_RINTERNAL, E_RTERMINAL };
 
@@ -104,7 +107,7 @@ enum : int { PA_PI = 0, PA_PIR = 1, PA_PX = 2 /* +phi */, PA_PXR = 5 /* +phi */,
  * begin signal + content prefix difference + length distribution, all table driven */
 enum : int { BS_NONE, BS_TSSF, BS_ASSF, BS_DSSR, BS_TTSR };           /* begin signal */
 enum : int { UE_ATG, UE_DSSF, UE_TTSF, UE_TSSR, UE_ASSR, UE_RSTOP };  /* end part (utrmodel.cc:1072-1110) */
-enum : int { US_INIT5 = 0, US_5 = 1, US_3 = 2, US_RINIT5 = 3, US_R5 = 4, US_R3 = 5, NUSEG = 6 };   /* SegProbs arrays (utrmodel.cc:701-712) */
+enum : int { US_INIT5 = 0, US_5 = 1, US_3 = 2, US_RINIT5 = 3, US_R5 = 4, US_R3 = 5, US_NC = 6 /* NcModel::segProbs: intron content */, NUSEG = 7 };   /* SegProbs arrays (utrmodel.cc:701-712) */
 struct UtrDesc {
     int8_t list;            /* candidate list */
     int8_t begsig, endkind, seg;
@@ -151,11 +154,12 @@ struct DevModel {
     int umax, umax3s, umax3t;
     int tssm_n, tssm_k, tsstm_n, tsstm_k, tatam_n, tatam_k, ttsm_n, ttsm_k;
     int8_t r_utr[2][2][6];          /* [rev][5'][U_*] -> state */
-    UtrDesc ud[16]; int8_t uslot[16];   /* UTR exon states: descriptors and state index per slot */
+    UtrDesc ud[18]; int8_t uslot[18];   /* UTR exon states: descriptors and state index per slot; 16, 17 = ncinternal, rncinternal */
     const sc_t *u5i, *u5, *u3, *tup;    /* content tables [c << 2(k+1) | kmer] */
     const sc_t *tssm, *tsstm, *tatam, *ttsm, *aataaa;
-    const sc_t* uld[10]; int n_uld[10]; /* 5single,5init,5internal,5term,3single,3init,3internal,3term, tail5single, tail3single */
+    const sc_t* uld[11]; int n_uld[11]; /* 5single,5init,5internal,5term,3single,3init,3internal,3term, tail5single, tail3single, nc internal (= coding internal) */
     sc_t log_polya, log_nopolya, log2, utr_tself;
+    int nc; sc_t nc_tself;             /* NcModel states present; self transition of ncintron / rncintron */
     uint8_t isstart[64];
 };
 
@@ -202,7 +206,7 @@ enum : int { CL_LD = 0 /* +f: longdss_f */, CL_RA = 3 /* +f: rlongass_f */, CL_L
              CL_R5I = 15 /* rDSS, rutr5intron, for rutr5init */, CL_R5N = 16 /* the same sites for rutr5internal (other content table) */,
              CL_R3 = 17 /* rDSS, rutr3intron */, CL_TR = 18 /* reverse polyA, igenic */, CL_X3 = 19 /* single, terminal cells */,
              CL_XRS = 20 /* rsingle, rinitial cells for rutr5single */, CL_XRT = 21 /* the same cells for rutr5term */,
-             NCL = 22 };
+             CL_NCA = 22 /* ASS, ncintron */, CL_NCR = 23 /* rDSS, rncintron */, NCL = 24 };
 /* An entry of a UTR list holds V[col][pred] + g, g = begin-signal score - SegProbs cumulative sum just before the middle part of an exon
  * that begins at col + 1: everything of a candidate's score that does not depend on where the exon ends (forward mode keeps g beside
  * ln F in WinView::clG). */

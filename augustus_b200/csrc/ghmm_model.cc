@@ -48,6 +48,14 @@ static void classify(StateDesc& s, const DevModel& m) {
         return;
     }
     s.uk = -1; s.u5 = 0;
+    if (t >= T_NCSINGLE && t < T_NCSINGLE + 12) {
+        /* NcModel (ncmodel.cc).  Without hints a transcript boundary of a non-coding gene has probability zero (precomputeTxEndProbs,
+         * :744-826), so only the one-base intron and the splice-site-to-splice-site internal exon ever hold cells beyond column 0 */
+        if (!m.utr || !m.nc) return;
+        s.fwd = t < T_RNCSINGLE; s.uk = (int8_t)((t - T_NCSINGLE) % 6); s.u5 = 2;
+        s.kind = (s.uk == U_INTRON || s.uk == U_INTERNAL) ? K_UTR : K_DEAD;
+        return;
+    }
     if ((t >= T_UTR5SINGLE && t <= T_UTR3TERM) || (t >= T_RUTR5SINGLE && t <= T_RUTR3TERM)) {
         if (!m.utr) return;
         int o = t - (s.fwd ? T_UTR5SINGLE : T_RUTR5SINGLE);
@@ -83,12 +91,13 @@ int HostModel::build(const void* blob, size_t nbytes) {
     if (m.S < 1 || m.S > MAXS || m.C < 1 || m.C > MAXC) { err = "state / class count out of range"; return AUGB200_ERR_UNSUPPORTED; }
     if (ik != m.k || gk != m.k || m.k < 1 || m.k > 4) { err = "content model orders must be equal and <= 4"; return AUGB200_ERR_UNSUPPORTED; }
     if (nbins > 0) { err = "TRANSINITBIN models are not supported yet"; return AUGB200_ERR_UNSUPPORTED; }
-    if (nc) { err = "nc state models are not supported yet"; return AUGB200_ERR_UNSUPPORTED; }
-    m.utr = utr ? 1 : 0;
+    m.utr = utr ? 1 : 0; m.nc = nc ? 1 : 0;
+    if (nc && !utr) { err = "nc states need the UTR states"; return AUGB200_ERR_UNSUPPORTED; }
     if (r.b.find("softmasking")) {          /* blobs written before softmasking support carry no entry: off */
         m.softmask = r.i32("softmasking") ? 1 : 0; m.nep_bonus = quantize(r.f64("softmask_bonus"));
         if (m.softmask && !r.i32("extrinsic_malus_all_one")) { err = "extrinsic configurations with a malus are not supported"; return AUGB200_ERR_UNSUPPORTED; }
     }
+    if (m.nc && m.softmask) { err = "nc states with softmasking are not supported yet"; return AUGB200_ERR_UNSUPPORTED; }
     m.dStateLen = m.d - 2 - m.dss_end - m.ass_start - 2 - m.ass_up;     /* intronmodel.cc:519-520 */
     if (m.dStateLen < 1) { err = "d too small"; return AUGB200_ERR_UNSUPPORTED; }
 
@@ -190,7 +199,7 @@ int HostModel::build(const void* blob, size_t nbytes) {
     m.r_single = m.r_terminal = m.r_rsingle = m.r_rinitial = -1;
     for (int f = 0; f < 3; f++) m.r_initial[f] = m.r_internal[f] = m.r_rinternal[f] = m.r_rterminal[f] = -1;
     for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) for (int c = 0; c < 6; c++) m.r_utr[a][b][c] = -1;
-    for (int i = 0; i < 16; i++) m.uslot[i] = -1;
+    for (int i = 0; i < 18; i++) m.uslot[i] = -1;
     const sc_t* T = tab.data() + o_trans;
     for (int s = 0; s < m.S; s++) {
         StateDesc& sd = m.st[s]; sd.type = (int16_t)stt[s]; classify(sd, m);
@@ -206,6 +215,12 @@ int HostModel::build(const void* blob, size_t nbytes) {
                 if (isneg(T[((size_t)c * m.S + a) * m.S + s]) != isneg(T[(size_t)a * m.S + s])) { err = "transition support differs between GC classes"; return AUGB200_ERR_UNSUPPORTED; }
         int dir = sd.fwd ? 0 : 1, f = sd.frame;
         int8_t* slot = nullptr;
+        if (sd.u5 == 2) {                      /* nc states: two chains, two table-driven exon states, the rest never evaluated */
+            if (sd.uk == U_INTRON) { sd.chain = (int8_t)(CH_NC + dir); slot = &m.chain_state[sd.chain]; }
+            else if (sd.uk == U_INTERNAL) { sd.ek = (int8_t)(16 + dir); slot = &m.uslot[16 + dir]; }
+            if (slot) { if (*slot >= 0) { err = "duplicate state role"; return AUGB200_ERR_UNSUPPORTED; } *slot = (int8_t)s; }
+            continue;
+        }
         switch (sd.kind) {
         case K_IGENIC: sd.chain = 0; slot = &m.chain_state[0]; break;
         case K_GEO: sd.chain = (int8_t)(1 + dir * 3 + f); slot = &m.chain_state[sd.chain]; break;
@@ -276,9 +291,26 @@ int HostModel::build(const void* blob, size_t nbytes) {
             /* every endOfPred of the loop must index the length table: lm_off bounds the length */
             if (u.rm_off < 1) { err = "UTR geometry lets a state end before it begins"; return AUGB200_ERR_UNSUPPORTED; }
         }
+        if (m.nc) {
+            /* ncinternal: acceptor site after ncintron ... donor site; rncinternal: reverse donor after rncintron ... reverse acceptor.
+             * NcModel::viterbiForwardAndSampling (ncmodel.cc:186-235): rightMost as for a UTR internal exon with minimum length 1, and
+             * without exon hints leftMost = rightMost - 200; getEndPositions :702-725; notEndPartEmiProb :471-479, :505-513; the
+             * content is NcModel::segProbs (intron emissions), the length distribution the coding internal one (:146) */
+            const int16_t rm = (int16_t)(DE + UP + AS + 5);
+            m.ud[16] = UtrDesc{CL_NCA, BS_ASSF, UE_DSSF, US_NC, 0, 0, (int16_t)(UP + AW), (int16_t)(UP + AS + 2), (int16_t)(rm + 200), rm, (int16_t)(-(DE + 2)), (int16_t)(-DW + 1), 0, 10};
+            m.ud[17] = UtrDesc{CL_NCR, BS_DSSR, UE_ASSR, US_NC, 0, 0, (int16_t)DW, (int16_t)(DE + 2), (int16_t)(rm + 200), rm, (int16_t)(-(UP + AS + 2)), (int16_t)(-AW - UP + 1), 0, 10};
+            bool haven = false;
+            for (int ch = CH_NC; ch < NCHAIN; ch++) {
+                int cs = m.chain_state[ch]; if (cs < 0) continue;
+                for (int c = 0; c < m.C; c++) {
+                    sc_t t = T[((size_t)c * m.S + cs) * m.S + cs];
+                    if (!haven) { m.nc_tself = t; haven = true; } else if (t != m.nc_tself) { err = "nc intron self-loops differ"; return AUGB200_ERR_UNSUPPORTED; }
+                }
+            }
+        }
         /* the four UTR-intron chains share the intron emission prefix and need one class-independent self transition */
         bool have = false;
-        for (int ch = CH_UTR; ch < NCHAIN; ch++) {
+        for (int ch = CH_UTR; ch < CH_NC; ch++) {
             int cs = m.chain_state[ch]; if (cs < 0) continue;
             for (int c = 0; c < m.C; c++) {
                 sc_t t = T[((size_t)c * m.S + cs) * m.S + cs];
@@ -305,8 +337,14 @@ int HostModel::build(const void* blob, size_t nbytes) {
             int a = sd.anc[i]; const StateDesc& ad = m.st[a];
             if (a == s) { selfloop = true; continue; }
             switch (sd.kind) {
-            case K_IGENIC: ok &= ad.kind == K_EXON || (ad.kind == K_UTR && ad.uk != U_INTRON); break;
+            case K_IGENIC: ok &= ad.kind == K_EXON || (ad.kind == K_UTR && ad.uk != U_INTRON) || ad.kind == K_DEAD; break;
+            case K_DEAD: break;                    /* never evaluated: only its column-0 cell exists */
             case K_UTR: {
+                if (sd.u5 == 2) {              /* nc: the chain is entered from nc exon states, the internal exon follows its chain (list of splice sites) */
+                    if (sd.uk == U_INTRON) ok &= ad.u5 == 2 && ad.fwd == sd.fwd && (ad.kind == K_DEAD || ad.uk == U_INTERNAL);
+                    else ok &= ad.u5 == 2 && ad.fwd == sd.fwd && (ad.kind == K_DEAD || ad.uk == U_INTRON);
+                    break;
+                }
                 /* the predecessor kinds the candidate lists of Sweep::utr_eval are built for; intronvar states (hint-only) never hold a cell */
                 if (ad.kind == K_UTR && ad.uk == U_INTRONVAR) break;
                 if (sd.uk == U_INTRONVAR) break;
@@ -337,6 +375,15 @@ int HostModel::build(const void* blob, size_t nbytes) {
             }
         }
         if (sd.kind == K_UTR && sd.uk == U_INTRONVAR) { if (!isneg(tab[o_init + s])) ok = false; }     /* must stay empty */
+        if (sd.kind == K_DEAD && sd.uk == U_INTRONVAR) { if (!isneg(tab[o_init + s])) ok = false; }
+        /* a dead state with an initial probability may only lead into chains (column 0 -> column 1) or other dead states: a table-driven
+         * exon state reads its predecessors from a site list, which holds chain values only */
+        if (sd.kind == K_DEAD)
+            for (int b2 = 0; b2 < m.S; b2++)
+                if (!isneg(T[(size_t)s * m.S + b2]) && m.st[b2].kind != K_DEAD && m.st[b2].chain < 0 && !isneg(tab[o_init + s])) {
+                    /* e.g. ncintronvar -> ncinternal: fine as long as the dead state itself starts empty */
+                    ok = false;
+                }
         if (selfloop != (sd.chain >= 0)) ok = false;
         if (!ok) { err = "unsupported transition topology at state " + std::to_string(s); return AUGB200_ERR_UNSUPPORTED; }
         (void)kind_of;
@@ -367,6 +414,7 @@ int HostModel::build(const void* blob, size_t nbytes) {
         m.u5i = b + o_u5i; m.u5 = b + o_u5; m.u3 = b + o_u3; m.tup = b + o_tup;
         m.tssm = b + o_tssm; m.tsstm = b + o_tsstm; m.tatam = b + o_tatam; m.ttsm = b + o_ttsm; m.aataaa = b + o_aat;
         for (int i = 0; i < 10; i++) m.uld[i] = b + o_uld[i];
+        m.uld[10] = m.ld_internal; m.n_uld[10] = m.n_ld_exon;          /* NcModel::lenDistInternal = ExonModel::lenDistInternal (ncmodel.cc:146) */
     }
     return AUGB200_OK;
 }
@@ -381,7 +429,7 @@ DevModel HostModel::rebased(const sc_t* base) const {
     r.ass_pat = rb(dm.ass_pat); r.ass_pat_non = rb(dm.ass_pat_non); r.dss_pat = rb(dm.dss_pat); r.dss_pat_non = rb(dm.dss_pat_non);
     r.u5i = rb(dm.u5i); r.u5 = rb(dm.u5); r.u3 = rb(dm.u3); r.tup = rb(dm.tup);
     r.tssm = rb(dm.tssm); r.tsstm = rb(dm.tsstm); r.tatam = rb(dm.tatam); r.ttsm = rb(dm.ttsm); r.aataaa = rb(dm.aataaa);
-    for (int i = 0; i < 10; i++) r.uld[i] = rb(dm.uld[i]);
+    for (int i = 0; i < 11; i++) r.uld[i] = rb(dm.uld[i]);
     return r;
 }
 

@@ -167,9 +167,9 @@ AUGB_HD sc_t tts_score(const DevModel* m, const Seq& sq, int cls, int fwd, int b
 }
 /* one factor of a SegProbs cumulative product (SegProbs::setEmiProbs, statemodel.cc:413-432), position i in 1..L */
 AUGB_HD sc_t useg_term(const DevModel* m, const Seq& sq, int cls, int g, int i) {
-    const sc_t* tab = (g == US_INIT5 || g == US_RINIT5) ? m->u5i : (g == US_5 || g == US_R5) ? m->u5 : m->u3;
+    const sc_t* tab = g == US_NC ? m->iemi : (g == US_INIT5 || g == US_RINIT5) ? m->u5i : (g == US_5 || g == US_R5) ? m->u5 : m->u3;
     int pn;
-    if (g < US_RINIT5) pn = i < m->k ? -1 : sq.kmer_end(i, m->k + 1);
+    if (g < US_RINIT5 || g == US_NC) pn = i < m->k ? -1 : sq.kmer_end(i, m->k + 1);       /* (NcModel::segProbs: forward k-mers, intron content) */
     else pn = i >= sq.L - m->k ? -1 : sq.kmer_rc(i, m->k + 1);
     return pn < 0 ? m->log025 : tab[((size_t)cls << (2 * (m->k + 1))) | pn];
 }

@@ -76,7 +76,7 @@ struct SweepT {
     /* ------------------------------------------------------------ chains */
     /* A[e] of a chain: prefix sum of (emission + self transition); the UTR-intron chains share the intron emission prefix and a
      * class-independent self transition (checked when the model is built) */
-    AUGB_D sc_t chainAv(int ch, int e) const { return ch == 0 ? w.AIG[e] : (!UTR || ch < CH_UTR) ? w.AGEO[e] : w.AINT[e] + (sc_t)e * m->utr_tself; }
+    AUGB_D sc_t chainAv(int ch, int e) const { return ch == 0 ? w.AIG[e] : (!UTR || ch < CH_UTR) ? w.AGEO[e] : w.AINT[e] + (sc_t)e * (ch < CH_NC ? m->utr_tself : m->nc_tself); }
     /* V[e][chain]: last change point with col <= e */
     AUGB_D sc_t chain_value(int ch, int e) const {
         int n = ws->cp_n[ch];
@@ -894,10 +894,12 @@ struct SweepT {
         if (mb & MB_ASSB) {
             const sc_t sv = sig(SG_ASSF, j + assw + m->ass_up - 1);
             site_append(CL_A5, -1, CH_UTR + 0, j, sv, US_5, 0, m->ass_up + assw); site_append(CL_A3, -1, CH_UTR + 1, j, sv, US_3, 0, m->ass_up + assw);
+            if (m->nc) site_append(CL_NCA, -1, CH_NC, j, sv, US_NC, 0, m->ass_up + assw);                    /* ncinternal after ncintron */
         }
         if (mb & MB_RDSSB) {
             const sc_t sv = sig(SG_DSSR, j + dssw - 1);
             site_append(CL_R5I, CL_R5N, CH_UTR + 2, j, sv, US_RINIT5, US_R5, dssw); site_append(CL_R3, -1, CH_UTR + 3, j, sv, US_R3, 0, dssw);
+            if (m->nc) site_append(CL_NCR, -1, CH_NC + 1, j, sv, US_NC, 0, dssw);                              /* rncinternal after rncintron */
         }
     }
     AUGB_DN void utr_eval(int s, int j) {
@@ -1048,6 +1050,7 @@ struct SweepT {
              * utr3internal, utr3term, then the same for the reverse strand */
             unsigned us = ((mb & MB_U5ATG) ? 0x0009u : 0u) | ((mb & MB_LONGDSS) ? 0x0066u : 0u) | ((mb & MB_UTTS) ? 0x0090u : 0u)
                         | ((mb & MB_URTSS) ? 0x0300u : 0u) | ((mb & MB_RLONGASS) ? 0xcc00u : 0u) | ((mb & MB_URSTOP) ? 0x3000u : 0u);
+            if (m->nc) us |= ((mb & MB_LONGDSS) ? 0x10000u : 0u) | ((mb & MB_RLONGASS) ? 0x20000u : 0u);      /* ncinternal, rncinternal */
             AUGB_ROLLED
             while (us) {
                 int q = wffs(us); us &= us - 1;

@@ -1,11 +1,12 @@
-"""NcModel states (--nc=on: 83 states) — ORACLE ONLY this round.
+"""NcModel states (--nc=on: 83 states).
 
 Without hints the six nc states that begin or end with a transcript boundary are dead (precomputeTxEndProbs leaves their tss / tts
 probabilities at zero, ncmodel.cc:744-826), but ncintron / rncintron (alive in every column) and ncinternal / rncinternal live on the
 initial probabilities of column 0, share the aSSProb memo with the intron model and compete for the path at the last column.  The C
 restatement (oracle/ghmm_oracle.c: nc_eval) is pinned here against the reference's own paths, scores, per-state cell counts, last
-matrix column and sampled paths (tests/golden/make_golden_nc.py); the CUDA path rejects such models (AUGB200_ERR_UNSUPPORTED) until
-the kernels learn the four live states."""
+matrix column and sampled paths (tests/golden/make_golden_nc.py); the kernel source (two more lazily evaluated chains, two table-driven
+exon states, the dead states as column-0 cells) is compared with the oracle cell for cell on the CPU, the GPU test runs the same
+windows through the C ABI."""
 import gzip
 import json
 import os
@@ -76,10 +77,49 @@ def test_oracle_sampling_matches_reference(oracle):
         assert mine["states"] == [tuple(s) for s in theirs["states"]]
 
 
-def test_product_rejects_nc_models_loudly(blob):
-    emu_err = None
-    try:
-        util.HostEmu(blob)
-    except Exception as ex:          # the model builder of the product (ghmm_model.cc) refuses: no approximation, no fallback
-        emu_err = str(ex)
-    assert emu_err is not None
+def _same_cells(oracle, emu, dna):
+    r, e = oracle.viterbi(dna, want_matrix=True), emu.decode(dna, want_cells=True)
+    assert e["status"] == 0 and e["states"] == r["condensed"] and e["log_prob"] == r["log_prob"]
+    V, E = r["V"], e["cells"]
+    assert ((V <= util.NEGT) == (E <= util.NEGT)).all() and (V[V > util.NEGT] == E[V > util.NEGT]).all()
+
+
+def test_kernel_source_matches_oracle_cells_one_lane_and_32_lanes(blob, oracle):
+    """the sweep with the two nc chains and the two table-driven nc exon states (ghmm_sweep.h, ghmm_model.cc), host build with one lane
+    and device flavour on the 32-lane executor: every cell of the 83-state matrix, paths, scores"""
+    seqs = util.read_fasta(util.GOLDEN + "/example.fa")
+    real = util.read_fasta(util.GOLDEN + "/real_windows.fa")[2][1]
+    for simt in (False, True):
+        emu = util.HostEmu(blob, simt32=simt)
+        _same_cells(oracle, emu, seqs[1][1])
+        _same_cells(oracle, emu, seqs[0][1][:6000] if simt else seqs[0][1])
+        _same_cells(oracle, emu, synth.window(7, 4000))
+        if not simt:
+            _same_cells(oracle, emu, real)
+            _same_cells(oracle, emu, synth.window(0, 50000))
+
+
+def test_kernel_source_sampling_matches_oracle(blob, oracle):
+    dna = util.read_fasta(util.GOLDEN + "/example.fa")[1][1]
+    o = oracle.sample(dna, 40)["samples"]
+    for simt in (False, True):
+        e = util.HostEmu(blob, simt32=simt).sample(dna, 39)
+        assert e["status"] == 0 and all(a["states"] == b["states"] for a, b in zip(e["samples"], o))
+
+
+@pytest.mark.gpu
+def test_gpu_nc_model_matches_reference_and_oracle(blob, oracle, golden):
+    from augustus_b200 import Decoder
+    dec = Decoder(blob, 0)
+    seqs = util.read_fasta(util.GOLDEN + "/example.fa")
+    wins = [s for _, s in seqs] + [synth.window(0, 50000)]
+    refs = golden["example"] + golden["synthetic50k"][:1]
+    for dna, p, ref in zip(wins, dec.decode_batch(wins), refs):
+        assert p.status == 0 and p.as_tuples() == [tuple(s) for s in ref["states"]]
+        assert abs(p.log_prob - ref["log_prob"]) <= 1e-6 * abs(ref["log_prob"])
+        o = oracle.viterbi(dna)
+        assert p.as_tuples() == o["condensed"] and p.log_prob == o["log_prob"]
+    (name, rec), = json.load(gzip.open(os.path.join(util.GOLDEN, "ref_samples_nc.json.gz"), "rt")).items()
+    dna = dict(seqs)[name]
+    vit, samples = dec.decode_batch_sampling([dna], 100)
+    assert [s.as_tuples() for s in samples[0]] == [[tuple(t) for t in sm["states"]] for sm in rec["samples"]]

@@ -175,7 +175,7 @@ class Oracle:
 
 
 class HostEmu:
-    NCHAIN = 11
+    NCHAIN = 13
 
     def __init__(self, blob: bytes, simt32: bool = False):
         """simt32=True: the 32-lane flavour of the kernel source (the lane-group paths of the device) on 32 fibers per warp,
