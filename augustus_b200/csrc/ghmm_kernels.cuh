@@ -27,10 +27,7 @@ struct WinDev {
 __constant__ DevModel c_model;
 
 constexpr int PREP_BS = 256;
-#ifndef AUGB_PREP_ITEMS
-#define AUGB_PREP_ITEMS 4
-#endif
-constexpr int PREP_ITEMS = AUGB_PREP_ITEMS;
+constexpr int PREP_ITEMS = 4;      /* measured: 8 / 16 items per thread and warp-segment scans are slower (24 / 30 / 37 / 36 ms per 1184 windows) */
 constexpr int PREP_TILE = PREP_BS * PREP_ITEMS;
 
 /* exclusive block-wide prefix of one value per thread; returns the prefix, *total = block sum */
@@ -56,40 +53,6 @@ __device__ __forceinline__ T block_excl_sum(T v, T* sm /* PREP_BS/32 + 1 */, T* 
     return r;
 }
 
-#if defined(AUGB_PREP_WARPSCAN)
-/* out[i] = init + sum_{t<=i} gen(t), i in [0, n).  Every warp scans its own contiguous segment with shuffles only (no block-wide
- * barrier per tile), the segment totals are exchanged once, and a second sweep adds each segment's offset.  Integer sums: the result
- * does not depend on the order. */
-template <typename T, typename Gen>
-__device__ __forceinline__ void block_scan_gen(Gen gen, T* out, int n, T init, T* sm) {
-    constexpr int NW = PREP_BS / 32, WTILE = 32 * PREP_ITEMS;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int per = (((n + NW - 1) / NW) + WTILE - 1) / WTILE * WTILE;
-    const int s0 = min(n, wid * per), s1 = min(n, s0 + per);
-    T carry = 0;
-    for (int t0 = s0; t0 < s1; t0 += WTILE) {
-        T v[PREP_ITEMS]; const int i0 = t0 + lane * PREP_ITEMS;
-        T run = 0;
-        #pragma unroll
-        for (int i = 0; i < PREP_ITEMS; i++) { int idx = i0 + i; T x = idx < s1 ? gen(idx) : (T)0; run += x; v[i] = run; }
-        T incl = run;
-        #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { T t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        const T ex = carry + incl - run;
-        #pragma unroll
-        for (int i = 0; i < PREP_ITEMS; i++) { int idx = i0 + i; if (idx < s1) out[idx] = ex + v[i]; }
-        carry += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (lane == 0) sm[wid] = carry;
-    __syncthreads();
-    T off = init;
-    for (int w2 = 0; w2 < wid; w2++) off += sm[w2];
-    __syncthreads();
-    #pragma unroll 8
-    for (int idx = s0 + lane; idx < s1; idx += 32) out[idx] += off;
-}
-
-#else
 /* out[off + i] = init + sum_{t<=i} gen(t), i in [0, n) */
 template <typename T, typename Gen>
 __device__ __forceinline__ void block_scan_gen(Gen gen, T* out, int n, T init, T* sm) {
@@ -106,7 +69,6 @@ __device__ __forceinline__ void block_scan_gen(Gen gen, T* out, int n, T init, T
     }
 }
 
-#endif
 /* nearest in-frame stop tables: a max-scan over (last stop position per residue class) */
 struct Int3 { int a, b, c; };
 __device__ __forceinline__ Int3 max3(Int3 x, Int3 y) { Int3 r; r.a = max(x.a, y.a); r.b = max(x.b, y.b); r.c = max(x.c, y.c); return r; }
