@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(PREP_BS) k_prep(const WinDev* __restrict__ win
             __syncthreads();
             if (anynuc) {
                 const sc_t* sg = (const sc_t*)(base + lay.sig);
-                for (int j = threadIdx.x; j < L; j += PREP_BS) mask[j] |= (mask_t)utr_column_mask(m, s, j, sg, tssF, tssR, ttsF, ttsR);
+                for (int j = threadIdx.x; j < L; j += PREP_BS) mask[j] |= (mask_t)utr_column_mask(m, s, j, sg, tssF, tssR, ttsF, ttsR, gc[L - 1]);
             }
             sc_t* useg = (sc_t*)(base + lay.useg);
             for (int g = 0; g < NUSEG; g++) {

@@ -259,7 +259,7 @@ inline void prep_window_seq(const DevModel* m, const char* dna, int L, const int
         sc_t* aint = (sc_t*)(base + lay.aint); aint[0] = 0;
         for (int j = 1; j < L; j++) aint[j] = aint[j - 1] + intron_emi1(m, s, gc[j], j) + nep_term(m, pmask, j);
         const sc_t* sg = (const sc_t*)(base + lay.sig);
-        if (anynuc) for (int j = 0; j < L; j++) mask[j] |= (mask_t)utr_column_mask(m, s, j, sg, tssF, tssR, ttsF, ttsR);
+        if (anynuc) for (int j = 0; j < L; j++) mask[j] |= (mask_t)utr_column_mask(m, s, j, sg, tssF, tssR, ttsF, ttsR, gc[L - 1]);
     }
     WinOuts* wo = (WinOuts*)(base + lay.outs);
     int nloc = 0;

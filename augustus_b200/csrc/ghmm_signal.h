@@ -174,7 +174,7 @@ AUGB_HD sc_t useg_term(const DevModel* m, const Seq& sq, int cls, int g, int i) 
     return pn < 0 ? m->log025 : tab[((size_t)cls << (2 * (m->k + 1))) | pn];
 }
 /* UTR part of the activity mask of column j (ends of UTR exon states, begin-signal sites); tss* / tts* arrays already written */
-AUGB_HD unsigned utr_column_mask(const DevModel* m, const Seq& s, int j, const sc_t* sg, const sc_t* tssF, const sc_t* tssR, const sc_t* ttsF, const sc_t* ttsR) {
+AUGB_HD unsigned utr_column_mask(const DevModel* m, const Seq& s, int j, const sc_t* sg, const sc_t* tssF, const sc_t* tssR, const sc_t* ttsF, const sc_t* ttsR, int gc_last) {
     unsigned mb = 0; const int L = s.L;
     const int dssw = m->dss_start + m->dss_end + 2, assw = m->ass_start + m->ass_end + 2;
     { int eobe = j + m->tiw; bool ok = true; if (eobe + 3 <= L - 1) { int c = s.kmer_end(eobe + 3, 3); ok = c >= 0 && m->isstart[c]; } if (ok) mb |= MB_U5ATG; }
@@ -186,7 +186,10 @@ AUGB_HD unsigned utr_column_mask(const DevModel* m, const Seq& s, int j, const s
     if (j == assw + m->ass_up - 1 && possRASS(s, j - m->ass_up - m->ass_start - 2 + 1)) mb |= MB_RLONGASS;
     if (j >= 1) {
         if (!isneg(tssF[j])) mb |= MB_TSSB;
-        { int jj = j + assw + m->ass_up - 1; if (jj < L && !isneg(sg[(size_t)SG_ASSF * L + jj])) mb |= MB_ASSB; }
+        { int jj = j + assw + m->ass_up - 1;        /* last base of the acceptor pattern; the tabulated scores end at L - 1, but a UTR exon may begin with a
+                                                      * site whose pattern runs up to ass_end - 1 bases past the window (the exon begins in its last bases; aSSProb then takes the
+                                                      * invalid-pattern probability, intronmodel.cc:1116-1188) */
+          if (jj < L ? !isneg(sg[(size_t)SG_ASSF * L + jj]) : (jj <= L + m->ass_end - 2 && !isneg(aSSProb(m, s, gc_last, j, 1)))) mb |= MB_ASSB; }
         { int jj = j + dssw - 1; if (jj < L && !isneg(sg[(size_t)SG_DSSR * L + jj])) mb |= MB_RDSSB; }
         if (j + m->dpc <= L && !isneg(ttsR[j + m->dpc])) mb |= MB_RTTSB;
     }

@@ -882,8 +882,9 @@ struct SweepT {
         if (isneg(v)) return;
         const double f = FWD ? chain_fvalue(ch, j - 1) : 0.0;
         if (lane == 0) {
-            cl_append(list, j - 1, cs, v, f, sigv - usegp(seg)[j + bom_off - 1]);
-            if (list2 >= 0) cl_append(list2, j - 1, cs, v, f, sigv - usegp(seg2)[j + bom_off - 1]);
+            const int bm1 = j + bom_off - 1 > L ? L : j + bom_off - 1;       /* beginOfMiddle - 1, inside the cumulative arrays (see utr_eval) */
+            cl_append(list, j - 1, cs, v, f, sigv - usegp(seg)[bm1]);
+            if (list2 >= 0) cl_append(list2, j - 1, cs, v, f, sigv - usegp(seg2)[bm1]);
         }
         wsync();
     }
@@ -892,7 +893,8 @@ struct SweepT {
         if (mb & MB_TSSB) site_append(CL_T5, -1, 0, j, w.tssF[j], US_INIT5, 0, m->tuw + m->tss_end);
         if (mb & MB_RTTSB) site_append(CL_TR, -1, 0, j, w.ttsR[j + m->dpc], US_R3, 0, m->boxlen + m->dpc);
         if (mb & MB_ASSB) {
-            const sc_t sv = sig(SG_ASSF, j + assw + m->ass_up - 1);
+            const int jj = j + assw + m->ass_up - 1;          /* >= L: the pattern ends past the window (ghmm_signal.h, MB_ASSB) */
+            const sc_t sv = jj < L ? sig(SG_ASSF, jj) : signal_term(m, sq, w.gc[L - 1], SG_ASSF, jj, w.pmask);      /* (with the softmasking bonus of its intron bases, like the table) */
             site_append(CL_A5, -1, CH_UTR + 0, j, sv, US_5, 0, m->ass_up + assw); site_append(CL_A3, -1, CH_UTR + 1, j, sv, US_3, 0, m->ass_up + assw);
             if (m->nc) site_append(CL_NCA, -1, CH_NC, j, sv, US_NC, 0, m->ass_up + assw);                    /* ncinternal after ncintron */
         }
@@ -947,7 +949,7 @@ struct SweepT {
                         const sc_t lp = ld[len];
                         sc_t mid;                                  /* content of the middle part + cum[bom - 1] */
                         if (mlen >= 0) mid = cumE;
-                        else mid = cum[bom - 1] + (u.shortrule ? shortfac * (sc_t)(-mlen) : (sc_t)0);
+                        else mid = cum[bom - 1 > L ? L : bom - 1] + (u.shortrule ? shortfac * (sc_t)(-mlen) : (sc_t)0);     /* (cancels the same term folded into c.V) */
                         if (!isneg(lp)) {
                             te = t + ((mid + lp) + ep); valid = true;
                             if (FWD) { const sc_t g = w.clG(u.list)[i]; pf = w.clF(u.list)[i]; pv = c.V - g; te += g; } else pv = c.V;

@@ -173,3 +173,32 @@ def test_gpu_sampling_matches_reference(dec):
     for mine, theirs in zip(samples[0], rec["samples"]):
         assert mine.as_tuples() == [tuple(s) for s in theirs["states"]]
         assert abs(mine.log_prob - theirs["log_prob"]) <= 1e-6 * max(1.0, abs(theirs["log_prob"]))
+
+
+def test_acceptor_pattern_running_past_the_window_end():
+    """a UTR exon may begin with an acceptor site whose downstream pattern ends one base past the window (the exon is the last base;
+    IntronModel::aSSProb then uses the invalid-pattern probability): found by tools/fuzz_simt32.py, 24 cells of utr5term were missing"""
+    dna = "TTCGGCTTCCGCCCACTAATAAATAANNNNNNNNNNNNNNNNNNNNNNGNNNNGGCTAGC"
+    blob = util.blob_bytes("human_utr")
+    orc = util.Oracle(blob)
+    r = orc.viterbi(dna, want_matrix=True)
+    assert (r["V"][36:, 29] > util.NEGT).all()                     # the reference holds utr5term cells in the last 24 columns (augdump)
+    for simt in (False, True):
+        e = util.HostEmu(blob, simt32=simt).decode(dna, want_cells=True)
+        V, E = r["V"], e["cells"]
+        assert e["status"] == 0 and e["states"] == r["condensed"] and e["log_prob"] == r["log_prob"]
+        assert ((V <= util.NEGT) == (E <= util.NEGT)).all() and (V[V > util.NEGT] == E[V > util.NEGT]).all()
+
+
+def test_acceptor_pattern_past_the_window_end_with_softmasking_fly():
+    """the same edge with ass_end = 4 (pattern up to two bases past the end) and the softmasking bonus of the site's intron bases"""
+    dna = "TTTCTACacggatcnnnnnnnnnnnnnnnnnnnnnnnnnnnnnnnnnnnnnntaaaaaagca"
+    blob = util.blob_bytes("fly_softmask_utr")
+    orc = util.Oracle(blob)
+    for seq in (dna, dna + "t", dna.upper()):
+        r = orc.viterbi(seq, want_matrix=True)
+        for simt in (False, True):
+            e = util.HostEmu(blob, simt32=simt).decode(seq, want_cells=True)
+            V, E = r["V"], e["cells"]
+            assert e["status"] == 0 and e["states"] == r["condensed"] and e["log_prob"] == r["log_prob"]
+            assert ((V <= util.NEGT) == (E <= util.NEGT)).all() and (V[V > util.NEGT] == E[V > util.NEGT]).all()

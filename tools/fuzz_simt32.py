@@ -1,6 +1,7 @@
 """Differential fuzz (CPU only): the device flavour of the kernel source on the 32-lane executor against the oracle on random windows —
 composition shifts (GC-class boundaries), N runs, soft-masked runs, tiny windows; cells, paths and scores must be identical.
-usage: fuzz_simt32.py [n_cases=100] [seed=1] [blob=human|human_utr|fly_noutr|fly_softmask_utr]"""
+usage: fuzz_simt32.py [n_cases=100] [seed=1] [blob=human|human_utr|human_nc|fly_noutr|fly_softmask_utr]
+FUZZ_ONE_CLASS=1 keeps the composition fixed (no GC-class boundaries: isolates everything but the class-history memos of DESIGN.md 3.6)"""
 import os, random, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -20,10 +21,10 @@ def piece(length, gc):
 
 
 def make():
-    L = rng.choice([2, 3, 5, 17, 60, 300, 1500, 4000, 9000, 14000])
+    L = rng.choice([2, 3, 5, 17, 60, 61, 62, 63, 64, 97, 300, 301, 1500, 4000, 9000, 14000])
     parts = []
     while sum(map(len, parts)) < L:
-        parts.append(piece(rng.randint(1, max(1, L // 2)), rng.choice([0.3, 0.41, 0.41, 0.5, 0.62, 0.7])))
+        parts.append(piece(rng.randint(1, max(1, L // 2)), 0.41 if os.environ.get("FUZZ_ONE_CLASS") else rng.choice([0.3, 0.41, 0.41, 0.5, 0.62, 0.7])))
     s = "".join(parts)[:L]
     s = list(s)
     for _ in range(rng.randint(0, 3)):                     # N runs
