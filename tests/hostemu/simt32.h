@@ -63,9 +63,13 @@ inline void run(const std::function<void()>& body, size_t stack_bytes = 1 << 20)
         w.ctx[l].uc_stack.ss_sp = w.stack[l].data(); w.ctx[l].uc_stack.ss_size = stack_bytes; w.ctx[l].uc_link = &w.sched;
         makecontext(&w.ctx[l], (void (*)())trampoline, 0);
     }
+    /* lane order inside a phase: ascending (lane 0's writes are seen by everybody in the same phase: catches a read that should have
+     * come BEFORE the write), descending with SIMT32_REVERSE=1 (lane 0 runs last: catches a read that needs a barrier AFTER the write) */
+    const bool rev = getenv("SIMT32_REVERSE") != nullptr;
     for (;;) {
         bool any = false;
-        for (int l = 0; l < NL; l++) {
+        for (int i = 0; i < NL; i++) {
+            const int l = rev ? NL - 1 - i : i;
             if (w.finished[l]) continue;
             any = true; w.cur = l;
             swapcontext(&w.sched, &w.ctx[l]);

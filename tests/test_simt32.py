@@ -104,3 +104,16 @@ def test_forward_matrix_32_lanes_matches_oracle():
         F = r["F"]; fin = np.isfinite(F)
         assert (np.isfinite(Fo) == fin).all()
         assert np.abs(F[fin] - Fo[fin]).max() <= 1e-9
+
+
+def test_reverse_lane_order(monkeypatch):
+    """the executor runs the lanes of a phase in ascending order by default (lane 0 first); with SIMT32_REVERSE lane 0 runs last, which
+    exposes a read that needs a barrier after lane 0's write: same cells, same sampled paths"""
+    monkeypatch.setenv("SIMT32_REVERSE", "1")
+    for name in ("human", "human_nc"):
+        blob = util.blob_bytes(name)
+        orc, emu = util.Oracle(blob), util.HostEmu(blob, simt32=True)
+        dna = util.read_fasta(util.GOLDEN + "/example.fa")[1][1]
+        _same_cells(orc, emu, dna)
+        o, e = orc.sample(dna, 16)["samples"], emu.sample(dna, 15)
+        assert e["status"] == 0 and all(a["states"] == b["states"] for a, b in zip(e["samples"], o))

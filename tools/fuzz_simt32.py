@@ -1,7 +1,7 @@
 """Differential fuzz (CPU only): the device flavour of the kernel source on the 32-lane executor against the oracle on random windows —
 composition shifts (GC-class boundaries), N runs, soft-masked runs, tiny windows; cells, paths and scores must be identical.
 usage: fuzz_simt32.py [n_cases=100] [seed=1] [blob=human|human_utr|human_nc|fly_noutr|fly_softmask_utr]
-FUZZ_ONE_CLASS=1 keeps the composition fixed (no GC-class boundaries: isolates everything but the class-history memos of DESIGN.md 3.6)"""
+FUZZ_SAMPLING=1 also compares 11 sampled paths per window (windows up to 4 kb); FUZZ_ONE_CLASS=1 keeps the composition fixed (no GC-class boundaries: isolates everything but the class-history memos of DESIGN.md 3.6)"""
 import os, random, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -49,6 +49,11 @@ for k in range(n):
             ok = ok and ((V <= util.NEGT) == (E <= util.NEGT)).all() and (V[V > util.NEGT] == E[V > util.NEGT]).all()
     else:
         ok = ok and r["n"] < 0 if "n" in r else False
+    if ok and os.environ.get("FUZZ_SAMPLING") and len(dna) <= 4000 and set(dna.upper()) - {"N"}:      # also the forward fill + sampling walks
+        ns = 12
+        so = orc.sample(dna, ns)["samples"]; se = emu.sample(dna, ns - 1)
+        ok = se["status"] == 0 and len(se["samples"]) == ns - 1 and all(a["states"] == b["states"] for a, b in zip(se["samples"], so))
+        if not ok: print("  (sampling differs)")
     if not ok:
         bad += 1
         print("MISMATCH case", k, "len", len(dna), "status", e["status"]); open("/tmp/fuzz_bad_%s_%d_%d.fa" % (blobname, seed, k), "w").write(">x\n" + dna + "\n")
