@@ -227,8 +227,8 @@ __global__ void __launch_bounds__(PREP_BS) k_prep(const WinDev* __restrict__ win
              * intron emission prefix of the UTR-intron chains (formulas in ghmm_signal.h, same as the sequential host builder) ---- */
             sc_t* tssF = (sc_t*)(base + lay.tssF); sc_t* tssR = (sc_t*)(base + lay.tssR); sc_t* ttsF = (sc_t*)(base + lay.ttsF); sc_t* ttsR = (sc_t*)(base + lay.ttsR);
             __syncthreads();
-            for (int i = threadIdx.x; i < L; i += PREP_BS) {
-                int r = i + m->tuw + m->tss_end - 1; int c = gc[r < L ? r : L - 1];
+            for (int i = threadIdx.x; i <= L; i += PREP_BS) {
+                int r = i + m->tuw + m->tss_end - 1; int c = gc[r < 0 ? 0 : r < L ? r : L - 1];
                 tssF[i] = anynuc ? tss_score(m, s, c, 1, i) : SC_NEG; tssR[i] = anynuc ? tss_score(m, s, c, 0, i) : SC_NEG;
             }
             for (int b = threadIdx.x; b <= L; b += PREP_BS) { int c = gc[b < L ? b : L - 1]; ttsF[b] = anynuc ? tts_score(m, s, c, 1, b) : SC_NEG; ttsR[b] = anynuc ? tts_score(m, s, c, 0, b) : SC_NEG; }

@@ -62,7 +62,7 @@ inline WinLayout make_layout(int L, int C, bool generous = false, bool forward =
     w.softmask = softmask ? 1 : 0; w.pmask = take(softmask ? (size_t)(L + 1) * 4 : 0);
     w.utr = utr ? 1 : 0; w.ncl = utr ? NCL : NCL_BASE; w.nchain = utr ? NCHAIN : CH_UTR;
     w.aint = take(utr ? (size_t)L * sizeof(sc_t) : 0); w.useg = take(utr ? (size_t)NUSEG * (L + 1) * sizeof(sc_t) : 0);
-    w.tssF = take(utr ? (size_t)L * sizeof(sc_t) : 0); w.tssR = take(utr ? (size_t)L * sizeof(sc_t) : 0);
+    w.tssF = take(utr ? (size_t)(L + 1) * sizeof(sc_t) : 0); w.tssR = take(utr ? (size_t)(L + 1) * sizeof(sc_t) : 0);     /* [L+1]: a model without a TSS window (tuw + tss_end = 0) asks for position L */
     w.ttsF = take(utr ? (size_t)(L + 1) * sizeof(sc_t) : 0); w.ttsR = take(utr ? (size_t)(L + 1) * sizeof(sc_t) : 0);
     if (generous) { w.ev_cap = 48 * L + 256; w.cl_cap = L + 64; w.cp_cap = L + 64; w.path_cap = L + 64; }
     else { w.ev_cap = (utr ? 5 : 3) * L + 256; w.cl_cap = L / 6 + 64; w.cp_cap = L / 16 + 64; w.path_cap = L / 8 + 64; }
@@ -246,8 +246,8 @@ inline void prep_window_seq(const DevModel* m, const char* dna, int L, const int
     if (lay.utr) {
         /* UTR models: TSS / TTS scores, SegProbs cumulative sums, intron emission prefix of the UTR-intron chains, mask bits */
         sc_t* tssF = (sc_t*)(base + lay.tssF); sc_t* tssR = (sc_t*)(base + lay.tssR); sc_t* ttsF = (sc_t*)(base + lay.ttsF); sc_t* ttsR = (sc_t*)(base + lay.ttsR);
-        for (int i = 0; i < L; i++) {
-            int r = i + m->tuw + m->tss_end - 1; int c = gc[r < L ? r : L - 1];
+        for (int i = 0; i <= L; i++) {
+            int r = i + m->tuw + m->tss_end - 1; int c = gc[r < 0 ? 0 : r < L ? r : L - 1];
             tssF[i] = anynuc ? tss_score(m, s, c, 1, i) : SC_NEG; tssR[i] = anynuc ? tss_score(m, s, c, 0, i) : SC_NEG;
         }
         for (int b = 0; b <= L; b++) { int c = gc[b < L ? b : L - 1]; ttsF[b] = anynuc ? tts_score(m, s, c, 1, b) : SC_NEG; ttsR[b] = anynuc ? tts_score(m, s, c, 0, b) : SC_NEG; }

@@ -179,7 +179,7 @@ AUGB_HD unsigned utr_column_mask(const DevModel* m, const Seq& s, int j, const s
     const int dssw = m->dss_start + m->dss_end + 2, assw = m->ass_start + m->ass_end + 2;
     { int eobe = j + m->tiw; bool ok = true; if (eobe + 3 <= L - 1) { int c = s.kmer_end(eobe + 3, 3); ok = c >= 0 && m->isstart[c]; } if (ok) mb |= MB_U5ATG; }
     { int b0 = j - m->dpc - m->boxlen + 1; if (j == L - 1 || (b0 >= 0 && b0 + m->boxlen - 1 < L && !isneg(ttsF[b0]))) mb |= MB_UTTS; }
-    { int b0 = j - m->tuw - m->tss_end + 1; if (b0 >= 0 && !isneg(tssR[b0])) mb |= MB_URTSS; }
+    { int b0 = j - m->tuw - m->tss_end + 1; if (b0 >= 0 && b0 <= L && !isneg(tssR[b0])) mb |= MB_URTSS; }
     if (!(j + 3 > L - 1 || !isRCStop(m, s, j + 1))) mb |= MB_URSTOP;
     /* ends that reuse the intron-state bits: one column earlier than longdss / rlongass can end (the window may start at base 0) */
     if (j == dssw - 1 && possDSS(m, s, j - m->dss_end - 2 + 1)) mb |= MB_LONGDSS;

@@ -542,6 +542,7 @@ struct SweepT {
                 const int bobe = bos - st.innerPartOffset, len = eobe - bobe + 1, pf = m->st[a].frame, il = right - bos;
                 if (listkind && win != mod3(fwd ? pf + len : pf - len)) valid = false;
                 else if (len < 1 || len >= m->n_ld_exon) valid = false;
+                else if (listkind && eop == 0) general = true;      /* predecessor = initial probabilities: no cell has vouched for the splice site */
                 else if (ek == E_INTERNAL || ek == E_TERMINAL || ek == E_RINTERNAL) {
                     /* begin part = 1: the splice site was checked by the longass / rlongdss cell (exonmodel.cc:1464-1486, 1518-1535) */
                     sc_t ld = ldtab[len], rest;
@@ -920,7 +921,7 @@ struct SweepT {
                 ep = 0; boe = L; rm = u.begsig == BS_NONE ? j - 1 : j - assw - m->ass_up; ld = m->uld[9]; nld = m->n_uld[9];
             } else ep = (boe < 0 || boe + m->boxlen - 1 >= L) ? SC_NEG : w.ttsF[boe];
             break;
-        case UE_TSSR: ep = boe < 0 ? SC_NEG : w.tssR[boe]; break;
+        case UE_TSSR: ep = (boe < 0 || boe > L) ? SC_NEG : w.tssR[boe]; break;
         case UE_ASSR: ep = boe < 0 ? SC_NEG : sig(SG_ASSR, j); break;
         default: ep = (j + 3 > L - 1 || !isRCStop(m, sq, j + 1)) ? SC_NEG : 0;
         }
@@ -1102,6 +1103,10 @@ struct SweepT {
                 const StateDesc& sd = m->st[s];
                 if (lane == 0 && sd.kind == K_LONGDSS && sd.fwd) cl_append(CL_LD + sd.frame, 0, s, v, sc2d(v));
                 if (lane == 0 && sd.kind == K_LONGASS && !sd.fwd) cl_append(CL_RA + sd.frame, 0, s, v, sc2d(v));
+                /* an exon can follow a splice-site state of column 0 when the exon part of the signal is shorter than two bases (ass_end < 2,
+                 * dss_start < 2 on the reverse strand): exonmodel.cc:1464-1486 then skips the site test for beginOfBioExon < 2 */
+                if (lane == 0 && sd.kind == K_LONGASS && sd.fwd) cl_append(CL_LA + mod3(sd.frame - (1 - m->ass_end)), 0, s, v, sc2d(v));
+                if (lane == 0 && sd.kind == K_LONGDSS && !sd.fwd) cl_append(CL_RD + mod3(sd.frame + 1 - m->dss_start), 0, s, v, sc2d(v));
                 if (UTR && lane == 0 && sd.kind == K_EXON && (sd.ek == E_SINGLE || sd.ek == E_TERMINAL)) cl_append(CL_X3, 0, s, v, sc2d(v), -usegp(US_3)[0]);
                 if (UTR && lane == 0 && sd.kind == K_EXON && (sd.ek == E_RSINGLE || sd.ek == E_RINITIAL)) { cl_append(CL_XRS, 0, s, v, sc2d(v), -usegp(US_RINIT5)[0]); cl_append(CL_XRT, 0, s, v, sc2d(v), -usegp(US_R5)[0]); }
                 if (lane == 0 && !alln) feed_chain(0, s, v, sc2d(v));
