@@ -46,13 +46,13 @@ AUGB_HD bool isneg(sc_t x) { return x <= SC_NEGT; }
 AUGB_HD int mod3(int k) { return (int)((unsigned)(k + 3 * (1 << 28)) % 3u); }
 
 constexpr int MAXS = 96;      /* states */
-constexpr int MAXC = 8;       /* GC classes */
+constexpr int MAXC = 16;      /* GC classes (chicken and maize use 10) */
 constexpr int MAXANC = 12;   /* (the intergenic state of the 83-state model has 10) */
 constexpr int NCHAIN = 13;    /* igenic + 3 geometric + 3 reverse geometric + 4 UTR introns (utr5, utr3, rutr5, rutr3) + ncintron, rncintron */
 constexpr int CH_UTR = 7;     /* first UTR-intron chain */
 constexpr int CH_NC = 11;     /* ncintron, rncintron (NcModel, --nc=on) */
-constexpr int WF_ALLN = 1 << 8;
-constexpr int WF_NOSLAB = 1 << 9;     /* the prefix-array pool ran out: decode this window again with the generous layout */
+constexpr int WF_ALLN = 1 << 24;      /* (window flags live above the class-presence bits 0 .. MAXC-1) */
+constexpr int WF_NOSLAB = 1 << 25;    /* the prefix-array pool ran out: decode this window again with the generous layout */
 
 /* reference StateType values (include/types.hh:492-512) used by the kernels */
 enum : int {
@@ -139,6 +139,7 @@ struct DevModel {
     const sc_t *iemi, *gemi;                        /* [c << 10 | kmer] */
     const sc_t* gfirst;                             /* igenic emission for columns <= k: [c][off(j)+pat] */
     const sc_t *tis, *assm;                         /* [(c*n + i) << 2(k+1) | pat] */
+    int tis_nbins; const sc_t *tis_bb, *tis_bp;     /* TRANSINITBIN (exonmodel.cc:1321-1326, 1437-1442): [c][nbins-1] bin boundaries, [c][nbins] bin probabilities */
     const sc_t *ld_single, *ld_initial, *ld_internal, *ld_terminal, *ld_intron;
     const sc_t *ass_pat, *ass_pat_non, *dss_pat, *dss_pat_non;
     sc_t startp[64];

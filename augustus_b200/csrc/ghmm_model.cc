@@ -90,7 +90,7 @@ int HostModel::build(const void* blob, size_t nbytes) {
     if (!r.ok) return AUGB200_ERR_BAD_BLOB;
     if (m.S < 1 || m.S > MAXS || m.C < 1 || m.C > MAXC) { err = "state / class count out of range"; return AUGB200_ERR_UNSUPPORTED; }
     if (ik != m.k || gk != m.k || m.k < 1 || m.k > 4) { err = "content model orders must be equal and <= 4"; return AUGB200_ERR_UNSUPPORTED; }
-    if (nbins > 0) { err = "TRANSINITBIN models are not supported yet"; return AUGB200_ERR_UNSUPPORTED; }
+    m.tis_nbins = nbins > 0 ? nbins : 0;
     m.utr = utr ? 1 : 0; m.nc = nc ? 1 : 0;
     if (nc && !utr) { err = "nc states need the UTR states"; return AUGB200_ERR_UNSUPPORTED; }
     if (r.b.find("softmasking")) {          /* blobs written before softmasking support carry no entry: off */
@@ -118,6 +118,7 @@ int HostModel::build(const void* blob, size_t nbytes) {
     for (int l = 0; l <= m.k; l++) { char nm[32]; snprintf(nm, sizeof nm, "exon_pls%d", l); o_xpls[l] = push(nm, (size_t)m.C * 3 << (2 * (l + 1))); }
     size_t o_iemi = push("intron_emi", m.C * K1), o_gemi = push("igenic_emi", m.C * K1);
     size_t o_tis = push("tis_motif", (size_t)m.C * m.tis_n << (2 * (m.tis_k + 1))), o_assm = push("ass_motif", (size_t)m.C * m.assm_n << (2 * (m.assm_k + 1)));
+    size_t o_tbb = m.tis_nbins > 1 ? push("tis_bin_bounds", (size_t)m.C * (m.tis_nbins - 1)) : 0, o_tbp = m.tis_nbins > 0 ? push("tis_bin_probs", (size_t)m.C * m.tis_nbins) : 0;
     size_t n0 = tab.size();
     size_t o_lds = push("lendist_single", 0); m.n_ld_exon = (int)(tab.size() - n0);
     size_t o_ldi = push("lendist_initial", m.n_ld_exon), o_ldn = push("lendist_internal", m.n_ld_exon), o_ldt = push("lendist_terminal", m.n_ld_exon);
@@ -408,6 +409,7 @@ int HostModel::build(const void* blob, size_t nbytes) {
     m.xemi = b + o_xemi; m.xinit = b + o_xinit; m.xet = b + o_xet;
     for (int l = 0; l < 5; l++) m.xpls[l] = l <= m.k ? b + o_xpls[l] : nullptr;
     m.iemi = b + o_iemi; m.gemi = b + o_gemi; m.gfirst = b + o_gfirst; m.tis = b + o_tis; m.assm = b + o_assm;
+    m.tis_bb = m.tis_nbins > 1 ? b + o_tbb : nullptr; m.tis_bp = m.tis_nbins > 0 ? b + o_tbp : nullptr;
     m.ld_single = b + o_lds; m.ld_initial = b + o_ldi; m.ld_internal = b + o_ldn; m.ld_terminal = b + o_ldt; m.ld_intron = b + o_ldx;
     m.ass_pat = b + o_ap; m.ass_pat_non = b + o_apn; m.dss_pat = b + o_dp; m.dss_pat_non = b + o_dpn;
     if (m.utr) {
@@ -425,6 +427,7 @@ DevModel HostModel::rebased(const sc_t* base) const {
     r.init = rb(dm.init); r.term = rb(dm.term); r.trans = rb(dm.trans); r.xemi = rb(dm.xemi); r.xinit = rb(dm.xinit); r.xet = rb(dm.xet);
     for (int l = 0; l < 5; l++) r.xpls[l] = rb(dm.xpls[l]);
     r.iemi = rb(dm.iemi); r.gemi = rb(dm.gemi); r.gfirst = rb(dm.gfirst); r.tis = rb(dm.tis); r.assm = rb(dm.assm);
+    r.tis_bb = rb(dm.tis_bb); r.tis_bp = rb(dm.tis_bp);
     r.ld_single = rb(dm.ld_single); r.ld_initial = rb(dm.ld_initial); r.ld_internal = rb(dm.ld_internal); r.ld_terminal = rb(dm.ld_terminal); r.ld_intron = rb(dm.ld_intron);
     r.ass_pat = rb(dm.ass_pat); r.ass_pat_non = rb(dm.ass_pat_non); r.dss_pat = rb(dm.dss_pat); r.dss_pat_non = rb(dm.dss_pat_non);
     r.u5i = rb(dm.u5i); r.u5 = rb(dm.u5); r.u3 = rb(dm.u3); r.tup = rb(dm.tup);

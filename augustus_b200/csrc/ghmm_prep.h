@@ -204,7 +204,7 @@ AUGB_HD sc_t begin_term(const DevModel* m, const Seq& s, int c, int bobe) {
     if (pn < 0 || isneg(m->startp[pn])) return SC_NEG;
     sc_t v = m->startp[pn];
     int tis = bobe - m->tiw;
-    if (tis > m->tis_k) v += motif_fwd(m, s, c, m->tis, m->tis_n, m->tis_k, tis);
+    if (tis > m->tis_k) v = tis_bin(m, c, v + motif_fwd(m, s, c, m->tis, m->tis_n, m->tis_k, tis));
     else v += (sc_t)(bos - 3) * m->log025;
     const int endOfStart = bos + k - 1;
     if (k >= 1) {

@@ -78,6 +78,16 @@ AUGB_HD sc_t aSSProb(const DevModel* m, const Seq& sq, int cls, int base, int fw
     return motif + pat;
 }
 /* ExonModel::endPartEmiProb for rsingle / rinitial (exonmodel.cc:1313-1332) */
+/* BinnedMMGroup::getIndex (merkmal.cc:155-168) + avprobs: with TRANSINITBIN the start codon x TIS motif probability is replaced by the
+ * probability of the bin it falls into */
+AUGB_HD sc_t tis_bin(const DevModel* m, int cls, sc_t p) {
+    const int nb = m->tis_nbins;
+    if (nb < 1) return p;
+    const sc_t* bb = m->tis_bb + (size_t)cls * (nb - 1); int a = 0, b = nb - 1;
+    AUGB_ROLLED
+    while (a < b) { int mid = (a + b) / 2; if (p < bb[mid]) b = mid; else a = mid + 1; }
+    return m->tis_bp[(size_t)cls * nb + a];
+}
 AUGB_HD sc_t rstart_endpart(const DevModel* m, const Seq& sq, int cls, int end) {
     const int L = sq.L;
     int sp = end - m->tiw - 3 + 1;
@@ -85,7 +95,7 @@ AUGB_HD sc_t rstart_endpart(const DevModel* m, const Seq& sq, int cls, int end) 
     int pn = sq.kmer_rc(sp, 3);
     if (pn < 0 || isneg(m->startp[pn])) return SC_NEG;
     sc_t p = m->startp[pn];
-    if (sp + 3 + m->tiw - 1 + m->tis_k < L) p += motif_rc(m, sq, cls, m->tis, m->tis_n, m->tis_k, sp + 3);
+    if (sp + 3 + m->tiw - 1 + m->tis_k < L) p = tis_bin(m, cls, p + motif_rc(m, sq, cls, m->tis, m->tis_n, m->tis_k, sp + 3));
     else p = (sc_t)(L - (sp + 3)) * m->log025;
     return p;
 }

@@ -292,7 +292,7 @@ struct SweepT {
             if (pn < 0 || isneg(m->startp[pn])) return SC_NEG;
             beginPart = m->startp[pn];
             int tis = bobe - m->tiw;
-            if (tis > m->tis_k) beginPart += motif_fwd1(m->tis, m->tis_n, m->tis_k, tis);
+            if (tis > m->tis_k) beginPart = tis_bin(m, cls, beginPart + motif_fwd1(m->tis, m->tis_n, m->tis_k, tis));
             else beginPart += (sc_t)(bos - 3) * m->log025;
             break;
         }
@@ -409,7 +409,7 @@ struct SweepT {
         if (pn < 0 || isneg(m->startp[pn]) || !(bobe >= 0 && bobe < L - 2)) return SC_NEG;
         sc_t v = m->startp[pn];
         int tis = bobe - m->tiw;
-        if (tis > m->tis_k) v += motif_fwd(m, sq, cls, m->tis, m->tis_n, m->tis_k, tis);
+        if (tis > m->tis_k) v = tis_bin(m, cls, v + motif_fwd(m, sq, cls, m->tis, m->tis_n, m->tis_k, tis));
         else v += (sc_t)(bos - 3) * m->log025;
         const int endOfStart = bos + k - 1;
         int p4 = sq.kmer_end(endOfStart, k);

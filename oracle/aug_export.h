@@ -257,6 +257,20 @@ static void build_params(NAMGene& ng, FeatureCollection& fc, BlobWriter& bw) {
     bw.f64("prob_short_intron", {(uint64_t)C}, psi);
     bw.f64("mal", {(uint64_t)C}, mal);
     export_motif(bw, "tis_motif", ExonModel::GCtransInitMotif, C);
+    if (ExonModel::GCtransInitBinProbs && ExonModel::GCtransInitBinProbs[0].nbins >= 1) {
+        // TRANSINITBIN (exonmodel.cc:706-713): the start codon x TIS motif probability is mapped to the probability of its bin
+        // (BinnedMMGroup::getIndex, merkmal.cc:155-168): per class nbins-1 boundaries and nbins bin probabilities
+        const int nb = ExonModel::GCtransInitBinProbs[0].nbins;
+        std::vector<double> bb, av;
+        for (int c = 0; c < C; c++) {
+            BinnedMMGroup& g = ExonModel::GCtransInitBinProbs[c];
+            if (g.nbins != nb || (int)g.bb.size() < nb - 1 || (int)g.avprobs.size() < nb) { fprintf(stderr, "tis bins differ across classes\n"); exit(2); }
+            for (int i = 0; i < nb - 1; i++) bb.push_back(lg(g.bb[i]));
+            for (int i = 0; i < nb; i++) av.push_back(lg(g.avprobs[i]));
+        }
+        if (nb > 1) bw.f64("tis_bin_bounds", {(uint64_t)C, (uint64_t)(nb - 1)}, bb);
+        bw.f64("tis_bin_probs", {(uint64_t)C, (uint64_t)nb}, av);
+    }
     export_motif(bw, "ass_motif", IntronModel::GCassMotif, C);
 
     if (Constant::utr_option_on) {

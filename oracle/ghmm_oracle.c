@@ -76,12 +76,13 @@ typedef struct {
     sc_t *iemi, *gemi;                           /* [c][1024] */
     double *gpls[8];                             /* igenic Pls, kept as double logs (ratio of sums) */
     sc_t *tis, *assm;                            /* [c][n][4^(k+1)] */
+    int tis_nbins; sc_t *tis_bb, *tis_bp;        /* TRANSINITBIN: [c][nbins-1] boundaries, [c][nbins] bin probabilities (exonmodel.cc:1321-1326, 1437-1442) */
     sc_t *ld_single, *ld_initial, *ld_internal, *ld_terminal, *ld_intron;
     int n_ld_exon, n_ld_intron;
     sc_t *ass_pat, *ass_pat_non, *dss_pat, *dss_pat_non;
     sc_t startp[64]; int isstop[64];
     sc_t ochre, amber, opal, probN, log025, log3;
-    double centroids[64][4]; int ncent; double wm[4][4];
+    double centroids[256][4]; int ncent; double wm[4][4];
     int softmask; sc_t nep_bonus;               /* softmasking: ln bonus of a nonexonpart hint of source RM (extrinsicinfo.cc:1696-1724) */
     /* UtrModel (utrmodel.cc), only with --UTR=on */
     int nc;                                     /* NcModel states present (--nc=on) */
@@ -185,7 +186,8 @@ Model* orc_model_load(const char* path) {
     m->max_exon_len = bint(&b, "max_exon_len"); m->min_exon_length = bint(&b, "min_exon_length");
     m->dss_gc_allowed = bint(&b, "dss_gc_allowed"); m->GCwinsize = bint(&b, "GCwinsize");
     m->weighing = bint(&b, "basecount_weighing_type");
-    if (bint(&b, "transinit_nbins") > 0) { fprintf(stderr, "oracle: TRANSINITBIN not restated\n"); return NULL; }
+    m->tis_nbins = bint(&b, "transinit_nbins");
+    if (m->tis_nbins > 0) { m->tis_bp = qarr(&b, "tis_bin_probs", NULL); m->tis_bb = m->tis_nbins > 1 ? qarr(&b, "tis_bin_bounds", NULL) : NULL; }
     m->tis_n = bint(&b, "tis_motif_n"); m->tis_k = bint(&b, "tis_motif_k");
     m->assm_n = bint(&b, "ass_motif_n"); m->assm_k = bint(&b, "ass_motif_k");
     /* intronmodel.cc:519-520 */
@@ -267,8 +269,8 @@ typedef struct {
     int cls;                                    /* class of current column */
     int *nsf, *nsr;                             /* nearestStopForward / Reverse */
     sc_t* V;                                    /* [L][S] */
-    sc_t *PX[8][3], *PXR[8][3];                 /* exon content prefix sums [class][phi] (lazily built) */
-    sc_t *PI[8], *PIR[8];                       /* intron content prefix sums per class (fwd k-mer / rc k-mer) */
+    sc_t *PX[16][3], *PXR[16][3];                 /* exon content prefix sums [class][phi] (lazily built) */
+    sc_t *PI[16], *PIR[16];                     /* intron content prefix sums per class (fwd k-mer / rc k-mer) */
     struct SnipEnt **snF, **snL;                /* SnippetProbs restatement: per base first/last entry, [2][L] (fwd, rc) */
     /* forward / sampling (NAMGene::viterbiAndForward with needForwardTable, getSampledPath namgene.cc:367-426) */
     int mode;                                   /* 0 Viterbi only, 1 Viterbi + forward fill, 2 sampling step */
@@ -720,6 +722,14 @@ static void intron_eval(Ctx* x, int s, int j, Oli* o) {
 
 /* ------------------------------------------------------------------ exons */
 /* ExonModel::endPartEmiProb, exonmodel.cc:1272-1400 (no hints) */
+/* BinnedMMGroup::getIndex (merkmal.cc:155-168) + avprobs: the start codon x TIS motif probability goes to the probability of its bin */
+static sc_t tis_bin(const Ctx* x, sc_t p) {
+    const Model* m = x->m; int nb = m->tis_nbins;
+    if (nb < 1) return p;
+    const sc_t* bb = m->tis_bb + (size_t)x->cls * (nb - 1); int a = 0, b = nb - 1;
+    while (a < b) { int mid = (a + b) / 2; if (p < bb[mid]) b = mid; else a = mid + 1; }
+    return m->tis_bp[(size_t)x->cls * nb + a];
+}
 static sc_t endPart(Ctx* x, const StateInfo* st, int end) {
     const Model* m = x->m; int L = x->L;
     switch (st->ek) {
@@ -738,7 +748,7 @@ static sc_t endPart(Ctx* x, const StateInfo* st, int end) {
         int pn = s2irc(x, sp, 3);
         if (pn < 0 || isneg(m->startp[pn])) return NEG;
         sc_t p = m->startp[pn];
-        if (sp + 3 + m->tiw - 1 + m->tis_k < L) p += motif_rc(x, m->tis, m->tis_n, m->tis_k, sp + 3);
+        if (sp + 3 + m->tiw - 1 + m->tis_k < L) p = tis_bin(x, p + motif_rc(x, m->tis, m->tis_n, m->tis_k, sp + 3));
         else p = (L - (sp + 3)) * m->log025;
         return p;
     }
@@ -770,7 +780,7 @@ static sc_t notEndPart(Ctx* x, const StateInfo* st, int bos, int right, int fram
         if (pn < 0 || isneg(m->startp[pn])) return NEG;
         beginPart = m->startp[pn];
         int tis = bobe - m->tiw;
-        if (tis > m->tis_k) beginPart += motif_fwd(x, m->tis, m->tis_n, m->tis_k, tis);
+        if (tis > m->tis_k) beginPart = tis_bin(x, beginPart + motif_fwd(x, m->tis, m->tis_n, m->tis_k, tis));
         else beginPart += (sc_t)(bos - 3) * m->log025;
         break;
     }
@@ -1615,7 +1625,7 @@ int orc_decode(const Model* m, const char* dna, int L, const int* gc_in, int64_t
         }
         free(tt);
     }
-    for (int cl = 0; cl < 8; cl++) {
+    for (int cl = 0; cl < 16; cl++) {
         for (int p = 0; p < 3; p++) { free(x->PX[cl][p]); free(x->PXR[cl][p]); }
         free(x->PI[cl]); free(x->PIR[cl]);
     }

@@ -3,7 +3,8 @@
 
 tools/species_sweep.py runs all 167 species directories of the reference through the oracle and the kernel source; two of the sets that
 exposed a defect (an exon following a splice-site state of column 0, possible when the exon part of the signal is shorter than two
-bases) are kept as fixtures:  nasonia (ass_end = 0, 5 GC classes)  and  Monosiga_brevicollis (dss_start = 1).
+bases) are kept as fixtures:  nasonia (ass_end = 0, 5 GC classes)  and  Monosiga_brevicollis (dss_start = 1);  zebrafish stands for the
+TRANSINITBIN sets (start codon x TIS motif probability mapped to bins, exonmodel.cc:1321-1326).
 Writes <species>.params.xz and ref_paths_species.json (the reference's paths + scores on example.fa, --UTR=off --softmasking=0)."""
 import json
 import lzma
@@ -18,7 +19,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 from make_golden import AUGDUMP, ENV, REF, condense  # noqa: E402
 
-SPECIES = ["nasonia", "Monosiga_brevicollis"]
+SPECIES = ["nasonia", "Monosiga_brevicollis", "zebrafish"]
 
 
 def main():

@@ -1,7 +1,7 @@
 """Parameter sets with another splice-signal geometry than human / fly (tools/species_sweep.py: 147 of the reference's species sets decode
 cell for cell like the oracle, the rest is rejected loudly).  Two of the sets that exposed a defect are fixtures: nasonia (ass_end = 0,
 five GC classes) and Monosiga_brevicollis (dss_start = 1) — an exon may follow a splice-site state of COLUMN 0 when the exon part of the
-signal is shorter than two bases (exonmodel.cc:1464-1486 skips the site test for beginOfBioExon < 2)."""
+signal is shorter than two bases (exonmodel.cc:1464-1486 skips the site test for beginOfBioExon < 2).  zebrafish: a TRANSINITBIN set."""
 import json
 import os
 
@@ -10,7 +10,7 @@ import pytest
 from augustus_b200 import synth
 from tests import util
 
-SPECIES = ["nasonia", "Monosiga_brevicollis"]
+SPECIES = ["nasonia", "Monosiga_brevicollis", "zebrafish"]
 
 
 @pytest.fixture(scope="module")

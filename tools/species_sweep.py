@@ -1,7 +1,7 @@
 """Parity sweep over the species parameter sets of the reference (build container only: needs /root/reference and oracle/_ref/augdump).
 For every config/species/<name>: export the blob, dump the reference's Viterbi matrix on a short sequence, load the blob into the oracle
 and into the kernel source (host build), compare every cell.  Prints one line per species: ok / rejected (why) / MISMATCH.
-usage: species_sweep.py [--utr] [species ...]"""
+usage: species_sweep.py [--utr | --nc] [species ...]"""
 import os, subprocess, sys, tempfile
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -10,14 +10,15 @@ from tests import util
 REF = "/root/reference"
 AUGDUMP = os.path.join(util.ROOT, "oracle", "_ref", "augdump")
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
-utr = "--utr" in sys.argv
+utr = "--utr" in sys.argv or "--nc" in sys.argv
+nc = "--nc" in sys.argv
 species = args or sorted(os.listdir(REF + "/config/species"))
 name, dna = util.read_fasta(util.GOLDEN + "/example.fa")[1]
 tot = {"ok": 0, "rejected": 0, "MISMATCH": 0, "reference failed": 0}
 for sp in species:
     with tempfile.TemporaryDirectory() as td:
         blobf, mat = os.path.join(td, "b"), os.path.join(td, "m")
-        cmd = [AUGDUMP, "--species=" + sp, "--softmasking=0"] + (["--UTR=on"] if utr else ["--UTR=off"]) + [util.GOLDEN + "/example.fa"]
+        cmd = [AUGDUMP, "--species=" + sp, "--softmasking=0"] + (["--UTR=on"] if utr else ["--UTR=off"]) + (["--nc=on"] if nc else []) + [util.GOLDEN + "/example.fa"]
         env = dict(os.environ, AUGUSTUS_CONFIG_PATH=REF + "/config", AUGDUMP_PARAMS=blobf, AUGDUMP_MATRIX=mat, AUGDUMP_PATH=os.path.join(td, "p"))
         try:
             r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=120)
