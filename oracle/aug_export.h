@@ -134,7 +134,7 @@ static std::vector<double> lgv(const std::vector<Double>& v) {
 
 static void export_motif(BlobWriter& bw, const char* name, Motif* arr, int C) {
     int n = arr[0].n, k = arr[0].k;
-    size_t w = arr[0].windowProbs[0].size();
+    size_t w = n > 0 ? arr[0].windowProbs[0].size() : 0;        // a motif of width 0 (toxoplasma: no TATA / TTS motif) has no windowProbs
     std::vector<double> v; v.reserve((size_t)C * n * w);
     for (int c = 0; c < C; c++) {
         if (arr[c].n != n || arr[c].k != k) { fprintf(stderr, "motif shape differs across classes\n"); exit(2); }

@@ -17,14 +17,15 @@ name, dna = util.read_fasta(util.GOLDEN + "/example.fa")[1]
 tot = {"ok": 0, "rejected": 0, "MISMATCH": 0, "reference failed": 0}
 for sp in species:
     with tempfile.TemporaryDirectory() as td:
-        blobf, mat = os.path.join(td, "b"), os.path.join(td, "m")
-        cmd = [AUGDUMP, "--species=" + sp, "--softmasking=0"] + (["--UTR=on"] if utr else ["--UTR=off"]) + (["--nc=on"] if nc else []) + [util.GOLDEN + "/example.fa"]
+        blobf, mat, fa = os.path.join(td, "b"), os.path.join(td, "m"), os.path.join(td, "w.fa")
+        open(fa, "w").write(">%s\n%s\n" % (name, dna))        # ONE sequence per process: the reference keeps per-class memos across sequences
+        cmd = [AUGDUMP, "--species=" + sp, "--softmasking=0"] + (["--UTR=on"] if utr else ["--UTR=off"]) + (["--nc=on"] if nc else []) + [fa]
         env = dict(os.environ, AUGUSTUS_CONFIG_PATH=REF + "/config", AUGDUMP_PARAMS=blobf, AUGDUMP_MATRIX=mat, AUGDUMP_PATH=os.path.join(td, "p"))
         try:
             r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=120)
         except subprocess.TimeoutExpired:
             print(sp, "reference failed: timeout"); tot["reference failed"] += 1; continue
-        if r.returncode != 0 or not os.path.exists(blobf) or not os.path.exists(mat + ".2.vit"):
+        if r.returncode != 0 or not os.path.exists(blobf) or not os.path.exists(mat + ".1.vit"):
             print(sp, "reference failed:", (r.stderr.strip().splitlines() or ["?"])[-1][:100]); tot["reference failed"] += 1; continue
         blob = open(blobf, "rb").read()
         from augustus_b200 import params as _p
@@ -35,7 +36,7 @@ for sp in species:
         except Exception as ex:
             print(sp, "rejected by the product's model builder:", str(ex)[:90]); tot["rejected"] += 1; continue
         S = emu.lib.hostemu_statecount(__import__("ctypes").c_void_p(emu.m))
-        V = np.fromfile(mat + ".2.vit").reshape(-1, S)
+        V = np.fromfile(mat + ".1.vit").reshape(-1, S)
         try:
             orc = util.Oracle(blob)
         except Exception as ex:
