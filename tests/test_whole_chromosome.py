@@ -1,0 +1,63 @@
+"""Chunked prediction end to end on the GPU (pytest -m gpu): the first 650 kb of chr2L, `--species=fly` defaults, four overlapping
+200 kb chunks decoded by the drop-in front end (oracle/_ref/augustus_b200 -> libaugb200.so), concatenated and joined by
+augustus_b200/chromosome.py.  Expected: the text the unmodified reference + its Perl scripts produced for the same region
+(tests/golden/chr2L_chunks.json.gz, made by tests/golden/make_golden_join.py) — every gene line, every posterior probability."""
+import gzip
+import json
+import os
+
+import pytest
+
+from augustus_b200 import chromosome as ch
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+REFDIR = os.path.join(util.ROOT, "oracle", "_ref")
+DROPIN = os.path.join(REFDIR, "augustus_b200")
+CFG = os.path.join(REFDIR, "config")
+CHR2L = os.path.join(REFDIR, "data", "chr2L.sm.fa.gz")
+
+
+def _body(text):
+    """Drop what depends on where the binaries and files live: header lines naming paths, and the echoed command lines."""
+    keep, skip = [], False
+    for l in text.splitlines():
+        if l.startswith("# command line:"):
+            skip = True
+            continue
+        if skip:
+            skip = False
+            continue
+        if l.startswith("# Initializing the parameters using config directory") or l.startswith("# Looks like "):
+            continue
+        keep.append(l)
+    return keep
+
+
+@pytest.mark.skipif(not (os.path.exists(DROPIN) and os.path.isdir(CFG) and os.path.exists(CHR2L)),
+                    reason="oracle/_ref/augustus_b200 or oracle/_ref/data/chr2L.sm.fa.gz not present (make -C oracle ref dropin)")
+def test_chr2L_650kb_in_chunks_equals_reference_pipeline(tmp_path):
+    with gzip.open(os.path.join(util.GOLDEN, "chr2L_chunks.json.gz"), "rt") as f:
+        d = json.load(f)
+    seq, n = [], 0
+    with gzip.open(CHR2L, "rt") as f:
+        for line in f:
+            if line.startswith(">"):
+                continue
+            seq.append(line.strip())
+            n += len(seq[-1])
+            if n >= d["region"]:
+                break
+    dna = "".join(seq)[: d["region"]]
+    fa = str(tmp_path / "chr2L_650k.fa")
+    with open(fa, "w") as f:
+        f.write(">chr2L\n")
+        for i in range(0, len(dna), 60):
+            f.write(dna[i:i + 60] + "\n")
+    chunks = ch.plan_chunks(1, d["region"], d["chunksize"], d["overlap"])
+    concat = ch.run_chunks(DROPIN, fa, chunks, ["--species=fly"], env=dict(os.environ, AUGUSTUS_CONFIG_PATH=CFG))
+    assert _body(concat) == _body(d["concat"])
+    joined = ch.join_predictions(concat)
+    assert _body(joined) == _body(d["joined"])
+    assert joined.count("# start gene") == d["joined"].count("# start gene") > 50
