@@ -13,17 +13,26 @@
  * takes the augustus command line and config/species files and prints GFF through the reference's own
  * post-processing; tests/test_dropin.py compares that GFF with the one of oracle/_ref/augustus.
  *
+ * Sequences longer than maxDNAPieceSize work as in the reference: doViterbiPiecewise (namgene.cc:516-676) and its cut search
+ * (getNextCutEndPoint, :973-1133) reach the DP only through these three entry points; at a cut the host swaps initProbs / termProbs
+ * for the synch-state vectors (:594-603), so the shim keeps one library model per (initial, terminal) vector pair it meets (at most
+ * four).  The cut search decodes without sampling; the sampled paths are therefore drawn at the first getSampledPath call, which
+ * keeps the rand() stream position of the process exact.
+ *
  * No CPU fallback: configurations the library does not decode (hints files, protein profiles, overlap
- * mode, CRF training, pieces cut by getNextCutEndPoint) raise ProjectError.
+ * mode, CRF training) raise ProjectError.
  */
+#include <map>
 #include "aug_export.h"
 #include "augb200.h"
 
 namespace {
 
 struct ShimState {
-    augb200_model* model = nullptr;
+    augb200_model* model = nullptr;                          /* the model for the current initProbs / termProbs */
+    std::map<std::string, augb200_model*> models;            /* one per (initProbs, termProbs) pair met so far */
     std::vector<char> blob;
+    bool sampled = false;                                    /* samples of the current window drawn */
     augb200_path vit;
     std::vector<augb200_path> samples;
     int next_sample = 0;
@@ -39,8 +48,17 @@ void fail(const std::string& what, int rc) {
     throw ProjectError("augb200: " + what + ": " + augb200_strerror(rc) + " " + augb200_last_cuda_error());
 }
 
-void ensure_model(NAMGene& ng) {
-    if (g.model) return;
+/* key of a model variant: the bytes of the initial and terminal vectors as NAMGene holds them right now */
+std::string probs_key(const std::vector<Double>& a, const std::vector<Double>& b) {
+    std::string k;
+    for (const std::vector<Double>* v : {&a, &b})
+        for (size_t i = 0; i < v->size(); i++) { double x = (*v)[i].log(); k.append((const char*)&x, sizeof x); }
+    return k;
+}
+
+void ensure_model(NAMGene& ng, const std::string& key) {
+    std::map<std::string, augb200_model*>::iterator it = g.models.find(key);
+    if (it != g.models.end()) { g.model = it->second; return; }
     /* the export reads extrinsic.cfg and swaps GC classes through the models; both chat on cout / cerr, which must not leak into
      * the GFF (the front end already printed its own "Sources of extrinsic information" line) */
     std::ostringstream sink;
@@ -49,15 +67,17 @@ void ensure_model(NAMGene& ng) {
         FeatureCollection fc;
         if (Constant::softmasking) fc.readExtrinsicCFGFile();
         BlobWriter bw;
-        build_params(ng, fc, bw);
+        build_params(ng, fc, bw);                            /* init_probs / term_probs = the vectors of this piece */
         g.blob = bw.bytes();
     } catch (...) { std::cout.rdbuf(oc); std::cerr.rdbuf(oe); throw; }
     std::cout.rdbuf(oc); std::cerr.rdbuf(oe);
     int dev = 0;
     if (const char* e = getenv("AUGB200_DEVICE")) dev = atoi(e);
-    int rc = augb200_model_create(g.blob.data(), g.blob.size(), dev, &g.model);
-    if (rc) { g.model = nullptr; fail("model_create", rc); }
-    if (getenv("AUGSHIM_VERBOSE")) fprintf(stderr, "augshim: model with %d states, %d GC classes on device %d\n",
+    augb200_model* m = nullptr;
+    int rc = augb200_model_create(g.blob.data(), g.blob.size(), dev, &m);
+    if (rc) fail("model_create", rc);
+    g.models[key] = g.model = m;
+    if (getenv("AUGSHIM_VERBOSE")) fprintf(stderr, "augshim: model %zu with %d states, %d GC classes on device %d\n", g.models.size(),
                                             augb200_model_statecount(g.model), augb200_model_num_gc_classes(g.model), dev);
 }
 
@@ -98,22 +118,15 @@ void NAMGene::viterbiAndForward(const char* dna, bool useProfile) {
             }
         }
     }
-    ensure_model(*this);
+    ensure_model(*this, probs_key(initProbs, termProbs));
     augb200_window w; w.dna = g.masked.data(); w.length = (int32_t)n; w.gc_class = nullptr;
     /* cs is public state other reference code reads (printing of GC classes); keep it filled as the original does (:228) */
     cs.computeStairs(dna);
     w.gc_class = cs.idx;
-    int rc;
-    const int ns = sampleiterations > 1 && needForwardTable ? sampleiterations : 1;
-    if (ns > 1) {
-        g.samples.assign(ns - 1, augb200_path());
-        if ((rc = augb200_set_rand_position(g.model, g.rand_pos))) fail("set_rand_position", rc);
-        rc = augb200_decode_batch_sampling(g.model, 1, &w, ns, &g.vit, g.samples.data());
-        if (!rc) g.rand_pos += (uint64_t)augb200_last_rand_consumed(g.model);
-    } else {
-        g.samples.clear();
-        rc = augb200_decode(g.model, &w, &g.vit);
-    }
+    /* Viterbi only: whether sampled paths are wanted is known at the first getSampledPath call (findGenes samples, the cut search
+     * of getNextCutEndPoint does not, and only sampling moves the rand() stream) */
+    g.samples.clear(); g.sampled = false;
+    int rc = augb200_decode(g.model, &w, &g.vit);
     if (rc) fail("decode", rc);
     g.next_sample = 0; g.dnalen = n; g.have = true; g.calls++;
 }
@@ -125,6 +138,18 @@ StatePath* NAMGene::getViterbiPath(const char* dna, const char* seqname) {
 
 StatePath* NAMGene::getSampledPath(const char* dna, const char* seqname) {
     if (!needForwardTable) return new StatePath();                                   /* namgene.cc:369-370 */
-    if (!g.have || g.next_sample >= (int)g.samples.size()) throw ProjectError("augb200: more sampled paths requested than --sample");
+    if (!g.have) throw ProjectError("augb200: getSampledPath before viterbiAndForward");
+    if (!g.sampled) {
+        /* forward matrix + the sampleiterations-1 paths findGenes will ask for (namgene.cc:848), from the process-wide stream position */
+        if (sampleiterations < 2) throw ProjectError("augb200: sampled path requested with --sample < 2");
+        augb200_window w; w.dna = g.masked.data(); w.length = (int32_t)g.dnalen; w.gc_class = cs.idx;
+        g.samples.assign(sampleiterations - 1, augb200_path());
+        int rc;
+        if ((rc = augb200_set_rand_position(g.model, g.rand_pos))) fail("set_rand_position", rc);
+        if ((rc = augb200_decode_batch_sampling(g.model, 1, &w, sampleiterations, &g.vit, g.samples.data()))) fail("decode_batch_sampling", rc);
+        g.rand_pos += (uint64_t)augb200_last_rand_consumed(g.model);
+        g.sampled = true;
+    }
+    if (g.next_sample >= (int)g.samples.size()) throw ProjectError("augb200: more sampled paths requested than --sample");
     return to_statepath(g.samples[g.next_sample++], seqname);
 }

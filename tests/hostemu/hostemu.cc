@@ -121,7 +121,8 @@ static int forward_impl(void* mp, const char* dna, int L, const int32_t* gc_in, 
 /* forward fill + nsamples sampled paths (condensed, concatenated) */
 template <class SW>
 static int sample_impl(void* mp, const char* dna, int L, const int32_t* gc_in, int nsamples, int cap,
-                   int32_t* sb, int32_t* se, uint8_t* st_, uint8_t* str_, int32_t* scount, double* slogp, int32_t* status) {
+                   int32_t* sb, int32_t* se, uint8_t* st_, uint8_t* str_, int32_t* scount, double* slogp, int32_t* status,
+                   uint64_t rand_pos = 0, int32_t* rand_used = nullptr) {
     EmuModel* e = (EmuModel*)mp; const DevModel* m = &e->hm.dm;
     WinLayout lay; std::vector<char> buf; char* base = nullptr; WinView v; WarpState ws; SW sw; WinOuts* outs = nullptr;
     std::vector<char> pool; size_t pool_used = 0;
@@ -140,12 +141,12 @@ static int sample_impl(void* mp, const char* dna, int L, const int32_t* gc_in, i
     }
     if (outs->status) { *status = outs->status; return -1; }
     size_t nrng = (size_t)nsamples * (L + 2);
-    std::vector<uint32_t> rng(nrng);
-    glibc_rand_stream(1, rng.data(), nrng);
+    std::vector<uint32_t> rng(rand_pos + nrng);           /* the walks start rand_pos values into the stream of seed 1 (augb200_set_rand_position) */
+    glibc_rand_stream(1, rng.data(), rand_pos + nrng);
     std::vector<SampleOpt> opts(L + 4096); std::vector<int32_t> sorted(L + 4096); int nopt = 0;
     SamplerT<SW> sp; sp.sw = &sw; sp.sc.opt = opts.data(); sp.sc.opt_cap = (int)opts.size(); sp.sc.sorted = sorted.data(); sp.sc.nopt = &nopt;
-    sp.rng = rng.data(); sp.nrng = (int)nrng;
-    SampleOut so; so.cap = cap; so.begin = sb; so.end = se; so.type = st_; so.trunc = str_; so.count = scount; so.logp = slogp; so.status = status;
+    sp.rng = rng.data() + rand_pos; sp.nrng = (int)nrng;
+    SampleOut so; so.rand_used = rand_used; so.cap = cap; so.begin = sb; so.end = se; so.type = st_; so.trunc = str_; so.count = scount; so.logp = slogp; so.status = status;
 #ifdef AUGB_SIMT32
     simt::run([&]() { SW mine = sw; mine.attach(); mine.lane = lane_id(); SamplerT<SW> sp2 = sp; sp2.sw = &mine; sp2.run(nsamples, so); });
 #else
@@ -173,6 +174,12 @@ int hostemu_sample(void* mp, const char* dna, int L, const int32_t* gc_in, int n
                    int32_t* sb, int32_t* se, uint8_t* st_, uint8_t* str_, int32_t* scount, double* slogp, int32_t* status) {
     return is_utr(mp) ? sample_impl<SweepFwdUtr>(mp, dna, L, gc_in, nsamples, cap, sb, se, st_, str_, scount, slogp, status)
                       : sample_impl<SweepFwd>(mp, dna, L, gc_in, nsamples, cap, sb, se, st_, str_, scount, slogp, status);
+}
+int hostemu_sample_at(void* mp, const char* dna, int L, const int32_t* gc_in, int nsamples, int cap,
+                      int32_t* sb, int32_t* se, uint8_t* st_, uint8_t* str_, int32_t* scount, double* slogp, int32_t* status,
+                      uint64_t rand_pos, int32_t* rand_used) {
+    return is_utr(mp) ? sample_impl<SweepFwdUtr>(mp, dna, L, gc_in, nsamples, cap, sb, se, st_, str_, scount, slogp, status, rand_pos, rand_used)
+                      : sample_impl<SweepFwd>(mp, dna, L, gc_in, nsamples, cap, sb, se, st_, str_, scount, slogp, status, rand_pos, rand_used);
 }
 int hostemu_nchain(void) { return NCHAIN; }
 int hostemu_statecount(void* mp) { return ((EmuModel*)mp)->hm.dm.S; }

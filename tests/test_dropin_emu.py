@@ -1,0 +1,89 @@
+"""The drop-in shim's own logic on the CPU: oracle/_ref/augustus_emu is the reference front end + oracle/augshim.cc (exactly as in
+the drop-in oracle/_ref/augustus_b200) linked against tests/hostemu/augb200_emu.cc — the C ABI served by the host build of the
+kernel source — instead of libaugb200.so.  Its GFF must equal the unmodified reference binary's.  Covers what the shim adds on
+top of the library: one model per (initProbs, termProbs) pair for the pieces of sequences longer than maxDNAPieceSize
+(doViterbiPiecewise, namgene.cc:516-676, cut search :973-1133), sampled paths drawn lazily at the first getSampledPath call, the
+rand() stream position carried across pieces and sequences.  Build container only (needs oracle/_ref/, made by oracle/Makefile);
+the same command lines run against the GPU library in tests/test_dropin.py."""
+import os
+import subprocess
+
+import pytest
+
+from tests import util
+
+REFDIR = os.path.join(util.ROOT, "oracle", "_ref")
+REF = os.path.join(REFDIR, "augustus")
+EMU = os.path.join(REFDIR, "augustus_emu")
+CFG = os.path.join(REFDIR, "config")
+EXAMPLE = os.path.join(util.GOLDEN, "example.fa")
+
+pytestmark = pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(EMU) and os.path.isdir(CFG)),
+                                reason="oracle/_ref/augustus{,_emu} not built (make -C oracle ref dropin_emu)")
+
+
+def _run(exe, args, extra_env=None, fasta=EXAMPLE):
+    env = dict(os.environ, AUGUSTUS_CONFIG_PATH=CFG, **(extra_env or {}))
+    r = subprocess.run([exe] + list(args) + [fasta], env=env, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stderr[-2000:] + r.stdout[-2000:]
+    lines = r.stdout.splitlines()
+    if "# command line:" in lines:                     # the trailer echoes argv[0]
+        lines = lines[: lines.index("# command line:")]
+    return lines, r.stderr
+
+
+def _same(args):
+    want, _ = _run(REF, args)
+    got, err = _run(EMU, args, {"AUGSHIM_VERBOSE": "1"})
+    assert sum(1 for l in want if "\tCDS\t" in l) >= 5, "reference predicted nothing: weak test"
+    assert got == want
+    return err
+
+
+def test_single_piece_sequences():
+    err = _same(["--species=human", "--softmasking=0"])
+    assert err.count("augshim: model") == 1
+
+
+def test_pieces_use_one_model_per_initial_terminal_vector_pair():
+    """maxDNAPieceSize below the sequence length: first / inner / last pieces swap initProbs and termProbs for the synch-state
+    vectors (namgene.cc:594-603) -> four model variants; the cut search decodes exam chunks with the vectors of the previous piece."""
+    err = _same(["--species=human", "--softmasking=0", "--maxDNAPieceSize=3000"])
+    assert err.count("augshim: model") == 4
+    _same(["--species=human", "--softmasking=0", "--UTR=on", "--maxDNAPieceSize=2500"])
+
+
+def test_pieces_with_sampling_keep_the_rand_stream():
+    """--sample=100 on pieces: the cut search runs the DP without sampling, so the sampled paths (and the posterior probabilities in
+    the GFF) only stay identical if the shim draws them lazily and carries the stream position across pieces and sequences."""
+    _same(["--species=human", "--softmasking=0", "--maxDNAPieceSize=4000", "--sample=100", "--alternatives-from-sampling=true"])
+
+
+def test_fly_defaults_260kb_two_pieces_cut_by_the_cut_search(tmp_path):
+    """--species=fly defaults (UTR states, softmasking, sample=100) on the first 260 kb of chr2L: longer than fly's maxDNAPieceSize
+    (200 000), so the cut search decodes an exam chunk around the end of the range and cuts inside a predicted intergenic region."""
+    import concurrent.futures as cf
+    import gzip
+    src = os.path.join(REFDIR, "data", "chr2L.sm.fa.gz")
+    if not os.path.exists(src):
+        pytest.skip("oracle/_ref/data/chr2L.sm.fa.gz not present")
+    seq, n = [], 0
+    with gzip.open(src, "rt") as f:
+        for line in f:
+            if not line.startswith(">"):
+                seq.append(line.strip())
+                n += len(seq[-1])
+                if n >= 260000:
+                    break
+    fa = str(tmp_path / "chr2L_260k.fa")
+    with open(fa, "w") as f:
+        f.write(">chr2L\n" + "".join(seq)[:260000] + "\n")
+    with cf.ThreadPoolExecutor(2) as ex:
+        fw = ex.submit(_run, REF, ["--species=fly", "--progress=true"], None, fa)
+        fg = ex.submit(_run, EMU, ["--species=fly", "--progress=true"], {"AUGSHIM_VERBOSE": "1"}, fa)
+        (want, werr), (got, gerr) = fw.result(), fg.result()
+    pieces = [l for l in werr.splitlines() if l.startswith("examining piece")]
+    assert len(pieces) == 2 and not pieces[0].startswith("examining piece 1..200000 "), pieces      # a cut found by the search, not the fallback
+    assert [l for l in gerr.splitlines() if l.startswith("examining piece")] == pieces
+    assert sum(1 for l in want if "\tCDS\t" in l) >= 50
+    assert got == want
