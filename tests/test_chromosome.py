@@ -68,3 +68,23 @@ def test_join_of_reference_chunk_outputs_equals_the_reference_pipeline():
     assert n_in > n_out > 50                                        # genes predicted twice in the overlaps were removed
     # streaming input (an iterable of lines) gives the same text
     assert ch.join_predictions(iter(d["concat"].splitlines(keepends=True))) == got
+
+
+def test_chunk_runs_through_the_shim_equal_the_reference_pipeline(tmp_path):
+    """run_chunks + join on the first 650 kb of chr2L with the CPU twin of the drop-in front end (oracle/_ref/augustus_emu: reference
+    front end + oracle/augshim.cc + host build of the kernel source, tests/test_dropin_emu.py) — the per-chunk outputs and the joined
+    text equal what the unmodified reference and its Perl scripts produced.  The GPU run of the same pipeline: tests/test_whole_chromosome.py."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("twc", os.path.join(util.ROOT, "tests", "test_whole_chromosome.py"))
+    twc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(twc)
+    emu = os.path.join(twc.REFDIR, "augustus_emu")
+    if not (os.path.exists(emu) and os.path.exists(twc.CHR2L) and os.path.isdir(twc.CFG)):
+        pytest.skip("oracle/_ref/augustus_emu or chr2L not present (make -C oracle ref dropin_emu)")
+    d = _load("chr2L_chunks.json.gz")
+    fa = str(tmp_path / "chr2L_650k.fa")
+    twc._write_region(fa, d["region"])
+    chunks = ch.plan_chunks(1, d["region"], d["chunksize"], d["overlap"])
+    concat = ch.run_chunks(emu, fa, chunks, ["--species=fly"], env=dict(os.environ, AUGUSTUS_CONFIG_PATH=twc.CFG))
+    assert twc._body(concat) == twc._body(d["concat"])
+    assert twc._body(ch.join_predictions(concat)) == twc._body(d["joined"])
