@@ -209,23 +209,28 @@ def join_predictions(text, droplist=None, err=None):
     return Joiner(droplist, err).join(lines)
 
 
-def run_chunks(exe, fasta, chunks, args=(), env=None, timeout=3600):
-    """One front-end process per chunk, in order, as the joblist of the reference does (`<command> --predictionStart=a
-    --predictionEnd=b <fasta>`, createAugustusJoblist.pl:176-178); returns the concatenated outputs.  `exe` is a binary with the
-    `augustus` command line — the drop-in front end of INTEGRATION.md §0 decodes on the GPU; a failing run raises (no fallback)."""
-    outs = []
-    for a, b in chunks:
+def run_chunks(exe, fasta, chunks, args=(), env=None, timeout=3600, jobs=1):
+    """One front-end process per chunk as the joblist of the reference does (`<command> --predictionStart=a --predictionEnd=b
+    <fasta>`, createAugustusJoblist.pl:176-178), `jobs` of them at a time (they share the GPU); returns the outputs concatenated in
+    chunk order.  `exe` is a binary with the `augustus` command line — the drop-in front end of INTEGRATION.md §0 decodes on the GPU;
+    a failing run raises (no fallback)."""
+    def one(chunk):
+        a, b = chunk
         r = subprocess.run([exe] + list(args) + ["--predictionStart=%d" % a, "--predictionEnd=%d" % b, fasta],
                            env=env if env is not None else os.environ, capture_output=True, text=True, timeout=timeout)
         if r.returncode != 0:
             raise RuntimeError("chunk %d..%d failed (%d): %s" % (a, b, r.returncode, (r.stderr or r.stdout)[-2000:]))
-        outs.append(r.stdout)
-    return "".join(outs)
+        return r.stdout
+    if jobs <= 1:
+        return "".join(one(c) for c in chunks)
+    import concurrent.futures as cf
+    with cf.ThreadPoolExecutor(jobs) as ex:
+        return "".join(ex.map(one, chunks))
 
 
-def predict_chromosome(exe, fasta, length, chunksize, overlap, args=(), env=None, padding=0):
+def predict_chromosome(exe, fasta, length, chunksize, overlap, args=(), env=None, padding=0, jobs=1):
     """Plan the chunks of a sequence of `length` bases, run them, join: the joined GFF text of the whole sequence."""
-    return join_predictions(run_chunks(exe, fasta, plan_chunks(1, length, chunksize, overlap, padding), args, env))
+    return join_predictions(run_chunks(exe, fasta, plan_chunks(1, length, chunksize, overlap, padding), args, env, jobs=jobs))
 
 
 if __name__ == "__main__":          # filter like the reference script: chromosome.py [--droplist=file] < augustus.concat > augustus.joined

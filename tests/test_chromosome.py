@@ -85,6 +85,6 @@ def test_chunk_runs_through_the_shim_equal_the_reference_pipeline(tmp_path):
     fa = str(tmp_path / "chr2L_650k.fa")
     twc._write_region(fa, d["region"])
     chunks = ch.plan_chunks(1, d["region"], d["chunksize"], d["overlap"])
-    concat = ch.run_chunks(emu, fa, chunks, ["--species=fly"], env=dict(os.environ, AUGUSTUS_CONFIG_PATH=twc.CFG))
+    concat = ch.run_chunks(emu, fa, chunks, ["--species=fly"], env=dict(os.environ, AUGUSTUS_CONFIG_PATH=twc.CFG), jobs=4)
     assert twc._body(concat) == twc._body(d["concat"])
     assert twc._body(ch.join_predictions(concat)) == twc._body(d["joined"])
