@@ -84,7 +84,9 @@ typedef struct augb200_path {
 } augb200_path;
 
 /* Create a model from an AUGB2PAR blob (copied; the caller may free it afterwards). `device` is the
- * CUDA device ordinal. */
+ * CUDA device ordinal.  Several models may live on one device and be used in turn by the host thread (each call uploads its own
+ * model constants): the reference swaps initProbs / termProbs for the synch-state vectors at the cut points of long sequences
+ * (NAMGene::doViterbiPiecewise, namgene.cc:594-603) — a host serves that with one model per vector pair (oracle/augshim.cc). */
 int augb200_model_create(const void* blob, size_t nbytes, int device, augb200_model** out);
 void augb200_model_destroy(augb200_model* m);
 

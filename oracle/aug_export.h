@@ -74,13 +74,13 @@ struct BlobWriter {
     std::vector<Ent> ents;
     void add(const char* name, uint32_t dtype, std::vector<uint64_t> dims, const void* p, size_t nbytes) {
         Ent x; memset(&x.e, 0, sizeof x.e);
-        if (strlen(name) >= sizeof x.e.name) { fprintf(stderr, "name too long %s\n", name); exit(2); }
+        if (strlen(name) >= sizeof x.e.name) throw ProjectError(std::string("augb200 export: array name too long: ") + name);
         strcpy(x.e.name, name);
         x.e.dtype = dtype; x.e.ndim = (uint32_t)dims.size();
         uint64_t n = 1;
         for (size_t i = 0; i < dims.size(); i++) { x.e.dims[i] = dims[i]; n *= dims[i]; }
         size_t es = dtype == AUGB200_DT_F64 ? 8 : 4;
-        if (n * es != nbytes) { fprintf(stderr, "size mismatch for %s\n", name); exit(2); }
+        if (n * es != nbytes) throw ProjectError(std::string("augb200 export: unexpected table size for ") + name + " (this model configuration is not exportable)");
         x.e.nbytes = nbytes;
         x.data.assign((const char*)p, (const char*)p + nbytes);
         ents.push_back(x);
@@ -137,7 +137,7 @@ static void export_motif(BlobWriter& bw, const char* name, Motif* arr, int C) {
     size_t w = n > 0 ? arr[0].windowProbs[0].size() : 0;        // a motif of width 0 (toxoplasma: no TATA / TTS motif) has no windowProbs
     std::vector<double> v; v.reserve((size_t)C * n * w);
     for (int c = 0; c < C; c++) {
-        if (arr[c].n != n || arr[c].k != k) { fprintf(stderr, "motif shape differs across classes\n"); exit(2); }
+        if (arr[c].n != n || arr[c].k != k) throw ProjectError(std::string("augb200 export: motif shape differs across GC classes: ") + name);
         for (int i = 0; i < n; i++) { auto t = lgv(arr[c].windowProbs[i]); v.insert(v.end(), t.begin(), t.end()); }
     }
     bw.f64(name, {(uint64_t)C, (uint64_t)n, (uint64_t)w}, v);
@@ -264,7 +264,7 @@ static void build_params(NAMGene& ng, FeatureCollection& fc, BlobWriter& bw) {
         std::vector<double> bb, av;
         for (int c = 0; c < C; c++) {
             BinnedMMGroup& g = ExonModel::GCtransInitBinProbs[c];
-            if (g.nbins != nb || (int)g.bb.size() < nb - 1 || (int)g.avprobs.size() < nb) { fprintf(stderr, "tis bins differ across classes\n"); exit(2); }
+            if (g.nbins != nb || (int)g.bb.size() < nb - 1 || (int)g.avprobs.size() < nb) throw ProjectError("augb200 export: TRANSINITBIN tables differ across GC classes");
             for (int i = 0; i < nb - 1; i++) bb.push_back(lg(g.bb[i]));
             for (int i = 0; i < nb; i++) av.push_back(lg(g.avprobs[i]));
         }
