@@ -87,3 +87,31 @@ def test_fly_defaults_260kb_two_pieces_cut_by_the_cut_search(tmp_path):
     assert [l for l in gerr.splitlines() if l.startswith("examining piece")] == pieces
     assert sum(1 for l in want if "\tCDS\t" in l) >= 50
     assert got == want
+
+
+def test_ragged_input_softmasked_runs_unknown_bases_tiny_sequences(tmp_path):
+    """One multi-FASTA with what real input holds: lower-case (soft-masked) runs with softmasking at its default (on), runs of N, IUPAC
+    codes, a 57-base and a 6-base sequence, an all-N sequence — through the front end, the shim and the kernel source, compared with the
+    unmodified reference (Viterbi, UTR states, fly defaults with sampling, and pieces with sampling)."""
+    import random
+    seqs = util.read_fasta(EXAMPLE)
+    rng = random.Random(5)
+    d = list(seqs[0][1])
+    for _ in range(25):
+        a = rng.randrange(len(d))
+        for i in range(a, min(len(d), a + rng.randrange(10, 400))):
+            d[i] = d[i].lower()
+    for _ in range(6):
+        a = rng.randrange(len(d))
+        for i in range(a, min(len(d), a + rng.randrange(1, 60))):
+            d[i] = "N"
+    fa = str(tmp_path / "ragged.fa")
+    with open(fa, "w") as f:
+        f.write(">masked_with_N\n" + "".join(d) + "\n>short\n" + seqs[1][1][:57] + "\n>tiny\nACGTAC\n>allN\n" + "N" * 300 + "\n>iupac\n"
+                + seqs[1][1][:1200].replace("A", "R", 3).replace("C", "y", 4) + "\n")
+    for args in (["--species=human"], ["--species=human", "--UTR=on"], ["--species=fly"],
+                 ["--species=human", "--softmasking=0", "--sample=50", "--alternatives-from-sampling=true", "--maxDNAPieceSize=2000"]):
+        want, _ = _run(REF, args, fasta=fa)
+        got, _ = _run(EMU, args, fasta=fa)
+        assert any("\tCDS\t" in l for l in want)
+        assert got == want, args
