@@ -82,15 +82,3 @@ def test_synthetic_50k_window_gff_identical(tmp_path):
     fa = str(tmp_path / "syn.fa")
     synth.write_fasta(fa, [synth.window(3, 50000)], ["w3"])
     _same_gff(["--species=human", "--softmasking=0"], fa)
-
-
-@needs_binaries
-def test_sequences_longer_than_maxDNAPieceSize_are_decoded_in_pieces():
-    """doViterbiPiecewise (namgene.cc:516-676): pieces with the synch-state vectors as initial / terminal probabilities at the cuts
-    (one library model per vector pair) and the cut search of getNextCutEndPoint (:973-1133) through the same three entry points;
-    with --sample=100 the rand() stream runs on across pieces while the cut search must not touch it.  The shim logic itself is
-    covered on the CPU by tests/test_dropin_emu.py; this is the same command line against libaugb200.so."""
-    fa = os.path.join(util.GOLDEN, "example.fa")
-    _same_gff(["--species=human", "--softmasking=0", "--maxDNAPieceSize=3000"], fa)
-    _same_gff(["--species=human", "--softmasking=0", "--UTR=on", "--maxDNAPieceSize=2500"], fa)
-    _same_gff(["--species=human", "--softmasking=0", "--maxDNAPieceSize=4000", "--sample=100", "--alternatives-from-sampling=true"], fa)

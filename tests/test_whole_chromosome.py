@@ -93,3 +93,24 @@ def test_chr2L_650kb_in_one_process_is_decoded_in_pieces_like_the_reference(tmp_
     assert len(wp) == 4 and gp == wp
     assert sum(1 for l in want if "\tCDS\t" in l) > 200
     assert got == want
+
+
+@needs_files
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/augustus not built")
+def test_example_fa_in_pieces_with_utr_and_sampling():
+    """Small pieces on example.fa (--maxDNAPieceSize below the sequence length): four model variants (initial / terminal vectors at
+    the cuts), UTR states, and --sample=100 whose rand() stream runs on across pieces while the cut search must not touch it.
+    The same command lines pass against the CPU twin in tests/test_dropin_emu.py."""
+    import subprocess
+    fa = os.path.join(util.GOLDEN, "example.fa")
+    env = dict(os.environ, AUGUSTUS_CONFIG_PATH=CFG)
+    for args in (["--species=human", "--softmasking=0", "--maxDNAPieceSize=3000"],
+                 ["--species=human", "--softmasking=0", "--UTR=on", "--maxDNAPieceSize=2500"],
+                 ["--species=human", "--softmasking=0", "--maxDNAPieceSize=4000", "--sample=100", "--alternatives-from-sampling=true"]):
+        outs = []
+        for exe in (REF, DROPIN):
+            r = subprocess.run([exe] + args + [fa], env=env, capture_output=True, text=True, timeout=1200)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs.append(_body(r.stdout))
+        assert any("\tCDS\t" in l for l in outs[0])
+        assert outs[0] == outs[1], args
