@@ -98,6 +98,8 @@ int HostModel::build(const void* blob, size_t nbytes) {
         if (m.softmask && !r.i32("extrinsic_malus_all_one")) { err = "extrinsic configurations with a malus are not supported"; return AUGB200_ERR_UNSUPPORTED; }
     }
     if (m.nc && m.softmask) { err = "nc states with softmasking are not supported yet"; return AUGB200_ERR_UNSUPPORTED; }
+    /* --temperature heats the forward summands of the sampling pass (LLDouble::heated, lldouble.cc:209-264); only 0 (cold) is decoded */
+    if (r.b.find("temperature") && r.i32("temperature") != 0) { err = "sampling temperature != 0 is not supported"; return AUGB200_ERR_UNSUPPORTED; }
     m.dStateLen = m.d - 2 - m.dss_end - m.ass_start - 2 - m.ass_up;     /* intronmodel.cc:519-520 */
     if (m.dStateLen < 1) { err = "d too small"; return AUGB200_ERR_UNSUPPORTED; }
 

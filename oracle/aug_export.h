@@ -150,6 +150,7 @@ static void build_params(NAMGene& ng, FeatureCollection& fc, BlobWriter& bw) {
     bw.scalar_i("num_gc_classes", C);
     bw.scalar_i("synchstate", Properties::getIntProperty("/NAMGene/SynchState"));
     bw.scalar_i("utr_option_on", Constant::utr_option_on);
+    bw.scalar_i("temperature", (int)Constant::temperature);      // types.cc:443-448: heats the sampling distribution (LLDouble::heated)
     {   // softmasking (extrinsicinfo.cc:1696-1724): every lower-case run becomes a nonexonpart hint of source RM; with the default
         // extrinsic.cfg its bonus (1.15) is the only factor different from 1 — every malus / local malus is 1
         double lb = 0; int plain = 1;

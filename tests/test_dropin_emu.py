@@ -115,3 +115,17 @@ def test_ragged_input_softmasked_runs_unknown_bases_tiny_sequences(tmp_path):
         got, _ = _run(EMU, args, fasta=fa)
         assert any("\tCDS\t" in l for l in want)
         assert got == want, args
+
+
+@pytest.mark.parametrize("args,needle", [
+    (["--temperature=3", "--sample=50"], "sampling temperature != 0 is not supported"),       # LLDouble::heated in the sampling pass
+    (["--genemodel=intronless"], "not exportable"),                                          # no intron tables in that model
+    (["--genemodel=exactlyone"], "duplicate state role"),                                    # two intergenic states
+    (["--genemodel=bacterium"], "overlap mode"),
+])
+def test_configurations_outside_the_scope_end_with_an_error_not_with_other_output(args, needle):
+    """No silent approximation: what the library does not decode stops the front end with a message (the reference's ProjectError path)."""
+    env = dict(os.environ, AUGUSTUS_CONFIG_PATH=CFG)
+    r = subprocess.run([EMU, "--species=human", "--softmasking=0"] + args + [EXAMPLE], env=env, capture_output=True, text=True, timeout=600)
+    assert needle in r.stderr + r.stdout
+    assert "\tCDS\t" not in r.stdout
