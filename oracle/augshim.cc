@@ -101,6 +101,11 @@ void NAMGene::viterbiAndForward(const char* dna, bool useProfile) {
     if (useProfile || profileModel) throw ProjectError("augb200: protein profile models are not decoded on the GPU");
     if (Constant::overlapmode) throw ProjectError("augb200: overlap mode is not decoded on the GPU");
     if (inCRFTraining) throw ProjectError("augb200: CRF training runs on the CPU build");
+    {   /* --emiprobs re-scores the predicted path against the CPU matrices (getPathEmiProb, augustus.cc:423-441): not available here */
+        bool emi = false;
+        try { emi = Properties::getBoolProperty("emiprobs"); } catch (...) {}
+        if (emi) throw ProjectError("augb200: --emiprobs needs the DP matrices of the CPU build");
+    }
     const long n = (long)strlen(dna);
     /* the DP sees a lower-cased sequence (SequenceFeatureCollection::prepare, extrinsicinfo.cc:1726-1727); soft-masked runs
      * arrive as nonexonpart hints of source RM (:1696-1724).  The library takes the case of the window instead, so rebuild it. */

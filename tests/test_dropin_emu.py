@@ -122,6 +122,7 @@ def test_ragged_input_softmasked_runs_unknown_bases_tiny_sequences(tmp_path):
     (["--genemodel=intronless"], "not exportable"),                                          # no intron tables in that model
     (["--genemodel=exactlyone"], "duplicate state role"),                                    # two intergenic states
     (["--genemodel=bacterium"], "overlap mode"),
+    (["--emiprobs=on"], "--emiprobs needs the DP matrices"),                                 # re-scores paths against the CPU matrices
 ])
 def test_configurations_outside_the_scope_end_with_an_error_not_with_other_output(args, needle):
     """No silent approximation: what the library does not decode stops the front end with a message (the reference's ProjectError path)."""
