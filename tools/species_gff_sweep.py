@@ -2,7 +2,7 @@
 run the unmodified `augustus` and the CPU twin of the drop-in (oracle/_ref/augustus_emu: reference front end + oracle/augshim.cc + host
 build of the kernel source) on tests/golden/example.fa with the species' own defaults (most sample 100 paths) and compare the output
 byte for byte.  Complements species_sweep.py (Viterbi cells) with the sampled paths / posterior probabilities per species.
-usage: species_gff_sweep.py [--utr] [species ...]"""
+usage: species_gff_sweep.py [--utr] [--fasta=file.fa --softmask] [species ...]   (--softmask: softmasking at its default, on)"""
 import concurrent.futures as cf
 import os
 import subprocess
@@ -14,6 +14,8 @@ REF = "/root/reference"
 BIN = os.path.join(util.ROOT, "oracle", "_ref")
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
 extra = ["--UTR=on"] if "--utr" in sys.argv else ["--UTR=off"]
+extra += [] if "--softmask" in sys.argv else ["--softmasking=0"]
+FASTA = ([a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--fasta=")] or [util.GOLDEN + "/example.fa"])[0]
 species = args or sorted(os.listdir(REF + "/config/species"))
 env = dict(os.environ, AUGUSTUS_CONFIG_PATH=REF + "/config")
 
@@ -24,7 +26,7 @@ def body(text):
 
 
 def one(sp):
-    cmd = ["--species=" + sp, "--softmasking=0"] + extra + [util.GOLDEN + "/example.fa"]
+    cmd = ["--species=" + sp] + extra + [FASTA]
     try:
         r = subprocess.run([BIN + "/augustus"] + cmd, env=env, capture_output=True, text=True, timeout=600)
         e = subprocess.run([BIN + "/augustus_emu"] + cmd, env=env, capture_output=True, text=True, timeout=600)
