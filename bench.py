@@ -374,7 +374,8 @@ def main():
                     "value": mbp3 / dt3, "unit": "Mbp/s", "windows": len(w3), "sweep_ms": dec3.last_sweep_ms, "path_states": int(vit3[0].sum()), "sampled_paths": int(len(samp3[0]))}
             if not args.no_cpu_baseline:
                 cores = os.cpu_count() or 1
-                sub = w3[: min(len(w3), cores)]
+                # half the cores: one 200 kb fly window costs the reference ~46 s on a free core and the default run has to end within minutes
+                sub = w3[: min(len(w3), max(1, cores // 2))]
                 v3, d3 = run_reference_sample(0, cores, seqs=sub, base_args=("--species=fly",), one_per_process=True)
                 sec3["cpu_baseline"] = {"value": v3, "unit": "Mbp/s", "cores": min(cores, len(sub)), "kind": "reference",
                                         "sample": "%d of the windows, one unmodified augustus --species=fly process per window (%.1f s wall)" % (len(sub), d3)}
