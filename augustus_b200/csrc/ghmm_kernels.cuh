@@ -13,15 +13,6 @@
 
 namespace augb {
 
-/* per-window descriptor in device memory */
-struct WinDev {
-    char* base;                /* workspace of this window */
-    const char* dna;           /* device copy of the ASCII window */
-    const uint8_t* gc_in;      /* device copy of host-provided classes or nullptr */
-    int L;
-    WinLayout lay;
-};
-
 /* The model lives in constant memory: its scalars become instruction operands (c[bank][offset]) instead of loads, which
  * matters for the sweep's code size.  One symbol per process: the host re-uploads it when another model runs. */
 __constant__ DevModel c_model;
@@ -299,21 +290,26 @@ __global__ void __launch_bounds__(PREP_BS) k_prep(const WinDev* __restrict__ win
 #define AUGB_SWEEP_MINB 4
 #endif
 constexpr int SWEEP_WARPS = AUGB_SWEEP_WARPS;
+constexpr int SWEEP_TEAMS = SWEEP_WARPS * 32 / AUGB_TEAM;      /* windows in flight per CTA: one per team of AUGB_TEAM lanes */
+/* the next window of the queue for the caller's team */
+__device__ __forceinline__ int next_window(int* __restrict__ next) {
+    int wi = 0;
+    if (lane_id() == 0) wi = atomicAdd(next, 1);
+    return wbcast(wi, 0);
+}
 template <class SW>
 __device__ __forceinline__ void sweep_body(const WinDev* __restrict__ wins, int nwin, int* __restrict__ next) {
     const DevModel* m = &c_model;
-    __shared__ WarpState wstate[SWEEP_WARPS];
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ WarpState wstate[SWEEP_TEAMS];
+    const int tid = threadIdx.x / AUGB_TEAM;
     for (;;) {
-        int wi = 0;
-        if (lane == 0) wi = atomicAdd(next, 1);
-        wi = __shfl_sync(0xffffffffu, wi, 0);
+        const int wi = next_window(next);
         if (wi >= nwin) break;
         const WinDev& wd = wins[wi];
-        SW sw; sw.m = m; sw.ws = &wstate[wid];
+        SW sw; sw.m = m; sw.ws = &wstate[tid];
         sw.w = make_view(wd.base, wd.lay, wd.L, 0);
         sw.run();
-        __syncwarp();
+        wsync();
     }
 }
 __global__ void __launch_bounds__(SWEEP_WARPS * 32, AUGB_SWEEP_MINB) k_sweep(const WinDev* __restrict__ wins, int nwin, int* __restrict__ next) { sweep_body<Sweep>(wins, nwin, next); }
@@ -324,19 +320,17 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32, 3) k_sweep_utr(const WinDev*
 template <class SW>
 __device__ __forceinline__ void sweep_sample_body(const WinDev* __restrict__ wins, int nwin, int* __restrict__ next, const uint32_t* __restrict__ rng, int nrng) {
     const DevModel* m = &c_model;
-    __shared__ WarpState wstate[SWEEP_WARPS];
-    __shared__ int s_nopt[SWEEP_WARPS];
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ WarpState wstate[SWEEP_TEAMS];
+    __shared__ int s_nopt[SWEEP_TEAMS];
+    const int wid = threadIdx.x / AUGB_TEAM, lane = lane_id();
     for (;;) {
-        int wi = 0;
-        if (lane == 0) wi = atomicAdd(next, 1);
-        wi = __shfl_sync(0xffffffffu, wi, 0);
+        const int wi = next_window(next);
         if (wi >= nwin) break;
         const WinDev& wd = wins[wi];
         SW sw; sw.m = m; sw.ws = &wstate[wid];
         sw.w = make_view(wd.base, wd.lay, wd.L, 0);
         sw.run();
-        __syncwarp();
+        wsync();
         WinOuts* outs = (WinOuts*)(wd.base + wd.lay.outs);
         if (wd.lay.nsamp > 0) {
             if (wstate[wid].status) { if (lane == 0) outs->samp_status = wstate[wid].status; }
@@ -351,7 +345,7 @@ __device__ __forceinline__ void sweep_sample_body(const WinDev* __restrict__ win
                 sp.run(wd.lay.nsamp, so);
             }
         }
-        __syncwarp();
+        wsync();
     }
 }
 

@@ -88,6 +88,15 @@ inline WinLayout make_layout(int L, int C, bool generous = false, bool forward =
     return w;
 }
 
+/* per-window descriptor in device memory */
+struct WinDev {
+    char* base;                /* workspace of this window */
+    const char* dna;           /* device copy of the ASCII window */
+    const uint8_t* gc_in;      /* device copy of host-provided classes or nullptr */
+    int L;
+    WinLayout lay;
+};
+
 AUGB_HD WinView make_view(char* base, const WinLayout& lay, int L, int classmask) {
     WinView v; v.L = L; v.nclassmask = classmask; v.ev_cap = lay.ev_cap; v.cl_cap = lay.cl_cap; v.cp_cap = lay.cp_cap;
     v.code = (const uint8_t*)(base + lay.code); v.gc = (const uint8_t*)(base + lay.gc); v.mask = (const mask_t*)(base + lay.mask);

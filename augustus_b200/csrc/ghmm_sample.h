@@ -66,7 +66,7 @@ struct SamplerT {
         res = wbcast(res, 0);
         cursor++;
 #if AUGB_SIMT
-        add = __shfl_sync(0xffffffffu, add, 0);
+        add = wbcastd(add, 0);
 #endif
         *lp += add;
         return res;

@@ -14,58 +14,92 @@ namespace augb {
 
 /* AUGB_SIMT: the 32-lane flavour of the source — the device, or (AUGB_SIMT32, set by the test suite only) a CPU executor that runs
  * 32 fibers per warp and supplies the warp intrinsics; the product library is never built with it */
+#ifndef AUGB_TEAM
+#define AUGB_TEAM 32
+#endif
+/* AUGB_TASKS (ghmm_tasks.cu): the task-engine flavour.  The state routines are compiled in their one-lane form (no collectives
+ * inside exon_eval / lessd_eval / ...) and the AUGB_EL "engine lanes" of a warp each run ONE (state, column) task of the current
+ * column of the warp's window; the engine collectives (e*) below publish the results.  AUGB_EL = 32 on the device and on the
+ * 32-fiber CPU executor of the test suite, 1 in a plain host build (tasks then run one after the other). */
+#if defined(AUGB_TASKS)
+#define AUGB_SIMT 0
 #if defined(__CUDA_ARCH__) || defined(AUGB_SIMT32)
+#define AUGB_EL 32
+#else
+#define AUGB_EL 1
+#endif
+#elif defined(__CUDA_ARCH__) || defined(AUGB_SIMT32)
 #define AUGB_SIMT 1
 #else
 #define AUGB_SIMT 0
 #endif
 #if AUGB_SIMT
-#define AUGB_NLANES 32
+/* AUGB_TEAM = lanes per window (power of two, default 32 = one warp per window).  With a smaller team a warp holds 32 / AUGB_TEAM
+ * windows whose teams walk the same routines together: the collectives below act on the lanes of the caller's team only
+ * (sub-warp masks; ballots are returned team-relative, bit 0 = first lane of the team). */
+#define AUGB_NLANES AUGB_TEAM
+/* the three reading frames of a state kind in one pass need 3 x 8 lanes */
+#define AUGB_GROUP3 (AUGB_NLANES == 32)
 #if defined(__CUDA_ARCH__)
-AUGB_D int lane_id() { return threadIdx.x & 31; }
+AUGB_D int lane_id() { return threadIdx.x & (AUGB_TEAM - 1); }
+#if AUGB_TEAM == 32
+AUGB_D unsigned tmask() { return 0xffffffffu; }
+AUGB_D int tbase() { return 0; }
+#else
+AUGB_D int tbase() { return (threadIdx.x & 31) & ~(AUGB_TEAM - 1); }
+AUGB_D unsigned tmask() { return ((1u << AUGB_TEAM) - 1u) << tbase(); }
+#endif
 #else
 inline int lane_id() { return simt::lane(); }
+inline unsigned tmask() { return 0xffffffffu; }
+inline int tbase() { return 0; }
 #endif
-AUGB_D void wsync() { __syncwarp(); }
+AUGB_D void wsync() { __syncwarp(tmask()); }
 AUGB_D sc_t wmax(sc_t v) {
-    for (int o = 16; o; o >>= 1) { sc_t t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+    for (int o = AUGB_TEAM / 2; o; o >>= 1) { sc_t t = __shfl_xor_sync(tmask(), v, o); v = t > v ? t : v; }
     return v;
 }
 AUGB_D sc_t wsum(sc_t v) {
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int o = AUGB_TEAM / 2; o; o >>= 1) v += __shfl_xor_sync(tmask(), v, o);
     return v;
 }
 AUGB_D int wmaxi(int v) {
-    for (int o = 16; o; o >>= 1) { int t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+    for (int o = AUGB_TEAM / 2; o; o >>= 1) { int t = __shfl_xor_sync(tmask(), v, o); v = t > v ? t : v; }
     return v;
 }
 AUGB_D double wmaxd(double v) {
-    for (int o = 16; o; o >>= 1) { double t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+    for (int o = AUGB_TEAM / 2; o; o >>= 1) { double t = __shfl_xor_sync(tmask(), v, o); v = t > v ? t : v; }
     return v;
 }
 AUGB_D double wsumd(double v) {
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int o = AUGB_TEAM / 2; o; o >>= 1) v += __shfl_xor_sync(tmask(), v, o);
     return v;
 }
-AUGB_D unsigned wballot(bool p) { return __ballot_sync(0xffffffffu, p); }
-AUGB_D int wbcast(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-AUGB_D sc_t wbcast64(sc_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+AUGB_D unsigned wballot(bool p) { return __ballot_sync(tmask(), p) >> tbase(); }
+AUGB_D int wbcast(int v, int src) { return __shfl_sync(tmask(), v, tbase() + src); }
+AUGB_D sc_t wbcast64(sc_t v, int src) { return __shfl_sync(tmask(), v, tbase() + src); }
 AUGB_D int wffs(unsigned b) { return __ffs(b) - 1; }
 AUGB_D int wpopc(unsigned b) { return __popc(b); }
 #else
 #define AUGB_NLANES 1
-inline int lane_id() { return 0; }
-inline void wsync() {}
-inline sc_t wmax(sc_t v) { return v; }
-inline sc_t wsum(sc_t v) { return v; }
-inline int wmaxi(int v) { return v; }
-inline double wmaxd(double v) { return v; }
-inline double wsumd(double v) { return v; }
-inline unsigned wballot(bool p) { return p ? 1u : 0u; }
-inline int wbcast(int v, int) { return v; }
-inline sc_t wbcast64(sc_t v, int) { return v; }
-inline int wffs(unsigned b) { return b ? __builtin_ctz(b) : -1; }
-inline int wpopc(unsigned b) { return __builtin_popcount(b); }
+#define AUGB_GROUP3 0
+AUGB_HD int lane_id() { return 0; }
+AUGB_HD void wsync() {}
+AUGB_HD sc_t wmax(sc_t v) { return v; }
+AUGB_HD sc_t wsum(sc_t v) { return v; }
+AUGB_HD int wmaxi(int v) { return v; }
+AUGB_HD double wmaxd(double v) { return v; }
+AUGB_HD double wsumd(double v) { return v; }
+AUGB_HD unsigned wballot(bool p) { return p ? 1u : 0u; }
+AUGB_HD int wbcast(int v, int) { return v; }
+AUGB_HD sc_t wbcast64(sc_t v, int) { return v; }
+#if defined(__CUDA_ARCH__)
+AUGB_HD int wffs(unsigned b) { return __ffs(b) - 1; }
+AUGB_HD int wpopc(unsigned b) { return __popc(b); }
+#else
+AUGB_HD int wffs(unsigned b) { return b ? __builtin_ctz(b) : -1; }
+AUGB_HD int wpopc(unsigned b) { return __builtin_popcount(b); }
+#endif
 #endif
 
 /* arg-max over lanes of (score, key): the highest score wins, ties go to the highest key.  Returns the
@@ -86,15 +120,15 @@ AUGB_D int wargbest(sc_t score, int key) {
  * winning lane of its own group */
 AUGB_D int gargbest(sc_t score, int key, int gl, unsigned gmask) {
 #if AUGB_SIMT
-    if (gl >= 32) return wargbest(score, key);
+    if (gl >= AUGB_NLANES) return wargbest(score, key);
     const unsigned have = wballot(!isneg(score));
     const unsigned hg = have & gmask;
     /* no reduction unless some group holds more than one candidate */
     if (wballot((hg & (hg - 1u)) != 0) == 0) return hg ? wffs(hg) : -1;
     sc_t m = score;
-    for (int o = gl >> 1; o; o >>= 1) { sc_t t = __shfl_xor_sync(0xffffffffu, m, o); m = t > m ? t : m; }
+    for (int o = gl >> 1; o; o >>= 1) { sc_t t = __shfl_xor_sync(tmask(), m, o); m = t > m ? t : m; }
     int k = score == m ? key : -0x7fffffff;
-    for (int o = gl >> 1; o; o >>= 1) { int t = __shfl_xor_sync(0xffffffffu, k, o); k = t > k ? t : k; }
+    for (int o = gl >> 1; o; o >>= 1) { int t = __shfl_xor_sync(tmask(), k, o); k = t > k ? t : k; }
     const unsigned win = wballot(!isneg(score) && score == m && key == k) & gmask;
     return win ? wffs(win) : -1;
 #else
@@ -116,9 +150,9 @@ struct Lse {
 AUGB_D Lse glse(Lse a, int gl) {
 #if AUGB_SIMT
     double M = a.m;
-    for (int o = gl >> 1; o; o >>= 1) { double t = __shfl_xor_sync(0xffffffffu, M, o); M = t > M ? t : M; }
+    for (int o = gl >> 1; o; o >>= 1) { double t = __shfl_xor_sync(tmask(), M, o); M = t > M ? t : M; }
     double s = a.s > 0 ? a.s * exp(a.m - M) : 0.0;
-    for (int o = gl >> 1; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    for (int o = gl >> 1; o; o >>= 1) s += __shfl_xor_sync(tmask(), s, o);
     Lse r; r.m = M; r.s = s;
     return r;
 #else
@@ -127,7 +161,7 @@ AUGB_D Lse glse(Lse a, int gl) {
 }
 AUGB_D double wbcastd(double v, int src) {
 #if AUGB_SIMT
-    return __shfl_sync(0xffffffffu, v, src);
+    return __shfl_sync(tmask(), v, tbase() + src);
 #else
     return v;
 #endif
@@ -138,5 +172,41 @@ AUGB_D Lse wlse(Lse a) {
     Lse r; r.m = M; r.s = wsumd(a.s > 0 ? a.s * exp(a.m - M) : 0.0);
     return r;
 }
+
+
+#if defined(AUGB_TASKS)
+/* ---- engine collectives (full warp) ---- */
+#if AUGB_EL == 32
+#if defined(__CUDA_ARCH__)
+AUGB_D int elane_id() { return threadIdx.x & 31; }
+AUGB_D unsigned ematch(int v) { return __match_any_sync(0xffffffffu, v); }
+/* n-th (0-based) set bit of a 64-bit mask, -1 if there are fewer */
+AUGB_D int efns64(unsigned long long b, int n) {
+    const unsigned lo = (unsigned)b, hi = (unsigned)(b >> 32); const int nlo = __popc(lo);
+    if (n < nlo) return (int)__fns(lo, 0, n + 1);
+    if (n - nlo < __popc(hi)) return 32 + (int)__fns(hi, 0, n - nlo + 1);
+    return -1;
+}
+#else
+inline int elane_id() { return simt::lane(); }
+inline unsigned ematch(int v) { const uint64_t* b = simt::rendezvous(simt::bits(v), 5); unsigned r = 0; for (int i = 0; i < 32; i++) if (simt::unbits<int>(b[i]) == v) r |= 1u << i; return r; }
+inline int efns64(unsigned long long b, int n) { for (int i = 0; i < 64; i++) if (b >> i & 1) { if (n == 0) return i; n--; } return -1; }
+#endif
+AUGB_D void esync() { __syncwarp(0xffffffffu); }
+AUGB_D unsigned eballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+AUGB_D int ebcast(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+AUGB_D sc_t emax64(sc_t v) { for (int o = 16; o; o >>= 1) { sc_t t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; } return v; }
+AUGB_D int emini(int v) { for (int o = 16; o; o >>= 1) { int t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; } return v; }
+#else
+AUGB_HD int elane_id() { return 0; }
+AUGB_HD unsigned ematch(int) { return 1u; }
+AUGB_HD int efns64(unsigned long long b, int n) { for (int i = 0; i < 64; i++) if (b >> i & 1) { if (n == 0) return i; n--; } return -1; }
+AUGB_HD void esync() {}
+AUGB_HD unsigned eballot(bool p) { return p ? 1u : 0u; }
+AUGB_HD int ebcast(int v, int) { return v; }
+AUGB_HD sc_t emax64(sc_t v) { return v; }
+AUGB_HD int emini(int v) { return v; }
+#endif
+#endif
 
 }  // namespace augb
