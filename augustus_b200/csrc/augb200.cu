@@ -14,7 +14,6 @@
 #include "../../include/augb200.h"
 #include "ghmm_kernels.cuh"
 #include "ghmm_model.h"
-#include "ghmm_tasks.h"
 
 using namespace augb;
 
@@ -183,8 +182,6 @@ static int run_kernels(augb200_model* M, int count) {
     static int bps = 0;
     if (!bps) { const char* e = getenv("AUGB200_SWEEP_BLOCKS_PER_SM"); bps = e ? atoi(e) : 4; if (bps < 1) bps = 1; }
     const bool utr = M->hm.dm.utr != 0;
-    static int sweep_mode = -1;
-    if (sweep_mode < 0) { const char* e = getenv("AUGB200_SWEEP"); sweep_mode = e && !strcmp(e, "tasks") ? 1 : 0; }
     const int nrng = (int)std::min<size_t>(M->rng_n - std::min<size_t>(M->rng_n, M->rand_pos), 0x7fffffff);
     const uint32_t* d_rng = M->d_rng.p ? M->d_rng.p + M->rand_pos : nullptr;
     if (M->waves.empty() || M->waves.back().first + M->waves.back().second != count) { M->waves.clear(); M->waves.push_back({0, count}); }
@@ -205,12 +202,6 @@ static int run_kernels(augb200_model* M, int count) {
         if (utr) gsweep = std::min(gsweep, sms * std::min(bps, 3));
         if (M->nsamp > 0 && utr) k_sweep_sample_utr<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(wins, n, M->d_counters.p, d_rng, nrng);
         else if (M->nsamp > 0) k_sweep_sample<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(wins, n, M->d_counters.p, d_rng, nrng);
-        else if (sweep_mode == 1) {
-            /* task engine (ghmm_tasks.cu) */
-            CK(tasks_upload_model(&M->dm_dev, M->stream));
-            const int gt = std::min((n + TASK_WARPS - 1) / TASK_WARPS, sms * bps);
-            CK(tasks_launch_sweep(utr ? 1 : 0, wins, n, M->d_counters.p, gt, M->stream));
-        }
         else if (utr) k_sweep_utr<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(wins, n, M->d_counters.p);
         else k_sweep<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(wins, n, M->d_counters.p);
         CK(cudaEventRecord(wv ? M->wave_ev[wv - 1].second : M->ev1, M->stream));

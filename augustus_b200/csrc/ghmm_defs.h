@@ -131,7 +131,6 @@ struct DevModel {
     /* role -> state index (-1 if absent) */
     int8_t r_longdss[2][3], r_lessd[2][3], r_equald[2][3], r_longass[2][3];      /* [0]=fwd [1]=rev */
     int8_t xslot[16];          /* exon states in the slot order used by Sweep::process_column */
-    uint64_t task_valid;       /* task engine: the (state, column) tasks this model has (Sweep::column_tasks) */
     int8_t r_single, r_initial[3], r_internal[3], r_terminal, r_rsingle, r_rinitial, r_rinternal[3], r_rterminal[3];
     /* tables (device pointers on the GPU, host pointers in the test emulator) */
     const sc_t *init, *term, *trans;                /* trans[(c*S + a)*S + s] */

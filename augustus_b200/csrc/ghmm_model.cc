@@ -330,18 +330,6 @@ int HostModel::build(const void* blob, size_t nbytes) {
         for (int f = 0; f < 3; f++) m.xslot[q++] = m.r_rinternal[f];
         for (int f = 0; f < 3; f++) m.xslot[q++] = m.r_rterminal[f];
     }
-    {   /* tasks of a column that exist in this model (bit layout: Sweep::column_tasks) */
-        uint64_t tv = 0;
-        for (int d = 0; d < 2; d++) for (int f = 0; f < 3; f++) {
-            if (m.r_lessd[d][f] >= 0) tv |= 1ull << (d * 3 + f);
-            if (m.r_equald[d][f] >= 0) tv |= 1ull << (6 + d * 3 + f);
-            if (m.r_longdss[d][f] >= 0) tv |= 1ull << (12 + d * 3 + f);
-            if (m.r_longass[d][f] >= 0) tv |= 1ull << (18 + d * 3 + f);
-        }
-        for (int q = 0; q < 16; q++) if (m.xslot[q] >= 0) tv |= 1ull << (24 + q);
-        if (m.utr) for (int q = 0; q < 18; q++) if (m.uslot[q] >= 0 && (q < 16 || m.nc)) tv |= 1ull << (40 + q);
-        m.task_valid = tv;
-    }
     if (m.chain_state[0] < 0) { err = "model has no intergenic state"; return AUGB200_ERR_UNSUPPORTED; }
     /* topology the kernels rely on (config/model/trans_shadow_*.pbl); anything else is rejected, not approximated */
     auto kind_of = [&](int a) { return m.st[a].kind; };

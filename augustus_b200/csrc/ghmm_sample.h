@@ -72,6 +72,56 @@ struct SamplerT {
         return res;
     }
 
+    /* OptionsList::sample on a short list held by one lane (the options of a self-loop state at a column that received entries):
+     * the same arithmetic as pick() above — cumprob in insertion order, draw against the stable descending order */
+    AUGB_D int pick_small(const double* lp, const int* ord, int n, uint32_t r, double* add) const {
+        double mx = -1e308;
+        AUGB_ROLLED
+        for (int i = 0; i < n; i++) mx = lp[i] > mx ? lp[i] : mx;
+        double cum = 0;
+        AUGB_ROLLED
+        for (int i = 0; i < n; i++) cum += exp(lp[i] - mx);
+        const double z = ((double)r / 2147483647.0) * cum * 0.99999;
+        int res = -1, first = -1; double cs = 0;
+        AUGB_ROLLED
+        for (int rk = 0; rk < n && res < 0; rk++) {
+            /* the option of rank rk */
+            int sel = -1;
+            AUGB_ROLLED
+            for (int i = 0; i < n && sel < 0; i++) {
+                int before = 0;
+                AUGB_ROLLED
+                for (int k = 0; k < n; k++) before += (lp[k] > lp[i] || (lp[k] == lp[i] && (ord[k] < ord[i] || (ord[k] == ord[i] && k < i)))) ? 1 : 0;
+                if (before == rk) sel = i;
+            }
+            if (rk == 0) first = sel;
+            cs += exp(lp[sel] - mx);
+            if (z < cs) res = sel;
+        }
+        if (res < 0) res = first;
+        *add = lp[res] - mx - log(cum);
+        return res;
+    }
+    /* one step of a self-loop state at column c (> 0), a column of its chain that received entries: list the ancestors at c - 1 in
+     * index order (igenicmodel.cc:247-261, intronmodel.cc:786-820), draw with the rand() value r.  Returns the chosen predecessor
+     * state, -1 if there is no option.  Everything is local to the calling lane: 32 lanes take 32 consecutive stops of a run. */
+    AUGB_D int chain_stop(int state, int c, uint32_t r, double* add) const {
+        const SW& S = *sw; const DevModel* m = S.m;
+        const StateDesc& sd = m->st[state];
+        const sc_t* T = m->trans + (size_t)S.w.gc[c] * m->S * m->S;
+        double lpv[MAXANC]; int ordv[MAXANC], prd[MAXANC]; int n = 0;
+        AUGB_ROLLED
+        for (int i = 0; i < sd.nanc; i++) {
+            const int a = sd.anc[i]; const sc_t t = T[a * m->S + state];
+            if (isneg(t)) continue;
+            const double f = S.lookupF(a, c - 1);
+            if (f > -1e300) { lpv[n] = f + SW::sc2d(t); ordv[n] = i; prd[n] = a; n++; }
+        }
+        if (n == 0) return -1;
+        const int k = pick_small(lpv, ordv, n, r, add);
+        return prd[k];
+    }
+
     /* all paths of one window */
     AUGB_D void run(int nsamples, SampleOut out) {
         SW& S = *sw; const DevModel* m = S.m; const int L = S.L;
@@ -115,20 +165,39 @@ struct SamplerT {
                         if (cp[hi].col <= base) lo = hi;
                         AUGB_ROLLED
                         while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (cp[mid].col <= base) lo = mid; else hi = mid - 1; }
-                        const int c = cp[lo].col;
-                        if (c < base) { cursor += base - c; base = c; if (cursor > nrng) { bad = 1; break; } }   /* self-only steps, one draw each */
-                        if (base == 0) break;
-                        /* column `base` received entries: choose among the ancestors at base-1, index order (igenicmodel.cc:247-261) */
+                        /* A run of the chain: between change points every step is the self transition (one draw each, nothing to
+                         * choose); at a change point column c the walk draws among the ancestors at c - 1.  The draw of the stop at
+                         * column c is number cursor + (base - c) whatever happened before it, so the lanes take consecutive change
+                         * points, each evaluates its stop on its own, and the first lane that does not stay in the state ends the run. */
+                        pred = state; eop = base;
+                        bool left = false;
                         AUGB_ROLLED
-                        for (int i = 0; i < sd.nanc; i++) {
-                            int a = sd.anc[i]; sc_t t = S.TR(a, state);
-                            double f = isneg(t) ? -1e308 : S.lookupF(a, base - 1);
-                            S.push_opt(lane == 0 && f > -1e300, f + SW::sc2d(t), i, a, base - 1);
+                        while (!left) {
+                            const int i = lo - lane; const bool valid = i >= 0;
+                            const int c = valid ? cp[i].col : -1;
+                            int mypred = state; double myadd = 0; bool fail = false;
+                            if (valid && c > 0) {
+                                const long d = (long)cursor + (base - c);
+                                if (d >= nrng) fail = true;
+                                else { mypred = chain_stop(state, c, rng[d], &myadd); if (mypred < 0) fail = true; }
+                            }
+                            const bool stopper = !valid || c == 0 || fail || mypred != state;
+                            const unsigned sb = wballot(stopper);
+                            const int f = sb ? wffs(sb) : AUGB_NLANES;
+                            /* the log-probabilities of the steps add up in walk order */
+                            AUGB_ROLLED
+                            for (int l = 0; l < AUGB_NLANES && l <= f; l++) { const double a = wbcastd(myadd, l); lp += a; }
+                            if (f > 0) { const int cp_ = wbcast(c, f - 1); cursor += (base - cp_) + 1; base = cp_ - 1; }       /* lanes < f stayed */
+                            if (f == AUGB_NLANES) { lo -= AUGB_NLANES; if (base == 0) left = true; continue; }
+                            const int cf = wbcast(c, f); const int vf = wbcast(valid ? 1 : 0, f), ff = wbcast(fail ? 1 : 0, f);
+                            left = true;
+                            if (!vf || ff) { bad = 1; }
+                            else if (cf == 0) { cursor += base; base = 0; }                        /* self steps down to column 1 */
+                            else { cursor += (base - cf) + 1; base = cf; pred = wbcast(mypred, f); eop = cf - 1; }
                         }
-                        k = pick(&lp);
-                        if (k < 0) { bad = 1; if (k == -2) status = 8; break; }
-                        pred = sc.opt[k].pred; eop = base - 1;
-                        if (pred == state) { base = eop; continue; }          /* the run goes on */
+                        if (bad) break;
+                        if (cursor > nrng) { bad = 1; break; }
+                        if (pred == state) continue;          /* the run reached column 0 (base == 0 ends the walk) */
                         if (used >= out.cap) { status = 8; break; }
                         if (lane == 0) {
                             out.begin[used] = base; out.end[used] = run_end; out.type[used] = (uint8_t)sd.type;

@@ -29,7 +29,11 @@
 
 namespace augb {
 
+/* a cell of the current column that has not been published yet (Sweep::emit / commit_cells) */
+struct PendCell { int16_t s, pred; int32_t base; sc_t V; };
+constexpr int CB_CAP = 32;
 struct WarpState {
+    PendCell cb[CB_CAP]; double cbF[CB_CAP];
     int n_ev;
     int filled;                 /* evstart[] is valid up to this column */
     int cl_n[NCL];
@@ -57,10 +61,7 @@ struct SweepT {
     /* sampling step (getSampledPath): when opt != nullptr the routines below list every option of state `only` instead of
      * reducing and recording a cell */
     SampleOpt* opt = nullptr; int* nopt = nullptr; int opt_cap = 0; int only = -1;
-#ifdef AUGB_TASKS
-    /* task engine: in capture mode a routine hands its cell to the engine (one cell per task) instead of recording it */
-    bool cap = false, r_have = false; int r_s = 0, r_pred = 0, r_base = 0; sc_t r_V = 0; double r_F = 0;
-#endif
+    int ncb = 0;                /* cells of the current column waiting in WarpState::cb (same value in every lane) */
     AUGB_D void push_opt(bool have, double lp, int ord, int pred, int eop) {
         unsigned b = wballot(have);
         int base = *nopt;
@@ -176,58 +177,115 @@ struct SweepT {
         }
         return -1;
     }
-    /* record a non-zero cell; route it to the structures later columns look back to.  All lanes hold the same
-     * arguments; lane 0 writes, one warp sync publishes. */
+    /* A new non-zero cell.  All lanes hold the same arguments.  The cell waits in the column buffer (WarpState::cb) until
+     * commit_cells publishes the cells of the column together, one lane per cell: nothing in a column reads a non-chain cell of the
+     * same column (candidate loops take entries with col < j only; a predecessor end AT the current column is read from a chain). */
     AUGB_EMIT void emit(int j, int s, sc_t V, int pred, int predbase, double F = 0) {
-#ifdef AUGB_TASKS
-        if (cap) { r_have = true; r_s = s; r_V = V; r_pred = pred; r_base = predbase; r_F = F; return; }
-#endif
         if (lane == 0) {
-            int n = ws->n_ev;
-            if (n >= w.ev_cap) ws->status = 8;
-            else {
-                Event e; e.state = (int16_t)s; e.pred = (int16_t)pred; e.predbase = predbase; e.V = V;
-                w.ev[n] = e; ws->n_ev = n + 1;
-                if (FWD) w.evF[n] = F;
-                sc_t G1, G2; int l2; const int l1 = cell_lists(j, s, &G1, &l2, &G2);
-                if (l1 >= 0) cl_append(l1, j, s, V, F, G1);
-                if (l2 >= 0) cl_append(l2, j, s, V, F, G2);
-                feed_chain(j, s, V, F);
-            }
+            PendCell c; c.s = (int16_t)s; c.pred = (int16_t)pred; c.base = predbase; c.V = V;
+            ws->cb[ncb] = c;
+            if (FWD) ws->cbF[ncb] = F;
         }
-        wsync();
+        if (++ncb == CB_CAP) commit_cells(j);
     }
-    /* end of column j: apply the pending chain entries for column j+1 (ancestors in index order, strict >) */
+    /* publish the buffered cells of column j in the order they were found: events by rank, candidate lists with one rank per list,
+     * chain entries by a per-chain arg-max (ancestors in index order on ties, like feed_chain) */
+    AUGB_D void commit_cells(int j) {
+        if (ncb == 0) return;
+        wsync();                                        /* the buffer is visible */
+        AUGB_ROLLED
+        for (int i0 = 0; i0 < ncb; i0 += AUGB_NLANES) {
+            const int i = i0 + lane; const bool have = i < ncb;
+            const unsigned below = (1u << lane) - 1u;
+            const int nr = ncb - i0 < AUGB_NLANES ? ncb - i0 : AUGB_NLANES;
+            const int base = ws->n_ev;
+            const bool room = base + nr <= w.ev_cap, mine = have && room;
+            int cs = 0; sc_t cV = 0; double cF = 0;
+            int l1 = -1, l2 = -1, fch = -1; sc_t G1 = 0, G2 = 0, fdelta = 0;
+            if (mine) {
+                const PendCell c = ws->cb[i]; cs = c.s; cV = c.V;
+                Event e; e.state = c.s; e.pred = c.pred; e.predbase = c.base; e.V = c.V;
+                w.ev[base + lane] = e;
+                if (FWD) { cF = ws->cbF[i]; w.evF[base + lane] = cF; }
+                l1 = cell_lists(j, cs, &G1, &l2, &G2);
+                fch = feed_term(j, cs, &fdelta);
+            }
+            wsync();                                    /* every lane has read n_ev */
+            if (lane == 0) { if (room) ws->n_ev = base + nr; else ws->status = 8; }
+            AUGB_ROLLED
+            for (int pass = 0; pass < (UTR ? 2 : 1); pass++) {
+                const int li = pass ? l2 : l1; const sc_t G = pass ? G2 : G1;
+                if (wballot(li >= 0) == 0) continue;
+                const unsigned same = wmatch(li >= 0 ? li : -1 - lane);      /* the cells that go to the same list take consecutive entries */
+                const bool ap = li >= 0;
+                int n0 = 0, r = 0, cnt = 0; bool fits = false;
+                if (ap) {
+                    n0 = ws->cl_n[li]; r = wpopc(same & below); cnt = wpopc(same); fits = n0 + cnt <= w.cl_cap;
+                    if (!fits) ws->status = 8;
+                    else {
+                        Cand c; c.col = j; c.state = cs; c.V = cV + G; w.cl(li)[n0 + r] = c;
+                        if (FWD) { w.clF(li)[n0 + r] = cF; if (UTR && li >= NCL_BASE) w.clG(li)[n0 + r] = G; }
+                    }
+                }
+                wsync();                                /* every lane of a list has read its length */
+                if (ap && r == 0 && fits) ws->cl_n[li] = n0 + cnt;
+                wsync();
+            }
+            unsigned fm = wballot(fch >= 0);
+            if (FWD) {
+                /* the forward sums are added in the order the cells were found */
+                AUGB_ROLLED
+                while (fm) {
+                    const int b = wffs(fm); fm &= fm - 1;
+                    if (lane == b) { feed_merge(fch, cs, cV + fdelta); ws->any_pend |= 1 << fch; ws->pend_f[fch].add(cF + sc2d(fdelta)); }
+                    wsync();
+                }
+            } else {
+                AUGB_ROLLED
+                while (fm) {
+                    const int b = wffs(fm); const int ch0 = wbcast(fch, b);
+                    const bool in = fch == ch0;
+                    const sc_t v = in ? cV + fdelta : SC_NEG;
+                    const sc_t mx = wmax(v);
+                    const int ps = wmini(in && v == mx ? cs : 0x7fffffff);
+                    if (lane == b) { feed_merge(ch0, ps, mx); ws->any_pend |= 1 << ch0; }
+                    fm &= ~wballot(in);
+                    wsync();
+                }
+            }
+            wsync();
+        }
+        ncb = 0;
+    }
+    /* end of column j: apply the pending chain entries for column j+1 (ancestors in index order, strict >), one lane per chain */
     AUGB_D void apply_pending(int j) {
         const unsigned pend = (unsigned)ws->any_pend;
         if (!pend) return;
         wsync();                              /* every lane has read the flags before lane 0 clears them */
-        if (lane == 0) {
-            unsigned pm = pend;
-            AUGB_ROLLED
-            while (pm) {
-                const int ch = wffs(pm); pm &= pm - 1;
-                sc_t pv = ws->pend_val[ch];
-                if (isneg(pv)) continue;
-                int pp = ws->pend_pred[ch], self = m->chain_state[ch];
-                sc_t cur = ws->tilde[ch];
-                bool take = pv > cur || (pv == cur && pp < self);
-                int n = ws->cp_n[ch];
-                if (take && n >= w.cp_cap) { ws->status = 8; take = false; }
-                if (take) { ChainCP c; c.col = j + 1; c.pred = pp; c.tilde = pv; w.cp(ch)[n] = c; ws->cp_n[ch] = n + 1; ws->tilde[ch] = pv; }
-                ws->pend_val[ch] = SC_NEG; ws->pend_pred[ch] = 0x7fffffff;
-                if (FWD && !ws->pend_f[ch].empty()) {
-                    /* forward[j+1][chain] = forward[j][chain]*self + sum of the entries: one more change point */
-                    Lse t = ws->pend_f[ch];
-                    if (ws->fcp_n[ch] > 0) t.add(ws->ftilde[ch]);
-                    int nf = ws->fcp_n[ch];
-                    if (nf >= w.fcp_cap) ws->status = 8;
-                    else { FChainCP c; c.col = j + 1; c.pad = 0; c.ft = t.value(); w.fcp(ch)[nf] = c; ws->fcp_n[ch] = nf + 1; ws->ftilde[ch] = c.ft; }
-                    ws->pend_f[ch].clear();
-                }
+        AUGB_ROLLED
+        for (int ch = lane; ch < NCHAIN; ch += AUGB_NLANES) {
+            if (!(pend >> ch & 1)) continue;
+            sc_t pv = ws->pend_val[ch];
+            if (isneg(pv)) continue;
+            int pp = ws->pend_pred[ch], self = m->chain_state[ch];
+            sc_t cur = ws->tilde[ch];
+            bool take = pv > cur || (pv == cur && pp < self);
+            int n = ws->cp_n[ch];
+            if (take && n >= w.cp_cap) { ws->status = 8; take = false; }
+            if (take) { ChainCP c; c.col = j + 1; c.pred = pp; c.tilde = pv; w.cp(ch)[n] = c; ws->cp_n[ch] = n + 1; ws->tilde[ch] = pv; }
+            ws->pend_val[ch] = SC_NEG; ws->pend_pred[ch] = 0x7fffffff;
+            if (FWD && !ws->pend_f[ch].empty()) {
+                /* forward[j+1][chain] = forward[j][chain]*self + sum of the entries: one more change point */
+                Lse t = ws->pend_f[ch];
+                if (ws->fcp_n[ch] > 0) t.add(ws->ftilde[ch]);
+                int nf = ws->fcp_n[ch];
+                if (nf >= w.fcp_cap) ws->status = 8;
+                else { FChainCP c; c.col = j + 1; c.pad = 0; c.ft = t.value(); w.fcp(ch)[nf] = c; ws->fcp_n[ch] = nf + 1; ws->ftilde[ch] = c.ft; }
+                ws->pend_f[ch].clear();
             }
-            ws->any_pend = 0;
         }
+        wsync();
+        if (lane == 0) ws->any_pend = 0;
         wsync();
     }
 
@@ -704,14 +762,9 @@ struct SweepT {
             return;
         }
         Cand c = w.cl(list)[cur]; double cf = FWD ? w.clF(list)[cur] : 0.0;
-#ifdef AUGB_TASKS
-        if (!cap)           /* (the engine advances the cursors of a column's equalD tasks itself) */
-#endif
-        {
         wsync();
         if (lane == 0) ws->eq_cur[dir * 3 + f] = cur + 1;
         wsync();
-        }
         if (s < 0) return;
         int eop = j - m->dStateLen;
         const sc_t* P = parr(cls, PA_PI);                 /* forward k-mers also for requalD (intronmodel.cc:1046-1108) */
@@ -1085,6 +1138,7 @@ struct SweepT {
                 if (xs >= 0) utr_eval(xs, j);
             }
         }
+        commit_cells(j);
         apply_pending(j);
     }
 
@@ -1092,6 +1146,7 @@ struct SweepT {
     AUGB_D void attach() { L = w.L; sq.c = w.code; sq.L = L; sq.kf = w.kf; sq.kr = w.kr; sq.k1 = m->k + 1; }      /* per-thread view of the window */
     /* per-window state + column 0; false: the window is not decodable with this layout (status written) */
     AUGB_D bool init_window() {
+        ncb = 0;
         if (lane == 0) {
             ws->n_ev = 0; ws->filled = -1; ws->status = 0; ws->any_pend = 0; ws->snip_cnt[0] = ws->snip_cnt[1] = 0;
             AUGB_ROLLED
@@ -1196,235 +1251,6 @@ struct SweepT {
         wsync();
     }
 
-#ifdef AUGB_TASKS
-    /* ------------------------------------------------------------ task engine
-     *
-     * One warp per window, but the lanes do not cooperate inside a routine: every (state, column) evaluation of the current column
-     * — lessD_f, equalD_f, longdss_f, longass_f of either strand, the 16 exon slots, the UTR exon slots — is a TASK, the tasks of a
-     * column are dealt to the engine lanes (task order = the order process_column runs them in) and every lane runs its task with
-     * the one-lane form of the routine in capture mode.  The cells are then published together: events by prefix rank (so the log
-     * is the one the sequential order writes), candidate lists with one rank per list, chain entries by a per-chain arg-max.
-     * Tasks of a column only read finished columns (and chains, whose value at j was fixed by apply_pending(j - 1)). */
-    AUGB_D unsigned long long column_tasks(unsigned mb, unsigned eqbits) const {
-        unsigned long long t = 0;
-        if (mb & MB_LESSD) t |= 7ull;
-        if (mb & MB_RLESSD) t |= 7ull << 3;
-        t |= (unsigned long long)eqbits << 6;
-        if (mb & MB_LONGDSS) t |= 7ull << 12;
-        if (mb & MB_RLONGDSS) t |= 7ull << 15;
-        if (mb & MB_LONGASS) t |= 7ull << 18;
-        if (mb & MB_RLONGASS) t |= 7ull << 21;
-        const unsigned slots = ((mb & MB_XSTOP) ? 0x3u : 0u) | ((mb & MB_XDSS) ? 0xfcu : 0u) | ((mb & MB_XRSTART) ? 0x300u : 0u) | ((mb & MB_XRASS) ? 0xfc00u : 0u);
-        t |= (unsigned long long)slots << 24;
-        if (UTR) {
-            unsigned us = ((mb & MB_U5ATG) ? 0x0009u : 0u) | ((mb & MB_LONGDSS) ? 0x0066u : 0u) | ((mb & MB_UTTS) ? 0x0090u : 0u)
-                        | ((mb & MB_URTSS) ? 0x0300u : 0u) | ((mb & MB_RLONGASS) ? 0xcc00u : 0u) | ((mb & MB_URSTOP) ? 0x3000u : 0u);
-            us |= ((mb & MB_LONGDSS) ? 0x10000u : 0u) | ((mb & MB_RLONGASS) ? 0x20000u : 0u);      /* ncinternal, rncinternal (masked by task_valid) */
-            t |= (unsigned long long)us << 40;
-        }
-        return t & m->task_valid;
-    }
-    AUGB_D void run_task(int b, int j) {
-        cap = true; r_have = false;
-        if (b < 6) { const int dir = b >= 3, f = b - 3 * dir; only = m->r_lessd[dir][f]; lessd_eval(dir, j); only = -1; }
-        else if (b < 12) { const int q = b - 6; equald_eval(q >= 3, q >= 3 ? q - 3 : q, j); }
-        else if (b < 24) {
-            const int t = (b - 12) / 3, f = (b - 12) - 3 * t, dir = t & 1;
-            only = t < 2 ? m->r_longdss[dir][f] : m->r_longass[dir][f];
-            fixed_eval(t < 2 ? K_LONGDSS : K_LONGASS, dir, j); only = -1;
-        }
-        else if (b < 40) exon_eval(m->xslot[b - 24], j);
-        else if (UTR) utr_eval(m->uslot[b - 40], j);
-        cap = false;
-    }
-    /* publish the cells the lanes hold (r_*), in lane order */
-    AUGB_D void commit_round(int j, int el) {
-        const unsigned have = eballot(r_have);
-        if (!have) return;
-        const unsigned below = (1u << el) - 1u;
-        const int n = wpopc(have), base = ws->n_ev, rank = wpopc(have & below);
-        const bool room = base + n <= w.ev_cap;
-        const bool mine = r_have && room;
-        int l1 = -1, l2 = -1, fch = -1; sc_t G1 = 0, G2 = 0, fdelta = 0;
-        if (mine) {
-            Event e; e.state = (int16_t)r_s; e.pred = (int16_t)r_pred; e.predbase = r_base; e.V = r_V;
-            w.ev[base + rank] = e;
-            if (FWD) w.evF[base + rank] = r_F;
-            l1 = cell_lists(j, r_s, &G1, &l2, &G2);
-            fch = feed_term(j, r_s, &fdelta);
-        }
-        esync();                                        /* everybody has read n_ev */
-        if (el == 0) { if (room) ws->n_ev = base + n; else ws->status = 8; }
-        /* candidate lists: the cells that go to the same list take consecutive entries in lane order */
-        AUGB_ROLLED
-        for (int pass = 0; pass < (UTR ? 2 : 1); pass++) {
-            const int li = pass ? l2 : l1; const sc_t G = pass ? G2 : G1;
-            if (eballot(li >= 0) == 0) continue;
-            const unsigned same = ematch(li >= 0 ? li : -1 - el);
-            const bool ap = li >= 0;
-            int n0 = 0, r = 0, cnt = 0; bool fits = false;
-            if (ap) {
-                n0 = ws->cl_n[li]; r = wpopc(same & below); cnt = wpopc(same); fits = n0 + cnt <= w.cl_cap;
-                if (!fits) ws->status = 8;
-                else {
-                    Cand c; c.col = j; c.state = r_s; c.V = r_V + G; w.cl(li)[n0 + r] = c;
-                    if (FWD) { w.clF(li)[n0 + r] = r_F; if (UTR && li >= NCL_BASE) w.clG(li)[n0 + r] = G; }
-                }
-            }
-            esync();                                    /* every lane of a list has read its length */
-            if (ap && r == 0 && fits) ws->cl_n[li] = n0 + cnt;
-            esync();
-        }
-        /* chain entries */
-        unsigned fm = eballot(fch >= 0);
-        if (FWD) {
-            /* the forward sums are added in lane (= task) order, like the sequential sweep */
-            AUGB_ROLLED
-            while (fm) {
-                const int b = wffs(fm); fm &= fm - 1;
-                if (el == b) { feed_merge(fch, r_s, r_V + fdelta); ws->any_pend |= 1 << fch; ws->pend_f[fch].add(r_F + sc2d(fdelta)); }
-                esync();
-            }
-        } else {
-            AUGB_ROLLED
-            while (fm) {
-                const int b = wffs(fm); const int ch0 = ebcast(fch, b);
-                const bool in = fch == ch0;
-                const sc_t v = in ? r_V + fdelta : SC_NEG;
-                const sc_t mx = emax64(v);
-                const int ps = emini(in && v == mx ? r_s : 0x7fffffff);
-                if (el == b) { feed_merge(ch0, ps, mx); ws->any_pend |= 1 << ch0; }
-                fm &= ~eballot(in);
-                esync();
-            }
-        }
-        esync();
-    }
-    /* apply_pending with one lane per chain */
-    AUGB_D void apply_pending_e(int j, int el) {
-        const unsigned pend = (unsigned)ws->any_pend;
-        if (!pend) return;
-        esync();
-        AUGB_ROLLED
-        for (int ch = el; ch < NCHAIN; ch += AUGB_EL) {
-            if (!(pend >> ch & 1)) continue;
-            sc_t pv = ws->pend_val[ch];
-            if (isneg(pv)) continue;
-            int pp = ws->pend_pred[ch], self = m->chain_state[ch];
-            sc_t cur = ws->tilde[ch];
-            bool take = pv > cur || (pv == cur && pp < self);
-            int n = ws->cp_n[ch];
-            if (take && n >= w.cp_cap) { ws->status = 8; take = false; }
-            if (take) { ChainCP c; c.col = j + 1; c.pred = pp; c.tilde = pv; w.cp(ch)[n] = c; ws->cp_n[ch] = n + 1; ws->tilde[ch] = pv; }
-            ws->pend_val[ch] = SC_NEG; ws->pend_pred[ch] = 0x7fffffff;
-            if (FWD && !ws->pend_f[ch].empty()) {
-                Lse t = ws->pend_f[ch];
-                if (ws->fcp_n[ch] > 0) t.add(ws->ftilde[ch]);
-                int nf = ws->fcp_n[ch];
-                if (nf >= w.fcp_cap) ws->status = 8;
-                else { FChainCP c; c.col = j + 1; c.pad = 0; c.ft = t.value(); w.fcp(ch)[nf] = c; ws->fcp_n[ch] = nf + 1; ws->ftilde[ch] = c.ft; }
-                ws->pend_f[ch].clear();
-            }
-        }
-        esync();
-        if (el == 0) ws->any_pend = 0;
-        esync();
-    }
-    AUGB_D void fill_evstart_e(int upto, int el) {
-        const int f = ws->filled, n = ws->n_ev;
-        AUGB_ROLLED
-        for (int i = f + 1 + el; i <= upto; i += AUGB_EL) w.evstart[i] = n;
-        esync();
-        if (el == 0) ws->filled = upto;
-        esync();
-    }
-    AUGB_D void process_column_tasks(int j, unsigned mb, unsigned eqbits, int el) {
-        fill_evstart_e(j, el);
-        set_class(w.gc[j]);
-        unsigned long long tasks = column_tasks(mb, eqbits);
-        if ((mb & MB_SLOW) || (UTR && (mb & MB_UTR_BEGINS))) {
-            /* sequential parts, engine lane 0 in the one-lane form: begin-signal sites of UTR exons; the lessD states of a column inside
-             * an emulated SnippetProbs region (the memo depends on the order of the calls) — first in the task order anyway */
-            if (el == 0) {
-                if (mb & MB_SLOW) snip_column_begin(j);
-                if (UTR && (mb & MB_UTR_BEGINS)) utr_begins(j, mb);
-                if (mb & MB_SLOW) { if (tasks & 7ull) lessd_eval(0, j); if (tasks & (7ull << 3)) lessd_eval(1, j); }
-            }
-            if (mb & MB_SLOW) tasks &= ~0x3full;
-            esync();
-        }
-        AUGB_ROLLED
-        while (tasks) {
-            const int b = efns64(tasks, el);
-            if (b >= 0) run_task(b, j); else r_have = false;
-            commit_round(j, el);
-            /* drop the AUGB_EL lowest tasks */
-            const int last = efns64(tasks, AUGB_EL - 1);
-            tasks = last < 0 || last >= 63 ? 0ull : tasks & ~((2ull << last) - 1ull);
-        }
-        if (eqbits) {
-            if (el == 0) { unsigned qm = eqbits; AUGB_ROLLED while (qm) { const int q = wffs(qm); qm &= qm - 1; ws->eq_cur[q]++; } }
-            esync();
-        }
-        apply_pending_e(j, el);
-    }
-    AUGB_D void run_tasks() {
-        attach(); lane = 0;
-        const int el = elane_id();
-        int ok = 1;
-        if (el == 0) ok = init_window() ? 1 : 0;
-        esync();
-        ok = ebcast(ok, 0);
-        if (!ok) return;
-        AUGB_ROLLED
-        for (int j0 = 1; j0 < L; j0 += 32) {
-            unsigned act = 0;
-#if AUGB_EL == 32
-            unsigned mymask; { const int j = j0 + el; mymask = j < L ? w.mask[j] : 0u; act = eballot(mymask != 0); }
-#else
-            unsigned maskbuf[32];
-            AUGB_ROLLED
-            for (int t = 0; t < 32; t++) { int j = j0 + t; maskbuf[t] = j < L ? w.mask[j] : 0u; if (maskbuf[t]) act |= 1u << t; }
-#endif
-            unsigned eqcol[6]; unsigned eqany = 0;
-            AUGB_ROLLED
-            for (int q = 0; q < 6; q++) {
-                eqcol[q] = 0;
-                if (m->r_equald[q / 3][q % 3] < 0) continue;
-                int list = (q / 3 ? CL_RA : CL_LD) + q % 3; int cur = ws->eq_cur[q], n = ws->cl_n[list];
-                AUGB_ROLLED
-                for (int i = cur; i < n; i++) {
-                    int due = w.cl(list)[i].col + m->dStateLen;
-                    if (due >= j0 + 32) break;
-                    if (due >= j0 && due < L) { eqcol[q] |= 1u << (due - j0); act |= 1u << (due - j0); eqany |= 1u << (due - j0); }
-                }
-            }
-            AUGB_ROLLED
-            while (act) {
-                const int t = wffs(act); act &= act - 1;
-                unsigned eqbits = 0;
-                if (eqany & (1u << t)) {
-                    AUGB_ROLLED
-                    for (int q = 0; q < 6; q++) if (eqcol[q] & (1u << t)) eqbits |= 1u << q;
-                }
-#if AUGB_EL == 32
-                const unsigned mb = (unsigned)ebcast((int)mymask, t);
-#else
-                const unsigned mb = maskbuf[t];
-#endif
-                process_column_tasks(j0 + t, mb, eqbits, el);
-            }
-            if (ws->status) break;
-        }
-        fill_evstart_e(L, el);
-        if (el == 0) {
-            *w.out_n_ev = ws->n_ev; *w.out_status = ws->status;
-            AUGB_ROLLED
-            for (int i = 0; i < NCHAIN; i++) { w.out_ncp[i] = ws->cp_n[i]; w.out_nfcp[i] = FWD ? ws->fcp_n[i] : 0; }
-        }
-        esync();
-    }
-#endif
 };
 
 typedef SweepT<false, false> Sweep;

@@ -17,18 +17,7 @@ namespace augb {
 #ifndef AUGB_TEAM
 #define AUGB_TEAM 32
 #endif
-/* AUGB_TASKS (ghmm_tasks.cu): the task-engine flavour.  The state routines are compiled in their one-lane form (no collectives
- * inside exon_eval / lessd_eval / ...) and the AUGB_EL "engine lanes" of a warp each run ONE (state, column) task of the current
- * column of the warp's window; the engine collectives (e*) below publish the results.  AUGB_EL = 32 on the device and on the
- * 32-fiber CPU executor of the test suite, 1 in a plain host build (tasks then run one after the other). */
-#if defined(AUGB_TASKS)
-#define AUGB_SIMT 0
 #if defined(__CUDA_ARCH__) || defined(AUGB_SIMT32)
-#define AUGB_EL 32
-#else
-#define AUGB_EL 1
-#endif
-#elif defined(__CUDA_ARCH__) || defined(AUGB_SIMT32)
 #define AUGB_SIMT 1
 #else
 #define AUGB_SIMT 0
@@ -75,7 +64,13 @@ AUGB_D double wsumd(double v) {
     for (int o = AUGB_TEAM / 2; o; o >>= 1) v += __shfl_xor_sync(tmask(), v, o);
     return v;
 }
+AUGB_D int wmini(int v) {
+    for (int o = AUGB_TEAM / 2; o; o >>= 1) { int t = __shfl_xor_sync(tmask(), v, o); v = t < v ? t : v; }
+    return v;
+}
 AUGB_D unsigned wballot(bool p) { return __ballot_sync(tmask(), p) >> tbase(); }
+/* the lanes (team-relative bits) that hold the same value */
+AUGB_D unsigned wmatch(int v) { return __match_any_sync(tmask(), v) >> tbase(); }
 AUGB_D int wbcast(int v, int src) { return __shfl_sync(tmask(), v, tbase() + src); }
 AUGB_D sc_t wbcast64(sc_t v, int src) { return __shfl_sync(tmask(), v, tbase() + src); }
 AUGB_D int wffs(unsigned b) { return __ffs(b) - 1; }
@@ -88,6 +83,8 @@ AUGB_HD void wsync() {}
 AUGB_HD sc_t wmax(sc_t v) { return v; }
 AUGB_HD sc_t wsum(sc_t v) { return v; }
 AUGB_HD int wmaxi(int v) { return v; }
+AUGB_HD int wmini(int v) { return v; }
+AUGB_HD unsigned wmatch(int) { return 1u; }
 AUGB_HD double wmaxd(double v) { return v; }
 AUGB_HD double wsumd(double v) { return v; }
 AUGB_HD unsigned wballot(bool p) { return p ? 1u : 0u; }
@@ -173,40 +170,5 @@ AUGB_D Lse wlse(Lse a) {
     return r;
 }
 
-
-#if defined(AUGB_TASKS)
-/* ---- engine collectives (full warp) ---- */
-#if AUGB_EL == 32
-#if defined(__CUDA_ARCH__)
-AUGB_D int elane_id() { return threadIdx.x & 31; }
-AUGB_D unsigned ematch(int v) { return __match_any_sync(0xffffffffu, v); }
-/* n-th (0-based) set bit of a 64-bit mask, -1 if there are fewer */
-AUGB_D int efns64(unsigned long long b, int n) {
-    const unsigned lo = (unsigned)b, hi = (unsigned)(b >> 32); const int nlo = __popc(lo);
-    if (n < nlo) return (int)__fns(lo, 0, n + 1);
-    if (n - nlo < __popc(hi)) return 32 + (int)__fns(hi, 0, n - nlo + 1);
-    return -1;
-}
-#else
-inline int elane_id() { return simt::lane(); }
-inline unsigned ematch(int v) { const uint64_t* b = simt::rendezvous(simt::bits(v), 5); unsigned r = 0; for (int i = 0; i < 32; i++) if (simt::unbits<int>(b[i]) == v) r |= 1u << i; return r; }
-inline int efns64(unsigned long long b, int n) { for (int i = 0; i < 64; i++) if (b >> i & 1) { if (n == 0) return i; n--; } return -1; }
-#endif
-AUGB_D void esync() { __syncwarp(0xffffffffu); }
-AUGB_D unsigned eballot(bool p) { return __ballot_sync(0xffffffffu, p); }
-AUGB_D int ebcast(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-AUGB_D sc_t emax64(sc_t v) { for (int o = 16; o; o >>= 1) { sc_t t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; } return v; }
-AUGB_D int emini(int v) { for (int o = 16; o; o >>= 1) { int t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; } return v; }
-#else
-AUGB_HD int elane_id() { return 0; }
-AUGB_HD unsigned ematch(int) { return 1u; }
-AUGB_HD int efns64(unsigned long long b, int n) { for (int i = 0; i < 64; i++) if (b >> i & 1) { if (n == 0) return i; n--; } return -1; }
-AUGB_HD void esync() {}
-AUGB_HD unsigned eballot(bool p) { return p ? 1u : 0u; }
-AUGB_HD int ebcast(int v, int) { return v; }
-AUGB_HD sc_t emax64(sc_t v) { return v; }
-AUGB_HD int emini(int v) { return v; }
-#endif
-#endif
 
 }  // namespace augb

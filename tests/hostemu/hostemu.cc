@@ -25,13 +25,7 @@ using namespace augb;
 /* run the sweep of one window: one lane, or 32 fibers that each own a copy of the per-thread state like the threads of a warp */
 template <class SW>
 static void run_sweep(SW& proto) {
-#if defined(AUGB_TASKS) && defined(AUGB_SIMT32)
-    /* task-engine flavour on 32 fibers: every fiber = one engine lane (its own copy of the per-thread state), tasks of a column side by side */
-    simt::run([&]() { SW mine = proto; mine.run_tasks(); });
-    proto.attach();
-#elif defined(AUGB_TASKS)
-    proto.run_tasks();            /* one engine lane: the tasks of a column one after the other */
-#elif defined(AUGB_SIMT32)
+#if defined(AUGB_SIMT32)
     simt::run([&]() { SW mine = proto; mine.run(); });
     proto.attach();
 #else
@@ -153,7 +147,7 @@ static int sample_impl(void* mp, const char* dna, int L, const int32_t* gc_in, i
     SamplerT<SW> sp; sp.sw = &sw; sp.sc.opt = opts.data(); sp.sc.opt_cap = (int)opts.size(); sp.sc.sorted = sorted.data(); sp.sc.nopt = &nopt;
     sp.rng = rng.data() + rand_pos; sp.nrng = (int)nrng;
     SampleOut so; so.rand_used = rand_used; so.cap = cap; so.begin = sb; so.end = se; so.type = st_; so.trunc = str_; so.count = scount; so.logp = slogp; so.status = status;
-#if defined(AUGB_SIMT32) && !defined(AUGB_TASKS)
+#ifdef AUGB_SIMT32
     simt::run([&]() { SW mine = sw; mine.attach(); mine.lane = lane_id(); SamplerT<SW> sp2 = sp; sp2.sw = &mine; sp2.run(nsamples, so); });
 #else
     sp.run(nsamples, so);

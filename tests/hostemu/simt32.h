@@ -114,5 +114,10 @@ inline unsigned __ballot_sync(unsigned, bool p) {
 }
 template <typename T> inline T __shfl_sync(unsigned, T v, int src) { const uint64_t* b = simt::rendezvous(simt::bits(v), 3); return simt::unbits<T>(b[src & 31]); }
 template <typename T> inline T __shfl_xor_sync(unsigned, T v, int o) { const int l = simt::lane(); const uint64_t* b = simt::rendezvous(simt::bits(v), 4); return simt::unbits<T>(b[(l ^ o) & 31]); }
+inline unsigned __match_any_sync(unsigned, int v) {
+    const uint64_t* b = simt::rendezvous(simt::bits(v), 5);
+    unsigned r = 0; for (int i = 0; i < 32; i++) if (simt::unbits<int>(b[i]) == v) r |= 1u << i;
+    return r;
+}
 inline int __ffs(unsigned b) { return b ? __builtin_ctz(b) + 1 : 0; }
 inline int __popc(unsigned b) { return __builtin_popcount(b); }

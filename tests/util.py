@@ -177,18 +177,16 @@ class Oracle:
 class HostEmu:
     NCHAIN = 13
 
-    def __init__(self, blob: bytes, simt32: bool = False, tasks: bool = False):
+    def __init__(self, blob: bytes, simt32: bool = False):
         """simt32=True: the 32-lane flavour of the kernel source (the lane-group paths of the device) on 32 fibers per warp,
-        tests/hostemu/simt32.h; default: one lane.  tasks=True: the task-engine flavour (ghmm_tasks.cu: lanes = tasks of a column),
-        with one engine lane, or with simt32 on 32 fibers like the device."""
+        tests/hostemu/simt32.h; default: one lane."""
         srcs = ["tests/hostemu/hostemu.cc", "augustus_b200/csrc/ghmm_model.cc"]
         hdrs = [os.path.join(ROOT, "augustus_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "augustus_b200", "csrc"))]
         hdrs.append(os.path.join(ROOT, "tests", "hostemu", "simt32.h"))
         newest = max(os.path.getmtime(p) for p in hdrs + [os.path.join(ROOT, s) for s in srcs])
-        so = HOSTEMU_SO.replace("hostemu.so", "hostemu%s%s.so" % ("_tasks" if tasks else "", "32" if simt32 else ""))
+        so = HOSTEMU_SO.replace("hostemu.so", "hostemu32.so") if simt32 else HOSTEMU_SO
         if not os.path.exists(so) or os.path.getmtime(so) < newest:
-            subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC"] + (["-DAUGB_SIMT32"] if simt32 else []) + (["-DAUGB_TASKS"] if tasks else [])
-                           + ["-o", so] + srcs, cwd=ROOT, check=True)
+            subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC"] + (["-DAUGB_SIMT32"] if simt32 else []) + ["-o", so] + srcs, cwd=ROOT, check=True)
         self.lib = ctypes.CDLL(so)
         self.lib.hostemu_model_create.restype = ctypes.c_void_p
         self.lib.hostemu_model_create.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_int]
