@@ -9,6 +9,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/augb200.h"
@@ -69,7 +70,8 @@ struct augb200_model {
     /* sampling */
     int nsamp = 0;                       /* sampled paths per window of the current batch (0 = Viterbi only) */
     augb200_path* samples_out = nullptr;
-    DevBuf<uint32_t> d_rng; size_t rng_n = 0;
+    DevBuf<uint32_t> d_rng; size_t rng_n = 0; uint64_t rng_base = 0;      /* the device holds values [rng_base, rng_base + rng_n) of the stream */
+    GlibcRand rng_gen;                   /* carried between calls: only values not produced yet are ever generated */
     uint64_t rand_pos = 0;               /* where in the rand() stream the windows of the next sampling call start */
     int64_t rand_used0 = 0;              /* draws window 0 of the last sampling call consumed */
     DevBuf<SampHdr> d_shdr; PinBuf<SampHdr> h_shdr; DevBuf<int32_t> d_sstatus; PinBuf<int32_t> h_sstatus;
@@ -160,15 +162,16 @@ static int upload_windows(augb200_model* M, const augb200_window* w, const int* 
         if ((rc = M->h_sbegin.reserve(M->scap)) || (rc = M->h_send.reserve(M->scap)) || (rc = M->h_stype.reserve(M->scap)) || (rc = M->h_strunc.reserve(M->scap))) return rc;
         size_t nh = (size_t)count * M->nsamp;
         if ((rc = M->d_shdr.reserve(nh)) || (rc = M->h_shdr.reserve(nh)) || (rc = M->d_sstatus.reserve(2 * (size_t)count)) || (rc = M->h_sstatus.reserve(2 * (size_t)count))) return rc;
-        /* the rand() stream every window draws from: an unseeded reference process per window = glibc seed 1 */
-        size_t need = (size_t)M->rand_pos + (size_t)M->nsamp * ((size_t)maxL + 2);
-        if (need > M->rng_n) {
+        /* the rand() stream every window draws from (an unseeded reference process per window = glibc seed 1), from the position the
+         * caller set: the window [rand_pos, rand_pos + need) of the stream, generated from the carried generator state */
+        const size_t need = (size_t)M->nsamp * ((size_t)maxL + 2);
+        if (!(M->rng_n && M->rng_base <= M->rand_pos && M->rand_pos + need <= M->rng_base + M->rng_n)) {
             std::vector<uint32_t> host(need);
-            glibc_rand_stream(1, host.data(), need);
+            M->rng_gen.seek(M->rand_pos); M->rng_gen.fill(host.data(), need);
             if ((rc = M->d_rng.reserve(need))) return rc;
             CK(cudaMemcpyAsync(M->d_rng.p, host.data(), need * 4, cudaMemcpyHostToDevice, M->stream));
             CK(cudaStreamSynchronize(M->stream));
-            M->rng_n = need;
+            M->rng_n = need; M->rng_base = M->rand_pos;
         }
     }
     return 0;
@@ -182,8 +185,9 @@ static int run_kernels(augb200_model* M, int count) {
     static int bps = 0;
     if (!bps) { const char* e = getenv("AUGB200_SWEEP_BLOCKS_PER_SM"); bps = e ? atoi(e) : 4; if (bps < 1) bps = 1; }
     const bool utr = M->hm.dm.utr != 0;
-    const int nrng = (int)std::min<size_t>(M->rng_n - std::min<size_t>(M->rng_n, M->rand_pos), 0x7fffffff);
-    const uint32_t* d_rng = M->d_rng.p ? M->d_rng.p + M->rand_pos : nullptr;
+    const size_t rng_off = M->rng_n && M->rand_pos >= M->rng_base ? (size_t)std::min<uint64_t>(M->rand_pos - M->rng_base, M->rng_n) : M->rng_n;
+    const int nrng = (int)std::min<size_t>(M->rng_n - rng_off, 0x7fffffff);
+    const uint32_t* d_rng = M->d_rng.p ? M->d_rng.p + rng_off : nullptr;
     if (M->waves.empty() || M->waves.back().first + M->waves.back().second != count) { M->waves.clear(); M->waves.push_back({0, count}); }
     while (M->wave_ev.size() + 1 < M->waves.size()) {
         std::pair<cudaEvent_t, cudaEvent_t> e;
@@ -339,8 +343,15 @@ static int check_windows(int32_t n, const augb200_window* w) {
     return 0;
 }
 
+/* The kernels read the model from one __constant__ symbol per device (c_model, re-uploaded by every call): calls on models that live on
+ * the same device take turns.  (The staged calls are asynchronous and are meant for one model per device.) */
+static std::mutex g_device_lock[64];
+
 static int decode_batch_impl(augb200_model* M, int32_t n, const augb200_window* w, augb200_path* out, int nsamp, augb200_path* samples) {
     if (!M || !out) return AUGB200_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> device_turn(g_device_lock[M->device & 63]);
+    struct Reset { augb200_model* m; ~Reset() { m->nsamp = 0; m->samples_out = nullptr; } } reset_on_exit{M};      /* also on the error returns */
+    M->staged_n = 0;                     /* a staged batch shares the descriptors and the arena with this call: it is gone */
     M->nsamp = nsamp; M->samples_out = samples;
     M->rs_begin.clear(); M->rs_end.clear(); M->rs_type.clear(); M->rs_trunc.clear();
     int rc = check_windows(n, w); if (rc) return rc;
@@ -381,7 +392,6 @@ static int decode_batch_impl(augb200_model* M, int32_t n, const augb200_window* 
             samples[i].begin = M->rs_begin.data() + off; samples[i].end = M->rs_end.data() + off;
             samples[i].type = M->rs_type.data() + off; samples[i].truncated = M->rs_trunc.data() + off;
         }
-    M->nsamp = 0; M->samples_out = nullptr;
     return AUGB200_OK;
 }
 
@@ -394,8 +404,42 @@ int augb200_decode_batch_sampling(augb200_model* M, int32_t n, const augb200_win
 
 int augb200_decode(augb200_model* M, const augb200_window* w, augb200_path* out) { return augb200_decode_batch(M, 1, w, out); }
 
+int augb200_decode_batch_multi(augb200_model* const* models, int32_t n_models, int32_t n, const augb200_window* w, int32_t nsample,
+                               augb200_path* out, augb200_path* samples) {
+    if (!models || n_models < 1 || !out || n < 0 || (n && !w) || (nsample != 0 && (nsample < 2 || !samples))) return AUGB200_ERR_BAD_ARG;
+    for (int d = 0; d < n_models; d++) {
+        if (!models[d]) return AUGB200_ERR_BAD_ARG;
+        for (int e = 0; e < d; e++) if (models[e] == models[d]) return AUGB200_ERR_BAD_ARG;
+    }
+    const int ns = nsample ? nsample - 1 : 0;
+    /* window i goes to model i mod n_models (block-cyclic); one host thread per device drives its share */
+    std::vector<std::vector<augb200_window>> sub(n_models);
+    std::vector<std::vector<augb200_path>> sout(n_models), ssamp(n_models);
+    for (int i = 0; i < n; i++) sub[i % n_models].push_back(w[i]);
+    std::vector<int> rcs(n_models, 0);
+    std::vector<std::string> errs(n_models);
+    std::vector<std::thread> th;
+    for (int d = 0; d < n_models; d++) {
+        sout[d].resize(sub[d].size()); ssamp[d].resize(sub[d].size() * (size_t)ns);
+        th.emplace_back([&, d]() {
+            if (sub[d].empty()) return;
+            rcs[d] = decode_batch_impl(models[d], (int32_t)sub[d].size(), sub[d].data(), sout[d].data(), ns, ns ? ssamp[d].data() : nullptr);
+            if (rcs[d]) errs[d] = g_cuda_err;          /* (the error text is thread-local) */
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int d = 0; d < n_models; d++) if (rcs[d]) { g_cuda_err = errs[d]; return rcs[d]; }
+    /* back into input order; the arrays stay owned by the model that decoded the window */
+    for (int i = 0; i < n; i++) {
+        const int d = i % n_models; const size_t k = (size_t)(i / n_models);
+        out[i] = sout[d][k];
+        for (int q = 0; q < ns; q++) samples[(size_t)i * ns + q] = ssamp[d][k * ns + q];
+    }
+    return AUGB200_OK;
+}
+
 int augb200_set_rand_position(augb200_model* M, uint64_t draws_consumed) {
-    if (!M || draws_consumed > ((uint64_t)1 << 31)) return AUGB200_ERR_BAD_ARG;
+    if (!M) return AUGB200_ERR_BAD_ARG;
     M->rand_pos = draws_consumed;
     return AUGB200_OK;
 }

@@ -122,6 +122,7 @@ struct UtrDesc {
 
 struct DevModel {
     int S, C, k, d, dStateLen;
+    int snip_before, snip_after;    /* memo-emulated columns around a GC-class boundary (MB_SLOW) */
     int dss_start, dss_end, ass_start, ass_end, ass_up, tiw, init_len, et_len;
     int max_exon_len, min_exon_length, dss_gc_allowed;
     int tis_n, tis_k, assm_n, assm_k, n_ld_exon, n_ld_intron;
@@ -193,9 +194,8 @@ struct SampleOpt { double lp; int32_t ord /* insertion order in the reference's 
 enum : int { SG_DSSF = 0, SG_DSSR = 1, SG_ASSF = 2, SG_ASSR = 3, SG_XRS = 4, NSIG = 5 };
 
 /* SnippetProbs memo restated for the columns around GC-class boundaries (Sweep::snip_get) */
-constexpr int SNIP_BEFORE = 540 + 8;    /* emulation starts this many columns before a boundary (>= dStateLen) ... */
-constexpr int SNIP_AFTER = 1080 + 16;   /* ... and ends this many after it (>= 2 * dStateLen) */
-constexpr int SNIP_RING = 2048;         /* key ring (positions), power of two > dStateLen + slack */
+/* the emulation starts DevModel::snip_before (= dStateLen + 8) columns before a boundary and ends snip_after (= 2 * dStateLen + 16) after it */
+constexpr int SNIP_RING = 2048;         /* key ring (positions), power of two > dStateLen + slack (checked when the model is built) */
 struct SnipEnt { int32_t len; uint32_t next; sc_t val; };        /* next = absolute entry id, 0 = none */
 struct SnipHead { uint32_t first, last; };
 struct SnipFrame { int32_t base, len; int32_t add, pad; sc_t part; };

@@ -194,13 +194,13 @@ __global__ void __launch_bounds__(PREP_BS) k_prep(const WinDev* __restrict__ win
         __syncthreads();
         { int cm = 0; for (int i = threadIdx.x; i < L; i += PREP_BS) cm |= 1 << gc[i]; if (cm) atomicOr(&s_classmask, cm); }
         {
-            /* columns near a GC-class boundary (number of boundaries in (j - SNIP_AFTER, j + SNIP_BEFORE]) get MB_SLOW */
+            /* columns near a GC-class boundary (number of boundaries in (j - snip_after, j + snip_before]) get MB_SLOW */
             int32_t* nb = (int32_t*)(base + lay.ev);           /* scratch: inclusive count of boundaries at positions <= i */
             block_scan_gen<int>([&](int i) { return i >= 1 && gc[i] != gc[i - 1] ? 1 : 0; }, nb, L, 0, sm32);
             __syncthreads();
             for (int j = threadIdx.x; j < L; j += PREP_BS) {
                 unsigned mb = anynuc ? column_mask(m, s, j) : 0u;
-                int hi = min(j + SNIP_BEFORE, L - 1), lo = j - SNIP_AFTER;
+                int hi = min(j + m->snip_before, L - 1), lo = j - m->snip_after;
                 if (anynuc && j >= 1 && nb[hi] - (lo >= 0 ? nb[lo] : 0) > 0) mb |= MB_SLOW;
                 mask[j] = (mask_t)mb;
             }
@@ -333,7 +333,7 @@ __device__ __forceinline__ void sweep_sample_body(const WinDev* __restrict__ win
         wsync();
         WinOuts* outs = (WinOuts*)(wd.base + wd.lay.outs);
         if (wd.lay.nsamp > 0) {
-            if (wstate[wid].status) { if (lane == 0) outs->samp_status = wstate[wid].status; }
+            if (wstate[wid].status) { if (lane == 0) { outs->samp_status = wstate[wid].status; outs->rand_used = 0; } }
             else {
                 SamplerT<SW> sp; sp.sw = &sw;
                 sp.sc.opt = (SampleOpt*)(wd.base + wd.lay.opt); sp.sc.opt_cap = wd.lay.opt_cap; sp.sc.sorted = (int32_t*)(wd.base + wd.lay.sorted); sp.sc.nopt = &s_nopt[wid];

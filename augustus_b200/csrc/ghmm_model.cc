@@ -8,16 +8,18 @@ namespace augb {
 namespace {
 struct Reader {
     HostModel::BlobView b; std::string* err; bool ok = true;
-    const augb200_blob_entry* need(const char* name) {
+    /* an entry whose payload lies inside the blob and holds at least `min_bytes` of the expected type */
+    const augb200_blob_entry* need(const char* name, uint32_t dtype, size_t min_bytes) {
         const augb200_blob_entry* e = b.find(name);
         if (!e) { ok = false; *err = std::string("blob entry missing: ") + name; return nullptr; }
-        if (e->offset + e->nbytes > b.n) { ok = false; *err = std::string("blob entry out of range: ") + name; return nullptr; }
+        if (e->offset > b.n || e->nbytes > b.n - e->offset) { ok = false; *err = std::string("blob entry out of range: ") + name; return nullptr; }
+        if (e->dtype != dtype || e->nbytes < min_bytes || (e->offset & 7)) { ok = false; *err = std::string("blob entry of unexpected type / size: ") + name; return nullptr; }
         return e;
     }
-    int i32(const char* name) { auto e = need(name); return e ? *(const int32_t*)(b.p + e->offset) : 0; }
-    double f64(const char* name) { auto e = need(name); return e ? *(const double*)(b.p + e->offset) : 0; }
-    const double* darr(const char* name, size_t* n) { auto e = need(name); if (!e) { *n = 0; return nullptr; } *n = e->nbytes / 8; return (const double*)(b.p + e->offset); }
-    const int32_t* iarr(const char* name, size_t* n) { auto e = need(name); if (!e) { *n = 0; return nullptr; } *n = e->nbytes / 4; return (const int32_t*)(b.p + e->offset); }
+    int i32(const char* name) { auto e = need(name, AUGB200_DT_I32, 4); int32_t v = 0; if (e) memcpy(&v, b.p + e->offset, 4); return v; }
+    double f64(const char* name) { auto e = need(name, AUGB200_DT_F64, 8); double v = 0; if (e) memcpy(&v, b.p + e->offset, 8); return v; }
+    const double* darr(const char* name, size_t* n) { auto e = need(name, AUGB200_DT_F64, 0); if (!e) { *n = 0; return nullptr; } *n = e->nbytes / 8; return (const double*)(b.p + e->offset); }
+    const int32_t* iarr(const char* name, size_t* n) { auto e = need(name, AUGB200_DT_I32, 0); if (!e) { *n = 0; return nullptr; } *n = e->nbytes / 4; return (const int32_t*)(b.p + e->offset); }
 };
 }  // namespace
 
@@ -89,6 +91,14 @@ int HostModel::build(const void* blob, size_t nbytes) {
     int nbins = r.i32("transinit_nbins"), utr = r.i32("utr_option_on"), nc = r.i32("nc_option_on");
     if (!r.ok) return AUGB200_ERR_BAD_BLOB;
     if (m.S < 1 || m.S > MAXS || m.C < 1 || m.C > MAXC) { err = "state / class count out of range"; return AUGB200_ERR_UNSUPPORTED; }
+    {   /* geometry integers feed shift counts, table sizes and loop bounds: check them before anything is computed from them */
+        auto in = [](int v, int lo, int hi) { return v >= lo && v <= hi; };
+        if (!in(m.dss_start, 0, 12) || !in(m.dss_end, 0, 12) || !in(m.ass_start, 0, 12) || !in(m.ass_end, 0, 12) || m.dss_start + m.dss_end > 14 || m.ass_start + m.ass_end > 14 ||
+            !in(m.ass_up, 0, 400) || !in(m.tiw, 0, 400) || !in(m.init_len, 0, 1000) || !in(m.et_len, 0, 1000) || !in(m.d, 1, 1 << 20) ||
+            !in(m.max_exon_len, 1, 1 << 24) || !in(m.min_exon_length, 0, 1 << 20) || !in(m.GCwinsize, 0, 1 << 28) || !in(m.weighing, 0, 16) ||
+            !in(m.tis_n, 0, 400) || !in(m.tis_k, 0, 4) || !in(m.assm_n, 0, 400) || !in(m.assm_k, 0, 4) || !in(nbins, -1, 64))
+            { err = "model geometry out of range"; return AUGB200_ERR_BAD_BLOB; }
+    }
     if (ik != m.k || gk != m.k || m.k < 1 || m.k > 4) { err = "content model orders must be equal and <= 4"; return AUGB200_ERR_UNSUPPORTED; }
     m.tis_nbins = nbins > 0 ? nbins : 0;
     m.utr = utr ? 1 : 0; m.nc = nc ? 1 : 0;
@@ -102,6 +112,10 @@ int HostModel::build(const void* blob, size_t nbytes) {
     if (r.b.find("temperature") && r.i32("temperature") != 0) { err = "sampling temperature != 0 is not supported"; return AUGB200_ERR_UNSUPPORTED; }
     m.dStateLen = m.d - 2 - m.dss_end - m.ass_start - 2 - m.ass_up;     /* intronmodel.cc:519-520 */
     if (m.dStateLen < 1) { err = "d too small"; return AUGB200_ERR_UNSUPPORTED; }
+    /* columns around a GC-class boundary in which the SnippetProbs memo is restated (Sweep::snip_get): dStateLen columns before it every
+     * key a later request can reach is created, 2 * dStateLen after it every piece in play carries the new class */
+    m.snip_before = m.dStateLen + 8; m.snip_after = 2 * m.dStateLen + 16;
+    if (m.C > 1 && m.dStateLen + 16 > SNIP_RING) { err = "intron d too large for the memo ring of multi-class models"; return AUGB200_ERR_UNSUPPORTED; }
 
     /* ---- tables ---- */
     tab.clear(); off.clear();

@@ -33,7 +33,7 @@ struct HostModel {
         const augb200_blob_entry* find(const char* name) const {
             const augb200_blob_header* h = (const augb200_blob_header*)p;
             const augb200_blob_entry* e = (const augb200_blob_entry*)(p + sizeof *h);
-            for (uint32_t i = 0; i < h->n_entries; i++) if (!strcmp(e[i].name, name)) return &e[i];
+            for (uint32_t i = 0; i < h->n_entries; i++) if (!strncmp(e[i].name, name, sizeof e[i].name) && strlen(name) < sizeof e[i].name) return &e[i];
             return nullptr;
         }
     };

@@ -246,7 +246,7 @@ inline void prep_window_seq(const DevModel* m, const char* dna, int L, const int
     }
     for (int j = 0; j < L; j++) mask[j] = anynuc ? (mask_t)column_mask(m, s, j) : 0;
     if (anynuc) for (int b = 1; b < L; b++) if (gc[b] != gc[b - 1])        /* GC-class boundary at b */
-        for (int j = (b - SNIP_BEFORE < 1 ? 1 : b - SNIP_BEFORE); j < L && j < b + SNIP_AFTER; j++) mask[j] |= MB_SLOW;
+        for (int j = (b - m->snip_before < 1 ? 1 : b - m->snip_before); j < L && j < b + m->snip_after; j++) mask[j] |= MB_SLOW;
     {
         sc_t* sg = (sc_t*)(base + lay.sig);
         for (int which = 0; which < NSIG; which++)

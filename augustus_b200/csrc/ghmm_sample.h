@@ -262,28 +262,40 @@ typedef SamplerT<SweepFwd> Sampler;
 typedef SamplerT<SweepFwdUtr> SamplerUtr;
 
 /* glibc rand() (random_r, TYPE_3 additive feedback generator: r[i] = r[i-3] + r[i-31], output r[i] >> 1; seeded by the
- * minimal-standard LCG and 310 discarded outputs) — the stream an unseeded `augustus` process draws from (seed 1) */
-inline void glibc_rand_stream(uint32_t seed, uint32_t* out, size_t n) {
-    int32_t r[34];
-    r[0] = (int32_t)seed;
-    for (int i = 1; i < 31; i++) {
-        long hi = r[i - 1] / 127773, lo = r[i - 1] % 127773;
-        long word = 16807 * lo - 2836 * hi;
-        if (word < 0) word += 2147483647;
-        r[i] = (int32_t)word;
+ * minimal-standard LCG and 310 discarded outputs) — the stream an unseeded `augustus` process draws from (seed 1).
+ * The generator keeps its 34-word ring and a 64-bit position, so a caller that moves forward through the stream (the drop-in
+ * accumulates the draws of all pieces and sequences of a process) only ever generates the values it has not seen yet. */
+struct GlibcRand {
+    uint32_t ring[34]; uint64_t pos = 0; bool seeded = false;      /* ring[(344 + pos + k) % 34] holds r of the last 34 indices */
+    void seed(uint32_t sd) {
+        int32_t r[34];
+        r[0] = (int32_t)sd;
+        for (int i = 1; i < 31; i++) {
+            long hi = r[i - 1] / 127773, lo = r[i - 1] % 127773;
+            long word = 16807 * lo - 2836 * hi;
+            if (word < 0) word += 2147483647;
+            r[i] = (int32_t)word;
+        }
+        uint32_t st[344];
+        for (int i = 0; i < 31; i++) st[i] = (uint32_t)r[i];
+        for (int i = 31; i < 34; i++) st[i] = st[i - 31];
+        for (int i = 34; i < 344; i++) st[i] = st[i - 31] + st[i - 3];
+        for (int i = 310; i < 344; i++) ring[i % 34] = st[i];
+        pos = 0; seeded = true;
     }
-    uint32_t st[344];
-    for (int i = 0; i < 31; i++) st[i] = (uint32_t)r[i];
-    for (int i = 31; i < 34; i++) st[i] = st[i - 31];
-    for (int i = 34; i < 344; i++) st[i] = st[i - 31] + st[i - 3];
-    uint32_t ring[34];                   /* ring[i % 34] = r_i for the last 34 indices */
-    for (int i = 310; i < 344; i++) ring[i % 34] = st[i];
-    for (size_t k = 0; k < n; k++) {
-        size_t i = 344 + k;
-        uint32_t v = ring[(i - 31) % 34] + ring[(i - 3) % 34];
-        ring[i % 34] = v;
-        out[k] = v >> 1;
+    uint32_t next() {
+        const uint64_t i = 344 + pos;
+        const uint32_t v = ring[(i - 31) % 34] + ring[(i - 3) % 34];
+        ring[i % 34] = v; pos++;
+        return v >> 1;
     }
-}
+    /* position the generator so that the next value is number p of the stream of seed 1 */
+    void seek(uint64_t p) {
+        if (!seeded || p < pos) seed(1);
+        while (pos < p) next();
+    }
+    void fill(uint32_t* out, size_t n) { for (size_t k = 0; k < n; k++) out[k] = next(); }
+};
+inline void glibc_rand_stream(uint32_t seed, uint32_t* out, size_t n) { GlibcRand g; g.seed(seed); g.fill(out, n); }
 
 }  // namespace augb

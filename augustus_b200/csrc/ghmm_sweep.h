@@ -780,8 +780,8 @@ struct SweepT {
      * table when the GC class changes but keeps the memo, so a piece keeps the class that was active when it was first
      * computed: around a class boundary a lessD emission is a mix of both tables that depends on the order of calls.
      * Away from boundaries every piece in play has the class of the current column and the value is the plain prefix
-     * difference; within [boundary - SNIP_BEFORE, boundary + SNIP_AFTER) the memo is restated entry for entry (lane 0).
-     * Starting from an empty memo SNIP_BEFORE columns ahead of the boundary is exact: the list of a key only depends on
+     * difference; within [boundary - snip_before, boundary + snip_after) the memo is restated entry for entry (lane 0).
+     * Starting from an empty memo snip_before (> dStateLen) columns ahead of the boundary is exact: the list of a key only depends on
      * requests coming from higher keys, all of which are replayed, and everything computed before the boundary has the old
      * class whatever its decomposition ("GC-class boundaries"). */
     AUGB_D SnipEnt* snip_ent(int rc, unsigned id) const { return w.snip_pool + (size_t)rc * w.snip_cap + (id & (unsigned)(w.snip_cap - 1)); }

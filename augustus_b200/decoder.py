@@ -42,8 +42,7 @@ class AugB200Error(RuntimeError):
 
 
 def library_path() -> str:
-    # AUGB200_LIB: another build of the same library (kernel experiments); never a different implementation
-    return os.environ.get("AUGB200_LIB") or os.path.join(_HERE, "libaugb200.so")
+    return os.path.join(_HERE, "libaugb200.so")
 
 
 class _Window(ctypes.Structure):
@@ -101,6 +100,9 @@ def _load():
         getattr(lib, f).argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(_Window), ctypes.POINTER(_Path)]
     lib.augb200_decode_batch_sampling.restype = ctypes.c_int
     lib.augb200_decode_batch_sampling.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(_Window), ctypes.c_int32, ctypes.POINTER(_Path), ctypes.POINTER(_Path)]
+    lib.augb200_decode_batch_multi.restype = ctypes.c_int
+    lib.augb200_decode_batch_multi.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(_Window), ctypes.c_int32,
+                                               ctypes.POINTER(_Path), ctypes.POINTER(_Path)]
     lib.augb200_decode.restype = ctypes.c_int
     lib.augb200_decode.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Window), ctypes.POINTER(_Path)]
     lib.augb200_stage_batch.restype = ctypes.c_int
@@ -259,6 +261,23 @@ class Decoder:
         samp = (_Path * (nw * ns))()
         self._check(self._lib.augb200_decode_batch_sampling(self._h, nw, arr, nsample, out, samp))
         return self._raw(out, nw), self._raw(samp, nw * ns, self._lib.augb200_sample_store)
+
+    @staticmethod
+    def decode_batch_multi(decoders: Sequence["Decoder"], seqs: Sequence, nsample: int = 0):
+        """augb200_decode_batch_multi: window i is decoded by decoders[i mod len(decoders)] (one model per device, same blob), results in
+        input order.  Returns the Viterbi paths, or (paths, samples) when nsample >= 2."""
+        lib = decoders[0]._lib
+        arr, keep = decoders[0]._windows(seqs)
+        nw, ns = len(seqs), (nsample - 1 if nsample else 0)
+        out = (_Path * nw)()
+        samp = (_Path * max(1, nw * ns))()
+        hs = (ctypes.c_void_p * len(decoders))(*[d._h for d in decoders])
+        decoders[0]._check(lib.augb200_decode_batch_multi(hs, len(decoders), nw, arr, nsample, out, samp if ns else None))
+        vit = Decoder._paths(out, nw)
+        if not ns:
+            return vit
+        allp = Decoder._paths(samp, nw * ns)
+        return vit, [allp[i * ns:(i + 1) * ns] for i in range(nw)]
 
     def set_rand_position(self, draws_consumed: int):
         """Where in the process-wide rand() stream (vitmatrix.cc:300) the next sampling call starts; 0 = a fresh process."""

@@ -1,5 +1,5 @@
 /*
- * aug_export.h — TEST / INTEGRATION INFRASTRUCTURE (shared by oracle/augdump.cc and oracle/augshim.cc).
+ * aug_export.h — host-side exporter of the parameter blob (shared by the drop-in binding host/augshim.cc and the test tool oracle/augdump.cc).
  *
  * Exports the AUGB2PAR parameter blob (include/augb200_params.h) from the reference's static tables after
  * StateModel::readAllParameters() (reference src/augustus.cc:176).  This is the function body a maintainer

@@ -1,7 +1,8 @@
 /*
- * augshim.cc — INTEGRATION DEMONSTRATOR (built only where /root/reference exists, into oracle/_ref/).
+ * augshim.cc — the host-side binding of the product (built only where /root/reference exists, into oracle/_ref/).
  *
- * The reference-side binding of INTEGRATION.md as working code: strong definitions of the three DP
+ * It lives in host/, not in oracle/: this is the code a maintainer adds to the reference, i.e. integration code of the product,
+ * while oracle/ holds the checker only.  The reference-side binding of INTEGRATION.md as working code: strong definitions of the three DP
  * entry points of NAMGene,
  *     NAMGene::viterbiAndForward   (reference src/namgene.cc:168-365)
  *     NAMGene::getViterbiPath      (src/namgene.cc:432-510)

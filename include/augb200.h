@@ -86,7 +86,8 @@ typedef struct augb200_path {
 /* Create a model from an AUGB2PAR blob (copied; the caller may free it afterwards). `device` is the
  * CUDA device ordinal.  Several models may live on one device and be used in turn by the host thread (each call uploads its own
  * model constants): the reference swaps initProbs / termProbs for the synch-state vectors at the cut points of long sequences
- * (NAMGene::doViterbiPiecewise, namgene.cc:594-603) — a host serves that with one model per vector pair (oracle/augshim.cc). */
+ * (NAMGene::doViterbiPiecewise, namgene.cc:594-603) — a host serves that with one model per vector pair (host/augshim.cc).
+ * Synchronous calls on models of the same device take turns (one set of model constants per device). */
 int augb200_model_create(const void* blob, size_t nbytes, int device, augb200_model** out);
 void augb200_model_destroy(augb200_model* m);
 
@@ -120,6 +121,18 @@ int64_t augb200_last_rand_consumed(const augb200_model* m);
 
 /* Decode one window. */
 int augb200_decode(augb200_model* m, const augb200_window* window, augb200_path* out);
+
+/*
+ * Several devices, one call: `models` are n_models models created from the same blob on different devices; window i
+ * is decoded by models[i mod n_models] (block-cyclic, like the reference's own scale-out: one `augustus --predictionStart/End` job
+ * per chunk of scripts/createAugustusJoblist.pl), one host thread per device, no exchange between devices.  out[] (and samples[],
+ * when nsample >= 2 asks for sampled paths as in augb200_decode_batch_sampling; pass nsample = 0 and samples = NULL otherwise)
+ * come back in input order; the arrays of window i stay owned by the model that decoded it until its next call.  This is the
+ * call a C++ host uses to spread the windows of a chromosome over the GPUs of a node; ranks of a multi-process job use
+ * augb200_decode_batch per rank and gather the path arrays themselves (bench.py: one NCCL gather).
+ */
+int augb200_decode_batch_multi(augb200_model* const* models, int32_t n_models, int32_t n, const augb200_window* windows,
+                               int32_t nsample, augb200_path* out, augb200_path* samples);
 
 /* Device-resident variant used for kernel-only timing: stage the windows once, run the kernels any
  * number of times (no host<->device traffic in between), fetch the paths at the end.  DNA and window

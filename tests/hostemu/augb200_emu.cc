@@ -1,5 +1,5 @@
 /*
- * augb200_emu.cc — TEST-ONLY stand-in for the part of the C ABI (include/augb200.h) that the drop-in shim (oracle/augshim.cc) calls,
+ * augb200_emu.cc — TEST-ONLY stand-in for the part of the C ABI (include/augb200.h) that the drop-in shim (host/augshim.cc) calls,
  * on top of the host build of the kernel source (hostemu.cc, one lane).
  *
  * Purpose: the shim's own logic — model variants per initial / terminal vector, pieces of sequences longer than maxDNAPieceSize,

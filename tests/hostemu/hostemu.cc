@@ -141,11 +141,14 @@ static int sample_impl(void* mp, const char* dna, int L, const int32_t* gc_in, i
     }
     if (outs->status) { *status = outs->status; return -1; }
     size_t nrng = (size_t)nsamples * (L + 2);
-    std::vector<uint32_t> rng(rand_pos + nrng);           /* the walks start rand_pos values into the stream of seed 1 (augb200_set_rand_position) */
-    glibc_rand_stream(1, rng.data(), rand_pos + nrng);
+    /* the walks start rand_pos values into the stream of seed 1 (augb200_set_rand_position); like the library the twin keeps the
+     * generator between calls and only produces the window [rand_pos, rand_pos + nrng) */
+    static GlibcRand gen;
+    std::vector<uint32_t> rng(nrng);
+    gen.seek(rand_pos); gen.fill(rng.data(), nrng);
     std::vector<SampleOpt> opts(L + 4096); std::vector<int32_t> sorted(L + 4096); int nopt = 0;
     SamplerT<SW> sp; sp.sw = &sw; sp.sc.opt = opts.data(); sp.sc.opt_cap = (int)opts.size(); sp.sc.sorted = sorted.data(); sp.sc.nopt = &nopt;
-    sp.rng = rng.data() + rand_pos; sp.nrng = (int)nrng;
+    sp.rng = rng.data(); sp.nrng = (int)nrng;
     SampleOut so; so.rand_used = rand_used; so.cap = cap; so.begin = sb; so.end = se; so.type = st_; so.trunc = str_; so.count = scount; so.logp = slogp; so.status = status;
 #ifdef AUGB_SIMT32
     simt::run([&]() { SW mine = sw; mine.attach(); mine.lane = lane_id(); SamplerT<SW> sp2 = sp; sp2.sw = &mine; sp2.run(nsamples, so); });

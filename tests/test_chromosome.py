@@ -72,7 +72,7 @@ def test_join_of_reference_chunk_outputs_equals_the_reference_pipeline():
 
 def test_chunk_runs_through_the_shim_equal_the_reference_pipeline(tmp_path):
     """run_chunks + join on the first 650 kb of chr2L with the CPU twin of the drop-in front end (oracle/_ref/augustus_emu: reference
-    front end + oracle/augshim.cc + host build of the kernel source, tests/test_dropin_emu.py) — the per-chunk outputs and the joined
+    front end + host/augshim.cc + host build of the kernel source, tests/test_dropin_emu.py) — the per-chunk outputs and the joined
     text equal what the unmodified reference and its Perl scripts produced.  The GPU run of the same pipeline: tests/test_whole_chromosome.py."""
     import importlib.util
     spec = importlib.util.spec_from_file_location("twc", os.path.join(util.ROOT, "tests", "test_whole_chromosome.py"))

@@ -1,5 +1,5 @@
 """Drop-in check (pytest -m gpu): the reference's own front end with its three DP entry points bound to
-libaugb200.so (oracle/augshim.cc -> oracle/_ref/augustus_b200) must print the same GFF as the unmodified
+libaugb200.so (host/augshim.cc -> oracle/_ref/augustus_b200) must print the same GFF as the unmodified
 reference binary (oracle/_ref/augustus) for the same command line.
 
 Both binaries are built by oracle/Makefile in the build container (they need /root/reference) and travel to

@@ -1,4 +1,4 @@
-"""The drop-in shim's own logic on the CPU: oracle/_ref/augustus_emu is the reference front end + oracle/augshim.cc (exactly as in
+"""The drop-in shim's own logic on the CPU: oracle/_ref/augustus_emu is the reference front end + host/augshim.cc (exactly as in
 the drop-in oracle/_ref/augustus_b200) linked against tests/hostemu/augb200_emu.cc — the C ABI served by the host build of the
 kernel source — instead of libaugb200.so.  Its GFF must equal the unmodified reference binary's.  Covers what the shim adds on
 top of the library: one model per (initProbs, termProbs) pair for the pieces of sequences longer than maxDNAPieceSize

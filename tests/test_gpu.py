@@ -1,9 +1,11 @@
 """GPU parity tests (pytest -m gpu): the CUDA path through the C ABI against the oracle on the same
 inputs, against the committed reference paths, and through size-independent properties at full size."""
+import ctypes
+
 import numpy as np
 import pytest
 
-from augustus_b200 import Decoder, synth
+from augustus_b200 import AugB200Error, Decoder, synth
 from tests import util
 
 pytestmark = pytest.mark.gpu
@@ -45,6 +47,19 @@ def test_synthetic_50k_windows_match_reference(dec, golden):
     for p, ref in zip(paths, golden["synthetic50k"]):
         assert p.as_tuples() == [tuple(s) for s in ref["states"]]
         assert abs(p.log_prob - ref["log_prob"]) <= 1e-6 * abs(ref["log_prob"])
+
+
+def test_config2_64_windows_match_reference_digests(dec):
+    """the first 64 windows of BASELINE.json configs[1] against the reference (tests/golden/ref_config2_digests.json,
+    written by make_golden_config2.py from the unmodified reference; bench.py checks its timed outputs against the same file)."""
+    import json
+    import bench
+    gold = json.load(open(util.GOLDEN + "/ref_config2_digests.json"))["windows"]
+    paths = dec.decode_batch(synth.windows(64, 50000))
+    for i, p in enumerate(paths):
+        g = gold[str(i)]
+        assert bench.path_digest(p.as_tuples()) == g["sha1"] and len(p.states) == g["n"]
+        assert abs(p.log_prob - g["log_prob"]) <= 1e-6 * abs(g["log_prob"])
 
 
 def test_real_dna_with_gc_class_boundaries_matches_reference(dec, oracle, golden):
@@ -164,3 +179,68 @@ def test_staged_batch_larger_than_the_arena_runs_in_waves(dec, monkeypatch):
             assert a.as_tuples() == b.as_tuples()
     finally:
         small.close()
+
+
+def test_multi_device_call_returns_input_order(dec):
+    """augb200_decode_batch_multi: windows dealt block-cyclically to several models (here two models on device 0, which take turns;
+    on a node one per GPU), results in input order — Viterbi paths and sampled paths identical to the single-model calls."""
+    wins = [synth.window(1300 + i, n) for i, n in enumerate([9000, 4000, 12000, 3000, 7000, 50, 8000])]
+    want = dec.decode_batch(wins)
+    wv, ws = dec.decode_batch_sampling(wins, 12)
+    other = Decoder(util.blob_bytes(), 0)
+    try:
+        got = Decoder.decode_batch_multi([dec, other], wins)
+        for a, b in zip(got, want):
+            assert a.status == 0 and a.as_tuples() == b.as_tuples() and a.log_prob == b.log_prob
+        gv, gs = Decoder.decode_batch_multi([dec, other], wins, nsample=12)
+        for a, b in zip(gv, wv):
+            assert a.as_tuples() == b.as_tuples()
+        for sa, sb in zip(gs, ws):
+            assert [x.as_tuples() for x in sa] == [x.as_tuples() for x in sb]
+        with pytest.raises(AugB200Error):
+            Decoder.decode_batch_multi([dec, dec], wins)           # the same model twice
+    finally:
+        other.close()
+
+
+def test_plain_call_invalidates_a_staged_batch(dec):
+    """stage(100) -> decode_batch(10) -> run_staged used to launch over stale descriptors; the staged batch is gone now"""
+    d2 = Decoder(util.blob_bytes(), 0)
+    try:
+        d2.stage([synth.window(40 + i, 3000) for i in range(12)])
+        d2.decode_batch([synth.window(7, 2000)])
+        with pytest.raises(AugB200Error):
+            d2.run_staged()
+    finally:
+        d2.close()
+
+
+def test_rand_position_is_a_64_bit_offset_and_may_move_backwards(dec):
+    """the rand() stream is generated from a carried generator state, window by window; positions beyond 2^31 are legal,
+    a smaller position restarts the generator.  Sampled paths at a position == the host build of the kernel source at that position."""
+    dna = util.read_fasta(util.GOLDEN + "/example.fa")[1][1]
+    emu = util.HostEmu(util.blob_bytes())
+    emu.lib.hostemu_sample_at.restype = ctypes.c_int
+    emu.lib.hostemu_sample_at.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 7 + [ctypes.c_uint64, ctypes.c_void_p]
+
+    def emu_at(pos, ns=20):
+        L = len(dna); cap = ns * (L // 8 + 64)
+        sb, se = np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=np.int32)
+        st, tr = np.zeros(cap, dtype=np.uint8), np.zeros(cap, dtype=np.uint8)
+        cnt, lp, status, used = np.zeros(ns, dtype=np.int32), np.zeros(ns), ctypes.c_int32(), ctypes.c_int32()
+        emu.lib.hostemu_sample_at(emu.m, dna.encode(), L, None, ns, cap, sb.ctypes.data, se.ctypes.data, st.ctypes.data, tr.ctypes.data,
+                                  cnt.ctypes.data, lp.ctypes.data, ctypes.byref(status), pos, ctypes.byref(used))
+        out, p = [], 0
+        for k in range(ns):
+            c = int(cnt[k]); out.append([(int(st[p + q]), int(sb[p + q]), int(se[p + q]), int(tr[p + q])) for q in range(c)]); p += c
+        return out, used.value
+    try:
+        for pos in (5_000_000, 1234, 5_000_000 + 77):          # forward, backwards (restart), forward inside the buffered window
+            dec.set_rand_position(pos)
+            _, samples = dec.decode_batch_sampling([dna], 21)
+            want, used = emu_at(pos)
+            assert [s.as_tuples() for s in samples[0]] == want
+            assert dec.last_rand_consumed == used
+        dec.set_rand_position(2 ** 33 + 5)                        # accepted (nothing is generated until a decode asks for it)
+    finally:
+        dec.set_rand_position(0)

@@ -1,5 +1,5 @@
 """GFF-level parity sweep over the species parameter sets of the reference (build container only): for every config/species/<name>
-run the unmodified `augustus` and the CPU twin of the drop-in (oracle/_ref/augustus_emu: reference front end + oracle/augshim.cc + host
+run the unmodified `augustus` and the CPU twin of the drop-in (oracle/_ref/augustus_emu: reference front end + host/augshim.cc + host
 build of the kernel source) on tests/golden/example.fa with the species' own defaults (most sample 100 paths) and compare the output
 byte for byte.  Complements species_sweep.py (Viterbi cells) with the sampled paths / posterior probabilities per species.
 usage: species_gff_sweep.py [--utr] [--fasta=file.fa --softmask] [species ...]   (--softmask: softmasking at its default, on)"""
