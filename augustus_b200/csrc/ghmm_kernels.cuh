@@ -336,7 +336,7 @@ __device__ __forceinline__ void sweep_sample_body(const WinDev* __restrict__ win
             if (wstate[wid].status) { if (lane == 0) { outs->samp_status = wstate[wid].status; outs->rand_used = 0; } }
             else {
                 SamplerT<SW> sp; sp.sw = &sw;
-                sp.sc.opt = (SampleOpt*)(wd.base + wd.lay.opt); sp.sc.opt_cap = wd.lay.opt_cap; sp.sc.sorted = (int32_t*)(wd.base + wd.lay.sorted); sp.sc.nopt = &s_nopt[wid];
+                sp.sc.opt = (SampleOpt*)(wd.base + wd.lay.opt); sp.sc.opt_cap = wd.lay.opt_cap; sp.sc.sorted = (int32_t*)(wd.base + wd.lay.sorted); sp.sc.ex = (double*)(wd.base + wd.lay.optex); sp.sc.nopt = &s_nopt[wid];
                 sp.rng = rng; sp.nrng = nrng;
                 SampleOut so; so.cap = wd.lay.samp_cap;
                 so.begin = (int32_t*)(wd.base + wd.lay.s_begin); so.end = (int32_t*)(wd.base + wd.lay.s_end);

@@ -37,7 +37,7 @@ struct WinLayout {
     size_t ev, evstart, cl[NCL], cp[NCHAIN], outs;           /* dynamic (sweep) */
     size_t snip_head, snip_pool, snip_stack; int snip_cap;
     size_t evF, clF, clG, fcp; int fcp_cap;                       /* forward pass (0 capacity when not requested) */
-    size_t opt, sorted, s_begin, s_end, s_type, s_trunc, s_count, s_logp; int opt_cap, samp_cap, nsamp;   /* sampling */
+    size_t opt, sorted, optex, s_begin, s_end, s_type, s_trunc, s_count, s_logp; int opt_cap, samp_cap, nsamp;   /* sampling */
     size_t path_begin, path_end, path_type, path_trunc;      /* backtrace output */
     size_t total, slab;
     int ev_cap, cl_cap, cp_cap, path_cap, nslab_local;
@@ -75,7 +75,7 @@ inline WinLayout make_layout(int L, int C, bool generous = false, bool forward =
     w.fcp = take((size_t)w.nchain * w.fcp_cap * sizeof(FChainCP));
     w.nsamp = forward ? nsamp : 0;
     w.opt_cap = w.nsamp ? w.cl_cap + 1024 : 0; w.samp_cap = w.nsamp ? (generous ? w.nsamp * (L / 8 + 64) : w.nsamp * (128 + L / 128)) : 0;   /* gene-dense fly DNA: ~3.5 path states per kb and sample */
-    w.opt = take((size_t)w.opt_cap * sizeof(SampleOpt)); w.sorted = take((size_t)w.opt_cap * 4);
+    w.opt = take((size_t)w.opt_cap * sizeof(SampleOpt)); w.sorted = take((size_t)w.opt_cap * 4); w.optex = take((size_t)w.opt_cap * 8);
     w.s_begin = take((size_t)w.samp_cap * 4); w.s_end = take((size_t)w.samp_cap * 4); w.s_type = take(w.samp_cap); w.s_trunc = take(w.samp_cap);
     w.s_count = take((size_t)w.nsamp * 4 + 16); w.s_logp = take((size_t)w.nsamp * 8);
     w.outs = take(sizeof(WinOuts));

@@ -22,7 +22,7 @@ struct SampleOut {
     int32_t* status;
     int32_t* rand_used = nullptr;    /* out: draws consumed (cursor at the end) */
 };
-struct SampleScratch { SampleOpt* opt; int opt_cap; int32_t* sorted; int* nopt; };
+struct SampleScratch { SampleOpt* opt; int opt_cap; int32_t* sorted /* 1 = option already drawn against */; double* ex /* exp(lp - max) */; int* nopt; };
 
 AUGB_HD int trunc_flag_s(int type, int end, int predEnd, int L) { return trunc_flag(type, end, predEnd, L); }
 
@@ -30,7 +30,11 @@ template <class SW>
 struct SamplerT {
     SW* sw; SampleScratch sc; const uint32_t* rng; int nrng; int cursor; int lane;
 
-    /* draw one option; returns its index in sc.opt (or -1), adds ln(p/cumprob) to *lp */
+    /* draw one option; returns its index in sc.opt (or -1), adds ln(p/cumprob) to *lp.
+     * OptionsList::sample (vitmatrix.cc:295-320) walks the options in stable descending order of probability until the cumulative sum
+     * passes z.  The sums are formed in the reference's order (cumprob in insertion order, the walk in sorted order); what is parallel
+     * is the exponentials (one per lane and option) and the search for the next option of the sorted order (warp arg-best over the
+     * options not taken yet) — the walk almost always ends after a few options, so the list is never sorted as a whole. */
     AUGB_D int pick(double* lp) {
         const int n = *sc.nopt;
         if (n > sc.opt_cap) return -2;
@@ -39,35 +43,38 @@ struct SamplerT {
         AUGB_ROLLED
         for (int i = lane; i < n; i += AUGB_NLANES) { double v = sc.opt[i].lp; mx = v > mx ? v : mx; }
         mx = wmaxd(mx);
-        /* stable descending order by probability: rank = options that come first */
         AUGB_ROLLED
-        for (int i = lane; i < n; i += AUGB_NLANES) {
-            const double v = sc.opt[i].lp; const int o = sc.opt[i].ord; int r = 0;
-            AUGB_ROLLED
-            for (int k = 0; k < n; k++) { double u = sc.opt[k].lp; r += (u > v || (u == v && (sc.opt[k].ord < o || (sc.opt[k].ord == o && k < i)))) ? 1 : 0; }
-            sc.sorted[r] = i;
-        }
+        for (int i = lane; i < n; i += AUGB_NLANES) { sc.ex[i] = exp(sc.opt[i].lp - mx); sc.sorted[i] = 0; }
         wsync();
-        int res = -1; double add = 0;
-        if (lane == 0) {
-            /* cumprob accumulates in insertion order (OptionsList::add); insertion order = ascending `ord`, which is how the
-             * options sit in the buffer when one lane lists them; with 32 lanes the buffer order is the same because lanes take
-             * candidates in the reference's order */
-            double cum = 0;
+        /* cumprob accumulates in insertion order (OptionsList::add); insertion order = ascending `ord`, which is how the options sit in
+         * the buffer when one lane lists them; with 32 lanes the buffer order is the same because lanes take candidates in the
+         * reference's order.  Every lane forms the same sum. */
+        double cum = 0;
+        AUGB_ROLLED
+        for (int i = 0; i < n; i++) cum += sc.ex[i];
+        const double z = ((double)rng[cursor] / 2147483647.0) * cum * 0.99999;
+        int res = -1, first = -1; double cs = 0;
+        AUGB_ROLLED
+        for (int r = 0; r < n && res < 0; r++) {
+            /* the next option of the stable descending order: highest lp, then lowest ord, then lowest index */
+            double bl = -1e308; int bo = 0x7fffffff, bi = 0x7fffffff;
             AUGB_ROLLED
-            for (int i = 0; i < n; i++) cum += exp(sc.opt[i].lp - mx);
-            const double z = ((double)rng[cursor] / 2147483647.0) * cum * 0.99999;
-            double cs = 0;
-            AUGB_ROLLED
-            for (int r = 0; r < n && res < 0; r++) { int i = sc.sorted[r]; cs += exp(sc.opt[i].lp - mx); if (z < cs) res = i; }
-            if (res < 0) res = sc.sorted[0];
-            add = sc.opt[res].lp - mx - log(cum);
+            for (int i = lane; i < n; i += AUGB_NLANES) {
+                if (sc.sorted[i]) continue;
+                const double v = sc.opt[i].lp; const int o = sc.opt[i].ord;
+                if (v > bl || (v == bl && (o < bo || (o == bo && i < bi)))) { bl = v; bo = o; bi = i; }
+            }
+            const double ml = wmaxd(bl);
+            const int mo = wmini(bl == ml && bi != 0x7fffffff ? bo : 0x7fffffff);
+            const int sel = wmini(bl == ml && bo == mo ? bi : 0x7fffffff);
+            if (r == 0) first = sel;
+            cs += sc.ex[sel];
+            if (z < cs) res = sel;
+            else { if (lane == 0) sc.sorted[sel] = 1; wsync(); }
         }
-        res = wbcast(res, 0);
+        if (res < 0) res = first;
+        const double add = sc.opt[res].lp - mx - log(cum);
         cursor++;
-#if AUGB_SIMT
-        add = wbcastd(add, 0);
-#endif
         *lp += add;
         return res;
     }
