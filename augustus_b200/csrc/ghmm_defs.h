@@ -199,6 +199,9 @@ constexpr int SNIP_RING = 2048;         /* key ring (positions), power of two > 
 struct SnipEnt { int32_t len; uint32_t next; sc_t val; };        /* next = absolute entry id, 0 = none */
 struct SnipHead { uint32_t first, last; };
 struct SnipFrame { int32_t base, len; int32_t add, pad; sc_t part; };
+/* forward pass with sampling: a lessD content value of a memo-emulated column that is NOT the plain prefix difference (the memo mixed
+ * the tables of two GC classes).  A sampling step at that column finds the value again here — the reference finds it in the memo. */
+struct SnipX { int32_t col; int32_t lendir /* len << 1 | strand */; sc_t val; };
 
 /* candidate lists of a window */
 enum : int { CL_LD = 0 /* +f: longdss_f */, CL_RA = 3 /* +f: rlongass_f */, CL_LA = 6 /* +phase */, CL_RD = 9 /* +phase */, NCL_BASE = 12,
@@ -240,6 +243,7 @@ struct WinView {
     SnipEnt* snip_pool;        /* [2][snip_cap] */
     SnipFrame* snip_stack;     /* [SNIP_RING] */
     int snip_cap;              /* power of two */
+    SnipX* snipx; int sx_cap;  /* forward + sampling only */
     AUGB_HD Cand* cl(int i) const { return cl0 + (size_t)i * cl_stride; }
     AUGB_HD ChainCP* cp(int i) const { return cp0 + (size_t)i * cp_stride; }
     /* results */

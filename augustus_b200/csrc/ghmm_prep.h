@@ -36,6 +36,7 @@ struct WinLayout {
     size_t pmask; int softmask;                                           /* softmasking models only */
     size_t ev, evstart, cl[NCL], cp[NCHAIN], outs;           /* dynamic (sweep) */
     size_t snip_head, snip_pool, snip_stack; int snip_cap;
+    size_t snipx; int sx_cap;
     size_t evF, clF, clG, fcp; int fcp_cap;                       /* forward pass (0 capacity when not requested) */
     size_t opt, sorted, optex, s_begin, s_end, s_type, s_trunc, s_count, s_logp; int opt_cap, samp_cap, nsamp;   /* sampling */
     size_t path_begin, path_end, path_type, path_trunc;      /* backtrace output */
@@ -82,6 +83,8 @@ inline WinLayout make_layout(int L, int C, bool generous = false, bool forward =
     w.snip_cap = generous ? 262144 : 16384;
     w.snip_head = take((size_t)2 * SNIP_RING * sizeof(SnipHead)); w.snip_pool = take((size_t)2 * w.snip_cap * sizeof(SnipEnt));
     w.snip_stack = take((size_t)SNIP_RING * sizeof(SnipFrame));
+    w.sx_cap = forward ? (generous ? 8 * L + 64 : L / 4 + 256) : 0;
+    w.snipx = take((size_t)w.sx_cap * sizeof(SnipX));
     w.path_begin = take((size_t)w.path_cap * 4); w.path_end = take((size_t)w.path_cap * 4);
     w.path_type = take(w.path_cap); w.path_trunc = take(w.path_cap);
     w.total = al16(o);
@@ -109,7 +112,7 @@ AUGB_HD WinView make_view(char* base, const WinLayout& lay, int L, int classmask
     v.ev = (Event*)(base + lay.ev); v.evstart = (int32_t*)(base + lay.evstart);
     v.cl0 = (Cand*)(base + lay.cl[0]); v.cp0 = (ChainCP*)(base + lay.cp[0]);
     v.evF = (double*)(base + lay.evF); v.clF0 = (double*)(base + lay.clF); v.clG0 = (sc_t*)(base + lay.clG); v.fcp0 = (FChainCP*)(base + lay.fcp); v.fcp_cap = lay.fcp_cap; v.fcp_stride = lay.fcp_cap;
-    v.snip_head = (SnipHead*)(base + lay.snip_head); v.snip_pool = (SnipEnt*)(base + lay.snip_pool); v.snip_stack = (SnipFrame*)(base + lay.snip_stack); v.snip_cap = lay.snip_cap;
+    v.snip_head = (SnipHead*)(base + lay.snip_head); v.snip_pool = (SnipEnt*)(base + lay.snip_pool); v.snip_stack = (SnipFrame*)(base + lay.snip_stack); v.snip_cap = lay.snip_cap; v.snipx = (SnipX*)(base + lay.snipx); v.sx_cap = lay.sx_cap;
     v.cl_stride = (int)((lay.cl[1] - lay.cl[0]) / sizeof(Cand)); v.cp_stride = (int)((lay.cp[1] - lay.cp[0]) / sizeof(ChainCP));
     WinOuts* o = (WinOuts*)(base + lay.outs);
     v.out_nfcp = o->nfcp;

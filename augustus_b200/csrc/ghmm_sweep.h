@@ -45,6 +45,7 @@ struct WarpState {
     int status;
     int any_pend;
     unsigned snip_cnt[2];       /* entries allocated so far per strand (ids start at 1) */
+    int n_sx;                   /* entries of WinView::snipx */
     /* forward pass */
     int fcp_n[NCHAIN];
     double ftilde[NCHAIN];      /* ln F[j][chain] - A[j] of the current column */
@@ -851,13 +852,27 @@ struct SweepT {
         wsync();
     }
 
+    /* a sampling step at a memo-emulated column: the content value the forward pass got from the memo for (strand, column, length), if it
+     * was not the plain prefix difference `plain` (entries are in column order) */
+    AUGB_D sc_t snipx_lookup(int dir, int j, int len, sc_t plain) const {
+        const int n = ws->n_sx;
+        if (n == 0) return plain;
+        const SnipX* x = w.snipx;
+        int lo = 0, hi = n;                       /* first entry with col >= j */
+        AUGB_ROLLED
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (x[mid].col < j) lo = mid + 1; else hi = mid; }
+        const int key = (len << 1) | dir;
+        AUGB_ROLLED
+        for (int i = lo; i < n && x[i].col == j; i++) if (x[i].lendir == key) return x[i].val;
+        return plain;
+    }
     /* lessD / rlessD (intronmodel.cc:540-629, 924-1000): max over the longdss / rlongass cells of the last dStateLen columns */
     AUGB_D void lessd_eval(int dir, int j) {
         const int fwd = !dir;
         int eob = fwd ? j + m->ass_up + m->ass_start + 2 : j + m->dss_end + 2;
         int lme = j - m->dStateLen; if (lme < 0) lme = 0;
         const sc_t* P = parr(cls, fwd ? PA_PI : PA_PIR);
-        /* (sampling steps use the plain prefix difference: the memo of the forward pass is gone by then) */
+        /* (a sampling step does not run the memo again: it takes the value the forward pass got from it, snipx_lookup) */
         const bool slow = (w.mask[j] & MB_SLOW) != 0 && !(FWD && opt);
         /* Viterbi kernels away from GC-class boundaries: the three frames in one pass, 8 lanes each (as Sweep::exon_eval) */
 #ifndef AUGB_LESSD_GL
@@ -912,7 +927,16 @@ struct SweepT {
                             sc_t ld = m->ld_intron[ilen], t = TR(c.state, s);
                             if (!isneg(ld) && !isneg(t)) {
                                 /* seqProb is evaluated (and memoised) for every candidate that passes the site tests (:970-972) */
-                                sc_t seq = slow ? snip_get(dir, j, j - begin + 1) : P[j + 1] - P[begin];
+                                sc_t seq = P[j + 1] - P[begin];
+                                if (slow) {
+                                    const sc_t plain = seq;
+                                    seq = snip_get(dir, j, j - begin + 1);
+                                    if (FWD && seq != plain) {       /* keep what the memo gave for the sampling steps at this column */
+                                        const int k = ws->n_sx;
+                                        if (k >= w.sx_cap) ws->status = 8;
+                                        else { SnipX x; x.col = j; x.lendir = ((j - begin + 1) << 1) | dir; x.val = seq; w.snipx[k] = x; ws->n_sx = k + 1; }
+                                    }
+                                } else if (FWD && opt && (w.mask[j] & MB_SLOW)) seq = snipx_lookup(dir, j, j - begin + 1, seq);
                                 sc_t sc = c.V + (t + (ld + seq));
                                 if (sc > best || (sc == best && e > bkey)) { best = sc; bkey = e; bpred = c.state; }
                                 if (FWD && !opt) fl.add(w.clF(list)[i] + sc2d(t + (ld + seq)));
@@ -1148,7 +1172,7 @@ struct SweepT {
     AUGB_D bool init_window() {
         ncb = 0;
         if (lane == 0) {
-            ws->n_ev = 0; ws->filled = -1; ws->status = 0; ws->any_pend = 0; ws->snip_cnt[0] = ws->snip_cnt[1] = 0;
+            ws->n_ev = 0; ws->filled = -1; ws->status = 0; ws->any_pend = 0; ws->snip_cnt[0] = ws->snip_cnt[1] = 0; ws->n_sx = 0;
             AUGB_ROLLED
             for (int i = 0; i < (UTR ? NCL : NCL_BASE); i++) ws->cl_n[i] = 0;
             AUGB_ROLLED

@@ -425,6 +425,7 @@ def main():
             if not ok:
                 raise SystemExit("bench: chr2L window %d (Viterbi path or sampled paths) differs from the reference" % g)
             nver += 1
+        nver = int(allsum([nver])[0])
         mbp3 = sum(len(w) for w in w3) / 1e6
         tot_states = int(allsum([int(vit3[0].sum())])[0]); tot_samp = int(allsum([len(samp3[0])])[0])
         dec3.close()
@@ -597,7 +598,7 @@ def main():
                              "(GPC instruction cache at > 90 % of its request rate, profiles/), not by HBM"},
         "clocks": clk,
         "sweep_ms": sweep_ms,
-        "devices": {"name": props.name, "sm_count_per_rank": [int(x) for x in sms], "first_pass_windows_per_s_per_rank": [round(x, 1) for x in rate0]},
+        "devices": {"name": props.name, "sm_count_per_rank": [int(x) for x in sms], "first_pass_windows_per_ms_per_rank": [round(x, 1) for x in rate0]},
     }
     if not args.no_cpu_baseline:
         try:

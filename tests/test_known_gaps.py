@@ -12,19 +12,20 @@ from tests import util
 
 
 def test_aedes_three_gc_classes_sampling_steps_at_class_boundaries():
-    """--species=aedes (three GC classes) on the soft-masked chr2L window, 99 sampled paths: the oracle draws the reference's 99, the
-    kernel source 96 — a sampling step of lessD inside the columns around a GC-class boundary takes the plain prefix difference, the
-    reference the SnippetProbs memo as the forward pass, the backtracking and the earlier walks left it (statemodel.cc:312-342)."""
+    """--species=aedes (three GC classes) on the soft-masked chr2L window, 99 sampled paths.  Round 1 drew 96 of the reference's 99: a
+    sampling step of lessD inside the columns around a GC-class boundary took the plain prefix difference, the reference the value its
+    SnippetProbs memo holds since the forward pass (statemodel.cc:312-342).  The forward fill now keeps every memo value that is not the
+    plain difference (SnipX) and the sampling steps look it up: 99 of 99, like the oracle."""
     blob = util.blob_bytes("aedes")
     dna = util.read_fasta(util.GOLDEN + "/fly_softmask_window.fa")[0][1]
     ref = [[tuple(x) for x in s["states"]] for s in json.load(gzip.open(util.GOLDEN + "/ref_samples_aedes.json.gz", "rt"))["samples"]]
     assert len(ref) == 99
     o = util.Oracle(blob).sample(dna, 100)
     assert [s["states"] for s in o["samples"]] == ref                                   # the oracle = the reference
-    e = util.HostEmu(blob).sample(dna, 99)
-    assert e["status"] == 0
-    bad = [k for k, (a, b) in enumerate(zip(e["samples"], ref)) if a["states"] != b]
-    assert bad == [7, 35, 41], "the pinned gap changed (a fix shortens this list; anything else is a regression): %s" % bad
+    for simt32 in (False, True):
+        e = util.HostEmu(blob, simt32=simt32).sample(dna, 99)
+        assert e["status"] == 0
+        assert [k for k, (a, b) in enumerate(zip(e["samples"], ref)) if a["states"] != b] == []
     v = util.HostEmu(blob).decode(dna, want_cells=True)
     r = util.Oracle(blob).viterbi(dna, want_matrix=True)
     assert v["states"] == r["condensed"] and (np.where(r["V"] <= util.NEGT, -(1 << 61), r["V"]) == v["cells"]).all()     # every Viterbi cell agrees
@@ -47,3 +48,20 @@ def test_human_utr_two_gc_classes_cells_behind_a_class_boundary():
         zv, ze = V <= util.NEGT, E <= util.NEGT
         diff = (zv != ze) | (~zv & ~ze & (V != E))
         assert [tuple(int(x) for x in ij) for ij in np.argwhere(diff)] == want[name], name
+
+
+def test_human_parameters_on_multi_class_real_dna_sampled_paths():
+    """human parameters on 100 kb of chr2L (13 / 38 GC-class boundaries), 99 sampled paths: kernel source == oracle (round 1: one path of
+    the first window differed, which moved two posterior probabilities of the GFF by 0.01).  Needs the chr2L data of the built checker."""
+    import os
+    import pytest
+    path = os.path.join(util.ROOT, "oracle", "_ref", "data", "chr2L.sm.fa.gz")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/data/chr2L.sm.fa.gz not present")
+    seq = "".join(l.strip() for l in gzip.open(path, "rt") if not l.startswith(">"))
+    blob = util.blob_bytes("human")
+    emu, orc = util.HostEmu(blob), util.Oracle(blob)
+    for off in (5000000, 12000000):
+        dna = seq[off:off + 100000].upper()
+        o, e = orc.sample(dna, 100), emu.sample(dna, 99)
+        assert e["status"] == 0 and [a["states"] for a in e["samples"]] == [b["states"] for b in o["samples"]]
