@@ -78,6 +78,8 @@ struct augb200_model {
     DevBuf<int32_t> d_sbegin, d_send; DevBuf<uint8_t> d_stype, d_strunc; PinBuf<int32_t> h_sbegin, h_send; PinBuf<uint8_t> h_stype, h_strunc;
     int scap = 0;
     std::vector<int32_t> rs_begin, rs_end; std::vector<uint8_t> rs_type, rs_trunc;
+    std::vector<int32_t> rs_first;        /* per (window, sample) of the last sampling call: the first sample of the window with the same states */
+    int64_t rs_total_states = 0;          /* states of all sampled paths of the last call, duplicates counted (rs_begin holds the unique ones) */
 };
 
 static int upload_windows(augb200_model* M, const augb200_window* w, const int* idx, int count, bool generous, size_t wave_cap = 0) {
@@ -256,6 +258,8 @@ static int fetch_results(augb200_model* M, int count, augb200_path* out, const i
                 const SampHdr& h = M->h_shdr.p[(size_t)i * M->nsamp + k]; augb200_path& p = M->samples_out[(size_t)idx[i] * M->nsamp + k];
                 p.n = h.n; p.status = M->h_sstatus.p[2 * i]; p.log_prob = h.logp;
                 p.begin = (const int32_t*)(uintptr_t)(sbase + h.offset);
+                M->rs_first[(size_t)idx[i] * M->nsamp + k] = h.first;
+                M->rs_total_states += h.n;
             }
         for (int i = 0; i < count; i++) if (idx[i] == 0) M->rand_used0 = M->h_sstatus.p[2 * i + 1];
     }
@@ -354,6 +358,7 @@ static int decode_batch_impl(augb200_model* M, int32_t n, const augb200_window* 
     M->staged_n = 0;                     /* a staged batch shares the descriptors and the arena with this call: it is gone */
     M->nsamp = nsamp; M->samples_out = samples;
     M->rs_begin.clear(); M->rs_end.clear(); M->rs_type.clear(); M->rs_trunc.clear();
+    M->rs_first.assign((size_t)(n > 0 ? n : 0) * (size_t)(nsamp > 0 ? nsamp : 0), 0); M->rs_total_states = 0;
     int rc = check_windows(n, w); if (rc) return rc;
     CK(cudaSetDevice(M->device));
     M->r_begin.clear(); M->r_end.clear(); M->r_type.clear(); M->r_trunc.clear();
@@ -494,6 +499,12 @@ int64_t augb200_sample_store(const augb200_model* M, const int32_t** b, const in
     if (t) *t = M->rs_type.data();
     if (tr) *tr = M->rs_trunc.data();
     return (int64_t)M->rs_begin.size();
+}
+
+int64_t augb200_sample_first_occurrence(const augb200_model* M, const int32_t** first) {
+    if (!M) return 0;
+    if (first) *first = M->rs_first.data();
+    return M->rs_total_states;
 }
 
 const char* augb200_strerror(int code) {

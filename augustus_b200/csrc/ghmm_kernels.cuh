@@ -354,8 +354,13 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep_sample(const WinDev*
 __global__ void __launch_bounds__(SWEEP_WARPS * 32) k_sweep_sample_utr(const WinDev* __restrict__ wins, int nwin, int* __restrict__ next,
                                                                        const uint32_t* __restrict__ rng, int nrng) { sweep_sample_body<SweepFwdUtr>(wins, nwin, next, rng, nrng); }
 
-/* gather the sampled paths of all windows: per (window, sample) a header, states contiguous per window */
-struct SampHdr { int32_t n, offset; double logp; };
+/* Gather the sampled paths of all windows: per (window, sample) a header, states contiguous per window.
+ * Row next-1 of SURVEY.md §8f starts here: the reference's host loop compares every sampled path's transcripts with the ones it has
+ * already seen (Transcript::operator==, namgene.cc:875-904); identical state paths are found on the device instead — a path that
+ * repeats an earlier sample of its window is not copied again, its header points to the states of the first occurrence and
+ * `first` names it, so the device->host traffic and the host's per-path work shrink by the duplicate factor. */
+struct SampHdr { int32_t n, offset; double logp; int32_t first, pad; };
+constexpr int PACKS_MAXS = 256;          /* samples per window handled by the de-duplication (more: every path is copied) */
 __global__ void k_pack_samples(const WinDev* __restrict__ wins, int nwin, SampHdr* __restrict__ hdr, int32_t* __restrict__ wstatus, int* __restrict__ total,
                                int32_t* __restrict__ obegin, int32_t* __restrict__ oend, uint8_t* __restrict__ otype, uint8_t* __restrict__ otrunc, int ocap) {
     int wi = blockIdx.x;
@@ -364,21 +369,68 @@ __global__ void k_pack_samples(const WinDev* __restrict__ wins, int nwin, SampHd
     const WinOuts* outs = (const WinOuts*)(wd.base + wd.lay.outs);
     const int ns = wd.lay.nsamp;
     const int32_t* cnt = (const int32_t*)(wd.base + wd.lay.s_count); const double* lp = (const double*)(wd.base + wd.lay.s_logp);
-    __shared__ int s_off, s_tot;
-    if (threadIdx.x == 0) {
-        int st = outs->samp_status, tot = 0;
-        if (!st) for (int k = 0; k < ns; k++) tot += cnt[k];
-        int off = atomicAdd(total, tot);
-        if (off + tot > ocap) { st = 8; tot = 0; }
-        wstatus[2 * wi] = st; wstatus[2 * wi + 1] = outs->rand_used; s_off = off; s_tot = tot;      /* (status, rand() draws consumed) per window */
-        int o = off;
-        for (int k = 0; k < ns; k++) { SampHdr h; h.n = st ? 0 : cnt[k]; h.offset = o; h.logp = st ? 0.0 : lp[k]; hdr[(size_t)wi * ns + k] = h; o += h.n; }
-    }
-    __syncthreads();
-    const int off = s_off, tot = s_tot;
     const int32_t* b = (const int32_t*)(wd.base + wd.lay.s_begin); const int32_t* e = (const int32_t*)(wd.base + wd.lay.s_end);
     const uint8_t* t = (const uint8_t*)(wd.base + wd.lay.s_type); const uint8_t* tr = (const uint8_t*)(wd.base + wd.lay.s_trunc);
-    for (int i = threadIdx.x; i < tot; i += blockDim.x) { obegin[off + i] = b[i]; oend[off + i] = e[i]; otype[off + i] = t[i]; otrunc[off + i] = tr[i]; }
+    __shared__ int s_src[PACKS_MAXS], s_dst[PACKS_MAXS], s_first[PACKS_MAXS];
+    __shared__ unsigned long long s_hash[PACKS_MAXS];
+    __shared__ int s_st;
+    const int st0 = outs->samp_status;
+    const bool dedup = ns <= PACKS_MAXS && !st0;
+    if (threadIdx.x == 0) {
+        int o = 0;
+        if (dedup) for (int k = 0; k < ns; k++) { s_src[k] = o; o += cnt[k]; }
+    }
+    __syncthreads();
+    if (dedup) {
+        for (int k = threadIdx.x; k < ns; k += blockDim.x) {          /* FNV-1a over the states of sample k */
+            unsigned long long h = 1469598103934665603ull;
+            const int o = s_src[k], n = cnt[k];
+            for (int i = 0; i < n; i++) {
+                const unsigned long long w0 = ((unsigned long long)(unsigned)b[o + i] << 32) | (unsigned)e[o + i], w1 = ((unsigned)t[o + i] << 8) | tr[o + i];
+                h = (h ^ w0) * 1099511628211ull; h = (h ^ w1) * 1099511628211ull;
+            }
+            s_hash[k] = h;
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < ns; k += blockDim.x) {          /* the earliest sample with the same states */
+            int f = k; const int n = cnt[k], o = s_src[k];
+            for (int j = 0; j < k && f == k; j++) {
+                if (s_hash[j] != s_hash[k] || cnt[j] != n) continue;
+                const int oj = s_src[j]; bool same = true;
+                for (int i = 0; i < n && same; i++) same = b[o + i] == b[oj + i] && e[o + i] == e[oj + i] && t[o + i] == t[oj + i] && tr[o + i] == tr[oj + i];
+                if (same) f = j;
+            }
+            s_first[k] = f;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        int st = st0, tot = 0;
+        if (!st) for (int k = 0; k < ns; k++) if (!dedup || s_first[k] == k) tot += cnt[k];
+        int off = atomicAdd(total, tot);
+        if (off + tot > ocap) { st = 8; tot = 0; }
+        wstatus[2 * wi] = st; wstatus[2 * wi + 1] = outs->rand_used;      /* (status, rand() draws consumed) per window */
+        s_st = st;
+        int o = off, src = 0;
+        for (int k = 0; k < ns; k++) {
+            SampHdr h; h.n = st ? 0 : cnt[k]; h.logp = st ? 0.0 : lp[k]; h.pad = 0;
+            const bool uniq = !dedup || s_first[k] == k;
+            h.first = dedup ? s_first[k] : k;
+            if (uniq) { h.offset = o; if (dedup) s_dst[k] = o; o += h.n; } else h.offset = s_dst[s_first[k]];
+            hdr[(size_t)wi * ns + k] = h;
+            if (!dedup && !st) {                                      /* plain copy of sample k (more samples than the tables hold) */
+                for (int i = 0; i < cnt[k]; i++) { obegin[h.offset + i] = b[src + i]; oend[h.offset + i] = e[src + i]; otype[h.offset + i] = t[src + i]; otrunc[h.offset + i] = tr[src + i]; }
+            }
+            src += cnt[k];
+        }
+    }
+    __syncthreads();
+    if (!dedup || s_st) return;
+    for (int k = 0; k < ns; k++) {
+        if (s_first[k] != k) continue;
+        const int o = s_src[k], d = s_dst[k], n = cnt[k];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) { obegin[d + i] = b[o + i]; oend[d + i] = e[o + i]; otype[d + i] = t[o + i]; otrunc[d + i] = tr[o + i]; }
+    }
 }
 
 /* ------------------------------------------------------------------ backtrace: one thread per window */

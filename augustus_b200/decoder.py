@@ -125,6 +125,8 @@ def _load():
     lib.augb200_result_store.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_void_p)] * 4
     lib.augb200_sample_store.restype = ctypes.c_int64
     lib.augb200_sample_store.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_void_p)] * 4
+    lib.augb200_sample_first_occurrence.restype = ctypes.c_int64
+    lib.augb200_sample_first_occurrence.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]
     lib.augb200_strerror.restype = ctypes.c_char_p
     lib.augb200_strerror.argtypes = [ctypes.c_int]
     lib.augb200_last_cuda_error.restype = ctypes.c_char_p
@@ -278,6 +280,15 @@ class Decoder:
             return vit
         allp = Decoder._paths(samp, nw * ns)
         return vit, [allp[i * ns:(i + 1) * ns] for i in range(nw)]
+
+    def sample_first_occurrence(self, n_windows: int, nsample: int):
+        """(first, total_states): first[i, k] = first sample of window i with the same states as sample k (k itself for a new path) for the
+        last sampling call; total_states counts duplicates, the sample store holds the unique paths only."""
+        p = ctypes.c_void_p()
+        total = self._lib.augb200_sample_first_occurrence(self._h, ctypes.byref(p))
+        ns = nsample - 1
+        arr = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_int32)), (n_windows * ns,)).copy() if n_windows * ns else np.zeros(0, np.int32)
+        return arr.reshape(n_windows, ns), int(total)
 
     def set_rand_position(self, draws_consumed: int):
         """Where in the process-wide rand() stream (vitmatrix.cc:300) the next sampling call starts; 0 = a fresh process."""

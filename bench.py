@@ -328,6 +328,61 @@ def deal_windows(world, M, rates):
     return base
 
 
+def dropin_leg(n_chr2l):
+    """What a user of the drop-in sees: wall clock of oracle/_ref/augustus_b200 (the reference's front end with its three DP entry points
+    bound to libaugb200.so, host/augshim.cc) against oracle/_ref/augustus for the same command lines, GFF compared line by line.
+    config 1 = examples/example.fa --species=human; then the first n chr2L windows with --species=fly defaults (UTR, softmasking,
+    sample=100), one process per window as scripts/createAugustusJoblist.pl runs a genome: the reference's processes side by side on
+    the host cores, the drop-in's one after the other on the GPU."""
+    from augustus_b200 import synth
+    refdir = os.path.join(ROOT, "oracle", "_ref")
+    ref, drop, cfg = os.path.join(refdir, "augustus"), os.path.join(refdir, "augustus_b200"), os.path.join(refdir, "config")
+    if not (os.path.exists(ref) and os.path.exists(drop)):
+        return {"unavailable": "oracle/_ref/augustus or augustus_b200 not built"}
+    env = dict(os.environ, AUGUSTUS_CONFIG_PATH=cfg)
+
+    def run(exe, args):
+        t0 = time.perf_counter()
+        r = subprocess.run([exe] + args, env=env, capture_output=True, text=True)
+        dt = time.perf_counter() - t0
+        lines = r.stdout.splitlines()
+        if "# command line:" in lines:
+            lines = lines[: lines.index("# command line:")]
+        return dt, r.returncode, lines
+    out = {}
+    ex = os.path.join(ROOT, "tests", "golden", "example.fa")
+    tr, rc1, g1 = run(ref, ["--species=human", "--softmasking=0", ex])
+    run(drop, ["--species=human", "--softmasking=0", ex])                    # (first start of the binary on this box: page-in)
+    td_, rc2, g2 = run(drop, ["--species=human", "--softmasking=0", ex])
+    out["config1_example_fa"] = {"reference_s": tr, "dropin_s": td_, "gff_identical": rc1 == 0 and rc2 == 0 and g1 == g2, "gff_lines": len(g1),
+                                 "note": "11.8 kb in two sequences: the drop-in's time is CUDA start-up"}
+    w3 = chr2l_windows()
+    if w3 is None or n_chr2l <= 0:
+        return out
+    pick = w3[1:1 + n_chr2l]
+    with tempfile.TemporaryDirectory() as td:
+        files = []
+        for i, s in enumerate(pick):
+            fa = os.path.join(td, "w%d.fa" % i); synth.write_fasta(fa, [s], ["chr2L_w%d" % (i + 1)]); files.append(fa)
+        import concurrent.futures as cf
+        t0 = time.perf_counter()
+        with cf.ThreadPoolExecutor(min(len(files), usable_cores())) as exq:
+            refs = list(exq.map(lambda fa: run(ref, ["--species=fly", fa]), files))
+        ref_wall = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        drops = [run(drop, ["--species=fly", fa]) for fa in files]
+        drop_wall = time.perf_counter() - t0
+    same = all(a[1] == 0 and b[1] == 0 and a[2] == b[2] for a, b in zip(refs, drops))
+    mbp = sum(len(s) for s in pick) / 1e6
+    out["chr2L_fly_defaults"] = {"windows": len(pick), "gff_identical": same, "gff_lines": sum(len(a[2]) for a in refs),
+                                 "reference_s_per_window": sum(a[0] for a in refs) / len(refs), "dropin_s_per_window": sum(b[0] for b in drops) / len(drops),
+                                 "reference_wall_s": ref_wall, "reference_processes_side_by_side": min(len(files), usable_cores()), "dropin_wall_s": drop_wall,
+                                 "reference_mbp_s": mbp / ref_wall, "dropin_mbp_s": mbp / drop_wall,
+                                 "note": "one process per 200 kb window; per window the drop-in pays process + CUDA start-up, the blob export and a GPU that holds ONE warp's work; "
+                                         "the batched C ABI (config3_chr2L) decodes all 157 windows in the time of one"}
+    return out
+
+
 # --------------------------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -339,6 +394,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the config 3 / 4 / 5 side measurements")
+    ap.add_argument("--dropin-windows", type=int, default=2, help="chr2L windows of the drop-in end-to-end leg (0 = skip the leg)")
     ap.add_argument("--no-balance", action="store_true", help="keep the block-cyclic deal (do not re-deal by measured sweep rate)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -654,6 +710,11 @@ def main():
             dec4.close()
         except Exception as ex:
             line["secondary"]["config4_utr"] = {"error": repr(ex)}
+    if not args.no_secondary and world == 1 and args.dropin_windows >= 0:
+        try:
+            line["secondary"]["dropin_e2e"] = dropin_leg(args.dropin_windows)
+        except Exception as ex:
+            line["secondary"]["dropin_e2e"] = {"error": repr(ex)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

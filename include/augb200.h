@@ -158,6 +158,18 @@ int64_t augb200_result_store(const augb200_model* m, const int32_t** begin, cons
 int64_t augb200_sample_store(const augb200_model* m, const int32_t** begin, const int32_t** end,
                              const uint8_t** type, const uint8_t** truncated);
 
+/*
+ * De-duplicated sampled paths (first step of SURVEY.md §8f next-1).  NAMGene::findGenes compares the transcripts of every sampled path
+ * with the ones it has collected (Transcript::operator==, namgene.cc:875-904); the library finds repeated state paths on the device: a
+ * sample whose states equal those of an earlier sample of the same window shares that sample's arrays (its augb200_path points to the
+ * same begin/end/type/truncated, so callers that walk every path see no difference), is not copied to the host a second time, and
+ * first[i*(nsample-1) + k] is the index of the first sample of window i with the same states (k itself for a new path).  A host that
+ * post-processes only the first occurrences and weighs them by their multiplicity does 1 / (duplicate factor) of the work.
+ * Returns the number of states of all sampled paths of the last augb200_decode_batch_sampling call with duplicates counted
+ * (augb200_sample_store returns the number actually held).
+ */
+int64_t augb200_sample_first_occurrence(const augb200_model* m, const int32_t** first);
+
 const char* augb200_strerror(int code);
 const char* augb200_last_cuda_error(void);
 

@@ -244,3 +244,24 @@ def test_rand_position_is_a_64_bit_offset_and_may_move_backwards(dec):
         dec.set_rand_position(2 ** 33 + 5)                        # accepted (nothing is generated until a decode asks for it)
     finally:
         dec.set_rand_position(0)
+
+
+def test_sampled_paths_are_deduplicated_on_the_device(dec):
+    """SURVEY.md §8f next-1, first step: a sampled path that repeats an earlier sample of its window shares that sample's arrays and is
+    not copied to the host again; first[i, k] names the first occurrence.  The paths themselves are what they were (the reference
+    comparisons above run through the same call)."""
+    wins = [synth.window(820 + i, n) for i, n in enumerate([30000, 9000, 2500, 400])]
+    ns = 100
+    vit, samples = dec.decode_batch_sampling(wins, ns)
+    first, total = dec.sample_first_occurrence(len(wins), ns)
+    held = 0
+    for i, ss in enumerate(samples):
+        tup = [s.as_tuples() for s in ss]
+        seen = {}
+        for k, t in enumerate(tup):
+            key = tuple(t)
+            assert first[i, k] == seen.setdefault(key, k)            # the earliest sample with the same states
+        held += sum(len(t) for k, t in enumerate(tup) if first[i, k] == k)
+    assert total == sum(len(s.states) for ss in samples for s in ss)
+    raw_v, raw_s = dec.decode_batch_sampling_raw(wins, ns)
+    assert len(raw_s[4]) == held and held < total                   # the store (and the device->host copy) holds the unique paths only
