@@ -16,8 +16,13 @@
  *                                   OpenReadingFrame :101-198
  *   ContentStairs::computeStairs    src/motif.cc:543-614
  *   State::setTruncFlag             src/gene.cc:309-321
- * Scope: ab initio (no hints, softmasking off), no protein profile, no overlap mode — the
- * configuration BASELINE.json configs 1 and 2 run.  UTR / nc states are rejected.
+ *   UtrModel::viterbi...            src/utrmodel.cc:796-1064 (+ endPartEmiProb :1072, notEndPartEmiProb :1167, tssProb :1761,
+ *                                   computeTtsProbs :1840, SegProbs statemodel.cc:398-465, EOPList :473-520)      [--UTR=on, 71 states]
+ *   NcModel::viterbi...             src/ncmodel.cc:154-359 (+ :366, :447, :702, :744)                              [--nc=on, 83 states]
+ *   NAMGene::getSampledPath         src/namgene.cc:367-426, OptionsList::sample vitmatrix.cc:295-320, forward sums of every model
+ * Scope: ab initio with or without softmasking (lower-case runs = nonexonpart bonus, extrinsicinfo.cc:1696-1724), no hints files,
+ * no protein profile, no overlap mode — what BASELINE.json's five configurations run.  Pinned against the unmodified reference:
+ * parity is NOT "unpinned" (tests/test_oracle.py, tests/golden/make_golden*.py).
  *
  * Arithmetic: the reference multiplies LLDouble probabilities; this restatement ADDS log
  * probabilities quantised to Q40 fixed point (int64, 2^-40 nat resolution), the same number
