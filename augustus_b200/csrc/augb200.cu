@@ -15,6 +15,7 @@
 #include "../../include/augb200.h"
 #include "ghmm_kernels.cuh"
 #include "ghmm_model.h"
+#include "ghmm_lockstep.h"
 
 using namespace augb;
 
@@ -53,10 +54,8 @@ struct augb200_model {
     HostModel hm;
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t stream2 = nullptr;      /* odd waves of a batch that needs several: their prep overlaps the sweep of the wave before */
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    size_t arena_half = 0, pool_half = 0;      /* a batch of several waves alternates between two arenas / slab pools of this size */
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> wave_ev;     /* sweep timing of the 2nd.. wave of a staged batch */
     std::vector<std::pair<int, int>> waves;                        /* (first window, count): groups of windows that share the arena in turn */
     DevBuf<sc_t> d_tab; DevModel dm_dev;      /* model with device table pointers; uploaded to the c_model constant */
     /* batch state */
@@ -96,9 +95,6 @@ static int upload_windows(augb200_model* M, const augb200_window* w, const int* 
         all += make_layout(x.length, M->hm.dm.C, generous, M->nsamp > 0, M->nsamp, M->hm.dm.utr != 0, M->hm.dm.softmask != 0).total;
     }
     M->waves.clear();
-    /* A batch that does not fit is cut into waves that alternate between TWO arenas (and two streams, run_kernels): while the sweep of one
-     * wave runs, the prep pass of the next fills the other arena, and the CTAs of the next sweep move in as the tail of this one drains. */
-    if (wave_cap && all > wave_cap) wave_cap /= 2;
     {
         const size_t nw = wave_cap && all > wave_cap ? (all + wave_cap - 1) / wave_cap : 1;
         const size_t target = (all + nw - 1) / nw;
@@ -114,9 +110,7 @@ static int upload_windows(augb200_model* M, const augb200_window* w, const int* 
     if ((rc = M->h_dna.reserve(dna_bytes + 16))) return rc;
     if ((rc = M->d_dna.reserve(dna_bytes + 16))) return rc;
     if (gc_bytes) { if ((rc = M->h_gc.reserve(gc_bytes + 16))) return rc; if ((rc = M->d_gc.reserve(gc_bytes + 16))) return rc; }
-    const size_t narena = M->waves.size() > 1 ? 2 : 1;
-    M->arena_half = (arena + 255) & ~(size_t)255;
-    if ((rc = M->d_arena.reserve(M->arena_half * narena))) return rc;
+    if ((rc = M->d_arena.reserve(arena))) return rc;
     /* slab pool for the prefix arrays of second / third ... GC classes (first class lives in the window) */
     {
         size_t need = 0;
@@ -126,18 +120,18 @@ static int upload_windows(augb200_model* M, const augb200_window* w, const int* 
                 for (int i = wv.first; i < wv.first + wv.second; i++) nd += (size_t)(M->hm.dm.C - 1) * make_layout(w[idx[i]].length, M->hm.dm.C).slab;
                 need = std::max(need, nd);
             }
-        size_t room = M->arena_budget > arena * narena ? M->arena_budget - arena * narena : 0;
-        size_t pool = (std::min(need, (room + M->arena_budget / 8) / narena) + 255) & ~(size_t)255;
-        if (pool && (rc = M->d_pool.reserve(pool * narena))) return rc;
-        M->pool_bytes = pool; M->pool_half = pool;
-        if ((rc = M->d_pool_used.reserve(2))) return rc;
+        size_t room = M->arena_budget > arena ? M->arena_budget - arena : 0;
+        size_t pool = std::min(need, room + M->arena_budget / 8);
+        if (pool && (rc = M->d_pool.reserve(pool))) return rc;
+        M->pool_bytes = pool;
+        if ((rc = M->d_pool_used.reserve(1))) return rc;
     }
     if ((rc = M->h_wins.reserve(count))) return rc;
     if ((rc = M->d_wins.reserve(count))) return rc;
     size_t od = 0, og = 0, oa = 0; long total_path_cap = 0;
     size_t wvi = 0;
     for (int i = 0; i < count; i++) {
-        if (wvi + 1 < M->waves.size() && i == M->waves[wvi + 1].first) { wvi++; oa = (wvi & 1) ? M->arena_half : 0; }      /* next wave: the other arena, from its start */
+        if (wvi + 1 < M->waves.size() && i == M->waves[wvi + 1].first) { wvi++; oa = 0; }      /* next wave: the arena starts over */
         const augb200_window& x = w[idx[i]];
         WinDev& d = M->h_wins.p[i];
         d.L = x.length; d.lay = make_layout(x.length, M->hm.dm.C, generous, M->nsamp > 0, M->nsamp, M->hm.dm.utr != 0, M->hm.dm.softmask != 0);
@@ -162,7 +156,7 @@ static int upload_windows(augb200_model* M, const augb200_window* w, const int* 
     if ((rc = M->d_obegin.reserve(M->ocap)) || (rc = M->d_oend.reserve(M->ocap)) || (rc = M->d_otype.reserve(M->ocap)) || (rc = M->d_otrunc.reserve(M->ocap))) return rc;
     if ((rc = M->h_obegin.reserve(M->ocap)) || (rc = M->h_oend.reserve(M->ocap)) || (rc = M->h_otype.reserve(M->ocap)) || (rc = M->h_otrunc.reserve(M->ocap))) return rc;
     if ((rc = M->d_hdr.reserve(count)) || (rc = M->h_hdr.reserve(count))) return rc;
-    if ((rc = M->d_counters.reserve(4 + M->waves.size())) || (rc = M->h_counters.reserve(4))) return rc;
+    if ((rc = M->d_counters.reserve(4)) || (rc = M->h_counters.reserve(4))) return rc;
     if (M->nsamp > 0) {
         long sc = 0; int maxL = 0;
         for (int i = 0; i < count; i++) { sc += M->h_wins.p[i].lay.samp_cap; maxL = std::max(maxL, M->h_wins.p[i].L); }
@@ -187,58 +181,53 @@ static int upload_windows(augb200_model* M, const augb200_window* w, const int* 
 }
 
 static int run_kernels(augb200_model* M, int count) {
-    if (M->waves.empty() || M->waves.back().first + M->waves.back().second != count) { M->waves.clear(); M->waves.push_back({0, count}); }
-    const size_t nwv = M->waves.size();
-    /* counters: [1] path states, [2] sampled-path states, [4 + w] window queue of wave w */
-    CK(cudaMemsetAsync(M->d_counters.p, 0, (4 + nwv) * sizeof(int), M->stream));
-    CK(cudaMemsetAsync(M->d_pool_used.p, 0, 2 * sizeof(unsigned long long), M->stream));
+    CK(cudaMemsetAsync(M->d_counters.p, 0, 4 * sizeof(int), M->stream));
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, M->device);
     CK(cudaMemcpyToSymbolAsync(c_model, &M->dm_dev, sizeof(DevModel), 0, cudaMemcpyHostToDevice, M->stream));
     /* resident sweep warps per SM: the kernel is instruction-fetch bound, more warps than this thrash the instruction cache */
     static int bps = 0;
     if (!bps) { const char* e = getenv("AUGB200_SWEEP_BLOCKS_PER_SM"); bps = e ? atoi(e) : 4; if (bps < 1) bps = 1; }
     const bool utr = M->hm.dm.utr != 0;
+    static int lockstep_mode = -1;
+    if (lockstep_mode < 0) { const char* e = getenv("AUGB200_SWEEP"); lockstep_mode = e && !strcmp(e, "lockstep") ? 1 : 0; }
     const size_t rng_off = M->rng_n && M->rand_pos >= M->rng_base ? (size_t)std::min<uint64_t>(M->rand_pos - M->rng_base, M->rng_n) : M->rng_n;
     const int nrng = (int)std::min<size_t>(M->rng_n - rng_off, 0x7fffffff);
     const uint32_t* d_rng = M->d_rng.p ? M->d_rng.p + rng_off : nullptr;
-    /* Several waves: even waves on the model's stream, odd waves on the second one.  Waves two apart share an arena and a stream, so they
-     * follow each other; neighbours overlap: the prep pass of wave w + 1 runs under the sweep of wave w (which leaves most issue slots idle),
-     * and the persistent CTAs of sweep w + 1 take over the SMs one by one as the last windows of sweep w finish. */
-    const bool two = nwv > 1;
-    if (two) { CK(cudaEventRecord(M->ev_fork, M->stream)); CK(cudaStreamWaitEvent(M->stream2, M->ev_fork, 0)); }
-    for (size_t wv = 0; wv < nwv; wv++) {
+    if (M->waves.empty() || M->waves.back().first + M->waves.back().second != count) { M->waves.clear(); M->waves.push_back({0, count}); }
+    while (M->wave_ev.size() + 1 < M->waves.size()) {
+        std::pair<cudaEvent_t, cudaEvent_t> e;
+        CK(cudaEventCreate(&e.first)); CK(cudaEventCreate(&e.second));
+        M->wave_ev.push_back(e);
+    }
+    for (size_t wv = 0; wv < M->waves.size(); wv++) {
         const int first = M->waves[wv].first, n = M->waves[wv].second;
         const WinDev* wins = M->d_wins.p + first;
-        cudaStream_t st = (two && (wv & 1)) ? M->stream2 : M->stream;
-        int* queue = M->d_counters.p + 4 + wv;
-        const int ar = two ? (int)(wv & 1) : 0;
-        if (wv >= 2) CK(cudaMemsetAsync(M->d_pool_used.p + ar, 0, sizeof(unsigned long long), st));      /* (after wave w - 2 on this stream) */
+        if (wv) CK(cudaMemsetAsync(M->d_counters.p, 0, sizeof(int), M->stream));      /* the window queue of the sweep; the output offsets run on */
+        CK(cudaMemsetAsync(M->d_pool_used.p, 0, sizeof(unsigned long long), M->stream));
         int gprep = std::min(n, sms * 8);
-        k_prep<<<gprep, PREP_BS, 0, st>>>(wins, n, M->pool_bytes ? M->d_pool.p + (size_t)ar * M->pool_half : nullptr, (unsigned long long)M->pool_bytes, M->d_pool_used.p + ar);
-        if (wv == 0) CK(cudaEventRecord(M->ev0, st));          /* the sweeps start here ... */
+        k_prep<<<gprep, PREP_BS, 0, M->stream>>>(wins, n, M->pool_bytes ? M->d_pool.p : nullptr, (unsigned long long)M->pool_bytes, M->d_pool_used.p);
+        CK(cudaEventRecord(wv ? M->wave_ev[wv - 1].first : M->ev0, M->stream));
         int gsweep = std::min((n + SWEEP_TEAMS - 1) / SWEEP_TEAMS, sms * bps);
         if (utr) gsweep = std::min(gsweep, sms * std::min(bps, 3));
-        if (M->nsamp > 0 && utr) k_sweep_sample_utr<<<gsweep, SWEEP_WARPS * 32, 0, st>>>(wins, n, queue, d_rng, nrng);
-        else if (M->nsamp > 0) k_sweep_sample<<<gsweep, SWEEP_WARPS * 32, 0, st>>>(wins, n, queue, d_rng, nrng);
-        else if (utr) k_sweep_utr<<<gsweep, SWEEP_WARPS * 32, 0, st>>>(wins, n, queue);
-        else k_sweep<<<gsweep, SWEEP_WARPS * 32, 0, st>>>(wins, n, queue);
-        if (wv + 1 == nwv) CK(cudaEventRecord(M->ev_join, st));      /* ... and the last one ends here */
-        k_backtrace<<<(n + 63) / 64, 64, 0, st>>>(wins, n);
-        k_pack<<<n, 64, 0, st>>>(wins, n, M->d_hdr.p + first, M->d_counters.p + 1, M->d_obegin.p, M->d_oend.p, M->d_otype.p, M->d_otrunc.p, M->ocap);
+        if (M->nsamp > 0 && utr) k_sweep_sample_utr<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(wins, n, M->d_counters.p, d_rng, nrng);
+        else if (M->nsamp > 0) k_sweep_sample<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(wins, n, M->d_counters.p, d_rng, nrng);
+        else if (!utr && lockstep_mode) {       /* EXPERIMENT (AUGB200_SWEEP=lockstep): lanes = windows kept in step per (column, kind) */
+            CK(lockstep_upload_model(&M->dm_dev, M->stream));
+            CK(lockstep_launch_sweep(wins, n, M->d_counters.p, std::min((n + 31) / 32, sms * 16), M->stream));
+        }
+        else if (utr) k_sweep_utr<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(wins, n, M->d_counters.p);
+        else k_sweep<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(wins, n, M->d_counters.p);
+        CK(cudaEventRecord(wv ? M->wave_ev[wv - 1].second : M->ev1, M->stream));
+        k_backtrace<<<(n + 63) / 64, 64, 0, M->stream>>>(wins, n);
+        k_pack<<<n, 64, 0, M->stream>>>(wins, n, M->d_hdr.p + first, M->d_counters.p + 1, M->d_obegin.p, M->d_oend.p, M->d_otype.p, M->d_otrunc.p, M->ocap);
         if (M->nsamp > 0) {
-            k_pack_samples<<<n, 64, 0, st>>>(wins, n, M->d_shdr.p + (size_t)first * M->nsamp, M->d_sstatus.p + 2 * (size_t)first, M->d_counters.p + 2,
-                                            M->d_sbegin.p, M->d_send.p, M->d_stype.p, M->d_strunc.p, M->scap);
+            k_pack_samples<<<n, 64, 0, M->stream>>>(wins, n, M->d_shdr.p + (size_t)first * M->nsamp, M->d_sstatus.p + 2 * (size_t)first, M->d_counters.p + 2,
+                                                     M->d_sbegin.p, M->d_send.p, M->d_stype.p, M->d_strunc.p, M->scap);
             M->launches += 1;
         }
         CK(cudaGetLastError());
         M->launches += 4;
     }
-    if (two) {
-        /* both streams join on the model's stream: whatever the caller enqueues there next sees every wave finished */
-        CK(cudaEventRecord(M->ev1, M->stream2)); CK(cudaStreamWaitEvent(M->stream, M->ev1, 0));
-        CK(cudaStreamWaitEvent(M->stream, M->ev_join, 0));
-    }
-    CK(cudaEventRecord(M->ev1, M->stream));
     return 0;
 }
 
@@ -281,8 +270,9 @@ static int fetch_results(augb200_model* M, int count, augb200_path* out, const i
             }
         for (int i = 0; i < count; i++) if (idx[i] == 0) M->rand_used0 = M->h_sstatus.p[2 * i + 1];
     }
-    /* the sweep kernels' share of the run: from the start of the first sweep to the end of the last (waves overlap, so the span is what counts) */
-    float ms = 0; if (cudaEventElapsedTime(&ms, M->ev0, M->ev_join) == cudaSuccess) M->sweep_ms += ms;
+    float ms = 0; if (cudaEventElapsedTime(&ms, M->ev0, M->ev1) == cudaSuccess) M->sweep_ms += ms;
+    for (size_t wv = 1; wv < M->waves.size() && wv - 1 < M->wave_ev.size(); wv++)
+        if (cudaEventElapsedTime(&ms, M->wave_ev[wv - 1].first, M->wave_ev[wv - 1].second) == cudaSuccess) M->sweep_ms += ms;
     /* append to the result store; pointers are fixed up by the caller once all sub-batches are in */
     size_t base = M->r_begin.size();
     M->r_begin.insert(M->r_begin.end(), M->h_obegin.p, M->h_obegin.p + total);
@@ -324,9 +314,7 @@ int augb200_model_create(const void* blob, size_t nbytes, int device, augb200_mo
     auto fail = [&](int code) { augb200_model_destroy(M); return code; };
     if (cudaSetDevice(device) != cudaSuccess) return fail(AUGB200_ERR_CUDA);
     if (cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(AUGB200_ERR_CUDA);
-    if (cudaStreamCreateWithFlags(&M->stream2, cudaStreamNonBlocking) != cudaSuccess) return fail(AUGB200_ERR_CUDA);
     if (cudaEventCreate(&M->ev0) != cudaSuccess || cudaEventCreate(&M->ev1) != cudaSuccess) return fail(AUGB200_ERR_CUDA);
-    if (cudaEventCreate(&M->ev_join) != cudaSuccess || cudaEventCreateWithFlags(&M->ev_fork, cudaEventDisableTiming) != cudaSuccess) return fail(AUGB200_ERR_CUDA);
     if (M->d_tab.reserve(M->hm.tab.size())) return fail(AUGB200_ERR_CUDA);
     if (cudaMemcpy(M->d_tab.p, M->hm.tab.data(), M->hm.tab.size() * sizeof(sc_t), cudaMemcpyHostToDevice) != cudaSuccess) return fail(AUGB200_ERR_CUDA);
     M->dm_dev = M->hm.rebased(M->d_tab.p);
@@ -349,9 +337,7 @@ void augb200_model_destroy(augb200_model* M) {
     M->d_sbegin.release(); M->d_send.release(); M->d_stype.release(); M->d_strunc.release(); M->h_sbegin.release(); M->h_send.release(); M->h_stype.release(); M->h_strunc.release();
     if (M->ev0) cudaEventDestroy(M->ev0);
     if (M->ev1) cudaEventDestroy(M->ev1);
-    if (M->ev_fork) cudaEventDestroy(M->ev_fork);
-    if (M->ev_join) cudaEventDestroy(M->ev_join);
-    if (M->stream2) cudaStreamDestroy(M->stream2);
+    for (auto& e : M->wave_ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (M->stream) cudaStreamDestroy(M->stream);
     delete M;
 }
@@ -388,11 +374,25 @@ static int decode_batch_impl(augb200_model* M, int32_t n, const augb200_window* 
     for (int i = 0; i < n; i++) order[i] = i;
     for (int pass = 0; pass < 2 && !order.empty(); pass++) {
         const bool generous = pass == 1;      /* second pass: windows whose default-sized structures overflowed */
-        /* a batch larger than the arena budget runs in waves that alternate between two arenas (upload_windows / run_kernels) */
+        size_t first = 0;
+        /* sub-batches under the arena budget, of (nearly) equal size: every sub-batch ends with a tail of windows that run at low
+         * occupancy, so two halves beat "as many as fit, then the rest" */
         const size_t cap = M->arena_budget - M->arena_budget / 8;
-        if ((rc = upload_windows(M, w, order.data(), (int)order.size(), generous, cap))) return rc;
-        if ((rc = run_kernels(M, (int)order.size()))) return rc;
-        if ((rc = fetch_results(M, (int)order.size(), out, order.data()))) return rc;
+        size_t all = 0;
+        for (int i : order) all += make_layout(w[i].length, M->hm.dm.C, generous, M->nsamp > 0, M->nsamp, M->hm.dm.utr != 0, M->hm.dm.softmask != 0).total;
+        const size_t nsub = all > cap ? (all + cap - 1) / cap : 1, target = (all + nsub - 1) / nsub;
+        while (first < order.size()) {
+            size_t bytes = 0; int count = 0;
+            while (first + count < order.size()) {
+                size_t t = make_layout(w[order[first + count]].length, M->hm.dm.C, generous, M->nsamp > 0, M->nsamp, M->hm.dm.utr != 0, M->hm.dm.softmask != 0).total;
+                if (count && (bytes + t > cap || bytes >= target)) break;
+                bytes += t; count++;
+            }
+            if ((rc = upload_windows(M, w, order.data() + first, count, generous))) return rc;
+            if ((rc = run_kernels(M, count))) return rc;
+            if ((rc = fetch_results(M, count, out, order.data() + first))) return rc;
+            first += count;
+        }
         std::vector<int> again;
         if (!generous) for (int i : order) if (out[i].status == AUGB200_ERR_CAPACITY) again.push_back(i);
         order.swap(again);

@@ -150,6 +150,9 @@ struct DevModel {
     double wm[4][4];
     /* softmasking (extrinsicinfo.cc:1696-1724): every lower-case run of the input is a nonexonpart hint; ln of its bonus */
     int softmask; sc_t nep_bonus;
+    /* --temperature T (types.cc:443-448): the forward summands of the sampling pass use transEmiProb^((8 - T) / 8) (LLDouble::heated,
+     * lldouble.cc:209-264); 1 = cold */
+    double heat;
     /* ---- UTR states (UtrModel), only when utr != 0 ---- */
     int utr;
     int tuw, tss_start, tss_end, tata_start, tata_end, d_tata_min, d_tata_max, tssup_k, dpc, boxlen, tts_spacing;

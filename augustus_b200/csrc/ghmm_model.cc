@@ -108,8 +108,13 @@ int HostModel::build(const void* blob, size_t nbytes) {
         if (m.softmask && !r.i32("extrinsic_malus_all_one")) { err = "extrinsic configurations with a malus are not supported"; return AUGB200_ERR_UNSUPPORTED; }
     }
     if (m.nc && m.softmask) { err = "nc states with softmasking are not supported yet"; return AUGB200_ERR_UNSUPPORTED; }
-    /* --temperature heats the forward summands of the sampling pass (LLDouble::heated, lldouble.cc:209-264); only 0 (cold) is decoded */
-    if (r.b.find("temperature") && r.i32("temperature") != 0) { err = "sampling temperature != 0 is not supported"; return AUGB200_ERR_UNSUPPORTED; }
+    /* --temperature heats the forward summands of the sampling pass (LLDouble::heated, lldouble.cc:209-264): exponent (8 - T) / 8 in the log domain */
+    m.heat = 1.0;
+    if (r.b.find("temperature")) {
+        const int T = r.i32("temperature");
+        if (T < 0 || T > 7) { err = "sampling temperature must be 0 .. 7"; return AUGB200_ERR_UNSUPPORTED; }
+        m.heat = (8.0 - T) / 8.0;
+    }
     m.dStateLen = m.d - 2 - m.dss_end - m.ass_start - 2 - m.ass_up;     /* intronmodel.cc:519-520 */
     if (m.dStateLen < 1) { err = "d too small"; return AUGB200_ERR_UNSUPPORTED; }
     /* columns around a GC-class boundary in which the SnippetProbs memo is restated (Sweep::snip_get): dStateLen columns before it every

@@ -89,9 +89,14 @@ struct SamplerT {
         AUGB_ROLLED
         for (int i = 0; i < n; i++) cum += exp(lp[i] - mx);
         const double z = ((double)r / 2147483647.0) * cum * 0.99999;
-        int res = -1, first = -1; double cs = 0;
+        /* the head of the sorted order is the first option that reaches the maximum (its term is exp(0) = 1): nearly every stop ends here */
+        int first = 0;
         AUGB_ROLLED
-        for (int rk = 0; rk < n && res < 0; rk++) {
+        for (int i = n - 1; i >= 0; i--) if (lp[i] == mx) first = i;
+        int res = -1; double cs = exp(lp[first] - mx);
+        if (z < cs) res = first;
+        AUGB_ROLLED
+        for (int rk = 1; rk < n && res < 0; rk++) {
             /* the option of rank rk */
             int sel = -1;
             AUGB_ROLLED
@@ -101,7 +106,6 @@ struct SamplerT {
                 for (int k = 0; k < n; k++) before += (lp[k] > lp[i] || (lp[k] == lp[i] && (ord[k] < ord[i] || (ord[k] == ord[i] && k < i)))) ? 1 : 0;
                 if (before == rk) sel = i;
             }
-            if (rk == 0) first = sel;
             cs += exp(lp[sel] - mx);
             if (z < cs) res = sel;
         }
@@ -112,17 +116,24 @@ struct SamplerT {
     /* one step of a self-loop state at column c (> 0), a column of its chain that received entries: list the ancestors at c - 1 in
      * index order (igenicmodel.cc:247-261, intronmodel.cc:786-820), draw with the rand() value r.  Returns the chosen predecessor
      * state, -1 if there is no option.  Everything is local to the calling lane: 32 lanes take 32 consecutive stops of a run. */
-    AUGB_D int chain_stop(int state, int c, uint32_t r, double* add) const {
+    AUGB_D int chain_stop(int state, int c, uint32_t r, double* add, const FChainCP* prev = nullptr) const {
         const SW& S = *sw; const DevModel* m = S.m;
         const StateDesc& sd = m->st[state];
         const sc_t* T = m->trans + (size_t)S.w.gc[c] * m->S * m->S;
         double lpv[MAXANC]; int ordv[MAXANC], prd[MAXANC]; int n = 0;
+        const int elo = S.w.evstart[c - 1], ehi = S.w.evstart[c];          /* the cells of column c - 1 */
         AUGB_ROLLED
         for (int i = 0; i < sd.nanc; i++) {
             const int a = sd.anc[i]; const sc_t t = T[a * m->S + state];
             if (isneg(t)) continue;
-            const double f = S.lookupF(a, c - 1);
-            if (f > -1e300) { lpv[n] = f + SW::sc2d(t); ordv[n] = i; prd[n] = a; n++; }
+            double f = -1e308;
+            if (a == state && prev) f = prev->ft + S.te2d(S.chainAv(sd.chain, c - 1));       /* the state itself: the change point before this stop (no search) */
+            else if (m->st[a].chain >= 0) f = S.chain_fvalue(m->st[a].chain, c - 1);
+            else {
+                AUGB_ROLLED
+                for (int k = elo; k < ehi; k++) if (S.w.ev[k].state == a) { f = S.w.evF[k]; break; }
+            }
+            if (f > -1e300) { lpv[n] = f + S.te2d(t); ordv[n] = i; prd[n] = a; n++; }
         }
         if (n == 0) return -1;
         const int k = pick_small(lpv, ordv, n, r, add);
@@ -186,7 +197,7 @@ struct SamplerT {
                             if (valid && c > 0) {
                                 const long d = (long)cursor + (base - c);
                                 if (d >= nrng) fail = true;
-                                else { mypred = chain_stop(state, c, rng[d], &myadd); if (mypred < 0) fail = true; }
+                                else { mypred = chain_stop(state, c, rng[d], &myadd, i > 0 ? &cp[i - 1] : nullptr); if (mypred < 0) fail = true; }
                             }
                             const bool stopper = !valid || c == 0 || fail || mypred != state;
                             const unsigned sb = wballot(stopper);

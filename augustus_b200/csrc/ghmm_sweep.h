@@ -106,6 +106,9 @@ struct SweepT {
     }
 
     AUGB_D static double sc2d(sc_t v) { return (double)v * (1.0 / (double)((sc_t)1 << FRAC_BITS)); }
+    /* ln of a heated transition x emission product: LLDouble::heated() raises it to (8 - temperature) / 8 before it enters a forward sum or
+     * an option list (exonmodel.cc:1095, intronmodel.cc:610, igenicmodel.cc:251, utrmodel.cc:978, ncmodel.cc:274); heat = 1 leaves the bits alone */
+    AUGB_D double te2d(sc_t v) const { return sc2d(v) * m->heat; }
     /* ln forward[e][a] (-1e308 = zero) */
     AUGB_D double chain_fvalue(int ch, int e) const {
         int n = ws->fcp_n[ch];
@@ -116,7 +119,7 @@ struct SweepT {
         if (cp[hi].col <= e) lo = hi;
         AUGB_ROLLED
         while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (cp[mid].col <= e) lo = mid; else hi = mid - 1; }
-        return cp[lo].ft + sc2d(chainAv(ch, e));
+        return cp[lo].ft + te2d(chainAv(ch, e));
     }
     AUGB_D double lookupF(int a, int e) const {
         int ch = m->st[a].chain;
@@ -163,7 +166,7 @@ struct SweepT {
         if (ch < 0) return;
         feed_merge(ch, s, V + delta);
         ws->any_pend |= 1 << ch;          /* bit per chain with a pending entry */
-        if (FWD) ws->pend_f[ch].add(F + sc2d(delta));
+        if (FWD) ws->pend_f[ch].add(F + te2d(delta));
     }
     /* the candidate lists later columns look a new cell (j, s) up in: returns the first list (-1: none), *l2 a second one (UTR) */
     AUGB_D int cell_lists(int j, int s, sc_t* G1, int* l2, sc_t* G2) const {
@@ -238,7 +241,7 @@ struct SweepT {
                 AUGB_ROLLED
                 while (fm) {
                     const int b = wffs(fm); fm &= fm - 1;
-                    if (lane == b) { feed_merge(fch, cs, cV + fdelta); ws->any_pend |= 1 << fch; ws->pend_f[fch].add(cF + sc2d(fdelta)); }
+                    if (lane == b) { feed_merge(fch, cs, cV + fdelta); ws->any_pend |= 1 << fch; ws->pend_f[fch].add(cF + te2d(fdelta)); }
                     wsync();
                 }
             } else {
@@ -658,11 +661,11 @@ struct SweepT {
                 } else general = true;
             }
             if (wballot(valid && general)) { if (valid && general) nep = notEndPart(st, bos, right, frameOfRight); }
-            if (FWD && opt) push_opt(valid && !isneg(nep), pf + sc2d(t + ep + nep), -(bos * 128 + (127 - a)), a, eop);
+            if (FWD && opt) push_opt(valid && !isneg(nep), pf + te2d(t + ep + nep), -(bos * 128 + (127 - a)), a, eop);
             if (valid && !isneg(nep)) {
                 sc_t sc = pv + (t + ep + nep); int key = bos * 128 + (127 - a);
                 if (sc > best || (sc == best && key > bkey)) { best = sc; bkey = key; bpred = a; bbase = eop; }
-                if (FWD && !opt) fl.add(pf + sc2d(t + ep + nep));
+                if (FWD && !opt) fl.add(pf + te2d(t + ep + nep));
             }
         }
         }
@@ -683,8 +686,8 @@ struct SweepT {
                 const bool use = ok && !stop;
                 sc_t sc = pv + (t + ep + nep0); int key = 127 - a;
                 if (use && li == 0 && (sc > best || (sc == best && key > bkey))) { best = sc; bkey = key; bpred = a; bbase = -1; }
-                if (FWD && !opt && use && li == 0) fl.add(sc2d(pv) + sc2d(t + ep + nep0));
-                if (FWD && opt) push_opt(use && li == 0, sc2d(pv) + sc2d(t + ep + nep0), -(127 - a), a, -1);
+                if (FWD && !opt && use && li == 0) fl.add(sc2d(pv) + te2d(t + ep + nep0));
+                if (FWD && opt) push_opt(use && li == 0, sc2d(pv) + te2d(t + ep + nep0), -(127 - a), a, -1);
             }
         }
         if (FWD && opt) return;
@@ -741,8 +744,8 @@ struct SweepT {
                 sc_t pv = lookupV(a, eop); if (isneg(pv)) continue;
                 sc_t pp = pv + (t + emi);
                 if (pp > best) { best = pp; bpred = a; }
-                if (FWD && !opt) fl.add(lookupF(a, eop) + sc2d(t + emi));
-                if (FWD && opt) push_opt(lane == 0, lookupF(a, eop) + sc2d(t + emi), i, a, eop);
+                if (FWD && !opt) fl.add(lookupF(a, eop) + te2d(t + emi));
+                if (FWD && opt) push_opt(lane == 0, lookupF(a, eop) + te2d(t + emi), i, a, eop);
             }
             if (!isneg(best) && !(FWD && opt)) emit(j, s, best, bpred, eop, FWD ? fl.value() : 0.0);
         }
@@ -759,7 +762,7 @@ struct SweepT {
             if (hi < 0 || cl[lo].col != want || s < 0) return;
             const sc_t* P = parr(cls, PA_PI);
             sc_t t = TR(cl[lo].state, s);
-            push_opt(lane == 0 && !isneg(t), w.clF(list)[lo] + sc2d(t + (P[j + 1] - P[want + 1])), 0, cl[lo].state, want);
+            push_opt(lane == 0 && !isneg(t), w.clF(list)[lo] + te2d(t + (P[j + 1] - P[want + 1])), 0, cl[lo].state, want);
             return;
         }
         Cand c = w.cl(list)[cur]; double cf = FWD ? w.clF(list)[cur] : 0.0;
@@ -772,7 +775,7 @@ struct SweepT {
         sc_t emi = P[j + 1] - P[eop + 1];
         sc_t t = TR(c.state, s);
         if (isneg(t)) return;
-        emit(j, s, c.V + (t + emi), c.state, eop, cf + sc2d(t + emi));
+        emit(j, s, c.V + (t + emi), c.state, eop, cf + te2d(t + emi));
     }
     /* ------------------------------------------------------------ SnippetProbs memo near GC-class boundaries
      *
@@ -939,8 +942,8 @@ struct SweepT {
                                 } else if (FWD && opt && (w.mask[j] & MB_SLOW)) seq = snipx_lookup(dir, j, j - begin + 1, seq);
                                 sc_t sc = c.V + (t + (ld + seq));
                                 if (sc > best || (sc == best && e > bkey)) { best = sc; bkey = e; bpred = c.state; }
-                                if (FWD && !opt) fl.add(w.clF(list)[i] + sc2d(t + (ld + seq)));
-                                if (FWD && opt) { okopt = true; olp = w.clF(list)[i] + sc2d(t + (ld + seq)); oe = e; opred = c.state; }
+                                if (FWD && !opt) fl.add(w.clF(list)[i] + te2d(t + (ld + seq)));
+                                if (FWD && opt) { okopt = true; olp = w.clF(list)[i] + te2d(t + (ld + seq)); oe = e; opred = c.state; }
                             }
                         }
                     }
@@ -1060,11 +1063,11 @@ struct SweepT {
                 }
             }
             more = wballot(below) == 0;
-            if (FWD && opt) push_opt(valid, pf + sc2d(te), -(eop * 128 + (127 - a)), a, eop);
+            if (FWD && opt) push_opt(valid, pf + te2d(te), -(eop * 128 + (127 - a)), a, eop);
             if (valid) {
                 const sc_t sc = pv + te; const int key = eop * 128 + (127 - a);
                 if (sc > best || (sc == best && key > bkey)) { best = sc; bkey = key; bpred = a; bbase = eop; }
-                if (FWD && !opt) fl.add(pf + sc2d(te));
+                if (FWD && !opt) fl.add(pf + te2d(te));
             }
         }
         if (u.trunc && lm < 0) {
@@ -1097,11 +1100,11 @@ struct SweepT {
                 for (int ia = 0; ia < st.nanc; ia++) {
                     const int a = st.anc[ia]; const sc_t pv = m->init[a], t = TR(a, s);
                     const bool ok = valid && !isneg(pv) && !isneg(t);
-                    if (FWD && opt) push_opt(ok, sc2d(pv) + sc2d(t + te), -(eop * 128 + (127 - a)), a, eop);
+                    if (FWD && opt) push_opt(ok, sc2d(pv) + te2d(t + te), -(eop * 128 + (127 - a)), a, eop);
                     if (ok) {
                         const sc_t sc = pv + (t + te); const int key = eop * 128 + (127 - a);
                         if (sc > best || (sc == best && key > bkey)) { best = sc; bkey = key; bpred = a; bbase = eop; }
-                        if (FWD && !opt) fl.add(sc2d(pv) + sc2d(t + te));
+                        if (FWD && !opt) fl.add(sc2d(pv) + te2d(t + te));
                     }
                 }
             }

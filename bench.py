@@ -688,6 +688,10 @@ def main():
             assert not samp5[1].any()
             sec = {"workload": "%d x 50 kb windows, --sample=100 --alternatives-from-sampling=true (Viterbi + forward + 99 sampled paths per window), 1 GPU, e2e from host buffers through augb200_decode_batch_sampling" % n5,
                    "value": n5 * WINDOW_LEN / 1e6 / dt5, "unit": "Mbp/s", "sampled_paths": int(len(samp5[0])), "kernel_ms": dec.last_sweep_ms}
+            first5, total5 = dec.sample_first_occurrence(n5, 100)
+            uniq5 = int((first5 == np.arange(99)[None, :]).sum())
+            sec["dedup"] = {"unique_sampled_paths": uniq5, "path_states_all_samples": total5, "path_states_copied_to_host": int(len(samp5[4])),
+                            "note": "k_pack_samples finds repeated state paths of a window on the device (SURVEY.md 8f next-1): only first occurrences cross PCIe"}
             if not args.no_cpu_baseline:
                 sec["cpu_baseline"] = calibrated_reference(n_per_proc=1, extra_args=("--sample=100", "--alternatives-from-sampling=true"))
             line["secondary"]["config5_sampling"] = sec

@@ -136,9 +136,9 @@ int augb200_decode_batch_multi(augb200_model* const* models, int32_t n_models, i
 
 /* Device-resident variant used for kernel-only timing: stage the windows once, run the kernels any
  * number of times (no host<->device traffic in between), fetch the paths at the end.  DNA and window
- * descriptors of the whole batch stay on the device; the per-window workspaces come from two arenas that
+ * descriptors of the whole batch stay on the device; the per-window workspaces come from one arena that
  * equal-sized waves of windows use in turn, so the batch may be larger than the device memory left for
- * workspaces (10 000 x 50 kb = three waves on a 180 GB part; augb200_decode_batch works the same way). */
+ * workspaces (10 000 x 50 kb = two waves on a 180 GB part). */
 int augb200_stage_batch(augb200_model* m, int32_t n, const augb200_window* windows);
 int augb200_run_staged(augb200_model* m);                 /* asynchronous on the model's stream    */
 int augb200_fetch_staged(augb200_model* m, augb200_path* out);
@@ -146,8 +146,7 @@ int augb200_fetch_staged(augb200_model* m, augb200_path* out);
 void* augb200_model_stream(augb200_model* m);
 /* number of kernel launches issued by the last run / decode call */
 int64_t augb200_last_launch_count(const augb200_model* m);
-/* device milliseconds from the start of the first sweep kernel to the end of the last one during the last run (CUDA events; the waves of a
- * batch that does not fit the workspace arena overlap: the prep pass of a wave runs under the sweep of the wave before) */
+/* device milliseconds spent in the sweep kernel during the last run (CUDA events on the model's stream) */
 double augb200_last_sweep_ms(const augb200_model* m);
 
 /* The contiguous store that every augb200_path of the last decode / fetch call points into (all windows'

@@ -47,3 +47,33 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def heated():
+    """ref_samples_heated.json.gz: the reference's 99 sampled paths of both sequences of example.fa with --temperature=3 (LLDouble::heated in
+    the forward sums; one process, the second sequence continues the rand() stream of the first)."""
+    fa = os.path.join(HERE, "example.fa")
+    with tempfile.TemporaryDirectory() as td:
+        pf, blob = os.path.join(td, "p"), os.path.join(td, "b")
+        subprocess.run([AUGDUMP, "--species=human", "--softmasking=0", "--sample=100", "--temperature=3", fa], env=dict(ENV, AUGDUMP_PATH=pf, AUGDUMP_PARAMS=blob),
+                       check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        with lzma.open(os.path.join(HERE, "human_t3.params.xz"), "wb", preset=9) as f:       # the human blob with temperature = 3
+            f.write(open(blob, "rb").read())
+        seqs = []
+        for line in open(pf):
+            t = line.split()
+            if t[0] == "seq":
+                seqs.append({"name": t[1], "samples": []})
+            elif t[0] == "sample":
+                seqs[-1]["samples"].append([])
+            elif t[0] == "sstate":
+                seqs[-1]["samples"][-1].append([int(v) for v in t[1:5]])
+    for s in seqs:
+        s["samples"] = [condense(x) for x in s["samples"]]
+    with gzip.open(os.path.join(HERE, "ref_samples_heated.json.gz"), "wt") as f:
+        json.dump({"command": "augustus --species=human --softmasking=0 --sample=100 --temperature=3 example.fa (one process, both sequences)",
+                   "sequences": seqs}, f, separators=(",", ":"))
+
+
+if __name__ == "__main__" and "--heated" in sys.argv:
+    heated()

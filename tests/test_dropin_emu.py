@@ -118,7 +118,6 @@ def test_ragged_input_softmasked_runs_unknown_bases_tiny_sequences(tmp_path):
 
 
 @pytest.mark.parametrize("args,needle", [
-    (["--temperature=3", "--sample=50"], "sampling temperature != 0 is not supported"),       # LLDouble::heated in the sampling pass
     (["--genemodel=intronless"], "not exportable"),                                          # no intron tables in that model
     (["--genemodel=exactlyone"], "duplicate state role"),                                    # two intergenic states
     (["--genemodel=bacterium"], "overlap mode"),
@@ -130,3 +129,12 @@ def test_configurations_outside_the_scope_end_with_an_error_not_with_other_outpu
     r = subprocess.run([EMU, "--species=human", "--softmasking=0"] + args + [EXAMPLE], env=env, capture_output=True, text=True, timeout=600)
     assert needle in r.stderr + r.stdout
     assert "\tCDS\t" not in r.stdout
+
+
+def test_sampling_temperature_gff_identical():
+    """--temperature=3 (heated forward sums, LLDouble::heated): posterior probabilities and alternative transcripts of the GFF through the
+    twin == the reference (round 1 refused the option)."""
+    args = ["--species=human", "--softmasking=0", "--sample=100", "--alternatives-from-sampling=true", "--temperature=3"]
+    want, _ = _run(REF, args)
+    got, _ = _run(EMU, args)
+    assert any("\tCDS\t" in l for l in want) and got == want

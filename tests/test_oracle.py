@@ -177,3 +177,23 @@ def test_kernel_source_on_host_edge_cases(oracle, emu):
         assert e["status"] == 0 and o["n"] >= 0, len(dna)
         assert e["states"] == o["condensed"], len(dna)
         assert e["log_prob"] == o["log_prob"]
+
+
+def test_heated_sampling_matches_the_reference():
+    """--temperature=3: the forward summands are transEmiProb^(5/8) (LLDouble::heated, lldouble.cc:209-264; exonmodel.cc:1095 and the other
+    state models).  The kernel source raises them in the log domain; all 99 sampled paths of both sequences of example.fa equal the
+    reference's (one process: the second sequence continues the rand() stream), one lane and 32 lanes."""
+    import gzip
+    import json
+    ref = json.load(gzip.open(util.GOLDEN + "/ref_samples_heated.json.gz", "rt"))["sequences"]
+    blob = util.blob_bytes("human_t3")                  # the human parameters exported with --temperature=3
+    dnas = [s for _, s in util.read_fasta(util.GOLDEN + "/example.fa")]
+    for simt32 in (False, True):
+        emu = util.HostEmu(blob, simt32=simt32)
+        pos = 0
+        for dna, r in zip(dnas, ref):
+            got, used = util.hostemu_samples_at(emu, dna, 99, pos)
+            assert got == [[tuple(x) for x in s] for s in r["samples"]]
+            pos += used
+    cold = util.HostEmu(util.blob_bytes()).sample(dnas[1], 99)["samples"]
+    assert [s["states"] for s in cold] != [[tuple(x) for x in s] for s in ref[1]["samples"]]          # the temperature does change the paths

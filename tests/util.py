@@ -268,3 +268,34 @@ class HostEmu:
                     E[:, s] = chV[:, c]
             res["cells"] = E
         return res
+
+
+def blob_with_int(blob: bytes, name: str, value: int) -> bytes:
+    """Copy of an AUGB2PAR blob with the int32 scalar `name` set to `value` (e.g. the sampling temperature)."""
+    import struct
+    b = bytearray(blob)
+    n_entries = struct.unpack_from("<I", b, 12)[0]
+    for i in range(n_entries):
+        o = 16 + i * 96
+        if bytes(b[o:o + 40]).split(b"\0")[0] == name.encode():
+            off = struct.unpack_from("<Q", b, o + 80)[0]
+            struct.pack_into("<i", b, off, value)
+            return bytes(b)
+    raise KeyError(name)
+
+
+def hostemu_samples_at(emu, dna, nsamples, rand_pos):
+    """Sampled paths of the host build with the rand() stream started `rand_pos` draws in; returns (paths, draws consumed)."""
+    emu.lib.hostemu_sample_at.restype = ctypes.c_int
+    emu.lib.hostemu_sample_at.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 7 + [ctypes.c_uint64, ctypes.c_void_p]
+    L = len(dna); cap = nsamples * (L // 8 + 64)
+    sb, se = np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=np.int32)
+    st, tr = np.zeros(cap, dtype=np.uint8), np.zeros(cap, dtype=np.uint8)
+    cnt, lp, status, used = np.zeros(nsamples, dtype=np.int32), np.zeros(nsamples), ctypes.c_int32(), ctypes.c_int32()
+    emu.lib.hostemu_sample_at(emu.m, dna.encode(), L, None, nsamples, cap, sb.ctypes.data, se.ctypes.data, st.ctypes.data, tr.ctypes.data,
+                              cnt.ctypes.data, lp.ctypes.data, ctypes.byref(status), rand_pos, ctypes.byref(used))
+    assert status.value == 0
+    out, p = [], 0
+    for k in range(nsamples):
+        c = int(cnt[k]); out.append([(int(st[p + q]), int(sb[p + q]), int(se[p + q]), int(tr[p + q])) for q in range(c)]); p += c
+    return out, used.value
