@@ -15,7 +15,6 @@
 #include "../../include/augb200.h"
 #include "ghmm_kernels.cuh"
 #include "ghmm_model.h"
-#include "ghmm_lockstep.h"
 
 using namespace augb;
 
@@ -188,8 +187,6 @@ static int run_kernels(augb200_model* M, int count) {
     static int bps = 0;
     if (!bps) { const char* e = getenv("AUGB200_SWEEP_BLOCKS_PER_SM"); bps = e ? atoi(e) : 4; if (bps < 1) bps = 1; }
     const bool utr = M->hm.dm.utr != 0;
-    static int lockstep_mode = -1;
-    if (lockstep_mode < 0) { const char* e = getenv("AUGB200_SWEEP"); lockstep_mode = e && !strcmp(e, "lockstep") ? 1 : 0; }
     const size_t rng_off = M->rng_n && M->rand_pos >= M->rng_base ? (size_t)std::min<uint64_t>(M->rand_pos - M->rng_base, M->rng_n) : M->rng_n;
     const int nrng = (int)std::min<size_t>(M->rng_n - rng_off, 0x7fffffff);
     const uint32_t* d_rng = M->d_rng.p ? M->d_rng.p + rng_off : nullptr;
@@ -211,10 +208,6 @@ static int run_kernels(augb200_model* M, int count) {
         if (utr) gsweep = std::min(gsweep, sms * std::min(bps, 3));
         if (M->nsamp > 0 && utr) k_sweep_sample_utr<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(wins, n, M->d_counters.p, d_rng, nrng);
         else if (M->nsamp > 0) k_sweep_sample<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(wins, n, M->d_counters.p, d_rng, nrng);
-        else if (!utr && lockstep_mode) {       /* EXPERIMENT (AUGB200_SWEEP=lockstep): lanes = windows kept in step per (column, kind) */
-            CK(lockstep_upload_model(&M->dm_dev, M->stream));
-            CK(lockstep_launch_sweep(wins, n, M->d_counters.p, std::min((n + 31) / 32, sms * 16), M->stream));
-        }
         else if (utr) k_sweep_utr<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(wins, n, M->d_counters.p);
         else k_sweep<<<gsweep, SWEEP_WARPS * 32, 0, M->stream>>>(wins, n, M->d_counters.p);
         CK(cudaEventRecord(wv ? M->wave_ev[wv - 1].second : M->ev1, M->stream));

@@ -17,9 +17,7 @@ namespace augb {
 #ifndef AUGB_TEAM
 #define AUGB_TEAM 32
 #endif
-/* AUGB_SCALAR_DEVICE (ghmm_lockstep.cu): the one-lane form of the routines compiled for the device — every THREAD owns a window, the
- * lanes of a warp are 32 windows kept in step by the driver; no collectives inside the routines */
-#if (defined(__CUDA_ARCH__) && !defined(AUGB_SCALAR_DEVICE)) || defined(AUGB_SIMT32)
+#if defined(__CUDA_ARCH__) || defined(AUGB_SIMT32)
 #define AUGB_SIMT 1
 #else
 #define AUGB_SIMT 0
