@@ -188,7 +188,10 @@ struct ChainCP {
 };
 
 /* forward (sum) counterpart of a chain: ln F[col][chain] = ft + A[col] from column col on, until the next entry */
-struct FChainCP { int32_t col; int32_t pad; double ft; };
+/* rstay / add are filled after the forward pass (Sampler::prepare_stops): a sampling walk that stands in the chain at column col stays in
+ * it iff its rand() value is <= rstay, and then adds `add` to the log-probability of the path (STOP_COMPLEX: the stop is evaluated in full) */
+struct FChainCP { int32_t col; uint32_t rstay; double ft; double add; };
+constexpr uint32_t STOP_COMPLEX = 0xffffffffu;
 
 /* one (predecessor, predecessor end) option of a sampling step: OptionListItem (vitmatrix.hh:748-770) */
 struct SampleOpt { double lp; int32_t ord /* insertion order in the reference's loops */, pred, eop, pad; };

@@ -113,14 +113,13 @@ struct SamplerT {
         *add = lp[res] - mx - log(cum);
         return res;
     }
-    /* one step of a self-loop state at column c (> 0), a column of its chain that received entries: list the ancestors at c - 1 in
-     * index order (igenicmodel.cc:247-261, intronmodel.cc:786-820), draw with the rand() value r.  Returns the chosen predecessor
-     * state, -1 if there is no option.  Everything is local to the calling lane: 32 lanes take 32 consecutive stops of a run. */
-    AUGB_D int chain_stop(int state, int c, uint32_t r, double* add, const FChainCP* prev = nullptr) const {
+    /* The options of a self-loop state at column c (> 0), a column of its chain that received entries: the ancestors at c - 1 in index
+     * order (igenicmodel.cc:247-261, intronmodel.cc:786-820).  Everything is local to the calling lane.  Returns the number of options. */
+    AUGB_D int chain_options(int state, int c, double* lpv, int* ordv, int* prd, const FChainCP* prev) const {
         const SW& S = *sw; const DevModel* m = S.m;
         const StateDesc& sd = m->st[state];
         const sc_t* T = m->trans + (size_t)S.w.gc[c] * m->S * m->S;
-        double lpv[MAXANC]; int ordv[MAXANC], prd[MAXANC]; int n = 0;
+        int n = 0;
         const int elo = S.w.evstart[c - 1], ehi = S.w.evstart[c];          /* the cells of column c - 1 */
         AUGB_ROLLED
         for (int i = 0; i < sd.nanc; i++) {
@@ -135,9 +134,58 @@ struct SamplerT {
             }
             if (f > -1e300) { lpv[n] = f + S.te2d(t); ordv[n] = i; prd[n] = a; n++; }
         }
+        return n;
+    }
+    /* one step of a self-loop state at such a column: draw with the rand() value r.  Returns the chosen predecessor state, -1 if there is
+     * no option.  32 lanes take 32 consecutive stops of a run. */
+    AUGB_D int chain_stop(int state, int c, uint32_t r, double* add, const FChainCP* prev = nullptr) const {
+        double lpv[MAXANC]; int ordv[MAXANC], prd[MAXANC];
+        const int n = chain_options(state, c, lpv, ordv, prd, prev);
         if (n == 0) return -1;
         const int k = pick_small(lpv, ordv, n, r, add);
         return prd[k];
+    }
+    /* After the forward pass, once per window: what every walk would recompute at a stop does not depend on the walk.  If the head of the
+     * sorted order is the state itself (its term is exp(0) = 1), OptionsList::sample stays in the state iff
+     *     (double)r / 2147483647.0 * cumprob * 0.99999 < 1.0,
+     * which is monotone in the rand() value r: the largest r that satisfies it (found with that very expression) and the ln-probability
+     * of staying are stored in the change point, and a walk compares its draw with it.  Other stops stay STOP_COMPLEX. */
+    AUGB_D void prepare_stops() {
+        SW& S = *sw; const DevModel* m = S.m;
+        AUGB_ROLLED
+        for (int ch = 0; ch < NCHAIN; ch++) {
+            const int state = m->chain_state[ch]; const int n = S.ws->fcp_n[ch];
+            if (state < 0 || n <= 0) continue;
+            FChainCP* cp = S.w.fcp(ch);
+            AUGB_ROLLED
+            for (int i = lane; i < n; i += AUGB_NLANES) {
+                const int c = cp[i].col;
+                if (c <= 0) continue;
+                double lpv[MAXANC]; int ordv[MAXANC], prd[MAXANC];
+                const int k = chain_options(state, c, lpv, ordv, prd, i > 0 ? &cp[i - 1] : nullptr);
+                if (k <= 0) continue;
+                double mx = -1e308;
+                AUGB_ROLLED
+                for (int q = 0; q < k; q++) mx = lpv[q] > mx ? lpv[q] : mx;
+                int first = 0;
+                AUGB_ROLLED
+                for (int q = k - 1; q >= 0; q--) if (lpv[q] == mx) first = q;
+                if (prd[first] != state) continue;
+                double cum = 0;
+                AUGB_ROLLED
+                for (int q = 0; q < k; q++) cum += exp(lpv[q] - mx);
+                /* largest r in [0, 2^31 - 1] with z(r) < 1 */
+                double est = 2147483647.0 / (cum * 0.99999);
+                long r0 = est >= 2147483647.0 ? 2147483647L : (long)est;
+                AUGB_ROLLED
+                while (r0 >= 0 && !(((double)r0 / 2147483647.0) * cum * 0.99999 < 1.0)) r0--;
+                AUGB_ROLLED
+                while (r0 < 2147483647L && (((double)(r0 + 1) / 2147483647.0) * cum * 0.99999 < 1.0)) r0++;
+                if (r0 < 0) continue;                   /* (never stays: leave it to the full evaluation) */
+                cp[i].rstay = (uint32_t)r0; cp[i].add = lpv[first] - mx - log(cum);
+            }
+        }
+        wsync();
     }
 
     /* all paths of one window */
@@ -145,6 +193,7 @@ struct SamplerT {
         SW& S = *sw; const DevModel* m = S.m; const int L = S.L;
         lane = lane_id(); cursor = 0;
         S.opt = sc.opt; S.nopt = sc.nopt; S.opt_cap = sc.opt_cap;
+        if (nsamples > 1) prepare_stops();
         int used = 0, status = 0;
         const bool alln = (*S.w.flags & WF_ALLN) != 0;
         AUGB_ROLLED
@@ -197,6 +246,7 @@ struct SamplerT {
                             if (valid && c > 0) {
                                 const long d = (long)cursor + (base - c);
                                 if (d >= nrng) fail = true;
+                                else if (cp[i].rstay != STOP_COMPLEX && rng[d] <= cp[i].rstay) myadd = cp[i].add;       /* stays (prepare_stops) */
                                 else { mypred = chain_stop(state, c, rng[d], &myadd, i > 0 ? &cp[i - 1] : nullptr); if (mypred < 0) fail = true; }
                             }
                             const bool stopper = !valid || c == 0 || fail || mypred != state;

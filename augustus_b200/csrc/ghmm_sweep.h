@@ -284,7 +284,7 @@ struct SweepT {
                 if (ws->fcp_n[ch] > 0) t.add(ws->ftilde[ch]);
                 int nf = ws->fcp_n[ch];
                 if (nf >= w.fcp_cap) ws->status = 8;
-                else { FChainCP c; c.col = j + 1; c.pad = 0; c.ft = t.value(); w.fcp(ch)[nf] = c; ws->fcp_n[ch] = nf + 1; ws->ftilde[ch] = c.ft; }
+                else { FChainCP c; c.col = j + 1; c.rstay = STOP_COMPLEX; c.add = 0; c.ft = t.value(); w.fcp(ch)[nf] = c; ws->fcp_n[ch] = nf + 1; ws->ftilde[ch] = c.ft; }
                 ws->pend_f[ch].clear();
             }
         }
@@ -1199,7 +1199,7 @@ struct SweepT {
             if (ch >= 0) {
                 if (lane == 0) {
                     ChainCP c; c.col = 0; c.pred = -1; c.tilde = v; w.cp(ch)[0] = c; ws->cp_n[ch] = 1; ws->tilde[ch] = v;
-                    if (FWD) { FChainCP f; f.col = 0; f.pad = 0; f.ft = sc2d(v); w.fcp(ch)[0] = f; ws->fcp_n[ch] = 1; ws->ftilde[ch] = f.ft; }
+                    if (FWD) { FChainCP f; f.col = 0; f.rstay = STOP_COMPLEX; f.add = 0; f.ft = sc2d(v); w.fcp(ch)[0] = f; ws->fcp_n[ch] = 1; ws->ftilde[ch] = f.ft; }
                 }
                 wsync();
             } else {

@@ -395,6 +395,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the config 3 / 4 / 5 side measurements")
     ap.add_argument("--dropin-windows", type=int, default=2, help="chr2L windows of the drop-in end-to-end leg (0 = skip the leg)")
+    ap.add_argument("--assume-rates", default="", help="testing only: comma-separated per-rank sweep rates to deal by instead of the measured ones")
     ap.add_argument("--no-balance", action="store_true", help="keep the block-cyclic deal (do not re-deal by measured sweep rate)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -548,7 +549,7 @@ def main():
     torch.cuda.synchronize()
     dec.fetch_staged()
     rate0 = per_rank(len(wins_b) / max(dec.last_sweep_ms, 1e-3))
-    deal = deal_windows(world, M, None if (args.no_balance or world == 1) else rate0)
+    deal = deal_windows(world, M, None if (args.no_balance or world == 1) else ([float(x) for x in args.assume_rates.split(",")] if args.assume_rates else rate0))
     if deal[rank] != my_idx:
         have = dict(zip(my_idx, wins_b))
         extra = [g for g in deal[rank] if g not in have]
