@@ -265,3 +265,21 @@ def test_sampled_paths_are_deduplicated_on_the_device(dec):
     assert total == sum(len(s.states) for ss in samples for s in ss)
     raw_v, raw_s = dec.decode_batch_sampling_raw(wins, ns)
     assert len(raw_s[4]) == held and held < total                   # the store (and the device->host copy) holds the unique paths only
+
+
+def test_heated_sampling_matches_the_reference_on_the_gpu():
+    """--temperature=3 through the C ABI: the 99 sampled paths of both sequences of example.fa == the reference's (one process: the second
+    sequence starts where the first left the rand() stream), fixture tests/golden/ref_samples_heated.json.gz."""
+    import gzip
+    import json
+    ref = json.load(gzip.open(util.GOLDEN + "/ref_samples_heated.json.gz", "rt"))["sequences"]
+    d3 = Decoder(util.blob_bytes("human_t3"), 0)
+    try:
+        pos = 0
+        for (_, dna), r in zip(util.read_fasta(util.GOLDEN + "/example.fa"), ref):
+            d3.set_rand_position(pos)
+            _, samples = d3.decode_batch_sampling([dna], 100)
+            assert [s.as_tuples() for s in samples[0]] == [[tuple(x) for x in s] for s in r["samples"]]
+            pos += d3.last_rand_consumed
+    finally:
+        d3.close()
