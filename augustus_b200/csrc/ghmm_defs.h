@@ -196,6 +196,13 @@ constexpr uint32_t STOP_COMPLEX = 0xffffffffu;
 /* one (predecessor, predecessor end) option of a sampling step: OptionListItem (vitmatrix.hh:748-770) */
 struct SampleOpt { double lp; int32_t ord /* insertion order in the reference's loops */, pred, eop, pad; };
 
+/* Sampling walks of one window meet the same cells again and again (99 walks follow similar paths): the option list of a cell
+ * (OptionsList of state s at column j: a function of the forward matrix only) is kept in drawing form after its first use — options in the
+ * stable descending order OptionsList::prepareSampling gives them, with exp(lp - max), so that a later visit only forms the cumulative sums. */
+struct OcSlot { long long key /* state << 32 | column, -1 = empty */; int32_t off, n; double mx, cum; };
+struct OcOpt { double ex, lpmx /* lp - max */; int32_t pred, eop; };
+constexpr int OC_SLOTS = 8192, OC_PROBE = 8, OC_MAXN = 4096;
+
 /* per-column signal score arrays written by the prep pass (ghmm_signal.h) */
 enum : int { SG_DSSF = 0, SG_DSSR = 1, SG_ASSF = 2, SG_ASSR = 3, SG_XRS = 4, NSIG = 5 };
 

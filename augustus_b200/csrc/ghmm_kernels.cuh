@@ -337,6 +337,7 @@ __device__ __forceinline__ void sweep_sample_body(const WinDev* __restrict__ win
             else {
                 SamplerT<SW> sp; sp.sw = &sw;
                 sp.sc.opt = (SampleOpt*)(wd.base + wd.lay.opt); sp.sc.opt_cap = wd.lay.opt_cap; sp.sc.sorted = (int32_t*)(wd.base + wd.lay.sorted); sp.sc.ex = (double*)(wd.base + wd.lay.optex); sp.sc.nopt = &s_nopt[wid];
+                sp.sc.oc_slots = (OcSlot*)(wd.base + wd.lay.oc_slots); sp.sc.oc_pool = (OcOpt*)(wd.base + wd.lay.oc_pool); sp.sc.oc_cap = wd.lay.oc_cap;
                 sp.rng = rng; sp.nrng = nrng;
                 SampleOut so; so.cap = wd.lay.samp_cap;
                 so.begin = (int32_t*)(wd.base + wd.lay.s_begin); so.end = (int32_t*)(wd.base + wd.lay.s_end);

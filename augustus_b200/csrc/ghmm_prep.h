@@ -38,7 +38,7 @@ struct WinLayout {
     size_t snip_head, snip_pool, snip_stack; int snip_cap;
     size_t snipx; int sx_cap;
     size_t evF, clF, clG, fcp; int fcp_cap;                       /* forward pass (0 capacity when not requested) */
-    size_t opt, sorted, optex, s_begin, s_end, s_type, s_trunc, s_count, s_logp; int opt_cap, samp_cap, nsamp;   /* sampling */
+    size_t opt, sorted, optex, oc_slots, oc_pool, s_begin, s_end, s_type, s_trunc, s_count, s_logp; int opt_cap, samp_cap, nsamp, oc_cap;   /* sampling */
     size_t path_begin, path_end, path_type, path_trunc;      /* backtrace output */
     size_t total, slab;
     int ev_cap, cl_cap, cp_cap, path_cap, nslab_local;
@@ -77,6 +77,8 @@ inline WinLayout make_layout(int L, int C, bool generous = false, bool forward =
     w.nsamp = forward ? nsamp : 0;
     w.opt_cap = w.nsamp ? w.cl_cap + 1024 : 0; w.samp_cap = w.nsamp ? (generous ? w.nsamp * (L / 8 + 64) : w.nsamp * (128 + L / 128)) : 0;   /* gene-dense fly DNA: ~3.5 path states per kb and sample */
     w.opt = take((size_t)w.opt_cap * sizeof(SampleOpt)); w.sorted = take((size_t)w.opt_cap * 4); w.optex = take((size_t)w.opt_cap * 8);
+    w.oc_cap = w.nsamp ? (generous ? 8 * L + 65536 : L / 2 + 32768) : 0;         /* cached option lists of the walks (Sampler::step_pick) */
+    w.oc_slots = take(w.nsamp ? (size_t)OC_SLOTS * sizeof(OcSlot) : 0); w.oc_pool = take((size_t)w.oc_cap * sizeof(OcOpt));
     w.s_begin = take((size_t)w.samp_cap * 4); w.s_end = take((size_t)w.samp_cap * 4); w.s_type = take(w.samp_cap); w.s_trunc = take(w.samp_cap);
     w.s_count = take((size_t)w.nsamp * 4 + 16); w.s_logp = take((size_t)w.nsamp * 8);
     w.outs = take(sizeof(WinOuts));

@@ -22,13 +22,14 @@ struct SampleOut {
     int32_t* status;
     int32_t* rand_used = nullptr;    /* out: draws consumed (cursor at the end) */
 };
-struct SampleScratch { SampleOpt* opt; int opt_cap; int32_t* sorted /* 1 = option already drawn against */; double* ex /* exp(lp - max) */; int* nopt; };
+struct SampleScratch { SampleOpt* opt; int opt_cap; int32_t* sorted /* 1 = option already drawn against */; double* ex /* exp(lp - max) */; int* nopt;
+                       OcSlot* oc_slots = nullptr; OcOpt* oc_pool = nullptr; int oc_cap = 0; /* cached option lists (step_pick) */ };
 
 AUGB_HD int trunc_flag_s(int type, int end, int predEnd, int L) { return trunc_flag(type, end, predEnd, L); }
 
 template <class SW>
 struct SamplerT {
-    SW* sw; SampleScratch sc; const uint32_t* rng; int nrng; int cursor; int lane;
+    SW* sw; SampleScratch sc; const uint32_t* rng; int nrng; int cursor; int lane; int oc_used = 0;
 
     /* draw one option; returns its index in sc.opt (or -1), adds ln(p/cumprob) to *lp.
      * OptionsList::sample (vitmatrix.cc:295-320) walks the options in stable descending order of probability until the cumulative sum
@@ -113,6 +114,81 @@ struct SamplerT {
         *add = lp[res] - mx - log(cum);
         return res;
     }
+    /* draw from a cached list: the cumulative sums are formed over the stored order exactly as OptionsList::sample forms them */
+    AUGB_D void draw_cached(const OcSlot& sl, double* lp, int* pred, int* eop) {
+        const OcOpt* o = sc.oc_pool + sl.off;
+        const double z = ((double)rng[cursor] / 2147483647.0) * sl.cum * 0.99999;
+        int res = -1; double cs = 0;
+        AUGB_ROLLED
+        for (int r = 0; r < sl.n && res < 0; r++) { cs += o[r].ex; if (z < cs) res = r; }
+        if (res < 0) res = 0;
+        *lp += o[res].lpmx - log(sl.cum);
+        *pred = o[res].pred; *eop = o[res].eop;
+        cursor++;
+    }
+    /* one step of the walk at a cell of a multi-base state: the options are listed by the state's routine the first time a walk of this
+     * window stands here and kept in drawing order; 0 = drawn, -1 = no option, -2 = option buffer too small */
+    AUGB_D int step_pick(int state, int base, const StateDesc& sd, double* lp, int* pred, int* eop) {
+        SW& S = *sw;
+        const long long key = ((long long)state << 32) | (unsigned)base;
+        int slot = -1, freeslot = -1;
+        if (sc.oc_slots) {
+            unsigned h = ((unsigned)base * 2654435761u) ^ ((unsigned)state * 40503u);
+            AUGB_ROLLED
+            for (int q = 0; q < OC_PROBE && slot < 0; q++) {
+                const int i = (int)((h + (unsigned)q) & (OC_SLOTS - 1));
+                const long long k = sc.oc_slots[i].key;
+                if (k == key) slot = i; else if (k == -1) { freeslot = i; break; }
+            }
+        }
+        if (cursor >= nrng) return -1;
+        if (slot >= 0) { draw_cached(sc.oc_slots[slot], lp, pred, eop); return 0; }
+        if (lane == 0) *sc.nopt = 0;
+        wsync();
+        S.only = state;
+        const int dir = sd.fwd ? 0 : 1;
+        if (sd.kind == K_EXON) S.exon_eval(state, base);
+        else if (sd.kind == K_UTR) S.utr_eval(state, base);
+        else if (sd.kind == K_LESSD) S.lessd_eval(dir, base);
+        else if (sd.kind == K_EQUALD) S.equald_eval(dir, sd.frame, base);
+        else S.fixed_eval(sd.kind, dir, base);
+        S.only = -1;
+        const int n = *sc.nopt;
+        if (n > sc.opt_cap) return -2;
+        if (n <= 0) return -1;
+        if (freeslot < 0 || n > OC_MAXN || oc_used + n > sc.oc_cap) {        /* not cached: draw as before */
+            const int k = pick(lp);
+            if (k < 0) return k;
+            *pred = sc.opt[k].pred; *eop = sc.opt[k].eop;
+            return 0;
+        }
+        /* maximum, exponentials, cumprob in insertion order (as pick()), then the whole stable descending order into the pool */
+        double mx = -1e308;
+        AUGB_ROLLED
+        for (int i = lane; i < n; i += AUGB_NLANES) { double v = sc.opt[i].lp; mx = v > mx ? v : mx; }
+        mx = wmaxd(mx);
+        AUGB_ROLLED
+        for (int i = lane; i < n; i += AUGB_NLANES) sc.ex[i] = exp(sc.opt[i].lp - mx);
+        wsync();
+        double cum = 0;
+        AUGB_ROLLED
+        for (int i = 0; i < n; i++) cum += sc.ex[i];
+        OcOpt* o = sc.oc_pool + oc_used;
+        AUGB_ROLLED
+        for (int i = lane; i < n; i += AUGB_NLANES) {
+            const double v = sc.opt[i].lp; const int od = sc.opt[i].ord; int r = 0;
+            AUGB_ROLLED
+            for (int k = 0; k < n; k++) { const double u = sc.opt[k].lp; r += (u > v || (u == v && (sc.opt[k].ord < od || (sc.opt[k].ord == od && k < i)))) ? 1 : 0; }
+            OcOpt x; x.ex = sc.ex[i]; x.lpmx = v - mx; x.pred = sc.opt[i].pred; x.eop = sc.opt[i].eop;
+            o[r] = x;
+        }
+        if (lane == 0) { OcSlot sl; sl.key = key; sl.off = oc_used; sl.n = n; sl.mx = mx; sl.cum = cum; sc.oc_slots[freeslot] = sl; }
+        wsync();
+        oc_used += n;
+        draw_cached(sc.oc_slots[freeslot], lp, pred, eop);
+        return 0;
+    }
+
     /* The options of a self-loop state at column c (> 0), a column of its chain that received entries: the ancestors at c - 1 in index
      * order (igenicmodel.cc:247-261, intronmodel.cc:786-820).  Everything is local to the calling lane.  Returns the number of options. */
     AUGB_D int chain_options(int state, int c, double* lpv, int* ordv, int* prd, const FChainCP* prev) const {
@@ -194,6 +270,12 @@ struct SamplerT {
         lane = lane_id(); cursor = 0;
         S.opt = sc.opt; S.nopt = sc.nopt; S.opt_cap = sc.opt_cap;
         if (nsamples > 1) prepare_stops();
+        oc_used = 0;
+        if (sc.oc_slots) {
+            AUGB_ROLLED
+            for (int i = lane; i < OC_SLOTS; i += AUGB_NLANES) sc.oc_slots[i].key = -1;
+            wsync();
+        }
         int used = 0, status = 0;
         const bool alln = (*S.w.flags & WF_ALLN) != 0;
         AUGB_ROLLED
@@ -273,17 +355,8 @@ struct SamplerT {
                         }
                         used++; run_end = -1;
                     } else {
-                        S.only = state;
-                        const int dir = sd.fwd ? 0 : 1;
-                        if (sd.kind == K_EXON) S.exon_eval(state, base);
-                        else if (sd.kind == K_UTR) S.utr_eval(state, base);
-                        else if (sd.kind == K_LESSD) S.lessd_eval(dir, base);
-                        else if (sd.kind == K_EQUALD) S.equald_eval(dir, sd.frame, base);
-                        else S.fixed_eval(sd.kind, dir, base);
-                        S.only = -1;
-                        k = pick(&lp);
+                        k = step_pick(state, base, sd, &lp, &pred, &eop);
                         if (k < 0) { bad = 1; if (k == -2) status = 8; break; }
-                        pred = sc.opt[k].pred; eop = sc.opt[k].eop;
                         if (used >= out.cap) { status = 8; break; }
                         if (lane == 0) { out.begin[used] = eop + 1; out.end[used] = base; out.type[used] = (uint8_t)sd.type; out.trunc[used] = (uint8_t)trunc_flag_s(sd.type, base, eop, L); }
                         used++;

@@ -147,7 +147,8 @@ static int sample_impl(void* mp, const char* dna, int L, const int32_t* gc_in, i
     std::vector<uint32_t> rng(nrng);
     gen.seek(rand_pos); gen.fill(rng.data(), nrng);
     std::vector<SampleOpt> opts(L + 4096); std::vector<int32_t> sorted(L + 4096); std::vector<double> optex(L + 4096); int nopt = 0;
-    SamplerT<SW> sp; sp.sw = &sw; sp.sc.opt = opts.data(); sp.sc.opt_cap = (int)opts.size(); sp.sc.sorted = sorted.data(); sp.sc.ex = optex.data(); sp.sc.nopt = &nopt;
+    std::vector<OcSlot> ocs(OC_SLOTS); std::vector<OcOpt> ocp(L / 2 + 32768);
+    SamplerT<SW> sp; sp.sw = &sw; sp.sc.opt = opts.data(); sp.sc.opt_cap = (int)opts.size(); sp.sc.sorted = sorted.data(); sp.sc.ex = optex.data(); sp.sc.nopt = &nopt; sp.sc.oc_slots = ocs.data(); sp.sc.oc_pool = ocp.data(); sp.sc.oc_cap = (int)ocp.size();
     sp.rng = rng.data(); sp.nrng = (int)nrng;
     SampleOut so; so.rand_used = rand_used; so.cap = cap; so.begin = sb; so.end = se; so.type = st_; so.trunc = str_; so.count = scount; so.logp = slogp; so.status = status;
 #ifdef AUGB_SIMT32
