@@ -447,7 +447,7 @@ def main():
         mine = list(range(rank, len(w3), world))
         w3b = [w3[i].encode() for i in mine]
         dec3 = Decoder(util.blob_bytes("fly_softmask_utr"), local)
-        dec3.decode_batch_sampling_raw(w3b[:2], 100)
+        dec3.decode_batch_sampling_raw(w3b, 100)          # untimed warm-up at full size: pinned and device buffers reach their final size
         barrier(); t0 = time.perf_counter()
         vit3, samp3 = dec3.decode_batch_sampling_raw(w3b, 100)
         torch.cuda.synchronize(); dt_mine = time.perf_counter() - t0
