@@ -3,6 +3,7 @@
  */
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda/barrier>
 
 #include "ghmm_backtrace.h"
 #include "ghmm_defs.h"
@@ -20,6 +21,7 @@ __constant__ DevModel c_model;
 constexpr int PREP_BS = 256;
 constexpr int PREP_ITEMS = 4;      /* measured: 8 / 16 items per thread and warp-segment scans are slower (24 / 30 / 37 / 36 ms per 1184 windows) */
 constexpr int PREP_TILE = PREP_BS * PREP_ITEMS;
+constexpr int PREP_DNA_TILE = 8192;      /* bases of a window staged in shared memory per bulk copy (multiple of 16) */
 
 /* exclusive block-wide prefix of one value per thread; returns the prefix, *total = block sum */
 template <typename T>
@@ -116,13 +118,48 @@ __global__ void __launch_bounds__(PREP_BS) k_prep(const WinDev* __restrict__ win
     __shared__ int s_nruns;
     __shared__ sc_t* s_slab[MAXC];
     __shared__ int s_noslab;
+    __shared__ alignas(128) char s_dna[PREP_DNA_TILE + 32];
+#pragma nv_diag_suppress static_var_with_dynamic_init
+    __shared__ cuda::barrier<cuda::thread_scope_block> s_bar;
+    if (threadIdx.x == 0) init(&s_bar, PREP_BS);
+    __syncthreads();
     for (int wi = blockIdx.x; wi < nwin; wi += gridDim.x) {
         const WinDev wd = wins[wi];
         const int L = wd.L; char* base = wd.base; const WinLayout& lay = wd.lay;
         uint8_t* code = (uint8_t*)(base + lay.code); uint8_t* gc = (uint8_t*)(base + lay.gc); mask_t* mask = (mask_t*)(base + lay.mask);
         if (threadIdx.x == 0) { s_classmask = 0; s_anynuc = 0; }
         __syncthreads();
-        { bool any = false; for (int i = threadIdx.x; i < L; i += PREP_BS) { uint8_t c = base_code(wd.dna[i]); code[i] = c; any |= c < 4; } if (any) s_anynuc = 1; }
+        uint16_t* kf = (uint16_t*)(base + lay.kf); uint16_t* kr = (uint16_t*)(base + lay.kr);
+        {
+            /* The window's DNA is staged tile by tile in shared memory by the TMA engine (cp.async.bulk global -> shared, completion on an
+             * mbarrier: UBLKCP / SYNCS in the SASS), with 16 bytes of halo on either side; base codes and the (k+1)-mer codes of both
+             * strands come out of one pass over the tile (Seq2Int::operator() / ::rc, geneticcode.hh:166-179: 0x8000 = a base that is not
+             * acgt or a position off the window). */
+            const int k1 = m->k + 1, Lpad = (L + 15) & ~15;
+            bool any = false;
+            for (int t0 = 0; t0 < L; t0 += PREP_DNA_TILE) {
+                const int lo = t0 >= 16 ? t0 - 16 : 0, hi = min(t0 + PREP_DNA_TILE + 16, Lpad), bytes = hi - lo;
+                cuda::barrier<cuda::thread_scope_block>::arrival_token tok;
+                if (threadIdx.x == 0) {
+                    cuda::device::memcpy_async_tx(s_dna, wd.dna + lo, cuda::aligned_size_t<16>(bytes), s_bar);
+                    tok = cuda::device::barrier_arrive_tx(s_bar, 1, bytes);
+                } else tok = s_bar.arrive();
+                s_bar.wait(std::move(tok));
+                const int pend = min(t0 + PREP_DNA_TILE, L);
+                for (int p = t0 + threadIdx.x; p < pend; p += PREP_BS) {
+                    const uint8_t c = base_code(s_dna[p - lo]);
+                    code[p] = c; any |= c < 4;
+                    int ef = 0, er = 0; bool okf = p - k1 + 1 >= 0, okr = p + k1 <= L;
+                    for (int i = 0; i < k1; i++) {
+                        if (okf) { const uint8_t b = base_code(s_dna[p - k1 + 1 + i - lo]); if (b > 3) okf = false; else ef = (ef << 2) | b; }
+                        if (okr) { const uint8_t b = base_code(s_dna[p + i - lo]); if (b > 3) okr = false; else er |= (3 - b) << (2 * i); }
+                    }
+                    kf[p] = okf ? (uint16_t)ef : (uint16_t)0x8000; kr[p] = okr ? (uint16_t)er : (uint16_t)0x8000;
+                }
+                __syncthreads();                      /* the tile is free for the next copy */
+            }
+            if (any) s_anynuc = 1;
+        }
         __syncthreads();
         int32_t* pmask = (int32_t*)(base + lay.pmask);
         if (lay.softmask) {         /* lower-case input bases = soft-masked (SequenceFeatureCollection::prepare, extrinsicinfo.cc:1696-1724) */
@@ -132,12 +169,7 @@ __global__ void __launch_bounds__(PREP_BS) k_prep(const WinDev* __restrict__ win
         }
         const bool anynuc = s_anynuc != 0;
         Seq s; s.c = code; s.L = L;
-        {
-            uint16_t* kf = (uint16_t*)(base + lay.kf); uint16_t* kr = (uint16_t*)(base + lay.kr);
-            for (int p = threadIdx.x; p < L; p += PREP_BS) { kf[p] = kmer_code_f(s, p, m->k + 1); kr[p] = kmer_code_r(s, p, m->k + 1); }
-            __syncthreads();
-            s.kf = kf; s.kr = kr; s.k1 = m->k + 1;
-        }
+        s.kf = kf; s.kr = kr; s.k1 = m->k + 1;
         /* ---- GC classes: ContentStairs::computeStairs (motif.cc:543-614) ---- */
         if (wd.gc_in) {
             for (int i = threadIdx.x; i < L; i += PREP_BS) gc[i] = wd.gc_in[i];
