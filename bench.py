@@ -543,20 +543,33 @@ def main():
     dec = Decoder(util.blob_bytes(), local)
     stream = torch.cuda.ExternalStream(dec.stream, device=torch.device("cuda", local))
 
-    # ---- a first pass with the block-cyclic deal measures every rank's sweep rate; the windows are then re-dealt in proportion ----
+    # ---- a first pass with the block-cyclic deal measures every rank's sweep rate; the windows are then re-dealt in proportion, and once
+    # more from the rates of the new deal (a partial last round of warps does not shrink in proportion to the window count) ----
     dec.stage(wins_b)
-    dec.run_staged(); dec.run_staged()
-    torch.cuda.synchronize()
-    dec.fetch_staged()
-    rate0 = per_rank(len(wins_b) / max(dec.last_sweep_ms, 1e-3))
-    deal = deal_windows(world, M, None if (args.no_balance or world == 1) else ([float(x) for x in args.assume_rates.split(",")] if args.assume_rates else rate0))
-    if deal[rank] != my_idx:
-        have = dict(zip(my_idx, wins_b))
-        extra = [g for g in deal[rank] if g not in have]
-        have.update(zip(extra, (w.encode() for w in synth.windows_parallel_indices(extra, WINDOW_LEN))))
-        my_idx = deal[rank]
-        wins_b = [have[g] for g in my_idx]
-        dec.stage(wins_b)
+    have = dict(zip(my_idx, wins_b))
+    deal = [list(range(r, world * M, world)) for r in range(world)]
+    rate0 = None
+    for it in range(1 if (args.no_balance or world == 1) else 2):
+        dec.run_staged(); dec.run_staged()
+        torch.cuda.synchronize()
+        dec.fetch_staged()
+        rates = per_rank(len(wins_b) / max(dec.last_sweep_ms, 1e-3))
+        if rate0 is None:
+            rate0 = rates
+        new_deal = deal if args.no_balance else deal_windows(world, M, [float(x) for x in args.assume_rates.split(",")] if (args.assume_rates and it == 0) else rates)
+        if new_deal == deal:
+            break
+        deal = new_deal
+        if deal[rank] != my_idx:
+            extra = [g for g in deal[rank] if g not in have]
+            have.update(zip(extra, (w.encode() for w in synth.windows_parallel_indices(extra, WINDOW_LEN))))
+            my_idx = deal[rank]
+            wins_b = [have[g] for g in my_idx]
+            dec.stage(wins_b)
+    if rate0 is None:
+        dec.run_staged(); torch.cuda.synchronize(); dec.fetch_staged()
+        rate0 = per_rank(len(wins_b) / max(dec.last_sweep_ms, 1e-3))
+    del have
     counts = [len(d) for d in deal]
     bases_mine = len(wins_b) * WINDOW_LEN
     bases_all = world * M * WINDOW_LEN
