@@ -190,3 +190,10 @@ int hostemu_statecount(void* mp) { return ((EmuModel*)mp)->hm.dm.S; }
 int hostemu_chain_state(void* mp, int ch) { return ((EmuModel*)mp)->hm.dm.chain_state[ch]; }
 
 }  // extern "C"
+
+/* the carried generator (GlibcRand): values [pos, pos + n) of the stream of seed 1 after an arbitrary history of seeks */
+extern "C" void hostemu_rand_window(const uint64_t* seeks, int nseeks, uint64_t pos, uint32_t* out, int n) {
+    GlibcRand g;
+    for (int i = 0; i < nseeks; i++) { g.seek(seeks[i]); (void)g.next(); }
+    g.seek(pos); g.fill(out, (size_t)n);
+}

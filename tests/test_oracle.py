@@ -197,3 +197,22 @@ def test_heated_sampling_matches_the_reference():
             pos += used
     cold = util.HostEmu(util.blob_bytes()).sample(dnas[1], 99)["samples"]
     assert [s["states"] for s in cold] != [[tuple(x) for x in s] for s in ref[1]["samples"]]          # the temperature does change the paths
+
+
+def test_carried_rand_generator_matches_libc_at_any_position():
+    """the library generates the rand() stream window by window from a carried generator state (ring + 64-bit position) instead
+    of from position 0.  Whatever the history of seeks (forwards, backwards = restart), the window at a position equals what an unseeded
+    libc process draws there."""
+    import ctypes
+    import ctypes.util
+    emu = util.HostEmu(util.blob_bytes())
+    libc = ctypes.CDLL(ctypes.util.find_library("c"))
+    libc.srand(1)
+    N = 300000
+    ref = np.array([libc.rand() for _ in range(N)], dtype=np.uint32)
+    emu.lib.hostemu_rand_window.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int]
+    for seeks, pos in (([], 0), ([5, 100000, 7], 123456), ([299000], 10), ([1, 2, 3, 250000, 4], 299000)):
+        sk = np.array(seeks, dtype=np.uint64)
+        out = np.zeros(1000, dtype=np.uint32)
+        emu.lib.hostemu_rand_window(sk.ctypes.data if len(seeks) else None, len(seeks), pos, out.ctypes.data, 1000)
+        assert (out == ref[pos:pos + 1000]).all(), (seeks, pos)
