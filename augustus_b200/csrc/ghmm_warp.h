@@ -138,7 +138,11 @@ struct Lse {
     double m, s;
     AUGB_HD void clear() { m = -1e308; s = 0; }
     AUGB_HD void add(double lp) {
-        if (lp > m) { s = s * exp(m - lp) + 1.0; m = lp; } else s += exp(lp - m);
+        /* one exponential whichever side is larger (lanes of a warp disagree about that all the time): exp(-|lp - m|), the same argument
+         * bit for bit as exp(m - lp) / exp(lp - m) */
+        const double d = lp - m;
+        const double e = exp(d > 0 ? -d : d);
+        if (d > 0) { s = s * e + 1.0; m = lp; } else s += e;
     }
     AUGB_HD bool empty() const { return !(s > 0); }
     AUGB_HD double value() const { return s > 0 ? m + log(s) : -1e308; }
